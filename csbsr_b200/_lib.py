@@ -1,0 +1,92 @@
+"""ctypes binding of the C-ABI library `libcsbsr_b200.so` (declared in include/csbsr_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, a
+`CsbsrError` is raised.  PyTorch is used only for device memory and streams.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcsbsr_b200.so")
+
+MAX_TAPS = 64
+MAX_PHASES = 16
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
+OUT_BF16_NHWC, OUT_F32_NCHW = 0, 1
+
+
+class CsbsrError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("x_pitch", C.c_int32), ("x_coff", C.c_int32), ("cin", C.c_int32),
+        ("wgt", C.c_void_p),
+        ("w_taps", C.c_int32), ("cout_pad", C.c_int32),
+        ("nphases", C.c_int32), ("ntaps", C.c_int32), ("stride", C.c_int32),
+        ("dh", C.c_int8 * MAX_TAPS), ("dw", C.c_int8 * MAX_TAPS),
+        ("widx", C.c_int16 * MAX_TAPS),
+        ("oh", C.c_int32), ("ow", C.c_int32),
+        ("os", C.c_int32),
+        ("ooh", C.c_int8 * MAX_PHASES), ("oow", C.c_int8 * MAX_PHASES),
+        ("yh", C.c_int32), ("yw", C.c_int32),
+        ("out_mode", C.c_int32),
+        ("y", C.c_void_p),
+        ("y_pitch", C.c_int32), ("y_coff", C.c_int32), ("cout_store", C.c_int32),
+        ("bias", C.c_void_p),
+        ("bias_sn", C.c_int32), ("bias_sc", C.c_int32), ("cls_bw", C.c_int32),
+        ("act", C.c_int32),
+        ("slope", C.c_float),
+        ("r0", C.c_void_p), ("r0_pitch", C.c_int32), ("r0_coff", C.c_int32),
+        ("rm", C.c_void_p), ("rm_pitch", C.c_int32), ("rm_coff", C.c_int32),
+        ("r1", C.c_void_p), ("r1_pitch", C.c_int32), ("r1_coff", C.c_int32),
+        ("r1_sign", C.c_float),
+        ("r32", C.c_void_p),
+        ("block_n", C.c_int32),
+    ]
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/csbsr_b200.h declares
+_SIGNATURES = {
+    "csbsr_last_error": (C.c_char_p, []),
+    "csbsr_version": (C.c_int, []),
+    "csbsr_device_ok": (C.c_int, []),
+    "csbsr_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load the C-ABI library (once). Raises CsbsrError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CsbsrError(
+                "csbsr_b200: %s not found -- run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                "there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().csbsr_last_error()
+        raise CsbsrError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,546 @@
+// Implicit-GEMM convolution for sm_100a: TMA-fed, tcgen05.mma with fp32 accumulators in TMEM,
+// persistent warp-specialised CTAs (1 per SM), double-buffered accumulators, fused epilogue.
+//
+// GEMM view: M = 128 output pixels (a TH x TW patch of one image), N = block_n output channels,
+// K = taps x cin.  For each (tap, 64-channel chunk) the A operand is ONE 4-D TMA box of the NHWC
+// activation tensor shifted by the tap offset (out-of-image elements are zero-filled by TMA, which
+// is the conv zero padding); strided convs use the tensor map's element strides.  The B operand is a
+// [block_n x 64] K-major slab of the packed weights.  Both land in 128B-swizzled shared memory and
+// are consumed by tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32).
+//
+// Replaces the cuDNN convs behind nn.Conv2d / nn.ConvTranspose2d of the reference
+// (model/modeling/kbpn.py:266-277, 450-518; pspnet_pytorch/extractors.py:37-70; pspnet.py:23-57).
+#include <cuda.h>
+#include "common.cuh"
+#include "../../include/csbsr_b200.h"
+
+namespace csbsr {
+
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;                  // bf16 elements = 128 bytes = one swizzle row
+static constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
+static constexpr int kMaxStages = 8;
+static constexpr int kThreads = 256;                // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
+static constexpr int kTmemCols = 512;
+static constexpr int kSmemBudget = 227 * 1024;
+
+struct ConvKParams {
+    // tiles
+    int tiles_h, tiles_w, m_tiles, n_tiles, nphases, total_tiles;
+    int TH, TW, block_n, kchunks, ntaps, stride, stages;
+    int OH, OW, os, YH, YW, N;
+    int out_mode, y_pitch, y_coff, cout_store;
+    int bias_sn, bias_sc, cls_bw, act;
+    float slope, r1_sign;
+    int r0_pitch, r0_coff, rm_pitch, rm_coff, r1_pitch, r1_coff;
+    void* y;
+    const float* bias;
+    const __nv_bfloat16* r0;
+    const __nv_bfloat16* rm;
+    const __nv_bfloat16* r1;
+    const float* r32;
+    int* err_flag;
+    int8_t dh[CSBSR_MAX_TAPS], dw[CSBSR_MAX_TAPS];
+    int16_t widx[CSBSR_MAX_TAPS];
+    int8_t ooh[CSBSR_MAX_PHASES], oow[CSBSR_MAX_PHASES];
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must fail loudly (trap) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {      // ~2 s at 2 GHz
+            if (err_flag) atomicExch(err_flag, code);
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* p) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(p)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+        "%6}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+        "[%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (SBO = 8 rows x 128 B, version 1 = sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+    uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+__device__ __forceinline__ int border_class(int i, int n, int bw) {
+    if (i < bw) return i;
+    int fromend = n - 1 - i;
+    if (fromend < bw) return 2 * bw - fromend;
+    return bw;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    if (act == CSBSR_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == CSBSR_ACT_LEAKY) return v > 0.f ? v : v * slope;
+    if (act == CSBSR_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    return v;
+}
+
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&f)[8]) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+
+// ------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ ConvKParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages x A tile][stages x B tile][barriers]
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_tile_bytes = p.block_n * kBlockK * 2;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + p.stages * kATileBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_tile_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full = empty_bar + kMaxStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);      // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int kblocks = p.ntaps * p.kchunks;
+    const int tiles_per_img = p.tiles_h * p.tiles_w;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = kATileBytes + b_tile_bytes;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                const int rest = tile / p.n_tiles;
+                const int ph = rest % p.nphases;
+                const int mt = rest / p.nphases;
+                const int img = mt / tiles_per_img;
+                const int tr = mt % tiles_per_img;
+                const int oh0 = (tr / p.tiles_w) * p.TH;
+                const int ow0 = (tr % p.tiles_w) * p.TW;
+                for (int t = 0; t < p.ntaps; ++t) {
+                    const int ti = ph * p.ntaps + t;
+                    const int ih0 = oh0 * p.stride + p.dh[ti];
+                    const int iw0 = ow0 * p.stride + p.dw[ti];
+                    const int wi = p.widx[ti];
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                        tma_load_4d(smem_u32(smem_a + stage * kATileBytes), &tmA, &full_bar[stage], kc * kBlockK, iw0,
+                                    ih0, img);
+                        tma_load_3d(smem_u32(smem_b + stage * b_tile_bytes), &tmB, &full_bar[stage], kc * kBlockK,
+                                    nt * p.block_n, wi);
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.block_n >> 3) << 17) |
+                                   (static_cast<uint32_t>(kBlockM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+                const int as = local & 1;
+                const uint32_t aphase = (local >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1u, p.err_flag, 2);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * 256);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * kATileBytes));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * b_tile_bytes));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // +32 bytes per K=16 step inside the 128B swizzle row -> +2 in the >>4 address field
+                        umma_bf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                                  idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+                    if (kb == kblocks - 1) umma_commit(&tmem_full[as]);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int q = warp & 3;                       // TMEM lane quarter owned by this warp
+        const int row = q * 32 + lane;                // accumulator row == pixel inside the tile
+        const int th = row / p.TW, tw = row % p.TW;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+            const int as = local & 1;
+            const uint32_t aphase = (local >> 1) & 1;
+            const int nt = tile % p.n_tiles;
+            const int rest = tile / p.n_tiles;
+            const int ph = rest % p.nphases;
+            const int mt = rest / p.nphases;
+            const int img = mt / tiles_per_img;
+            const int tr = mt % tiles_per_img;
+            const int oh = (tr / p.tiles_w) * p.TH + th;
+            const int ow = (tr % p.tiles_w) * p.TW + tw;
+            const bool valid = (oh < p.OH) && (ow < p.OW);
+            const int oy = oh * p.os + p.ooh[ph];
+            const int ox = ow * p.os + p.oow[ph];
+            const size_t pix = (static_cast<size_t>(img) * p.YH + oy) * p.YW + ox;
+            int cls = 0;
+            if (p.cls_bw > 0)
+                cls = border_class(oy, p.YH, p.cls_bw) * (2 * p.cls_bw + 1) + border_class(ox, p.YW, p.cls_bw);
+            const float* bias_row = p.bias ? p.bias + static_cast<size_t>(img) * p.bias_sn +
+                                                 static_cast<size_t>(cls) * p.bias_sc
+                                           : nullptr;
+
+            mbar_wait(&tmem_full[as], aphase, p.err_flag, 4);
+            tcgen05_fence_after();
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * 256);
+            const int c_base = nt * p.block_n;
+            for (int cc = 0; cc < p.block_n; cc += 16) {
+                uint32_t v[16];
+                __syncwarp();
+                tmem_ld16(taddr0 + static_cast<uint32_t>(cc), v);
+                tmem_ld_wait();
+                const int c0 = c_base + cc;
+                if (valid && c0 < p.cout_store) {
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                if (bias_row) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        float4 b = *reinterpret_cast<const float4*>(bias_row + c0 + i);
+                        f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+                    }
+                }
+                if (p.out_mode == CSBSR_OUT_BF16_NHWC) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int c = c0 + g * 8;
+                        if (c >= p.cout_store) break;
+                        float* fg = f + g * 8;
+                        if (p.r0) {
+                            float r[8];
+                            load8_bf16(p.r0 + pix * p.r0_pitch + p.r0_coff + c, r);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) fg[i] += r[i];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) fg[i] = apply_act(fg[i], p.act, p.slope);
+                        if (p.rm) {
+                            float r[8];
+                            load8_bf16(p.rm + pix * p.rm_pitch + p.rm_coff + c, r);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) fg[i] *= r[i];
+                        }
+                        if (p.r1) {
+                            float r[8];
+                            load8_bf16(p.r1 + pix * p.r1_pitch + p.r1_coff + c, r);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) fg[i] += p.r1_sign * r[i];
+                        }
+                        uint4 o;
+                        __nv_bfloat162* oh2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) oh2[i] = __floats2bfloat162_rn(fg[2 * i], fg[2 * i + 1]);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.y_pitch + p.y_coff +
+                                                  c) = o;
+                    }
+                } else {
+                    // fp32 planar [n][cout_store][YH][YW]
+                    float* y32 = reinterpret_cast<float*>(p.y);
+                    const size_t plane = static_cast<size_t>(p.YH) * p.YW;
+                    const size_t base = (static_cast<size_t>(img) * p.cout_store) * plane +
+                                        static_cast<size_t>(oy) * p.YW + ox;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = c0 + i;
+                        if (c < p.cout_store) {
+                            float val = apply_act(f[i], p.act, p.slope);
+                            if (p.r32) val += p.r32[base + c * plane];
+                            y32[base + c * plane] = val;
+                        }
+                    }
+                }
+                }  // valid
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+static int* g_err_flag = nullptr;   // device int, lazily allocated (one per process; diagnostic only)
+
+}  // namespace csbsr
+
+using namespace csbsr;
+
+extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CSBSR_REQUIRE(d && d->x && d->wgt && d->y, "conv_igemm: null pointer");
+    CSBSR_REQUIRE(d->cin > 0 && d->cin % kBlockK == 0, "conv_igemm: cin=%d must be a positive multiple of 64", d->cin);
+    CSBSR_REQUIRE(d->cout_pad > 0 && d->cout_pad % 16 == 0, "conv_igemm: cout_pad=%d must be a multiple of 16",
+                  d->cout_pad);
+    CSBSR_REQUIRE(d->x_pitch % 8 == 0 && d->x_coff % 8 == 0, "conv_igemm: x pitch/offset must be multiples of 8");
+    CSBSR_REQUIRE(d->nphases >= 1 && d->nphases <= CSBSR_MAX_PHASES && d->ntaps >= 1 &&
+                      d->nphases * d->ntaps <= CSBSR_MAX_TAPS,
+                  "conv_igemm: bad phase/tap counts (%d x %d)", d->nphases, d->ntaps);
+    CSBSR_REQUIRE(d->stride >= 1 && d->stride <= 8, "conv_igemm: bad stride %d", d->stride);
+    CSBSR_REQUIRE(d->n >= 1 && d->oh >= 1 && d->ow >= 1, "conv_igemm: empty output");
+    if (d->out_mode == CSBSR_OUT_BF16_NHWC) {
+        CSBSR_REQUIRE(d->cout_store % 8 == 0 && d->y_pitch % 8 == 0 && d->y_coff % 8 == 0,
+                      "conv_igemm: bf16 output needs cout_store/pitch/offset multiples of 8");
+        CSBSR_REQUIRE(!d->r32, "conv_igemm: r32 only with f32 planar output");
+    } else {
+        CSBSR_REQUIRE(d->cout_store >= 1 && d->cout_store <= 8, "conv_igemm: f32 planar output needs cout_store<=8");
+        CSBSR_REQUIRE(!d->r0 && !d->rm && !d->r1, "conv_igemm: bf16 residuals only with bf16 output");
+    }
+    CSBSR_REQUIRE(d->cout_store <= d->cout_pad, "conv_igemm: cout_store > cout_pad");
+    for (int i = 0; i < d->nphases * d->ntaps; ++i)
+        CSBSR_REQUIRE(d->widx[i] >= 0 && d->widx[i] < d->w_taps, "conv_igemm: widx[%d]=%d out of range", i, d->widx[i]);
+
+    PFN_encodeTiled encode = get_encode_fn();
+    CSBSR_REQUIRE(encode, "conv_igemm: cuTensorMapEncodeTiled entry point unavailable");
+
+    ConvKParams p;
+    memset(&p, 0, sizeof(p));
+    int block_n = d->block_n;
+    if (block_n <= 0) {
+        if (d->cout_pad % 256 == 0) block_n = 256;
+        else if (d->cout_pad % 128 == 0) block_n = 128;
+        else if (d->cout_pad <= 256) block_n = d->cout_pad;
+        else if (d->cout_pad % 64 == 0) block_n = 64;
+        else if (d->cout_pad % 32 == 0) block_n = 32;
+        else block_n = 16;
+    }
+    CSBSR_REQUIRE(block_n % 16 == 0 && block_n >= 16 && block_n <= 256 && d->cout_pad % block_n == 0,
+                  "conv_igemm: block_n=%d incompatible with cout_pad=%d", block_n, d->cout_pad);
+    p.block_n = block_n;
+    p.TW = d->ow > 8 ? 16 : 8;
+    p.TH = kBlockM / p.TW;
+    p.tiles_h = (d->oh + p.TH - 1) / p.TH;
+    p.tiles_w = (d->ow + p.TW - 1) / p.TW;
+    p.m_tiles = d->n * p.tiles_h * p.tiles_w;
+    p.n_tiles = d->cout_pad / block_n;
+    p.nphases = d->nphases;
+    p.total_tiles = p.m_tiles * p.n_tiles * p.nphases;
+    p.kchunks = d->cin / kBlockK;
+    p.ntaps = d->ntaps;
+    p.stride = d->stride;
+    const int stage_bytes = kATileBytes + block_n * kBlockK * 2;
+    int stages = (kSmemBudget - 2048) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    CSBSR_REQUIRE(stages >= 2, "conv_igemm: not enough shared memory for 2 stages");
+    p.stages = stages;
+    p.OH = d->oh; p.OW = d->ow; p.os = d->os > 0 ? d->os : 1; p.YH = d->yh; p.YW = d->yw; p.N = d->n;
+    p.out_mode = d->out_mode; p.y_pitch = d->y_pitch; p.y_coff = d->y_coff; p.cout_store = d->cout_store;
+    p.bias_sn = d->bias_sn; p.bias_sc = d->bias_sc; p.cls_bw = d->cls_bw; p.act = d->act;
+    p.slope = d->slope; p.r1_sign = d->r1_sign;
+    p.r0_pitch = d->r0_pitch; p.r0_coff = d->r0_coff; p.rm_pitch = d->rm_pitch; p.rm_coff = d->rm_coff;
+    p.r1_pitch = d->r1_pitch; p.r1_coff = d->r1_coff;
+    p.y = d->y; p.bias = d->bias;
+    p.r0 = reinterpret_cast<const __nv_bfloat16*>(d->r0);
+    p.rm = reinterpret_cast<const __nv_bfloat16*>(d->rm);
+    p.r1 = reinterpret_cast<const __nv_bfloat16*>(d->r1);
+    p.r32 = d->r32;
+    memcpy(p.dh, d->dh, sizeof(p.dh)); memcpy(p.dw, d->dw, sizeof(p.dw)); memcpy(p.widx, d->widx, sizeof(p.widx));
+    memcpy(p.ooh, d->ooh, sizeof(p.ooh)); memcpy(p.oow, d->oow, sizeof(p.oow));
+    CSBSR_REQUIRE(!d->bias || (d->bias_sn % 4 == 0 && d->bias_sc % 4 == 0), "conv_igemm: bias strides must be multiples of 4");
+    for (int ph = 0; ph < p.nphases; ++ph)
+        CSBSR_REQUIRE((p.OH - 1) * p.os + p.ooh[ph] < p.YH && (p.OW - 1) * p.os + p.oow[ph] < p.YW && p.ooh[ph] >= 0 &&
+                          p.oow[ph] >= 0,
+                      "conv_igemm: phase %d writes outside the %dx%d output", ph, p.YH, p.YW);
+
+    if (!g_err_flag) {
+        CSBSR_CHECK_CUDA(cudaMalloc(&g_err_flag, sizeof(int)));
+        CSBSR_CHECK_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
+    }
+    p.err_flag = g_err_flag;
+
+    // ---- tensor maps
+    CUtensorMap tmA, tmB;
+    {
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(d->x) + d->x_coff;
+        cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+        cuuint64_t strides[3] = {(cuuint64_t)d->x_pitch * 2, (cuuint64_t)d->x_pitch * 2 * d->w,
+                                 (cuuint64_t)d->x_pitch * 2 * d->w * d->h};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.TW * d->stride), (cuuint32_t)(p.TH * d->stride), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+        CSBSR_REQUIRE(box[1] <= 256 && box[2] <= 256, "conv_igemm: TMA box too large");
+        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CSBSR_REQUIRE(r == CUDA_SUCCESS, "conv_igemm: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)d->cout_pad, (cuuint64_t)d->w_taps};
+        cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * d->cout_pad};
+        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d->wgt, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CSBSR_REQUIRE(r == CUDA_SUCCESS, "conv_igemm: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    }
+
+    const int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static int smem_attr_set = 0;
+    if (smem_attr_set < smem_bytes) {
+        CSBSR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              kSmemBudget));
+        smem_attr_set = kSmemBudget;
+    }
+    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,201 @@
+"""Python launchers for the C-ABI kernels: weight packing + descriptor filling. No math happens here.
+
+Activations live in HBM as NHWC bf16 "feature maps" (`Fmap`): a [N,H,W,P] tensor plus a channel
+window, so that the reference's torch.cat calls (kbpn.py:173-186) become writes into channel slices.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, OUT_BF16_NHWC, OUT_F32_NCHW, ConvDesc)
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class Fmap:
+    """A channel window [coff, coff+c) of an NHWC bf16 tensor."""
+
+    def __init__(self, t, coff=0, c=None):
+        assert t.dim() == 4 and t.dtype == torch.bfloat16 and t.is_contiguous()
+        self.t = t
+        self.coff = coff
+        self.c = t.shape[3] - coff if c is None else c
+        assert 0 <= coff and coff + self.c <= t.shape[3]
+
+    @staticmethod
+    def empty(n, h, w, c, device="cuda", zero=False):
+        f = torch.zeros if zero else torch.empty
+        return Fmap(f((n, h, w, c), dtype=torch.bfloat16, device=device))
+
+    @property
+    def n(self):
+        return self.t.shape[0]
+
+    @property
+    def h(self):
+        return self.t.shape[1]
+
+    @property
+    def w(self):
+        return self.t.shape[2]
+
+    @property
+    def pitch(self):
+        return self.t.shape[3]
+
+    def window(self, coff, c):
+        return Fmap(self.t, self.coff + coff, c)
+
+    def ptr(self):
+        return self.t.data_ptr()
+
+    def to_nchw_f32(self, c=None):
+        c = self.c if c is None else c
+        return self.t[..., self.coff:self.coff + c].permute(0, 3, 1, 2).float().contiguous()
+
+    @staticmethod
+    def from_nchw(x, cpad=None):
+        n, c, h, w = x.shape
+        cpad = cpad or round_up(c, 64)
+        t = torch.zeros((n, h, w, cpad), dtype=torch.bfloat16, device=x.device)
+        t[..., :c] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+        return Fmap(t, 0, cpad)
+
+
+class PackedConv:
+    """Weights of one conv / transposed conv packed K-major per tap: [taps][cout_pad][cin_pad] bf16."""
+
+    def __init__(self, wp, taps, nphases, ntaps, stride, os, ooh, oow, cout, bias=None):
+        self.wp = wp                      # [w_taps, cout_pad, cin_pad] bf16, contiguous
+        self.taps = taps                  # list of (dh, dw, widx), length nphases*ntaps
+        self.nphases, self.ntaps = nphases, ntaps
+        self.stride, self.os = stride, os
+        self.ooh, self.oow = ooh, oow
+        self.cout = cout
+        self.bias = bias                  # fp32 [cout_pad] or None
+
+    @property
+    def cout_pad(self):
+        return self.wp.shape[1]
+
+    @property
+    def cin_pad(self):
+        return self.wp.shape[2]
+
+
+def _pad_bias(bias, cout_pad, device):
+    if bias is None:
+        return None
+    b = torch.zeros(cout_pad, dtype=torch.float32, device=device)
+    b[:bias.numel()] = bias.detach().float()
+    return b
+
+
+def pack_conv(weight, bias=None, stride=1, padding=0, dilation=1, cin_pad=None, cout_pad=None, scale=None,
+              cin_map=None):
+    """nn.Conv2d weight [Cout,Cin,R,S] -> PackedConv. `scale` (per-cout) folds an eval-mode BatchNorm.
+    `cin_map`: optional list of (src_start, src_len, dst_start) placing input-channel ranges in the padded K axis."""
+    w = weight.detach().float()
+    if scale is not None:
+        w = w * scale.view(-1, 1, 1, 1)
+    cout, cin, R, S = w.shape
+    cout_pad = cout_pad or round_up(cout, 16)
+    if cin_map is None:
+        cin_map = [(0, cin, 0)]
+    need = max(d + l for _, l, d in cin_map)
+    cin_pad = cin_pad or round_up(need, 64)
+    wp = torch.zeros((R * S, cout_pad, cin_pad), dtype=torch.float32, device=w.device)
+    wt = w.permute(2, 3, 0, 1).reshape(R * S, cout, cin)
+    for s0, ln, d0 in cin_map:
+        wp[:, :cout, d0:d0 + ln] = wt[:, :, s0:s0 + ln]
+    taps = [(r * dilation - padding, s * dilation - padding, r * S + s) for r in range(R) for s in range(S)]
+    return PackedConv(wp.to(torch.bfloat16).contiguous(), taps, 1, R * S, stride, 1, [0], [0], cout,
+                      _pad_bias(bias, cout_pad, w.device))
+
+
+def pack_deconv8s4(weight, bias=None, cin_pad=None, cout_pad=None):
+    """nn.ConvTranspose2d(k=8, s=4, p=2) weight [Cin,Cout,8,8] -> 16 output phases of a 2x2 conv.
+
+    out[4q+rho] = sum_{ih} x[ih] * w[.., r = 4q+rho+2-4ih]; for rho in {0,1}: ih in {q-1 (r=rho+6), q (r=rho+2)},
+    for rho in {2,3}: ih in {q (r=rho+2), q+1 (r=rho-2)}  (kbpn.py:274-277 DeconvBlock, 8/4/2 setting :23-26)."""
+    w = weight.detach().float()
+    cin, cout, R, S = w.shape
+    assert R == 8 and S == 8
+    cout_pad = cout_pad or round_up(cout, 16)
+    cin_pad = cin_pad or round_up(cin, 64)
+    wp = torch.zeros((64, cout_pad, cin_pad), dtype=torch.float32, device=w.device)
+    wp[:, :cout, :cin] = w.permute(2, 3, 1, 0).reshape(64, cout, cin)
+
+    def axis_taps(rho):
+        return [(-1, rho + 6), (0, rho + 2)] if rho < 2 else [(0, rho + 2), (1, rho - 2)]
+
+    taps, ooh, oow = [], [], []
+    for rh in range(4):
+        for rw in range(4):
+            for dh, r in axis_taps(rh):
+                for dw, s in axis_taps(rw):
+                    taps.append((dh, dw, r * 8 + s))
+            ooh.append(rh)
+            oow.append(rw)
+    return PackedConv(wp.to(torch.bfloat16).contiguous(), taps, 16, 4, 1, 4, ooh, oow, cout,
+                      _pad_bias(bias, cout_pad, w.device))
+
+
+def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, act=ACT_NONE, slope=0.0,
+         r0=None, rm=None, r1=None, r1_sign=1.0, r32=None, cout_store=None, block_n=0):
+    """Launch the tcgen05 implicit-GEMM conv. `y` is an Fmap (bf16 NHWC) or an fp32 [N,C,H,W] tensor."""
+    d = ConvDesc()
+    d.x = x.ptr()
+    d.n, d.h, d.w = x.n, x.h, x.w
+    d.x_pitch, d.x_coff, d.cin = x.pitch, x.coff, pc.cin_pad
+    assert x.c >= pc.cin_pad or x.coff + pc.cin_pad <= x.pitch, "input window narrower than packed K"
+    d.wgt = pc.wp.data_ptr()
+    d.w_taps, d.cout_pad = pc.wp.shape[0], pc.cout_pad
+    d.nphases, d.ntaps, d.stride = pc.nphases, pc.ntaps, pc.stride
+    for i, (dh, dw, wi) in enumerate(pc.taps):
+        d.dh[i], d.dw[i], d.widx[i] = dh, dw, wi
+    d.os = pc.os
+    for i in range(pc.nphases):
+        d.ooh[i], d.oow[i] = pc.ooh[i], pc.oow[i]
+    if isinstance(y, Fmap):
+        d.out_mode = OUT_BF16_NHWC
+        d.yh, d.yw = y.h, y.w
+        d.y = y.ptr()
+        d.y_pitch, d.y_coff = y.pitch, y.coff
+        d.cout_store = cout_store if cout_store is not None else min(y.c, pc.cout_pad)
+        assert y.n == x.n
+    else:
+        assert y.dtype == torch.float32 and y.is_contiguous() and y.dim() == 4
+        d.out_mode = OUT_F32_NCHW
+        d.yh, d.yw = y.shape[2], y.shape[3]
+        d.y = y.data_ptr()
+        d.cout_store = y.shape[1]
+        assert y.shape[0] == x.n
+    if oh is None:
+        oh = (d.yh - pc.ooh[0] + pc.os - 1) // pc.os if pc.os > 1 else d.yh
+        ow = (d.yw - pc.oow[0] + pc.os - 1) // pc.os if pc.os > 1 else d.yw
+    d.oh, d.ow = oh, ow
+    b = bias if bias is not None else pc.bias
+    if b is not None:
+        assert b.dtype == torch.float32 and b.is_contiguous()
+        d.bias = b.data_ptr()
+        d.bias_sn, d.bias_sc, d.cls_bw = bias_sn, bias_sc, cls_bw
+    d.act, d.slope = act, float(slope)
+    keep = [b]
+    for name, r in (("r0", r0), ("rm", rm), ("r1", r1)):
+        if r is not None:
+            assert r.n == x.n and r.h == d.yh and r.w == d.yw
+            setattr(d, name, r.ptr())
+            setattr(d, name + "_pitch", r.pitch)
+            setattr(d, name + "_coff", r.coff)
+    d.r1_sign = float(r1_sign)
+    if r32 is not None:
+        assert r32.dtype == torch.float32 and r32.is_contiguous()
+        d.r32 = r32.data_ptr()
+    d.block_n = block_n
+    rc = _lib.lib().csbsr_conv_igemm(C.byref(d), _lib.stream_ptr())
+    _lib.check(rc, "csbsr_conv_igemm")
+    return y
