@@ -1,0 +1,176 @@
+"""Parameter inventory of the CSBSR networks: names and shapes identical to the reference's state_dict
+(SURVEY.md App. A.4), so released / reference checkpoints load with strict=True.
+
+KBPN:   model/modeling/kbpn.py:17-82 (KBPN.__init__), :157-170 (stage), :344-375 (KBlock), :450-489
+        (Up/DownBlock), :493-507 (SFTlayer), :521-541 (KernelPredictorLikeIKC), :292-312 (predictor_withGAP)
+PSPNet: model/modeling/pspnet_pytorch/pspnet.py:23-86, extractors.py:37-148 (ResNet-34, BasicBlock)
+"""
+import zlib
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+
+def kbpn_param_shapes(num_stages=4, md_ch=128, k_est=7, k_out=21, num_ch=3, reduction_ch=32):
+    """OrderedDict name -> shape for `sr_model.*` (KBPN, scale 4: conv setting 8/4/2)."""
+    P = OrderedDict()
+    kc = k_est * k_est          # 49
+    cond = k_out * k_out        # 441
+
+    def convblock(pfx, cin, cout, k, bias=False, act=None):
+        P[pfx + ".layer.weight"] = (cout, cin, k, k)
+        if bias:
+            P[pfx + ".layer.bias"] = (cout,)
+        if act == "prelu":
+            P[pfx + ".act.weight"] = (1,)
+
+    def deconvblock(pfx, cin, cout, k, act="prelu"):
+        P[pfx + ".layer.weight"] = (cin, cout, k, k)
+        if act == "prelu":
+            P[pfx + ".act.weight"] = (1,)
+
+    for idx, (ci, co) in zip((0, 2, 4, 6), ((num_ch, 64), (64, 64), (64, 128), (128, 128))):
+        P["feat.%d.weight" % idx] = (co, ci, 3, 3)
+        P["feat.%d.bias" % idx] = (co,)
+    for i in range(3):
+        convblock("predictor.feat_ext.%d" % i, md_ch, md_ch if i < 2 else kc, 3, act="prelu")
+    for s in range(num_stages):
+        stages = s + 1
+        up_stages = stages - 1 if stages > 1 else 1
+        sp = "back_projection_stages.%d" % s
+        convblock(sp + ".up.conv", md_ch * up_stages, md_ch, 1, bias=True, act="prelu")
+        convblock(sp + ".up.up_conv2", md_ch, md_ch, 8, act="prelu")
+        deconvblock(sp + ".up.up_conv1", md_ch, md_ch, 8)
+        deconvblock(sp + ".up.up_conv3", md_ch, md_ch, 8)
+        convblock(sp + ".kb.sr_reconst", stages * md_ch, 3, 3)
+        kp = sp + ".kb.kernel_predictor"
+        convblock(kp + ".fe_SR.0", 3, kc, 3)
+        convblock(kp + ".fe_SR.1", kc, reduction_ch, 1)
+        convblock(kp + ".fe_SR.2", reduction_ch, reduction_ch, 3)
+        convblock(kp + ".fe_SR.3", reduction_ch, reduction_ch, 3)
+        convblock(kp + ".fe_SR.4", reduction_ch, kc, 3)
+        convblock(kp + ".fe_kernel.0", cond, kc, 3)
+        convblock(kp + ".fe_kernel.1", kc, kc, 3)
+        convblock(kp + ".fe_cat.0", 2 * kc, reduction_ch, 1)
+        convblock(kp + ".fe_cat.1", reduction_ch, reduction_ch, 3)
+        convblock(kp + ".fe_cat.2", reduction_ch, kc, 3)
+        deconvblock(sp + ".kb.up_conv1", 3, md_ch, 8)
+        if s < num_stages - 1:
+            convblock(sp + ".down.conv", md_ch * stages, md_ch, 1, bias=True, act="prelu")
+            convblock(sp + ".down.down_conv1", md_ch, md_ch, 8, act="prelu")
+            convblock(sp + ".down.down_conv3", md_ch, md_ch, 8, act="prelu")
+            deconvblock(sp + ".down.down_conv2", md_ch, md_ch, 8)
+            cc = stages * md_ch + cond
+            for br in ("scale", "shift"):
+                P[sp + ".sft.SFT_%s_conv0.weight" % br] = (cc, cc, 3, 3)
+                P[sp + ".sft.SFT_%s_conv0.bias" % br] = (cc,)
+                P[sp + ".sft.SFT_%s_conv1.weight" % br] = (stages * md_ch, cc, 3, 3)
+                P[sp + ".sft.SFT_%s_conv1.bias" % br] = (stages * md_ch,)
+    convblock("output_conv", num_stages * md_ch, num_ch, 3)
+    return P
+
+
+def _bn(P, pfx, c):
+    P[pfx + ".weight"] = (c,)
+    P[pfx + ".bias"] = (c,)
+    P[pfx + ".running_mean"] = (c,)
+    P[pfx + ".running_var"] = (c,)
+    P[pfx + ".num_batches_tracked"] = ()
+
+
+RESNET34_LAYERS = ((64, 3, 1, 1), (128, 4, 2, 1), (256, 6, 1, 2), (512, 3, 1, 4))   # planes, blocks, stride, dilation
+
+
+def pspnet_param_shapes(n_classes=1, sizes=(1, 2, 3, 6), psp_size=512, deep_features_size=256):
+    """OrderedDict name -> shape for `segmentation_model.*` (PSPNet on a dilated ResNet-34)."""
+    P = OrderedDict()
+    P["feats.conv1.weight"] = (64, 3, 7, 7)
+    _bn(P, "feats.bn1", 64)
+    inplanes = 64
+    for li, (planes, blocks, stride, _dil) in enumerate(RESNET34_LAYERS, 1):
+        for b in range(blocks):
+            bp = "feats.layer%d.%d" % (li, b)
+            P[bp + ".conv1.weight"] = (planes, inplanes if b == 0 else planes, 3, 3)
+            _bn(P, bp + ".bn1", planes)
+            P[bp + ".conv2.weight"] = (planes, planes, 3, 3)
+            _bn(P, bp + ".bn2", planes)
+            if b == 0 and (stride != 1 or inplanes != planes):
+                P[bp + ".downsample.0.weight"] = (planes, inplanes, 1, 1)
+                _bn(P, bp + ".downsample.1", planes)
+        inplanes = planes
+    for i, _ in enumerate(sizes):
+        P["psp.stages.%d.1.weight" % i] = (psp_size, psp_size, 1, 1)
+    P["psp.bottleneck.weight"] = (1024, psp_size * (len(sizes) + 1), 1, 1)
+    P["psp.bottleneck.bias"] = (1024,)
+    for name, (ci, co) in (("up_1", (1024, 256)), ("up_2", (256, 64)), ("up_3", (64, 64))):
+        P[name + ".conv.0.weight"] = (co, ci, 3, 3)
+        P[name + ".conv.0.bias"] = (co,)
+        _bn(P, name + ".conv.1", co)
+        P[name + ".conv.2.weight"] = (1,)
+    P["final.0.weight"] = (n_classes, 64, 1, 1)
+    P["final.0.bias"] = (n_classes,)
+    P["aux.0.weight"] = (256, deep_features_size, 3, 3)
+    _bn(P, "aux.1", 256)
+    P["aux.4.weight"] = (n_classes, 256, 1, 1)
+    P["aux.4.bias"] = (n_classes,)
+    return P
+
+
+_BUFFER_SUFFIXES = ("running_mean", "running_var", "num_batches_tracked")
+
+
+class ParamTree(nn.Module):
+    """Nested parameter holder reproducing dotted state_dict keys (never called as a network)."""
+
+    def __init__(self, shapes=None):
+        super().__init__()
+        for name, shape in (shapes or {}).items():
+            self._add(name.split("."), shape)
+
+    def _add(self, parts, shape):
+        if len(parts) == 1:
+            leaf = parts[0]
+            if leaf == "num_batches_tracked":
+                self.register_buffer(leaf, torch.zeros((), dtype=torch.long))
+            elif leaf in _BUFFER_SUFFIXES:
+                self.register_buffer(leaf, torch.ones(shape) if leaf == "running_var" else torch.zeros(shape))
+            else:
+                self.register_parameter(leaf, nn.Parameter(torch.zeros(shape)))
+            return
+        child = self._modules.get(parts[0])
+        if child is None:
+            child = ParamTree()
+            self.add_module(parts[0], child)
+        child._add(parts[1:], shape)
+
+
+def synth_state_dict(shapes, seed=1121, prefix=""):
+    """Deterministic synthetic weights, independent of construction order (keyed by parameter name).
+
+    Distributions mimic the reference's random init (kaiming-normal convs, kbpn.py:73-82,228-238;
+    extractors.py:126-132) but also randomise biases / BN statistics / PReLU slopes so every parameter
+    is exercised by the parity tests."""
+    sd = OrderedDict()
+    for name, shape in shapes.items():
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 31))
+        leaf = name.rsplit(".", 1)[-1]
+        if leaf == "num_batches_tracked":
+            t = torch.zeros((), dtype=torch.long)
+        elif len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            t = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
+        elif leaf == "running_var":
+            t = 0.5 + torch.rand(shape, generator=g)
+        elif leaf == "running_mean":
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif leaf == "weight" and shape == (1,):            # PReLU slope
+            t = 0.01 + 0.24 * torch.rand(shape, generator=g)
+        elif leaf == "weight":                               # BatchNorm gamma
+            t = 0.5 + torch.rand(shape, generator=g)
+        elif leaf == "bias":
+            t = 0.05 * torch.randn(shape, generator=g)
+        else:
+            raise ValueError(name)
+        sd[prefix + name] = t
+    return sd
