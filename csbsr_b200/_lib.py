@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcsbsr_b200.so")
 MAX_TAPS = 64
 MAX_PHASES = 16
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
-OUT_BF16_NHWC, OUT_F32_NCHW = 0, 1
+OUT_BF16_NHWC, OUT_F32_NCHW, OUT_F32_NHWC = 0, 1, 2
 
 
 class CsbsrError(RuntimeError):
@@ -57,6 +57,21 @@ _SIGNATURES = {
     "csbsr_version": (C.c_int, []),
     "csbsr_device_ok": (C.c_int, []),
     "csbsr_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "csbsr_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]),
+    "csbsr_patchify": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 12 + [C.c_void_p, C.c_void_p, C.c_int,
+                                                                            C.c_void_p]),
+    "csbsr_gap_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    "csbsr_kernel_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "csbsr_vec_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "csbsr_broadcast_vec": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_blur_per_sample": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_bicubic_upsample": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "csbsr_instnorm_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "csbsr_clip_instnorm_stats": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_float, C.c_void_p]),
+    "csbsr_maxpool3s2_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]),
+    "csbsr_adaptive_avgpool_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
+    "csbsr_bilinear_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 11 + [C.c_void_p]),
+    "csbsr_bilinear_f32": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
 }
 
 

@@ -368,6 +368,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.y_pitch + p.y_coff +
                                                   c) = o;
                     }
+                } else if (p.out_mode == CSBSR_OUT_F32_NHWC) {
+                    float* y32 = reinterpret_cast<float*>(p.y) + pix * p.y_pitch + p.y_coff + c0;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        if (c0 + i < p.cout_store) {
+                            float4 o;
+                            o.x = apply_act(f[i], p.act, p.slope);
+                            o.y = apply_act(f[i + 1], p.act, p.slope);
+                            o.z = apply_act(f[i + 2], p.act, p.slope);
+                            o.w = apply_act(f[i + 3], p.act, p.slope);
+                            *reinterpret_cast<float4*>(y32 + i) = o;
+                        }
+                    }
                 } else {
                     // fp32 planar [n][cout_store][YH][YW]
                     float* y32 = reinterpret_cast<float*>(p.y);
@@ -440,6 +453,10 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
         CSBSR_REQUIRE(d->cout_store % 8 == 0 && d->y_pitch % 8 == 0 && d->y_coff % 8 == 0,
                       "conv_igemm: bf16 output needs cout_store/pitch/offset multiples of 8");
         CSBSR_REQUIRE(!d->r32, "conv_igemm: r32 only with f32 planar output");
+    } else if (d->out_mode == CSBSR_OUT_F32_NHWC) {
+        CSBSR_REQUIRE(d->cout_store % 4 == 0 && d->y_pitch % 4 == 0 && d->y_coff % 4 == 0,
+                      "conv_igemm: f32 NHWC output needs cout_store/pitch/offset multiples of 4");
+        CSBSR_REQUIRE(!d->r0 && !d->rm && !d->r1 && !d->r32, "conv_igemm: no residuals with f32 NHWC output");
     } else {
         CSBSR_REQUIRE(d->cout_store >= 1 && d->cout_store <= 8, "conv_igemm: f32 planar output needs cout_store<=8");
         CSBSR_REQUIRE(!d->r0 && !d->rm && !d->r1, "conv_igemm: bf16 residuals only with bf16 output");

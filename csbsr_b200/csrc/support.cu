@@ -1,0 +1,562 @@
+// HBM-bound support kernels around the tensor-core convs: layout conversion, 3-channel patch gather
+// (im2col for the 3-channel image inputs), pooling, resampling, per-sample kernel-vector updates,
+// per-sample depthwise blur (KBlock), clip + instance-norm statistics.  All are coalesced along the
+// NHWC channel axis (128-bit vectors where the channel count allows) or along W for planar fp32.
+#include "common.cuh"
+#include "../../include/csbsr_b200.h"
+
+namespace csbsr {
+
+static inline int grid_for(size_t work, int threads) {
+    size_t b = (work + threads - 1) / threads;
+    size_t cap = static_cast<size_t>(num_sms()) * 32;
+    return static_cast<int>(b < cap ? (b ? b : 1) : cap);
+}
+
+// ------------------------------------------------------------------ NCHW f32 -> NHWC bf16 (channel window)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int H,
+                                    int W, int pitch, int coff, int cwrite) {
+    const size_t total = static_cast<size_t>(N) * H * W * cwrite;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % cwrite);
+        const size_t pix = i / cwrite;
+        const int w = static_cast<int>(pix % W);
+        const int h = static_cast<int>((pix / W) % H);
+        const int n = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+        float v = c < C ? x[((static_cast<size_t>(n) * C + c) * H + h) * W + w] : 0.f;
+        y[pix * pitch + coff + c] = __float2bfloat16(v);
+    }
+}
+
+// ------------------------------------------------------------------ 3-channel patch gather (im2col)
+// y[n,oh,ow,(r*S+s)*C+c] = f(x[n,c,oh*st+r*dil-pad, ow*st+s*dil-pad]) (0 outside), channels >= R*S*C zero.
+// f = identity, or clamp to [0,1] followed by (v-mean[n,c])*rstd[n,c] (clip_sr + norm_sr, build_model.py:135-146).
+__global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int H, int W,
+                                int OH, int OW, int R, int S, int stride, int pad, int pitch, int cwrite,
+                                const float* __restrict__ mean, const float* __restrict__ rstd, int clamp01) {
+    const size_t total = static_cast<size_t>(N) * OH * OW * (cwrite / 8);
+    const int K = R * S * C;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % (cwrite / 8));
+        const size_t pix = i / (cwrite / 8);
+        const int ow = static_cast<int>(pix % OW);
+        const int oh = static_cast<int>((pix / OW) % OH);
+        const int n = static_cast<int>(pix / (static_cast<size_t>(OW) * OH));
+        __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = g * 8 + j;
+            float v = 0.f;
+            if (k < K) {
+                const int c = k % C;
+                const int rs = k / C;
+                const int ih = oh * stride + (rs / S) - pad;
+                const int iw = ow * stride + (rs % S) - pad;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+                    v = x[((static_cast<size_t>(n) * C + c) * H + ih) * W + iw];
+                    if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+                    if (mean) v = (v - mean[n * C + c]) * rstd[n * C + c];
+                }
+            }
+            o[j] = __float2bfloat16(v);
+        }
+        *reinterpret_cast<uint4*>(y + pix * pitch + g * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+
+// ------------------------------------------------------------------ global average pool NHWC bf16 -> f32 [N][C]
+__global__ void gap_nhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int HW, int pitch,
+                                int coff, int C, int slices) {
+    // grid: (N, slices); block: C threads (rounded to 32). Each block sums a slice of pixels; atomicAdd to out.
+    const int n = blockIdx.x, sl = blockIdx.y;
+    const int c = threadIdx.x;
+    if (c >= C) return;
+    const int per = (HW + slices - 1) / slices;
+    const int p0 = sl * per;
+    const int p1 = min(HW, p0 + per);
+    const __nv_bfloat16* base = x + static_cast<size_t>(n) * HW * pitch + coff + c;
+    float acc = 0.f;
+    for (int p = p0; p < p1; ++p) acc += __bfloat162float(base[static_cast<size_t>(p) * pitch]);
+    atomicAdd(out + n * C + c, acc / static_cast<float>(HW));
+}
+
+// ------------------------------------------------------------------ kernel-vector update
+// cubic convolution coefficients as torch's upsample_bicubic2d (A = -0.75, align_corners=False)
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+    const float A = -0.75f;
+    c[0] = cubic2(t + 1.f, A);
+    c[1] = cubic1(t, A);
+    c[2] = cubic1(1.f - t, A);
+    c[3] = cubic2(2.f - t, A);
+}
+__device__ __forceinline__ float src_index(float scale, int dst) { return scale * (dst + 0.5f) - 0.5f; }
+
+// out[b] = normalize( (pre ? pre[b] : 0) + bicubic_{ke->ko}(v[b]) ), one block per sample.
+// predictor_withGAP.upscale_and_reshape (kbpn.py:335-341), KernelPredictorLikeIKC (:574-578) + KBlock (:391-392).
+__global__ void kernel_update_kernel(const float* __restrict__ v, const float* __restrict__ pre,
+                                     float* __restrict__ out, int ke, int ko, int normalize) {
+    extern __shared__ float sh[];
+    float* sv = sh;                    // ke*ke
+    float* so = sh + ke * ke;          // ko*ko
+    __shared__ float ssum;
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < ke * ke; i += blockDim.x) sv[i] = v[b * ke * ke + i];
+    if (threadIdx.x == 0) ssum = 0.f;
+    __syncthreads();
+    const float scale = static_cast<float>(ke) / static_cast<float>(ko);
+    float local = 0.f;
+    for (int i = threadIdx.x; i < ko * ko; i += blockDim.x) {
+        const int oy = i / ko, ox = i % ko;
+        const float ry = src_index(scale, oy), rx = src_index(scale, ox);
+        const int iy = static_cast<int>(floorf(ry)), ix = static_cast<int>(floorf(rx));
+        float cy[4], cx[4];
+        cubic_coeffs(ry - iy, cy);
+        cubic_coeffs(rx - ix, cx);
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int yy = min(max(iy - 1 + a, 0), ke - 1);
+            float row = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int xx = min(max(ix - 1 + c, 0), ke - 1);
+                row += sv[yy * ke + xx] * cx[c];
+            }
+            acc += row * cy[a];
+        }
+        if (pre) acc += pre[b * ko * ko + i];
+        so[i] = acc;
+        local += acc;
+    }
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&ssum, local);
+    __syncthreads();
+    const float inv = normalize ? 1.f / ssum : 1.f;
+    for (int i = threadIdx.x; i < ko * ko; i += blockDim.x) out[b * ko * ko + i] = so[i] * inv;
+}
+
+// out[b] = v[b] / sum(v[b])   (build_model.py:491-494)
+__global__ void vec_normalize_kernel(const float* __restrict__ v, float* __restrict__ out, int L) {
+    __shared__ float ssum;
+    if (threadIdx.x == 0) ssum = 0.f;
+    __syncthreads();
+    const int b = blockIdx.x;
+    float local = 0.f;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) local += v[b * L + i];
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&ssum, local);
+    __syncthreads();
+    for (int i = threadIdx.x; i < L; i += blockDim.x) out[b * L + i] = v[b * L + i] / ssum;
+}
+
+// broadcast a per-sample vector over a small NHWC bf16 image (spatially constant conditioning)
+__global__ void broadcast_vec_kernel(const float* __restrict__ v, __nv_bfloat16* __restrict__ y, int N, int HW, int L,
+                                     int pitch, int coff, int cwrite) {
+    const size_t total = static_cast<size_t>(N) * HW * cwrite;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % cwrite);
+        const size_t pix = i / cwrite;
+        const int n = static_cast<int>(pix / HW);
+        y[pix * pitch + coff + c] = __float2bfloat16(c < L ? v[n * L + c] : 0.f);
+    }
+}
+
+// ------------------------------------------------------------------ per-sample depthwise blur, stride s, minus LR
+// err[n,c,oh,ow] = sum_{r,s} x[n,c,oh*st+r-pad, ow*st+s-pad] * k[n,r,s] - lr[n,c,oh,ow]   (kbpn.py:395-405)
+// block = one (n, c, tile of 8x32 outputs); the input patch and the kernel are staged in shared memory.
+template <int KS, int ST>
+__global__ void blur_ps_kernel(const float* __restrict__ x, const float* __restrict__ kvec,
+                               const float* __restrict__ lr, float* __restrict__ err, int C, int H, int W, int OH,
+                               int OW) {
+    constexpr int TOH = 8, TOW = 32;
+    constexpr int PH = (TOH - 1) * ST + KS, PW = (TOW - 1) * ST + KS;
+    __shared__ float sk[KS * KS];
+    __shared__ float sp[PH][PW + 1];
+    const int nc = blockIdx.z;
+    const int n = nc / C;
+    const int oh0 = blockIdx.y * TOH, ow0 = blockIdx.x * TOW;
+    const int pad = (KS - 1) / 2;
+    const float* xp = x + static_cast<size_t>(nc) * H * W;
+    for (int i = threadIdx.x; i < KS * KS; i += blockDim.x) sk[i] = kvec[n * KS * KS + i];
+    const int ih0 = oh0 * ST - pad, iw0 = ow0 * ST - pad;
+    for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
+        const int r = i / PW, c = i % PW;
+        const int ih = ih0 + r, iw = iw0 + c;
+        sp[r][c] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? xp[static_cast<size_t>(ih) * W + iw] : 0.f;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x % TOW, ty = threadIdx.x / TOW;
+    const int oh = oh0 + ty, ow = ow0 + tx;
+    if (oh < OH && ow < OW) {
+        float acc = 0.f;
+#pragma unroll 3
+        for (int r = 0; r < KS; ++r)
+#pragma unroll
+            for (int s = 0; s < KS; ++s) acc += sp[ty * ST + r][tx * ST + s] * sk[r * KS + s];
+        const size_t o = (static_cast<size_t>(nc) * OH + oh) * OW + ow;
+        err[o] = lr ? acc - lr[o] : acc;
+    }
+}
+
+// ------------------------------------------------------------------ bicubic x4 upsample, f32 planar (kbpn.py:70,113)
+__global__ void bicubic_up_kernel(const float* __restrict__ x, float* __restrict__ y, int NC, int H, int W, int f) {
+    const int OH = H * f, OW = W * f;
+    const size_t total = static_cast<size_t>(NC) * OH * OW;
+    const float scale = 1.f / f;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(i % OW);
+        const int oy = static_cast<int>((i / OW) % OH);
+        const int nc = static_cast<int>(i / (static_cast<size_t>(OW) * OH));
+        const float ry = src_index(scale, oy), rx = src_index(scale, ox);
+        const int iy = static_cast<int>(floorf(ry)), ix = static_cast<int>(floorf(rx));
+        float cy[4], cx[4];
+        cubic_coeffs(ry - iy, cy);
+        cubic_coeffs(rx - ix, cx);
+        const float* xp = x + static_cast<size_t>(nc) * H * W;
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int yy = min(max(iy - 1 + a, 0), H - 1);
+            float row = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int xx = min(max(ix - 1 + c, 0), W - 1);
+                row += xp[static_cast<size_t>(yy) * W + xx] * cx[c];
+            }
+            acc += row * cy[a];
+        }
+        y[i] = acc;
+    }
+}
+
+// ------------------------------------------------------------------ clip to [0,1] in place + per-(n,c) statistics
+__global__ void clip_stats_kernel(float* __restrict__ x, double* __restrict__ sums, int HW, int do_clip) {
+    // grid: (slices, N*C). sums[nc*2+0] += sum, sums[nc*2+1] += sum of squares (fp64 accumulation)
+    const int nc = blockIdx.y;
+    float* xp = x + static_cast<size_t>(nc) * HW;
+    double s = 0.0, ss = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        float v = xp[i];
+        if (do_clip) {
+            v = fminf(fmaxf(v, 0.f), 1.f);
+            xp[i] = v;
+        }
+        s += v;
+        ss += static_cast<double>(v) * v;
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sums[nc * 2], s);
+        atomicAdd(&sums[nc * 2 + 1], ss);
+    }
+}
+__global__ void finish_stats_kernel(const double* __restrict__ sums, float* __restrict__ mean,
+                                    float* __restrict__ rstd, int NC, int HW, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NC) return;
+    const double m = sums[i * 2] / HW;
+    double var = sums[i * 2 + 1] / HW - m * m;      // biased variance (InstanceNorm2d)
+    if (var < 0) var = 0;
+    mean[i] = static_cast<float>(m);
+    rstd[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// ------------------------------------------------------------------ NHWC bf16 pooling / resampling (8-channel vectors)
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 o;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return o;
+}
+
+// 3x3 stride-2 pad-1 max pool (extractors.py:119)
+__global__ void maxpool3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
+                                  int W, int OH, int OW, int C, int xp, int xo, int yp, int yo) {
+    const int G = C / 8;
+    const size_t total = static_cast<size_t>(N) * OH * OW * G;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const size_t pix = i / G;
+        const int ow = static_cast<int>(pix % OW);
+        const int oh = static_cast<int>((pix / OW) % OH);
+        const int n = static_cast<int>(pix / (static_cast<size_t>(OW) * OH));
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int r = 0; r < 3; ++r) {
+            const int ih = oh * 2 + r - 1;
+            if (ih < 0 || ih >= H) continue;
+            for (int s = 0; s < 3; ++s) {
+                const int iw = ow * 2 + s - 1;
+                if (iw < 0 || iw >= W) continue;
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + ih) * W + iw) * xp + xo + g * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+            }
+        }
+        *reinterpret_cast<uint4*>(y + pix * yp + yo + g * 8) = pack8(m);
+    }
+}
+
+// adaptive average pool to SxS (pspnet.py:32): bin i covers [floor(i*H/S), ceil((i+1)*H/S))
+__global__ void adaptive_avgpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N,
+                                        int H, int W, int S, int C, int xp, int xo, int yp, int yo) {
+    const int G = C / 8;
+    const size_t total = static_cast<size_t>(N) * S * S * G;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const size_t pix = i / G;
+        const int ow = static_cast<int>(pix % S);
+        const int oh = static_cast<int>((pix / S) % S);
+        const int n = static_cast<int>(pix / (static_cast<size_t>(S) * S));
+        const int h0 = (oh * H) / S, h1 = ((oh + 1) * H + S - 1) / S;
+        const int w0 = (ow * W) / S, w1 = ((ow + 1) * W + S - 1) / S;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int ih = h0; ih < h1; ++ih)
+            for (int iw = w0; iw < w1; ++iw) {
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + ih) * W + iw) * xp + xo + g * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+        const float inv = 1.f / static_cast<float>((h1 - h0) * (w1 - w0));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= inv;
+        *reinterpret_cast<uint4*>(y + pix * yp + yo + g * 8) = pack8(acc);
+    }
+}
+
+__device__ __forceinline__ void bilinear_src(int dst, int in, int out, int align, int& i0, int& i1, float& l1) {
+    float src;
+    if (align) {
+        src = out > 1 ? dst * (static_cast<float>(in - 1) / static_cast<float>(out - 1)) : 0.f;
+    } else {
+        src = (dst + 0.5f) * (static_cast<float>(in) / static_cast<float>(out)) - 0.5f;
+        if (src < 0.f) src = 0.f;
+    }
+    i0 = static_cast<int>(src);
+    if (i0 > in - 1) i0 = in - 1;
+    i1 = i0 < in - 1 ? i0 + 1 : i0;
+    l1 = src - i0;
+}
+
+// bilinear resize NHWC bf16 (F.interpolate mode='bilinear'; pspnet.py:39,56)
+__global__ void bilinear_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
+                                     int W, int OH, int OW, int C, int xp, int xo, int yp, int yo, int align) {
+    const int G = C / 8;
+    const size_t total = static_cast<size_t>(N) * OH * OW * G;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const size_t pix = i / G;
+        const int ow = static_cast<int>(pix % OW);
+        const int oh = static_cast<int>((pix / OW) % OH);
+        const int n = static_cast<int>(pix / (static_cast<size_t>(OW) * OH));
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilinear_src(oh, H, OH, align, y0, y1, ly);
+        bilinear_src(ow, W, OW, align, x0, x1, lx);
+        const __nv_bfloat16* base = x + static_cast<size_t>(n) * H * W * xp + xo + g * 8;
+        float a[8], b[8], c[8], d[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y0) * W + x0) * xp), a);
+        unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y0) * W + x1) * xp), b);
+        unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y1) * W + x0) * xp), c);
+        unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y1) * W + x1) * xp), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
+        *reinterpret_cast<uint4*>(y + pix * yp + yo + g * 8) = pack8(o);
+    }
+}
+
+// bilinear resize of planar f32 maps (aux head, align_corners=True; pspnet.py:122)
+__global__ void bilinear_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int NC, int H, int W, int OH,
+                                    int OW, int align) {
+    const size_t total = static_cast<size_t>(NC) * OH * OW;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ow = static_cast<int>(i % OW);
+        const int oh = static_cast<int>((i / OW) % OH);
+        const int nc = static_cast<int>(i / (static_cast<size_t>(OW) * OH));
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilinear_src(oh, H, OH, align, y0, y1, ly);
+        bilinear_src(ow, W, OW, align, x0, x1, lx);
+        const float* b = x + static_cast<size_t>(nc) * H * W;
+        y[i] = (1.f - ly) * ((1.f - lx) * b[y0 * W + x0] + lx * b[y0 * W + x1]) +
+               ly * ((1.f - lx) * b[y1 * W + x0] + lx * b[y1 * W + x1]);
+    }
+}
+
+}  // namespace csbsr
+
+using namespace csbsr;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int csbsr_nchw_f32_to_nhwc_bf16(const float* x, void* y, int n, int c, int h, int w, int y_pitch,
+                                           int y_coff, int cwrite, void* stream) {
+    CSBSR_REQUIRE(x && y && n > 0 && c > 0 && h > 0 && w > 0 && cwrite >= c, "nchw_to_nhwc: bad arguments");
+    const size_t total = static_cast<size_t>(n) * h * w * cwrite;
+    nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, c,
+                                                                         h, w, y_pitch, y_coff, cwrite);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_patchify(const float* x, void* y, int n, int c, int h, int w, int oh, int ow, int r, int s,
+                              int stride, int pad, int y_pitch, int cwrite, const float* mean, const float* rstd,
+                              int clamp01, void* stream) {
+    CSBSR_REQUIRE(x && y && n > 0 && cwrite % 8 == 0 && y_pitch % 8 == 0 && cwrite >= r * s * c && cwrite <= y_pitch,
+                  "patchify: bad arguments (cwrite=%d, need >= %d)", cwrite, r * s * c);
+    CSBSR_REQUIRE((mean == nullptr) == (rstd == nullptr), "patchify: mean/rstd must come together");
+    const size_t total = static_cast<size_t>(n) * oh * ow * (cwrite / 8);
+    patchify_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, c, h, w,
+                                                                     oh, ow, r, s, stride, pad, y_pitch, cwrite, mean,
+                                                                     rstd, clamp01);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_gap_nhwc(const void* x, float* out, int n, int hw, int pitch, int coff, int c, void* stream) {
+    CSBSR_REQUIRE(x && out && n > 0 && hw > 0 && c > 0 && c <= 1024, "gap_nhwc: bad arguments");
+    CSBSR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n * c, STREAM(stream)));
+    int slices = hw / 256;
+    if (slices < 1) slices = 1;
+    if (slices > 128) slices = 128;
+    dim3 grid(n, slices);
+    gap_nhwc_kernel<<<grid, (c + 31) / 32 * 32, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, hw,
+                                                                    pitch, coff, c, slices);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_kernel_update(const float* v, const float* pre, float* out, int b, int ke, int ko, int normalize,
+                                   void* stream) {
+    CSBSR_REQUIRE(v && out && b > 0 && ke > 0 && ko > 0, "kernel_update: bad arguments");
+    kernel_update_kernel<<<b, 128, sizeof(float) * (ke * ke + ko * ko), STREAM(stream)>>>(v, pre, out, ke, ko, normalize);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_vec_normalize(const float* v, float* out, int b, int len, void* stream) {
+    CSBSR_REQUIRE(v && out && b > 0 && len > 0, "vec_normalize: bad arguments");
+    vec_normalize_kernel<<<b, 128, 0, STREAM(stream)>>>(v, out, len);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_broadcast_vec(const float* v, void* y, int n, int hw, int len, int y_pitch, int y_coff,
+                                   int cwrite, void* stream) {
+    CSBSR_REQUIRE(v && y && n > 0 && hw > 0 && cwrite >= len, "broadcast_vec: bad arguments");
+    const size_t total = static_cast<size_t>(n) * hw * cwrite;
+    broadcast_vec_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(v, reinterpret_cast<__nv_bfloat16*>(y), n, hw,
+                                                                          len, y_pitch, y_coff, cwrite);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_blur_per_sample(const float* x, const float* kvec, const float* lr, float* err, int n, int c,
+                                     int h, int w, int ksize, int stride, void* stream) {
+    CSBSR_REQUIRE(x && kvec && err && n > 0 && c > 0, "blur_per_sample: bad arguments");
+    CSBSR_REQUIRE(ksize == 21 && (stride == 4 || stride == 1), "blur_per_sample: only ksize=21, stride in {1,4}");
+    const int pad = (ksize - 1) / 2;
+    const int oh = (h + 2 * pad - ksize) / stride + 1, ow = (w + 2 * pad - ksize) / stride + 1;
+    dim3 grid((ow + 31) / 32, (oh + 7) / 8, n * c);
+    if (stride == 4)
+        blur_ps_kernel<21, 4><<<grid, 256, 0, STREAM(stream)>>>(x, kvec, lr, err, c, h, w, oh, ow);
+    else
+        blur_ps_kernel<21, 1><<<grid, 256, 0, STREAM(stream)>>>(x, kvec, lr, err, c, h, w, oh, ow);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_bicubic_upsample(const float* x, float* y, int nc, int h, int w, int factor, void* stream) {
+    CSBSR_REQUIRE(x && y && nc > 0 && factor >= 1, "bicubic_upsample: bad arguments");
+    const size_t total = static_cast<size_t>(nc) * h * w * factor * factor;
+    bicubic_up_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, y, nc, h, w, factor);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" size_t csbsr_instnorm_workspace_bytes(int nc) { return sizeof(double) * 2 * static_cast<size_t>(nc); }
+
+extern "C" int csbsr_clip_instnorm_stats(float* x, float* mean, float* rstd, void* workspace, int nc, int hw,
+                                         int do_clip, float eps, void* stream) {
+    CSBSR_REQUIRE(x && mean && rstd && workspace && nc > 0 && hw > 0, "clip_instnorm_stats: bad arguments");
+    double* sums = reinterpret_cast<double*>(workspace);
+    CSBSR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * nc, STREAM(stream)));
+    int slices = (hw + 256 * 16 - 1) / (256 * 16);
+    if (slices < 1) slices = 1;
+    dim3 grid(slices, nc);
+    clip_stats_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, sums, hw, do_clip);
+    finish_stats_kernel<<<(nc + 127) / 128, 128, 0, STREAM(stream)>>>(sums, mean, rstd, nc, hw, eps);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_maxpool3s2_nhwc(const void* x, void* y, int n, int h, int w, int c, int x_pitch, int x_coff,
+                                     int y_pitch, int y_coff, void* stream) {
+    CSBSR_REQUIRE(x && y && c % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && x_coff % 8 == 0 && y_coff % 8 == 0,
+                  "maxpool: channel counts/offsets must be multiples of 8");
+    const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
+    const size_t total = static_cast<size_t>(n) * oh * ow * (c / 8);
+    maxpool3s2_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                       reinterpret_cast<__nv_bfloat16*>(y), n, h, w, oh,
+                                                                       ow, c, x_pitch, x_coff, y_pitch, y_coff);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_adaptive_avgpool_nhwc(const void* x, void* y, int n, int h, int w, int s, int c, int x_pitch,
+                                           int x_coff, int y_pitch, int y_coff, void* stream) {
+    CSBSR_REQUIRE(x && y && s > 0 && c % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && x_coff % 8 == 0 &&
+                      y_coff % 8 == 0,
+                  "adaptive_avgpool: bad arguments");
+    const size_t total = static_cast<size_t>(n) * s * s * (c / 8);
+    adaptive_avgpool_kernel<<<grid_for(total, 128), 128, 0, STREAM(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), n, h, w, s, c, x_pitch, x_coff,
+        y_pitch, y_coff);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_bilinear_nhwc(const void* x, void* y, int n, int h, int w, int oh, int ow, int c, int x_pitch,
+                                   int x_coff, int y_pitch, int y_coff, int align_corners, void* stream) {
+    CSBSR_REQUIRE(x && y && c % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && x_coff % 8 == 0 && y_coff % 8 == 0,
+                  "bilinear_nhwc: channel counts/offsets must be multiples of 8");
+    const size_t total = static_cast<size_t>(n) * oh * ow * (c / 8);
+    bilinear_nhwc_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), n, h, w, oh, ow, c, x_pitch,
+        x_coff, y_pitch, y_coff, align_corners);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_bilinear_f32(const float* x, float* y, int nc, int h, int w, int oh, int ow, int align_corners,
+                                  void* stream) {
+    CSBSR_REQUIRE(x && y && nc > 0, "bilinear_f32: bad arguments");
+    const size_t total = static_cast<size_t>(nc) * oh * ow;
+    bilinear_f32_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, y, nc, h, w, oh, ow, align_corners);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -8,7 +8,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, OUT_BF16_NHWC, OUT_F32_NCHW, ConvDesc)
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, OUT_BF16_NHWC, OUT_F32_NCHW, OUT_F32_NHWC,
+                   ConvDesc)
 
 
 def round_up(v, m):
@@ -63,6 +64,14 @@ class Fmap:
         t = torch.zeros((n, h, w, cpad), dtype=torch.bfloat16, device=x.device)
         t[..., :c] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
         return Fmap(t, 0, cpad)
+
+
+class F32Map:
+    """fp32 NHWC conv output [N,H,W,P] (used for the per-sample border-class biases)."""
+
+    def __init__(self, t):
+        assert t.dim() == 4 and t.dtype == torch.float32 and t.is_contiguous()
+        self.t = t
 
 
 class PackedConv:
@@ -167,6 +176,13 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
         d.y_pitch, d.y_coff = y.pitch, y.coff
         d.cout_store = cout_store if cout_store is not None else min(y.c, pc.cout_pad)
         assert y.n == x.n
+    elif isinstance(y, F32Map):
+        d.out_mode = OUT_F32_NHWC
+        d.yh, d.yw = y.t.shape[1], y.t.shape[2]
+        d.y = y.t.data_ptr()
+        d.y_pitch, d.y_coff = y.t.shape[3], 0
+        d.cout_store = cout_store if cout_store is not None else min(y.t.shape[3], pc.cout_pad)
+        assert y.t.shape[0] == x.n
     else:
         assert y.dtype == torch.float32 and y.is_contiguous() and y.dim() == 4
         d.out_mode = OUT_F32_NCHW
@@ -198,4 +214,100 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
     d.block_n = block_n
     rc = _lib.lib().csbsr_conv_igemm(C.byref(d), _lib.stream_ptr())
     _lib.check(rc, "csbsr_conv_igemm")
+    return y
+
+
+# ------------------------------------------------------------------ support-kernel launchers
+def _call(name, *args):
+    rc = getattr(_lib.lib(), name)(*args, _lib.stream_ptr())
+    _lib.check(rc, name)
+
+
+def _f32(t):
+    assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    return t.data_ptr()
+
+
+def nchw_to_nhwc(x, y, cwrite=None):
+    """fp32 [N,C,H,W] -> bf16 NHWC window `y` (channels [C, cwrite) zeroed)."""
+    n, c, h, w = x.shape
+    assert (y.n, y.h, y.w) == (n, h, w)
+    _call("csbsr_nchw_f32_to_nhwc_bf16", _f32(x), y.ptr(), n, c, h, w, y.pitch, y.coff, cwrite or y.c)
+    return y
+
+
+def patchify(x, y, r, s, stride, pad, mean=None, rstd=None, clamp01=False):
+    """fp32 [N,C,H,W] -> bf16 NHWC im2col rows ((r*S+s)*C+c ordering), see csbsr_patchify."""
+    n, c, h, w = x.shape
+    assert y.coff == 0 and y.n == n
+    _call("csbsr_patchify", _f32(x), y.ptr(), n, c, h, w, y.h, y.w, r, s, stride, pad, y.pitch, y.c,
+          _f32(mean) if mean is not None else None, _f32(rstd) if rstd is not None else None, int(clamp01))
+    return y
+
+
+def gap(x, out, c=None):
+    c = c or x.c
+    assert out.shape == (x.n, c)
+    _call("csbsr_gap_nhwc", x.ptr(), _f32(out), x.n, x.h * x.w, x.pitch, x.coff, c)
+    return out
+
+
+def kernel_update(v, pre, out, ke, ko, normalize=True):
+    _call("csbsr_kernel_update", _f32(v), _f32(pre) if pre is not None else None, _f32(out), v.shape[0], ke, ko,
+          int(normalize))
+    return out
+
+
+def vec_normalize(v, out):
+    _call("csbsr_vec_normalize", _f32(v), _f32(out), v.shape[0], v.shape[1])
+    return out
+
+
+def broadcast_vec(v, y):
+    _call("csbsr_broadcast_vec", _f32(v), y.ptr(), y.n, y.h * y.w, v.shape[1], y.pitch, y.coff, y.c)
+    return y
+
+
+def blur_per_sample(x, kvec, lr, err, ksize=21, stride=4):
+    n, c, h, w = x.shape
+    _call("csbsr_blur_per_sample", _f32(x), _f32(kvec), _f32(lr) if lr is not None else None, _f32(err), n, c, h, w,
+          ksize, stride)
+    return err
+
+
+def bicubic_upsample(x, y, factor):
+    n, c, h, w = x.shape
+    assert y.shape == (n, c, h * factor, w * factor)
+    _call("csbsr_bicubic_upsample", _f32(x), _f32(y), n * c, h, w, factor)
+    return y
+
+
+def clip_instnorm_stats(x, mean, rstd, do_clip=True, eps=1e-5):
+    n, c, h, w = x.shape
+    ws = torch.empty(_lib.lib().csbsr_instnorm_workspace_bytes(n * c) // 8, dtype=torch.float64, device=x.device)
+    _call("csbsr_clip_instnorm_stats", _f32(x), _f32(mean), _f32(rstd), ws.data_ptr(), n * c, h * w, int(do_clip),
+          C.c_float(eps))
+    return mean, rstd
+
+
+def maxpool3s2(x, y):
+    _call("csbsr_maxpool3s2_nhwc", x.ptr(), y.ptr(), x.n, x.h, x.w, x.c, x.pitch, x.coff, y.pitch, y.coff)
+    return y
+
+
+def adaptive_avgpool(x, y, s):
+    _call("csbsr_adaptive_avgpool_nhwc", x.ptr(), y.ptr(), x.n, x.h, x.w, s, x.c, x.pitch, x.coff, y.pitch, y.coff)
+    return y
+
+
+def bilinear(x, y, align_corners=False):
+    assert x.c == y.c
+    _call("csbsr_bilinear_nhwc", x.ptr(), y.ptr(), x.n, x.h, x.w, y.h, y.w, x.c, x.pitch, x.coff, y.pitch, y.coff,
+          int(align_corners))
+    return y
+
+
+def bilinear_f32(x, y, align_corners=False):
+    n, c, h, w = x.shape
+    _call("csbsr_bilinear_f32", _f32(x), _f32(y), n * c, h, w, y.shape[2], y.shape[3], int(align_corners))
     return y

@@ -160,6 +160,8 @@ def synth_state_dict(shapes, seed=1121, prefix=""):
         elif len(shape) == 4:
             fan_in = shape[1] * shape[2] * shape[3]
             t = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
+            if shape[0] == 1:                                # 1-channel heads: widen the logit range
+                t = t * 8.0
         elif leaf == "running_var":
             t = 0.5 + torch.rand(shape, generator=g)
         elif leaf == "running_mean":
@@ -167,7 +169,7 @@ def synth_state_dict(shapes, seed=1121, prefix=""):
         elif leaf == "weight" and shape == (1,):            # PReLU slope
             t = 0.01 + 0.24 * torch.rand(shape, generator=g)
         elif leaf == "weight":                               # BatchNorm gamma
-            t = 0.5 + torch.rand(shape, generator=g)
+            t = 0.3 + 0.5 * torch.rand(shape, generator=g)   # keeps the residual stack's activations O(1)
         elif leaf == "bias":
             t = 0.05 * torch.randn(shape, generator=g)
         else:

@@ -24,7 +24,7 @@ extern "C" {
 /* activation codes of the fused conv epilogue */
 enum { CSBSR_ACT_NONE = 0, CSBSR_ACT_RELU = 1, CSBSR_ACT_LEAKY = 2, CSBSR_ACT_SIGMOID = 3 };
 /* output modes of the fused conv epilogue */
-enum { CSBSR_OUT_BF16_NHWC = 0, CSBSR_OUT_F32_NCHW = 1 };
+enum { CSBSR_OUT_BF16_NHWC = 0, CSBSR_OUT_F32_NCHW = 1, CSBSR_OUT_F32_NHWC = 2 };
 
 const char* csbsr_last_error(void);
 int csbsr_version(void);
@@ -80,6 +80,54 @@ typedef struct csbsr_conv_desc {
 } csbsr_conv_desc;
 
 int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HBM-bound support kernels (csrc/support.cu).  NHWC tensors are bf16 with `*_pitch` channels per
+ * pixel and a channel window starting at `*_coff`; planar tensors are fp32 NCHW.
+ * ------------------------------------------------------------------------------------------- */
+/* boundary layout change: fp32 NCHW (reference tensors) -> bf16 NHWC window; channels [c, cwrite) are zeroed */
+int csbsr_nchw_f32_to_nhwc_bf16(const float* x, void* y, int n, int c, int h, int w, int y_pitch, int y_coff,
+                                int cwrite, void* stream);
+/* im2col of a few-channel fp32 image: y[n,oh,ow,(r*S+s)*c+ci] = f(x[n,ci,oh*stride+r-pad,ow*stride+s-pad]);
+ * f optionally clamps to [0,1] and instance-normalises (MetaSRModel.clip_sr / norm_sr,
+ * model/modeling/build_model.py:135-146).  Feeds the first conv of VGG feat (kbpn.py:42-44), fe_SR.0
+ * (kbpn.py:528), KBlock.up_conv1 (kbpn.py:375) and ResNet conv1 (extractors.py:115). */
+int csbsr_patchify(const float* x, void* y, int n, int c, int h, int w, int oh, int ow, int r, int s, int stride,
+                   int pad, int y_pitch, int cwrite, const float* mean, const float* rstd, int clamp01, void* stream);
+/* nn.AdaptiveAvgPool2d(1) (kbpn.py:324,391,565,572): out[n][c] = mean over h*w, fp32 */
+int csbsr_gap_nhwc(const void* x, float* out, int n, int hw, int pitch, int coff, int c, void* stream);
+/* out[b] = norm((pre ? pre[b] : 0) + bicubic_{ke x ke -> ko x ko}(v[b])), norm = divide by the sum when
+ * `normalize` (predictor_withGAP.upscale_and_reshape kbpn.py:335-341; KernelPredictorLikeIKC.forward :574-578
+ * followed by KBlock's renormalisation :391-392) */
+int csbsr_kernel_update(const float* v, const float* pre, float* out, int b, int ke, int ko, int normalize,
+                        void* stream);
+/* out[b] = v[b] / sum(v[b]) (JointModel.forward, build_model.py:491-494) */
+int csbsr_vec_normalize(const float* v, float* out, int b, int len, void* stream);
+/* spatially constant conditioning: y[n, :, :, coff + i] = v[n][i] (i < len), zero up to cwrite */
+int csbsr_broadcast_vec(const float* v, void* y, int n, int hw, int len, int y_pitch, int y_coff, int cwrite,
+                        void* stream);
+/* per-sample depthwise blur of a planar fp32 image with its own ksize x ksize kernel, zero padding
+ * (ksize-1)/2, given stride; err = blur - lr when lr != NULL (KBlock.forward kbpn.py:395-405; stride 1:
+ * Get_pseudo_lr model/utils/sr_loss_functions.py:90-94 and conv_kernel2d model/data/blur/blur.py:182-200) */
+int csbsr_blur_per_sample(const float* x, const float* kvec, const float* lr, float* err, int n, int c, int h, int w,
+                          int ksize, int stride, void* stream);
+/* nn.Upsample(scale_factor=f, mode='bicubic') on planar fp32 (kbpn.py:70,113) */
+int csbsr_bicubic_upsample(const float* x, float* y, int nc, int h, int w, int factor, void* stream);
+/* clip to [0,1] in place (optional) + InstanceNorm2d statistics: mean[nc], rstd[nc] = 1/sqrt(biased var + eps)
+ * (build_model.py:135-146) */
+size_t csbsr_instnorm_workspace_bytes(int nc);
+int csbsr_clip_instnorm_stats(float* x, float* mean, float* rstd, void* workspace, int nc, int hw, int do_clip,
+                              float eps, void* stream);
+/* nn.MaxPool2d(3, 2, 1) (extractors.py:119) */
+int csbsr_maxpool3s2_nhwc(const void* x, void* y, int n, int h, int w, int c, int x_pitch, int x_coff, int y_pitch,
+                          int y_coff, void* stream);
+/* nn.AdaptiveAvgPool2d((s, s)) (pspnet.py:32) */
+int csbsr_adaptive_avgpool_nhwc(const void* x, void* y, int n, int h, int w, int s, int c, int x_pitch, int x_coff,
+                                int y_pitch, int y_coff, void* stream);
+/* F.interpolate(mode='bilinear', align_corners=...) (pspnet.py:39,56) */
+int csbsr_bilinear_nhwc(const void* x, void* y, int n, int h, int w, int oh, int ow, int c, int x_pitch, int x_coff,
+                        int y_pitch, int y_coff, int align_corners, void* stream);
+int csbsr_bilinear_f32(const float* x, float* y, int nc, int h, int w, int oh, int ow, int align_corners, void* stream);
 
 #ifdef __cplusplus
 }

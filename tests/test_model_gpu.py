@@ -1,0 +1,86 @@
+"""End-to-end parity of the sm_100a JointModel against the fp32 oracle restatement (oracle/torch_ref.py,
+itself pinned to the unmodified reference by tests/golden) on the same synthetic weights and inputs.
+
+Tolerances (bf16 activations/weights, fp32 accumulation, ~100 conv layers deep):
+  SR image: max-abs <= 3e-2 on a [0,1] image and PSNR(ours, oracle) >= 40 dB;
+  segmentation probability: max-abs <= 5e-2, mean-abs <= 5e-3;  blur kernel: max-abs <= 2e-3."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _model_and_sd():
+    from csbsr_b200.config import cfg
+    from csbsr_b200.modeling.build_model import JointModel
+    from csbsr_b200.modeling import params as P
+    c = cfg.clone()
+    c.merge_from_file("config/config_csbsr_pspnet.yaml")
+    m = JointModel(c)
+    sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
+    sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+    m.load_state_dict(sd, strict=True)
+    return m, sd
+
+
+def _psnr(a, b):
+    mse = ((a - b) ** 2).mean().item()
+    return 10 * math.log10(1.0 / max(mse, 1e-20))
+
+
+def test_kbpn_stagewise_vs_oracle():
+    from oracle import torch_ref as T
+    m, sd = _model_and_sd()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, 24, 32, generator=g).cuda()
+    sr_eng, _ = m._ensure_engines(torch.device("cuda", 0))
+    sr, kvec = sr_eng.forward(x)
+    with torch.no_grad():
+        sr_ref, kvec_ref = T.kbpn_forward(sdc, x)
+    torch.cuda.synchronize()
+    print("sr max-abs", (sr - sr_ref).abs().max().item(), "psnr", _psnr(sr, sr_ref),
+          "kvec max-abs", (kvec - kvec_ref.view(2, -1)).abs().max().item())
+    assert (sr - sr_ref).abs().max().item() <= 3e-2
+    assert _psnr(sr, sr_ref) >= 40.0
+    assert (kvec - kvec_ref.view(2, -1)).abs().max().item() <= 2e-3
+
+
+def test_pspnet_vs_oracle():
+    from oracle import torch_ref as T
+    m, sd = _model_and_sd()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(6)
+    img = torch.randn(2, 3, 96, 128, generator=g).cuda()
+    _, ss_eng = m._ensure_engines(torch.device("cuda", 0))
+    seg, aux = ss_eng.forward(img)
+    with torch.no_grad():
+        seg_ref, aux_ref = T.pspnet_forward(sdc, img)
+    torch.cuda.synchronize()
+    print("seg max-abs", (seg - seg_ref).abs().max().item(), "aux max-abs", (aux - aux_ref).abs().max().item())
+    assert (seg - seg_ref).abs().max().item() <= 5e-2
+    assert (aux - aux_ref).abs().max().item() <= 5e-2
+    assert (seg - seg_ref).abs().mean().item() <= 5e-3
+
+
+@pytest.mark.parametrize("b,h,w", [(3, 24, 32), (1, 40, 24)])
+def test_joint_model_vs_oracle(b, h, w):
+    from oracle import torch_ref as T
+    m, sd = _model_and_sd()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(b, 3, h, w, generator=g)
+    m.chunk = 2
+    sr, seg, kp, aux = m(x, torch.zeros(b, 1, 7, 7), return_aux=True)
+    with torch.no_grad():
+        sr_ref, seg_ref, kp_ref, aux_ref = T.joint_forward(sdc, x.cuda())
+    torch.cuda.synchronize()
+    assert sr.shape == (b, 3, 4 * h, 4 * w) and seg.shape == (b, 1, 4 * h, 4 * w) and kp.shape == (b, 1, 21, 21)
+    print("sr", (sr - sr_ref).abs().max().item(), _psnr(sr, sr_ref), "seg", (seg - seg_ref).abs().max().item(),
+          (seg - seg_ref).abs().mean().item(), "kp", (kp - kp_ref).abs().max().item())
+    assert (sr - sr_ref).abs().max().item() <= 3e-2 and _psnr(sr, sr_ref) >= 40.0
+    assert (seg - seg_ref).abs().max().item() <= 5e-2 and (seg - seg_ref).abs().mean().item() <= 5e-3
+    assert (kp - kp_ref).abs().max().item() <= 2e-3
+    assert sr.min().item() >= 0.0 and sr.max().item() <= 1.0
