@@ -50,6 +50,7 @@ class KBPNEngine:
         self.device = device
         self.ws = _Workspace(device)
         self.p = None
+        self.debug = None                 # set to a dict to capture per-stage intermediates (tests only)
 
     # ------------------------------------------------------------------ weight packing
     def load(self, sd, prefix="sr_model."):
@@ -150,6 +151,9 @@ class KBPNEngine:
         z = K.conv(z, P["pred2"][0], ws.fmap("f64a", B, h, w, 64), act=ACT_LEAKY, slope=P["pred2"][1])
         v49 = K.gap(z, ws.f32("v49", B, kc), kc)
         kvec = K.kernel_update(v49, None, ws.f32("kvec_a", B, cond), self.ke, self.ko, True)
+        if self.debug is not None:
+            self.debug["init_f"] = init_f.to_nchw_f32()
+            self.debug["init_kernel"] = kvec.clone()
 
         concat_h = ws.fmap("concat_h", B, H, W, self.S * C)
         concat_l = ws.fmap("concat_l", B, h, w, max(1, self.S - 1) * C)
@@ -168,6 +172,9 @@ class KBPNEngine:
             pre = concat_h.window(0, (s + 1) * C)
             sr_t = K.conv(pre, st["kb.sr"], ws.f32("sr_t", B, 3, H, W))
             kvec = self._kernel_predictor(st, sr_t, kvec, B, H, W, s)
+            if self.debug is not None:
+                self.debug["sr_t%d" % s] = sr_t.clone()
+                self.debug["kvec%d" % s] = kvec.clone()
             err = K.blur_per_sample(sr_t, kvec, x, ws.f32("err", B, 3, h, w), self.ko, self.scale)
             ep = K.patchify(err, ws.fmap("xp", B, h, w, 64), 3, 3, 1, 1)
             K.conv(ep, st["kb.d1"][0], hs, act=ACT_LEAKY, slope=st["kb.d1"][1], r1=hs)      # h + e_h, in place
@@ -205,6 +212,8 @@ class KBPNEngine:
         a = K.conv(b, st["cat1"], ws.fmap("hr_a64", B, H, W, 64), act=ACT_LEAKY, slope=0.01)
         b = K.conv(a, st["cat2"], ws.fmap("hr_b64", B, H, W, 64))
         d49 = K.gap(b, ws.f32("v49", B, kc), kc)
+        if self.debug is not None:
+            self.debug["delta49_%d" % s] = d49.clone()
         out = ws.f32("kvec_b" if (s % 2 == 0) else "kvec_a", B, cond)
         return K.kernel_update(d49, kvec, out, self.ke, self.ko, True)
 

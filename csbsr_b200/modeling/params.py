@@ -162,6 +162,8 @@ def synth_state_dict(shapes, seed=1121, prefix=""):
             t = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
             if shape[0] == 1:                                # 1-channel heads: widen the logit range
                 t = t * 8.0
+            if name.endswith("fe_cat.2.layer.weight"):       # keep the kernel refinement small (as after training):
+                t = t * 0.01                                 # sum(pre + delta) stays near 1 -> well-conditioned /sum
         elif leaf == "running_var":
             t = 0.5 + torch.rand(shape, generator=g)
         elif leaf == "running_mean":
