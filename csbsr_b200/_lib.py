@@ -72,6 +72,12 @@ _SIGNATURES = {
     "csbsr_adaptive_avgpool_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
     "csbsr_bilinear_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 11 + [C.c_void_p]),
     "csbsr_bilinear_f32": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_blur_kernel_synth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "csbsr_resize_bicubic_aa": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_degrade": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_void_p]),
+    "csbsr_metrics_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "csbsr_seg_metrics": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_double, C.c_void_p,
+                                                                                         C.c_size_t, C.c_void_p]),
 }
 
 

@@ -1,0 +1,521 @@
+// AIU (IoU swept over 99 thresholds) and the Hausdorff / mean-surface-distance sweep, bit-exact with the
+// reference's numpy/scipy path:
+//   thresholds + binarisation   model/engine/inference.py:49-53,111
+//   IoU counts                  model/utils/estimate_metrics.py:72-84
+//   calc_distance_metrics       model/engine/inference.py:293-336
+//   compute_surface_distances   model/utils/metrics/surface_distance/metrics/surface_distance.py:136-288
+//   robust Hausdorff / ASD      same file :291-359 ; contour-length table lookup_tables.py:330-400
+//
+// Everything up to the final quantile is integer work on the (H+1)x(W+1) grid of pixel corners:
+//   q[y,x]   = #{i : p[y,x] > t_i}  (uint8): the prediction at threshold i is (q >= i), so a corner is a
+//              prediction-border corner for exactly the thresholds in (qlo, qhi] of its 2x2 pixel block;
+//   exact squared Euclidean distance to the nearest border corner = column scan + exact row search;
+//   keys (d2 << 2 | length-code) are sorted per (image, threshold, direction) with a shared-memory
+//   bitonic sort, then ONE thread replays numpy's floating-point order of operations (sequential
+//   cumsum, pairwise sum with 8 accumulators / blocks of 128, fp64 sqrt) so the percentile index and
+//   the value are identical to the reference's, bit for bit.
+#include <math_constants.h>
+#include "common.cuh"
+#include "../../include/csbsr_b200.h"
+
+namespace csbsr {
+
+static constexpr int kNumThr = 99;
+static constexpr unsigned short kInf16 = 0xFFFFu;
+static constexpr unsigned int kInfD2 = 0x3FFFFFFFu;       // "no border anywhere" marker (fits the key's 30 bits)
+
+// ------------------------------------------------------------------ quantise + AIU histogram
+// thr[i] = float32(i * 0.01) for i = 1..99, exactly what torch.Tensor([i*0.01 ...]) holds.
+__global__ void quantize_hist_kernel(const float* __restrict__ prob, const float* __restrict__ mask,
+                                     const float* __restrict__ thr, unsigned char* __restrict__ q,
+                                     unsigned char* __restrict__ gt, int* __restrict__ hist, int HW) {
+    // grid: (slices, B).  hist[b][2][100]: [0] = target false, [1] = target true (mask > 0.5)
+    __shared__ int sh[2][100];
+    __shared__ float sthr[kNumThr];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < 200; i += blockDim.x) (&sh[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < kNumThr; i += blockDim.x) sthr[i] = thr[i];
+    __syncthreads();
+    const float* pp = prob + static_cast<size_t>(b) * HW;
+    const float* mp = mask + static_cast<size_t>(b) * HW;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const float p = pp[i];
+        // count thresholds strictly below p: thresholds are increasing -> binary search for the first t >= p
+        int lo = 0, hi = kNumThr;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (p > sthr[mid]) lo = mid + 1; else hi = mid;
+        }
+        const float m = mp[i];
+        const int t_iou = m > 0.5f ? 1 : 0;              // IoU binarisation (estimate_metrics.py:79-80)
+        const int t_hd = m != 0.f ? 1 : 0;               // astype(bool) (inference.py:305)
+        q[static_cast<size_t>(b) * HW + i] = static_cast<unsigned char>(lo);
+        gt[static_cast<size_t>(b) * HW + i] = static_cast<unsigned char>(t_iou | (t_hd << 1));
+        atomicAdd(&sh[t_iou][lo], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 200; i += blockDim.x) {
+        const int v = (&sh[0][0])[i];
+        if (v) atomicAdd(&hist[b * 200 + i], v);
+    }
+}
+
+// I[b][i-1] = #(pred_i & tgt), U[b][i-1] = #(pred_i | tgt), pred_i = (q >= i)
+__global__ void aiu_counts_kernel(const int* __restrict__ hist, long long* __restrict__ inter,
+                                  long long* __restrict__ uni) {
+    const int b = blockIdx.x;
+    const int i = threadIdx.x + 1;
+    if (i > kNumThr) return;
+    const int* h0 = hist + b * 200;
+    const int* h1 = h0 + 100;
+    long long I = 0, P = 0, T = 0;
+    for (int k = 0; k < 100; ++k) {
+        T += h1[k];
+        if (k >= i) {
+            I += h1[k];
+            P += h0[k] + h1[k];
+        }
+    }
+    inter[b * kNumThr + i - 1] = I;
+    uni[b * kNumThr + i - 1] = P + T - I;
+}
+
+// ------------------------------------------------------------------ corner grid
+__device__ __forceinline__ int pix(const unsigned char* a, int y, int x, int H, int W) {
+    return (y >= 0 && y < H && x >= 0 && x < W) ? a[y * W + x] : 0;
+}
+
+// per corner: qlo/qhi of the 2x2 block (out-of-image pixels count as q = 0) and the gt neighbour code
+// code = 8*in[y-1,x-1] + 4*in[y-1,x] + 2*in[y,x-1] + in[y,x]   (scipy correlate with [[8,4],[2,1]], zero padded)
+__global__ void corner_kernel(const unsigned char* __restrict__ q, const unsigned char* __restrict__ gt,
+                              unsigned char* __restrict__ qlo, unsigned char* __restrict__ qhi,
+                              unsigned char* __restrict__ cg, int H, int W) {
+    const int Hc = H + 1, Wc = W + 1;
+    const int b = blockIdx.y;
+    const unsigned char* qb = q + static_cast<size_t>(b) * H * W;
+    const unsigned char* gb = gt + static_cast<size_t>(b) * H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Hc * Wc; i += gridDim.x * blockDim.x) {
+        const int y = i / Wc, x = i % Wc;
+        const int a = pix(qb, y - 1, x - 1, H, W), bb = pix(qb, y - 1, x, H, W), c = pix(qb, y, x - 1, H, W),
+                  d = pix(qb, y, x, H, W);
+        const size_t o = static_cast<size_t>(b) * Hc * Wc + i;
+        qlo[o] = static_cast<unsigned char>(min(min(a, bb), min(c, d)));
+        qhi[o] = static_cast<unsigned char>(max(max(a, bb), max(c, d)));
+        const int ga = (pix(gb, y - 1, x - 1, H, W) >> 1) & 1, gbb = (pix(gb, y - 1, x, H, W) >> 1) & 1,
+                  gc = (pix(gb, y, x - 1, H, W) >> 1) & 1, gd = (pix(gb, y, x, H, W) >> 1) & 1;
+        cg[o] = static_cast<unsigned char>(8 * ga + 4 * gbb + 2 * gc + gd);
+    }
+}
+
+// column pass of the exact EDT: g[y][x] = vertical distance to the nearest border corner in column x.
+// MODE 0: gt borders (code not in {0,15}); MODE 1: prediction borders at threshold t = blockIdx.y % 99 + 1.
+template <int MODE>
+__global__ void column_scan_kernel(const unsigned char* __restrict__ cg, const unsigned char* __restrict__ qlo,
+                                   const unsigned char* __restrict__ qhi, unsigned short* __restrict__ g, int Hc,
+                                   int Wc) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= Wc) return;
+    int b, t = 0;
+    if (MODE == 0) {
+        b = blockIdx.y;
+    } else {
+        b = blockIdx.y / kNumThr;
+        t = blockIdx.y % kNumThr + 1;
+    }
+    const size_t cbase = static_cast<size_t>(b) * Hc * Wc;
+    unsigned short* gp = g + static_cast<size_t>(blockIdx.y) * Hc * Wc;
+    int last = -1;
+    for (int y = 0; y < Hc; ++y) {
+        const size_t o = cbase + static_cast<size_t>(y) * Wc + x;
+        bool border;
+        if (MODE == 0) {
+            const int c = cg[o];
+            border = (c != 0 && c != 15);
+        } else {
+            border = (qlo[o] < t) && (t <= qhi[o]);
+        }
+        if (border) last = y;
+        gp[static_cast<size_t>(y) * Wc + x] = last < 0 ? kInf16 : static_cast<unsigned short>(y - last);
+    }
+    last = -1;
+    for (int y = Hc - 1; y >= 0; --y) {
+        const size_t go = static_cast<size_t>(y) * Wc + x;
+        const unsigned short cur = gp[go];
+        if (cur == 0) last = y;
+        else if (last >= 0) {
+            const int dd = last - y;
+            if (cur == kInf16 || dd < cur) gp[go] = static_cast<unsigned short>(dd);
+        }
+    }
+}
+
+// exact row search: min over x' of (x-x')^2 + g[y][x']^2, expanding from x with early exit
+__device__ __forceinline__ unsigned int row_search(const unsigned short* __restrict__ grow, int x, int Wc) {
+    unsigned int best = kInfD2;
+    const int maxd = max(x, Wc - 1 - x);
+    for (int d = 0; d <= maxd; ++d) {
+        const unsigned int dd = static_cast<unsigned int>(d) * d;
+        if (dd >= best) break;
+        if (x - d >= 0) {
+            const unsigned int gv = grow[x - d];
+            if (gv != kInf16) best = min(best, dd + gv * gv);
+        }
+        if (d > 0 && x + d < Wc) {
+            const unsigned int gv = grow[x + d];
+            if (gv != kInf16) best = min(best, dd + gv * gv);
+        }
+    }
+    return best;
+}
+
+// full squared-distance map to the gt borders (needed at every prediction-border corner)
+__global__ void gt_edt_kernel(const unsigned short* __restrict__ gcol, unsigned int* __restrict__ d2g, int Hc, int Wc) {
+    const int b = blockIdx.y;
+    const unsigned short* gb = gcol + static_cast<size_t>(b) * Hc * Wc;
+    unsigned int* ob = d2g + static_cast<size_t>(b) * Hc * Wc;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Hc * Wc; i += gridDim.x * blockDim.x) {
+        const int y = i / Wc, x = i % Wc;
+        ob[i] = row_search(gb + static_cast<size_t>(y) * Wc, x, Wc);
+    }
+}
+
+// neighbour code -> contour-length class: 0 = none, 1 = diag (0.5*sqrt2), 2 = 1.0, 3 = 2*diag (lookup_tables.py:351-398)
+__device__ __forceinline__ int len_class(int code) {
+    //            0  1  2  3  4  5  6  7  8  9 10 11 12 13 14 15
+    const unsigned int tbl = (0u) | (1u << 2) | (1u << 4) | (2u << 6) | (1u << 8) | (2u << 10) | (3u << 12) | (1u << 14) |
+                             (1u << 16) | (3u << 18) | (2u << 20) | (1u << 22) | (2u << 24) | (1u << 26) | (1u << 28) |
+                             (0u << 30);
+    return (tbl >> (2 * code)) & 3;
+}
+
+// compact list of gt border corners per image (order is irrelevant: keys are sorted later)
+__global__ void gt_list_kernel(const unsigned char* __restrict__ cg, int* __restrict__ list, int* __restrict__ count,
+                               int NC) {
+    const int b = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NC; i += gridDim.x * blockDim.x) {
+        const int c = cg[static_cast<size_t>(b) * NC + i];
+        if (c != 0 && c != 15) {
+            const int slot = atomicAdd(&count[b], 1);
+            list[static_cast<size_t>(b) * NC + slot] = i;
+        }
+    }
+}
+
+// keys of distances_gt_to_pred: for every gt border corner and threshold, d2 to the nearest prediction border
+__global__ void g2p_keys_kernel(const int* __restrict__ list, const int* __restrict__ count,
+                                const unsigned char* __restrict__ cg, const unsigned short* __restrict__ gcol_t,
+                                unsigned int* __restrict__ keys, int Hc, int Wc, int cap) {
+    const int bt = blockIdx.y;                 // b * 99 + (t-1)
+    const int b = bt / kNumThr;
+    const int NC = Hc * Wc;
+    const int n = count[b];
+    const unsigned short* g = gcol_t + static_cast<size_t>(bt) * NC;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int i = list[static_cast<size_t>(b) * NC + k];
+        const int y = i / Wc, x = i % Wc;
+        const unsigned int d2 = row_search(g + static_cast<size_t>(y) * Wc, x, Wc);
+        keys[static_cast<size_t>(bt) * cap + k] = (d2 << 2) | len_class(cg[static_cast<size_t>(b) * NC + i]);
+    }
+}
+
+// keys of distances_pred_to_gt: every corner contributes to the thresholds in (qlo, qhi]
+__global__ void p2g_keys_kernel(const unsigned char* __restrict__ q, const unsigned char* __restrict__ qlo,
+                                const unsigned char* __restrict__ qhi, const unsigned int* __restrict__ d2g,
+                                unsigned int* __restrict__ keys, int* __restrict__ count, int H, int W, int cap) {
+    const int Hc = H + 1, Wc = W + 1, NC = Hc * Wc;
+    const int b = blockIdx.y;
+    const unsigned char* qb = q + static_cast<size_t>(b) * H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NC; i += gridDim.x * blockDim.x) {
+        const size_t o = static_cast<size_t>(b) * NC + i;
+        const int lo = qlo[o], hi = qhi[o];
+        if (lo == hi) continue;
+        const int y = i / Wc, x = i % Wc;
+        const int a = pix(qb, y - 1, x - 1, H, W), bb = pix(qb, y - 1, x, H, W), c = pix(qb, y, x - 1, H, W),
+                  d = pix(qb, y, x, H, W);
+        const unsigned int dd = d2g[o];
+        for (int t = lo + 1; t <= hi; ++t) {
+            const int code = ((a >= t) << 3) | ((bb >= t) << 2) | ((c >= t) << 1) | (d >= t);
+            const int bt = b * kNumThr + t - 1;
+            const int slot = atomicAdd(&count[bt], 1);
+            keys[static_cast<size_t>(bt) * cap + slot] = (dd << 2) | len_class(code);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ numpy-order floating point replay
+__device__ __forceinline__ double len_value(int cls) {
+    // 0.5 * math.sqrt(1**2 + 1**2), 1, 2 * diag  (lookup_tables.py:351-398 with spacing (1, 1))
+    const double diag = 0.5 * 1.4142135623730951;
+    return cls == 1 ? diag : (cls == 2 ? 1.0 : (cls == 3 ? 2.0 * diag : 0.0));
+}
+__device__ __forceinline__ double key_dist(unsigned int key) {
+    const unsigned int d2 = key >> 2;
+    return d2 == kInfD2 ? CUDART_INF : sqrt(static_cast<double>(d2));    // IEEE sqrt == np.sqrt on exact integers
+}
+template <bool PROD>
+__device__ __forceinline__ double elem(const unsigned int* keys, int i) {
+    const unsigned int k = keys[i];
+    const double l = len_value(k & 3);
+    return PROD ? key_dist(k) * l : l;
+}
+// numpy pairwise_sum for n <= 128 (numpy/_core/src/umath/loops_utils.h.src): 8 interleaved accumulators
+template <bool PROD>
+__device__ double pairwise_leaf(const unsigned int* keys, int start, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res += elem<PROD>(keys, start + i);
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = elem<PROD>(keys, start + k);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] += elem<PROD>(keys, start + i + k);
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += elem<PROD>(keys, start + i);
+    return res;
+}
+// recursion of pairwise_sum for n > 128: n2 = n/2 rounded down to a multiple of 8
+template <bool PROD>
+__device__ double pairwise_rec(const unsigned int* keys, int start, int n) {
+    // explicit stack (depth <= 20) to avoid device recursion
+    int s_start[24], s_n[24], s_state[24];
+    double s_left[24];
+    int sp = 0;
+    s_start[0] = start; s_n[0] = n; s_state[0] = 0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        const int cs = s_start[sp], cn = s_n[sp];
+        if (cn <= 128) {
+            ret = pairwise_leaf<PROD>(keys, cs, cn);
+            --sp;
+            continue;
+        }
+        int n2 = cn / 2;
+        n2 -= n2 % 8;
+        if (s_state[sp] == 0) {
+            s_state[sp] = 1;
+            ++sp;
+            s_start[sp] = cs; s_n[sp] = n2; s_state[sp] = 0;
+        } else if (s_state[sp] == 1) {
+            s_left[sp] = ret;
+            s_state[sp] = 2;
+            ++sp;
+            s_start[sp] = cs + n2; s_n[sp] = cn - n2; s_state[sp] = 0;
+        } else {
+            ret = s_left[sp] + ret;
+            --sp;
+        }
+    }
+    return ret;
+}
+
+// After sorting: out[0] = percentile distance (compute_robust_hausdorff :344-347), out[1] = average distance (:315-319)
+__device__ void replay_list(const unsigned int* keys, int n, double pct, double* out) {
+    const double total = pairwise_rec<false>(keys, 0, n);
+    const double wsum = pairwise_rec<true>(keys, 0, n);
+    double c = 0.0;
+    int idx = n;
+    for (int i = 0; i < n; ++i) {                      // np.cumsum: sequential; np.searchsorted(side='left')
+        c += len_value(keys[i] & 3);
+        if (c / total >= pct) { idx = i; break; }
+    }
+    if (idx > n - 1) idx = n - 1;
+    out[0] = key_dist(keys[idx]);
+    out[1] = wsum / total;
+}
+
+// bitonic sort of one list in shared memory + replay. CAP = power of two capacity; lists longer than CAP or
+// not longer than MINN are handled by another instantiation (the block exits at once).
+template <int CAP, int MINN>
+__global__ void sort_replay_kernel(const unsigned int* __restrict__ keys_g2p, const unsigned int* __restrict__ keys_p2g,
+                                   const int* __restrict__ count_gt, const int* __restrict__ count_pred, int cap,
+                                   double pct, double* __restrict__ res) {
+    extern __shared__ unsigned int sk[];
+    const int bt = blockIdx.x >> 1;
+    const int dir = blockIdx.x & 1;                    // 0: gt->pred, 1: pred->gt
+    const int b = bt / kNumThr;
+    const int ng = count_gt[b], np_ = count_pred[bt];
+    if (ng == 0 || np_ == 0) return;                   // empty cases are resolved by finalize_kernel
+    const int n = dir == 0 ? ng : np_;
+    if (n > CAP || n <= MINN) return;
+    const unsigned int* src = (dir == 0 ? keys_g2p : keys_p2g) + static_cast<size_t>(bt) * cap;
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) sk[i] = i < n ? src[i] : 0xFFFFFFFFu;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned int a = sk[i], c = sk[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > c) == up) { sk[i] = c; sk[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) replay_list(sk, n, pct, res + (static_cast<size_t>(bt) * 2 + dir) * 2);
+}
+
+// lists that do not fit in shared memory: bitonic sort in place in global memory by one block (rare, slow path)
+__global__ void sort_replay_global_kernel(unsigned int* __restrict__ keys_g2p, unsigned int* __restrict__ keys_p2g,
+                                          const int* __restrict__ count_gt, const int* __restrict__ count_pred,
+                                          int cap, int cap_pow2, int minn, double pct, double* __restrict__ res) {
+    const int bt = blockIdx.x >> 1;
+    const int dir = blockIdx.x & 1;
+    const int b = bt / kNumThr;
+    const int ng = count_gt[b], np_ = count_pred[bt];
+    if (ng == 0 || np_ == 0) return;
+    const int n = dir == 0 ? ng : np_;
+    if (n <= minn) return;
+    unsigned int* sk = (dir == 0 ? keys_g2p : keys_p2g) + static_cast<size_t>(bt) * cap;
+    int m = 1;
+    while (m < n) m <<= 1;
+    if (m > cap_pow2) m = cap_pow2;                    // cap is allocated as a power of two >= NC
+    for (int i = n + threadIdx.x; i < m; i += blockDim.x) sk[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned int a = sk[i], c = sk[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > c) == up) { sk[i] = c; sk[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) replay_list(sk, n, pct, res + (static_cast<size_t>(bt) * 2 + dir) * 2);
+}
+
+// combine the two directions and resolve the empty-mask branches (inference.py:315-334)
+__global__ void finalize_kernel(const int* __restrict__ count_gt, const int* __restrict__ count_pred,
+                                const double* __restrict__ res, double* __restrict__ hd, double* __restrict__ msd,
+                                int total, double max_img_len) {
+    const int bt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bt >= total) return;
+    const int b = bt / kNumThr;
+    const int ng = count_gt[b], np_ = count_pred[bt];
+    if (ng == 0 && np_ == 0) {
+        hd[bt] = 0.0;
+        msd[bt] = 0.0;
+    } else if (ng == 0 || np_ == 0) {
+        hd[bt] = max_img_len;
+        msd[bt] = max_img_len;
+    } else {
+        const double* r = res + static_cast<size_t>(bt) * 4;
+        hd[bt] = fmax(r[0], r[2]);
+        msd[bt] = (r[1] + r[3]) / 2;
+    }
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int pow2_at_least(int v) { int m = 1; while (m < v) m <<= 1; return m; }
+
+struct MetricsWs {
+    unsigned char *q, *gt, *qlo, *qhi, *cg;
+    int *hist, *gt_list, *count_gt, *count_pred;
+    unsigned short *gcol_g, *gcol_t;
+    unsigned int *d2g, *keys_g2p, *keys_p2g;
+    double* res;
+    int cap;
+    size_t total;
+};
+
+static MetricsWs carve(void* base, int b, int h, int w, bool with_hd) {
+    MetricsWs m;
+    const size_t HW = static_cast<size_t>(h) * w, NC = static_cast<size_t>(h + 1) * (w + 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* p = base ? static_cast<char*>(base) + off : nullptr; off += align_up(bytes, 256); return p; };
+    m.q = static_cast<unsigned char*>(take(b * HW));
+    m.gt = static_cast<unsigned char*>(take(b * HW));
+    m.hist = static_cast<int*>(take(sizeof(int) * b * 200));
+    m.cap = pow2_at_least(static_cast<int>(NC));
+    if (with_hd) {
+        m.qlo = static_cast<unsigned char*>(take(b * NC));
+        m.qhi = static_cast<unsigned char*>(take(b * NC));
+        m.cg = static_cast<unsigned char*>(take(b * NC));
+        m.gt_list = static_cast<int*>(take(sizeof(int) * b * NC));
+        m.count_gt = static_cast<int*>(take(sizeof(int) * b));
+        m.count_pred = static_cast<int*>(take(sizeof(int) * b * kNumThr));
+        m.gcol_g = static_cast<unsigned short*>(take(sizeof(short) * b * NC));
+        m.d2g = static_cast<unsigned int*>(take(sizeof(int) * b * NC));
+        m.gcol_t = static_cast<unsigned short*>(take(sizeof(short) * b * kNumThr * NC));
+        m.keys_g2p = static_cast<unsigned int*>(take(sizeof(int) * static_cast<size_t>(b) * kNumThr * m.cap));
+        m.keys_p2g = static_cast<unsigned int*>(take(sizeof(int) * static_cast<size_t>(b) * kNumThr * m.cap));
+        m.res = static_cast<double*>(take(sizeof(double) * b * kNumThr * 4));
+    }
+    m.total = off;
+    return m;
+}
+
+}  // namespace csbsr
+
+using namespace csbsr;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" size_t csbsr_metrics_workspace_bytes(int b, int h, int w, int with_hd) {
+    return carve(nullptr, b, h, w, with_hd != 0).total;
+}
+
+extern "C" int csbsr_seg_metrics(const float* prob, const float* mask, const float* thresholds, int b, int h, int w,
+                                 long long* inter, long long* uni, double* hd, double* msd, double percent,
+                                 void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = STREAM(stream_);
+    CSBSR_REQUIRE(prob && mask && thresholds && inter && uni && workspace && b > 0 && h > 0 && w > 0,
+                  "seg_metrics: bad arguments");
+    CSBSR_REQUIRE((hd == nullptr) == (msd == nullptr), "seg_metrics: hd and msd must come together");
+    CSBSR_REQUIRE(h <= 16384 && w <= 16384, "seg_metrics: image too large (squared distances are packed in 30 bits)");
+    const bool with_hd = hd != nullptr;
+    MetricsWs m = carve(workspace, b, h, w, with_hd);
+    CSBSR_REQUIRE(workspace_bytes >= m.total, "seg_metrics: workspace too small (%zu < %zu)", workspace_bytes, m.total);
+    const int HW = h * w, Hc = h + 1, Wc = w + 1, NC = Hc * Wc;
+    CSBSR_CHECK_CUDA(cudaMemsetAsync(m.hist, 0, sizeof(int) * b * 200, stream));
+    {
+        int slices = (HW + 256 * 8 - 1) / (256 * 8);
+        dim3 grid(slices, b);
+        quantize_hist_kernel<<<grid, 256, 0, stream>>>(prob, mask, thresholds, m.q, m.gt, m.hist, HW);
+        aiu_counts_kernel<<<b, 128, 0, stream>>>(m.hist, inter, uni);
+    }
+    if (with_hd) {
+        CSBSR_CHECK_CUDA(cudaMemsetAsync(m.count_gt, 0, sizeof(int) * b, stream));
+        CSBSR_CHECK_CUDA(cudaMemsetAsync(m.count_pred, 0, sizeof(int) * b * kNumThr, stream));
+        const int cslices = (NC + 255) / 256;
+        corner_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.q, m.gt, m.qlo, m.qhi, m.cg, h, w);
+        column_scan_kernel<0><<<dim3((Wc + 127) / 128, b), 128, 0, stream>>>(m.cg, m.qlo, m.qhi, m.gcol_g, Hc, Wc);
+        gt_edt_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.gcol_g, m.d2g, Hc, Wc);
+        gt_list_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.cg, m.gt_list, m.count_gt, NC);
+        column_scan_kernel<1><<<dim3((Wc + 127) / 128, b * kNumThr), 128, 0, stream>>>(m.cg, m.qlo, m.qhi, m.gcol_t,
+                                                                                      Hc, Wc);
+        g2p_keys_kernel<<<dim3(64, b * kNumThr), 256, 0, stream>>>(m.gt_list, m.count_gt, m.cg, m.gcol_t, m.keys_g2p,
+                                                                  Hc, Wc, m.cap);
+        p2g_keys_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.q, m.qlo, m.qhi, m.d2g, m.keys_p2g, m.count_pred, h, w,
+                                                             m.cap);
+        const double pct = percent / 100.0;
+        const int lists = b * kNumThr * 2;
+        static bool attr_set = false;
+        if (!attr_set) {
+            CSBSR_CHECK_CUDA(cudaFuncSetAttribute(sort_replay_kernel<32768, 4096>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+            attr_set = true;
+        }
+        sort_replay_kernel<4096, 0><<<lists, 256, 4096 * 4, stream>>>(m.keys_g2p, m.keys_p2g, m.count_gt, m.count_pred,
+                                                                      m.cap, pct, m.res);
+        sort_replay_kernel<32768, 4096><<<lists, 1024, 32768 * 4, stream>>>(m.keys_g2p, m.keys_p2g, m.count_gt,
+                                                                            m.count_pred, m.cap, pct, m.res);
+        sort_replay_global_kernel<<<lists, 1024, 0, stream>>>(m.keys_g2p, m.keys_p2g, m.count_gt, m.count_pred, m.cap,
+                                                              m.cap, 32768, pct, m.res);
+        finalize_kernel<<<(b * kNumThr + 127) / 128, 128, 0, stream>>>(m.count_gt, m.count_pred, m.res, hd, msd,
+                                                                      b * kNumThr, static_cast<double>(w));
+    }
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

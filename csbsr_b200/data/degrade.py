@@ -1,0 +1,106 @@
+"""On-the-fly degradation with the reference's function names (model/data/blur/blur.py, transforms.py) running
+on the device through the C-ABI: set_blur / GaussianBlur.make -> csbsr_blur_kernel_synth, conv_kernel2d ->
+csbsr_blur_per_sample, FactorResize -> csbsr_resize_bicubic_aa, and the batched `degrade` used by the eval loop.
+
+Random draws stay on the host exactly as in the reference (theta from torch.rand, sigmas from np.random.rand:
+blur.py:129,170-179), so seeding torch / numpy reproduces the reference's kernels."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def draw_gaussian_params(n=1, range_theta=(0, 180), range_sigma=(0.2, 4), range_sigma2=None, isotropic=False):
+    """The reference's per-sample draws: returns float64 [n,3] = (theta [rad], sigma_x, sigma_y)."""
+    out = np.empty((n, 3), dtype=np.float64)
+    for i in range(n):
+        theta = ((range_theta[1] - range_theta[0]) * torch.rand(1).item() + range_theta[0]) * np.pi / 180
+        a, b = range_sigma
+        sx = (b - a) * np.random.rand() + a
+        if range_sigma2 is not None:
+            a, b = range_sigma2
+        sy = (b - a) * np.random.rand() + a
+        out[i] = (theta, sx, sx if isotropic else sy)
+    return out
+
+
+def gaussian_kernels(params, size=21):
+    """params float64 [n,3] -> fp32 [n,size,size] on the device (GaussianBlur.make, blur.py:128-168)."""
+    p = torch.as_tensor(np.asarray(params, dtype=np.float64)).to(_dev()).contiguous()
+    out = torch.empty((p.shape[0], size, size), dtype=torch.float32, device=p.device)
+    _lib.check(_lib.lib().csbsr_blur_kernel_synth(p.data_ptr(), out.data_ptr(), p.shape[0], size, _lib.stream_ptr()),
+               "csbsr_blur_kernel_synth")
+    return out
+
+
+def set_blur(size=21, device="cuda", mode="gaus", range_gaus_deterioration_ratio=(0.2, 4),
+             range_gaus_deterioration_ratio2=None, isotropic=True, **_unused):
+    """blur.py:207-238 for mode='gaus' (the only mode the CSBSR configs use, crack_dataset.py:52)."""
+    if mode != "gaus":
+        raise NotImplementedError("set_blur(mode=%r): only 'gaus' is on the CSBSR path" % (mode,))
+    prm = draw_gaussian_params(1, range_sigma=range_gaus_deterioration_ratio,
+                               range_sigma2=range_gaus_deterioration_ratio2, isotropic=isotropic)
+    return gaussian_kernels(prm, size)[0]
+
+
+def conv_kernel2d(img, kernel, device="cuda", add_minibatch=True):
+    """blur.py:182-200: same kernel for every channel, zero padding, stride 1. img [C,H,W] (or [B,C,H,W] with
+    kernel [B,k,k])."""
+    x = img.to(device=_dev(), dtype=torch.float32)
+    single = x.dim() == 3
+    if single:
+        x = x.unsqueeze(0)
+    x = x.contiguous()
+    k = kernel.to(device=_dev(), dtype=torch.float32).reshape(-1, kernel.shape[-2], kernel.shape[-1]).contiguous()
+    if k.shape[0] == 1 and x.shape[0] > 1:
+        k = k.expand(x.shape[0], -1, -1).contiguous()
+    out = torch.empty_like(x)
+    n, c, h, w = x.shape
+    _lib.check(_lib.lib().csbsr_blur_per_sample(x.data_ptr(), k.data_ptr(), None, out.data_ptr(), n, c, h, w,
+                                                k.shape[-1], 1, _lib.stream_ptr()), "csbsr_blur_per_sample")
+    return out[0] if single else out
+
+
+class FactorResize:
+    """transforms.py:505-531 with interpolation='bicubic' (antialiased, as torchvision >= 0.17 resizes tensors)."""
+
+    def __init__(self, factor, interpolation="bicubic"):
+        if interpolation != "bicubic":
+            raise NotImplementedError(interpolation)
+        self.factor = factor
+
+    def __call__(self, image, clamp01=False):
+        x = image.to(device=_dev(), dtype=torch.float32)
+        single = x.dim() == 3
+        if single:
+            x = x.unsqueeze(0)
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        oh, ow = int(h / self.factor), int(w / self.factor)
+        out = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().csbsr_resize_bicubic_aa(x.data_ptr(), out.data_ptr(), n * c, h, w, oh, ow, int(clamp01),
+                                                      _lib.stream_ptr()), "csbsr_resize_bicubic_aa")
+        return out[0] if single else out
+
+
+def degrade(hr, params, ksize=21, factor=4, clamp01=False, return_blurred=False):
+    """Batched CrackDataSet.__getitem__ degradation (crack_dataset.py:51-62): hr fp32 [B,3,H,W] + params float64
+    [B,3] -> (lr [B,3,H/f,W/f], kernels [B,k,k])."""
+    x = hr.to(device=_dev(), dtype=torch.float32).contiguous()
+    p = torch.as_tensor(np.asarray(params, dtype=np.float64)).to(x.device).contiguous()
+    b, c, h, w = x.shape
+    kernels = torch.empty((b, ksize, ksize), dtype=torch.float32, device=x.device)
+    blurred = torch.empty_like(x)
+    lr = torch.empty((b, c, h // factor, w // factor), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().csbsr_degrade(x.data_ptr(), p.data_ptr(), kernels.data_ptr(), blurred.data_ptr(),
+                                        lr.data_ptr(), b, c, h, w, ksize, factor, int(clamp01), _lib.stream_ptr()),
+               "csbsr_degrade")
+    if return_blurred:
+        return lr, kernels, blurred
+    return lr, kernels

@@ -1,0 +1,84 @@
+"""Evaluation metrics of the reference's inference loop (model/engine/inference.py:25-207) on the device.
+
+`seg_metrics` replaces, for one batch, the threshold sweep (:49-53,111), IoU (:119 ->
+model/utils/estimate_metrics.py:72-84) and calc_distance_metrics (:121 -> :293-336): it never materialises
+the (B,99,H,W) binarised tensor and returns integer IoU counts plus fp64 HD / MSD values that are
+bit-identical to the reference's.  The fp64 ratio/mean arithmetic on the tiny (B,99) results is the same
+numpy expression the reference uses (:171-173)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+NUM_THRESHOLDS = 99
+# torch.Tensor([i*0.01 for i in range(1,100)]) -> float32 (inference.py:49-51)
+THRESHOLDS = np.array([i * 0.01 for i in range(1, 100)], dtype=np.float64).astype(np.float32)
+HD_PERCENTILE = 50        # the shipped reference evaluates "HD95" with percentile = 50 (inference.py:302)
+
+_thr_cache = {}
+_ws_cache = {}
+
+
+def _thresholds(device):
+    t = _thr_cache.get(device)
+    if t is None:
+        t = torch.from_numpy(THRESHOLDS.copy()).to(device)
+        _thr_cache[device] = t
+    return t
+
+
+def seg_metrics(segment_preds, masks, with_hd=True, percent=HD_PERCENTILE, to_host=True):
+    """segment_preds, masks: fp32 [B,1,H,W] (any device; moved to the current CUDA device).
+    Returns dict(inter, union [B,99] int64; iou [B,99] float64; hd, msd [B,99] float64 or None)."""
+    L = _lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    p = segment_preds.to(device=dev, dtype=torch.float32).contiguous()
+    m = masks.to(device=dev, dtype=torch.float32).contiguous()
+    B, c, H, W = p.shape
+    assert c == 1 and m.shape == p.shape
+    inter = torch.empty((B, NUM_THRESHOLDS), dtype=torch.int64, device=dev)
+    union = torch.empty_like(inter)
+    hd = torch.empty((B, NUM_THRESHOLDS), dtype=torch.float64, device=dev) if with_hd else None
+    msd = torch.empty_like(hd) if with_hd else None
+    need = L.csbsr_metrics_workspace_bytes(B, H, W, int(with_hd))
+    key = (dev, B, H, W, bool(with_hd))
+    ws = _ws_cache.get(key)
+    if ws is None:
+        _ws_cache.clear()
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _ws_cache[key] = ws
+    rc = L.csbsr_seg_metrics(p.data_ptr(), m.data_ptr(), _thresholds(dev).data_ptr(), B, H, W, inter.data_ptr(),
+                             union.data_ptr(), hd.data_ptr() if with_hd else None, msd.data_ptr() if with_hd else None,
+                             C.c_double(float(percent)), ws.data_ptr(), need, _lib.stream_ptr())
+    _lib.check(rc, "csbsr_seg_metrics")
+    out = {"inter": inter, "union": union, "hd": hd, "msd": msd}
+    if to_host:
+        out = {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+        out["iou"] = (out["inter"] + 1e-5) / (out["union"] + 1e-5)      # estimate_metrics.py:75,84
+    return out
+
+
+class IoU:
+    """Same call convention as the reference's IoU for the swept case: __call__(prob, target) -> (B,99) ndarray."""
+
+    def __init__(self, th=0.5):
+        self.name = "IoU"
+        self.th = 0.5
+
+    def __call__(self, segment_preds, target):
+        return seg_metrics(segment_preds, target, with_hd=False)["iou"]
+
+
+def calc_distance_metrics(segment_preds, gts, num_hd_outliner=0, num_msd_outliner=0, percent=HD_PERCENTILE):
+    """Same return convention as the reference (inference.py:293-336): (hd[B,99], msd[B,99], n_hd_outliers,
+    n_msd_outliers); an "outlier" is a (image, threshold) pair where exactly one of gt / prediction is empty."""
+    r = seg_metrics(segment_preds, gts, with_hd=True, percent=percent)
+    g = gts.to(dtype=torch.float32)
+    tgt_iou = (g > 0.5).flatten(1).sum(1).cpu().numpy().astype(np.int64)[:, None]
+    gt_empty = (~(g != 0).flatten(1).any(1)).cpu().numpy()[:, None]
+    pred_empty = (r["union"] - tgt_iou + r["inter"]) == 0
+    one_empty = gt_empty ^ pred_empty
+    n = int(one_empty.sum())
+    return r["hd"], r["msd"], num_hd_outliner + n, num_msd_outliner + n

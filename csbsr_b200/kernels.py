@@ -12,6 +12,9 @@ from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, OUT_BF16_NHWC, OU
                    ConvDesc)
 
 
+PROFILE = None        # set to a list to collect (label, flops, start_event, end_event) per conv launch
+
+
 def round_up(v, m):
     return (v + m - 1) // m * m
 
@@ -212,8 +215,16 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
         assert r32.dtype == torch.float32 and r32.is_contiguous()
         d.r32 = r32.data_ptr()
     d.block_n = block_n
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = _lib.lib().csbsr_conv_igemm(C.byref(d), _lib.stream_ptr())
     _lib.check(rc, "csbsr_conv_igemm")
+    if PROFILE is not None:
+        e1.record()
+        flops = 2.0 * x.n * d.oh * d.ow * pc.nphases * pc.ntaps * pc.cin_pad * pc.cout_pad
+        PROFILE.append(("conv n%d %dx%d cin%d cout%d taps%dx%d s%d" % (x.n, d.oh, d.ow, pc.cin_pad, pc.cout_pad,
+                                                                        pc.nphases, pc.ntaps, pc.stride), flops, e0, e1))
     return y
 
 

@@ -129,6 +129,37 @@ int csbsr_bilinear_nhwc(const void* x, void* y, int n, int h, int w, int oh, int
                         int y_pitch, int y_coff, int align_corners, void* stream);
 int csbsr_bilinear_f32(const float* x, float* y, int nc, int h, int w, int oh, int ow, int align_corners, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Synthetic degradation (csrc/degrade.cu).
+ * ------------------------------------------------------------------------------------------- */
+/* GaussianBlur.make (model/data/blur/blur.py:128-168): params[b] = (theta [rad], sigma_x, sigma_y) fp64, the draws
+ * of :129 and get_deterioration :170-179 made by the caller; kernels[b] = ksize x ksize fp32, normalised in fp64 */
+int csbsr_blur_kernel_synth(const double* params, float* kernels, int b, int ksize, void* stream);
+/* torchvision Resize(BICUBIC) on tensors = antialiased bicubic, a = -0.5 (FactorResize.__call__,
+ * model/data/transforms/transforms.py:516-531); clamp01 as make_test_blur.py:62 */
+int csbsr_resize_bicubic_aa(const float* x, float* y, int nc, int h, int w, int oh, int ow, int clamp01, void* stream);
+/* CrackDataSet.__getitem__ degradation (model/data/crack_dataset.py:51-62): kernel synth -> conv_kernel2d
+ * (blur.py:182-200) -> FactorResize.  hr, blurred: fp32 [b,c,h,w]; lr: fp32 [b,c,h/factor,w/factor] */
+int csbsr_degrade(const float* hr, const double* params, float* kernels, float* blurred, float* lr, int b, int c,
+                  int h, int w, int ksize, int factor, int clamp01, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Segmentation metrics (csrc/metrics.cu): AIU threshold sweep and the Hausdorff / mean-surface-distance
+ * sweep, bit-exact with the reference.
+ *   prob, mask: fp32 [b,1,h,w]; thresholds: fp32 [99] = float32(i*0.01), i = 1..99
+ *   inter, uni: int64 [b,99]  -- IoU.__call__ counts (model/utils/estimate_metrics.py:72-84) for
+ *               pred_i = (prob - t_i > 0) (model/engine/inference.py:49-53,111) and target = mask > 0.5
+ *   hd, msd:    fp64 [b,99] or both NULL -- calc_distance_metrics (model/engine/inference.py:293-336) with
+ *               gt = mask.astype(bool), `percent` the robust-Hausdorff percentile (the reference ships 50,
+ *               inference.py:302); compute_surface_distances / compute_robust_hausdorff /
+ *               compute_average_surface_distance of surface_distance.py:136-359.
+ * ------------------------------------------------------------------------------------------- */
+size_t csbsr_metrics_workspace_bytes(int b, int h, int w, int with_hd);
+int csbsr_seg_metrics(const float* prob, const float* mask, const float* thresholds, int b, int h, int w,
+                      long long* inter, long long* uni, double* hd, double* msd, double percent, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,128 @@
+"""Generates the committed golden fixtures by running the UNMODIFIED reference (/root/reference) in-process.
+
+Run in the build container only:  python tests/golden/gen_golden.py
+Outputs (small .npz files next to this script):
+  metrics_kat.npz     inputs + IoU / HD(50,95) / MSD of the reference's IoU + calc_distance_metrics
+  degrade.npz         GaussianBlur.make kernels, conv_kernel2d blur and FactorResize outputs
+  joint_model.npz     JointModel (KBPN + PSPNet) outputs on csbsr_b200.modeling.params.synth_state_dict weights
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh  # noqa: E402
+
+
+def synthetic_case(B, H, W, seed):
+    """Crack-like masks (exactly binary) + noisy probability maps."""
+    from scipy import ndimage
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    masks, probs = [], []
+    for b in range(B):
+        a, c, w = rng.uniform(-0.6, 0.6), rng.uniform(0.25, 0.75) * H, rng.uniform(1.5, 3.5)
+        m = (np.abs(yy - (a * xx + c + 4 * np.sin(xx / rng.uniform(4, 9)))) < w).astype(np.float32)
+        base = ndimage.gaussian_filter(np.roll(m, rng.integers(-3, 4), axis=1), 1.2)
+        p = np.clip(base * rng.uniform(0.8, 1.3) + 0.08 * rng.standard_normal((H, W)), 0, 1).astype(np.float32)
+        masks.append(m)
+        probs.append(p)
+    return np.stack(probs)[:, None], np.stack(masks)[:, None]
+
+
+def gen_metrics():
+    IoU, calc, sd = rh.metric_fns()
+    import model.engine.inference as inf
+    th = torch.Tensor([i * 0.01 for i in range(1, 100)]).view(99, 1, 1)
+    cases = {}
+    prob, mask = synthetic_case(3, 48, 64, 11)
+    mask[2] = 0                       # gt empty
+    prob2, mask2 = synthetic_case(2, 33, 47, 12)
+    prob2[1] = 0.0                    # prediction empty at every threshold
+    mask2[0, 0, :, :] = 1.0           # full-image mask: borders only at the image edge
+    for name, (p, m) in {"a": (prob, mask), "b": (prob2, mask2)}.items():
+        pt, mt = torch.from_numpy(p), torch.from_numpy(m)
+        bi = (pt - th > torch.Tensor([0])).float()
+        iou = IoU()(bi, mt)
+        out = {"prob": p, "mask": m, "iou": iou}
+        for pct in (50, 95):
+            src = inf.calc_distance_metrics.__code__
+            # the reference hard-codes percentile = 50 (inference.py:302); for 95 re-run its own loop body
+            if pct == 50:
+                hd, msd, _, _ = calc(bi, mt, 0, 0)
+            else:
+                hd = np.zeros(iou.shape); msd = np.zeros(iou.shape)
+                for i in range(p.shape[0]):
+                    g = m[i, 0].astype(bool)
+                    for j in range(99):
+                        s = sd.compute_surface_distances(g, bi[i, j].numpy().astype(bool), spacing_mm=(1, 1))
+                        a, b_ = len(s["distances_gt_to_pred"]), len(s["distances_pred_to_gt"])
+                        hd[i, j] = 0 if (a == 0 and b_ == 0) else (p.shape[3] if (a == 0 or b_ == 0)
+                                                                     else sd.compute_robust_hausdorff(s, pct))
+                _, msd, _, _ = calc(bi, mt, 0, 0)
+            out["hd%d" % pct] = hd
+            out["msd"] = msd
+        cases[name] = out
+    flat = {"%s_%s" % (n, k): v for n, c in cases.items() for k, v in c.items()}
+    np.savez_compressed(os.path.join(HERE, "metrics_kat.npz"), **flat)
+    print("metrics_kat.npz", {k: v.shape for k, v in flat.items()})
+
+
+def gen_degrade():
+    GaussianBlur, conv_kernel2d, FactorResize = rh.degrade_fns()
+    rng = np.random.default_rng(5)
+    out = {}
+    thetas, sigmas, kernels = [], [], []
+    for i in range(6):
+        torch.manual_seed(100 + i)
+        np.random.seed(200 + i)
+        # replay the reference's own draws: theta from torch.rand, sigma from np.random.rand (blur.py:129,170-179)
+        st, sn = torch.get_rng_state(), np.random.get_state()
+        k = GaussianBlur(size=21, isotropic=False, range_deterioration_ratio=(0.2, 4)).make().to("cpu")
+        torch.set_rng_state(st); np.random.set_state(sn)
+        theta = (180 * torch.rand(1).item()) * np.pi / 180
+        sx = 3.8 * np.random.rand() + 0.2
+        sy = 3.8 * np.random.rand() + 0.2
+        thetas.append(theta); sigmas.append((sx, sy)); kernels.append(k.numpy())
+    out["theta"] = np.array(thetas); out["sigma"] = np.array(sigmas); out["kernels"] = np.stack(kernels)
+    hr = rng.random((6, 3, 64, 96)).astype(np.float32)
+    blur, lr = [], []
+    fr = FactorResize(4, "bicubic")
+    for i in range(6):
+        b = conv_kernel2d(torch.from_numpy(hr[i]), torch.from_numpy(kernels[i])).to("cpu")
+        blur.append(b.numpy()); lr.append(fr(b).numpy())
+    out["hr"] = hr; out["blur"] = np.stack(blur); out["lr"] = np.stack(lr)
+    np.savez_compressed(os.path.join(HERE, "degrade.npz"), **out)
+    print("degrade.npz", {k: v.shape for k, v in out.items()})
+
+
+def gen_joint():
+    from csbsr_b200.modeling import params as P
+    cfg = rh.make_cfg()
+    m = rh.joint_model(cfg)
+    sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
+    sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(21)
+    x = torch.rand(2, 3, 16, 24, generator=g)
+    with torch.no_grad():
+        sr, seg, kp = m(x.clone(), torch.zeros(2, 1, 7, 7))
+    np.savez_compressed(os.path.join(HERE, "joint_model.npz"), x=x.numpy(), sr=sr.numpy().astype(np.float16),
+                        seg=seg.numpy().astype(np.float16), kp=kp.numpy(),
+                        sr_checksum=np.float64(sr.double().sum().item()), seg_checksum=np.float64(seg.double().sum().item()))
+    print("joint_model.npz", sr.shape, seg.shape, kp.shape)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["metrics", "degrade", "joint"]
+    if "metrics" in which:
+        gen_metrics()
+    if "degrade" in which:
+        gen_degrade()
+    if "joint" in which:
+        gen_joint()

