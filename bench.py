@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the CSBSR hot path (BASELINE.json metric): SR + segmentation + AIU/AHD95 images/sec.
+
+One "step" = one pass of the whole eval hot path over one batch of synthetic 448x448 crack images per GPU:
+on-the-fly degradation -> KBPN x4 blind SR -> clip + instance norm -> PSPNet -> AIU + HD/MSD sweeps (99
+thresholds).  Workload = BASELINE.json configs[1] ("CSBSR w/ PSPNet x4 inference bf16 batch 64 on 1 B200 with
+on-the-fly anisotropic-blur degradation and full AIU/AHD95"); under torchrun every rank runs its own batch
+(weak scaling, no data-path collective; the integer counts / HD values are all-gathered once per step).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 64] [--impl reference]
+
+`--impl reference` times the reference's own algorithm on the host CPU cores (the oracle port under oracle/,
+pinned to the unmodified reference by tests/golden) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SR+seg+AIU/AHD95 images/sec (448^2 HR, x4)"
+UNIT = "images/s"
+HR = 448
+# algorithmic (reference-dense) forward FLOPs per 448^2 image, BASELINE.md section 3
+DENSE_GFLOP_PER_IMG = 2255.38
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active")
+                                                          for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_step(hr, mask, params, sd):
+    """The reference's algorithm on the CPU (oracle port): degrade -> JointModel.forward -> AIU + HD sweep."""
+    import torch
+    from oracle import degrade_ref, metrics_ref, torch_ref
+    with torch.no_grad():
+        lr, _, _ = degrade_ref.degrade(hr, params)
+        sr, seg, kp, _ = torch_ref.joint_forward(sd, lr)
+    inter, union = metrics_ref.iou_counts(seg.numpy(), mask.numpy())
+    hd, msd = metrics_ref.distance_metrics(seg.numpy(), mask.numpy(), 50)
+    return metrics_ref.iou_from_counts(inter, union), hd, msd
+
+
+def run_reference(args):
+    import torch
+    from csbsr_b200.utils import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.model_state_dict()
+    n_img = 1                                   # bounded sample: one 448^2 image per step (~20-30 s of CPU work)
+    hr, mask = synth.batch(0, n_img, HR)
+    params = synth.degradation_params(n_img)
+    budget_s = 170.0
+    t0 = time.time()
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(hr, mask, params, sd)
+    per = max(time.time() - t0, 1e-3) if args.warmup > 0 else 25.0
+    steps = max(1, min(args.steps, int(budget_s / per)))
+    t0 = time.time()
+    for _ in range(steps):
+        cpu_reference_step(hr, mask, params, sd)
+    dt = time.time() - t0
+    value = n_img * steps / dt
+    sample = ("%d x 448^2 image(s) per step through the oracle port of the reference (degrade + KBPN + PSPNet fp32 on "
+              "torch CPU, numpy/scipy AIU + HD sweep), %d of %d requested steps run within the %.0f s budget"
+              % (n_img, steps, args.steps, budget_s))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "CSBSR w/ PSPNet x4 eval, 448^2 HR, on-the-fly degradation, AIU+HD sweep (99 thr)",
+                       "batch_per_step": n_img},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--chunk", type=int, default=8, help="images per pass through the network engines")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from csbsr_b200 import _lib, kernels as K
+    from csbsr_b200.config import cfg
+    from csbsr_b200.data import degrade as G
+    from csbsr_b200.engine import inference as E
+    from csbsr_b200.modeling.build_model import JointModel
+    from csbsr_b200.utils import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()                                   # fail loudly if the CUDA library is missing
+    if not _lib.lib().csbsr_device_ok():
+        raise _lib.CsbsrError("bench.py needs an sm_100 device")
+
+    B = args.batch
+    c = cfg.clone()
+    c.merge_from_file(os.path.join(ROOT, "config", "config_csbsr_pspnet.yaml"))
+    model = JointModel(c)
+    model.load_state_dict(synth.model_state_dict(), strict=True)
+    model.chunk = args.chunk
+
+    # synthetic inputs: a few distinct images tiled to the batch (generation is untimed); each rank its own shard
+    n_unique = min(B, 16)
+    hr_u, mask_u = synth.batch(rank * B, n_unique, HR)
+    reps = (B + n_unique - 1) // n_unique
+    hr_host = hr_u.repeat(reps, 1, 1, 1)[:B].contiguous().pin_memory()
+    mask_host = mask_u.repeat(reps, 1, 1, 1)[:B].contiguous().pin_memory()
+    params = synth.degradation_params(B, seed=5 + rank)
+    hr_dev, mask_dev = hr_host.to(dev), mask_host.to(dev)
+    params_dev = torch.as_tensor(params).to(dev)
+    mchunk = 16
+
+    def hot_path(hr, mask):
+        """degrade -> SR -> seg -> metrics for one batch resident on the device; returns device tensors."""
+        lr, _ = G.degrade(hr, params_dev)
+        sr, seg, kp = model(lr, None)
+        outs = []
+        for i in range(0, B, mchunk):
+            r = E.seg_metrics(seg[i:i + mchunk], mask[i:i + mchunk], with_hd=True, to_host=False)
+            outs.append(torch.cat([r["inter"].double(), r["union"].double(), r["hd"], r["msd"]], dim=1))
+        return torch.cat(outs, 0)               # [B, 4*99] fp64
+
+    def gather(res):
+        if world > 1:
+            out = [torch.empty_like(res) for _ in range(world)]
+            dist.all_gather(out, res)            # the only exchange: B x 396 fp64 per rank
+            res = torch.cat(out, 0)
+        return res
+
+    def step_device():
+        return gather(hot_path(hr_dev, mask_dev))
+
+    def step_e2e():
+        hr = hr_host.to(dev, non_blocking=True)
+        mask = mask_host.to(dev, non_blocking=True)
+        res = gather(hot_path(hr, mask)).cpu().numpy()
+        inter, union, hd = res[:, :99], res[:, 99:198], res[:, 198:297]
+        iou = (inter + 1e-5) / (union + 1e-5)
+        return float(np.mean(iou)), float(np.mean(hd))     # AIU, AHD (inference.py:171-173)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.LAUNCHES
+    ms_dev, _ = timed(step_device, args.steps)
+    launches = (_lib.LAUNCHES - l0) // max(args.steps, 1)
+    step_e2e()
+    ms_e2e, (aiu, ahd) = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel (conv_igemm_kernel), measured live with CUDA events per launch
+    K.PROFILE = []
+    step_device()
+    torch.cuda.synchronize()
+    conv_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1, _ in K.PROFILE)
+    conv_useful = sum(u for _, _, _, _, u in K.PROFILE)
+    conv_padded = sum(f for _, f, _, _, _ in K.PROFILE)
+    n_conv = len(K.PROFILE)
+    K.PROFILE = None
+    peak_tf, peak_bw, peak_src = _peaks()
+    achieved_tf = conv_useful / (conv_ms * 1e-3) / 1e12
+    value = world * B * args.steps / (ms_dev * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d = int(hr_host.numel() * 4 + mask_host.numel() * 4)
+    d2h = int(world * B * 4 * 99 * 8)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "CSBSR w/ PSPNet x4 eval (config_csbsr_pspnet.yaml), batch %d x 448^2 HR per GPU, on-the-fly "
+                               "anisotropic-blur degradation, AIU + HD(p50)/MSD sweep over 99 thresholds" % B,
+                   "batch_per_gpu": B, "chunk": args.chunk, "hr": HR, "scale": 4, "weights": "synthetic random-init (seed 1121)",
+                   "l2": "per-step inputs (%.0f MB) and activations exceed the 126 MB L2; no flush needed" % (h2d / 1e6),
+                   "aiu": aiu, "ahd_p50": ahd},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "csbsr::conv_igemm_kernel", "achieved": achieved_tf, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src + " (sustained bf16)",
+                     "launches_per_step": n_conv, "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / (ms_dev / args.steps),
+                     "useful_gflop_per_step": conv_useful / 1e9, "padded_gflop_per_step": conv_padded / 1e9,
+                     "reference_dense_gflop_per_step": DENSE_GFLOP_PER_IMG * B,
+                     "reference_dense_tflops_equiv": DENSE_GFLOP_PER_IMG * B / 1e3 / (ms_dev / args.steps * 1e-3)},
+        "clocks": clocks,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            sd = synth.model_state_dict()
+            t0 = time.time()
+            cpu_reference_step(hr_u[:1], mask_u[:1], params[:1], sd)
+            dt = time.time() - t0
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "1 x 448^2 image through the oracle port (degrade + KBPN + PSPNet fp32 "
+                                              "torch CPU + numpy/scipy AIU/HD sweep), single run, %.1f s" % dt}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -111,3 +111,16 @@ def check(rc, what):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# kernels launched per C-ABI call (our own __global__ functions only; memsets are not counted)
+KERNELS_PER_CALL = {"csbsr_conv_igemm": 1, "csbsr_clip_instnorm_stats": 2, "csbsr_degrade": 3, "csbsr_seg_metrics": 14}
+LAUNCHES = 0
+
+
+def count_launch(name, with_hd=True):
+    global LAUNCHES
+    n = KERNELS_PER_CALL.get(name, 1)
+    if name == "csbsr_seg_metrics" and not with_hd:
+        n = 2
+    LAUNCHES += n

@@ -256,7 +256,7 @@ template <bool PROD>
 __device__ __forceinline__ double elem(const unsigned int* keys, int i) {
     const unsigned int k = keys[i];
     const double l = len_value(k & 3);
-    return PROD ? key_dist(k) * l : l;
+    return PROD ? __dmul_rn(key_dist(k), l) : l;     // separate multiply: no FMA contraction with the following add
 }
 // numpy pairwise_sum for n <= 128 (numpy/_core/src/umath/loops_utils.h.src): 8 interleaved accumulators
 template <bool PROD>

@@ -101,6 +101,7 @@ def degrade(hr, params, ksize=21, factor=4, clamp01=False, return_blurred=False)
     _lib.check(_lib.lib().csbsr_degrade(x.data_ptr(), p.data_ptr(), kernels.data_ptr(), blurred.data_ptr(),
                                         lr.data_ptr(), b, c, h, w, ksize, factor, int(clamp01), _lib.stream_ptr()),
                "csbsr_degrade")
+    _lib.count_launch("csbsr_degrade")
     if return_blurred:
         return lr, kernels, blurred
     return lr, kernels

@@ -53,6 +53,7 @@ def seg_metrics(segment_preds, masks, with_hd=True, percent=HD_PERCENTILE, to_ho
                              union.data_ptr(), hd.data_ptr() if with_hd else None, msd.data_ptr() if with_hd else None,
                              C.c_double(float(percent)), ws.data_ptr(), need, _lib.stream_ptr())
     _lib.check(rc, "csbsr_seg_metrics")
+    _lib.count_launch("csbsr_seg_metrics", with_hd)
     out = {"inter": inter, "union": union, "hd": hd, "msd": msd}
     if to_host:
         out = {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}

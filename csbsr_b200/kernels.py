@@ -80,7 +80,7 @@ class F32Map:
 class PackedConv:
     """Weights of one conv / transposed conv packed K-major per tap: [taps][cout_pad][cin_pad] bf16."""
 
-    def __init__(self, wp, taps, nphases, ntaps, stride, os, ooh, oow, cout, bias=None):
+    def __init__(self, wp, taps, nphases, ntaps, stride, os, ooh, oow, cout, bias=None, macs_per_pixel=None):
         self.wp = wp                      # [w_taps, cout_pad, cin_pad] bf16, contiguous
         self.taps = taps                  # list of (dh, dw, widx), length nphases*ntaps
         self.nphases, self.ntaps = nphases, ntaps
@@ -88,6 +88,8 @@ class PackedConv:
         self.ooh, self.oow = ooh, oow
         self.cout = cout
         self.bias = bias                  # fp32 [cout_pad] or None
+        # useful (unpadded, non-zero-weight) multiply-accumulates per output pixel of ONE phase
+        self.macs_per_pixel = macs_per_pixel if macs_per_pixel is not None else ntaps * wp.shape[2] * cout
 
     @property
     def cout_pad(self):
@@ -125,7 +127,7 @@ def pack_conv(weight, bias=None, stride=1, padding=0, dilation=1, cin_pad=None, 
         wp[:, :cout, d0:d0 + ln] = wt[:, :, s0:s0 + ln]
     taps = [(r * dilation - padding, s * dilation - padding, r * S + s) for r in range(R) for s in range(S)]
     return PackedConv(wp.to(torch.bfloat16).contiguous(), taps, 1, R * S, stride, 1, [0], [0], cout,
-                      _pad_bias(bias, cout_pad, w.device))
+                      _pad_bias(bias, cout_pad, w.device), macs_per_pixel=R * S * cin * cout)
 
 
 def pack_deconv8s4(weight, bias=None, cin_pad=None, cout_pad=None):
@@ -153,7 +155,7 @@ def pack_deconv8s4(weight, bias=None, cin_pad=None, cout_pad=None):
             ooh.append(rh)
             oow.append(rw)
     return PackedConv(wp.to(torch.bfloat16).contiguous(), taps, 16, 4, 1, 4, ooh, oow, cout,
-                      _pad_bias(bias, cout_pad, w.device))
+                      _pad_bias(bias, cout_pad, w.device), macs_per_pixel=4 * cin * cout)
 
 
 def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, act=ACT_NONE, slope=0.0,
@@ -220,11 +222,14 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
         e0.record()
     rc = _lib.lib().csbsr_conv_igemm(C.byref(d), _lib.stream_ptr())
     _lib.check(rc, "csbsr_conv_igemm")
+    _lib.count_launch("csbsr_conv_igemm")
     if PROFILE is not None:
         e1.record()
         flops = 2.0 * x.n * d.oh * d.ow * pc.nphases * pc.ntaps * pc.cin_pad * pc.cout_pad
+        useful = 2.0 * x.n * d.oh * d.ow * pc.nphases * pc.macs_per_pixel
         PROFILE.append(("conv n%d %dx%d cin%d cout%d taps%dx%d s%d" % (x.n, d.oh, d.ow, pc.cin_pad, pc.cout_pad,
-                                                                        pc.nphases, pc.ntaps, pc.stride), flops, e0, e1))
+                                                                        pc.nphases, pc.ntaps, pc.stride), flops, e0, e1,
+                        useful))
     return y
 
 
@@ -232,6 +237,7 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
 def _call(name, *args):
     rc = getattr(_lib.lib(), name)(*args, _lib.stream_ptr())
     _lib.check(rc, name)
+    _lib.count_launch(name)
 
 
 def _f32(t):

@@ -107,7 +107,7 @@ class KBPNEngine:
                                 continue
                             wp[rh * 4 + rw, :, (a * 3 + b) * 3:(a * 3 + b) * 3 + 3] = w[:, :, r, q].t()
             st["kb.d1"] = (K.PackedConv(wp.to(torch.bfloat16).contiguous(), [(0, 0, i) for i in range(16)], 16, 1, 1, 4,
-                                        [i // 4 for i in range(16)], [i % 4 for i in range(16)], C),
+                                        [i // 4 for i in range(16)], [i % 4 for i in range(16)], C, macs_per_pixel=4 * 3 * C),
                            slope(sp + "kb.up_conv1.act.weight"))
             if s < self.S - 1:
                 fc = (s + 1) * C

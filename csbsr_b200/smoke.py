@@ -1,0 +1,47 @@
+"""smoke(): one small invocation of the whole hot path on cuda:0, checked against the oracle (test infrastructure)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+
+def run():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from csbsr_b200 import _lib
+    from csbsr_b200.config import cfg
+    from csbsr_b200.data import degrade as G
+    from csbsr_b200.engine import inference as E
+    from csbsr_b200.modeling.build_model import JointModel
+    from csbsr_b200.utils import synth
+    from oracle import degrade_ref, metrics_ref, torch_ref
+
+    torch.cuda.set_device(0)
+    _lib.lib()
+    c = cfg.clone()
+    c.merge_from_file(os.path.join(root, "config", "config_csbsr_pspnet.yaml"))
+    model = JointModel(c)
+    sd = synth.model_state_dict()
+    model.load_state_dict(sd, strict=True)
+    hr, mask = synth.batch(0, 2, 96)
+    params = synth.degradation_params(2)
+    lr, kern = G.degrade(hr, params)
+    sr, seg, kp = model(lr, torch.zeros(2, 1, 7, 7))
+    r = E.seg_metrics(seg, mask, with_hd=True)
+    torch.cuda.synchronize()
+
+    lr_ref, k_ref, _ = degrade_ref.degrade(hr, params)
+    assert (lr.cpu() - lr_ref).abs().max().item() <= 2e-6, "degrade mismatch"
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        sr_ref, seg_ref, kp_ref, _ = torch_ref.joint_forward(sdc, lr)
+    e_sr, e_seg = (sr - sr_ref).abs().max().item(), (seg - seg_ref).abs().max().item()
+    assert e_sr <= 3e-2 and e_seg <= 5e-2, "network mismatch sr %g seg %g" % (e_sr, e_seg)
+    inter, union = metrics_ref.iou_counts(seg.cpu().numpy(), mask.numpy())
+    hd, msd = metrics_ref.distance_metrics(seg.cpu().numpy(), mask.numpy(), 50)
+    assert np.array_equal(r["inter"], inter) and np.array_equal(r["union"], union), "AIU counts mismatch"
+    assert np.array_equal(r["hd"], hd) and np.array_equal(r["msd"], msd), "HD/MSD mismatch"
+    print("smoke ok: sr max-abs %.4f, seg max-abs %.4f, AIU %.4f, AHD(p50) %.3f, %d kernel launches"
+          % (e_sr, e_seg, float(np.mean(r["iou"])), float(np.mean(r["hd"])), _lib.LAUNCHES))
