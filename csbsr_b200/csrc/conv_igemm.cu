@@ -20,7 +20,8 @@ static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;                  // bf16 elements = 128 bytes = one swizzle row
 static constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
 static constexpr int kMaxStages = 8;
-static constexpr int kThreads = 256;                // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
+static constexpr int kEpiWarps = 8;                 // 2 warps per TMEM lane quarter, interleaved 16-column units
+static constexpr int kThreads = 128 + 32 * kEpiWarps;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4.. epilogue
 static constexpr int kTmemCols = 512;
 static constexpr int kSmemBudget = 227 * 1024;
 
@@ -163,14 +164,159 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     return v;
 }
 
-__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&f)[8]) {
-    uint4 raw = *reinterpret_cast<const uint4*>(p);
+__device__ __forceinline__ void unpack8_bf16(const uint4& raw, float (&f)[8]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float2 t = __bfloat1622float2(h[i]);
         f[2 * i] = t.x;
         f[2 * i + 1] = t.y;
+    }
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v, float slope) {
+    if (ACT == CSBSR_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == CSBSR_ACT_LEAKY) return v > 0.f ? v : v * slope;
+    if (ACT == CSBSR_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    return v;
+}
+
+struct EpiRow {
+    bool valid;
+    size_t pix;
+    int img, oy, ox;
+    const float* bias_row;
+};
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& raw, float (&f)[8]) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+}
+
+// bf16 NHWC epilogue: one accumulator row (= one output pixel) per thread; this warp handles the 16-column units
+// u0, u0+2, ...; the residual operands of a unit are requested before its TMEM load is awaited.
+template <int ACT>
+__device__ __forceinline__ void epilogue_bf16(const ConvKParams& p, const EpiRow& er, uint32_t taddr0, int c_base,
+                                              int u0, int units) {
+    const float slope = p.slope;
+    const __nv_bfloat16* r0p = p.r0 ? p.r0 + er.pix * p.r0_pitch + p.r0_coff : nullptr;
+    const __nv_bfloat16* rmp = p.rm ? p.rm + er.pix * p.rm_pitch + p.rm_coff : nullptr;
+    const __nv_bfloat16* r1p = p.r1 ? p.r1 + er.pix * p.r1_pitch + p.r1_coff : nullptr;
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + er.pix * p.y_pitch + p.y_coff;
+    const float r1s = p.r1_sign;
+    for (int u = u0; u < units; u += 2) {
+        const int c0 = c_base + u * 16;
+        const bool on = er.valid && c0 < p.cout_store;
+        uint4 q0[2], qm[2], q1[2];
+        if (on) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const int c = c0 + g * 8;
+                const bool okc = c < p.cout_store;
+                q0[g] = (r0p && okc) ? *reinterpret_cast<const uint4*>(r0p + c) : make_uint4(0, 0, 0, 0);
+                qm[g] = (rmp && okc) ? *reinterpret_cast<const uint4*>(rmp + c) : make_uint4(0, 0, 0, 0);
+                q1[g] = (r1p && okc) ? *reinterpret_cast<const uint4*>(r1p + c) : make_uint4(0, 0, 0, 0);
+            }
+        }
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(taddr0 + static_cast<uint32_t>(u * 16), v);
+        tmem_ld_wait();
+        if (on) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const int c = c0 + g * 8;
+                if (c >= p.cout_store) break;
+                float fg[8], r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) fg[i] = __uint_as_float(v[g * 8 + i]);
+                if (er.bias_row) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(er.bias_row + c);
+                    const float4 b1 = *reinterpret_cast<const float4*>(er.bias_row + c + 4);
+                    fg[0] += b0.x; fg[1] += b0.y; fg[2] += b0.z; fg[3] += b0.w;
+                    fg[4] += b1.x; fg[5] += b1.y; fg[6] += b1.z; fg[7] += b1.w;
+                }
+                if (r0p) {
+                    bf16x8_to_f32(q0[g], r);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) fg[i] += r[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) fg[i] = act_fn<ACT>(fg[i], slope);
+                if (rmp) {
+                    bf16x8_to_f32(qm[g], r);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) fg[i] *= r[i];
+                }
+                if (r1p) {
+                    bf16x8_to_f32(q1[g], r);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) fg[i] = fmaf(r1s, r[i], fg[i]);
+                }
+                uint4 o;
+                __nv_bfloat162* oh2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) oh2[i] = __floats2bfloat162_rn(fg[2 * i], fg[2 * i + 1]);
+                *reinterpret_cast<uint4*>(yp + c) = o;
+            }
+        }
+    }
+}
+
+// fp32 outputs (NHWC for the class biases, planar for images / probabilities): few columns, simple loop
+template <int ACT>
+__device__ __forceinline__ void epilogue_units(const ConvKParams& p, const EpiRow& er, uint32_t taddr0, int c_base,
+                                               int u0, int units) {
+    const float slope = p.slope;
+    for (int u = u0; u < units; u += 2) {
+        const int c0 = c_base + u * 16;
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(taddr0 + static_cast<uint32_t>(u * 16), v);
+        tmem_ld_wait();
+        if (!(er.valid && c0 < p.cout_store)) continue;
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        if (er.bias_row) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(er.bias_row + c0 + i);
+                f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+            }
+        }
+        if (p.out_mode == CSBSR_OUT_F32_NHWC) {
+            float* y32 = reinterpret_cast<float*>(p.y) + er.pix * p.y_pitch + p.y_coff + c0;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                if (c0 + i < p.cout_store) {
+                    float4 o;
+                    o.x = act_fn<ACT>(f[i], slope);
+                    o.y = act_fn<ACT>(f[i + 1], slope);
+                    o.z = act_fn<ACT>(f[i + 2], slope);
+                    o.w = act_fn<ACT>(f[i + 3], slope);
+                    *reinterpret_cast<float4*>(y32 + i) = o;
+                }
+            }
+        } else {                                        // fp32 planar [n][cout_store][YH][YW]
+            float* y32 = reinterpret_cast<float*>(p.y);
+            const size_t plane = static_cast<size_t>(p.YH) * p.YW;
+            const size_t base = (static_cast<size_t>(er.img) * p.cout_store) * plane + static_cast<size_t>(er.oy) * p.YW + er.ox;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = c0 + i;
+                if (c < p.cout_store) {
+                    float val = act_fn<ACT>(f[i], slope);
+                    if (p.r32) val += p.r32[base + c * plane];
+                    y32[base + c * plane] = val;
+                }
+            }
+        }
     }
 }
 
@@ -204,7 +350,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);      // one arrive per epilogue warp
+            mbar_init(&tmem_empty[a], kEpiWarps);      // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -314,90 +460,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                                  static_cast<size_t>(cls) * p.bias_sc
                                            : nullptr;
 
-            mbar_wait(&tmem_full[as], aphase, p.err_flag, 4);
-            tcgen05_fence_after();
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * 256);
             const int c_base = nt * p.block_n;
-            for (int cc = 0; cc < p.block_n; cc += 16) {
-                uint32_t v[16];
-                __syncwarp();
-                tmem_ld16(taddr0 + static_cast<uint32_t>(cc), v);
-                tmem_ld_wait();
-                const int c0 = c_base + cc;
-                if (valid && c0 < p.cout_store) {
-                float f[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-                if (bias_row) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        float4 b = *reinterpret_cast<const float4*>(bias_row + c0 + i);
-                        f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
-                    }
+            const int units = p.block_n >> 4;               // 16-column units, interleaved between the 2 warps
+            const int u0 = (warp - 4) >> 2;
+            EpiRow er;
+            er.valid = valid; er.pix = pix; er.img = img; er.oy = oy; er.ox = ox; er.bias_row = bias_row;
+            mbar_wait(&tmem_full[as], aphase, p.err_flag, 4);
+            tcgen05_fence_after();
+            if (p.out_mode == CSBSR_OUT_BF16_NHWC) {
+                switch (p.act) {
+                    case CSBSR_ACT_RELU:    epilogue_bf16<CSBSR_ACT_RELU>(p, er, taddr0, c_base, u0, units); break;
+                    case CSBSR_ACT_LEAKY:   epilogue_bf16<CSBSR_ACT_LEAKY>(p, er, taddr0, c_base, u0, units); break;
+                    case CSBSR_ACT_SIGMOID: epilogue_bf16<CSBSR_ACT_SIGMOID>(p, er, taddr0, c_base, u0, units); break;
+                    default:                epilogue_bf16<CSBSR_ACT_NONE>(p, er, taddr0, c_base, u0, units); break;
                 }
-                if (p.out_mode == CSBSR_OUT_BF16_NHWC) {
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const int c = c0 + g * 8;
-                        if (c >= p.cout_store) break;
-                        float* fg = f + g * 8;
-                        if (p.r0) {
-                            float r[8];
-                            load8_bf16(p.r0 + pix * p.r0_pitch + p.r0_coff + c, r);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) fg[i] += r[i];
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) fg[i] = apply_act(fg[i], p.act, p.slope);
-                        if (p.rm) {
-                            float r[8];
-                            load8_bf16(p.rm + pix * p.rm_pitch + p.rm_coff + c, r);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) fg[i] *= r[i];
-                        }
-                        if (p.r1) {
-                            float r[8];
-                            load8_bf16(p.r1 + pix * p.r1_pitch + p.r1_coff + c, r);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) fg[i] += p.r1_sign * r[i];
-                        }
-                        uint4 o;
-                        __nv_bfloat162* oh2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) oh2[i] = __floats2bfloat162_rn(fg[2 * i], fg[2 * i + 1]);
-                        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.y_pitch + p.y_coff +
-                                                  c) = o;
-                    }
-                } else if (p.out_mode == CSBSR_OUT_F32_NHWC) {
-                    float* y32 = reinterpret_cast<float*>(p.y) + pix * p.y_pitch + p.y_coff + c0;
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        if (c0 + i < p.cout_store) {
-                            float4 o;
-                            o.x = apply_act(f[i], p.act, p.slope);
-                            o.y = apply_act(f[i + 1], p.act, p.slope);
-                            o.z = apply_act(f[i + 2], p.act, p.slope);
-                            o.w = apply_act(f[i + 3], p.act, p.slope);
-                            *reinterpret_cast<float4*>(y32 + i) = o;
-                        }
-                    }
-                } else {
-                    // fp32 planar [n][cout_store][YH][YW]
-                    float* y32 = reinterpret_cast<float*>(p.y);
-                    const size_t plane = static_cast<size_t>(p.YH) * p.YW;
-                    const size_t base = (static_cast<size_t>(img) * p.cout_store) * plane +
-                                        static_cast<size_t>(oy) * p.YW + ox;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int c = c0 + i;
-                        if (c < p.cout_store) {
-                            float val = apply_act(f[i], p.act, p.slope);
-                            if (p.r32) val += p.r32[base + c * plane];
-                            y32[base + c * plane] = val;
-                        }
-                    }
+            } else {
+                switch (p.act) {
+                    case CSBSR_ACT_RELU:    epilogue_units<CSBSR_ACT_RELU>(p, er, taddr0, c_base, u0, units); break;
+                    case CSBSR_ACT_LEAKY:   epilogue_units<CSBSR_ACT_LEAKY>(p, er, taddr0, c_base, u0, units); break;
+                    case CSBSR_ACT_SIGMOID: epilogue_units<CSBSR_ACT_SIGMOID>(p, er, taddr0, c_base, u0, units); break;
+                    default:                epilogue_units<CSBSR_ACT_NONE>(p, er, taddr0, c_base, u0, units); break;
                 }
-                }  // valid
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -472,12 +556,9 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     memset(&p, 0, sizeof(p));
     int block_n = d->block_n;
     if (block_n <= 0) {
-        if (d->cout_pad % 256 == 0) block_n = 256;
-        else if (d->cout_pad % 128 == 0) block_n = 128;
-        else if (d->cout_pad <= 256) block_n = d->cout_pad;
-        else if (d->cout_pad % 64 == 0) block_n = 64;
-        else if (d->cout_pad % 32 == 0) block_n = 32;
-        else block_n = 16;
+        // widest tile (<= 256 columns, multiple of 16) that divides cout_pad: fewer re-reads of the A operand
+        for (block_n = 256; block_n > 16; block_n -= 16)
+            if (d->cout_pad % block_n == 0) break;
     }
     CSBSR_REQUIRE(block_n % 16 == 0 && block_n >= 16 && block_n <= 256 && d->cout_pad % block_n == 0,
                   "conv_igemm: block_n=%d incompatible with cout_pad=%d", block_n, d->cout_pad);

@@ -16,6 +16,12 @@ def _dev():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _params_tensor(params, device):
+    if torch.is_tensor(params):
+        return params.to(device=device, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.asarray(params, dtype=np.float64)).to(device).contiguous()
+
+
 def draw_gaussian_params(n=1, range_theta=(0, 180), range_sigma=(0.2, 4), range_sigma2=None, isotropic=False):
     """The reference's per-sample draws: returns float64 [n,3] = (theta [rad], sigma_x, sigma_y)."""
     out = np.empty((n, 3), dtype=np.float64)
@@ -32,7 +38,7 @@ def draw_gaussian_params(n=1, range_theta=(0, 180), range_sigma=(0.2, 4), range_
 
 def gaussian_kernels(params, size=21):
     """params float64 [n,3] -> fp32 [n,size,size] on the device (GaussianBlur.make, blur.py:128-168)."""
-    p = torch.as_tensor(np.asarray(params, dtype=np.float64)).to(_dev()).contiguous()
+    p = _params_tensor(params, _dev())
     out = torch.empty((p.shape[0], size, size), dtype=torch.float32, device=p.device)
     _lib.check(_lib.lib().csbsr_blur_kernel_synth(p.data_ptr(), out.data_ptr(), p.shape[0], size, _lib.stream_ptr()),
                "csbsr_blur_kernel_synth")
@@ -93,7 +99,7 @@ def degrade(hr, params, ksize=21, factor=4, clamp01=False, return_blurred=False)
     """Batched CrackDataSet.__getitem__ degradation (crack_dataset.py:51-62): hr fp32 [B,3,H,W] + params float64
     [B,3] -> (lr [B,3,H/f,W/f], kernels [B,k,k])."""
     x = hr.to(device=_dev(), dtype=torch.float32).contiguous()
-    p = torch.as_tensor(np.asarray(params, dtype=np.float64)).to(x.device).contiguous()
+    p = _params_tensor(params, x.device)
     b, c, h, w = x.shape
     kernels = torch.empty((b, ksize, ksize), dtype=torch.float32, device=x.device)
     blurred = torch.empty_like(x)

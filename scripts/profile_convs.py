@@ -15,7 +15,7 @@ K.PROFILE = []
 m(x, dk)
 torch.cuda.synchronize()
 agg = collections.OrderedDict()
-for label, flops, e0, e1 in K.PROFILE:
+for label, flops, e0, e1, _u in K.PROFILE:
     t = e0.elapsed_time(e1)
     a = agg.setdefault(label, [0, 0.0, 0.0])
     a[0] += 1; a[1] += t; a[2] += flops
