@@ -11,6 +11,7 @@
 // Replaces the cuDNN convs behind nn.Conv2d / nn.ConvTranspose2d of the reference
 // (model/modeling/kbpn.py:266-277, 450-518; pspnet_pytorch/extractors.py:37-70; pspnet.py:23-57).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/csbsr_b200.h"
 
@@ -41,6 +42,9 @@ struct ConvKParams {
     const __nv_bfloat16* r1;
     const float* r32;
     int* err_flag;
+    int G, ngroups, dstep, a_stage_bytes;   // tap groups: G taps sharing dw, dh = dh0 + j*dstep, one A box per group
+    int staged;          // 1: epilogue through swizzled smem panels, residual via TMA load, output via TMA store
+    int res_mode;        // staged only: 0 none, 1 pre-activation add (r0), 2 post-activation add/sub (r1)
     int8_t dh[CSBSR_MAX_TAPS], dw[CSBSR_MAX_TAPS];
     int16_t widx[CSBSR_MAX_TAPS];
     int8_t ooh[CSBSR_MAX_PHASES], oow[CSBSR_MAX_PHASES];
@@ -106,6 +110,33 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
         "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+        "%7}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -268,6 +299,58 @@ __device__ __forceinline__ void epilogue_bf16(const ConvKParams& p, const EpiRow
     }
 }
 
+// Staged bf16 epilogue of ONE tile: the (optional) residual tile was TMA-loaded into the swizzled staging panels
+// (64 channels x 128 pixels x bf16 = 16 KB each, 128B swizzle like the A operand); every thread owns one pixel row,
+// combines accumulator + bias + residual + activation in place and the panels leave through one TMA store each.
+template <int ACT>
+__device__ __forceinline__ void epilogue_staged(const ConvKParams& p, uint8_t* stage_set, int row, uint32_t taddr0,
+                                                int c_base, int u_begin, int u_end, const float* bias_row) {
+    const float slope = p.slope, r1s = p.r1_sign;
+    const int res_mode = p.res_mode;
+    for (int u = u_begin; u < u_end; ++u) {
+        uint8_t* prow = stage_set + (u >> 2) * kATileBytes + row * 128;
+        const int j0 = (u & 3) * 2;                        // first 16-byte chunk of this unit inside the 128-byte row
+        uint4 q[2];
+        if (res_mode) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) q[g] = *reinterpret_cast<const uint4*>(prow + (((j0 + g) ^ (row & 7)) << 4));
+        }
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(taddr0 + static_cast<uint32_t>(u * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int c = c_base + u * 16 + g * 8;
+            float fg[8], r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) fg[i] = __uint_as_float(v[g * 8 + i]);
+            if (bias_row) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bias_row + c);
+                const float4 b1 = *reinterpret_cast<const float4*>(bias_row + c + 4);
+                fg[0] += b0.x; fg[1] += b0.y; fg[2] += b0.z; fg[3] += b0.w;
+                fg[4] += b1.x; fg[5] += b1.y; fg[6] += b1.z; fg[7] += b1.w;
+            }
+            if (res_mode) bf16x8_to_f32(q[g], r);
+            if (res_mode == 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) fg[i] += r[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) fg[i] = act_fn<ACT>(fg[i], slope);
+            if (res_mode == 2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) fg[i] = fmaf(r1s, r[i], fg[i]);
+            }
+            uint4 o;
+            __nv_bfloat162* oh2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) oh2[i] = __floats2bfloat162_rn(fg[2 * i], fg[2 * i + 1]);
+            *reinterpret_cast<uint4*>(prow + (((j0 + g) ^ (row & 7)) << 4)) = o;
+        }
+    }
+}
+
 // fp32 outputs (NHWC for the class biases, planar for images / probabilities): few columns, simple loop
 template <int ACT>
 __device__ __forceinline__ void epilogue_units(const ConvKParams& p, const EpiRow& er, uint32_t taddr0, int c_base,
@@ -323,18 +406,23 @@ __device__ __forceinline__ void epilogue_units(const ConvKParams& p, const EpiRo
 // ------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                   const __grid_constant__ ConvKParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x A tile][stages x B tile][barriers]
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_tile_bytes = p.block_n * kBlockK * 2;
+    const int b_stage_bytes = p.G * b_tile_bytes;
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + p.stages * kATileBytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_tile_bytes);
+    uint8_t* smem_b = smem + p.stages * p.a_stage_bytes;
+    const int n_panels = p.block_n >> 6;                      // staged epilogue: 64-channel panels per tile
+    uint8_t* smem_stage = smem_b + p.stages * b_stage_bytes;  // 2 sets x n_panels x 16 KB (staged epilogue only)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage + (p.staged ? 2 * n_panels * kATileBytes : 0));
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_full = tmem_empty + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -342,6 +430,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (p.staged) {
+            tma_prefetch_desc(&tmY);
+            if (p.res_mode) tma_prefetch_desc(&tmR);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -351,6 +443,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], kEpiWarps);      // one arrive per epilogue warp
+            mbar_init(&res_full[a], 1);
         }
         fence_barrier_init();
     }
@@ -360,7 +453,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int kblocks = p.ntaps * p.kchunks;
+    const int kblocks = p.ngroups * p.kchunks;
     const int tiles_per_img = p.tiles_h * p.tiles_w;
 
     if (warp == 0) {
@@ -368,7 +461,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = kATileBytes + b_tile_bytes;
+            const uint32_t tx_bytes = p.a_stage_bytes + b_stage_bytes;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
                 const int rest = tile / p.n_tiles;
@@ -378,18 +471,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int tr = mt % tiles_per_img;
                 const int oh0 = (tr / p.tiles_w) * p.TH;
                 const int ow0 = (tr % p.tiles_w) * p.TW;
-                for (int t = 0; t < p.ntaps; ++t) {
-                    const int ti = ph * p.ntaps + t;
-                    const int ih0 = oh0 * p.stride + p.dh[ti];
-                    const int iw0 = ow0 * p.stride + p.dw[ti];
-                    const int wi = p.widx[ti];
+                for (int g = 0; g < p.ngroups; ++g) {
+                    const int gi = (ph * p.ngroups + g) * p.G;          // first tap of the group
+                    const int ih0 = oh0 * p.stride + p.dh[gi];
+                    const int iw0 = ow0 * p.stride + p.dw[gi];
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 1);
                         mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                        tma_load_4d(smem_u32(smem_a + stage * kATileBytes), &tmA, &full_bar[stage], kc * kBlockK, iw0,
-                                    ih0, img);
-                        tma_load_3d(smem_u32(smem_b + stage * b_tile_bytes), &tmB, &full_bar[stage], kc * kBlockK,
-                                    nt * p.block_n, wi);
+                        // one A box covers the G vertically shifted taps of the group (rows TH + (G-1)*dstep)
+                        tma_load_4d(smem_u32(smem_a + stage * p.a_stage_bytes), &tmA, &full_bar[stage], kc * kBlockK,
+                                    iw0, ih0, img);
+                        for (int j = 0; j < p.G; ++j)
+                            tma_load_3d(smem_u32(smem_b + stage * b_stage_bytes + j * b_tile_bytes), &tmB,
+                                        &full_bar[stage], kc * kBlockK, nt * p.block_n, p.widx[gi + j]);
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1u;
@@ -415,13 +509,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
                     tcgen05_fence_after();
-                    const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * kATileBytes));
-                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * b_tile_bytes));
+                    const uint32_t a_base = smem_u32(smem_a + stage * p.a_stage_bytes);
+                    const uint32_t b_base = smem_u32(smem_b + stage * b_stage_bytes);
+                    const uint32_t a_shift = static_cast<uint32_t>(p.dstep * p.TW * 128);   // bytes per vertical tap step
+                    for (int j = 0; j < p.G; ++j) {
+                        const uint64_t adesc = make_smem_desc(a_base + j * a_shift);
+                        const uint64_t bdesc = make_smem_desc(b_base + j * b_tile_bytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // +32 bytes per K=16 step inside the 128B swizzle row -> +2 in the >>4 address field
-                        umma_bf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
-                                  idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // +32 bytes per K=16 step inside the 128B swizzle row -> +2 in the >>4 address field
+                            umma_bf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                                      idesc, (kb > 0 || j > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
                     if (kb == kblocks - 1) umma_commit(&tmem_full[as]);
@@ -437,6 +536,90 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int q = warp & 3;                       // TMEM lane quarter owned by this warp
         const int row = q * 32 + lane;                // accumulator row == pixel inside the tile
         const int th = row / p.TW, tw = row % p.TW;
+        if (p.staged) {
+            // ---------------- staged epilogue (see epilogue_staged) ----------------
+            const bool leader = (warp == 4 && lane == 0);
+            const int units = p.block_n >> 4;
+            const int half = (warp - 4) >> 2;
+            const int u_begin = half ? (units >> 1) : 0, u_end = half ? units : (units >> 1);
+            const uint32_t res_bytes = static_cast<uint32_t>(n_panels) * kATileBytes;
+            auto tile_coords = [&](int tile, int& nt, int& ph, int& img, int& oh0, int& ow0) {
+                nt = tile % p.n_tiles;
+                const int rest = tile / p.n_tiles;
+                ph = rest % p.nphases;
+                const int mt = rest / p.nphases;
+                img = mt / tiles_per_img;
+                const int tr = mt % tiles_per_img;
+                oh0 = (tr / p.tiles_w) * p.TH;
+                ow0 = (tr % p.tiles_w) * p.TW;
+            };
+            auto load_residual = [&](int tile, int set) {
+                int nt, ph, img, oh0, ow0;
+                tile_coords(tile, nt, ph, img, oh0, ow0);
+                mbar_arrive_expect_tx(&res_full[set], res_bytes);
+                for (int pn = 0; pn < n_panels; ++pn) {
+                    const uint32_t dst = smem_u32(smem_stage + (set * n_panels + pn) * kATileBytes);
+                    const int c = nt * p.block_n + pn * 64;
+                    if (p.os == 1) tma_load_4d(dst, &tmR, &res_full[set], c, ow0, oh0, img);
+                    else tma_load_5d(dst, &tmR, &res_full[set], c, p.oow[ph], ow0, p.ooh[ph], img * p.OH + oh0);
+                }
+            };
+            if (leader && p.res_mode && blockIdx.x < p.total_tiles) load_residual(blockIdx.x, 0);
+            int local = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+                const int as = local & 1;
+                const uint32_t aphase = (local >> 1) & 1;
+                int nt, ph, img, oh0, ow0;
+                tile_coords(tile, nt, ph, img, oh0, ow0);
+                uint8_t* stage_set = smem_stage + as * n_panels * kATileBytes;
+                if (p.res_mode) {
+                    // prefetch the next tile's residual into the other set (its last reader, the TMA store of the
+                    // previous tile, must have finished reading shared memory)
+                    if (leader && tile + gridDim.x < p.total_tiles) {
+                        tma_store_wait_read<0>();
+                        load_residual(tile + gridDim.x, as ^ 1);
+                    }
+                    mbar_wait(&res_full[as], aphase, p.err_flag, 5);
+                } else {
+                    if (leader) tma_store_wait_read<1>();       // the store that last used this set is done reading
+                    epi_bar_sync();
+                }
+                const int oy = (oh0 + th) * p.os + p.ooh[ph];
+                const int ox = (ow0 + tw) * p.os + p.oow[ph];
+                int cls = 0;
+                if (p.cls_bw > 0)
+                    cls = border_class(min(oy, p.YH - 1), p.YH, p.cls_bw) * (2 * p.cls_bw + 1) +
+                          border_class(min(ox, p.YW - 1), p.YW, p.cls_bw);
+                const float* bias_row = p.bias ? p.bias + static_cast<size_t>(img) * p.bias_sn +
+                                                     static_cast<size_t>(cls) * p.bias_sc
+                                               : nullptr;
+                mbar_wait(&tmem_full[as], aphase, p.err_flag, 4);
+                tcgen05_fence_after();
+                const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * 256);
+                const int c_base = nt * p.block_n;
+                switch (p.act) {
+                    case CSBSR_ACT_RELU:    epilogue_staged<CSBSR_ACT_RELU>(p, stage_set, row, taddr0, c_base, u_begin, u_end, bias_row); break;
+                    case CSBSR_ACT_LEAKY:   epilogue_staged<CSBSR_ACT_LEAKY>(p, stage_set, row, taddr0, c_base, u_begin, u_end, bias_row); break;
+                    case CSBSR_ACT_SIGMOID: epilogue_staged<CSBSR_ACT_SIGMOID>(p, stage_set, row, taddr0, c_base, u_begin, u_end, bias_row); break;
+                    default:                epilogue_staged<CSBSR_ACT_NONE>(p, stage_set, row, taddr0, c_base, u_begin, u_end, bias_row); break;
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                fence_proxy_async_smem();                       // make the generic-proxy writes visible to the TMA store
+                epi_bar_sync();
+                if (leader) {
+                    for (int pn = 0; pn < n_panels; ++pn) {
+                        const uint32_t src = smem_u32(stage_set + pn * kATileBytes);
+                        const int c = c_base + pn * 64;
+                        if (p.os == 1) tma_store_4d(&tmY, src, c, ow0, oh0, img);
+                        else tma_store_5d(&tmY, src, c, p.oow[ph], ow0, p.ooh[ph], img * p.OH + oh0);
+                    }
+                    tma_store_commit();
+                }
+            }
+            if (leader) tma_store_wait_read<0>();
+        } else {
         int local = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
             const int as = local & 1;
@@ -487,6 +670,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
         }
+        }  // direct epilogue
     }
 
     tcgen05_fence_before();
@@ -555,11 +739,24 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     ConvKParams p;
     memset(&p, 0, sizeof(p));
     int block_n = d->block_n;
+    const int TWh = d->ow > 8 ? 16 : 8, THh = kBlockM / TWh;
+    const int os_h = d->os > 0 ? d->os : 1;
+    // staged epilogue (smem panels + TMA residual load + TMA store): bf16 output, at most one residual operand,
+    // 64/128-column tiles; strided (deconv) outputs additionally need whole tiles per image for the merged 5-D map
+    bool can_stage = d->out_mode == CSBSR_OUT_BF16_NHWC && !d->rm && !(d->r0 && d->r1) && d->cout_pad % 64 == 0 &&
+                     (os_h == 1 || (d->yh == d->oh * os_h && d->yw == d->ow * os_h && d->oh % THh == 0));
+    if (getenv("CSBSR_NO_STAGED")) can_stage = false;
+    const bool prefer_stage = can_stage && (d->r0 || d->r1 || d->ntaps * d->cin <= 1024 || d->cout_pad <= 128);
     if (block_n <= 0) {
-        // widest tile (<= 256 columns, multiple of 16) that divides cout_pad: fewer re-reads of the A operand
-        for (block_n = 256; block_n > 16; block_n -= 16)
-            if (d->cout_pad % block_n == 0) break;
+        if (prefer_stage) {
+            block_n = d->cout_pad % 128 == 0 ? 128 : 64;
+        } else {
+            // widest tile (<= 256 columns, multiple of 16) that divides cout_pad: fewer re-reads of the A operand
+            for (block_n = 256; block_n > 16; block_n -= 16)
+                if (d->cout_pad % block_n == 0) break;
+        }
     }
+    const bool staged = can_stage && (block_n == 64 || block_n == 128);
     CSBSR_REQUIRE(block_n % 16 == 0 && block_n >= 16 && block_n <= 256 && d->cout_pad % block_n == 0,
                   "conv_igemm: block_n=%d incompatible with cout_pad=%d", block_n, d->cout_pad);
     p.block_n = block_n;
@@ -574,8 +771,68 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     p.kchunks = d->cin / kBlockK;
     p.ntaps = d->ntaps;
     p.stride = d->stride;
-    const int stage_bytes = kATileBytes + block_n * kBlockK * 2;
-    int stages = (kSmemBudget - 2048) / stage_bytes;
+    // ---- tap grouping: taps of one phase that share dw and whose dh form dh0 + j*dstep are served by ONE A box of
+    // TH + (G-1)*dstep rows (stride-1 convs only): cuts the L2 -> smem traffic of the A operand by G
+    int G = 1, ngroups = d->ntaps, dstep = 0;
+    int8_t g_dh[CSBSR_MAX_TAPS], g_dw[CSBSR_MAX_TAPS];
+    int16_t g_widx[CSBSR_MAX_TAPS];
+    memcpy(g_dh, d->dh, sizeof(g_dh)); memcpy(g_dw, d->dw, sizeof(g_dw)); memcpy(g_widx, d->widx, sizeof(g_widx));
+    const int staging_bytes = staged ? 2 * (block_n / 64) * kATileBytes : 0;
+    if (d->stride == 1 && d->ntaps >= 2 && !getenv("CSBSR_NO_GROUPING")) {
+        // distinct dw values of phase 0, in order of appearance
+        int dws[CSBSR_MAX_TAPS], ndw = 0;
+        for (int t = 0; t < d->ntaps; ++t) {
+            bool seen = false;
+            for (int i = 0; i < ndw; ++i) seen |= (dws[i] == d->dw[t]);
+            if (!seen) dws[ndw++] = d->dw[t];
+        }
+        const int cand = d->ntaps / ndw;
+        bool ok = cand >= 2 && cand * ndw == d->ntaps;
+        int step = 0;
+        int8_t n_dh[CSBSR_MAX_TAPS], n_dw[CSBSR_MAX_TAPS];
+        int16_t n_widx[CSBSR_MAX_TAPS];
+        for (int ph = 0; ph < d->nphases && ok; ++ph) {
+            // per phase the dw set may differ (deconv): recompute it
+            int pd[CSBSR_MAX_TAPS], pn = 0;
+            for (int t = 0; t < d->ntaps; ++t) {
+                const int v = d->dw[ph * d->ntaps + t];
+                bool seen = false;
+                for (int i = 0; i < pn; ++i) seen |= (pd[i] == v);
+                if (!seen) pd[pn++] = v;
+            }
+            if (pn != ndw) { ok = false; break; }
+            for (int gi = 0; gi < ndw && ok; ++gi) {
+                // taps of this phase with dw == pd[gi], sorted by dh
+                int idx[CSBSR_MAX_TAPS], cnt = 0;
+                for (int t = 0; t < d->ntaps; ++t)
+                    if (d->dw[ph * d->ntaps + t] == pd[gi]) idx[cnt++] = ph * d->ntaps + t;
+                if (cnt != cand) { ok = false; break; }
+                for (int a = 0; a < cnt; ++a)
+                    for (int b = a + 1; b < cnt; ++b)
+                        if (d->dh[idx[b]] < d->dh[idx[a]]) { int tmp = idx[a]; idx[a] = idx[b]; idx[b] = tmp; }
+                for (int j = 0; j < cnt; ++j) {
+                    if (j > 0) {
+                        const int st = d->dh[idx[j]] - d->dh[idx[j - 1]];
+                        if (st <= 0 || (step != 0 && st != step)) ok = false;
+                        step = st;
+                    }
+                    const int o = (ph * ndw + gi) * cand + j;
+                    n_dh[o] = d->dh[idx[j]]; n_dw[o] = d->dw[idx[j]]; n_widx[o] = d->widx[idx[j]];
+                }
+            }
+        }
+        if (ok) {
+            const int a_bytes = (THh + (cand - 1) * step) * TWh * 128;
+            const int st_bytes = a_bytes + cand * block_n * kBlockK * 2;
+            if ((THh + (cand - 1) * step) * 1 <= 256 && (kSmemBudget - 2048 - staging_bytes) / st_bytes >= 3) {
+                G = cand; ngroups = ndw; dstep = step;
+                memcpy(g_dh, n_dh, sizeof(g_dh)); memcpy(g_dw, n_dw, sizeof(g_dw)); memcpy(g_widx, n_widx, sizeof(g_widx));
+            }
+        }
+    }
+    const int a_stage_bytes = (THh + (G - 1) * dstep) * TWh * 128;
+    const int stage_bytes = a_stage_bytes + G * block_n * kBlockK * 2;
+    int stages = (kSmemBudget - 2048 - staging_bytes) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     CSBSR_REQUIRE(stages >= 2, "conv_igemm: not enough shared memory for 2 stages");
     p.stages = stages;
@@ -590,7 +847,10 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     p.rm = reinterpret_cast<const __nv_bfloat16*>(d->rm);
     p.r1 = reinterpret_cast<const __nv_bfloat16*>(d->r1);
     p.r32 = d->r32;
-    memcpy(p.dh, d->dh, sizeof(p.dh)); memcpy(p.dw, d->dw, sizeof(p.dw)); memcpy(p.widx, d->widx, sizeof(p.widx));
+    p.staged = staged ? 1 : 0;
+    p.res_mode = staged ? (d->r0 ? 1 : (d->r1 ? 2 : 0)) : 0;
+    memcpy(p.dh, g_dh, sizeof(p.dh)); memcpy(p.dw, g_dw, sizeof(p.dw)); memcpy(p.widx, g_widx, sizeof(p.widx));
+    p.G = G; p.ngroups = ngroups; p.dstep = dstep; p.a_stage_bytes = a_stage_bytes;
     memcpy(p.ooh, d->ooh, sizeof(p.ooh)); memcpy(p.oow, d->oow, sizeof(p.oow));
     CSBSR_REQUIRE(!d->bias || (d->bias_sn % 4 == 0 && d->bias_sc % 4 == 0), "conv_igemm: bias strides must be multiples of 4");
     for (int ph = 0; ph < p.nphases; ++ph)
@@ -611,7 +871,8 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
         cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
         cuuint64_t strides[3] = {(cuuint64_t)d->x_pitch * 2, (cuuint64_t)d->x_pitch * 2 * d->w,
                                  (cuuint64_t)d->x_pitch * 2 * d->w * d->h};
-        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.TW * d->stride), (cuuint32_t)(p.TH * d->stride), 1};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.TW * d->stride),
+                             (cuuint32_t)((p.TH + (G - 1) * dstep) * d->stride), 1};
         cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
         CSBSR_REQUIRE(box[1] <= 256 && box[2] <= 256, "conv_igemm: TMA box too large");
         CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
@@ -630,7 +891,43 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
         CSBSR_REQUIRE(r == CUDA_SUCCESS, "conv_igemm: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
 
-    const int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    CUtensorMap tmY, tmR;
+    memset(&tmY, 0, sizeof(tmY));
+    memset(&tmR, 0, sizeof(tmR));
+    if (staged) {
+        auto encode_out = [&](CUtensorMap* tm, const void* base_ptr, int pitch, int coff) -> int {
+            const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(base_ptr) + coff;
+            const cuuint64_t pb = (cuuint64_t)pitch * 2;
+            CUresult r;
+            if (p.os == 1) {
+                cuuint64_t dims[4] = {(cuuint64_t)d->cout_store, (cuuint64_t)p.YW, (cuuint64_t)p.YH, (cuuint64_t)d->n};
+                cuuint64_t strides[3] = {pb, pb * p.YW, pb * p.YW * p.YH};
+                cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+                cuuint32_t estr[4] = {1, 1, 1, 1};
+                r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            } else {
+                // pixel (n, oh*os+ooh, ow*os+oow) -> 5-D view (c, oow, ow, ooh, n*OH+oh)
+                cuuint64_t dims[5] = {(cuuint64_t)d->cout_store, (cuuint64_t)p.os, (cuuint64_t)p.OW, (cuuint64_t)p.os,
+                                      (cuuint64_t)d->n * p.OH};
+                cuuint64_t strides[4] = {pb, pb * p.os, pb * p.YW, pb * p.YW * p.os};
+                cuuint32_t box[5] = {64, 1, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH};
+                cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+                r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            }
+            return (int)r;
+        };
+        int r = encode_out(&tmY, d->y, d->y_pitch, d->y_coff);
+        CSBSR_REQUIRE(r == 0, "conv_igemm: cuTensorMapEncodeTiled(Y) failed with %d", r);
+        if (p.res_mode == 1) r = encode_out(&tmR, d->r0, d->r0_pitch, d->r0_coff);
+        if (p.res_mode == 2) r = encode_out(&tmR, d->r1, d->r1_pitch, d->r1_coff);
+        CSBSR_REQUIRE(r == 0, "conv_igemm: cuTensorMapEncodeTiled(R) failed with %d", r);
+    }
+
+    const int smem_bytes = stages * stage_bytes + staging_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
     static int smem_attr_set = 0;
     if (smem_attr_set < smem_bytes) {
         CSBSR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -638,7 +935,7 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
         smem_attr_set = kSmemBudget;
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+    conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmY, tmR, p);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
