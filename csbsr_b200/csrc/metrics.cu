@@ -15,6 +15,7 @@
 //   cumsum, pairwise sum with 8 accumulators / blocks of 128, fp64 sqrt) so the percentile index and
 //   the value are identical to the reference's, bit for bit.
 #include <math_constants.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/csbsr_b200.h"
 
@@ -328,13 +329,149 @@ __device__ void replay_list(const unsigned int* keys, int n, double pct, double*
     out[1] = wsum / total;
 }
 
+// Block-parallel replay with the same results as replay_list:
+//  * the two pairwise sums are evaluated leaf by leaf (<= 128 elements each, one thread per leaf, numpy's own
+//    8-accumulator order inside a leaf) and combined by one thread in numpy's recursion order -> bit-identical;
+//  * the percentile index is located with exact integer prefix counts.  The sequential fp64 cumsum c_i differs from
+//    the exactly rounded value e_i = n1*diag + n2 + n3*2diag by at most n*2^-53 relative (< 3e-11 for n <= 2^18), so
+//    whenever e_i/total is further than 1e-9 from the percentile on both sides of the crossing the float predicate
+//    `c_i/total >= pct` is decided; otherwise (a near tie, e.g. all-equal surfels and an even count) one thread falls
+//    back to the literal sequential replay.
+struct ReplayAux {
+    int* leaf_start;     // [max_leaves]
+    int* leaf_n;         // [max_leaves]
+    double* leaf_l;      // [max_leaves] pairwise sums of lengths
+    double* leaf_w;      // [max_leaves] pairwise sums of dist*length
+    int* cnt;            // [blockDim][3] class counts per thread chunk
+    int* misc;           // [4]: n_leaves, found index, flags
+    double* dres;        // [2]: total, wsum
+};
+
+__device__ void replay_parallel(const unsigned int* keys, int n, double pct, double* out, ReplayAux ax) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // ---- leaves of numpy's pairwise recursion, in left-to-right order (thread 0)
+    if (tid == 0) {
+        int st_s[24], st_n[24], sp = 0, nl = 0;
+        st_s[0] = 0; st_n[0] = n;
+        while (sp >= 0) {
+            const int cs = st_s[sp], cn = st_n[sp];
+            --sp;
+            if (cn <= 128) {
+                ax.leaf_start[nl] = cs; ax.leaf_n[nl] = cn; ++nl;
+            } else {
+                int n2 = cn / 2;
+                n2 -= n2 % 8;
+                ++sp; st_s[sp] = cs + n2; st_n[sp] = cn - n2;      // right pushed first so the left is popped first
+                ++sp; st_s[sp] = cs; st_n[sp] = n2;
+            }
+        }
+        ax.misc[0] = nl;
+        ax.misc[1] = 0x7FFFFFFF;
+    }
+    __syncthreads();
+    const int nl = ax.misc[0];
+    for (int i = tid; i < nl; i += nt) {
+        ax.leaf_l[i] = pairwise_leaf<false>(keys, ax.leaf_start[i], ax.leaf_n[i]);
+        ax.leaf_w[i] = pairwise_leaf<true>(keys, ax.leaf_start[i], ax.leaf_n[i]);
+    }
+    // ---- class counts per contiguous chunk
+    const int L = (n + nt - 1) / nt;
+    const int c0 = min(n, tid * L), c1 = min(n, c0 + L);
+    int k1 = 0, k2 = 0, k3 = 0;
+    for (int i = c0; i < c1; ++i) {
+        const int c = keys[i] & 3;
+        k1 += (c == 1); k2 += (c == 2); k3 += (c == 3);
+    }
+    ax.cnt[tid * 3] = k1; ax.cnt[tid * 3 + 1] = k2; ax.cnt[tid * 3 + 2] = k3;
+    __syncthreads();
+    if (tid == 0) {
+        // combine the leaf sums in recursion order: post-order over the same tree
+        for (int pass = 0; pass < 2; ++pass) {
+            const double* leaf = pass == 0 ? ax.leaf_l : ax.leaf_w;
+            int st_n[24], st_state[24], sp = 0, li = 0;
+            double st_left[24], ret = 0.0;
+            st_n[0] = n; st_state[0] = 0;
+            while (sp >= 0) {
+                const int cn = st_n[sp];
+                if (cn <= 128) { ret = leaf[li++]; --sp; continue; }
+                int n2 = cn / 2;
+                n2 -= n2 % 8;
+                if (st_state[sp] == 0) { st_state[sp] = 1; ++sp; st_n[sp] = n2; st_state[sp] = 0; }
+                else if (st_state[sp] == 1) { st_left[sp] = ret; st_state[sp] = 2; ++sp; st_n[sp] = cn - n2; st_state[sp] = 0; }
+                else { ret = st_left[sp] + ret; --sp; }
+            }
+            ax.dres[pass] = ret;
+        }
+        // exclusive prefix of the chunk counts
+        int a1 = 0, a2 = 0, a3 = 0;
+        for (int t = 0; t < nt; ++t) {
+            const int b1 = ax.cnt[t * 3], b2 = ax.cnt[t * 3 + 1], b3 = ax.cnt[t * 3 + 2];
+            ax.cnt[t * 3] = a1; ax.cnt[t * 3 + 1] = a2; ax.cnt[t * 3 + 2] = a3;
+            a1 += b1; a2 += b2; a3 += b3;
+        }
+    }
+    __syncthreads();
+    const double total = ax.dres[0];
+    const double diag = 0.5 * 1.4142135623730951;
+    const double margin = 1e-9;
+    k1 = ax.cnt[tid * 3]; k2 = ax.cnt[tid * 3 + 1]; k3 = ax.cnt[tid * 3 + 2];
+    for (int i = c0; i < c1; ++i) {
+        const int c = keys[i] & 3;
+        k1 += (c == 1); k2 += (c == 2); k3 += (c == 3);
+        const double e = (static_cast<double>(k1) + 2.0 * static_cast<double>(k3)) * diag + static_cast<double>(k2);
+        if (e / total >= pct - margin) {
+            atomicMin(&ax.misc[1], i);
+            break;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int idx = ax.misc[1];
+        bool decided = false;
+        if (idx < n) {
+            // recompute e at idx from the owning chunk
+            const int t = idx / L;
+            int q1 = ax.cnt[t * 3], q2 = ax.cnt[t * 3 + 1], q3 = ax.cnt[t * 3 + 2];
+            for (int i = t * L; i <= idx; ++i) {
+                const int c = keys[i] & 3;
+                q1 += (c == 1); q2 += (c == 2); q3 += (c == 3);
+            }
+            const double e = (static_cast<double>(q1) + 2.0 * static_cast<double>(q3)) * diag + static_cast<double>(q2);
+            decided = (e / total >= pct + margin);
+        }
+        if (decided) {
+            out[0] = key_dist(keys[idx]);
+        } else {                                       // near tie (or nothing found): literal sequential replay
+            double c = 0.0;
+            idx = n;
+            for (int i = 0; i < n; ++i) {
+                c += len_value(keys[i] & 3);
+                if (c / total >= pct) { idx = i; break; }
+            }
+            if (idx > n - 1) idx = n - 1;
+            out[0] = key_dist(keys[idx]);
+        }
+        out[1] = ax.dres[1] / total;
+    }
+}
+
 // bitonic sort of one list in shared memory + replay. CAP = power of two capacity; lists longer than CAP or
 // not longer than MINN are handled by another instantiation (the block exits at once).
 template <int CAP, int MINN>
 __global__ void sort_replay_kernel(const unsigned int* __restrict__ keys_g2p, const unsigned int* __restrict__ keys_p2g,
                                    const int* __restrict__ count_gt, const int* __restrict__ count_pred, int cap,
-                                   double pct, double* __restrict__ res) {
-    extern __shared__ unsigned int sk[];
+                                   double pct, double* __restrict__ res, int force_sequential) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    unsigned int* sk = reinterpret_cast<unsigned int*>(smem_dyn);
+    constexpr int kMaxLeaves = CAP / 64 + 2;
+    ReplayAux ax;
+    ax.leaf_l = reinterpret_cast<double*>(smem_dyn + static_cast<size_t>(CAP) * 4);
+    ax.leaf_w = ax.leaf_l + kMaxLeaves;
+    ax.dres = ax.leaf_w + kMaxLeaves;
+    ax.leaf_start = reinterpret_cast<int*>(ax.dres + 2);
+    ax.leaf_n = ax.leaf_start + kMaxLeaves;
+    ax.cnt = ax.leaf_n + kMaxLeaves;
+    ax.misc = ax.cnt + 3 * 1024;
     const int bt = blockIdx.x >> 1;
     const int dir = blockIdx.x & 1;                    // 0: gt->pred, 1: pred->gt
     const int b = bt / kNumThr;
@@ -360,7 +497,17 @@ __global__ void sort_replay_kernel(const unsigned int* __restrict__ keys_g2p, co
             __syncthreads();
         }
     }
-    if (threadIdx.x == 0) replay_list(sk, n, pct, res + (static_cast<size_t>(bt) * 2 + dir) * 2);
+    double* out = res + (static_cast<size_t>(bt) * 2 + dir) * 2;
+    if (force_sequential) {
+        if (threadIdx.x == 0) replay_list(sk, n, pct, out);
+    } else {
+        replay_parallel(sk, n, pct, out, ax);
+    }
+}
+
+template <int CAP>
+constexpr size_t sort_smem_bytes() {
+    return static_cast<size_t>(CAP) * 4 + (CAP / 64 + 2) * (8 + 8 + 4 + 4) + 16 + 3 * 1024 * 4 + 16;
 }
 
 // lists that do not fit in shared memory: bitonic sort in place in global memory by one block (rare, slow path)
@@ -504,13 +651,15 @@ extern "C" int csbsr_seg_metrics(const float* prob, const float* mask, const flo
         static bool attr_set = false;
         if (!attr_set) {
             CSBSR_CHECK_CUDA(cudaFuncSetAttribute(sort_replay_kernel<32768, 4096>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  static_cast<int>(sort_smem_bytes<32768>())));
             attr_set = true;
         }
-        sort_replay_kernel<4096, 0><<<lists, 256, 4096 * 4, stream>>>(m.keys_g2p, m.keys_p2g, m.count_gt, m.count_pred,
-                                                                      m.cap, pct, m.res);
-        sort_replay_kernel<32768, 4096><<<lists, 1024, 32768 * 4, stream>>>(m.keys_g2p, m.keys_p2g, m.count_gt,
-                                                                            m.count_pred, m.cap, pct, m.res);
+        const int force_seq = getenv("CSBSR_METRICS_SEQUENTIAL") ? 1 : 0;
+        sort_replay_kernel<4096, 0><<<lists, 256, sort_smem_bytes<4096>(), stream>>>(
+            m.keys_g2p, m.keys_p2g, m.count_gt, m.count_pred, m.cap, pct, m.res, force_seq);
+        sort_replay_kernel<32768, 4096><<<lists, 1024, sort_smem_bytes<32768>(), stream>>>(
+            m.keys_g2p, m.keys_p2g, m.count_gt, m.count_pred, m.cap, pct, m.res, force_seq);
         sort_replay_global_kernel<<<lists, 1024, 0, stream>>>(m.keys_g2p, m.keys_p2g, m.count_gt, m.count_pred, m.cap,
                                                               m.cap, 32768, pct, m.res);
         finalize_kernel<<<(b * kNumThr + 127) / 128, 128, 0, stream>>>(m.count_gt, m.count_pred, m.res, hd, msd,

@@ -35,34 +35,49 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
 __global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int H, int W,
                                 int OH, int OW, int R, int S, int stride, int pad, int pitch, int cwrite,
                                 const float* __restrict__ mean, const float* __restrict__ rstd, int clamp01) {
-    const size_t total = static_cast<size_t>(N) * OH * OW * (cwrite / 8);
+    // lut[k] = (dy << 16) | (dx << 8) | c for the K = R*S*C gathered channels (no div/mod in the hot loop)
+    __shared__ int lut[256];
     const int K = R * S * C;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int c = k % C, rs = k / C;
+        lut[k] = ((rs / S) << 16) | ((rs % S) << 8) | c;
+    }
+    __syncthreads();
+    const int G = cwrite / 8;
+    const size_t total = static_cast<size_t>(N) * OH * OW * G;
+    const size_t plane = static_cast<size_t>(H) * W;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i % (cwrite / 8));
-        const size_t pix = i / (cwrite / 8);
-        const int ow = static_cast<int>(pix % OW);
-        const int oh = static_cast<int>((pix / OW) % OH);
-        const int n = static_cast<int>(pix / (static_cast<size_t>(OW) * OH));
-        __align__(16) __nv_bfloat16 o[8];
+        const int g = static_cast<int>(i % G);
+        const size_t pix = i / G;
+        uint4 out = make_uint4(0, 0, 0, 0);
+        if (g * 8 < K) {
+            const int ow = static_cast<int>(pix % OW);
+            const int oh = static_cast<int>((pix / OW) % OH);
+            const int n = static_cast<int>(pix / (static_cast<size_t>(OW) * OH));
+            const int ih0 = oh * stride - pad, iw0 = ow * stride - pad;
+            const float* xn = x + static_cast<size_t>(n) * C * plane;
+            float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = g * 8 + j;
-            float v = 0.f;
-            if (k < K) {
-                const int c = k % C;
-                const int rs = k / C;
-                const int ih = oh * stride + (rs / S) - pad;
-                const int iw = ow * stride + (rs % S) - pad;
-                if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-                    v = x[((static_cast<size_t>(n) * C + c) * H + ih) * W + iw];
-                    if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
-                    if (mean) v = (v - mean[n * C + c]) * rstd[n * C + c];
+            for (int j = 0; j < 8; ++j) {
+                const int k = g * 8 + j;
+                float val = 0.f;
+                if (k < K) {
+                    const int e = lut[k];
+                    const int ih = ih0 + (e >> 16), iw = iw0 + ((e >> 8) & 0xFF), c = e & 0xFF;
+                    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+                        val = xn[c * plane + static_cast<size_t>(ih) * W + iw];
+                        if (clamp01) val = fminf(fmaxf(val, 0.f), 1.f);
+                        if (mean) val = (val - mean[n * C + c]) * rstd[n * C + c];
+                    }
                 }
+                v[j] = val;
             }
-            o[j] = __float2bfloat16(v);
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
         }
-        *reinterpret_cast<uint4*>(y + pix * pitch + g * 8) = *reinterpret_cast<const uint4*>(o);
+        *reinterpret_cast<uint4*>(y + pix * pitch + g * 8) = out;
     }
 }
 
@@ -320,29 +335,38 @@ __global__ void maxpool3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
 // adaptive average pool to SxS (pspnet.py:32): bin i covers [floor(i*H/S), ceil((i+1)*H/S))
 __global__ void adaptive_avgpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N,
                                         int H, int W, int S, int C, int xp, int xo, int yp, int yo) {
-    const int G = C / 8;
-    const size_t total = static_cast<size_t>(N) * S * S * G;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i % G);
-        const size_t pix = i / G;
-        const int ow = static_cast<int>(pix % S);
-        const int oh = static_cast<int>((pix / S) % S);
-        const int n = static_cast<int>(pix / (static_cast<size_t>(S) * S));
-        const int h0 = (oh * H) / S, h1 = ((oh + 1) * H + S - 1) / S;
-        const int w0 = (ow * W) / S, w1 = ((ow + 1) * W + S - 1) / S;
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int ih = h0; ih < h1; ++ih)
-            for (int iw = w0; iw < w1; ++iw) {
-                float f[8];
-                unpack8(*reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + ih) * W + iw) * xp + xo + g * 8), f);
+    // grid: (S*S bins, N, channel slabs of 32 groups); block 256 = 32 channel groups (8 ch each) x 8 pixel lanes
+    __shared__ float red[8][32][8];
+    const int bin = blockIdx.x, n = blockIdx.y;
+    const int g = blockIdx.z * 32 + (threadIdx.x & 31);
+    const int pl = threadIdx.x >> 5;
+    const int oh = bin / S, ow = bin % S;
+    const int h0 = (oh * H) / S, h1 = ((oh + 1) * H + S - 1) / S;
+    const int w0 = (ow * W) / S, w1 = ((ow + 1) * W + S - 1) / S;
+    const int bw = w1 - w0, npix = (h1 - h0) * bw;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (g * 8 < C) {
+        for (int pidx = pl; pidx < npix; pidx += 8) {
+            const int ih = h0 + pidx / bw, iw = w0 + pidx % bw;
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + ih) * W + iw) * xp + xo + g * 8), f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += f[j];
-            }
-        const float inv = 1.f / static_cast<float>((h1 - h0) * (w1 - w0));
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] *= inv;
-        *reinterpret_cast<uint4*>(y + pix * yp + yo + g * 8) = pack8(acc);
+    for (int j = 0; j < 8; ++j) red[pl][threadIdx.x & 31][j] = acc[j];
+    __syncthreads();
+    if (pl == 0 && g * 8 < C) {
+        const float inv = 1.f / static_cast<float>(npix);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = 0.f;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) t += red[l][threadIdx.x & 31][j];
+            acc[j] = t * inv;
+        }
+        *reinterpret_cast<uint4*>(y + ((static_cast<size_t>(n) * S + oh) * S + ow) * yp + yo + g * 8) = pack8(acc);
     }
 }
 
@@ -429,6 +453,7 @@ extern "C" int csbsr_patchify(const float* x, void* y, int n, int c, int h, int 
     CSBSR_REQUIRE(x && y && n > 0 && cwrite % 8 == 0 && y_pitch % 8 == 0 && cwrite >= r * s * c && cwrite <= y_pitch,
                   "patchify: bad arguments (cwrite=%d, need >= %d)", cwrite, r * s * c);
     CSBSR_REQUIRE((mean == nullptr) == (rstd == nullptr), "patchify: mean/rstd must come together");
+    CSBSR_REQUIRE(r * s * c <= 256 && r <= 255 && s <= 255 && c <= 255, "patchify: at most 256 gathered channels");
     const size_t total = static_cast<size_t>(n) * oh * ow * (cwrite / 8);
     patchify_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, c, h, w,
                                                                      oh, ow, r, s, stride, pad, y_pitch, cwrite, mean,
@@ -532,8 +557,8 @@ extern "C" int csbsr_adaptive_avgpool_nhwc(const void* x, void* y, int n, int h,
     CSBSR_REQUIRE(x && y && s > 0 && c % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && x_coff % 8 == 0 &&
                       y_coff % 8 == 0,
                   "adaptive_avgpool: bad arguments");
-    const size_t total = static_cast<size_t>(n) * s * s * (c / 8);
-    adaptive_avgpool_kernel<<<grid_for(total, 128), 128, 0, STREAM(stream)>>>(
+    dim3 grid(s * s, n, (c / 8 + 31) / 32);
+    adaptive_avgpool_kernel<<<grid, 256, 0, STREAM(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), n, h, w, s, c, x_pitch, x_coff,
         y_pitch, y_coff);
     CSBSR_CHECK_CUDA(cudaGetLastError());

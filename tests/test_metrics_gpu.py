@@ -52,6 +52,36 @@ def test_matches_oracle_bit_exact(B, H, W, seed, noise):
         assert np.array_equal(r["msd"], msd), np.argwhere(r["msd"] != msd)[:5]
 
 
+def test_large_lists_and_sequential_replay_agree():
+    """Salt-and-pepper probabilities: tens of thousands of border corners per list (32768-key shared-memory sort and
+    the global-memory fallback), checked against the oracle; the block-parallel replay must equal the literal
+    sequential one (CSBSR_METRICS_SEQUENTIAL=1)."""
+    from oracle import metrics_ref as M
+    rng = np.random.default_rng(9)
+    H, W = 200, 216
+    prob = rng.random((1, 1, H, W)).astype(np.float32)
+    mask = (rng.random((1, 1, H, W)) < 0.3).astype(np.float32)
+    r = _run(prob, mask, 50)
+    os.environ["CSBSR_METRICS_SEQUENTIAL"] = "1"
+    try:
+        r_seq = _run(prob, mask, 50)
+    finally:
+        del os.environ["CSBSR_METRICS_SEQUENTIAL"]
+    assert np.array_equal(r["hd"], r_seq["hd"]) and np.array_equal(r["msd"], r_seq["msd"])
+    sel = [0, 24, 49, 74, 98]
+    hd, msd = M.distance_metrics(prob, mask, 50)
+    assert np.array_equal(r["hd"][:, sel], hd[:, sel]) and np.array_equal(r["msd"][:, sel], msd[:, sel])
+    assert np.array_equal(r["hd"], hd) and np.array_equal(r["msd"], msd)
+    prob2, mask2 = _case(2, 96, 128, 5, 0.1)
+    a = _run(prob2, mask2, 95)
+    os.environ["CSBSR_METRICS_SEQUENTIAL"] = "1"
+    try:
+        b = _run(prob2, mask2, 95)
+    finally:
+        del os.environ["CSBSR_METRICS_SEQUENTIAL"]
+    assert np.array_equal(a["hd"], b["hd"]) and np.array_equal(a["msd"], b["msd"])
+
+
 def test_edge_cases():
     from oracle import metrics_ref as M
     H, W = 24, 40
