@@ -21,12 +21,33 @@ static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;                  // bf16 elements = 128 bytes = one swizzle row
 static constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
 static constexpr int kMaxStages = 8;
-static constexpr int kEpiWarps = 8;                 // 2 warps per TMEM lane quarter, interleaved 16-column units
+static constexpr int kEpiWarps = 16;                // 4 warps per TMEM lane quarter, each a share of the 16-column units
 static constexpr int kThreads = 128 + 32 * kEpiWarps;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4.. epilogue
 static constexpr int kTmemCols = 512;
 static constexpr int kSmemBudget = 227 * 1024;
 
+// division by a runtime constant without the ~25-instruction integer divide: q = umulhi(a, mul) >> shr (exact for a < 2^31)
+struct FastDiv {
+    uint32_t mul, shr, div;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.div = d;
+    if (d == 1) { f.mul = 0; f.shr = 0; return f; }
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;                      // ceil(log2 d)
+    const uint64_t m = ((static_cast<uint64_t>(1) << (32 + l - 1)) + d - 1) / d;   // ceil(2^(31+l) / d) < 2^32 for a < 2^31
+    f.mul = static_cast<uint32_t>(m);
+    f.shr = l - 1;
+    return f;
+}
+__device__ __forceinline__ void fast_divmod(uint32_t a, const FastDiv& f, uint32_t& q, uint32_t& r) {
+    q = f.div == 1 ? a : (__umulhi(a, f.mul) >> f.shr);
+    r = a - q * f.div;
+}
+
 struct ConvKParams {
+    FastDiv fd_ntiles, fd_nphases, fd_tiles_per_img, fd_tiles_w;
     // tiles
     int tiles_h, tiles_w, m_tiles, n_tiles, nphases, total_tiles;
     int TH, TW, block_n, kchunks, ntaps, stride, stages;
@@ -42,6 +63,7 @@ struct ConvKParams {
     const __nv_bfloat16* r1;
     const float* r32;
     int* err_flag;
+    long long* trace;
     int G, ngroups, dstep, a_stage_bytes;   // tap groups: G taps sharing dw, dh = dh0 + j*dstep, one A box per group
     int staged;          // 1: epilogue through swizzled smem panels, residual via TMA load, output via TMA store
     int res_mode;        // staged only: 0 none, 1 pre-activation add (r0), 2 post-activation add/sub (r1)
@@ -49,6 +71,19 @@ struct ConvKParams {
     int16_t widx[CSBSR_MAX_TAPS];
     int8_t ooh[CSBSR_MAX_PHASES], oow[CSBSR_MAX_PHASES];
 };
+
+// tile index -> (n tile, phase, image, first output row / column); tiles are ordered n fastest, then phase, then m
+__device__ __forceinline__ void decode_tile(const ConvKParams& p, int tile, int& nt, int& ph, int& img, int& oh0, int& ow0) {
+    uint32_t rest, mt, tr, a, b, c, d2;
+    fast_divmod(static_cast<uint32_t>(tile), p.fd_ntiles, rest, a);
+    fast_divmod(rest, p.fd_nphases, mt, b);
+    fast_divmod(mt, p.fd_tiles_per_img, c, tr);
+    uint32_t trh;
+    fast_divmod(tr, p.fd_tiles_w, trh, d2);
+    nt = static_cast<int>(a); ph = static_cast<int>(b); img = static_cast<int>(c);
+    oh0 = static_cast<int>(trh) * p.TH;
+    ow0 = static_cast<int>(d2) * p.TW;
+}
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -88,6 +123,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
             asm volatile("trap;");
         }
     }
+}
+// elect.sync: exactly one lane of the (converged) warp gets a true predicate.  Branching on it tells the compiler that
+// a single thread issues the following uniform-datapath instructions (TMA / tcgen05), so they are emitted once instead
+// of inside an ELECT / branch loop over the active lanes.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, %1;\n"
+        "@px mov.s32 %0, 1;\n"
+        "}\n"
+        : "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -157,6 +208,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// same instruction with the two 64-bit smem descriptors assembled from a per-operand low word and the shared high word
+// (keeps the single issuing thread's instruction count per MMA minimal)
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -240,7 +307,7 @@ __device__ __forceinline__ void epilogue_bf16(const ConvKParams& p, const EpiRow
     const __nv_bfloat16* r1p = p.r1 ? p.r1 + er.pix * p.r1_pitch + p.r1_coff : nullptr;
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + er.pix * p.y_pitch + p.y_coff;
     const float r1s = p.r1_sign;
-    for (int u = u0; u < units; u += 2) {
+    for (int u = u0; u < units; u += kEpiWarps / 4) {
         const int c0 = c_base + u * 16;
         const bool on = er.valid && c0 < p.cout_store;
         uint4 q0[2], qm[2], q1[2];
@@ -356,7 +423,7 @@ template <int ACT>
 __device__ __forceinline__ void epilogue_units(const ConvKParams& p, const EpiRow& er, uint32_t taddr0, int c_base,
                                                int u0, int units) {
     const float slope = p.slope;
-    for (int u = u0; u < units; u += 2) {
+    for (int u = u0; u < units; u += kEpiWarps / 4) {
         const int c0 = c_base + u * 16;
         uint32_t v[16];
         __syncwarp();
@@ -413,10 +480,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_tile_bytes = p.block_n * kBlockK * 2;
     const int b_stage_bytes = p.G * b_tile_bytes;
+    const int b_total_bytes = p.stages * b_stage_bytes;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + p.stages * p.a_stage_bytes;
     const int n_panels = p.block_n >> 6;                      // staged epilogue: 64-channel panels per tile
-    uint8_t* smem_stage = smem_b + p.stages * b_stage_bytes;  // 2 sets x n_panels x 16 KB (staged epilogue only)
+    uint8_t* smem_stage = smem_b + b_total_bytes;             // 2 sets x n_panels x 16 KB (staged epilogue only)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage + (p.staged ? 2 * n_panels * kATileBytes : 0));
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;
@@ -451,39 +519,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    // The CTA allocates all 512 TMEM columns, so the allocation starts at column 0 / lane 0.  Using the literal 0
+    // keeps every TMEM address warp-uniform for the compiler: with a value loaded from shared memory each
+    // tcgen05.mma was wrapped in an ELECT / R2UR / branch "waterfall" costing ~75 cycles per instruction.
+    if (*tmem_ptr_smem != 0u) {
+        if (p.err_flag) atomicExch(p.err_flag, 7);
+        asm volatile("trap;");
+    }
+    constexpr uint32_t tmem_base = 0u;
 
     const int kblocks = p.ngroups * p.kchunks;
-    const int tiles_per_img = p.tiles_h * p.tiles_w;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+        {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = p.a_stage_bytes + b_stage_bytes;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles;
-                const int rest = tile / p.n_tiles;
-                const int ph = rest % p.nphases;
-                const int mt = rest / p.nphases;
-                const int img = mt / tiles_per_img;
-                const int tr = mt % tiles_per_img;
-                const int oh0 = (tr / p.tiles_w) * p.TH;
-                const int ow0 = (tr % p.tiles_w) * p.TW;
+                int nt, ph, img, oh0, ow0;
+                decode_tile(p, tile, nt, ph, img, oh0, ow0);
+                if (p.trace && blockIdx.x == 0 && lane == 0 && tile / gridDim.x < 256) p.trace[0 * 256 + tile / gridDim.x] = clock64();
                 for (int g = 0; g < p.ngroups; ++g) {
                     const int gi = (ph * p.ngroups + g) * p.G;          // first tap of the group
                     const int ih0 = oh0 * p.stride + p.dh[gi];
                     const int iw0 = ow0 * p.stride + p.dw[gi];
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 1);
-                        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                        // one A box covers the G vertically shifted taps of the group (rows TH + (G-1)*dstep)
-                        tma_load_4d(smem_u32(smem_a + stage * p.a_stage_bytes), &tmA, &full_bar[stage], kc * kBlockK,
-                                    iw0, ih0, img);
-                        for (int j = 0; j < p.G; ++j)
-                            tma_load_3d(smem_u32(smem_b + stage * b_stage_bytes + j * b_tile_bytes), &tmB,
-                                        &full_bar[stage], kc * kBlockK, nt * p.block_n, p.widx[gi + j]);
+                        if (elect_one_sync()) {
+                            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                            // one A box covers the G vertically shifted taps of the group (rows TH + (G-1)*dstep)
+                            tma_load_4d(smem_u32(smem_a + stage * p.a_stage_bytes), &tmA, &full_bar[stage],
+                                        kc * kBlockK, iw0, ih0, img);
+                            for (int j = 0; j < p.G; ++j)
+                                tma_load_3d(smem_u32(smem_b + stage * b_stage_bytes + j * b_tile_bytes), &tmB,
+                                            &full_bar[stage], kc * kBlockK, nt * p.block_n, p.widx[gi + j]);
+                        }
+                        __syncwarp();
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1u;
@@ -493,40 +565,64 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+        {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.block_n >> 3) << 17) |
                                    (static_cast<uint32_t>(kBlockM >> 4) << 24);
+            // descriptor words: lo = (smem address >> 4) | LBO(1) << 16 ; hi = SBO(1024 B) | version 1 | 128B swizzle
+            const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t a_stage16 = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
+            const uint32_t b_stage16 = static_cast<uint32_t>(b_stage_bytes) >> 4;
+            const uint32_t a_shift16 = static_cast<uint32_t>(p.dstep * p.TW * 128) >> 4;   // vertical tap step inside the A box
+            const uint32_t b_tile16 = static_cast<uint32_t>(b_tile_bytes) >> 4;
+            const int G = p.G;
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, a_lo = a_lo0, b_lo = b_lo0;
             int local = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
                 const int as = local & 1;
                 const uint32_t aphase = (local >> 1) & 1;
                 mbar_wait(&tmem_empty[as], aphase ^ 1u, p.err_flag, 2);
                 tcgen05_fence_after();
+                if (p.trace && blockIdx.x == 0 && lane == 0 && local < 256) p.trace[1 * 256 + local] = clock64();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * 256);
+                uint32_t acc = 0;
+                long long wait_cyc = 0;
                 for (int kb = 0; kb < kblocks; ++kb) {
+                    const long long tw0 = p.trace ? clock64() : 0;
                     mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
                     tcgen05_fence_after();
-                    const uint32_t a_base = smem_u32(smem_a + stage * p.a_stage_bytes);
-                    const uint32_t b_base = smem_u32(smem_b + stage * b_stage_bytes);
-                    const uint32_t a_shift = static_cast<uint32_t>(p.dstep * p.TW * 128);   // bytes per vertical tap step
-                    for (int j = 0; j < p.G; ++j) {
-                        const uint64_t adesc = make_smem_desc(a_base + j * a_shift);
-                        const uint64_t bdesc = make_smem_desc(b_base + j * b_tile_bytes);
-#pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
+                    if (p.trace) wait_cyc += clock64() - tw0;
+                    if (elect_one_sync()) {
+                        uint32_t ja = a_lo, jb = b_lo;
+                        for (int j = 0; j < G; ++j) {
                             // +32 bytes per K=16 step inside the 128B swizzle row -> +2 in the >>4 address field
-                            umma_bf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
-                                      idesc, (kb > 0 || j > 0 || k > 0) ? 1u : 0u);
+                            umma_bf16_lohi(tmem_d, ja, jb, desc_hi, idesc, acc);
+                            umma_bf16_lohi(tmem_d, ja + 2, jb + 2, desc_hi, idesc, 1u);
+                            umma_bf16_lohi(tmem_d, ja + 4, jb + 4, desc_hi, idesc, 1u);
+                            umma_bf16_lohi(tmem_d, ja + 6, jb + 6, desc_hi, idesc, 1u);
+                            acc = 1u;
+                            ja += a_shift16;
+                            jb += b_tile16;
                         }
+                        umma_commit(&empty_bar[stage]);      // frees the smem slot when these MMAs retire
+                        if (kb == kblocks - 1) umma_commit(&tmem_full[as]);
                     }
-                    umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
-                    if (kb == kblocks - 1) umma_commit(&tmem_full[as]);
+                    __syncwarp();
+                    acc = 1u;
+                    if (kb == kblocks - 1 && p.trace && blockIdx.x == 0 && lane == 0 && local < 256) {
+                        p.trace[2 * 256 + local] = wait_cyc;
+                        p.trace[3 * 256 + local] = clock64();
+                    }
+                    a_lo += a_stage16;
+                    b_lo += b_stage16;
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1u;
+                        a_lo = a_lo0;
+                        b_lo = b_lo0;
                     }
                 }
             }
@@ -540,18 +636,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // ---------------- staged epilogue (see epilogue_staged) ----------------
             const bool leader = (warp == 4 && lane == 0);
             const int units = p.block_n >> 4;
-            const int half = (warp - 4) >> 2;
-            const int u_begin = half ? (units >> 1) : 0, u_end = half ? units : (units >> 1);
+            // the kEpiWarps/4 warps of a lane quarter split the 16-column units into contiguous shares
+            const int share = (warp - 4) >> 2, nshare = kEpiWarps / 4;
+            const int u_begin = (units * share) / nshare, u_end = (units * (share + 1)) / nshare;
             const uint32_t res_bytes = static_cast<uint32_t>(n_panels) * kATileBytes;
             auto tile_coords = [&](int tile, int& nt, int& ph, int& img, int& oh0, int& ow0) {
-                nt = tile % p.n_tiles;
-                const int rest = tile / p.n_tiles;
-                ph = rest % p.nphases;
-                const int mt = rest / p.nphases;
-                img = mt / tiles_per_img;
-                const int tr = mt % tiles_per_img;
-                oh0 = (tr / p.tiles_w) * p.TH;
-                ow0 = (tr % p.tiles_w) * p.TW;
+                decode_tile(p, tile, nt, ph, img, oh0, ow0);
             };
             auto load_residual = [&](int tile, int set) {
                 int nt, ph, img, oh0, ow0;
@@ -595,6 +685,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                                : nullptr;
                 mbar_wait(&tmem_full[as], aphase, p.err_flag, 4);
                 tcgen05_fence_after();
+                if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[4 * 256 + local] = clock64();
                 const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * 256);
                 const int c_base = nt * p.block_n;
                 switch (p.act) {
@@ -616,6 +707,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         else tma_store_5d(&tmY, src, c, p.oow[ph], ow0, p.ooh[ph], img * p.OH + oh0);
                     }
                     tma_store_commit();
+                    if (p.trace && blockIdx.x == 0 && local < 256) p.trace[5 * 256 + local] = clock64();
                 }
             }
             if (leader) tma_store_wait_read<0>();
@@ -624,14 +716,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
             const int as = local & 1;
             const uint32_t aphase = (local >> 1) & 1;
-            const int nt = tile % p.n_tiles;
-            const int rest = tile / p.n_tiles;
-            const int ph = rest % p.nphases;
-            const int mt = rest / p.nphases;
-            const int img = mt / tiles_per_img;
-            const int tr = mt % tiles_per_img;
-            const int oh = (tr / p.tiles_w) * p.TH + th;
-            const int ow = (tr % p.tiles_w) * p.TW + tw;
+            int nt, ph, img, oh0d, ow0d;
+            decode_tile(p, tile, nt, ph, img, oh0d, ow0d);
+            const int oh = oh0d + th;
+            const int ow = ow0d + tw;
             const bool valid = (oh < p.OH) && (ow < p.OW);
             const int oy = oh * p.os + p.ooh[ph];
             const int ox = ow * p.os + p.oow[ph];
@@ -699,7 +787,8 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-static int* g_err_flag = nullptr;   // device int, lazily allocated (one per process; diagnostic only)
+static int* g_err_flag = nullptr;
+static long long* g_trace = nullptr;   // debug timeline of CTA 0 (CSBSR_CONV_TRACE=1): [6][256] clock64 stamps   // device int, lazily allocated (one per process; diagnostic only)
 
 }  // namespace csbsr
 
@@ -768,71 +857,75 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     p.n_tiles = d->cout_pad / block_n;
     p.nphases = d->nphases;
     p.total_tiles = p.m_tiles * p.n_tiles * p.nphases;
+    p.fd_ntiles = make_fastdiv(p.n_tiles); p.fd_nphases = make_fastdiv(p.nphases);
+    p.fd_tiles_per_img = make_fastdiv(p.tiles_h * p.tiles_w); p.fd_tiles_w = make_fastdiv(p.tiles_w);
     p.kchunks = d->cin / kBlockK;
     p.ntaps = d->ntaps;
     p.stride = d->stride;
-    // ---- tap grouping: taps of one phase that share dw and whose dh form dh0 + j*dstep are served by ONE A box of
-    // TH + (G-1)*dstep rows (stride-1 convs only): cuts the L2 -> smem traffic of the A operand by G
+    // ---- tap grouping: taps of one phase that share dw and whose dh are dh0 + j*step (step a multiple of the conv
+    // stride) are served by ONE A box of TH + (G-1)*step/stride rows: cuts the L2 -> smem traffic of the A operand.
     int G = 1, ngroups = d->ntaps, dstep = 0;
     int8_t g_dh[CSBSR_MAX_TAPS], g_dw[CSBSR_MAX_TAPS];
     int16_t g_widx[CSBSR_MAX_TAPS];
     memcpy(g_dh, d->dh, sizeof(g_dh)); memcpy(g_dw, d->dw, sizeof(g_dw)); memcpy(g_widx, d->widx, sizeof(g_widx));
     const int staging_bytes = staged ? 2 * (block_n / 64) * kATileBytes : 0;
-    if (d->stride == 1 && d->ntaps >= 2 && !getenv("CSBSR_NO_GROUPING")) {
-        // distinct dw values of phase 0, in order of appearance
-        int dws[CSBSR_MAX_TAPS], ndw = 0;
-        for (int t = 0; t < d->ntaps; ++t) {
-            bool seen = false;
-            for (int i = 0; i < ndw; ++i) seen |= (dws[i] == d->dw[t]);
-            if (!seen) dws[ndw++] = d->dw[t];
-        }
-        const int cand = d->ntaps / ndw;
-        bool ok = cand >= 2 && cand * ndw == d->ntaps;
-        int step = 0;
-        int8_t n_dh[CSBSR_MAX_TAPS], n_dw[CSBSR_MAX_TAPS];
-        int16_t n_widx[CSBSR_MAX_TAPS];
+    const int smem_avail = kSmemBudget - 2048 - staging_bytes;
+    const int b_tile = block_n * kBlockK * 2;
+    int cand = 1, cand_groups = d->ntaps, cand_step = 0;
+    int8_t n_dh[CSBSR_MAX_TAPS], n_dw[CSBSR_MAX_TAPS];
+    int16_t n_widx[CSBSR_MAX_TAPS];
+    if (d->ntaps >= 2 && !getenv("CSBSR_NO_GROUPING")) {
+        const int st = d->stride;
+        auto key_of = [&](int t) { return d->dw[t] * 64 + (((d->dh[t] % st) + st) % st); };
+        bool ok = true;
+        int ng0 = -1, gsz = -1, step = 0;
         for (int ph = 0; ph < d->nphases && ok; ++ph) {
-            // per phase the dw set may differ (deconv): recompute it
-            int pd[CSBSR_MAX_TAPS], pn = 0;
+            int keys[CSBSR_MAX_TAPS], nk = 0;
             for (int t = 0; t < d->ntaps; ++t) {
-                const int v = d->dw[ph * d->ntaps + t];
+                const int k = key_of(ph * d->ntaps + t);
                 bool seen = false;
-                for (int i = 0; i < pn; ++i) seen |= (pd[i] == v);
-                if (!seen) pd[pn++] = v;
+                for (int i = 0; i < nk; ++i) seen |= (keys[i] == k);
+                if (!seen) keys[nk++] = k;
             }
-            if (pn != ndw) { ok = false; break; }
-            for (int gi = 0; gi < ndw && ok; ++gi) {
-                // taps of this phase with dw == pd[gi], sorted by dh
+            if (ng0 < 0) ng0 = nk;
+            if (nk != ng0 || d->ntaps % nk != 0) { ok = false; break; }
+            if (gsz < 0) gsz = d->ntaps / nk;
+            for (int gi = 0; gi < nk && ok; ++gi) {
                 int idx[CSBSR_MAX_TAPS], cnt = 0;
                 for (int t = 0; t < d->ntaps; ++t)
-                    if (d->dw[ph * d->ntaps + t] == pd[gi]) idx[cnt++] = ph * d->ntaps + t;
-                if (cnt != cand) { ok = false; break; }
+                    if (key_of(ph * d->ntaps + t) == keys[gi]) idx[cnt++] = ph * d->ntaps + t;
+                if (cnt != gsz) { ok = false; break; }
                 for (int a = 0; a < cnt; ++a)
-                    for (int b = a + 1; b < cnt; ++b)
-                        if (d->dh[idx[b]] < d->dh[idx[a]]) { int tmp = idx[a]; idx[a] = idx[b]; idx[b] = tmp; }
+                    for (int b2 = a + 1; b2 < cnt; ++b2)
+                        if (d->dh[idx[b2]] < d->dh[idx[a]]) { int tmp = idx[a]; idx[a] = idx[b2]; idx[b2] = tmp; }
                 for (int j = 0; j < cnt; ++j) {
                     if (j > 0) {
-                        const int st = d->dh[idx[j]] - d->dh[idx[j - 1]];
-                        if (st <= 0 || (step != 0 && st != step)) ok = false;
-                        step = st;
+                        const int sd = d->dh[idx[j]] - d->dh[idx[j - 1]];
+                        if (sd <= 0 || sd % st != 0 || (step != 0 && sd != step)) ok = false;
+                        step = sd;
                     }
-                    const int o = (ph * ndw + gi) * cand + j;
+                    const int o = (ph * nk + gi) * gsz + j;
                     n_dh[o] = d->dh[idx[j]]; n_dw[o] = d->dw[idx[j]]; n_widx[o] = d->widx[idx[j]];
                 }
             }
         }
-        if (ok) {
-            const int a_bytes = (THh + (cand - 1) * step) * TWh * 128;
-            const int st_bytes = a_bytes + cand * block_n * kBlockK * 2;
-            if ((THh + (cand - 1) * step) * 1 <= 256 && (kSmemBudget - 2048 - staging_bytes) / st_bytes >= 3) {
-                G = cand; ngroups = ndw; dstep = step;
-                memcpy(g_dh, n_dh, sizeof(g_dh)); memcpy(g_dw, n_dw, sizeof(g_dw)); memcpy(g_widx, n_widx, sizeof(g_widx));
-            }
+        if (ok && gsz >= 2 && (THh + (gsz - 1) * (step / st)) * st <= 256) {
+            cand = gsz; cand_groups = ng0; cand_step = step / st;
         }
     }
-    const int a_stage_bytes = (THh + (G - 1) * dstep) * TWh * 128;
-    const int stage_bytes = a_stage_bytes + G * block_n * kBlockK * 2;
-    int stages = (kSmemBudget - 2048 - staging_bytes) / stage_bytes;
+    int a_stage_bytes = kATileBytes, stages = 0;
+    {
+        // grouped taps when they leave >= 3 pipeline stages, else one tap per stage
+        const int a_b = (THh + (cand - 1) * cand_step) * TWh * 128;
+        const int st_g = cand > 1 ? smem_avail / (a_b + cand * b_tile) : 0;
+        if (cand > 1 && st_g >= 3) {
+            G = cand; ngroups = cand_groups; dstep = cand_step; a_stage_bytes = a_b; stages = st_g;
+            memcpy(g_dh, n_dh, sizeof(g_dh)); memcpy(g_dw, n_dw, sizeof(g_dw)); memcpy(g_widx, n_widx, sizeof(g_widx));
+        } else {
+            stages = smem_avail / (kATileBytes + b_tile);
+        }
+    }
+    const int stage_bytes = a_stage_bytes + G * b_tile;
     if (stages > kMaxStages) stages = kMaxStages;
     CSBSR_REQUIRE(stages >= 2, "conv_igemm: not enough shared memory for 2 stages");
     p.stages = stages;
@@ -863,6 +956,12 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
         CSBSR_CHECK_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
     }
     p.err_flag = g_err_flag;
+    p.trace = nullptr;
+    if (getenv("CSBSR_CONV_TRACE")) {
+        if (!g_trace) CSBSR_CHECK_CUDA(cudaMalloc(&g_trace, sizeof(long long) * 6 * 256));
+        CSBSR_CHECK_CUDA(cudaMemsetAsync(g_trace, 0, sizeof(long long) * 6 * 256, stream));
+        p.trace = g_trace;
+    }
 
     // ---- tensor maps
     CUtensorMap tmA, tmB;
@@ -938,4 +1037,10 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmY, tmR, p);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+// debug only (not part of the public header): copies the CTA-0 timeline recorded under CSBSR_CONV_TRACE=1
+extern "C" int csbsr_conv_trace_read(long long* host_out) {
+    if (!csbsr::g_trace) return -1;
+    return cudaMemcpy(host_out, csbsr::g_trace, sizeof(long long) * 6 * 256, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
