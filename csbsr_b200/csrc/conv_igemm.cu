@@ -187,7 +187,9 @@ __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
+__device__ __forceinline__ void team_bar_sync(int team) {          // named barriers 1 / 2: one per epilogue team
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(32 * kEpiWarps / 2) : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -510,7 +512,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], kEpiWarps);      // one arrive per epilogue warp
+            mbar_init(&tmem_empty[a], p.staged ? kEpiWarps / 2 : kEpiWarps);   // one arrive per draining warp
             mbar_init(&res_full[a], 1);
         }
         fence_barrier_init();
@@ -634,45 +636,42 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int th = row / p.TW, tw = row % p.TW;
         if (p.staged) {
             // ---------------- staged epilogue (see epilogue_staged) ----------------
-            const bool leader = (warp == 4 && lane == 0);
+            // Two teams of 8 warps; team t owns accumulator buffer t and staging set t and handles every other tile
+            // of this CTA, so two tile epilogues are in flight and their latencies overlap.
+            const int team = (warp - 4) >> 3;
+            const int wteam = (warp - 4) & 7;
+            const bool leader = (wteam == 0 && lane == 0);
             const int units = p.block_n >> 4;
-            // the kEpiWarps/4 warps of a lane quarter split the 16-column units into contiguous shares
-            const int share = (warp - 4) >> 2, nshare = kEpiWarps / 4;
-            const int u_begin = (units * share) / nshare, u_end = (units * (share + 1)) / nshare;
+            const int share = wteam >> 2;                   // the 2 warps of a lane quarter split the 16-column units
+            const int u_begin = (units * share) / 2, u_end = (units * (share + 1)) / 2;
             const uint32_t res_bytes = static_cast<uint32_t>(n_panels) * kATileBytes;
-            auto tile_coords = [&](int tile, int& nt, int& ph, int& img, int& oh0, int& ow0) {
-                decode_tile(p, tile, nt, ph, img, oh0, ow0);
-            };
-            auto load_residual = [&](int tile, int set) {
+            uint8_t* stage_set = smem_stage + team * n_panels * kATileBytes;
+            const int as = team;
+            auto load_residual = [&](int tile) {
                 int nt, ph, img, oh0, ow0;
-                tile_coords(tile, nt, ph, img, oh0, ow0);
-                mbar_arrive_expect_tx(&res_full[set], res_bytes);
+                decode_tile(p, tile, nt, ph, img, oh0, ow0);
+                mbar_arrive_expect_tx(&res_full[as], res_bytes);
                 for (int pn = 0; pn < n_panels; ++pn) {
-                    const uint32_t dst = smem_u32(smem_stage + (set * n_panels + pn) * kATileBytes);
+                    const uint32_t dst = smem_u32(stage_set + pn * kATileBytes);
                     const int c = nt * p.block_n + pn * 64;
-                    if (p.os == 1) tma_load_4d(dst, &tmR, &res_full[set], c, ow0, oh0, img);
-                    else tma_load_5d(dst, &tmR, &res_full[set], c, p.oow[ph], ow0, p.ooh[ph], img * p.OH + oh0);
+                    if (p.os == 1) tma_load_4d(dst, &tmR, &res_full[as], c, ow0, oh0, img);
+                    else tma_load_5d(dst, &tmR, &res_full[as], c, p.oow[ph], ow0, p.ooh[ph], img * p.OH + oh0);
                 }
             };
-            if (leader && p.res_mode && blockIdx.x < p.total_tiles) load_residual(blockIdx.x, 0);
-            int local = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-                const int as = local & 1;
-                const uint32_t aphase = (local >> 1) & 1;
+            const int stride_tiles = 2 * gridDim.x;
+            const int first_tile = blockIdx.x + team * gridDim.x;
+            if (leader && p.res_mode && first_tile < p.total_tiles) load_residual(first_tile);
+            int n_use = 0;                                  // how many tiles this team has processed
+            for (int tile = first_tile; tile < p.total_tiles; tile += stride_tiles, ++n_use) {
+                const uint32_t aphase = n_use & 1;
+                const int local = 2 * n_use + team;
                 int nt, ph, img, oh0, ow0;
-                tile_coords(tile, nt, ph, img, oh0, ow0);
-                uint8_t* stage_set = smem_stage + as * n_panels * kATileBytes;
+                decode_tile(p, tile, nt, ph, img, oh0, ow0);
                 if (p.res_mode) {
-                    // prefetch the next tile's residual into the other set (its last reader, the TMA store of the
-                    // previous tile, must have finished reading shared memory)
-                    if (leader && tile + gridDim.x < p.total_tiles) {
-                        tma_store_wait_read<0>();
-                        load_residual(tile + gridDim.x, as ^ 1);
-                    }
                     mbar_wait(&res_full[as], aphase, p.err_flag, 5);
                 } else {
-                    if (leader) tma_store_wait_read<1>();       // the store that last used this set is done reading
-                    epi_bar_sync();
+                    if (leader) tma_store_wait_read<0>();       // the previous store of this team is done reading the set
+                    team_bar_sync(team);
                 }
                 const int oy = (oh0 + th) * p.os + p.ooh[ph];
                 const int ox = (ow0 + tw) * p.os + p.oow[ph];
@@ -698,7 +697,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[as]);
                 fence_proxy_async_smem();                       // make the generic-proxy writes visible to the TMA store
-                epi_bar_sync();
+                team_bar_sync(team);
                 if (leader) {
                     for (int pn = 0; pn < n_panels; ++pn) {
                         const uint32_t src = smem_u32(stage_set + pn * kATileBytes);
@@ -708,6 +707,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                     tma_store_commit();
                     if (p.trace && blockIdx.x == 0 && local < 256) p.trace[5 * 256 + local] = clock64();
+                    // the set is single-buffered per team: its next residual tile can only land once the store has
+                    // finished reading; the other team's tile hides this latency
+                    if (p.res_mode && tile + stride_tiles < p.total_tiles) {
+                        tma_store_wait_read<0>();
+                        load_residual(tile + stride_tiles);
+                    }
                 }
             }
             if (leader) tma_store_wait_read<0>();
