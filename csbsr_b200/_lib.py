@@ -46,6 +46,7 @@ class ConvDesc(C.Structure):
         ("r1_sign", C.c_float),
         ("r32", C.c_void_p),
         ("block_n", C.c_int32),
+        ("r32_pitch", C.c_int32), ("r32_coff", C.c_int32),
     ]
 
 

@@ -55,7 +55,7 @@ struct ConvKParams {
     int out_mode, y_pitch, y_coff, cout_store;
     int bias_sn, bias_sc, cls_bw, act;
     float slope, r1_sign;
-    int r0_pitch, r0_coff, rm_pitch, rm_coff, r1_pitch, r1_coff;
+    int r0_pitch, r0_coff, rm_pitch, rm_coff, r1_pitch, r1_coff, r32_pitch, r32_coff;
     void* y;
     const float* bias;
     const __nv_bfloat16* r0;
@@ -458,13 +458,16 @@ __device__ __forceinline__ void epilogue_units(const ConvKParams& p, const EpiRo
         } else {                                        // fp32 planar [n][cout_store][YH][YW]
             float* y32 = reinterpret_cast<float*>(p.y);
             const size_t plane = static_cast<size_t>(p.YH) * p.YW;
-            const size_t base = (static_cast<size_t>(er.img) * p.cout_store) * plane + static_cast<size_t>(er.oy) * p.YW + er.ox;
+            // planar tensors may be channel windows of wider buffers: [n][pitch][YH][YW], window start coff
+            const size_t pixo = static_cast<size_t>(er.oy) * p.YW + er.ox;
+            const size_t base = (static_cast<size_t>(er.img) * p.y_pitch + p.y_coff) * plane + pixo;
+            const size_t rbase = (static_cast<size_t>(er.img) * p.r32_pitch + p.r32_coff) * plane + pixo;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 16; ++i) {
                 const int c = c0 + i;
                 if (c < p.cout_store) {
                     float val = act_fn<ACT>(f[i], slope);
-                    if (p.r32) val += p.r32[base + c * plane];
+                    if (p.r32) val += p.r32[rbase + c * plane];
                     y32[base + c * plane] = val;
                 }
             }
@@ -820,7 +823,7 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
                       "conv_igemm: f32 NHWC output needs cout_store/pitch/offset multiples of 4");
         CSBSR_REQUIRE(!d->r0 && !d->rm && !d->r1 && !d->r32, "conv_igemm: no residuals with f32 NHWC output");
     } else {
-        CSBSR_REQUIRE(d->cout_store >= 1 && d->cout_store <= 8, "conv_igemm: f32 planar output needs cout_store<=8");
+        CSBSR_REQUIRE(d->cout_store >= 1 && d->cout_store <= 16, "conv_igemm: f32 planar output needs cout_store<=16");
         CSBSR_REQUIRE(!d->r0 && !d->rm && !d->r1, "conv_igemm: bf16 residuals only with bf16 output");
     }
     CSBSR_REQUIRE(d->cout_store <= d->cout_pad, "conv_igemm: cout_store > cout_pad");
@@ -945,6 +948,12 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     p.rm = reinterpret_cast<const __nv_bfloat16*>(d->rm);
     p.r1 = reinterpret_cast<const __nv_bfloat16*>(d->r1);
     p.r32 = d->r32;
+    if (d->out_mode == CSBSR_OUT_F32_NCHW) {
+        // planar: pitch = channels of the destination / residual buffers (0 -> exactly cout_store), coff = first channel
+        p.y_pitch = d->y_pitch > 0 ? d->y_pitch : d->cout_store;
+        p.r32_pitch = d->r32_pitch > 0 ? d->r32_pitch : d->cout_store;
+        p.r32_coff = d->r32_coff;
+    }
     p.staged = staged ? 1 : 0;
     p.res_mode = staged ? (d->r0 ? 1 : (d->r1 ? 2 : 0)) : 0;
     memcpy(p.dh, g_dh, sizeof(p.dh)); memcpy(p.dw, g_dw, sizeof(p.dw)); memcpy(p.widx, g_widx, sizeof(p.widx));

@@ -69,6 +69,16 @@ class Fmap:
         return Fmap(t, 0, cpad)
 
 
+class PlanarWin:
+    """Channel window [coff, coff+c) of a planar fp32 [N,P,H,W] tensor (conv output / fp32 residual)."""
+
+    def __init__(self, t, coff=0, c=None):
+        assert t.dim() == 4 and t.dtype == torch.float32 and t.is_contiguous()
+        self.t, self.coff = t, coff
+        self.c = t.shape[1] - coff if c is None else c
+        assert 0 <= coff and coff + self.c <= t.shape[1]
+
+
 class F32Map:
     """fp32 NHWC conv output [N,H,W,P] (used for the per-sample border-class biases)."""
 
@@ -188,6 +198,12 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
         d.y_pitch, d.y_coff = y.t.shape[3], 0
         d.cout_store = cout_store if cout_store is not None else min(y.t.shape[3], pc.cout_pad)
         assert y.t.shape[0] == x.n
+    elif isinstance(y, PlanarWin):
+        d.out_mode = OUT_F32_NCHW
+        d.yh, d.yw = y.t.shape[2], y.t.shape[3]
+        d.y = y.t.data_ptr()
+        d.y_pitch, d.y_coff, d.cout_store = y.t.shape[1], y.coff, y.c
+        assert y.t.shape[0] == x.n
     else:
         assert y.dtype == torch.float32 and y.is_contiguous() and y.dim() == 4
         d.out_mode = OUT_F32_NCHW
@@ -214,8 +230,13 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
             setattr(d, name + "_coff", r.coff)
     d.r1_sign = float(r1_sign)
     if r32 is not None:
-        assert r32.dtype == torch.float32 and r32.is_contiguous()
-        d.r32 = r32.data_ptr()
+        if isinstance(r32, PlanarWin):
+            assert r32.c == d.cout_store and r32.t.shape[2:] == (d.yh, d.yw)
+            d.r32 = r32.t.data_ptr()
+            d.r32_pitch, d.r32_coff = r32.t.shape[1], r32.coff
+        else:
+            assert r32.dtype == torch.float32 and r32.is_contiguous()
+            d.r32 = r32.data_ptr()
     d.block_n = block_n
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

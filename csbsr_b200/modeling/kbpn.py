@@ -78,7 +78,10 @@ class KBPNEngine:
             st["up.d1"] = (K.pack_deconv8s4(g(sp + "up.up_conv1.layer.weight")), slope(sp + "up.up_conv1.act.weight"))
             st["up.c2"] = (K.pack_conv(g(sp + "up.up_conv2.layer.weight"), stride=4, padding=2), slope(sp + "up.up_conv2.act.weight"))
             st["up.d3"] = (K.pack_deconv8s4(g(sp + "up.up_conv3.layer.weight")), slope(sp + "up.up_conv3.act.weight"))
-            st["kb.sr"] = K.pack_conv(g(sp + "kb.sr_reconst.layer.weight"), padding=1)
+            # sr_reconst of stage s reads concat_h[0:(s+1)C]; by linearity its response is a sum over the C-channel
+            # slices, so slice j is read ONCE more after its KBlock update for all later consumers (see forward)
+            w_sr = g(sp + "kb.sr_reconst.layer.weight")                  # [3, (s+1)C, 3, 3]
+            st["kb.sr_own"] = K.pack_conv(w_sr[:, s * C:(s + 1) * C].contiguous(), padding=1)
             kp = sp + "kb.kernel_predictor."
             st["sr0"] = K.pack_conv(as1x1(g(kp + "fe_SR.0.layer.weight")), cout_pad=64)
             st["sr1"] = K.pack_conv(g(kp + "fe_SR.1.layer.weight"), cout_pad=64)
@@ -123,7 +126,12 @@ class KBPNEngine:
                     st["sft.%s.1" % br] = K.pack_conv(g(sp + "sft.SFT_%s_conv1.weight" % br), g(sp + "sft.SFT_%s_conv1.bias" % br),
                                                       padding=1, cin_pad=cc_pad)
             P[s] = st
-        P["out"] = K.pack_conv(g("output_conv.layer.weight"), padding=1)
+        w_out = g("output_conv.layer.weight")                             # [3, S*C, 3, 3]
+        for j in range(self.S):
+            # consumers of the final slice j: sr_reconst of stages j+1..S-1 (3 channels each), then output_conv
+            ws = [g("back_projection_stages.%d.kb.sr_reconst.layer.weight" % c)[:, j * C:(j + 1) * C] for c in range(j + 1, self.S)]
+            ws.append(w_out[:, j * C:(j + 1) * C])
+            P[j]["kb.sr_later"] = K.pack_conv(torch.cat(ws, 0).contiguous(), padding=1)
         self.p = P
         return self
 
@@ -158,7 +166,14 @@ class KBPNEngine:
         concat_h = ws.fmap("concat_h", B, H, W, self.S * C)
         concat_l = ws.fmap("concat_l", B, h, w, max(1, self.S - 1) * C)
         t0 = ws.fmap("hr_t0", B, H, W, C)
-        up_res = K.bicubic_upsample(x, ws.f32("up_res", B, 3, H, W), self.scale)
+        # sr_acc[:, 3c:3c+3] collects, slice by slice, sr_reconst of stage c+1 (c < S-1) and output_conv (+ the bicubic
+        # residual of kbpn.py:113, c = S-1): fp32 planar accumulators
+        sr_acc = ws.f32("sr_acc", B, 3 * self.S, H, W)
+        up_tail = K.PlanarWin(sr_acc, 0, 3 * self.S)
+        sr_acc.zero_()
+        K.bicubic_upsample(x, ws.f32("up_res", B, 3, H, W), self.scale)
+        sr_acc[:, 3 * (self.S - 1):] = ws.f32("up_res", B, 3, H, W)
+        sr = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
         low = init_f
         for s in range(self.S):
             st = P[s]
@@ -170,7 +185,9 @@ class KBPNEngine:
             K.conv(d, st["up.d3"][0], hs, act=ACT_LEAKY, slope=st["up.d3"][1], r1=h0)
             # ---- KBlock (kbpn.py:382-412)
             pre = concat_h.window(0, (s + 1) * C)
-            sr_t = K.conv(pre, st["kb.sr"], ws.f32("sr_t", B, 3, H, W))
+            # sr_t = sr_reconst(cat(slices)) = own-slice conv + contributions of the earlier (final) slices in sr_acc
+            sr_t = K.conv(hs, st["kb.sr_own"], ws.f32("sr_t", B, 3, H, W),
+                          r32=K.PlanarWin(sr_acc, 3 * (s - 1), 3) if s > 0 else None)
             kvec = self._kernel_predictor(st, sr_t, kvec, B, H, W, s)
             if self.debug is not None:
                 self.debug["sr_t%d" % s] = sr_t.clone()
@@ -178,8 +195,13 @@ class KBPNEngine:
             err = K.blur_per_sample(sr_t, kvec, x, ws.f32("err", B, 3, h, w), self.ko, self.scale)
             ep = K.patchify(err, ws.fmap("xp", B, h, w, 64), 3, 3, 1, 1)
             K.conv(ep, st["kb.d1"][0], hs, act=ACT_LEAKY, slope=st["kb.d1"][1], r1=hs)      # h + e_h, in place
+            # the slice is final now: add its response to every later consumer (channels [3s, 3S) of sr_acc:
+            # sr_reconst of stages s+1.., then output_conv), reading the 448^2 x C slice only once
+            later = K.PlanarWin(sr_acc, 3 * s, 3 * (self.S - s))
             if s == self.S - 1:
+                K.conv(hs, st["kb.sr_later"], sr, r32=later)                # output_conv + bicubic residual -> sr
                 break
+            K.conv(hs, st["kb.sr_later"], later, r32=later if s > 0 else up_tail)
             # ---- DownBlock (kbpn.py:484-489) on concat_h[0:(s+1)C], result into its concat_l slice
             xh = K.conv(pre, st["dn.conv"][0], t0, act=ACT_LEAKY, slope=st["dn.conv"][1])
             l0 = K.conv(xh, st["dn.c1"][0], ws.fmap("lr_x", B, h, w, C), act=ACT_LEAKY, slope=st["dn.c1"][1])
@@ -187,8 +209,6 @@ class KBPNEngine:
             K.conv(t0, st["dn.c3"][0], concat_l.window(s * C, C), act=ACT_LEAKY, slope=st["dn.c3"][1], r1=l0)
             # ---- SFT layer (kbpn.py:511-518)
             low = self._sft(st, concat_l.window(0, (s + 1) * C), kvec, B, h, w, s)
-        sr = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
-        K.conv(concat_h, P["out"], sr, r32=up_res)
         return sr, kvec.clone()
 
     def _kernel_predictor(self, st, sr_t, kvec, B, H, W, s):

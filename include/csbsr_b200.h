@@ -65,7 +65,7 @@ typedef struct csbsr_conv_desc {
     int32_t yh, yw;                                 /* stored output image size */
     int32_t out_mode;                               /* CSBSR_OUT_* */
     void* y;
-    int32_t y_pitch, y_coff, cout_store;            /* bf16: %8==0 channels written; f32 planes: <= 8 */
+    int32_t y_pitch, y_coff, cout_store;            /* bf16: %8==0 channels written; f32 planes: <= 16 */
     /* epilogue */
     const float* bias;                              /* may be NULL */
     int32_t bias_sn, bias_sc, cls_bw;
@@ -75,8 +75,11 @@ typedef struct csbsr_conv_desc {
     const void* rm; int32_t rm_pitch, rm_coff;      /* post-activation multiply */
     const void* r1; int32_t r1_pitch, r1_coff;      /* post-activation add (r1_sign = +1) / subtract (-1) */
     float r1_sign;
-    const float* r32;                               /* f32 planar residual [n][cout_store][yh][yw] (out_mode 1) */
+    const float* r32;                               /* f32 planar residual added after the activation (out_mode 1) */
     int32_t block_n;                                /* 0 = auto */
+    /* out_mode 1: y / r32 are channel windows [coff, coff+cout_store) of planar buffers with `pitch` channels
+     * (y_pitch / y_coff above and r32_pitch / r32_coff; pitch 0 = exactly cout_store channels) */
+    int32_t r32_pitch, r32_coff;
 } csbsr_conv_desc;
 
 int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream);
