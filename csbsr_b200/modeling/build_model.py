@@ -20,7 +20,7 @@ class JointModel(nn.Module):
         super().__init__()
         if cfg.MODEL.SR != "KBPN":
             raise NotImplementedError(cfg.MODEL.SR)
-        if cfg.MODEL.DETECTOR_TYPE != "PSPNet":
+        if cfg.MODEL.DETECTOR_TYPE not in ("PSPNet", "PSPNet_BlurSkip"):
             raise NotImplementedError(cfg.MODEL.DETECTOR_TYPE)
         if cfg.MODEL.SCALE_FACTOR != 4:
             raise NotImplementedError("SCALE_FACTOR=%r" % (cfg.MODEL.SCALE_FACTOR,))
@@ -30,9 +30,10 @@ class JointModel(nn.Module):
         self.ksize = cfg.BLUR.KERNEL_SIZE_OUTPUT
         self.blur_ksize = cfg.BLUR.KERNEL_SIZE
         self.num_stages = cfg.MODEL.NUM_STAGES
-        self.seg_model_name = "PSPNet"
+        self.seg_model_name = cfg.MODEL.DETECTOR_TYPE
         self.norm_method = cfg.SOLVER.NORM_SR_OUTPUT
-        self.segmentation_model = ParamTree(pspnet_param_shapes(cfg.MODEL.NUM_CLASSES))
+        blur_dim = cfg.BLUR.KERNEL_SIZE_OUTPUT ** 2 if self.seg_model_name == "PSPNet_BlurSkip" else None
+        self.segmentation_model = ParamTree(pspnet_param_shapes(cfg.MODEL.NUM_CLASSES, blur_dim=blur_dim))
         self.sr_model = ParamTree(kbpn_param_shapes(self.num_stages, 128, self.blur_ksize, self.ksize))
         self.chunk = 8                      # images per pass through the engines (activation working set)
         self._engines = None
@@ -74,7 +75,8 @@ class JointModel(nn.Module):
             mean = torch.empty(b * 3, dtype=torch.float32, device=device)
             rstd = torch.empty(b * 3, dtype=torch.float32, device=device)
             K.clip_instnorm_stats(sr, mean, rstd, do_clip=True)            # clip_sr :143-146 + norm_sr stats :135-137
-            seg, aux = ss_eng.forward(sr, mean, rstd)
+            # PSPNet_BlurSkip also receives the (spatially constant) kernel map of KBPN (build_model.py:482-483, 498-500)
+            seg, aux = ss_eng.forward(sr, mean, rstd, kvec=kvec if self.seg_model_name == "PSPNet_BlurSkip" else None)
             kp = torch.empty_like(kvec)
             K.vec_normalize(kvec, kp)                                       # :491-494
             srs.append(sr); segs.append(seg); kps.append(kp.view(b, 1, self.ksize, self.ksize)); auxs.append(aux)

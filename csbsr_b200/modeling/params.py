@@ -82,8 +82,10 @@ def _bn(P, pfx, c):
 RESNET34_LAYERS = ((64, 3, 1, 1), (128, 4, 2, 1), (256, 6, 1, 2), (512, 3, 1, 4))   # planes, blocks, stride, dilation
 
 
-def pspnet_param_shapes(n_classes=1, sizes=(1, 2, 3, 6), psp_size=512, deep_features_size=256):
-    """OrderedDict name -> shape for `segmentation_model.*` (PSPNet on a dilated ResNet-34)."""
+def pspnet_param_shapes(n_classes=1, sizes=(1, 2, 3, 6), psp_size=512, deep_features_size=256, blur_dim=None,
+                        n_layer_blurskip=2):
+    """OrderedDict name -> shape for `segmentation_model.*` (PSPNet on a dilated ResNet-34); with `blur_dim`
+    (= KERNEL_SIZE_OUTPUT**2) also the BlurSkip blocks of PSPNet_BlurSkip (pspnet.py:127-160, blocks.py:105-120)."""
     P = OrderedDict()
     P["feats.conv1.weight"] = (64, 3, 7, 7)
     _bn(P, "feats.bn1", 64)
@@ -108,6 +110,18 @@ def pspnet_param_shapes(n_classes=1, sizes=(1, 2, 3, 6), psp_size=512, deep_feat
         P[name + ".conv.0.bias"] = (co,)
         _bn(P, name + ".conv.1", co)
         P[name + ".conv.2.weight"] = (1,)
+    if blur_dim is not None:
+        cc = blur_dim + 64
+        for i in range(n_layer_blurskip):
+            for br in ("scale", "shift"):
+                bp = "blur_skip.%d.conv_%s" % (2 * i, br)
+                P[bp + ".0.layer.weight"] = (cc, cc, 3, 3)
+                P[bp + ".0.layer.bias"] = (cc,)
+                P[bp + ".0.act.weight"] = (1,)
+                P[bp + ".1.layer.weight"] = (64, cc, 3, 3)
+                P[bp + ".1.layer.bias"] = (64,)
+            P["blur_skip.%d.layer.weight" % (2 * i + 1)] = (64, 64, 3, 3)
+            _bn(P, "blur_skip.%d.norm" % (2 * i + 1), 64)
     P["final.0.weight"] = (n_classes, 64, 1, 1)
     P["final.0.bias"] = (n_classes,)
     P["aux.0.weight"] = (256, deep_features_size, 3, 3)

@@ -55,6 +55,27 @@ class PSPNetEngine:
             sc, sh = bn_fold(name + ".conv.1", g(name + ".conv.0.bias"))
             P[name] = (K.pack_conv(g(name + ".conv.0.weight"), sh, padding=1, scale=sc),
                        float(sd[prefix + name + ".conv.2.weight"].detach().float().reshape(-1)[0]))
+        # ---- BlurSkip (PSPNet_BlurSkip, pspnet.py:143-160; SFTLikeBlock blocks.py:105-120): the 441 conditioning channels
+        # are spatially constant, so their half of conv 0 becomes a per-sample 3x3-border-class bias (as in KBPN's SFT)
+        self.blur_layers = 0
+        while (prefix + "blur_skip.%d.conv_scale.0.layer.weight" % (2 * self.blur_layers)) in sd:
+            i = self.blur_layers
+            for br in ("scale", "shift"):
+                bp = "blur_skip.%d.conv_%s" % (2 * i, br)
+                w0, b0 = g(bp + ".0.layer.weight"), g(bp + ".0.layer.bias")
+                cc = w0.shape[0]
+                cc_pad = K.round_up(cc, 64)
+                P["bs%d.%s.0f" % (i, br)] = (K.pack_conv(w0[:, :64].contiguous(), padding=1, cout_pad=cc_pad),
+                                             float(sd[prefix + bp + ".0.act.weight"].detach().float().reshape(-1)[0]))
+                P["bs%d.%s.0k" % (i, br)] = K.pack_conv(w0[:, 64:].contiguous(), b0, padding=1, cout_pad=cc_pad,
+                                                        cin_pad=K.round_up(cc - 64, 64))
+                P["bs%d.%s.1" % (i, br)] = K.pack_conv(g(bp + ".1.layer.weight"), g(bp + ".1.layer.bias"), padding=1,
+                                                       cin_pad=cc_pad)
+            bp = "blur_skip.%d" % (2 * i + 1)
+            sc, sh = bn_fold(bp + ".norm")
+            P["bs%d.conv" % i] = K.pack_conv(g(bp + ".layer.weight"), sh, padding=1, scale=sc)
+            self.blur_layers += 1
+            self.blur_cc_pad, self.blur_cond = cc_pad, cc - 64
         P["final"] = K.pack_conv(g("final.0.weight"), g("final.0.bias"))
         sc, sh = bn_fold("aux.1")
         P["aux0"] = K.pack_conv(g("aux.0.weight"), sh, padding=1, scale=sc)
@@ -62,7 +83,7 @@ class PSPNetEngine:
         self.p = P
         return self
 
-    def forward(self, img, mean=None, rstd=None, clamp01=False):
+    def forward(self, img, mean=None, rstd=None, clamp01=False, kvec=None):
         """img: fp32 [B,3,H,W]; when mean/rstd ([B*3]) are given the input is clamp/instance-normalised on the
         fly while it is gathered for conv1 (build_model.py:135-146).  Returns (seg, aux) fp32 [B,1,H,W]."""
         P, ws = self.p, self.ws
@@ -106,6 +127,8 @@ class PSPNetEngine:
             h, w = 2 * h, 2 * w
             up = K.bilinear(y, ws.fmap(name + "_in", B, h, w, y.c))
             y = K.conv(up, P[name][0], ws.fmap(name + "_out", B, h, w, co), act=ACT_LEAKY, slope=P[name][1])
+        if self.blur_layers and kvec is not None:
+            y = self._blur_skip(y, kvec, B, h, w)
         seg = torch.empty((B, 1, h, w), dtype=torch.float32, device=img.device)
         K.conv(y, P["final"], seg, act=ACT_SIGMOID)
         # ---- auxiliary head on layer3 features (pspnet.py:118-122)
@@ -116,3 +139,27 @@ class PSPNetEngine:
         if (h, w) != (H, W):
             raise K._lib.CsbsrError("PSPNet output %dx%d != input %dx%d (input must be a multiple of 8)" % (h, w, H, W))
         return seg, aux
+
+    def _blur_skip(self, p0, kvec, B, h, w):
+        """p + BlurSkip(p, kernel) (pspnet.py:189-198): 2 x [SFTLikeBlock(64 + 441 -> 64), Conv3x3 + BN + ReLU]."""
+        from ..kernels import F32Map
+        P, ws = self.p, self.ws
+        ccp, cond_pad = self.blur_cc_pad, K.round_up(self.blur_cond, 64)
+        small = K.broadcast_vec(kvec, ws.fmap("bs_k3", B, 3, 3, cond_pad))
+        t = p0
+        for i in range(self.blur_layers):
+            branch = {}
+            for br in ("shift", "scale"):
+                cb = K.conv(small, P["bs%d.%s.0k" % (i, br)], F32Map(ws.f32("bs_k3bias", B, 3, 3, ccp)))
+                pc0, slope = P["bs%d.%s.0f" % (i, br)]
+                u = K.conv(t, pc0, ws.fmap("bs_t", B, h, w, ccp), bias=cb.t, bias_sn=9 * ccp, bias_sc=ccp, cls_bw=1,
+                           act=ACT_LEAKY, slope=slope)
+                if br == "shift":
+                    branch = K.conv(u, P["bs%d.shift.1" % i], ws.fmap("bs_shift", B, h, w, 64))
+                else:
+                    t2 = K.conv(u, P["bs%d.scale.1" % i], ws.fmap("bs_sft%d" % (i % 2), B, h, w, 64), act=ACT_SIGMOID, rm=t,
+                                r1=branch)
+            last = (i == self.blur_layers - 1)
+            t = K.conv(t2, P["bs%d.conv" % i], ws.fmap("bs_out%d" % (i % 2), B, h, w, 64), act=ACT_RELU,
+                       r1=p0 if last else None)
+        return t

@@ -180,8 +180,19 @@ def resnet34_dilated(sd, p, x):
     return x, x3
 
 
-def pspnet_forward(sd, x, prefix="segmentation_model.", sizes=(1, 2, 3, 6)):
-    """PSPNet.forward in eval mode (dropout = identity): pspnet_pytorch/pspnet.py:95-123, 23-57."""
+def _sft_like_block(sd, p, feats, cond):
+    """SFTLikeBlock.forward: model/modeling/blocks.py:105-120 (PReLU after conv 0, sigmoid / none after conv 1)."""
+    c = torch.cat((feats, cond), 1)
+    def branch(name, last):
+        t = F.prelu(_conv(sd, p + ".conv_%s.0.layer" % name, c, padding=1), sd[p + ".conv_%s.0.act.weight" % name])
+        t = _conv(sd, p + ".conv_%s.1.layer" % name, t, padding=1)
+        return torch.sigmoid(t) if last == "sigmoid" else t
+    return feats * branch("scale", "sigmoid") + branch("shift", None)
+
+
+def pspnet_forward(sd, x, prefix="segmentation_model.", sizes=(1, 2, 3, 6), kvec=None):
+    """PSPNet.forward in eval mode (dropout = identity): pspnet_pytorch/pspnet.py:95-123, 23-57.
+    With `kvec` (B,441,1,1) and blur_skip weights: PSPNet_BlurSkip.forward, pspnet.py:174-207."""
     p = prefix
     H, W = x.shape[2:]
     f, x3 = resnet34_dilated(sd, p + "feats.", x)
@@ -196,6 +207,18 @@ def pspnet_forward(sd, x, prefix="segmentation_model.", sizes=(1, 2, 3, 6)):
         y = F.interpolate(y, size=(2 * y.shape[2], 2 * y.shape[3]), mode="bilinear")
         y = _bn(sd, p + name + ".conv.1", _conv(sd, p + name + ".conv.0", y, padding=1))
         y = F.prelu(y, sd[p + name + ".conv.2.weight"])
+    if kvec is not None:
+        cond = kvec.expand(-1, -1, H, W)
+        t = y
+        i = 0
+        while (p + "blur_skip.%d.conv_scale.0.layer.weight" % (2 * i)) in sd:
+            t = _sft_like_block(sd, p + "blur_skip.%d" % (2 * i), t, cond)
+            bp = p + "blur_skip.%d" % (2 * i + 1)
+            t = F.relu(F.batch_norm(_conv(sd, bp + ".layer", t, padding=1), sd[bp + ".norm.running_mean"],
+                                    sd[bp + ".norm.running_var"], sd[bp + ".norm.weight"], sd[bp + ".norm.bias"],
+                                    training=False, eps=1e-5))
+            i += 1
+        y = y + t
     seg = torch.sigmoid(_conv(sd, p + "final.0", y))
     a = F.relu(_bn(sd, p + "aux.1", _conv(sd, p + "aux.0", x3, padding=1)))
     a = torch.sigmoid(_conv(sd, p + "aux.4", a))
@@ -203,11 +226,11 @@ def pspnet_forward(sd, x, prefix="segmentation_model.", sizes=(1, 2, 3, 6)):
     return seg, aux
 
 
-def joint_forward(sd, x, k_out=21, num_stages=4):
+def joint_forward(sd, x, k_out=21, num_stages=4, blur_skip=False):
     """JointModel.forward (KBPN + PSPNet, NORM_SR_OUTPUT='instance'): model/modeling/build_model.py:466-496,
     clip_sr :143-146, norm_sr :135-137 (fresh InstanceNorm2d(3): eps 1e-5, biased variance, no affine)."""
     sr, kvec = kbpn_forward(sd, x, num_stages=num_stages, k_out=k_out)
     sr = sr.clamp(0.0, 1.0)
-    seg, aux = pspnet_forward(sd, F.instance_norm(sr, eps=1e-5))
+    seg, aux = pspnet_forward(sd, F.instance_norm(sr, eps=1e-5), kvec=kvec if blur_skip else None)
     kp = kvec / kvec.sum(dim=1).view(-1, 1, 1, 1)
     return sr, seg, kp.view(-1, 1, k_out, k_out), aux

@@ -5,6 +5,7 @@ Outputs (small .npz files next to this script):
   metrics_kat.npz     inputs + IoU / HD(50,95) / MSD of the reference's IoU + calc_distance_metrics
   degrade.npz         GaussianBlur.make kernels, conv_kernel2d blur and FactorResize outputs
   joint_model.npz     JointModel (KBPN + PSPNet) outputs on csbsr_b200.modeling.params.synth_state_dict weights
+  joint_blurskip.npz  the same with DETECTOR_TYPE = PSPNet_BlurSkip
 """
 import os
 import sys
@@ -101,18 +102,18 @@ def gen_degrade():
     print("degrade.npz", {k: v.shape for k, v in out.items()})
 
 
-def gen_joint():
+def gen_joint(blur_skip=False):
     from csbsr_b200.modeling import params as P
-    cfg = rh.make_cfg()
+    cfg = rh.make_cfg(detector="PSPNet_BlurSkip" if blur_skip else "PSPNet")
     m = rh.joint_model(cfg)
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-    sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+    sd.update(P.synth_state_dict(P.pspnet_param_shapes(blur_dim=441 if blur_skip else None), prefix="segmentation_model."))
     m.load_state_dict(sd, strict=True)
     g = torch.Generator().manual_seed(21)
     x = torch.rand(2, 3, 16, 24, generator=g)
     with torch.no_grad():
         sr, seg, kp = m(x.clone(), torch.zeros(2, 1, 7, 7))
-    np.savez_compressed(os.path.join(HERE, "joint_model.npz"), x=x.numpy(), sr=sr.numpy().astype(np.float16),
+    np.savez_compressed(os.path.join(HERE, "joint_blurskip.npz" if blur_skip else "joint_model.npz"), x=x.numpy(), sr=sr.numpy().astype(np.float16),
                         seg=seg.numpy().astype(np.float16), kp=kp.numpy(),
                         sr_checksum=np.float64(sr.double().sum().item()), seg_checksum=np.float64(seg.double().sum().item()))
     print("joint_model.npz", sr.shape, seg.shape, kp.shape)
@@ -126,3 +127,5 @@ if __name__ == "__main__":
         gen_degrade()
     if "joint" in which:
         gen_joint()
+    if "blurskip" in which or not sys.argv[1:]:
+        gen_joint(blur_skip=True)

@@ -13,15 +13,17 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _model_and_sd():
+def _model_and_sd(blur_skip=False):
     from csbsr_b200.config import cfg
     from csbsr_b200.modeling.build_model import JointModel
     from csbsr_b200.modeling import params as P
     c = cfg.clone()
     c.merge_from_file("config/config_csbsr_pspnet.yaml")
+    if blur_skip:
+        c.MODEL.DETECTOR_TYPE = "PSPNet_BlurSkip"
     m = JointModel(c)
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-    sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+    sd.update(P.synth_state_dict(P.pspnet_param_shapes(blur_dim=441 if blur_skip else None), prefix="segmentation_model."))
     m.load_state_dict(sd, strict=True)
     return m, sd
 
@@ -85,3 +87,24 @@ def test_joint_model_vs_oracle(b, h, w):
     assert (seg - seg_ref).abs().max().item() <= 5e-2 and (seg - seg_ref).abs().mean().item() <= 5e-3
     assert (kp - kp_ref).abs().max().item() <= 2e-2 * kp_ref.abs().max().item()
     assert sr.min().item() >= 0.0 and sr.max().item() <= 1.0
+
+
+def test_blurskip_joint_model_vs_oracle_and_golden():
+    """PSPNet_BlurSkip (config #5 detector): p + BlurSkip(p, kernel) with the 441 conditioning channels folded."""
+    import os
+    import numpy as np
+    from oracle import torch_ref as T
+    m, sd = _model_and_sd(blur_skip=True)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "joint_blurskip.npz"))
+    x = torch.from_numpy(g["x"])
+    sr, seg, kp = m(x, torch.zeros(x.shape[0], 1, 7, 7))
+    with torch.no_grad():
+        sr_ref, seg_ref, kp_ref, _ = T.joint_forward(sdc, x.cuda(), blur_skip=True)
+    torch.cuda.synchronize()
+    print("blurskip sr", (sr - sr_ref).abs().max().item(), "seg", (seg - seg_ref).abs().max().item(), (seg - seg_ref).abs().mean().item())
+    assert (sr - sr_ref).abs().max().item() <= 3e-2 and _psnr(sr, sr_ref) >= 40.0
+    assert (seg - seg_ref).abs().max().item() <= 5e-2 and (seg - seg_ref).abs().mean().item() <= 5e-3
+    # and against the unmodified reference's own outputs (fp16-stored fixture)
+    assert np.abs(seg.cpu().numpy() - g["seg"].astype(np.float32)).max() <= 5e-2
+    assert np.abs(sr.cpu().numpy() - g["sr"].astype(np.float32)).max() <= 3e-2

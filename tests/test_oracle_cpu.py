@@ -110,15 +110,16 @@ def test_degrade_oracle_matches_reference_golden():
     assert abs(col[32 - 6].item() + 0.001709) < 1e-5 and abs(col[32 + 1].item() - 0.240967) < 1e-5
 
 
-def test_network_oracle_matches_reference_golden():
+@pytest.mark.parametrize("blur_skip", [False, True])
+def test_network_oracle_matches_reference_golden(blur_skip):
     """oracle/torch_ref.py against the real JointModel's outputs on the same synthetic weights (fp16-stored)."""
     from csbsr_b200.modeling import params as P
     from oracle import torch_ref as T
-    g = np.load(os.path.join(GOLD, "joint_model.npz"))
+    g = np.load(os.path.join(GOLD, "joint_blurskip.npz" if blur_skip else "joint_model.npz"))
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-    sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+    sd.update(P.synth_state_dict(P.pspnet_param_shapes(blur_dim=441 if blur_skip else None), prefix="segmentation_model."))
     with torch.no_grad():
-        sr, seg, kp, _ = T.joint_forward(sd, torch.from_numpy(g["x"]))
+        sr, seg, kp, _ = T.joint_forward(sd, torch.from_numpy(g["x"]), blur_skip=blur_skip)
     assert np.abs(sr.numpy() - g["sr"].astype(np.float32)).max() <= 1e-3        # fp16 storage of the fixture
     assert np.abs(seg.numpy() - g["seg"].astype(np.float32)).max() <= 1e-3
     assert np.abs(kp.numpy() - g["kp"]).max() <= 1e-5
