@@ -148,6 +148,7 @@ def main():
     from csbsr_b200 import _lib, kernels as K
     from csbsr_b200.config import cfg
     from csbsr_b200.data import degrade as G
+    from csbsr_b200.engine import distributed as D
     from csbsr_b200.engine import inference as E
     from csbsr_b200.modeling.build_model import JointModel
     from csbsr_b200.utils import synth
@@ -188,15 +189,11 @@ def main():
         outs = []
         for i in range(0, B, mchunk):
             r = E.seg_metrics(seg[i:i + mchunk], mask[i:i + mchunk], with_hd=True, to_host=False)
-            outs.append(torch.cat([r["inter"].double(), r["union"].double(), r["hd"], r["msd"]], dim=1))
+            outs.append(D.pack_metrics(r["inter"], r["union"], r["hd"], r["msd"]))
         return torch.cat(outs, 0)               # [B, 4*99] fp64
 
     def gather(res):
-        if world > 1:
-            out = [torch.empty_like(res) for _ in range(world)]
-            dist.all_gather(out, res)            # the only exchange: B x 396 fp64 per rank
-            res = torch.cat(out, 0)
-        return res
+        return D.gather_rows(res)                # the only exchange: B x 396 fp64 per rank (no-op at world size 1)
 
     def step_device():
         return gather(hot_path(hr_dev, mask_dev))

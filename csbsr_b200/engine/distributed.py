@@ -1,0 +1,52 @@
+"""Batch sharding across ranks (one process per GPU) and the single exchange step of the eval path.
+
+Every image is an independent unit: rank r evaluates the contiguous shard
+[r*B/R, (r+1)*B/R) with no data-path collective; the only exchange is one all_gather of the per-image
+integer IoU counts and fp64 HD / MSD values before rank 0 forms the means exactly as the reference does
+(model/engine/inference.py:171-173).  Works with NCCL (CUDA tensors) and gloo (CPU tensors, tests)."""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n, rank=None, world_size=None):
+    """Contiguous shard of `n` units for `rank`; the first n % world ranks get one extra unit."""
+    if rank is None:
+        rank, world_size = world()
+    base, extra = divmod(n, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def gather_rows(t):
+    """all_gather of a [rows, cols] tensor whose row count may differ per rank (zero-padded to the max, then trimmed).
+    Returns the concatenation in rank order on every rank."""
+    rank, ws = world()
+    if ws == 1:
+        return t
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    counts = [torch.zeros_like(n) for _ in range(ws)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    m = max(counts)
+    pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    out = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(out, pad)
+    return torch.cat([o[:c] for o, c in zip(out, counts)], 0)
+
+
+def pack_metrics(inter, union, hd, msd):
+    """[B,99] x4 -> one fp64 [B, 396] tensor (integer counts are exact in fp64)."""
+    return torch.cat([inter.to(torch.float64), union.to(torch.float64), hd, msd], dim=1)
+
+
+def unpack_metrics(packed):
+    n = packed.shape[1] // 4
+    p = packed.cpu().numpy()
+    return (p[:, :n].astype("int64"), p[:, n:2 * n].astype("int64"), p[:, 2 * n:3 * n], p[:, 3 * n:])

@@ -83,3 +83,52 @@ def calc_distance_metrics(segment_preds, gts, num_hd_outliner=0, num_msd_outline
     one_empty = gt_empty ^ pred_empty
     n = int(one_empty.sum())
     return r["hd"], r["msd"], num_hd_outliner + n, num_msd_outliner + n
+
+
+# ------------------------------------------------------------------ evaluation loop (host glue around the kernels)
+def psnr_per_image(pred, target):
+    """PSNR of [0,1] images per sample: 10*log10(1/mse) (model/utils/estimate_metrics.py:89-100); torch reductions on
+    the device are plumbing here, the hot path stays in the C-ABI kernels."""
+    mse = ((pred.float() - target.to(pred.device).float()) ** 2).flatten(1).mean(1)
+    return (10.0 * torch.log10(1.0 / mse)).cpu().numpy()
+
+
+def inference_for_ss(model, loader, test_surface_distance=True, percent=HD_PERCENTILE, output_dir=None, log=print):
+    """Counterpart of the reference's inference_for_ss (model/engine/inference.py:25-207) for loaders that yield
+    (lr_imgs[B,3,h,w], sr_targets[B,3,H,W], masks[B,1,H,W], kernel_targets[B,1,k,k], fnames): runs the model, the AIU
+    sweep and (optionally) the HD/MSD sweep per batch, prints the running means and writes iou_log.csv.
+    Under torch.distributed every rank evaluates its own loader shard; results are gathered on all ranks."""
+    import os
+    from . import distributed as D
+    rows, fnames, psnrs, kpsnrs = [], [], [], []
+    n_hd_out = 0
+    for it, (imgs, sr_targets, masks, kernel_targets, names) in enumerate(loader, 1):
+        sr, seg, kp = model(imgs, torch.zeros(imgs.shape[0], 1, model.blur_ksize, model.blur_ksize), sr_targets=sr_targets)
+        psnrs.append(psnr_per_image(sr, sr_targets))
+        kpsnrs.append(psnr_per_image(kp.clamp(0, 1), kernel_targets))
+        r = seg_metrics(seg, masks, with_hd=test_surface_distance, percent=percent, to_host=False)
+        hd = r["hd"] if test_surface_distance else torch.zeros_like(r["inter"], dtype=torch.float64)
+        msd = r["msd"] if test_surface_distance else torch.zeros_like(hd)
+        rows.append(D.pack_metrics(r["inter"], r["union"], hd, msd))
+        fnames += list(names)
+        if it % 10 == 0:
+            log("batch %d done" % it)
+    packed = D.gather_rows(torch.cat(rows, 0))
+    inter, union, hd, msd = D.unpack_metrics(packed)
+    iou = (inter + 1e-5) / (union + 1e-5)
+    out = {"AIU": float(np.mean(iou)), "IoU_max": float(np.max(np.mean(iou, axis=0))), "iou": iou,
+           "PSNR": float(np.mean(np.concatenate(psnrs))), "PSNR_kernel": float(np.mean(np.concatenate(kpsnrs)))}
+    if test_surface_distance:
+        out.update({"AHD": float(np.mean(hd)), "HD_min": float(np.min(np.mean(hd, axis=0))), "AMSD": float(np.mean(msd)),
+                    "hd": hd, "msd": msd})
+    log("estimation finish!!  PSNR_mean:%.4f PSNR(Kernel)_mean:%.4f AIU_mean:%.4f" % (out["PSNR"], out["PSNR_kernel"], out["AIU"])
+        + ("  HD%d_mean:%.4f MSD_mean:%.4f" % (percent, out["AHD"], out["AMSD"]) if test_surface_distance else ""))
+    rank, _ = D.world()
+    if output_dir and rank == 0:
+        os.makedirs(output_dir, exist_ok=True)
+        with open(os.path.join(output_dir, "iou_log.csv"), "w") as f:       # save_iou_log, inference.py:287-291
+            f.write("," + ",".join("%g" % (i * 0.01) for i in range(1, 100)) + "\n")
+            for i in range(iou.shape[0]):
+                name = fnames[i] if i < len(fnames) else "rank_other_%d" % i
+                f.write(name + "," + ",".join(repr(float(v)) for v in iou[i]) + "\n")
+    return out

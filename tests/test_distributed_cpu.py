@@ -1,0 +1,60 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host logic: contiguous batch shards + the one all_gather of metrics."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, B, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from csbsr_b200.engine import distributed as D
+    from oracle import metrics_ref as M
+    rng = np.random.default_rng(0)
+    prob = rng.random((B, 1, 12, 16)).astype(np.float32)
+    mask = (rng.random((B, 1, 12, 16)) < 0.4).astype(np.float32)
+    lo, hi = D.shard_range(B)
+    inter, union = M.iou_counts(prob[lo:hi], mask[lo:hi])          # the oracle stands in for the GPU kernel here
+    hd, msd = M.distance_metrics(prob[lo:hi], mask[lo:hi], 50)
+    packed = D.pack_metrics(torch.from_numpy(inter), torch.from_numpy(union), torch.from_numpy(hd), torch.from_numpy(msd))
+    allm = D.gather_rows(packed)
+    if rank == 0:
+        q.put(allm.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [5, 8])
+def test_sharded_metrics_equal_single_process(B):
+    from csbsr_b200.engine import distributed as D
+    from oracle import metrics_ref as M
+    assert [D.shard_range(5, r, 2) for r in range(2)] == [(0, 3), (3, 5)]
+    assert [D.shard_range(8, r, 4) for r in range(4)] == [(0, 2), (2, 4), (4, 6), (6, 8)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + B
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(0)
+    prob = rng.random((B, 1, 12, 16)).astype(np.float32)
+    mask = (rng.random((B, 1, 12, 16)) < 0.4).astype(np.float32)
+    inter, union = M.iou_counts(prob, mask)
+    hd, msd = M.distance_metrics(prob, mask, 50)
+    i2, u2, h2, m2 = D.unpack_metrics(torch.from_numpy(got))
+    assert np.array_equal(i2, inter) and np.array_equal(u2, union)
+    assert np.array_equal(h2, hd) and np.array_equal(m2, msd)
+    # AIU / AHD exactly as inference.py:171-173
+    assert np.mean((i2 + 1e-5) / (u2 + 1e-5)) == np.mean((inter + 1e-5) / (union + 1e-5))
