@@ -246,6 +246,12 @@ def main():
     n_conv = len(K.PROFILE)
     K.PROFILE = None
     peak_tf, peak_bw, peak_src = _peaks()
+    traffic = None                       # DRAM bytes of the conv kernel per step, from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
+            traffic = json.load(f)["dram_bytes_per_image"] * B
+    except Exception:
+        pass
     achieved_tf = conv_useful / (conv_ms * 1e-3) / 1e12
     value = world * B * args.steps / (ms_dev * 1e-3)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
@@ -265,7 +271,9 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "csbsr::conv_igemm_kernel", "achieved": achieved_tf, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src + " (sustained bf16)",
+                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
+                     "traffic_note": "dram__bytes_read+write of all conv launches of one step (profiles/r01_launches.md), bytes",
+                     "peak_source": peak_src + " (sustained bf16)",
                      "launches_per_step": n_conv, "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / (ms_dev / args.steps),
                      "useful_gflop_per_step": conv_useful / 1e9, "padded_gflop_per_step": conv_padded / 1e9,
                      "reference_dense_gflop_per_step": DENSE_GFLOP_PER_IMG * B,

@@ -76,6 +76,17 @@ _SIGNATURES = {
     "csbsr_blur_kernel_synth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "csbsr_resize_bicubic_aa": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "csbsr_degrade": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_void_p]),
+    "csbsr_sdf_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
+    "csbsr_sdf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csbsr_seg_loss_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "csbsr_seg_loss": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_float] * 3 + [C.c_void_p] * 5 +
+                       [C.c_size_t, C.c_void_p]),
+    "csbsr_seg_loss_wf_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "csbsr_seg_loss_wf_mean": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_void_p,
+                                                                                              C.c_size_t, C.c_void_p]),
+    "csbsr_sr_loss_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "csbsr_sr_loss": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_float] * 3 + [C.c_void_p, C.c_void_p, C.c_size_t,
+                                                                                 C.c_void_p]),
     "csbsr_metrics_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "csbsr_seg_metrics": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_double, C.c_void_p,
                                                                                          C.c_size_t, C.c_void_p]),

@@ -148,6 +148,35 @@ int csbsr_degrade(const float* hr, const double* params, float* kernels, float* 
                   int h, int w, int ksize, int factor, int clamp01, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Joint-training losses (csrc/losses.cu): forward values and the gradient w.r.t. the segmentation predictions.
+ * ------------------------------------------------------------------------------------------- */
+/* compute_sdf1_1 (model/utils/boundary_loss.py:40-67): normalised signed distance map of mask.astype(uint8), exact EDT,
+ * fp64 normalisation, 0 on the inner boundary; mask, sdf: fp32 [b,1,h,w] */
+size_t csbsr_sdf_workspace_bytes(int b, int h, int w);
+int csbsr_sdf(const float* mask, float* sdf, int b, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
+/* BoundaryComboLoss with out_map=False on the main and auxiliary heads (model/utils/loss_functions.py:49-74, 196-210,
+ * 284-345; combination model/modeling/build_model.py:258-278): loss[b] = main_w*l(p_main) + aux_w*l(p_aux),
+ * l = alpha*(WBCE + Dice)/2 + (1-alpha)*mean(p*sdf).  grad_* (optional): d(sum_b upstream[b]*loss[b])/dp */
+size_t csbsr_seg_loss_workspace_bytes(int b);
+int csbsr_seg_loss(const float* p_main, const float* p_aux, const float* target, const float* sdf, int b, int hw,
+                   float alpha, float main_w, float aux_w, float* loss, float* grad_main, float* grad_aux,
+                   const float* upstream, void* workspace, size_t workspace_bytes, void* stream);
+/* the scalar `.mean()` of the (B,B,H,W) tensor the reference builds when the failure-oriented weight w^F =
+ * exp(amp*|p_main.detach() - g|) is on (oriented_weight.py:73-83, build_model.py:422-438);
+ * `out`: device double */
+size_t csbsr_seg_loss_wf_workspace_bytes(int b, int hw);
+int csbsr_seg_loss_wf_mean(const float* p_main, const float* p_aux, const float* target, const float* sdf, int b, int hw,
+                           float alpha, float main_w, float aux_w, float wf_amp, double* out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* KBPNLoss.forward (model/utils/sr_loss_functions.py:39-56) given the pseudo-LR image of Get_pseudo_lr (:84-102, built
+ * with csbsr_blur_per_sample stride 1 + csbsr_resize_bicubic_aa): loss[b] = w_hr*mean|sr-hr| + w_lr*mean|plr-lr| +
+ * w_k*mean((k_pred-k_gt)^2); n_* = elements per sample */
+size_t csbsr_sr_loss_workspace_bytes(int b);
+int csbsr_sr_loss(const float* sr, const float* hr, const float* pseudo_lr, const float* lr, const float* k_pred,
+                  const float* k_gt, int b, int n_hr, int n_lr, int n_k, float w_hr, float w_lr, float w_k, float* loss,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Segmentation metrics (csrc/metrics.cu): AIU threshold sweep and the Hausdorff / mean-surface-distance
  * sweep, bit-exact with the reference.
  *   prob, mask: fp32 [b,1,h,w]; thresholds: fp32 [99] = float32(i*0.01), i = 1..99

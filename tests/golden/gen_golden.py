@@ -6,6 +6,7 @@ Outputs (small .npz files next to this script):
   degrade.npz         GaussianBlur.make kernels, conv_kernel2d blur and FactorResize outputs
   joint_model.npz     JointModel (KBPN + PSPNet) outputs on csbsr_b200.modeling.params.synth_state_dict weights
   joint_blurskip.npz  the same with DETECTOR_TYPE = PSPNet_BlurSkip
+  losses.npz          BoundaryComboLoss (+ w^F map mean), compute_sdf1_1 and KBPNLoss values / gradients
 """
 import os
 import sys
@@ -119,6 +120,61 @@ def gen_joint(blur_skip=False):
     print("joint_model.npz", sr.shape, seg.shape, kp.shape)
 
 
+def gen_losses():
+    """Loss values / gradients of the reference's own classes (BoundaryComboLoss, SegmentFailerOrientedExpWeight, KBPNLoss)."""
+    rh.setup()
+    import contextlib, io
+    from model.utils.loss_functions import BoundaryComboLoss
+    from model.utils.oriented_weight import SegmentFailerOrientedExpWeight
+    from model.utils.boundary_loss import compute_sdf1_1
+    from model.utils.sr_loss_functions import KBPNLoss
+    from model.data.transforms.transforms import FactorResize
+    cfg = rh.make_cfg()
+    _, mask = synthetic_case(3, 40, 56, 31)
+    g = torch.from_numpy(mask)
+    gen = torch.Generator().manual_seed(3)
+    p_main = (0.05 + 0.9 * torch.rand(3, 1, 40, 56, generator=gen))
+    p_main[0, 0, :3, :5] = 1e-9                                  # below the clamp
+    p_aux = (0.05 + 0.9 * torch.rand(3, 1, 40, 56, generator=gen))
+    out = {"mask": mask, "p_main": p_main.numpy(), "p_aux": p_aux.numpy()}
+    out["sdf"] = compute_sdf1_1(mask, mask.shape).astype(np.float32)
+    alpha = 0.37
+    for mode, out_map in (("plain", False), ("map", True)):
+        with contextlib.redirect_stdout(io.StringIO()):
+            fn = BoundaryComboLoss(per_epoch=10, resume_iter=0, pos_weight=[1, 1], loss_weight=[1, 1], decrease_ratio=1.0,
+                                   out_map=out_map)
+        fn.alpha = alpha
+        pm, pa = p_main.clone().requires_grad_(True), p_aux.clone().requires_grad_(True)
+        loss = 1.0 * fn(pm, g, iter_cnt=True) + 0.4 * fn(pa, g, iter_cnt=False)          # build_model.py:258-270
+        if out_map:
+            loss = SegmentFailerOrientedExpWeight(cfg, 1.0, 1.0)(pm, g) * loss           # build_model.py:433-434
+            out["map_shape"] = np.array(loss.shape)
+            out["map_mean"] = np.float64(loss.double().mean().item())
+            out["map_mean_f32"] = np.float32(loss.mean().item())
+        else:
+            out["plain_loss"] = loss.detach().numpy()
+            up = torch.tensor([0.3, 0.5, 0.2])
+            (loss * up).sum().backward()
+            out["plain_upstream"] = up.numpy()
+            out["plain_grad_main"] = pm.grad.numpy()
+            out["plain_grad_aux"] = pa.grad.numpy()
+    out["alpha"] = np.float32(alpha)
+    # KBPNLoss (weights [0.4, 0.4, 0, 2] -> kernel term weight 0)
+    sr = torch.rand(2, 3, 48, 64, generator=gen)
+    hr = torch.rand(2, 3, 48, 64, generator=gen)
+    lr = torch.rand(2, 3, 12, 16, generator=gen)
+    kv = torch.rand(2, 441, generator=gen)
+    kmap = kv.view(2, 441, 1, 1).expand(2, 441, 12, 16).contiguous()
+    kgt = torch.rand(2, 1, 21, 21, generator=gen); kgt = kgt / kgt.sum(dim=(2, 3), keepdim=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        kl = KBPNLoss(cfg, FactorResize(4, "bicubic"))
+    l, kp = kl(sr, hr, lr, kmap, kgt, None, None, 40000)
+    out.update({"sr": sr.numpy(), "hr": hr.numpy(), "lr": lr.numpy(), "kvec": kv.numpy(), "kgt": kgt.numpy(),
+                "kbpn_loss": l.numpy(), "kbpn_kernel": kp.numpy()})
+    np.savez_compressed(os.path.join(HERE, "losses.npz"), **out)
+    print("losses.npz", {k: np.asarray(v).shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["metrics", "degrade", "joint"]
     if "metrics" in which:
@@ -127,5 +183,7 @@ if __name__ == "__main__":
         gen_degrade()
     if "joint" in which:
         gen_joint()
+    if "losses" in which or not sys.argv[1:]:
+        gen_losses()
     if "blurskip" in which or not sys.argv[1:]:
         gen_joint(blur_skip=True)

@@ -1,0 +1,54 @@
+"""Parity of the loss kernels (C-ABI csbsr_sdf / csbsr_seg_loss / csbsr_seg_loss_wf_mean / csbsr_sr_loss) against the
+golden vectors produced by the UNMODIFIED reference classes and against the oracle restatement.
+Tolerances: SDF bit-exact (integer EDT, fp64 normalisation, fp32 store); loss values 2e-6 relative (fp64 accumulation
+here vs fp32 reductions in torch); gradients 1e-6 abs + 1e-4 rel."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "losses.npz")
+
+
+def test_sdf_bit_exact_vs_reference_golden_and_oracle():
+    from csbsr_b200.engine import losses as LS
+    from oracle import loss_ref as R
+    g = np.load(GOLD)
+    s = LS.compute_sdf(torch.from_numpy(g["mask"])).cpu().numpy()
+    assert np.array_equal(s, g["sdf"])
+    rng = np.random.default_rng(1)
+    m = (rng.random((3, 1, 61, 45)) < 0.2).astype(np.float32)
+    m[1] = 0                                              # empty mask -> zeros
+    m[2, 0, 10:30, 5:20] = 1
+    assert np.array_equal(LS.compute_sdf(torch.from_numpy(m)).cpu().numpy(), R.sdf(m).numpy())
+
+
+def test_seg_loss_values_and_gradients_vs_reference_golden():
+    from csbsr_b200.engine import losses as LS
+    g = np.load(GOLD)
+    pm, pa, m = (torch.from_numpy(g[k]) for k in ("p_main", "p_aux", "mask"))
+    loss, gm, ga = LS.seg_loss(pm, pa, m, float(g["alpha"]), upstream=torch.from_numpy(g["plain_upstream"]), need_grad=True)
+    assert np.allclose(loss.cpu().numpy(), g["plain_loss"], rtol=2e-6, atol=0)
+    assert np.allclose(gm.cpu().numpy(), g["plain_grad_main"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(ga.cpu().numpy(), g["plain_grad_aux"], rtol=1e-4, atol=1e-6)
+    assert (gm.cpu().numpy()[0, 0, :3, :5] == 0).all()        # below the clamp: no gradient
+
+
+def test_wf_loss_mean_vs_reference_golden():
+    from csbsr_b200.engine import losses as LS
+    g = np.load(GOLD)
+    pm, pa, m = (torch.from_numpy(g[k]) for k in ("p_main", "p_aux", "mask"))
+    out = LS.seg_loss_wf_mean(pm, pa, m, float(g["alpha"]), 1.0).item()
+    assert abs(out - float(g["map_mean"])) <= 2e-6 * abs(float(g["map_mean"]))
+
+
+def test_kbpn_loss_vs_reference_golden():
+    from csbsr_b200.engine import losses as LS
+    g = np.load(GOLD)
+    loss, kn = LS.kbpn_loss(*(torch.from_numpy(g[k]) for k in ("sr", "hr", "lr", "kvec", "kgt")))
+    assert np.allclose(loss.cpu().numpy(), g["kbpn_loss"], rtol=2e-5, atol=1e-7)
+    assert np.allclose(kn.cpu().numpy(), g["kbpn_kernel"], rtol=1e-5, atol=1e-9)
+    total = LS.calc_loss(loss, torch.tensor(0.25, device=loss.device), 0.3).item()
+    assert abs(total - (0.7 * float(g["kbpn_loss"].mean()) + 0.3 * 0.25)) < 1e-5

@@ -127,6 +127,21 @@ def test_network_oracle_matches_reference_golden(blur_skip):
     assert abs(seg.double().sum().item() - float(g["seg_checksum"])) <= 1e-2
 
 
+def test_loss_oracle_matches_reference_golden():
+    """oracle/loss_ref.py against the reference's own BoundaryComboLoss / w^F / compute_sdf1_1 / KBPNLoss outputs."""
+    from oracle import loss_ref as L
+    g = np.load(os.path.join(GOLD, "losses.npz"))
+    pm, pa, m = (torch.from_numpy(g[k]) for k in ("p_main", "p_aux", "mask"))
+    assert np.array_equal(L.sdf(g["mask"]).numpy(), g["sdf"])
+    assert np.array_equal(L.seg_loss(pm, pa, m, float(g["alpha"])).numpy(), g["plain_loss"])
+    lm = L.seg_loss(pm, pa, m, float(g["alpha"]), wf_amp=1.0)
+    assert tuple(lm.shape) == tuple(g["map_shape"]) == (3, 3, 40, 56)          # the (B,B,H,W) broadcasting quirk
+    assert lm.double().mean().item() == float(g["map_mean"])
+    kl, _, w = L.kbpn_loss(*(torch.from_numpy(g[k]) for k in ("sr", "hr", "lr")),
+                           torch.from_numpy(g["kvec"]).view(2, 441, 1, 1).expand(2, 441, 12, 16), torch.from_numpy(g["kgt"]))
+    assert np.allclose(kl.numpy(), g["kbpn_loss"], rtol=0, atol=1e-7) and np.allclose(w.numpy(), g["kbpn_kernel"], atol=1e-8)
+
+
 # ------------------------------------------------------------------ host logic
 def test_config_tree_reads_reference_yaml():
     from csbsr_b200.config import cfg
