@@ -32,51 +32,58 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
 // ------------------------------------------------------------------ 3-channel patch gather (im2col)
 // y[n,oh,ow,(r*S+s)*C+c] = f(x[n,c,oh*st+r*dil-pad, ow*st+s*dil-pad]) (0 outside), channels >= R*S*C zero.
 // f = identity, or clamp to [0,1] followed by (v-mean[n,c])*rstd[n,c] (clip_sr + norm_sr, build_model.py:135-146).
+// One block = an 8 x 32 tile of output pixels: the (clamped / normalised, zero-padded) input patch is staged once in
+// shared memory with coalesced reads, then each (pixel, 8-channel group) item is assembled from it and written as
+// one 128-bit store (consecutive items -> consecutive 16-byte chunks of a pixel's channel vector).
 __global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int H, int W,
                                 int OH, int OW, int R, int S, int stride, int pad, int pitch, int cwrite,
                                 const float* __restrict__ mean, const float* __restrict__ rstd, int clamp01) {
-    // lut[k] = (dy << 16) | (dx << 8) | c for the K = R*S*C gathered channels (no div/mod in the hot loop)
-    __shared__ int lut[256];
+    constexpr int TY = 8, TX = 32;
+    extern __shared__ float patch[];                 // [C][PH][PW]
+    __shared__ int lut[256];                         // gathered channel k -> offset inside the patch
+    const int PH = (TY - 1) * stride + R, PW = (TX - 1) * stride + S;
     const int K = R * S * C;
+    const int n = blockIdx.z;
+    const int oh0 = blockIdx.y * TY, ow0 = blockIdx.x * TX;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         const int c = k % C, rs = k / C;
-        lut[k] = ((rs / S) << 16) | ((rs % S) << 8) | c;
+        lut[k] = (c * PH + rs / S) * PW + rs % S;
+    }
+    const int ih0 = oh0 * stride - pad, iw0 = ow0 * stride - pad;
+    const size_t plane = static_cast<size_t>(H) * W;
+    const float* xn = x + static_cast<size_t>(n) * C * plane;
+    for (int i = threadIdx.x; i < C * PH * PW; i += blockDim.x) {
+        const int c = i / (PH * PW), r = (i / PW) % PH, col = i % PW;
+        const int ih = ih0 + r, iw = iw0 + col;
+        float v = 0.f;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+            v = xn[c * plane + static_cast<size_t>(ih) * W + iw];
+            if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+            if (mean) v = (v - mean[n * C + c]) * rstd[n * C + c];
+        }
+        patch[i] = v;
     }
     __syncthreads();
     const int G = cwrite / 8;
-    const size_t total = static_cast<size_t>(N) * OH * OW * G;
-    const size_t plane = static_cast<size_t>(H) * W;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i % G);
-        const size_t pix = i / G;
+    for (int item = threadIdx.x; item < TY * TX * G; item += blockDim.x) {
+        const int g = item % G, pixel = item / G;
+        const int ty = pixel / TX, tx = pixel % TX;
+        const int oh = oh0 + ty, ow = ow0 + tx;
+        if (oh >= OH || ow >= OW) continue;
         uint4 out = make_uint4(0, 0, 0, 0);
         if (g * 8 < K) {
-            const int ow = static_cast<int>(pix % OW);
-            const int oh = static_cast<int>((pix / OW) % OH);
-            const int n = static_cast<int>(pix / (static_cast<size_t>(OW) * OH));
-            const int ih0 = oh * stride - pad, iw0 = ow * stride - pad;
-            const float* xn = x + static_cast<size_t>(n) * C * plane;
+            const int base = (ty * PW + tx) * stride;
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int k = g * 8 + j;
-                float val = 0.f;
-                if (k < K) {
-                    const int e = lut[k];
-                    const int ih = ih0 + (e >> 16), iw = iw0 + ((e >> 8) & 0xFF), c = e & 0xFF;
-                    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-                        val = xn[c * plane + static_cast<size_t>(ih) * W + iw];
-                        if (clamp01) val = fminf(fmaxf(val, 0.f), 1.f);
-                        if (mean) val = (val - mean[n * C + c]) * rstd[n * C + c];
-                    }
-                }
-                v[j] = val;
+                v[j] = k < K ? patch[lut[k] + base] : 0.f;
             }
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&out);
 #pragma unroll
             for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
         }
+        const size_t pix = (static_cast<size_t>(n) * OH + oh) * OW + ow;
         *reinterpret_cast<uint4*>(y + pix * pitch + g * 8) = out;
     }
 }
@@ -454,10 +461,12 @@ extern "C" int csbsr_patchify(const float* x, void* y, int n, int c, int h, int 
                   "patchify: bad arguments (cwrite=%d, need >= %d)", cwrite, r * s * c);
     CSBSR_REQUIRE((mean == nullptr) == (rstd == nullptr), "patchify: mean/rstd must come together");
     CSBSR_REQUIRE(r * s * c <= 256 && r <= 255 && s <= 255 && c <= 255, "patchify: at most 256 gathered channels");
-    const size_t total = static_cast<size_t>(n) * oh * ow * (cwrite / 8);
-    patchify_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, c, h, w,
-                                                                     oh, ow, r, s, stride, pad, y_pitch, cwrite, mean,
-                                                                     rstd, clamp01);
+    const int ph = 7 * stride + r, pw = 31 * stride + s;
+    const size_t smem = sizeof(float) * static_cast<size_t>(c) * ph * pw;
+    CSBSR_REQUIRE(smem <= 48 * 1024, "patchify: patch of %zu bytes does not fit in shared memory", smem);
+    dim3 grid((ow + 31) / 32, (oh + 7) / 8, n);
+    patchify_kernel<<<grid, 256, smem, STREAM(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, c, h, w, oh, ow, r, s,
+                                                        stride, pad, y_pitch, cwrite, mean, rstd, clamp01);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -35,7 +35,8 @@ class JointModel(nn.Module):
         blur_dim = cfg.BLUR.KERNEL_SIZE_OUTPUT ** 2 if self.seg_model_name == "PSPNet_BlurSkip" else None
         self.segmentation_model = ParamTree(pspnet_param_shapes(cfg.MODEL.NUM_CLASSES, blur_dim=blur_dim))
         self.sr_model = ParamTree(kbpn_param_shapes(self.num_stages, 128, self.blur_ksize, self.ksize))
-        self.chunk = 8                      # images per pass through the engines (activation working set)
+        self.chunk = 8                      # images per pass through KBPN (activation working set)
+        self.seg_chunk = 32                 # images per pass through the segmentation net
         self._engines = None
         self._packed_version = None
 
@@ -67,7 +68,8 @@ class JointModel(nn.Module):
         x = x.to(device=device, dtype=torch.float32)          # MetaSRModel.mount_cuda, build_model.py:118-123
         sr_eng, ss_eng = self._ensure_engines(device)
         B = x.shape[0]
-        srs, segs, kps, auxs = [], [], [], []
+        srs, segs, kps, auxs, kvecs, stats = [], [], [], [], [], []
+        # KBPN in chunks of `chunk` images (its 448^2 x 512-channel activations dominate the working set) ...
         for i in range(0, B, self.chunk):
             xc = x[i:i + self.chunk].contiguous()
             b = xc.shape[0]
@@ -75,11 +77,22 @@ class JointModel(nn.Module):
             mean = torch.empty(b * 3, dtype=torch.float32, device=device)
             rstd = torch.empty(b * 3, dtype=torch.float32, device=device)
             K.clip_instnorm_stats(sr, mean, rstd, do_clip=True)            # clip_sr :143-146 + norm_sr stats :135-137
-            # PSPNet_BlurSkip also receives the (spatially constant) kernel map of KBPN (build_model.py:482-483, 498-500)
-            seg, aux = ss_eng.forward(sr, mean, rstd, kvec=kvec if self.seg_model_name == "PSPNet_BlurSkip" else None)
             kp = torch.empty_like(kvec)
             K.vec_normalize(kvec, kp)                                       # :491-494
-            srs.append(sr); segs.append(seg); kps.append(kp.view(b, 1, self.ksize, self.ksize)); auxs.append(aux)
+            srs.append(sr); kvecs.append(kvec); stats.append((mean, rstd))
+            kps.append(kp.view(b, 1, self.ksize, self.ksize))
+        sr_all = srs[0] if len(srs) == 1 else torch.cat(srs, 0)
+        kvec_all = kvecs[0] if len(kvecs) == 1 else torch.cat(kvecs, 0)
+        mean_all = torch.cat([m for m, _ in stats]); rstd_all = torch.cat([r for _, r in stats])
+        # ... the segmentation net in larger chunks: its 56^2 layers need more images to fill 148 SMs
+        blur = self.seg_model_name == "PSPNet_BlurSkip"
+        for i in range(0, B, self.seg_chunk):
+            j = min(B, i + self.seg_chunk)
+            # PSPNet_BlurSkip also receives the (spatially constant) kernel map of KBPN (build_model.py:482-483, 498-500)
+            seg, aux = ss_eng.forward(sr_all[i:j], mean_all[3 * i:3 * j].contiguous(), rstd_all[3 * i:3 * j].contiguous(),
+                                      kvec=kvec_all[i:j].contiguous() if blur else None)
+            segs.append(seg); auxs.append(aux)
+        srs = [sr_all]
         cat = (lambda l: l[0] if len(l) == 1 else torch.cat(l, 0))
         if return_aux:
             return cat(srs), cat(segs), cat(kps), cat(auxs)
