@@ -73,6 +73,9 @@ _SIGNATURES = {
     "csbsr_adaptive_avgpool_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
     "csbsr_bilinear_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 11 + [C.c_void_p]),
     "csbsr_bilinear_f32": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_bilinear_f32_sigmoid": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_bilinear_add_nhwc": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 14 + [C.c_void_p]),
+    "csbsr_softmax_gather": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),
     "csbsr_blur_kernel_synth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "csbsr_resize_bicubic_aa": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "csbsr_degrade": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_void_p]),

@@ -420,9 +420,77 @@ __global__ void bilinear_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_b
     }
 }
 
+// y = [relu](base + bilinear(x)): branch fusion of HighResolutionModule.forward (hrnet_backbone.py:274-288)
+__global__ void bilinear_add_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ base,
+                                         __nv_bfloat16* __restrict__ y, int N, int H, int W, int OH, int OW, int C, int xp,
+                                         int xo, int bp, int bo, int yp, int yo, int align, int relu) {
+    const int G = C / 8;
+    const size_t total = static_cast<size_t>(N) * OH * OW * G;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const size_t pix = i / G;
+        const int ow = static_cast<int>(pix % OW);
+        const int oh = static_cast<int>((pix / OW) % OH);
+        const int n = static_cast<int>(pix / (static_cast<size_t>(OW) * OH));
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilinear_src(oh, H, OH, align, y0, y1, ly);
+        bilinear_src(ow, W, OW, align, x0, x1, lx);
+        const __nv_bfloat16* src = x + static_cast<size_t>(n) * H * W * xp + xo + g * 8;
+        float a[8], b[8], c[8], d[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y0) * W + x0) * xp), a);
+        unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y0) * W + x1) * xp), b);
+        unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y1) * W + x0) * xp), c);
+        unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y1) * W + x1) * xp), d);
+        unpack8(*reinterpret_cast<const uint4*>(base + pix * bp + bo + g * 8), o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            o[j] += (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
+            if (relu) o[j] = fmaxf(o[j], 0.f);
+        }
+        *reinterpret_cast<uint4*>(y + pix * yp + yo + g * 8) = pack8(o);
+    }
+}
+
+// SpatialGather_Module.forward for one object class (spatial_ocr_block.py:59-66): ctx[n][c] = sum_hw softmax_hw(logit)[hw] *
+// feats[n][hw][c].  One block per (sample, 64-channel slab); the softmax statistics are recomputed per block (HW is small).
+__global__ void softmax_gather_kernel(const float* __restrict__ logits, const __nv_bfloat16* __restrict__ feats,
+                                      float* __restrict__ ctx, int HW, int C, int fp, int fo) {
+    __shared__ float red[32];
+    __shared__ float acc_s[4][64];
+    const int n = blockIdx.y, c0 = blockIdx.x * 64;
+    const float* lg = logits + static_cast<size_t>(n) * HW;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) m = fmaxf(m, lg[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int i = 1; i < (blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) sum += expf(lg[i] - m);
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) sum += red[i];
+    // 256 threads = 4 pixel lanes x 64 channels
+    const int c = threadIdx.x & 63, pl = threadIdx.x >> 6;
+    float acc = 0.f;
+    if (c0 + c < C) {
+        const __nv_bfloat16* f = feats + static_cast<size_t>(n) * HW * fp + fo + c0 + c;
+        for (int i = pl; i < HW; i += 4) acc += expf(lg[i] - m) * __bfloat162float(f[static_cast<size_t>(i) * fp]);
+    }
+    acc_s[pl][c] = acc;
+    __syncthreads();
+    if (pl == 0 && c0 + c < C) ctx[n * C + c0 + c] = (acc_s[0][c] + acc_s[1][c] + acc_s[2][c] + acc_s[3][c]) / sum;
+}
+
 // bilinear resize of planar f32 maps (aux head, align_corners=True; pspnet.py:122)
 __global__ void bilinear_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int NC, int H, int W, int OH,
-                                    int OW, int align) {
+                                    int OW, int align, int sigmoid) {
     const size_t total = static_cast<size_t>(NC) * OH * OW;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -434,8 +502,10 @@ __global__ void bilinear_f32_kernel(const float* __restrict__ x, float* __restri
         bilinear_src(oh, H, OH, align, y0, y1, ly);
         bilinear_src(ow, W, OW, align, x0, x1, lx);
         const float* b = x + static_cast<size_t>(nc) * H * W;
-        y[i] = (1.f - ly) * ((1.f - lx) * b[y0 * W + x0] + lx * b[y0 * W + x1]) +
-               ly * ((1.f - lx) * b[y1 * W + x0] + lx * b[y1 * W + x1]);
+        float v = (1.f - ly) * ((1.f - lx) * b[y0 * W + x0] + lx * b[y0 * W + x1]) +
+                  ly * ((1.f - lx) * b[y1 * W + x0] + lx * b[y1 * W + x1]);
+        if (sigmoid) v = 1.f / (1.f + expf(-v));
+        y[i] = v;
     }
 }
 
@@ -590,7 +660,40 @@ extern "C" int csbsr_bilinear_f32(const float* x, float* y, int nc, int h, int w
                                   void* stream) {
     CSBSR_REQUIRE(x && y && nc > 0, "bilinear_f32: bad arguments");
     const size_t total = static_cast<size_t>(nc) * oh * ow;
-    bilinear_f32_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, y, nc, h, w, oh, ow, align_corners);
+    bilinear_f32_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, y, nc, h, w, oh, ow, align_corners, 0);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_bilinear_f32_sigmoid(const float* x, float* y, int nc, int h, int w, int oh, int ow,
+                                          int align_corners, void* stream) {
+    CSBSR_REQUIRE(x && y && nc > 0, "bilinear_f32_sigmoid: bad arguments");
+    const size_t total = static_cast<size_t>(nc) * oh * ow;
+    bilinear_f32_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, y, nc, h, w, oh, ow, align_corners, 1);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_bilinear_add_nhwc(const void* x, const void* base, void* y, int n, int h, int w, int oh, int ow, int c,
+                                       int x_pitch, int x_coff, int b_pitch, int b_coff, int y_pitch, int y_coff,
+                                       int align_corners, int relu, void* stream) {
+    CSBSR_REQUIRE(x && base && y && c % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && b_pitch % 8 == 0 &&
+                      x_coff % 8 == 0 && y_coff % 8 == 0 && b_coff % 8 == 0,
+                  "bilinear_add_nhwc: channel counts/offsets must be multiples of 8");
+    const size_t total = static_cast<size_t>(n) * oh * ow * (c / 8);
+    bilinear_add_nhwc_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(base),
+        reinterpret_cast<__nv_bfloat16*>(y), n, h, w, oh, ow, c, x_pitch, x_coff, b_pitch, b_coff, y_pitch, y_coff,
+        align_corners, relu);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_softmax_gather(const float* logits, const void* feats, float* ctx, int n, int hw, int c, int f_pitch,
+                                    int f_coff, void* stream) {
+    CSBSR_REQUIRE(logits && feats && ctx && n > 0 && hw > 0 && c > 0, "softmax_gather: bad arguments");
+    softmax_gather_kernel<<<dim3((c + 63) / 64, n), 256, 0, STREAM(stream)>>>(
+        logits, reinterpret_cast<const __nv_bfloat16*>(feats), ctx, hw, c, f_pitch, f_coff);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -349,3 +349,25 @@ def bilinear_f32(x, y, align_corners=False):
     n, c, h, w = x.shape
     _call("csbsr_bilinear_f32", _f32(x), _f32(y), n * c, h, w, y.shape[2], y.shape[3], int(align_corners))
     return y
+
+
+def bilinear_f32_sigmoid(x, y, align_corners=True):
+    n, c, h, w = x.shape
+    _call("csbsr_bilinear_f32_sigmoid", _f32(x), _f32(y), n * c, h, w, y.shape[2], y.shape[3], int(align_corners))
+    return y
+
+
+def bilinear_add(x, base, y, align_corners=True, relu=False):
+    """y = [relu](base + bilinear(x)) (x is resampled to y's size; base / y may alias)."""
+    assert x.c == y.c == base.c and (base.h, base.w) == (y.h, y.w)
+    _call("csbsr_bilinear_add_nhwc", x.ptr(), base.ptr(), y.ptr(), x.n, x.h, x.w, y.h, y.w, x.c, x.pitch, x.coff,
+          base.pitch, base.coff, y.pitch, y.coff, int(align_corners), int(relu))
+    return y
+
+
+def softmax_gather(logits, feats, ctx, c=None):
+    """logits fp32 [N,1,H,W], feats Fmap -> ctx fp32 [N,C]."""
+    c = c or feats.c
+    _call("csbsr_softmax_gather", _f32(logits), feats.ptr(), _f32(ctx), feats.n, feats.h * feats.w, c, feats.pitch,
+          feats.coff)
+    return ctx

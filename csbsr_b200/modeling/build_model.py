@@ -8,7 +8,8 @@ from torch import nn
 from .. import _lib
 from .. import kernels as K
 from .kbpn import KBPNEngine
-from .params import ParamTree, kbpn_param_shapes, pspnet_param_shapes
+from .hrnet_ocr import HRNetOCREngine
+from .params import ParamTree, hrnet_ocr_param_shapes, kbpn_param_shapes, pspnet_param_shapes
 from .pspnet import PSPNetEngine
 
 
@@ -20,7 +21,7 @@ class JointModel(nn.Module):
         super().__init__()
         if cfg.MODEL.SR != "KBPN":
             raise NotImplementedError(cfg.MODEL.SR)
-        if cfg.MODEL.DETECTOR_TYPE not in ("PSPNet", "PSPNet_BlurSkip"):
+        if cfg.MODEL.DETECTOR_TYPE not in ("PSPNet", "PSPNet_BlurSkip", "HRNet_OCR"):
             raise NotImplementedError(cfg.MODEL.DETECTOR_TYPE)
         if cfg.MODEL.SCALE_FACTOR != 4:
             raise NotImplementedError("SCALE_FACTOR=%r" % (cfg.MODEL.SCALE_FACTOR,))
@@ -33,7 +34,10 @@ class JointModel(nn.Module):
         self.seg_model_name = cfg.MODEL.DETECTOR_TYPE
         self.norm_method = cfg.SOLVER.NORM_SR_OUTPUT
         blur_dim = cfg.BLUR.KERNEL_SIZE_OUTPUT ** 2 if self.seg_model_name == "PSPNet_BlurSkip" else None
-        self.segmentation_model = ParamTree(pspnet_param_shapes(cfg.MODEL.NUM_CLASSES, blur_dim=blur_dim))
+        if self.seg_model_name == "HRNet_OCR":
+            self.segmentation_model = ParamTree(hrnet_ocr_param_shapes(cfg.MODEL.NUM_CLASSES))
+        else:
+            self.segmentation_model = ParamTree(pspnet_param_shapes(cfg.MODEL.NUM_CLASSES, blur_dim=blur_dim))
         self.sr_model = ParamTree(kbpn_param_shapes(self.num_stages, 128, self.blur_ksize, self.ksize))
         self.chunk = 8                      # images per pass through KBPN (activation working set)
         self.seg_chunk = 32                 # images per pass through the segmentation net
@@ -54,7 +58,7 @@ class JointModel(nn.Module):
         if self._engines is None or self._packed_version != ver:
             sd = self.state_dict()
             sr = KBPNEngine(self.num_stages, 128, self.blur_ksize, self.ksize, self.scale_factor, device).load(sd)
-            ss = PSPNetEngine(device=device).load(sd)
+            ss = (HRNetOCREngine(device=device) if self.seg_model_name == "HRNet_OCR" else PSPNetEngine(device=device)).load(sd)
             self._engines = (sr, ss)
             self._packed_version = ver
         return self._engines

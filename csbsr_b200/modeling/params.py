@@ -131,6 +131,76 @@ def pspnet_param_shapes(n_classes=1, sizes=(1, 2, 3, 6), psp_size=512, deep_feat
     return P
 
 
+HRNET48_STAGES = (          # (modules, channels per branch): hrnet_ocr/backbones/hrnet/hrnet_config.py:46-73 (4 BASIC blocks each)
+    (1, (48, 96)),
+    (4, (48, 96, 192)),
+    (3, (48, 96, 192, 384)),
+)
+
+
+def hrnet_ocr_param_shapes(n_classes=1):
+    """OrderedDict name -> shape for `segmentation_model.*` when DETECTOR_TYPE = 'HRNet_OCR' (HRNet-W48 backbone +
+    OCR head: hrnet_ocr/nets/hrnet.py:101-135, backbones/hrnet/hrnet_backbone.py:108-290,295-512,
+    modules/spatial_ocr_block.py:114-280; every norm is nn.BatchNorm2d, bn_type 'torchbn')."""
+    P = OrderedDict()
+
+    def conv(name, co, ci, k, bias=False):
+        P[name + ".weight"] = (co, ci, k, k)
+        if bias:
+            P[name + ".bias"] = (co,)
+
+    b = "backbone."
+    conv(b + "conv1", 64, 3, 3); _bn(P, b + "bn1", 64)
+    conv(b + "conv2", 64, 64, 3); _bn(P, b + "bn2", 64)
+    inpl = 64
+    for i in range(4):                                   # layer1: 4 Bottlenecks, planes 64, expansion 4
+        p = b + "layer1.%d" % i
+        conv(p + ".conv1", 64, inpl, 1); _bn(P, p + ".bn1", 64)
+        conv(p + ".conv2", 64, 64, 3); _bn(P, p + ".bn2", 64)
+        conv(p + ".conv3", 256, 64, 1); _bn(P, p + ".bn3", 256)
+        if i == 0:
+            conv(p + ".downsample.0", 256, 64, 1); _bn(P, p + ".downsample.1", 256)
+        inpl = 256
+    pre = (256,)
+    for si, (modules, chans) in enumerate(HRNET48_STAGES, 2):
+        t = b + "transition%d" % (si - 1)
+        for i, c in enumerate(chans):                    # _make_transition_layer :402-447
+            if i < len(pre):
+                if c != pre[i]:
+                    conv(t + ".%d.0" % i, c, pre[i], 3); _bn(P, t + ".%d.1" % i, c)
+            else:
+                conv(t + ".%d.0.0" % i, c, pre[-1], 3); _bn(P, t + ".%d.0.1" % i, c)
+        for m in range(modules):
+            mp = b + "stage%d.%d" % (si, m)
+            for bi, c in enumerate(chans):
+                for k in range(4):
+                    bp = mp + ".branches.%d.%d" % (bi, k)
+                    conv(bp + ".conv1", c, c, 3); _bn(P, bp + ".bn1", c)
+                    conv(bp + ".conv2", c, c, 3); _bn(P, bp + ".bn2", c)
+            for i, ci in enumerate(chans):               # _make_fuse_layers :199-258
+                for j, cj in enumerate(chans):
+                    fp = mp + ".fuse_layers.%d.%d" % (i, j)
+                    if j > i:
+                        conv(fp + ".0", ci, cj, 1); _bn(P, fp + ".1", ci)
+                    elif j < i:
+                        for k in range(i - j):
+                            co = ci if k == i - j - 1 else cj
+                            conv(fp + ".%d.0" % k, co, cj, 3); _bn(P, fp + ".%d.1" % k, co)
+        pre = chans
+    conv("conv3x3.0", 512, 720, 3, bias=True); _bn(P, "conv3x3.1.0", 512)
+    o = "ocr_distri_head.object_context_block."
+    for name in ("f_pixel", "f_object"):
+        conv(o + name + ".0", 256, 512, 1, bias=True); _bn(P, o + name + ".1.0", 256)
+        conv(o + name + ".2", 256, 256, 1, bias=True); _bn(P, o + name + ".3.0", 256)
+    conv(o + "f_down.0", 256, 512, 1, bias=True); _bn(P, o + "f_down.1.0", 256)
+    conv(o + "f_up.0", 512, 256, 1, bias=True); _bn(P, o + "f_up.1.0", 512)
+    conv("ocr_distri_head.conv_bn_dropout.0", 512, 1024, 1, bias=True); _bn(P, "ocr_distri_head.conv_bn_dropout.1.0", 512)
+    conv("cls_head", n_classes, 512, 1, bias=True)
+    conv("aux_head.0", 720, 720, 3, bias=True); _bn(P, "aux_head.1.0", 720)
+    conv("aux_head.2", n_classes, 720, 1, bias=True)
+    return P
+
+
 _BUFFER_SUFFIXES = ("running_mean", "running_var", "num_batches_tracked")
 
 
@@ -176,6 +246,8 @@ def synth_state_dict(shapes, seed=1121, prefix=""):
             t = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
             if shape[0] == 1:                                # 1-channel heads: widen the logit range
                 t = t * 8.0
+            if name in ("cls_head.weight", "aux_head.2.weight"):   # HRNet features are O(30) with random BN stacks:
+                t = t * (0.03 / 8.0)                              # keep the head's logits O(1) instead of saturated
             if name.endswith("fe_cat.2.layer.weight"):       # keep the kernel refinement small (as after training):
                 t = t * 0.01                                 # sum(pre + delta) stays near 1 -> well-conditioned /sum
         elif leaf == "running_var":

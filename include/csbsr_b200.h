@@ -131,6 +131,18 @@ int csbsr_adaptive_avgpool_nhwc(const void* x, void* y, int n, int h, int w, int
 int csbsr_bilinear_nhwc(const void* x, void* y, int n, int h, int w, int oh, int ow, int c, int x_pitch, int x_coff,
                         int y_pitch, int y_coff, int align_corners, void* stream);
 int csbsr_bilinear_f32(const float* x, float* y, int nc, int h, int w, int oh, int ow, int align_corners, void* stream);
+/* sigmoid(F.interpolate(logits, bilinear, align_corners)) (hrnet_ocr/nets/hrnet.py:156-157) */
+int csbsr_bilinear_f32_sigmoid(const float* x, float* y, int nc, int h, int w, int oh, int ow, int align_corners,
+                               void* stream);
+/* y = [relu](base + F.interpolate(x, bilinear)): multi-resolution fusion of HighResolutionModule.forward
+ * (hrnet_ocr/backbones/hrnet/hrnet_backbone.py:274-288) */
+int csbsr_bilinear_add_nhwc(const void* x, const void* base, void* y, int n, int h, int w, int oh, int ow, int c,
+                            int x_pitch, int x_coff, int b_pitch, int b_coff, int y_pitch, int y_coff, int align_corners,
+                            int relu, void* stream);
+/* SpatialGather_Module.forward for one class (hrnet_ocr/modules/spatial_ocr_block.py:59-66): ctx[n][c] =
+ * sum_hw softmax_hw(logits[n])[hw] * feats[n][hw][c]; logits fp32 [n,hw], feats bf16 NHWC, ctx fp32 [n,c] */
+int csbsr_softmax_gather(const float* logits, const void* feats, float* ctx, int n, int hw, int c, int f_pitch,
+                         int f_coff, void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------

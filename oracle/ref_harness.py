@@ -74,7 +74,17 @@ def joint_model(cfg):
     setup()
     import contextlib
     import io
+    import model.modeling.build_model as bm
     from model.modeling.build_model import JointModel
+    if not _state.get("configer_patched"):        # H_48_D_4_composite.json names an ImageNet checkpoint that is not here
+        _orig = bm.set_configer
+
+        def _no_pretrained(path):
+            c = _orig(path)
+            c.update(["network", "pretrained"], None)
+            return c
+        bm.set_configer = _no_pretrained
+        _state["configer_patched"] = True
     with contextlib.redirect_stdout(io.StringIO()):
         m = JointModel(cfg)
     return m.eval()

@@ -226,11 +226,105 @@ def pspnet_forward(sd, x, prefix="segmentation_model.", sizes=(1, 2, 3, 6), kvec
     return seg, aux
 
 
-def joint_forward(sd, x, k_out=21, num_stages=4, blur_skip=False):
+HRNET48_STAGES = ((1, (48, 96)), (4, (48, 96, 192)), (3, (48, 96, 192, 384)))
+
+
+def _cbr(sd, p_conv, p_bn, x, stride=1, padding=0, relu=True):
+    y = _bn(sd, p_bn, _conv(sd, p_conv, x, stride=stride, padding=padding))
+    return F.relu(y) if relu else y
+
+
+def hrnet_w48(sd, p, x):
+    """HighResolutionNet.forward: hrnet_ocr/backbones/hrnet/hrnet_backbone.py:514-572 (stem :308-318, Bottleneck layer1,
+    transitions :402-447, HighResolutionModule.forward :265-290 with bilinear align_corners=True fusion)."""
+    x = _cbr(sd, p + "conv1", p + "bn1", x, stride=2, padding=1)
+    x = _cbr(sd, p + "conv2", p + "bn2", x, stride=2, padding=1)
+    for i in range(4):
+        bp = p + "layer1.%d" % i
+        out = _cbr(sd, bp + ".conv1", bp + ".bn1", x)
+        out = _cbr(sd, bp + ".conv2", bp + ".bn2", out, padding=1)
+        out = _cbr(sd, bp + ".conv3", bp + ".bn3", out, relu=False)
+        res = _cbr(sd, bp + ".downsample.0", bp + ".downsample.1", x, relu=False) if i == 0 else x
+        x = F.relu(out + res)
+    ys = [x]
+    pre = (256,)
+    for si, (modules, chans) in enumerate(HRNET48_STAGES, 2):
+        t = p + "transition%d" % (si - 1)
+        xs = []
+        for i, c in enumerate(chans):
+            if i < len(pre):
+                xs.append(_cbr(sd, t + ".%d.0" % i, t + ".%d.1" % i, ys[i], padding=1) if c != pre[i] else ys[i])
+            else:
+                xs.append(_cbr(sd, t + ".%d.0.0" % i, t + ".%d.0.1" % i, ys[-1], stride=2, padding=1))
+        for m in range(modules):
+            mp = p + "stage%d.%d" % (si, m)
+            for bi in range(len(chans)):
+                for k in range(4):
+                    bp = mp + ".branches.%d.%d" % (bi, k)
+                    out = _cbr(sd, bp + ".conv1", bp + ".bn1", xs[bi], padding=1)
+                    out = _cbr(sd, bp + ".conv2", bp + ".bn2", out, padding=1, relu=False)
+                    xs[bi] = F.relu(out + xs[bi])
+            fused = []
+            for i in range(len(chans)):
+                y = None
+                for j in range(len(chans)):
+                    fp = mp + ".fuse_layers.%d.%d" % (i, j)
+                    if j == i:
+                        term = xs[j]
+                    elif j > i:
+                        term = F.interpolate(_cbr(sd, fp + ".0", fp + ".1", xs[j], relu=False), size=xs[i].shape[-2:],
+                                             mode="bilinear", align_corners=True)
+                    else:
+                        term = xs[j]
+                        for k in range(i - j):
+                            term = _cbr(sd, fp + ".%d.0" % k, fp + ".%d.1" % k, term, stride=2, padding=1, relu=(k != i - j - 1))
+                    y = term if y is None else y + term
+                fused.append(F.relu(y))
+            xs = fused
+        ys = xs
+        pre = chans
+    return ys
+
+
+def hrnet_ocr_forward(sd, x, prefix="segmentation_model."):
+    """HRNet_W48_OCR.forward in eval mode: hrnet_ocr/nets/hrnet.py:137-158; SpatialGather_Module
+    modules/spatial_ocr_block.py:49-66; _ObjectAttentionBlock.forward :172-196; SpatialOCR_Module.forward :281-303."""
+    p = prefix
+    H, W = x.shape[2:]
+    ys = hrnet_w48(sd, p + "backbone.", x)
+    h, w = ys[0].shape[2:]
+    feats = torch.cat([ys[0]] + [F.interpolate(y, size=(h, w), mode="bilinear", align_corners=True) for y in ys[1:]], 1)
+    a = F.relu(_bn(sd, p + "aux_head.1.0", _conv(sd, p + "aux_head.0", feats, padding=1)))
+    out_aux = _conv(sd, p + "aux_head.2", a)
+    f = F.relu(_bn(sd, p + "conv3x3.1.0", _conv(sd, p + "conv3x3.0", feats, padding=1)))
+    B, C = f.shape[:2]
+    probs = F.softmax(out_aux.view(B, out_aux.shape[1], -1), dim=2)                       # (B, K=1, HW)
+    ctx = torch.matmul(probs, f.view(B, C, -1).permute(0, 2, 1)).permute(0, 2, 1).unsqueeze(3)   # (B, C, K, 1)
+    o = p + "ocr_distri_head.object_context_block."
+    def seq2(name, t):
+        t = F.relu(_bn(sd, o + name + ".1.0", _conv(sd, o + name + ".0", t)))
+        return F.relu(_bn(sd, o + name + ".3.0", _conv(sd, o + name + ".2", t)))
+    query = seq2("f_pixel", f).view(B, 256, -1).permute(0, 2, 1)
+    key = seq2("f_object", ctx).view(B, 256, -1)
+    value = F.relu(_bn(sd, o + "f_down.1.0", _conv(sd, o + "f_down.0", ctx))).view(B, 256, -1).permute(0, 2, 1)
+    sim = F.softmax((256 ** -0.5) * torch.matmul(query, key), dim=-1)
+    context = torch.matmul(sim, value).permute(0, 2, 1).contiguous().view(B, 256, h, w)
+    context = F.relu(_bn(sd, o + "f_up.1.0", _conv(sd, o + "f_up.0", context)))
+    q = p + "ocr_distri_head.conv_bn_dropout."
+    f2 = F.relu(_bn(sd, q + "1.0", _conv(sd, q + "0", torch.cat([context, f], 1))))
+    out = _conv(sd, p + "cls_head", f2)
+    up = lambda t: F.interpolate(t, size=(H, W), mode="bilinear", align_corners=True)
+    return torch.sigmoid(up(out)), torch.sigmoid(up(out_aux))
+
+
+def joint_forward(sd, x, k_out=21, num_stages=4, blur_skip=False, hrnet=False):
     """JointModel.forward (KBPN + PSPNet, NORM_SR_OUTPUT='instance'): model/modeling/build_model.py:466-496,
     clip_sr :143-146, norm_sr :135-137 (fresh InstanceNorm2d(3): eps 1e-5, biased variance, no affine)."""
     sr, kvec = kbpn_forward(sd, x, num_stages=num_stages, k_out=k_out)
     sr = sr.clamp(0.0, 1.0)
-    seg, aux = pspnet_forward(sd, F.instance_norm(sr, eps=1e-5), kvec=kvec if blur_skip else None)
+    if hrnet:
+        seg, aux = hrnet_ocr_forward(sd, F.instance_norm(sr, eps=1e-5))
+    else:
+        seg, aux = pspnet_forward(sd, F.instance_norm(sr, eps=1e-5), kvec=kvec if blur_skip else None)
     kp = kvec / kvec.sum(dim=1).view(-1, 1, 1, 1)
     return sr, seg, kp.view(-1, 1, k_out, k_out), aux

@@ -6,6 +6,7 @@ Outputs (small .npz files next to this script):
   degrade.npz         GaussianBlur.make kernels, conv_kernel2d blur and FactorResize outputs
   joint_model.npz     JointModel (KBPN + PSPNet) outputs on csbsr_b200.modeling.params.synth_state_dict weights
   joint_blurskip.npz  the same with DETECTOR_TYPE = PSPNet_BlurSkip
+  joint_hrnet.npz     the same with DETECTOR_TYPE = HRNet_OCR (HRNet-W48 + OCR head)
   losses.npz          BoundaryComboLoss (+ w^F map mean), compute_sdf1_1 and KBPNLoss values / gradients
 """
 import os
@@ -103,18 +104,21 @@ def gen_degrade():
     print("degrade.npz", {k: v.shape for k, v in out.items()})
 
 
-def gen_joint(blur_skip=False):
+def gen_joint(blur_skip=False, hrnet=False):
     from csbsr_b200.modeling import params as P
-    cfg = rh.make_cfg(detector="PSPNet_BlurSkip" if blur_skip else "PSPNet")
+    cfg = rh.make_cfg(detector="HRNet_OCR" if hrnet else "PSPNet_BlurSkip" if blur_skip else "PSPNet")
     m = rh.joint_model(cfg)
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-    sd.update(P.synth_state_dict(P.pspnet_param_shapes(blur_dim=441 if blur_skip else None), prefix="segmentation_model."))
+    if hrnet:
+        sd.update(P.synth_state_dict(P.hrnet_ocr_param_shapes(), prefix="segmentation_model."))
+    else:
+        sd.update(P.synth_state_dict(P.pspnet_param_shapes(blur_dim=441 if blur_skip else None), prefix="segmentation_model."))
     m.load_state_dict(sd, strict=True)
     g = torch.Generator().manual_seed(21)
     x = torch.rand(2, 3, 16, 24, generator=g)
     with torch.no_grad():
         sr, seg, kp = m(x.clone(), torch.zeros(2, 1, 7, 7))
-    np.savez_compressed(os.path.join(HERE, "joint_blurskip.npz" if blur_skip else "joint_model.npz"), x=x.numpy(), sr=sr.numpy().astype(np.float16),
+    np.savez_compressed(os.path.join(HERE, "joint_hrnet.npz" if hrnet else "joint_blurskip.npz" if blur_skip else "joint_model.npz"), x=x.numpy(), sr=sr.numpy().astype(np.float16),
                         seg=seg.numpy().astype(np.float16), kp=kp.numpy(),
                         sr_checksum=np.float64(sr.double().sum().item()), seg_checksum=np.float64(seg.double().sum().item()))
     print("joint_model.npz", sr.shape, seg.shape, kp.shape)
@@ -187,3 +191,5 @@ if __name__ == "__main__":
         gen_losses()
     if "blurskip" in which or not sys.argv[1:]:
         gen_joint(blur_skip=True)
+    if "hrnet" in which or not sys.argv[1:]:
+        gen_joint(hrnet=True)

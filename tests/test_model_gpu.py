@@ -108,3 +108,50 @@ def test_blurskip_joint_model_vs_oracle_and_golden():
     # and against the unmodified reference's own outputs (fp16-stored fixture)
     assert np.abs(seg.cpu().numpy() - g["seg"].astype(np.float32)).max() <= 5e-2
     assert np.abs(sr.cpu().numpy() - g["sr"].astype(np.float32)).max() <= 3e-2
+
+
+def _hrnet_model_and_sd():
+    from csbsr_b200.config import cfg
+    from csbsr_b200.modeling.build_model import JointModel
+    from csbsr_b200.modeling import params as P
+    c = cfg.clone()
+    c.merge_from_file("config/config_csbsr_pspnet.yaml")
+    c.MODEL.DETECTOR_TYPE = "HRNet_OCR"
+    c.SOLVER.TASK_LOSS_WEIGHT = 0.9
+    m = JointModel(c)
+    sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
+    sd.update(P.synth_state_dict(P.hrnet_ocr_param_shapes(), prefix="segmentation_model."))
+    m.load_state_dict(sd, strict=True)
+    return m, sd
+
+
+def test_hrnet_ocr_vs_oracle():
+    """HRNet-W48 + OCR head (config #4 detector) on a normalised image, against the fp32 oracle."""
+    from oracle import torch_ref as T
+    m, sd = _hrnet_model_and_sd()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(8)
+    img = torch.randn(2, 3, 128, 160, generator=g).cuda()
+    _, ss_eng = m._ensure_engines(torch.device("cuda", 0))
+    seg, aux = ss_eng.forward(img)
+    with torch.no_grad():
+        seg_ref, aux_ref = T.hrnet_ocr_forward(sdc, img)
+    torch.cuda.synchronize()
+    print("hrnet seg", (seg - seg_ref).abs().max().item(), (seg - seg_ref).abs().mean().item(), "aux", (aux - aux_ref).abs().max().item())
+    assert (seg - seg_ref).abs().mean().item() <= 5e-3 and (aux - aux_ref).abs().mean().item() <= 5e-3
+    assert (seg - seg_ref).abs().max().item() <= 8e-2 and (aux - aux_ref).abs().max().item() <= 8e-2
+
+
+def test_hrnet_joint_model_vs_reference_golden():
+    """JointModel(KBPN + HRNet_OCR) against the unmodified reference's outputs (tests/golden/joint_hrnet.npz)."""
+    import os
+    import numpy as np
+    m, sd = _hrnet_model_and_sd()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "joint_hrnet.npz"))
+    x = torch.from_numpy(g["x"])
+    sr, seg, kp = m(x, torch.zeros(x.shape[0], 1, 7, 7))
+    assert sr.shape == (2, 3, 64, 96) and seg.shape == (2, 1, 64, 96) and kp.shape == (2, 1, 21, 21)
+    d = np.abs(seg.cpu().numpy() - g["seg"].astype(np.float32))
+    print("hrnet joint seg", d.max(), d.mean())
+    assert d.max() <= 5e-2 and d.mean() <= 5e-3
+    assert np.abs(sr.cpu().numpy() - g["sr"].astype(np.float32)).max() <= 3e-2

@@ -110,16 +110,21 @@ def test_degrade_oracle_matches_reference_golden():
     assert abs(col[32 - 6].item() + 0.001709) < 1e-5 and abs(col[32 + 1].item() - 0.240967) < 1e-5
 
 
-@pytest.mark.parametrize("blur_skip", [False, True])
-def test_network_oracle_matches_reference_golden(blur_skip):
+@pytest.mark.parametrize("detector", ["PSPNet", "PSPNet_BlurSkip", "HRNet_OCR"])
+def test_network_oracle_matches_reference_golden(detector):
     """oracle/torch_ref.py against the real JointModel's outputs on the same synthetic weights (fp16-stored)."""
     from csbsr_b200.modeling import params as P
     from oracle import torch_ref as T
-    g = np.load(os.path.join(GOLD, "joint_blurskip.npz" if blur_skip else "joint_model.npz"))
+    blur_skip, hrnet = detector == "PSPNet_BlurSkip", detector == "HRNet_OCR"
+    g = np.load(os.path.join(GOLD, {"PSPNet": "joint_model.npz", "PSPNet_BlurSkip": "joint_blurskip.npz",
+                                    "HRNet_OCR": "joint_hrnet.npz"}[detector]))
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-    sd.update(P.synth_state_dict(P.pspnet_param_shapes(blur_dim=441 if blur_skip else None), prefix="segmentation_model."))
+    if hrnet:
+        sd.update(P.synth_state_dict(P.hrnet_ocr_param_shapes(), prefix="segmentation_model."))
+    else:
+        sd.update(P.synth_state_dict(P.pspnet_param_shapes(blur_dim=441 if blur_skip else None), prefix="segmentation_model."))
     with torch.no_grad():
-        sr, seg, kp, _ = T.joint_forward(sd, torch.from_numpy(g["x"]), blur_skip=blur_skip)
+        sr, seg, kp, _ = T.joint_forward(sd, torch.from_numpy(g["x"]), blur_skip=blur_skip, hrnet=hrnet)
     assert np.abs(sr.numpy() - g["sr"].astype(np.float32)).max() <= 1e-3        # fp16 storage of the fixture
     assert np.abs(seg.numpy() - g["seg"].astype(np.float32)).max() <= 1e-3
     assert np.abs(kp.numpy() - g["kp"]).max() <= 1e-5
