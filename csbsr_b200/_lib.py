@@ -50,6 +50,19 @@ class ConvDesc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("g", C.c_void_p),
+        ("n", C.c_int32), ("gh", C.c_int32), ("gw", C.c_int32), ("g_pitch", C.c_int32), ("g_coff", C.c_int32),
+        ("cg", C.c_int32),
+        ("s", C.c_void_p),
+        ("sh", C.c_int32), ("sw", C.c_int32), ("s_pitch", C.c_int32), ("s_coff", C.c_int32), ("cs", C.c_int32),
+        ("ntaps", C.c_int32), ("stride", C.c_int32),
+        ("dh", C.c_int8 * MAX_TAPS), ("dw", C.c_int8 * MAX_TAPS),
+        ("wg", C.c_void_p),
+    ]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/csbsr_b200.h declares
@@ -58,6 +71,7 @@ _SIGNATURES = {
     "csbsr_version": (C.c_int, []),
     "csbsr_device_ok": (C.c_int, []),
     "csbsr_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "csbsr_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
     "csbsr_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]),
     "csbsr_patchify": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 12 + [C.c_void_p, C.c_void_p, C.c_int,
                                                                             C.c_void_p]),

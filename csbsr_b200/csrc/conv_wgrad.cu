@@ -1,0 +1,298 @@
+// Weight-gradient GEMM of a convolution for sm_100a (training path):
+//
+//   Wg[m][tap][c] = sum over pixels (n, y, x) of  G[n, y, x, m] * S[n, y*stride + dh[tap], x*stride + dw[tap], c]
+//
+// For nn.Conv2d: G = dL/dy (NHWC bf16), S = the layer input, m = cout, c = cin.  For nn.ConvTranspose2d(8, 4, 2):
+// G = the layer input, S = dL/dy, m = cin, c = cout (the same expression with the roles swapped).  Replaces the cuDNN
+// wgrad behind loss.backward() (reference model/engine/trainer.py:57-72 -> autograd of kbpn.py:266-277).
+//
+// GEMM view: M = 128 channels of G, N = up to 128 channels of S per (tap, channel chunk) "unit", K = pixels.  Both
+// operands are pixel-major in memory, so they are fed to tcgen05.mma as MN-major 128B-swizzled tiles: a TMA box of
+// 64 pixels x 64 channels is exactly one [K = 64][MN = 64] slab.  Up to four units share one G tile per pipeline stage
+// and accumulate side by side in the 512 TMEM columns; the pixel range is split across CTAs and every CTA adds its
+// partial sums into the fp32 result with vector reductions (red.global.add.v4.f32).
+#include <cuda.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "../../include/csbsr_b200.h"
+
+namespace csbsr {
+
+static constexpr int kWgK = 64;                      // pixels per pipeline stage
+static constexpr int kWgBox = kWgK * 128;            // one TMA box: 64 pixels x 64 bf16 channels = 8 KB
+static constexpr int kWgThreads = 256;               // warp0 TMA, warp1 MMA (+TMEM alloc), warps 4-7 epilogue
+static constexpr int kWgMaxUnits = 4;                // 4 x 128 fp32 columns = all of TMEM
+static constexpr int kWgSmem = 200 * 1024;
+
+struct WgradParams {
+    int N, OH, OW, TH, TW, tiles_h, tiles_w, ptiles;
+    int stride, ntaps, ncs, cs_pad, units_total, upp, passes_per_m, npass, nsplit, tiles_per_split, nitems;
+    int stages, stage_bytes;
+    float* wg;
+    int* err_flag;
+    int8_t dh[CSBSR_MAX_TAPS], dw[CSBSR_MAX_TAPS];
+};
+
+// MN-major, 128B-swizzled operand: 8 pixel rows of 128 B form one swizzle atom (SBO = 1024 B between K groups of 8 pixels),
+// the next 64 channels live one TMA box further (LBO = 8 KB).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((static_cast<uint32_t>(kWgBox) >> 4) << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmS, const WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+    uint64_t* full_bar = bars;                 // [stages]
+    uint64_t* empty_bar = bars + 8;            // [stages]
+    uint64_t* tmem_full = bars + 16;
+    uint64_t* tmem_empty = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmG);
+        tma_prefetch_desc(&tmS);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tiles_h * p.tiles_w;
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+            const int split = item / p.npass, pass = item - split * p.npass;
+            const int mt = pass / p.passes_per_m, pl = pass - mt * p.passes_per_m;
+            const int u0 = pl * p.upp, u1 = min(u0 + p.upp, p.units_total);
+            const int t0 = split * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.ptiles);
+            for (int t = t0; t < t1; ++t, ++it) {
+                const int stage = it % p.stages;
+                const uint32_t par = (it / p.stages) & 1u;
+                mbar_wait(&empty_bar[stage], par ^ 1u, p.err_flag, 21);
+                if (elect_one_sync()) {
+                    const int img = t / tiles_per_img, tr = t - img * tiles_per_img;
+                    const int oy0 = (tr / p.tiles_w) * p.TH, ox0 = (tr % p.tiles_w) * p.TW;
+                    uint32_t bytes = 2 * kWgBox;
+                    for (int u = u0; u < u1; ++u) {
+                        const int csc = u % p.ncs;
+                        bytes += (min(128, p.cs_pad - csc * 128) / 64) * kWgBox;
+                    }
+                    mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                    uint32_t dst = smem_base + stage * p.stage_bytes;
+                    tma_load_4d(dst, &tmG, &full_bar[stage], mt * 128, ox0, oy0, img);
+                    tma_load_4d(dst + kWgBox, &tmG, &full_bar[stage], mt * 128 + 64, ox0, oy0, img);
+                    dst += 2 * kWgBox;
+                    for (int u = u0; u < u1; ++u) {
+                        const int tap = u / p.ncs, csc = u - tap * p.ncs;
+                        const int nb = min(128, p.cs_pad - csc * 128) / 64;
+                        const int sx = ox0 * p.stride + p.dw[tap], sy = oy0 * p.stride + p.dh[tap];
+                        for (int h = 0; h < nb; ++h)
+                            tma_load_4d(dst + h * kWgBox, &tmS, &full_bar[stage], csc * 128 + h * 64, sx, sy, img);
+                        dst += 2 * kWgBox;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        uint32_t it = 0, nitem = 0;
+        for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+            const int split = item / p.npass, pass = item - split * p.npass;
+            const int pl = pass % p.passes_per_m;
+            const int u0 = pl * p.upp, u1 = min(u0 + p.upp, p.units_total);
+            const int t0 = split * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.ptiles);
+            if (t1 <= t0) continue;
+            mbar_wait(tmem_empty, (nitem & 1u) ^ 1u, p.err_flag, 22);
+            tcgen05_fence_after();
+            for (int t = t0; t < t1; ++t, ++it) {
+                const int stage = it % p.stages;
+                const uint32_t par = (it / p.stages) & 1u;
+                mbar_wait(&full_bar[stage], par, p.err_flag, 23);
+                tcgen05_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t a_addr = smem_base + stage * p.stage_bytes;
+                    for (int u = u0; u < u1; ++u) {
+                        const int csc = u % p.ncs;
+                        const int nw = min(128, p.cs_pad - csc * 128);
+                        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                               (static_cast<uint32_t>(nw >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+                        const uint32_t b_addr = a_addr + 2 * kWgBox * (1 + (u - u0));
+                        const uint32_t d_addr = tmem_base + static_cast<uint32_t>((u - u0) * 128);
+#pragma unroll
+                        for (int k = 0; k < kWgK / 16; ++k)
+                            umma_bf16(d_addr, make_desc_mn(a_addr + k * 2048), make_desc_mn(b_addr + k * 2048), idesc,
+                                      (t > t0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (t == t1 - 1) umma_commit(tmem_full);
+                }
+                __syncwarp();
+            }
+            ++nitem;
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------ epilogue: TMEM -> red.add into the fp32 gradient
+        const int q = warp - 4;                           // TMEM lane quarter
+        uint32_t nitem = 0;
+        for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+            const int split = item / p.npass, pass = item - split * p.npass;
+            const int mt = pass / p.passes_per_m, pl = pass - mt * p.passes_per_m;
+            const int u0 = pl * p.upp, u1 = min(u0 + p.upp, p.units_total);
+            const int t0 = split * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.ptiles);
+            if (t1 <= t0) continue;
+            mbar_wait(tmem_full, nitem & 1u, p.err_flag, 24);
+            tcgen05_fence_after();
+            const int row = mt * 128 + q * 32 + lane;
+            float* wrow = p.wg + static_cast<size_t>(row) * p.ntaps * p.cs_pad;
+            for (int u = u0; u < u1; ++u) {
+                const int tap = u / p.ncs, csc = u - tap * p.ncs;
+                const int nw = min(128, p.cs_pad - csc * 128);
+                float* dst = wrow + static_cast<size_t>(tap) * p.cs_pad + csc * 128;
+                for (int c = 0; c < nw; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((u - u0) * 128 + c), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        red_add_v4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            ++nitem;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+typedef CUresult (*PFN_encodeTiledW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiledW wg_encode_fn() {
+    static PFN_encodeTiledW fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiledW>(ptr);
+    }
+    return fn;
+}
+static int* g_wg_err = nullptr;
+
+}  // namespace csbsr
+
+using namespace csbsr;
+
+extern "C" int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CSBSR_REQUIRE(d && d->g && d->s && d->wg, "conv_wgrad: null pointer");
+    CSBSR_REQUIRE(d->cg > 0 && d->cg % 64 == 0 && d->cs > 0 && d->cs % 64 == 0,
+                  "conv_wgrad: channel counts (%d, %d) must be positive multiples of 64", d->cg, d->cs);
+    CSBSR_REQUIRE(d->g_pitch % 8 == 0 && d->g_coff % 8 == 0 && d->s_pitch % 8 == 0 && d->s_coff % 8 == 0,
+                  "conv_wgrad: pitches / offsets must be multiples of 8");
+    CSBSR_REQUIRE(d->ntaps >= 1 && d->ntaps <= CSBSR_MAX_TAPS, "conv_wgrad: bad tap count %d", d->ntaps);
+    CSBSR_REQUIRE(d->stride >= 1 && d->stride <= 8, "conv_wgrad: bad stride %d", d->stride);
+    CSBSR_REQUIRE(d->n >= 1 && d->gh >= 1 && d->gw >= 1 && d->sh >= 1 && d->sw >= 1, "conv_wgrad: empty tensor");
+    PFN_encodeTiledW encode = wg_encode_fn();
+    CSBSR_REQUIRE(encode, "conv_wgrad: cuTensorMapEncodeTiled entry point unavailable");
+
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = d->n; p.OH = d->gh; p.OW = d->gw;
+    p.TW = d->gw > 8 ? 16 : 8;
+    p.TH = kWgK / p.TW;
+    p.tiles_h = (p.OH + p.TH - 1) / p.TH;
+    p.tiles_w = (p.OW + p.TW - 1) / p.TW;
+    p.ptiles = p.N * p.tiles_h * p.tiles_w;
+    p.stride = d->stride; p.ntaps = d->ntaps;
+    p.cs_pad = d->cs;
+    p.ncs = (d->cs + 127) / 128;
+    p.units_total = p.ntaps * p.ncs;
+    const int m_tiles = (d->cg + 127) / 128;
+    // units per pass: at most 4 (TMEM columns); spread the units evenly over the passes
+    const int min_passes = (p.units_total + kWgMaxUnits - 1) / kWgMaxUnits;
+    p.upp = (p.units_total + min_passes - 1) / min_passes;
+    p.passes_per_m = (p.units_total + p.upp - 1) / p.upp;
+    p.npass = m_tiles * p.passes_per_m;
+    const int sms = num_sms();
+    int nsplit = (2 * sms + p.npass - 1) / p.npass;
+    if (nsplit > p.ptiles) nsplit = p.ptiles;
+    if (nsplit < 1) nsplit = 1;
+    p.tiles_per_split = (p.ptiles + nsplit - 1) / nsplit;
+    p.nsplit = (p.ptiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    p.nitems = p.npass * p.nsplit;
+    p.stage_bytes = 2 * kWgBox * (1 + p.upp);
+    p.stages = (kWgSmem - 2048) / p.stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    CSBSR_REQUIRE(p.stages >= 2, "conv_wgrad: not enough shared memory for 2 stages");
+    p.wg = d->wg;
+    memcpy(p.dh, d->dh, sizeof(p.dh));
+    memcpy(p.dw, d->dw, sizeof(p.dw));
+    if (!g_wg_err) {
+        CSBSR_CHECK_CUDA(cudaMalloc(&g_wg_err, sizeof(int)));
+        CSBSR_CHECK_CUDA(cudaMemset(g_wg_err, 0, sizeof(int)));
+    }
+    p.err_flag = g_wg_err;
+    CSBSR_CHECK_CUDA(cudaMemsetAsync(d->wg, 0, sizeof(float) * static_cast<size_t>(m_tiles) * 128 * p.ntaps * p.cs_pad, stream));
+
+    CUtensorMap tmG, tmS;
+    {
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(d->g) + d->g_coff;
+        cuuint64_t dims[4] = {(cuuint64_t)d->cg, (cuuint64_t)d->gw, (cuuint64_t)d->gh, (cuuint64_t)d->n};
+        const cuuint64_t pb = (cuuint64_t)d->g_pitch * 2;
+        cuuint64_t strides[3] = {pb, pb * d->gw, pb * d->gw * d->gh};
+        cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&tmG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CSBSR_REQUIRE(r == CUDA_SUCCESS, "conv_wgrad: cuTensorMapEncodeTiled(G) failed with %d", (int)r);
+    }
+    {
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(d->s) + d->s_coff;
+        cuuint64_t dims[4] = {(cuuint64_t)d->cs, (cuuint64_t)d->sw, (cuuint64_t)d->sh, (cuuint64_t)d->n};
+        const cuuint64_t pb = (cuuint64_t)d->s_pitch * 2;
+        cuuint64_t strides[3] = {pb, pb * d->sw, pb * d->sw * d->sh};
+        cuuint32_t box[4] = {64, (cuuint32_t)(p.TW * d->stride), (cuuint32_t)(p.TH * d->stride), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+        CUresult r = encode(&tmS, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CSBSR_REQUIRE(r == CUDA_SUCCESS, "conv_wgrad: cuTensorMapEncodeTiled(S) failed with %d", (int)r);
+    }
+    const int smem_bytes = p.stages * p.stage_bytes + 1024 + 512;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CSBSR_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+        attr_set = true;
+    }
+    const int grid = p.nitems < sms ? p.nitems : sms;
+    conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tmG, tmS, p);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -254,6 +254,24 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
     return y
 
 
+def wgrad(g, s, taps, stride=1):
+    """Weight gradient wg[m][t][c] = sum_pix g[pix, m] * s[pix*stride + taps[t], c] (fp32 [round_up(g.c,128), T, s.c]).
+    `g`, `s`: Fmaps whose channel windows are multiples of 64; `taps`: list of (dh, dw)."""
+    d = _lib.WgradDesc()
+    assert g.c % 64 == 0 and s.c % 64 == 0 and g.n == s.n and len(taps) <= _lib.MAX_TAPS
+    d.g, d.n, d.gh, d.gw, d.g_pitch, d.g_coff, d.cg = g.ptr(), g.n, g.h, g.w, g.pitch, g.coff, g.c
+    d.s, d.sh, d.sw, d.s_pitch, d.s_coff, d.cs = s.ptr(), s.h, s.w, s.pitch, s.coff, s.c
+    d.ntaps, d.stride = len(taps), stride
+    for i, (dh, dw) in enumerate(taps):
+        d.dh[i], d.dw[i] = dh, dw
+    out = torch.empty((round_up(g.c, 128), len(taps), s.c), dtype=torch.float32, device=g.t.device)
+    d.wg = out.data_ptr()
+    rc = _lib.lib().csbsr_conv_wgrad(C.byref(d), _lib.stream_ptr())
+    _lib.check(rc, "csbsr_conv_wgrad")
+    _lib.count_launch("csbsr_conv_wgrad")
+    return out
+
+
 # ------------------------------------------------------------------ support-kernel launchers
 def _call(name, *args):
     rc = getattr(_lib.lib(), name)(*args, _lib.stream_ptr())

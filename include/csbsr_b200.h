@@ -85,6 +85,27 @@ typedef struct csbsr_conv_desc {
 int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Weight gradient of a convolution (csrc/conv_wgrad.cu): the cuDNN wgrad behind loss.backward()
+ * (model/engine/trainer.py:57-72 through autograd of nn.Conv2d / nn.ConvTranspose2d, kbpn.py:266-277).
+ *   wg[m][t][c] = sum_{n,y,x} g[n, y, x, m] * s[n, y*stride + dh[t], x*stride + dw[t], c]     (fp32)
+ * nn.Conv2d: g = dL/dy, s = layer input (m = cout, c = cin, dh = r*dilation - pad).
+ * nn.ConvTranspose2d: g = layer input, s = dL/dy (m = cin, c = cout, dh = r - pad, stride = the layer's stride).
+ * Both tensors are NHWC bf16 channel windows; cg and cs are multiples of 64 (zero-padded channels).
+ * `wg` holds round_up(cg, 128) * ntaps * cs floats and is overwritten.  Out-of-image taps read zeros.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct csbsr_wgrad_desc {
+    const void* g;
+    int32_t n, gh, gw, g_pitch, g_coff, cg;
+    const void* s;
+    int32_t sh, sw, s_pitch, s_coff, cs;
+    int32_t ntaps, stride;
+    int8_t dh[CSBSR_MAX_TAPS], dw[CSBSR_MAX_TAPS];
+    float* wg;
+} csbsr_wgrad_desc;
+
+int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * HBM-bound support kernels (csrc/support.cu).  NHWC tensors are bf16 with `*_pitch` channels per
  * pixel and a channel window starting at `*_coff`; planar tensors are fp32 NCHW.
  * ------------------------------------------------------------------------------------------- */
