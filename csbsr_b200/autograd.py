@@ -1,0 +1,135 @@
+"""Differentiable conv / transposed-conv ops on the tcgen05 engine (training path).
+
+Activations are NHWC bf16 tensors [N, H, W, Cp] with Cp = round_up(C, 64); the padding channels are always zero
+(zero weight rows / bias entries produce them, ReLU / PReLU / add / mul keep them).  Parameters stay fp32 in the
+reference's layouts (nn.Conv2d [Cout, Cin, R, S], nn.ConvTranspose2d [Cin, Cout, R, S]) so the optimizer and the
+checkpoints are unchanged; they are packed to bf16 per call.
+
+forward   y  = conv(x, w) + b                       -> csbsr_conv_igemm
+backward  dx = conv^T(dy, w)                        -> csbsr_conv_igemm with the transposed / flipped packing
+          dw = sum_pix dy (x) x                     -> csbsr_conv_wgrad
+          db = sum_pix dy                           (torch reduction)
+Replaces autograd through cuDNN for nn.Conv2d / nn.ConvTranspose2d (reference model/modeling/kbpn.py:190-277,
+pspnet_pytorch/extractors.py:37-70, trainer.py:57-72).
+"""
+import torch
+
+from . import kernels as K
+from .kernels import Fmap, round_up
+
+
+def cpad(c):
+    return round_up(c, 64)
+
+
+def to_nhwc(x, dtype=torch.bfloat16):
+    """fp32 NCHW -> NHWC bf16 with zero-padded channels (differentiable)."""
+    n, c, h, w = x.shape
+    y = x.permute(0, 2, 3, 1).to(dtype)
+    if cpad(c) != c:
+        y = torch.nn.functional.pad(y, (0, cpad(c) - c))
+    return y.contiguous()
+
+
+def to_nchw(x, c):
+    """NHWC (padded) -> fp32 NCHW with the first `c` channels (differentiable)."""
+    return x[..., :c].permute(0, 3, 1, 2).float()
+
+
+def _out_size(h, k, stride, pad, dil):
+    return (h + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+class _Conv2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation):
+        assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
+        co, ci, R, S = weight.shape
+        n, h, w, cp = x.shape
+        assert cp == cpad(ci), "input has %d channels, expected %d (padded %d)" % (cp, ci, cpad(ci))
+        oh, ow = _out_size(h, R, stride, padding, dilation), _out_size(w, S, stride, padding, dilation)
+        pc = K.pack_conv(weight, bias, stride=stride, padding=padding, dilation=dilation, cin_pad=cp, cout_pad=cpad(co))
+        y = Fmap.empty(n, oh, ow, cpad(co), device=x.device)
+        K.conv(Fmap(x), pc, y)
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (stride, padding, dilation, bias is not None)
+        return y.t
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        stride, padding, dilation, has_bias = ctx.cfg
+        co, ci, R, S = weight.shape
+        n, h, w, cp = x.shape
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if R == 8 and stride == 4 and padding == 2 and dilation == 1 and h == 4 * dy.shape[1] and w == 4 * dy.shape[2]:
+                pc = K.pack_deconv8s4(weight, cin_pad=dy.shape[3], cout_pad=cp)        # conv 8/4/2 <-> convT 8/4/2
+                g = Fmap.empty(n, h, w, cp, device=x.device)
+                K.conv(Fmap(dy), pc, g)
+            else:
+                src = dy
+                if stride > 1:                                                             # zero-stuffed gradient
+                    hs, ws = h + 2 * padding - dilation * (R - 1), w + 2 * padding - dilation * (S - 1)
+                    src = torch.zeros((n, hs, ws, dy.shape[3]), dtype=dy.dtype, device=dy.device)
+                    src[:, ::stride, ::stride][:, :dy.shape[1], :dy.shape[2]] = dy
+                wt = weight.detach().flip(2, 3).transpose(0, 1)
+                pc = K.pack_conv(wt, None, stride=1, padding=dilation * (R - 1) - padding, dilation=dilation,
+                                 cin_pad=dy.shape[3], cout_pad=cp)
+                g = Fmap.empty(n, h, w, cp, device=x.device)
+                K.conv(Fmap(src), pc, g)
+            dx = g.t
+        if ctx.needs_input_grad[1]:
+            taps = [(r * dilation - padding, s * dilation - padding) for r in range(R) for s in range(S)]
+            wg = K.wgrad(Fmap(dy), Fmap(x), taps, stride=stride)
+            dw = wg[:co, :, :ci].reshape(co, R, S, ci).permute(0, 3, 1, 2).contiguous()
+        if has_bias and ctx.needs_input_grad[2]:
+            db = dy[..., :co].sum(dim=(0, 1, 2), dtype=torch.float32)
+        return dx, dw, db, None, None, None
+
+
+class _Deconv8s4Fn(torch.autograd.Function):
+    """nn.ConvTranspose2d(kernel 8, stride 4, padding 2): reference DeconvBlock (kbpn.py:273-277)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        assert x.dtype == torch.bfloat16 and x.is_contiguous()
+        ci, co, R, S = weight.shape
+        assert R == 8 and S == 8
+        n, h, w, cp = x.shape
+        assert cp == cpad(ci)
+        pc = K.pack_deconv8s4(weight, bias, cin_pad=cp, cout_pad=cpad(co))
+        y = Fmap.empty(n, 4 * h, 4 * w, cpad(co), device=x.device)
+        K.conv(Fmap(x), pc, y)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y.t
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        ci, co, R, S = weight.shape
+        n, h, w, cp = x.shape
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            pc = K.pack_conv(weight, None, stride=4, padding=2, cin_pad=dy.shape[3], cout_pad=cp)
+            g = Fmap.empty(n, h, w, cp, device=x.device)
+            K.conv(Fmap(dy), pc, g)
+            dx = g.t
+        if ctx.needs_input_grad[1]:
+            taps = [(r - 2, s - 2) for r in range(8) for s in range(8)]
+            wg = K.wgrad(Fmap(x), Fmap(dy), taps, stride=4)
+            dw = wg[:ci, :, :co].reshape(ci, 8, 8, co).permute(0, 3, 1, 2).contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy[..., :co].sum(dim=(0, 1, 2), dtype=torch.float32)
+        return dx, dw, db
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1):
+    return _Conv2dFn.apply(x, weight, bias, stride, padding, dilation)
+
+
+def deconv8s4(x, weight, bias=None):
+    return _Deconv8s4Fn.apply(x, weight, bias)
