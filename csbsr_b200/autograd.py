@@ -133,3 +133,35 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1):
 
 def deconv8s4(x, weight, bias=None):
     return _Deconv8s4Fn.apply(x, weight, bias)
+
+
+class _PReLUFn(torch.autograd.Function):
+    """Single-parameter nn.PReLU on a bf16 map; the slope gradient sum_{x<0} dy*x is accumulated in fp32 on the device
+    (a bf16 reduction of that heavily cancelling sum is off by tens of percent)."""
+
+    @staticmethod
+    def forward(ctx, x, slope):
+        from . import _lib
+        assert x.dtype == torch.bfloat16 and x.is_contiguous() and slope.numel() == 1 and slope.dtype == torch.float32
+        y = torch.empty_like(x)
+        _lib.check(_lib.lib().csbsr_prelu_fwd(x.data_ptr(), y.data_ptr(), slope.data_ptr(), x.numel(), _lib.stream_ptr()),
+                   "csbsr_prelu_fwd")
+        _lib.count_launch("csbsr_prelu_fwd")
+        ctx.save_for_backward(x, slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _lib
+        x, slope = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        ds = torch.empty(1, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().csbsr_prelu_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), slope.data_ptr(), ds.data_ptr(),
+                                              x.numel(), _lib.stream_ptr()), "csbsr_prelu_bwd")
+        _lib.count_launch("csbsr_prelu_bwd")
+        return dx, ds.view(slope.shape)
+
+
+def prelu(x, slope):
+    return _PReLUFn.apply(x, slope)

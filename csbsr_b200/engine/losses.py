@@ -104,3 +104,57 @@ def kbpn_loss(sr, hr, lr, kvec, k_gt, weights=(0.4, 0.4, 0, 2), ksize=21, factor
 def calc_loss(sr_loss, segment_loss_mean, task_loss_weight):
     """trainer.calc_loss (trainer.py:406-430): (1-beta)*mean(sr_loss) + beta*mean(segment_loss)."""
     return (1 - task_loss_weight) * sr_loss.mean() + task_loss_weight * segment_loss_mean
+
+
+# ------------------------------------------------------------------ differentiable forms used by the training step
+class _SegLossFn(torch.autograd.Function):
+    """Per-sample BoundaryCombo loss (out_map=False) on the fused kernel; backward re-runs it with the upstream weights."""
+
+    @staticmethod
+    def forward(ctx, p_main, p_aux, target, sdf, alpha, main_w, aux_w):
+        ctx.save_for_backward(p_main, p_aux, target, sdf)
+        ctx.cfg = (alpha, main_w, aux_w)
+        return seg_loss(p_main, p_aux, target, alpha, main_w, aux_w, sdf=sdf)
+
+    @staticmethod
+    def backward(ctx, up):
+        p_main, p_aux, target, sdf = ctx.saved_tensors
+        alpha, main_w, aux_w = ctx.cfg
+        _, gm, ga = seg_loss(p_main, p_aux, target, alpha, main_w, aux_w, sdf=sdf, upstream=up, need_grad=True)
+        return gm, ga, None, None, None, None, None
+
+
+def seg_loss_train(p_main, p_aux, target, alpha, wf_amp=0.0, main_w=1.0, aux_w=0.4):
+    """MetaSSLossCalc.calc_ss_loss + JointModelWithLoss.multiple_weight (build_model.py:258-278, 422-438) as an autograd
+    node.  wf_amp == 0: per-sample (B,) loss on the fused fwd/bwd kernel.  wf_amp != 0: the reference's out_map=True
+    path, whose BCE map (B,1,H,W) + Dice term (B,H,W) broadcast to (B,B,H,W) before the w^F weight
+    exp(amp*|p.detach() - g|) multiplies it (loss_functions.py:196-210, 284-345; oriented_weight.py:80-83); formed with
+    elementwise torch ops (the SDF comes from the EDT kernel either way)."""
+    g = _f(target)
+    sdf = compute_sdf(g)
+    if wf_amp == 0:
+        return _SegLossFn.apply(p_main, p_aux, g, sdf, alpha, main_w, aux_w)
+
+    def combo(p):
+        p = p.clamp(min=1e-8)
+        wbce = -(g * torch.log(p + 1e-8) + (1 - g) * torch.log(1 - p + 1e-8)) / 2
+        dice = 1.0 / g.numel() - (2 * torch.sum(p * g, dim=1) + 1e-6) / (torch.sum(p.pow(2) + g.pow(2)) + 1e-6)
+        return alpha * ((wbce + dice) / 2) + (1 - alpha) * (p * sdf)
+
+    loss = main_w * combo(p_main) + aux_w * combo(p_aux)
+    return torch.exp(wf_amp * torch.abs(p_main.detach() - g)) * loss
+
+
+def kbpn_loss_train(sr, hr, lr, kvec, k_gt, weights=(0.4, 0.4, 0, 2), ksize=21, factor=4):
+    """KBPNLoss.forward (sr_loss_functions.py:39-56, Get_pseudo_lr :73-102) as an autograd graph: gradients reach the SR
+    image (through the L1 terms, the per-sample blur and the antialiased bicubic resize) and the kernel vector."""
+    import torch.nn.functional as F
+    from ..modeling.train_graph import blur_per_sample
+    k = kvec / kvec.sum(dim=1, keepdim=True)
+    plr = F.interpolate(blur_per_sample(sr, k, ksize, 1), size=(sr.shape[2] // factor, sr.shape[3] // factor),
+                        mode="bicubic", antialias=True, align_corners=False)
+    kn = k.view(-1, 1, ksize, ksize)
+    loss = weights[0] * (sr - hr).abs().mean((1, 2, 3)) + weights[1] * (plr - lr).abs().mean((1, 2, 3))
+    if weights[2] != 0:
+        loss = loss + weights[2] * ((kn - k_gt) ** 2).mean((1, 2, 3))
+    return loss, kn

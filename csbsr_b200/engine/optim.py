@@ -1,0 +1,76 @@
+"""Optimizer side of the training step (reference train.py:91-96, trainer.py:57-72): Adam on flat buffers with one
+fused kernel per step (csrc/train.cu), the LambdaLR(UpDownScheduler) factor, and the NCCL gradient all-reduce that
+replaces nn.DataParallel's scatter / gather (train.py:117-121)."""
+import torch
+
+from .. import _lib
+
+
+class UpDownScheduler:
+    """model/utils/lr_scheduler.py:31-43: x10 between main-phase iterations 70000 and 95000 when enabled."""
+
+    def __init__(self, pretrain_iter, resume_iter, scheduler_flag):
+        self.pretrain_iter, self.resume_iter, self.scheduler_flag = pretrain_iter, resume_iter, scheduler_flag
+
+    def __call__(self, _iter):
+        main = _iter - (self.pretrain_iter - 1) + self.resume_iter
+        return 10 if (70000 < main < 95000 and self.scheduler_flag) else 1
+
+
+class FusedAdam:
+    """torch.optim.Adam(params, lr, betas=(0.9, 0.999), eps=1e-8) semantics (no weight decay / amsgrad).
+
+    All parameters are re-pointed at views of ONE flat fp32 buffer, their .grad at views of a second one, so that
+    a step is a single elementwise kernel over the flat buffers (gradient zeroing for the next step fused in) and the
+    data-parallel gradient exchange is a handful of large NCCL all-reduces on slices of the flat gradient."""
+
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, lr_lambda=None, bucket_elems=1 << 25):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params)
+        dev = self.params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]            # 16-byte aligned slots
+        self.n = sum(sizes)
+        self.flat_p = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        off = 0
+        for p, sz in zip(self.params, sizes):
+            view = self.flat_p[off:off + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_g[off:off + p.numel()].view(p.shape)
+            off += sz
+        self.base_lr, self.betas, self.eps = lr, betas, eps
+        self.lr_lambda = lr_lambda
+        self.step_count = 0                   # optimizer steps taken
+        self.sched_count = 0                  # LambdaLR epoch counter (scheduler.step() calls)
+        self.bucket_elems = bucket_elems
+
+    @property
+    def lr(self):
+        return self.base_lr * (self.lr_lambda(self.sched_count) if self.lr_lambda else 1.0)
+
+    def zero_grad(self):
+        """Gradients are cleared inside step(); before the first step they are already zero."""
+        return None
+
+    def all_reduce_grads(self, group=None):
+        """SUM all-reduce of the flat gradient in large buckets; step() then scales by 1 / world_size."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return 1
+        for s in range(0, self.n, self.bucket_elems):
+            dist.all_reduce(self.flat_g[s:s + self.bucket_elems], op=dist.ReduceOp.SUM, group=group)
+        return dist.get_world_size(group)
+
+    def step(self, world_size=1):
+        self.step_count += 1
+        rc = _lib.lib().csbsr_adam_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
+                                        self.exp_avg_sq.data_ptr(), self.n, self.lr, self.betas[0], self.betas[1], self.eps,
+                                        self.step_count, 1.0 / world_size, 1, _lib.stream_ptr())
+        _lib.check(rc, "csbsr_adam_step")
+        _lib.count_launch("csbsr_adam_step")
+
+    def scheduler_step(self):
+        self.sched_count += 1

@@ -101,3 +101,88 @@ class JointModel(nn.Module):
         if return_aux:
             return cat(srs), cat(segs), cat(kps), cat(auxs)
         return cat(srs), cat(segs), cat(kps)
+
+
+class BoundaryComboSchedule:
+    """The attributes of BoundaryComboLoss the trainer pokes (loss_functions.py:26-41, 76-81; trainer.py:93-96,
+    497-508): alpha starts at 1 and drops by 0.01*decrease_ratio per epoch down to alpha_min."""
+
+    def __init__(self, per_epoch, resume_iter=0, alpha_min=0.01, decrease_ratio=1.0):
+        self.alpha_min, self.decrease_ratio, self.per_epoch = alpha_min, decrease_ratio, per_epoch
+        self.fix_alpha = False
+        self.iter = resume_iter % per_epoch
+        self.alpha = max(alpha_min, 1.0 - (resume_iter // per_epoch) * 0.01 * decrease_ratio)
+
+    def update_alpha(self):
+        if self.iter % self.per_epoch == 0 and self.alpha > self.alpha_min and not self.fix_alpha:
+            self.alpha -= 0.01 * self.decrease_ratio
+            self.iter = 1
+        else:
+            self.iter += 1
+
+
+class JointModelWithLoss(JointModel):
+    """JointModelWithLoss(cfg, num_train_ds, resume_iter, sr_transforms).forward(iter, x, sr_targets, segment_targets,
+    kernel_targets) -> (segment_loss, sr_loss, segment_preds, sr_preds, kernel_preds) -- reference build_model.py:323-416.
+
+    The returned losses carry an autograd graph whose conv / transposed-conv nodes run forward, dgrad and wgrad on the
+    tcgen05 engine (csbsr_b200/autograd.py, modeling/train_graph.py).  Supported: KBPN + PSPNet outside the pre-training
+    phases (iteration >= SOLVER.SR_PRETRAIN_ITER[1], all modules trainable), SEG_LOSS_FUNC 'BoundaryCombo', SR_LOSS_FUNC
+    'KBPN'.  In eval mode (`.eval()`), forward falls through to JointModel's engines."""
+
+    def __init__(self, cfg, num_train_ds, resume_iter=0, sr_transforms=None):
+        super().__init__(cfg)
+        if self.seg_model_name != "PSPNet":
+            raise NotImplementedError("training graph: DETECTOR_TYPE=%r" % (self.seg_model_name,))
+        if cfg.SOLVER.SEG_LOSS_FUNC != "BoundaryCombo" or cfg.SOLVER.SR_LOSS_FUNC != "KBPN":
+            raise NotImplementedError("training graph: SEG_LOSS_FUNC=%r SR_LOSS_FUNC=%r" %
+                                      (cfg.SOLVER.SEG_LOSS_FUNC, cfg.SOLVER.SR_LOSS_FUNC))
+        self.cfg = cfg
+        self.main_weight, self.aux_weight = cfg.SOLVER.SEG_MAIN_LOSS_WEIGHT, cfg.SOLVER.SEG_AUX_LOSS_WEIGHT
+        self.wf_amp = cfg.SOLVER.SEG_FAIL_ORIENTED_WEIGHT4SS_AMP
+        self.oriented_w_iter = cfg.SOLVER.ORIENTED_WEIGHT_ITER
+        self.sr_loss_weights = tuple(cfg.SOLVER.SR_LOSS_FUNC_SR_WEIGHT)          # [HR, LR, kernel, -] defaults.py:72
+        sr_pre = cfg.SOLVER.SR_PRETRAIN_ITER
+        seg_rsm = resume_iter - (sr_pre[1] - 1) if resume_iter > (sr_pre[1] - 1) else 0
+        self.ss_loss_fn = BoundaryComboSchedule(num_train_ds // cfg.SOLVER.BATCH_SIZE + 1, seg_rsm,
+                                                decrease_ratio=cfg.SOLVER.BOUNDARY_DEC_RATIO)
+        self.iter_cnt = True
+        self.dropout = True                       # parity harness switches Dropout2d off (masks are random)
+        self.freeze_bn = False                    # True: BatchNorm uses its running statistics in train mode too
+
+    def _tensors(self):
+        t = dict(self.named_parameters())
+        t.update(dict(self.named_buffers()))
+        return t
+
+    def forward(self, iter, x, sr_targets=None, segment_targets=None, kernel_targets=None):
+        from ..engine import losses as LS
+        from . import train_graph as TG
+        if not torch.cuda.is_available() or not _lib.lib().csbsr_device_ok():
+            raise _lib.CsbsrError("csbsr_b200 needs an sm_100 CUDA device; there is no CPU fallback")
+        cfg = self.cfg
+        for lo, hi in (cfg.SOLVER.SR_PRETRAIN_ITER, cfg.SOLVER.SEG_PRETRAIN_ITER, cfg.SOLVER.SR_SR_MODULE_PRETRAIN_ITER,
+                       cfg.SOLVER.SR_KERNEL_MODULE_PRETRAIN_ITER):
+            if lo <= iter < hi:
+                raise NotImplementedError("training graph covers the joint phase only (iteration %d is inside the "
+                                          "pre-training window [%d, %d))" % (iter, lo, hi))
+        device = torch.device("cuda", torch.cuda.current_device())
+        mv = lambda t: None if t is None else t.to(device=device, dtype=torch.float32)
+        x, sr_targets, segment_targets, kernel_targets = mv(x), mv(sr_targets), mv(segment_targets), mv(kernel_targets)
+        P = self._tensors()
+        was = torch.backends.cudnn.enabled
+        torch.backends.cudnn.enabled = False        # glue ops (BN, pooling, resampling) stay on native aten kernels
+        try:
+            sr, kvec = TG.kbpn_forward(P, x, self.num_stages, self.ksize, self.scale_factor)
+            normed = torch.nn.functional.instance_norm(sr, eps=1e-5)              # norm_sr, build_model.py:135-137
+            seg, aux = TG.pspnet_forward(P, normed, bn_training=self.training and not self.freeze_bn, dropout=self.dropout and self.training)
+            sr_loss, kernel_preds = LS.kbpn_loss_train(sr, sr_targets, x, kvec, kernel_targets, self.sr_loss_weights,
+                                                       self.ksize, self.scale_factor)
+            amp = self.wf_amp if self.oriented_w_iter <= iter else 0.0
+            if self.wf_amp != 0 and amp == 0:
+                raise NotImplementedError("out_map loss without the w^F weight (iteration < ORIENTED_WEIGHT_ITER)")
+            seg_loss = LS.seg_loss_train(seg, aux, segment_targets, self.ss_loss_fn.alpha, amp, self.main_weight,
+                                         self.aux_weight)
+        finally:
+            torch.backends.cudnn.enabled = was
+        return seg_loss, sr_loss, seg, sr, kernel_preds

@@ -1,0 +1,223 @@
+"""Training-mode forward of KBPN + PSPNet as an autograd graph over the tcgen05 conv Functions.
+
+Every dense conv / transposed conv runs forward, dgrad and wgrad on the csbsr_b200 engine (csbsr_b200/autograd.py);
+the elementwise / pooling / resampling / normalisation glue between them is plain aten (cuDNN disabled by the caller:
+no cuDNN kernel runs in the step).  Activations are NHWC bf16 with channels zero-padded to a multiple of 64; the SR
+image, the blur-kernel vectors and everything feeding the losses stay fp32.
+
+Mirrors, in train mode and outside the pre-training phases (iteration >= SR_PRETRAIN_ITER[1]):
+  KBPN.forward                      model/modeling/kbpn.py:84-116
+  KernelBackProjectionStageWithSFT  kbpn.py:172-189, KBlock :382-412, UpBlock :464-469, DownBlock :484-489,
+  SFTlayer :511-518, KernelPredictorLikeIKC :562-578, predictor_withGAP :320-341
+  PSPNet.forward                    model/modeling/pspnet_pytorch/pspnet.py:95-123 (BatchNorm batch statistics,
+                                    Dropout2d 0.3 / 0.15 / 0.1), ResNet extractors.py:150-161
+"""
+import torch
+import torch.nn.functional as F
+
+from ..autograd import conv2d, cpad, deconv8s4, prelu, to_nchw, to_nhwc
+from .params import RESNET34_LAYERS
+
+
+def _nchw(x):          # NHWC tensor -> NCHW view (channels_last strides), no copy
+    return x.permute(0, 3, 1, 2)
+
+
+def _nhwc(x):          # NCHW (channels_last) -> NHWC contiguous
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _cat(parts, real=None):
+    """Concatenate NHWC tensors along channels (taking the first real[i] channels of part i) and zero-pad to 64."""
+    if real is not None:
+        parts = [p[..., :r] for p, r in zip(parts, real)]
+    c = sum(p.shape[3] for p in parts)
+    if cpad(c) != c:
+        n, h, w, _ = parts[0].shape
+        parts = list(parts) + [torch.zeros((n, h, w, cpad(c) - c), dtype=parts[0].dtype, device=parts[0].device)]
+    return torch.cat(parts, dim=3)
+
+
+def _act(P, p, y, act):
+    if act == "prelu":
+        return prelu(y, P[p + ".act.weight"])
+    if act == "relu":
+        return F.relu(y)
+    if act == "lrelu":
+        return F.leaky_relu(y, 0.01)
+    return y
+
+
+def _convblock(P, p, x, stride=1, padding=0, act=None):
+    y = conv2d(x, P[p + ".layer.weight"], P.get(p + ".layer.bias"), stride=stride, padding=padding)
+    return _act(P, p, y, act)
+
+
+def _deconvblock(P, p, x, act="prelu"):
+    return _act(P, p, deconv8s4(x, P[p + ".layer.weight"], P.get(p + ".layer.bias")), act)
+
+
+def _gap(x, c):
+    return x[..., :c].mean(dim=(1, 2), dtype=torch.float32)          # [B, c] fp32
+
+
+def _upscale_kernel(vec, k_out):
+    k = int(round(vec.shape[1] ** 0.5))
+    return F.interpolate(vec.view(vec.shape[0], 1, k, k), size=(k_out, k_out), mode="bicubic")
+
+
+def _expand_vec(kvec, h, w):
+    """(B, 441) fp32 -> NHWC bf16 [B, h, w, 448] conditioning map (differentiable)."""
+    b, c = kvec.shape
+    v = F.pad(kvec, (0, cpad(c) - c)).to(torch.bfloat16)
+    return v.view(b, 1, 1, -1).expand(b, h, w, -1)
+
+
+def _kernel_predictor(P, p, sr_t, kvec, k_out):
+    n, H, W, _ = sr_t.shape
+    fsr = _convblock(P, p + ".fe_SR.0", sr_t, padding=1, act="relu")
+    fsr = _convblock(P, p + ".fe_SR.1", fsr, act="lrelu")
+    fsr = _convblock(P, p + ".fe_SR.2", fsr, padding=1, act="lrelu")
+    fsr = _convblock(P, p + ".fe_SR.3", fsr, padding=1, act="lrelu")
+    fsr = _convblock(P, p + ".fe_SR.4", fsr, padding=1, act="lrelu")
+    fh = _expand_vec(kvec, H, W).contiguous()
+    fh = _convblock(P, p + ".fe_kernel.0", fh, padding=1, act="lrelu")
+    fh = _convblock(P, p + ".fe_kernel.1", fh, padding=1, act="lrelu")
+    c = P[p + ".fe_SR.4.layer.weight"].shape[0]
+    d = _cat((fsr, fh), real=(c, c))
+    d = _convblock(P, p + ".fe_cat.0", d, act="lrelu")
+    d = _convblock(P, p + ".fe_cat.1", d, padding=1, act="lrelu")
+    d = _convblock(P, p + ".fe_cat.2", d, padding=1, act=None)
+    delta = _upscale_kernel(_gap(d, c), k_out).reshape(n, k_out * k_out)
+    return kvec + delta
+
+
+def blur_per_sample(img, kvec, k_out, stride):
+    """Depthwise cross-correlation of every sample with its own kernel (kbpn.py:395-402; sr_loss_functions.py:73-102).
+    img fp32 [B,3,H,W], kvec [B, k*k] -> [B,3,H/stride,W/stride]."""
+    b, c, h, w = img.shape
+    wgt = kvec.view(b, 1, 1, k_out, k_out).expand(b, c, 1, k_out, k_out).reshape(b * c, 1, k_out, k_out)
+    out = F.conv2d(img.reshape(1, b * c, h, w), wgt, stride=stride, padding=(k_out - 1) // 2, groups=b * c)
+    return out.view(b, c, out.shape[2], out.shape[3])
+
+
+def _up_block(P, p, x):
+    x = _convblock(P, p + ".conv", x, act="prelu")
+    h0 = _deconvblock(P, p + ".up_conv1", x)
+    l0 = _convblock(P, p + ".up_conv2", h0, stride=4, padding=2, act="prelu")
+    h1 = _deconvblock(P, p + ".up_conv3", l0 - x)
+    return h1 + h0
+
+
+def _down_block(P, p, x):
+    x = _convblock(P, p + ".conv", x, act="prelu")
+    l0 = _convblock(P, p + ".down_conv1", x, stride=4, padding=2, act="prelu")
+    h0 = _deconvblock(P, p + ".down_conv2", l0)
+    l1 = _convblock(P, p + ".down_conv3", h0 - x, stride=4, padding=2, act="prelu")
+    return l1 + l0
+
+
+def _k_block(P, p, concat_h, h, x_lr, kvec, k_out, scale):
+    sr_t = _convblock(P, p + ".sr_reconst", concat_h, padding=1)
+    d_kernel = _kernel_predictor(P, p + ".kernel_predictor", sr_t, kvec, k_out)
+    vec = d_kernel / d_kernel.sum(dim=1, keepdim=True)
+    pseudo_lr = blur_per_sample(to_nchw(sr_t, 3), vec, k_out, scale)
+    e_h = _deconvblock(P, p + ".up_conv1", to_nhwc(pseudo_lr - x_lr))
+    return h + e_h, vec
+
+
+def _sft(P, p, feats, kvec):
+    n, h, w, _ = feats.shape
+    c = _cat((feats, _expand_vec(kvec, h, w)[..., :kvec.shape[1]]))
+    def branch(name):
+        t = conv2d(c, P[p + ".SFT_%s_conv0.weight" % name], P[p + ".SFT_%s_conv0.bias" % name], padding=1)
+        return conv2d(F.leaky_relu(t, 0.1), P[p + ".SFT_%s_conv1.weight" % name], P[p + ".SFT_%s_conv1.bias" % name], padding=1)
+    return feats * torch.sigmoid(branch("scale")) + branch("shift")
+
+
+def kbpn_forward(P, x_lr, num_stages=4, k_out=21, scale=4, prefix="sr_model."):
+    """x_lr fp32 [B,3,h,w] -> (sr fp32 [B,3,4h,4w], kernel vector fp32 [B, 441] (normalised, as KBlock returns it))."""
+    p = prefix
+    f = to_nhwc(x_lr)
+    for i in (0, 2, 4, 6):
+        f = F.relu(conv2d(f, P[p + "feat.%d.weight" % i], P[p + "feat.%d.bias" % i], padding=1))
+    init_f = f
+    z = init_f
+    for i in range(3):
+        z = _convblock(P, p + "predictor.feat_ext.%d" % i, z, padding=1, act="prelu")
+    ke2 = P[p + "predictor.feat_ext.2.layer.weight"].shape[0]
+    ker = _upscale_kernel(_gap(z, ke2), k_out)
+    kvec = (ker / ker.sum(dim=(2, 3), keepdim=True)).reshape(x_lr.shape[0], k_out * k_out)
+    low, concat_h, concat_l = init_f, None, None
+    for s in range(num_stages):
+        sp = p + "back_projection_stages.%d" % s
+        h = _up_block(P, sp + ".up", low)
+        pre = h if concat_h is None else torch.cat((concat_h, h), dim=3)
+        h, kvec = _k_block(P, sp + ".kb", pre, h, x_lr, kvec, k_out, scale)
+        concat_h = h if concat_h is None else torch.cat((concat_h, h), dim=3)
+        if s < num_stages - 1:
+            low = _down_block(P, sp + ".down", concat_h)
+            concat_l = low if concat_l is None else torch.cat((concat_l, low), dim=3)
+            low = _sft(P, sp + ".sft", concat_l, kvec)
+    sr = to_nchw(_convblock(P, p + "output_conv", concat_h, padding=1), 3)
+    sr = sr + F.interpolate(x_lr, scale_factor=scale, mode="bicubic")
+    return sr, kvec
+
+
+# ---------------------------------------------------------------------------------------------- PSPNet (train mode)
+def _bn(P, p, x, training, momentum=0.1):
+    """BatchNorm2d on an NHWC tensor; train mode uses batch statistics and updates the running buffers in place."""
+    y = F.batch_norm(_nchw(x), P[p + ".running_mean"], P[p + ".running_var"], P[p + ".weight"], P[p + ".bias"],
+                     training=training, momentum=momentum, eps=1e-5)
+    if training and (p + ".num_batches_tracked") in P:
+        P[p + ".num_batches_tracked"] += 1
+    return _nhwc(y)
+
+
+def _drop(x, p, on):
+    return _nhwc(F.dropout2d(_nchw(x), p, training=True)) if (on and p > 0) else x
+
+
+def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_training=True, dropout=True):
+    """img fp32 [B,3,H,W] (already normalised) -> (seg, aux) fp32 [B,1,H,W]."""
+    p = prefix
+    H, W = img.shape[2:]
+    x = to_nhwc(img)
+    x = F.relu(_bn(P, p + "feats.bn1", conv2d(x, P[p + "feats.conv1.weight"], None, stride=2, padding=3), bn_training))
+    x = _nhwc(F.max_pool2d(_nchw(x), kernel_size=3, stride=2, padding=1))
+    x3 = None
+    for li, (planes, blocks, stride, dil) in enumerate(RESNET34_LAYERS, 1):
+        for b in range(blocks):
+            bp = p + "feats.layer%d.%d" % (li, b)
+            st = stride if b == 0 else 1
+            d = 1 if b == 0 else dil
+            out = F.relu(_bn(P, bp + ".bn1", conv2d(x, P[bp + ".conv1.weight"], None, stride=st, padding=d, dilation=d), bn_training))
+            out = _bn(P, bp + ".bn2", conv2d(out, P[bp + ".conv2.weight"], None, padding=d, dilation=d), bn_training)
+            res = x
+            if (bp + ".downsample.0.weight") in P:
+                res = _bn(P, bp + ".downsample.1", conv2d(x, P[bp + ".downsample.0.weight"], None, stride=st), bn_training)
+            x = F.relu(out + res)
+        if li == 3:
+            x3 = x
+    f = x
+    h, w = f.shape[1:3]
+    priors = []
+    for i, s in enumerate(sizes):
+        pooled = _nhwc(F.adaptive_avg_pool2d(_nchw(f), (s, s)))
+        pr = conv2d(pooled, P[p + "psp.stages.%d.1.weight" % i], None)
+        priors.append(_nhwc(F.interpolate(_nchw(pr), size=(h, w), mode="bilinear")))
+    priors.append(f)
+    y = F.relu(conv2d(torch.cat(priors, dim=3), P[p + "psp.bottleneck.weight"], P[p + "psp.bottleneck.bias"]))
+    y = _drop(y, 0.3, dropout)
+    for name, dp in (("up_1", 0.15), ("up_2", 0.15), ("up_3", 0.15)):      # drop_2 after every up block (pspnet.py:106-113)
+        y = _nhwc(F.interpolate(_nchw(y), size=(2 * y.shape[1], 2 * y.shape[2]), mode="bilinear"))
+        y = _bn(P, p + name + ".conv.1", conv2d(y, P[p + name + ".conv.0.weight"], P[p + name + ".conv.0.bias"], padding=1),
+                bn_training)
+        y = prelu(y, P[p + name + ".conv.2.weight"])
+        y = _drop(y, dp, dropout)
+    seg = torch.sigmoid(to_nchw(conv2d(y, P[p + "final.0.weight"], P[p + "final.0.bias"]), 1))
+    a = F.relu(_bn(P, p + "aux.1", conv2d(x3, P[p + "aux.0.weight"], None, padding=1), bn_training))
+    a = _drop(a, 0.1, dropout)
+    a = torch.sigmoid(to_nchw(conv2d(a, P[p + "aux.4.weight"], P[p + "aux.4.bias"]), 1))
+    aux = F.interpolate(a, size=(H, W), mode="bilinear", align_corners=True)
+    return seg, aux

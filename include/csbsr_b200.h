@@ -106,6 +106,20 @@ typedef struct csbsr_wgrad_desc {
 int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training-step support (csrc/train.cu).
+ * csbsr_prelu_fwd / _bwd: single-parameter PReLU on `n` bf16 values (n % 8 == 0); `slope` is a device float;
+ *   _bwd writes dx and overwrites *dslope with sum_{x<0} dy*x accumulated in fp32 (nn.PReLU of ConvBlock /
+ *   DeconvBlock, model/modeling/kbpn.py:190-248).
+ * csbsr_adam_step: torch.optim.Adam(lr, betas, eps) without weight decay / amsgrad on flat fp32 buffers of n
+ *   elements (n % 4 == 0): g is first multiplied by grad_scale (1/world_size after a SUM all-reduce), `step` counts
+ *   from 1 (bias corrections), zero_grad != 0 clears g for the next step (train.py:91; trainer.py:61,70).
+ * ------------------------------------------------------------------------------------------- */
+int csbsr_prelu_fwd(const void* x, void* y, const float* slope, long long n, void* stream);
+int csbsr_prelu_bwd(const void* x, const void* dy, void* dx, const float* slope, float* dslope, long long n, void* stream);
+int csbsr_adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                    int step, float grad_scale, int zero_grad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * HBM-bound support kernels (csrc/support.cu).  NHWC tensors are bf16 with `*_pitch` channels per
  * pixel and a channel window starting at `*_coff`; planar tensors are fp32 NCHW.
  * ------------------------------------------------------------------------------------------- */

@@ -65,7 +65,7 @@ def wf_weight(p, g, amp):
 
 def seg_loss(p_main, p_aux, g, alpha, main_w=1.0, aux_w=0.4, wf_amp=0.0):
     """-> per-sample loss (B,) when wf_amp == 0, else the (B,B,H,W) tensor of the reference."""
-    s = sdf(g.numpy()).to(p_main.device)
+    s = sdf(g.detach().cpu().numpy()).to(p_main.device)
     out_map = wf_amp != 0
     loss = main_w * boundary_combo(p_main, g, s, alpha, out_map) + aux_w * boundary_combo(p_aux, g, s, alpha, out_map)
     if out_map:

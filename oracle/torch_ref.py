@@ -150,7 +150,12 @@ def kbpn_forward(sd, x, num_stages=4, k_out=21, scale=4, prefix="sr_model.", ret
     return sr, kvec
 
 
+BN_TRAIN = False      # oracle/train_ref.py switches this on: BatchNorm uses batch statistics (model.train())
+
+
 def _bn(sd, p, x):
+    if BN_TRAIN:
+        return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], training=True, eps=1e-5)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
                         training=False, eps=1e-5)
 

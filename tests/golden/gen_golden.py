@@ -193,3 +193,81 @@ if __name__ == "__main__":
         gen_joint(blur_skip=True)
     if "hrnet" in which or not sys.argv[1:]:
         gen_joint(hrnet=True)
+
+
+def gen_train(bn_eval=False):
+    """One JointModelWithLoss forward + backward of the UNMODIFIED reference at iteration 40000 (all phases active,
+    w^F on, m^F = 1), Dropout2d disabled (p = 0) so the step is deterministic: losses and a sample of gradients.
+    bn_eval=True additionally puts the BatchNorm layers in eval mode (running statistics): with random weights and a
+    batch of 2, batch-statistics BN makes the gradients chaotic under bf16 rounding, so the GPU gradient-parity test
+    uses this well-conditioned variant and the batch-statistics variant checks losses / gradient norms."""
+    rh.setup()
+    import contextlib, io
+    from csbsr_b200.modeling import params as P
+    from model.modeling.build_model import JointModelWithLoss
+    from model.data.transforms.transforms import FactorResize
+    from model.engine.trainer import calc_loss
+    cfg = rh.make_cfg(wf_amp=1.0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = JointModelWithLoss(cfg, num_train_ds=100, resume_iter=40000, sr_transforms=FactorResize(4, "bicubic"))
+    sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
+    sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("sr_loss_fn") or "vgg" in k.lower() for k in missing), (missing, unexpected)
+    m.train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout2d):
+            mod.p = 0.0
+        if bn_eval and isinstance(mod, torch.nn.BatchNorm2d):
+            mod.eval()
+    alpha = 0.63
+    m.ss_loss_fn.alpha = alpha
+    m.ss_loss_fn.fix_alpha = True
+    _, mask_np = synthetic_case(2, 64, 96, 77)
+    rng = np.random.default_rng(79)
+    hr_np = np.clip(0.55 + 0.1 * rng.standard_normal((2, 3, 64, 96)) - 0.3 * mask_np, 0, 1).astype(np.float32)
+    hr = torch.from_numpy(hr_np)
+    mask = torch.from_numpy(mask_np)
+    g = torch.Generator().manual_seed(78)
+    lr = torch.nn.functional.interpolate(hr, size=(16, 24), mode="bicubic", antialias=True).clamp(0, 1)
+    kgt = torch.rand(2, 1, 21, 21, generator=g)
+    kgt = kgt / kgt.sum(dim=(2, 3), keepdim=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        seg_loss, sr_loss, seg, sr, kp = m(40000, lr.clone(), sr_targets=hr.clone(), segment_targets=mask.clone(),
+                                           kernel_targets=kgt.clone())
+
+        class A:
+            pass
+        loss, _, _ = calc_loss(seg_loss, 0.0, sr_loss, 0.0, 40000, cfg, A())
+    loss.backward()
+    out = {"hr": hr_np, "mask": mask_np, "lr": lr.numpy(), "kgt": kgt.numpy(), "alpha": np.float32(alpha),
+           "loss": np.float64(loss.item()), "seg_loss_mean": np.float64(seg_loss.mean().item()),
+           "sr_loss": sr_loss.detach().numpy(), "seg_loss_shape": np.array(seg_loss.shape),
+           "sr": sr.detach().numpy().astype(np.float16), "seg": seg.detach().numpy().astype(np.float16)}
+    names = ["sr_model.feat.0.weight", "sr_model.predictor.feat_ext.2.layer.weight",
+             "sr_model.back_projection_stages.0.up.up_conv1.layer.weight",
+             "sr_model.back_projection_stages.1.sft.SFT_scale_conv0.weight",
+             "sr_model.back_projection_stages.2.kb.kernel_predictor.fe_cat.2.layer.weight",
+             "sr_model.back_projection_stages.3.kb.sr_reconst.layer.weight", "sr_model.output_conv.layer.weight",
+             "segmentation_model.feats.conv1.weight", "segmentation_model.feats.layer3.2.conv1.weight",
+             "segmentation_model.feats.layer4.2.bn2.weight", "segmentation_model.psp.bottleneck.weight",
+             "segmentation_model.up_2.conv.0.weight", "segmentation_model.final.0.weight", "segmentation_model.aux.4.bias"]
+    params = dict(m.named_parameters())
+    norms = {}
+    for k, p_ in params.items():
+        if p_.grad is not None:
+            norms[k] = float(p_.grad.double().norm().item())
+    out["grad_norm_names"] = np.array(sorted(norms))
+    out["grad_norms"] = np.array([norms[k] for k in sorted(norms)])
+    for k in names:                      # flattened gradients, subsampled with a fixed stride to keep the fixture small
+        gflat = params[k].grad.numpy().astype(np.float32).reshape(-1)
+        stride = max(1, gflat.size // 20000)
+        out["grad:" + k] = gflat[::stride].astype(np.float16 if False else np.float32)
+        out["stride:" + k] = np.int64(stride)
+    np.savez_compressed(os.path.join(HERE, "train_step_bneval.npz" if bn_eval else "train_step.npz"), **out)
+    print("train_step.npz loss", loss.item(), "seg", seg_loss.mean().item(), "sr", sr_loss.detach().numpy(), "grads", len(norms))
+
+
+if __name__ == "__main__" and "train" in sys.argv[1:]:
+    gen_train()
+    gen_train(bn_eval=True)
