@@ -50,3 +50,14 @@ def unpack_metrics(packed):
     n = packed.shape[1] // 4
     p = packed.cpu().numpy()
     return (p[:, :n].astype("int64"), p[:, n:2 * n].astype("int64"), p[:, 2 * n:3 * n], p[:, 3 * n:])
+
+
+def allreduce_flat(flat, bucket_elems=1 << 25, group=None):
+    """Training exchange step: SUM all-reduce of the flat gradient buffer in large buckets (replaces nn.DataParallel's
+    gradient reduction, reference train.py:117-121).  Returns the world size; the optimizer scales by 1 / world_size."""
+    rank, ws = world()
+    if ws == 1:
+        return 1
+    for s in range(0, flat.numel(), bucket_elems):
+        dist.all_reduce(flat[s:s + bucket_elems], op=dist.ReduceOp.SUM, group=group)
+    return ws

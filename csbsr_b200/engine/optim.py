@@ -57,12 +57,8 @@ class FusedAdam:
 
     def all_reduce_grads(self, group=None):
         """SUM all-reduce of the flat gradient in large buckets; step() then scales by 1 / world_size."""
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-            return 1
-        for s in range(0, self.n, self.bucket_elems):
-            dist.all_reduce(self.flat_g[s:s + self.bucket_elems], op=dist.ReduceOp.SUM, group=group)
-        return dist.get_world_size(group)
+        from .distributed import allreduce_flat
+        return allreduce_flat(self.flat_g, self.bucket_elems, group)
 
     def step(self, world_size=1):
         self.step_count += 1

@@ -1,0 +1,73 @@
+"""Time the joint training step (config #3: batch 8 per GPU, 224^2 HR crops, iteration 40000, w^F on) on one GPU."""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--profile", action="store_true")
+    a = ap.parse_args()
+    from csbsr_b200 import _lib
+    from csbsr_b200.config import cfg
+    from csbsr_b200.engine.losses import calc_loss
+    from csbsr_b200.engine.optim import FusedAdam
+    from csbsr_b200.modeling import params as P
+    from csbsr_b200.modeling.build_model import JointModelWithLoss
+    c = cfg.clone()
+    c.merge_from_file("config/config_csbsr_pspnet.yaml")
+    c.SOLVER.SEG_FAIL_ORIENTED_WEIGHT4SS_AMP = 1.0
+    m = JointModelWithLoss(c, num_train_ds=1000, resume_iter=40000)
+    sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
+    sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+    m.load_state_dict(sd)
+    m.cuda().train()
+    opt = FusedAdam(m.parameters(), lr=c.SOLVER.LR)
+    g = torch.Generator().manual_seed(1)
+    B, S = a.batch, a.size
+    hr = torch.rand(B, 3, S, S, generator=g).cuda()
+    lr = torch.nn.functional.interpolate(hr, size=(S // 4, S // 4), mode="bicubic", antialias=True).clamp(0, 1)
+    mask = (torch.rand(B, 1, S, S, generator=g) > 0.9).float().cuda()
+    kgt = torch.rand(B, 1, 21, 21, generator=g).cuda()
+    kgt = kgt / kgt.sum(dim=(2, 3), keepdim=True)
+
+    def step(it):
+        seg_loss, sr_loss, *_ = m(it, lr, sr_targets=hr, segment_targets=mask, kernel_targets=kgt)
+        loss = calc_loss(sr_loss, seg_loss.mean(), c.SOLVER.TASK_LOSS_WEIGHT)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(a.warmup):
+        l = step(40000 + i)
+    torch.cuda.synchronize()
+    print("warm loss", l.item(), "mem GB", torch.cuda.max_memory_allocated() / 2 ** 30)
+    if a.profile:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(40010)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+    n0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        l = step(40020 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    print("train step %.1f ms  -> %.2f steps/s, %.1f img/s (batch %d, %dx%d)  loss %.4f  launches/step %s" %
+          (ms, 1000 / ms, B * 1000 / ms, B, S, S, l.item(), (_lib.LAUNCHES - n0) // a.steps))
+
+
+if __name__ == "__main__":
+    main()

@@ -58,3 +58,34 @@ def test_sharded_metrics_equal_single_process(B):
     assert np.array_equal(h2, hd) and np.array_equal(m2, msd)
     # AIU / AHD exactly as inference.py:171-173
     assert np.mean((i2 + 1e-5) / (u2 + 1e-5)) == np.mean((inter + 1e-5) / (union + 1e-5))
+
+
+def _grad_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from csbsr_b200.engine import distributed as D
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(1000, generator=g)
+    ws = D.allreduce_flat(flat, bucket_elems=256)                   # 4 buckets, the last one ragged
+    if rank == 0:
+        q.put((ws, (flat / ws).numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_is_mean_over_ranks():
+    """The training exchange step: bucketed SUM all-reduce of the flat gradient, scaled by 1 / world in the optimizer."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ws, got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = sum(torch.randn(1000, generator=torch.Generator().manual_seed(100 + r)) for r in range(2)) / 2
+    assert ws == 2 and np.allclose(got, ref.numpy(), rtol=0, atol=1e-7)
