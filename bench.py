@@ -129,6 +129,49 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- our arm
+def train_leg(args, c, dev, world, rank, timed):
+    """Second half of BASELINE.json's metric ("train steps/sec"): config #3, the joint training step at iteration 40000
+    (all phases active, w^F on with m^F = 1), 224^2 HR crops, 8 images per GPU: on-device degradation -> forward ->
+    calc_loss -> backward (conv dgrad / wgrad on the tcgen05 engine) -> NCCL gradient all-reduce -> fused Adam."""
+    import torch
+    from csbsr_b200 import _lib
+    from csbsr_b200.engine.optim import FusedAdam
+    from csbsr_b200.engine.trainer import train_step
+    from csbsr_b200.modeling.build_model import JointModelWithLoss
+    from csbsr_b200.utils import synth
+    tc = c.clone()
+    tc.SOLVER.SEG_FAIL_ORIENTED_WEIGHT4SS_AMP = 1.0
+    bt, size = 8, 224
+    m = JointModelWithLoss(tc, num_train_ds=1000, resume_iter=40000)
+    m.load_state_dict(synth.model_state_dict(), strict=True)
+    m.to(dev).train()
+    opt = FusedAdam(m.parameters(), lr=tc.SOLVER.LR)
+    hr, mask = synth.batch(1000 + rank * bt, bt, size)
+    hr, mask = hr.to(dev), mask.to(dev)
+    params = torch.as_tensor(synth.degradation_params(bt, seed=50 + rank)).to(dev)
+    it = [40000]
+
+    def step():
+        it[0] += 1
+        return train_step(m, opt, tc, it[0], hr, mask, params, world)[0]
+
+    for _ in range(3):
+        step()
+    l0 = _lib.LAUNCHES
+    ms, loss = timed(step, args.train_steps)
+    launches = (_lib.LAUNCHES - l0) // args.train_steps
+    ms /= args.train_steps
+    dense_tf = 3 * DENSE_GFLOP_PER_IMG * (size / HR) ** 2 * bt / 1e3 / (ms * 1e-3)
+    return {"metric": "CSBSR w/ PSPNet joint training steps/sec", "value": 1000.0 / ms, "unit": "steps/s",
+            "images_per_sec": world * bt * 1000.0 / ms, "ms_per_step": ms, "n_gpus": world, "batch_per_gpu": bt, "crop": size,
+            "steps": args.train_steps, "warmup": 3, "loss": float(loss.item()), "dtype": "bf16 activations / fp32 master weights",
+            "gpu_launches": int(launches),
+            "reference_dense_tflops_equiv_per_gpu": dense_tf,
+            "config": "iteration 40000 (joint phase), SR L1 + pseudo-LR L1 + BoundaryCombo with w^F (m^F=1), Dropout2d and "
+                      "BatchNorm batch statistics on, Adam lr 2e-5; gradients all-reduced over NCCL when n_gpus > 1; "
+                      "elementwise / pooling / BatchNorm glue between the convs is aten (cuDNN disabled)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -138,6 +181,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=8, help="images per pass through the network engines")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE metric part 2)")
+    ap.add_argument("--train-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -280,6 +325,8 @@ def main():
                      "reference_dense_tflops_equiv": DENSE_GFLOP_PER_IMG * B / 1e3 / (ms_dev / args.steps * 1e-3)},
         "clocks": clocks,
     }
+    if not args.no_train:
+        line["train"] = train_leg(args, c, dev, world, rank, timed)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
