@@ -285,9 +285,9 @@ def main():
     K.PROFILE = []
     step_device()
     torch.cuda.synchronize()
-    conv_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1, _ in K.PROFILE)
-    conv_useful = sum(u for _, _, _, _, u in K.PROFILE)
-    conv_padded = sum(f for _, f, _, _, _ in K.PROFILE)
+    conv_ms = sum(r[2].elapsed_time(r[3]) for r in K.PROFILE)
+    conv_useful = sum(r[4] for r in K.PROFILE)
+    conv_padded = sum(r[1] for r in K.PROFILE)
     n_conv = len(K.PROFILE)
     K.PROFILE = None
     peak_tf, peak_bw, peak_src = _peaks()

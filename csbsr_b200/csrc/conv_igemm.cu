@@ -52,6 +52,7 @@ struct ConvKParams {
     // tiles
     int tiles_h, tiles_w, m_tiles, n_tiles, nphases, total_tiles;
     int TH, TW, block_n, kchunks, ntaps, stride, stages;
+    int kb;              // K elements per pipeline chunk: 64 (128B swizzle rows), 32 (64B) or 16 (32B)
     int OH, OW, os, YH, YW, N;
     int out_mode, y_pitch, y_coff, cout_store;
     int bias_sn, bias_sc, cls_bw, act;
@@ -302,14 +303,15 @@ __device__ __forceinline__ void epilogue_units(const ConvKParams& p, const EpiRo
             const size_t pixo = static_cast<size_t>(er.oy) * p.YW + er.ox;
             const size_t base = (static_cast<size_t>(er.img) * p.y_pitch + p.y_coff) * plane + pixo;
             const size_t rbase = (static_cast<size_t>(er.img) * p.r32_pitch + p.r32_coff) * plane + pixo;
+            // y and r32 may be the same buffer (in-place accumulation), so the compiler cannot hoist the residual loads
+            // above the stores: read all of them first (16 loads in flight instead of one load-store chain per channel)
+            float rv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rv[i] = (p.r32 && c0 + i < p.cout_store) ? __ldg(p.r32 + rbase + (c0 + i) * plane) : 0.f;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int c = c0 + i;
-                if (c < p.cout_store) {
-                    float val = act_fn<ACT>(f[i], slope);
-                    if (p.r32) val += p.r32[rbase + c * plane];
-                    y32[base + c * plane] = val;
-                }
+                if (c < p.cout_store) y32[base + c * plane] = act_fn<ACT>(f[i], slope) + rv[i];
             }
         }
     }
@@ -323,9 +325,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x A tile][stages x B tile][barriers]
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_tile_bytes = p.block_n * kBlockK * 2;
+    const int b_tile_bytes = p.block_n * p.kb * 2;
     const int b_stage_bytes = p.G * b_tile_bytes;
-    const int b_total_bytes = p.stages * b_stage_bytes;
+    const int b_total_bytes = (p.stages * b_stage_bytes + 1023) & ~1023;      // keeps the staging panels 1024-B aligned
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + p.stages * p.a_stage_bytes;
     const int n_panels = p.block_n >> 6;                      // staged epilogue: 64-channel panels per tile
@@ -395,10 +397,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                             // one A box covers the G vertically shifted taps of the group (rows TH + (G-1)*dstep)
                             tma_load_4d(smem_u32(smem_a + stage * p.a_stage_bytes), &tmA, &full_bar[stage],
-                                        kc * kBlockK, iw0, ih0, img);
+                                        kc * p.kb, iw0, ih0, img);
                             for (int j = 0; j < p.G; ++j)
                                 tma_load_3d(smem_u32(smem_b + stage * b_stage_bytes + j * b_tile_bytes), &tmB,
-                                            &full_bar[stage], kc * kBlockK, nt * p.block_n, p.widx[gi + j]);
+                                            &full_bar[stage], kc * p.kb, nt * p.block_n, p.widx[gi + j]);
                         }
                         __syncwarp();
                         if (++stage == p.stages) {
@@ -414,13 +416,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.block_n >> 3) << 17) |
                                    (static_cast<uint32_t>(kBlockM >> 4) << 24);
-            // descriptor words: lo = (smem address >> 4) | LBO(1) << 16 ; hi = SBO(1024 B) | version 1 | 128B swizzle
-            const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            // descriptor words: lo = (smem address >> 4) | LBO(1) << 16 ; hi = SBO (8 rows of kb*2 bytes) | version 1 |
+            // swizzle mode of the row width (128B: 2, 64B: 4, 32B: 6)
+            const uint32_t row_bytes = static_cast<uint32_t>(p.kb) * 2u;
+            const uint32_t desc_hi = ((8u * row_bytes) >> 4) | (1u << 14) | ((p.kb == 64 ? 2u : (p.kb == 32 ? 4u : 6u)) << 29);
+            const int ksteps = p.kb >> 4;
             const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t a_stage16 = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
             const uint32_t b_stage16 = static_cast<uint32_t>(b_stage_bytes) >> 4;
-            const uint32_t a_shift16 = static_cast<uint32_t>(p.dstep * p.TW * 128) >> 4;   // vertical tap step inside the A box
+            const uint32_t a_shift16 = static_cast<uint32_t>(p.dstep * p.TW) * row_bytes >> 4;   // vertical tap step inside the A box
             const uint32_t b_tile16 = static_cast<uint32_t>(b_tile_bytes) >> 4;
             const int G = p.G;
             int stage = 0;
@@ -445,9 +450,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int j = 0; j < G; ++j) {
                             // +32 bytes per K=16 step inside the 128B swizzle row -> +2 in the >>4 address field
                             umma_bf16_lohi(tmem_d, ja, jb, desc_hi, idesc, acc);
-                            umma_bf16_lohi(tmem_d, ja + 2, jb + 2, desc_hi, idesc, 1u);
-                            umma_bf16_lohi(tmem_d, ja + 4, jb + 4, desc_hi, idesc, 1u);
-                            umma_bf16_lohi(tmem_d, ja + 6, jb + 6, desc_hi, idesc, 1u);
+                            if (ksteps == 4) {
+                                umma_bf16_lohi(tmem_d, ja + 2, jb + 2, desc_hi, idesc, 1u);
+                                umma_bf16_lohi(tmem_d, ja + 4, jb + 4, desc_hi, idesc, 1u);
+                                umma_bf16_lohi(tmem_d, ja + 6, jb + 6, desc_hi, idesc, 1u);
+                            } else if (ksteps == 2) {
+                                umma_bf16_lohi(tmem_d, ja + 2, jb + 2, desc_hi, idesc, 1u);
+                            }
                             acc = 1u;
                             ja += a_shift16;
                             jb += b_tile16;
@@ -645,7 +654,10 @@ using namespace csbsr;
 extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     CSBSR_REQUIRE(d && d->x && d->wgt && d->y, "conv_igemm: null pointer");
-    CSBSR_REQUIRE(d->cin > 0 && d->cin % kBlockK == 0, "conv_igemm: cin=%d must be a positive multiple of 64", d->cin);
+    CSBSR_REQUIRE(d->cin > 0 && (d->cin % kBlockK == 0 || d->cin == 32 || d->cin == 16),
+                  "conv_igemm: cin=%d must be a positive multiple of 64, or 32, or 16", d->cin);
+    const int kb = d->cin % kBlockK == 0 ? kBlockK : d->cin;         // K elements per chunk
+    const int a_tile_bytes = kBlockM * kb * 2;
     CSBSR_REQUIRE(d->cout_pad > 0 && d->cout_pad % 16 == 0, "conv_igemm: cout_pad=%d must be a multiple of 16",
                   d->cout_pad);
     CSBSR_REQUIRE(d->x_pitch % 8 == 0 && d->x_coff % 8 == 0, "conv_igemm: x pitch/offset must be multiples of 8");
@@ -707,7 +719,8 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     p.total_tiles = p.m_tiles * p.n_tiles * p.nphases;
     p.fd_ntiles = make_fastdiv(p.n_tiles); p.fd_nphases = make_fastdiv(p.nphases);
     p.fd_tiles_per_img = make_fastdiv(p.tiles_h * p.tiles_w); p.fd_tiles_w = make_fastdiv(p.tiles_w);
-    p.kchunks = d->cin / kBlockK;
+    p.kchunks = d->cin / kb;
+    p.kb = kb;
     p.ntaps = d->ntaps;
     p.stride = d->stride;
     // ---- tap grouping: taps of one phase that share dw and whose dh are dh0 + j*step (step a multiple of the conv
@@ -717,8 +730,8 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     int16_t g_widx[CSBSR_MAX_TAPS];
     memcpy(g_dh, d->dh, sizeof(g_dh)); memcpy(g_dw, d->dw, sizeof(g_dw)); memcpy(g_widx, d->widx, sizeof(g_widx));
     const int staging_bytes = staged ? 2 * (block_n / 64) * kATileBytes : 0;
-    const int smem_avail = kSmemBudget - 2048 - staging_bytes;
-    const int b_tile = block_n * kBlockK * 2;
+    const int smem_avail = kSmemBudget - 3072 - staging_bytes;
+    const int b_tile = block_n * kb * 2;
     int cand = 1, cand_groups = d->ntaps, cand_step = 0;
     int8_t n_dh[CSBSR_MAX_TAPS], n_dw[CSBSR_MAX_TAPS];
     int16_t n_widx[CSBSR_MAX_TAPS];
@@ -761,16 +774,16 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
             cand = gsz; cand_groups = ng0; cand_step = step / st;
         }
     }
-    int a_stage_bytes = kATileBytes, stages = 0;
+    int a_stage_bytes = a_tile_bytes, stages = 0;
     {
         // grouped taps when they leave >= 3 pipeline stages, else one tap per stage
-        const int a_b = (THh + (cand - 1) * cand_step) * TWh * 128;
+        const int a_b = (THh + (cand - 1) * cand_step) * TWh * kb * 2;
         const int st_g = cand > 1 ? smem_avail / (a_b + cand * b_tile) : 0;
         if (cand > 1 && st_g >= 3) {
             G = cand; ngroups = cand_groups; dstep = cand_step; a_stage_bytes = a_b; stages = st_g;
             memcpy(g_dh, n_dh, sizeof(g_dh)); memcpy(g_dw, n_dw, sizeof(g_dw)); memcpy(g_widx, n_widx, sizeof(g_widx));
         } else {
-            stages = smem_avail / (kATileBytes + b_tile);
+            stages = smem_avail / (a_tile_bytes + b_tile);
         }
     }
     const int stage_bytes = a_stage_bytes + G * b_tile;
@@ -818,28 +831,30 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     }
 
     // ---- tensor maps
+    const CUtensorMapSwizzle swz_in = kb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                               : (kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUtensorMap tmA, tmB;
     {
         const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(d->x) + d->x_coff;
         cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
         cuuint64_t strides[3] = {(cuuint64_t)d->x_pitch * 2, (cuuint64_t)d->x_pitch * 2 * d->w,
                                  (cuuint64_t)d->x_pitch * 2 * d->w * d->h};
-        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.TW * d->stride),
+        cuuint32_t box[4] = {(cuuint32_t)kb, (cuuint32_t)(p.TW * d->stride),
                              (cuuint32_t)((p.TH + (G - 1) * dstep) * d->stride), 1};
         cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
         CSBSR_REQUIRE(box[1] <= 256 && box[2] <= 256, "conv_igemm: TMA box too large");
         CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz_in, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         CSBSR_REQUIRE(r == CUDA_SUCCESS, "conv_igemm: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)d->cout_pad, (cuuint64_t)d->w_taps};
         cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * d->cout_pad};
-        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n, 1};
+        cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)block_n, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d->wgt, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz_in, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         CSBSR_REQUIRE(r == CUDA_SUCCESS, "conv_igemm: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
@@ -880,7 +895,7 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
         CSBSR_REQUIRE(r == 0, "conv_igemm: cuTensorMapEncodeTiled(R) failed with %d", r);
     }
 
-    const int smem_bytes = stages * stage_bytes + staging_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
+    const int smem_bytes = stages * stage_bytes + staging_bytes + 2048 /*align slack (base + staging)*/ + 512 /*barriers*/;
     static int smem_attr_set = 0;
     if (smem_attr_set < smem_bytes) {
         CSBSR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

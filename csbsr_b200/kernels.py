@@ -176,6 +176,7 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
     d.n, d.h, d.w = x.n, x.h, x.w
     d.x_pitch, d.x_coff, d.cin = x.pitch, x.coff, pc.cin_pad
     assert x.c >= pc.cin_pad or x.coff + pc.cin_pad <= x.pitch, "input window narrower than packed K"
+    assert pc.cin_pad % 64 == 0 or pc.cin_pad in (16, 32), "packed K must be a multiple of 64, or 32 / 16"
     d.wgt = pc.wp.data_ptr()
     d.w_taps, d.cout_pad = pc.wp.shape[0], pc.cout_pad
     d.nphases, d.ntaps, d.stride = pc.nphases, pc.ntaps, pc.stride
@@ -248,9 +249,13 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
         e1.record()
         flops = 2.0 * x.n * d.oh * d.ow * pc.nphases * pc.ntaps * pc.cin_pad * pc.cout_pad
         useful = 2.0 * x.n * d.oh * d.ow * pc.nphases * pc.macs_per_pixel
+        # algorithmic HBM bytes: the input window once, the stored output once, each residual operand once
+        out_b = x.n * d.oh * d.ow * pc.nphases * d.cout_store * (2 if d.out_mode == OUT_BF16_NHWC else 4)
+        nres = sum(r is not None for r in (r0, rm, r1)) + (2 if r32 is not None else 0)
+        nbytes = x.n * x.h * x.w * pc.cin_pad * 2.0 + out_b * (1 + nres)
         PROFILE.append(("conv n%d %dx%d cin%d cout%d taps%dx%d s%d" % (x.n, d.oh, d.ow, pc.cin_pad, pc.cout_pad,
                                                                         pc.nphases, pc.ntaps, pc.stride), flops, e0, e1,
-                        useful))
+                        useful, nbytes))
     return y
 
 

@@ -132,7 +132,7 @@ class JointModelWithLoss(JointModel):
 
     def __init__(self, cfg, num_train_ds, resume_iter=0, sr_transforms=None):
         super().__init__(cfg)
-        if self.seg_model_name != "PSPNet":
+        if self.seg_model_name not in ("PSPNet", "HRNet_OCR"):
             raise NotImplementedError("training graph: DETECTOR_TYPE=%r" % (self.seg_model_name,))
         if cfg.SOLVER.SEG_LOSS_FUNC != "BoundaryCombo" or cfg.SOLVER.SR_LOSS_FUNC != "KBPN":
             raise NotImplementedError("training graph: SEG_LOSS_FUNC=%r SR_LOSS_FUNC=%r" %
@@ -175,7 +175,9 @@ class JointModelWithLoss(JointModel):
         try:
             sr, kvec = TG.kbpn_forward(P, x, self.num_stages, self.ksize, self.scale_factor)
             normed = torch.nn.functional.instance_norm(sr, eps=1e-5)              # norm_sr, build_model.py:135-137
-            seg, aux = TG.pspnet_forward(P, normed, bn_training=self.training and not self.freeze_bn, dropout=self.dropout and self.training)
+            seg_fwd = TG.hrnet_ocr_forward if self.seg_model_name == "HRNet_OCR" else TG.pspnet_forward
+            seg, aux = seg_fwd(P, normed, bn_training=self.training and not self.freeze_bn,
+                               dropout=self.dropout and self.training)
             sr_loss, kernel_preds = LS.kbpn_loss_train(sr, sr_targets, x, kvec, kernel_targets, self.sr_loss_weights,
                                                        self.ksize, self.scale_factor)
             amp = self.wf_amp if self.oriented_w_iter <= iter else 0.0

@@ -83,21 +83,21 @@ class KBPNEngine:
             w_sr = g(sp + "kb.sr_reconst.layer.weight")                  # [3, (s+1)C, 3, 3]
             st["kb.sr_own"] = K.pack_conv(w_sr[:, s * C:(s + 1) * C].contiguous(), padding=1)
             kp = sp + "kb.kernel_predictor."
-            st["sr0"] = K.pack_conv(as1x1(g(kp + "fe_SR.0.layer.weight")), cout_pad=64)
+            st["sr0"] = K.pack_conv(as1x1(g(kp + "fe_SR.0.layer.weight")), cout_pad=64, cin_pad=32)   # K = 27 -> 32
             st["sr1"] = K.pack_conv(g(kp + "fe_SR.1.layer.weight"), cout_pad=64)
-            for i in (2, 3, 4):
-                st["sr%d" % i] = K.pack_conv(g(kp + "fe_SR.%d.layer.weight" % i), padding=1, cout_pad=64)
+            for i in (2, 3, 4):        # 32-channel layers: one 32-wide K chunk per tap (64B swizzle rows) halves the MMAs
+                st["sr%d" % i] = K.pack_conv(g(kp + "fe_SR.%d.layer.weight" % i), padding=1, cout_pad=64, cin_pad=32)
             st["fk0"] = K.pack_conv(g(kp + "fe_kernel.0.layer.weight"), padding=1, cout_pad=64, cin_pad=cond_pad)
             st["fk1"] = K.pack_conv(g(kp + "fe_kernel.1.layer.weight"), padding=1, cout_pad=64)
             wcat = g(kp + "fe_cat.0.layer.weight")                       # [32, 98, 1, 1]
             st["cat0_sr"] = K.pack_conv(wcat[:, :kc].contiguous(), cout_pad=64)
             st["cat0_k"] = K.pack_conv(wcat[:, kc:].contiguous(), cout_pad=64)
-            st["cat1"] = K.pack_conv(g(kp + "fe_cat.1.layer.weight"), padding=1, cout_pad=64)
-            st["cat2"] = K.pack_conv(g(kp + "fe_cat.2.layer.weight"), padding=1, cout_pad=64)
+            st["cat1"] = K.pack_conv(g(kp + "fe_cat.1.layer.weight"), padding=1, cout_pad=64, cin_pad=32)
+            st["cat2"] = K.pack_conv(g(kp + "fe_cat.2.layer.weight"), padding=1, cout_pad=64, cin_pad=32)
             # KBlock.up_conv1: ConvTranspose2d(3 -> C, 8, 4, 2) evaluated on the 3x3-patchified LR error:
             # per output phase a 1x1 conv over K = (a*3+b)*3+c with w[c, co, rho_h+6-4a, rho_w+6-4b]
             w = g(sp + "kb.up_conv1.layer.weight")                       # [3, C, 8, 8]
-            wp = torch.zeros((16, C, 64), dtype=torch.float32, device=dev)
+            wp = torch.zeros((16, C, 32), dtype=torch.float32, device=dev)              # K = 27 -> one 32-wide chunk
             for rh in range(4):
                 for rw in range(4):
                     for a in range(3):

@@ -166,12 +166,16 @@ def kbpn_forward(P, x_lr, num_stages=4, k_out=21, scale=4, prefix="sr_model."):
 
 # ---------------------------------------------------------------------------------------------- PSPNet (train mode)
 def _bn(P, p, x, training, momentum=0.1):
-    """BatchNorm2d on an NHWC tensor; train mode uses batch statistics and updates the running buffers in place."""
-    y = F.batch_norm(_nchw(x), P[p + ".running_mean"], P[p + ".running_var"], P[p + ".weight"], P[p + ".bias"],
+    """BatchNorm2d on an NHWC tensor; train mode uses batch statistics and updates the running buffers in place.
+    Tensors whose channel count was padded to 64 are normalised on their real channels and re-padded with zeros."""
+    c = P[p + ".weight"].numel()
+    xin = x if x.shape[3] == c else x[..., :c]
+    y = F.batch_norm(_nchw(xin), P[p + ".running_mean"], P[p + ".running_var"], P[p + ".weight"], P[p + ".bias"],
                      training=training, momentum=momentum, eps=1e-5)
     if training and (p + ".num_batches_tracked") in P:
         P[p + ".num_batches_tracked"] += 1
-    return _nhwc(y)
+    y = _nhwc(y)
+    return y if x.shape[3] == c else F.pad(y, (0, x.shape[3] - c))
 
 
 def _drop(x, p, on):
@@ -221,3 +225,99 @@ def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_
     a = torch.sigmoid(to_nchw(conv2d(a, P[p + "aux.4.weight"], P[p + "aux.4.bias"]), 1))
     aux = F.interpolate(a, size=(H, W), mode="bilinear", align_corners=True)
     return seg, aux
+
+
+# ---------------------------------------------------------------------------------------------- HRNet-W48 + OCR (train mode)
+def _cbr(P, pc, pb, x, training, stride=1, padding=0, relu=True):
+    y = _bn(P, pb, conv2d(x, P[pc + ".weight"], P.get(pc + ".bias"), stride=stride, padding=padding), training)
+    return F.relu(y) if relu else y
+
+
+def _resize_ac(x, size):
+    return _nhwc(F.interpolate(_nchw(x), size=size, mode="bilinear", align_corners=True))
+
+
+def hrnet_w48(P, p, x, training):
+    """HighResolutionNet.forward (hrnet_ocr/backbones/hrnet/hrnet_backbone.py:514-572) on NHWC tensors."""
+    from .params import HRNET48_STAGES
+    x = _cbr(P, p + "conv1", p + "bn1", x, training, stride=2, padding=1)
+    x = _cbr(P, p + "conv2", p + "bn2", x, training, stride=2, padding=1)
+    for i in range(4):
+        bp = p + "layer1.%d" % i
+        out = _cbr(P, bp + ".conv1", bp + ".bn1", x, training)
+        out = _cbr(P, bp + ".conv2", bp + ".bn2", out, training, padding=1)
+        out = _cbr(P, bp + ".conv3", bp + ".bn3", out, training, relu=False)
+        res = _cbr(P, bp + ".downsample.0", bp + ".downsample.1", x, training, relu=False) if i == 0 else x
+        x = F.relu(out + res)
+    ys, pre = [x], (256,)
+    for si, (modules, chans) in enumerate(HRNET48_STAGES, 2):
+        t = p + "transition%d" % (si - 1)
+        xs = []
+        for i, c in enumerate(chans):
+            if i < len(pre):
+                xs.append(_cbr(P, t + ".%d.0" % i, t + ".%d.1" % i, ys[i], training, padding=1) if c != pre[i] else ys[i])
+            else:
+                xs.append(_cbr(P, t + ".%d.0.0" % i, t + ".%d.0.1" % i, ys[-1], training, stride=2, padding=1))
+        for m in range(modules):
+            mp = p + "stage%d.%d" % (si, m)
+            for bi in range(len(chans)):
+                for k in range(4):
+                    bp = mp + ".branches.%d.%d" % (bi, k)
+                    out = _cbr(P, bp + ".conv1", bp + ".bn1", xs[bi], training, padding=1)
+                    out = _cbr(P, bp + ".conv2", bp + ".bn2", out, training, padding=1, relu=False)
+                    xs[bi] = F.relu(out + xs[bi])
+            fused = []
+            for i in range(len(chans)):
+                y = None
+                for j in range(len(chans)):
+                    fp = mp + ".fuse_layers.%d.%d" % (i, j)
+                    if j == i:
+                        term = xs[j]
+                    elif j > i:
+                        term = _resize_ac(_cbr(P, fp + ".0", fp + ".1", xs[j], training, relu=False), xs[i].shape[1:3])
+                    else:
+                        term = xs[j]
+                        for k in range(i - j):
+                            term = _cbr(P, fp + ".%d.0" % k, fp + ".%d.1" % k, term, training, stride=2, padding=1,
+                                        relu=(k != i - j - 1))
+                    y = term if y is None else y + term
+                fused.append(F.relu(y))
+            xs = fused
+        ys, pre = xs, chans
+    return ys, HRNET48_STAGES[-1][1]
+
+
+def hrnet_ocr_forward(P, img, prefix="segmentation_model.", bn_training=True, dropout=True):
+    """HRNet_W48_OCR.forward (hrnet_ocr/nets/hrnet.py:137-158) in train mode; SpatialGather_Module / _ObjectAttentionBlock /
+    SpatialOCR_Module (modules/spatial_ocr_block.py:49-66, 172-214, 281-303).  img fp32 [B,3,H,W] -> (seg, aux) fp32."""
+    p = prefix
+    tr = bn_training
+    H, W = img.shape[2:]
+    ys, chans = hrnet_w48(P, p + "backbone.", to_nhwc(img), tr)
+    h, w = ys[0].shape[1:3]
+    feats = _cat([ys[0]] + [_resize_ac(y, (h, w)) for y in ys[1:]], real=chans)                 # 720 -> 768
+    a = F.relu(_bn(P, p + "aux_head.1.0", conv2d(feats, P[p + "aux_head.0.weight"], P[p + "aux_head.0.bias"], padding=1), tr))
+    out_aux = to_nchw(conv2d(a, P[p + "aux_head.2.weight"], P[p + "aux_head.2.bias"]), 1)      # [B,1,h,w] fp32
+    f = F.relu(_bn(P, p + "conv3x3.1.0", conv2d(feats, P[p + "conv3x3.0.weight"], P[p + "conv3x3.0.bias"], padding=1), tr))
+    B, C = f.shape[0], f.shape[3]
+    probs = F.softmax(out_aux.view(B, 1, -1), dim=2)                                            # (B, K=1, HW)
+    ctx = torch.matmul(probs, f.view(B, h * w, C).float())                                      # (B, 1, C)
+    ctx = ctx.to(torch.bfloat16).view(B, 1, 1, C)                                               # object region feature
+    o = p + "ocr_distri_head.object_context_block."
+
+    def seq2(name, t):
+        t = F.relu(_bn(P, o + name + ".1.0", conv2d(t, P[o + name + ".0.weight"], P.get(o + name + ".0.bias")), tr))
+        return F.relu(_bn(P, o + name + ".3.0", conv2d(t, P[o + name + ".2.weight"], P.get(o + name + ".2.bias")), tr))
+
+    query = seq2("f_pixel", f).view(B, h * w, 256).float()
+    key = seq2("f_object", ctx).view(B, 1, 256).float().permute(0, 2, 1)
+    value = F.relu(_bn(P, o + "f_down.1.0", conv2d(ctx, P[o + "f_down.0.weight"], P.get(o + "f_down.0.bias")), tr))
+    sim = F.softmax((256 ** -0.5) * torch.matmul(query, key), dim=-1)                           # (B, HW, K=1) == 1
+    context = torch.matmul(sim, value.view(B, 1, 256).float()).to(torch.bfloat16).view(B, h, w, 256)
+    context = F.relu(_bn(P, o + "f_up.1.0", conv2d(context, P[o + "f_up.0.weight"], P.get(o + "f_up.0.bias")), tr))
+    q = p + "ocr_distri_head.conv_bn_dropout."
+    f2 = F.relu(_bn(P, q + "1.0", conv2d(torch.cat((context, f), dim=3), P[q + "0.weight"], P.get(q + "0.bias")), tr))
+    f2 = _drop(f2, 0.05, dropout)
+    out = to_nchw(conv2d(f2, P[p + "cls_head.weight"], P[p + "cls_head.bias"]), 1)
+    up = lambda t: F.interpolate(t, size=(H, W), mode="bilinear", align_corners=True)
+    return torch.sigmoid(up(out)), torch.sigmoid(up(out_aux))

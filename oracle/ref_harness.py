@@ -70,13 +70,11 @@ def make_cfg(detector="PSPNet", wf_amp=0.0):
     return cfg
 
 
-def joint_model(cfg):
+def patch_hrnet_configer():
+    """H_48_D_4_composite.json names an ImageNet checkpoint that is not here: null network.pretrained."""
     setup()
-    import contextlib
-    import io
     import model.modeling.build_model as bm
-    from model.modeling.build_model import JointModel
-    if not _state.get("configer_patched"):        # H_48_D_4_composite.json names an ImageNet checkpoint that is not here
+    if not _state.get("configer_patched"):
         _orig = bm.set_configer
 
         def _no_pretrained(path):
@@ -85,6 +83,14 @@ def joint_model(cfg):
             return c
         bm.set_configer = _no_pretrained
         _state["configer_patched"] = True
+
+
+def joint_model(cfg):
+    setup()
+    import contextlib
+    import io
+    from model.modeling.build_model import JointModel
+    patch_hrnet_configer()
     with contextlib.redirect_stdout(io.StringIO()):
         m = JointModel(cfg)
     return m.eval()

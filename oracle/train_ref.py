@@ -14,12 +14,12 @@ from . import loss_ref as L
 from . import torch_ref as T
 
 
-def train_forward(sd, lr, hr, mask, kgt, alpha, beta=0.3, wf_amp=1.0, bn_train=True):
+def train_forward(sd, lr, hr, mask, kgt, alpha, beta=0.3, wf_amp=1.0, bn_train=True, hrnet=False):
     """-> (loss, seg_loss, sr_loss, sr, seg, aux).  `sd` tensors that require grad receive gradients."""
     T.BN_TRAIN = bn_train
     try:
         sr, kvec = T.kbpn_forward(sd, lr)
-        seg, aux = T.pspnet_forward(sd, F.instance_norm(sr, eps=1e-5))
+        seg, aux = (T.hrnet_ocr_forward if hrnet else T.pspnet_forward)(sd, F.instance_norm(sr, eps=1e-5))
     finally:
         T.BN_TRAIN = False
     kmap = kvec.expand(-1, -1, lr.shape[2], lr.shape[3])

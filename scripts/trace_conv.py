@@ -11,6 +11,12 @@ if which == "hr1":
 elif which == "ikc3":
     x = K.Fmap.empty(B, 448, 448, 64); x.t.normal_()
     pc = K.pack_conv(torch.randn(64, 64, 3, 3, device="cuda") * 0.05, padding=1); y = K.Fmap.empty(B, 448, 448, 64); kw = dict(act=K.ACT_LEAKY, slope=0.01)
+elif which == "ikc32":
+    x = K.Fmap.empty(B, 448, 448, 64); x.t.normal_()
+    pc = K.pack_conv(torch.randn(32, 32, 3, 3, device="cuda") * 0.05, padding=1, cout_pad=64, cin_pad=32); y = K.Fmap.empty(B, 448, 448, 64); kw = dict(act=K.ACT_LEAKY, slope=0.01)
+elif which == "n16":
+    x = K.Fmap.empty(B, 448, 448, 128); x.t.normal_()
+    pc = K.pack_conv(torch.randn(12, 128, 3, 3, device="cuda") * 0.05, padding=1); y = torch.zeros(B, 12, 448, 448, device="cuda"); kw = dict()
 else:
     x = K.Fmap.empty(B, 112, 112, 128); x.t.normal_()
     pc = K.pack_deconv8s4(torch.randn(128, 128, 8, 8, device="cuda") * 0.02); y = K.Fmap.empty(B, 448, 448, 128)

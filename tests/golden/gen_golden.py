@@ -195,7 +195,7 @@ if __name__ == "__main__":
         gen_joint(hrnet=True)
 
 
-def gen_train(bn_eval=False):
+def gen_train(bn_eval=False, hrnet=False):
     """One JointModelWithLoss forward + backward of the UNMODIFIED reference at iteration 40000 (all phases active,
     w^F on, m^F = 1), Dropout2d disabled (p = 0) so the step is deterministic: losses and a sample of gradients.
     bn_eval=True additionally puts the BatchNorm layers in eval mode (running statistics): with random weights and a
@@ -207,18 +207,21 @@ def gen_train(bn_eval=False):
     from model.modeling.build_model import JointModelWithLoss
     from model.data.transforms.transforms import FactorResize
     from model.engine.trainer import calc_loss
-    cfg = rh.make_cfg(wf_amp=1.0)
+    cfg = rh.make_cfg(wf_amp=1.0, detector="HRNet_OCR" if hrnet else "PSPNet")
+    if hrnet:
+        cfg.SOLVER.TASK_LOSS_WEIGHT = 0.9                       # config #4 (beta = 0.9)
+        rh.patch_hrnet_configer()
     with contextlib.redirect_stdout(io.StringIO()):
         m = JointModelWithLoss(cfg, num_train_ds=100, resume_iter=40000, sr_transforms=FactorResize(4, "bicubic"))
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-    sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+    sd.update(P.synth_state_dict(P.hrnet_ocr_param_shapes() if hrnet else P.pspnet_param_shapes(), prefix="segmentation_model."))
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected and all(k.startswith("sr_loss_fn") or "vgg" in k.lower() for k in missing), (missing, unexpected)
     m.train()
     for mod in m.modules():
         if isinstance(mod, torch.nn.Dropout2d):
             mod.p = 0.0
-        if bn_eval and isinstance(mod, torch.nn.BatchNorm2d):
+        if bn_eval and isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
             mod.eval()
     alpha = 0.63
     m.ss_loss_fn.alpha = alpha
@@ -252,6 +255,15 @@ def gen_train(bn_eval=False):
              "segmentation_model.feats.conv1.weight", "segmentation_model.feats.layer3.2.conv1.weight",
              "segmentation_model.feats.layer4.2.bn2.weight", "segmentation_model.psp.bottleneck.weight",
              "segmentation_model.up_2.conv.0.weight", "segmentation_model.final.0.weight", "segmentation_model.aux.4.bias"]
+    if hrnet:
+        names = [n for n in names if n.startswith("sr_model.")] + [
+            "segmentation_model.backbone.conv1.weight", "segmentation_model.backbone.layer1.2.conv2.weight",
+            "segmentation_model.backbone.stage3.1.branches.2.1.conv1.weight",
+            "segmentation_model.backbone.stage4.2.fuse_layers.0.3.0.weight",
+            "segmentation_model.backbone.stage4.0.fuse_layers.3.0.1.0.weight",
+            "segmentation_model.conv3x3.0.weight", "segmentation_model.aux_head.2.weight",
+            "segmentation_model.ocr_distri_head.object_context_block.f_down.0.weight",
+            "segmentation_model.ocr_distri_head.conv_bn_dropout.0.weight", "segmentation_model.cls_head.weight"]
     params = dict(m.named_parameters())
     norms = {}
     for k, p_ in params.items():
@@ -264,10 +276,13 @@ def gen_train(bn_eval=False):
         stride = max(1, gflat.size // 20000)
         out["grad:" + k] = gflat[::stride].astype(np.float16 if False else np.float32)
         out["stride:" + k] = np.int64(stride)
-    np.savez_compressed(os.path.join(HERE, "train_step_bneval.npz" if bn_eval else "train_step.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "train_step_hrnet.npz" if hrnet else "train_step_bneval.npz" if bn_eval else "train_step.npz"), **out)
     print("train_step.npz loss", loss.item(), "seg", seg_loss.mean().item(), "sr", sr_loss.detach().numpy(), "grads", len(norms))
 
 
 if __name__ == "__main__" and "train" in sys.argv[1:]:
-    gen_train()
-    gen_train(bn_eval=True)
+    if "hrnet" in sys.argv[1:]:
+        gen_train(bn_eval=True, hrnet=True)
+    else:
+        gen_train()
+        gen_train(bn_eval=True)

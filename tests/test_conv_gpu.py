@@ -44,6 +44,30 @@ def test_conv_matches_torch(n, cin, cout, h, w, k, stride, pad, dil):
     _check(y.to_nchw_f32(cout), ref)
 
 
+@pytest.mark.parametrize("n,cin,cout,h,w,k,pad,kpad,pitch", [
+    (2, 32, 32, 24, 40, 3, 1, 32, 64),      # 64-byte swizzle rows, input stored with a 64-channel pitch
+    (1, 32, 49, 56, 56, 3, 1, 32, 32),
+    (2, 27, 49, 16, 24, 1, 0, 32, 64),
+    (2, 3, 64, 20, 20, 3, 1, 16, 16),       # 32-byte swizzle rows
+    (1, 16, 128, 9, 33, 3, 1, 16, 64),
+])
+def test_conv_narrow_k_chunks(n, cin, cout, h, w, k, pad, kpad, pitch):
+    """K chunks of 32 / 16 channels (64B / 32B swizzle) for the layers whose cin is 32 or less."""
+    from csbsr_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = _bf(torch.randn(n, cin, h, w, device="cuda", generator=g))
+    wt = _bf(torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5)
+    ref = F.conv2d(x, wt, None, padding=pad)
+    pc = K.pack_conv(wt, None, padding=pad, cin_pad=kpad)
+    assert pc.cin_pad == kpad
+    xf = K.Fmap.from_nchw(x, cpad=pitch)
+    xf.t[..., cin:] = 7.0                     # channels past cin_pad must never be read; inside it they meet zero weights
+    y = K.Fmap.empty(n, h, w, K.round_up(cout, 16))
+    K.conv(xf.window(0, kpad), pc, y)
+    torch.cuda.synchronize()
+    _check(y.to_nchw_f32(cout), ref)
+
+
 def test_deconv8s4_matches_torch():
     from csbsr_b200 import kernels as K
     g = torch.Generator(device="cuda").manual_seed(2)

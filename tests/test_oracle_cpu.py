@@ -226,19 +226,22 @@ def test_deconv_phase_decomposition_matches_conv_transpose():
     assert (out - ref).abs().max().item() < 0.05 * ref.abs().max().item()        # bf16-rounded weights
 
 
-@pytest.mark.parametrize("bn_eval", [False, True])
-def test_train_oracle_matches_reference_golden(bn_eval):
+@pytest.mark.parametrize("variant", ["pspnet", "pspnet_bneval", "hrnet_bneval"])
+def test_train_oracle_matches_reference_golden(variant):
     """oracle/train_ref.py (fp32 autograd) against the unmodified JointModelWithLoss forward + backward."""
     from csbsr_b200.modeling import params as P
     from oracle import train_ref as TR
-    g = np.load(os.path.join(GOLD, "train_step_bneval.npz" if bn_eval else "train_step.npz"))
+    bn_eval, hrnet = variant.endswith("bneval"), variant.startswith("hrnet")
+    g = np.load(os.path.join(GOLD, {"pspnet": "train_step.npz", "pspnet_bneval": "train_step_bneval.npz",
+                                    "hrnet_bneval": "train_step_hrnet.npz"}[variant]))
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-    sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+    sd.update(P.synth_state_dict(P.hrnet_ocr_param_shapes() if hrnet else P.pspnet_param_shapes(), prefix="segmentation_model."))
     names = [k[5:] for k in g.files if k.startswith("grad:")]
     for k in names:
         sd[k] = sd[k].clone().requires_grad_(True)
     loss, seg_loss, sr_loss, sr, seg, _ = TR.train_forward(sd, *(torch.from_numpy(g[k]) for k in ("lr", "hr", "mask", "kgt")),
-                                                           alpha=float(g["alpha"]), beta=0.3, wf_amp=1.0, bn_train=not bn_eval)
+                                                           alpha=float(g["alpha"]), beta=0.9 if hrnet else 0.3, wf_amp=1.0, bn_train=not bn_eval,
+                                                           hrnet=hrnet)
     loss.backward()
     assert tuple(seg_loss.shape) == tuple(g["seg_loss_shape"])
     assert abs(loss.item() - float(g["loss"])) <= 1e-5
@@ -251,5 +254,5 @@ def test_train_oracle_matches_reference_golden(bn_eval):
         # differences (mkldnn vs native conv paths), visible as a few outlier entries: cosine stays > 0.9999
         cos = float((got.astype(np.float64) * ref).sum() / np.sqrt((got.astype(np.float64) ** 2).sum() * (ref.astype(np.float64) ** 2).sum()))
         assert cos >= 0.9995 and np.abs(got - ref).max() <= 0.1 * np.abs(ref).max(), (k, cos)
-        if k in ("segmentation_model.final.0.weight", "segmentation_model.aux.4.bias"):
+        if k in ("segmentation_model.final.0.weight", "segmentation_model.aux.4.bias", "segmentation_model.cls_head.weight"):
             assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-7, k

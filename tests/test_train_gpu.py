@@ -131,22 +131,25 @@ def test_deconv8s4_autograd_fn():
         assert _rel(x.grad, x_ref.grad) <= 1e-2 and _rel(w_.grad, w_ref.grad) <= 1e-2
 
 
-def _train_model():
+def _train_model(hrnet=False):
     from csbsr_b200.config import cfg
     from csbsr_b200.modeling.build_model import JointModelWithLoss
     from csbsr_b200.modeling import params as P
     c = cfg.clone()
     c.merge_from_file("config/config_csbsr_pspnet.yaml")
     c.SOLVER.SEG_FAIL_ORIENTED_WEIGHT4SS_AMP = 1.0
+    if hrnet:
+        c.MODEL.DETECTOR_TYPE = "HRNet_OCR"
+        c.SOLVER.TASK_LOSS_WEIGHT = 0.9
     m = JointModelWithLoss(c, num_train_ds=100, resume_iter=40000)
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-    sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+    sd.update(P.synth_state_dict(P.hrnet_ocr_param_shapes() if hrnet else P.pspnet_param_shapes(), prefix="segmentation_model."))
     m.load_state_dict(sd, strict=True)
     return m.cuda(), sd, c
 
 
-@pytest.mark.parametrize("bn_eval", [True, False])
-def test_train_step_vs_reference_golden(bn_eval):
+@pytest.mark.parametrize("variant", ["pspnet_bneval", "pspnet", "hrnet_bneval"])
+def test_train_step_vs_reference_golden(variant):
     """One joint training step (iteration 40000, w^F on, Dropout2d off) of the tcgen05 training graph against the
     unmodified reference's losses and gradients (tests/golden/train_step*.npz; the fp32 oracle is pinned to the same
     fixtures on CPU).
@@ -159,9 +162,11 @@ def test_train_step_vs_reference_golden(bn_eval):
     import os
     import numpy as np
     from csbsr_b200.engine.losses import calc_loss
+    bn_eval, hrnet = variant.endswith("bneval"), variant.startswith("hrnet")     # hrnet: config #4 (HRNet-W48 + OCR, beta 0.9)
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
-                             "train_step_bneval.npz" if bn_eval else "train_step.npz"))
-    m, sd, c = _train_model()
+                             {"pspnet": "train_step.npz", "pspnet_bneval": "train_step_bneval.npz",
+                              "hrnet_bneval": "train_step_hrnet.npz"}[variant]))
+    m, sd, c = _train_model(hrnet)
     m.train()
     m.dropout = False
     m.freeze_bn = bn_eval
@@ -206,6 +211,9 @@ def test_train_step_vs_reference_golden(bn_eval):
                 # relative (the fp32 oracle with bf16-rounded conv operands shows the same outliers): absolute bound
                 if abs(p_.grad.double().norm().item() - ref_n) > max(0.5 * ref_n, 2e-3):
                     bad.append((k, p_.grad.item(), ref_n))
+                continue
+            if ref_n == 0:                      # OCR f_pixel / f_object: softmax over K = 1 object region -> exactly zero
+                assert p_.grad.abs().max().item() == 0, k
                 continue
             r = p_.grad.double().norm().item() / (ref_n + 1e-30)
             if abs(r - 1) > (0.15 if bn_eval else 0.5):

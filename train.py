@@ -63,7 +63,8 @@ def main():
         print("Resume from {}".format(ckpt))
     else:
         sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-        sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+        seg_shapes = P.hrnet_ocr_param_shapes() if cfg.MODEL.DETECTOR_TYPE == "HRNet_OCR" else P.pspnet_param_shapes()
+        sd.update(P.synth_state_dict(seg_shapes, prefix="segmentation_model."))
         model.load_state_dict(sd, strict=True)
     model.cuda()
     sched = UpDownScheduler(cfg.SOLVER.SR_PRETRAIN_ITER[1], args.resume_iter, cfg.SOLVER.SCHEDULER)
