@@ -72,6 +72,8 @@ _SIGNATURES = {
     "csbsr_device_ok": (C.c_int, []),
     "csbsr_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "csbsr_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    "csbsr_tap_gather3x3": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "csbsr_prelu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "csbsr_prelu_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
     "csbsr_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong] + [C.c_float] * 4 + [C.c_int, C.c_float, C.c_int,

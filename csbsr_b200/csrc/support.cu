@@ -697,3 +697,59 @@ extern "C" int csbsr_softmax_gather(const float* logits, const void* feats, floa
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 conv with very few output channels (sr_reconst / output_conv, 128 -> 3: kbpn.py:361, :68) as "tap expansion":
+// a 1x1 GEMM z[q][t*co + c] = sum_ci x[q][ci] * w[c][ci][t] on the tensor cores (N = 9*co instead of nine N = co GEMMs
+// that each pay the full 128-row A-operand read), then this gather: out[p][c] = sum_t z[p + d_t][t*co + c] (zero outside
+// the image = the conv zero padding), accumulated into fp32 planar windows.
+namespace csbsr {
+template <int CO>
+__global__ void tap_gather_kernel(const __nv_bfloat16* __restrict__ z, int z_pitch, float* out, int out_pitch,
+                                  int out_coff, const float* r32, int r_pitch, int r_coff, int n, int h, int w) {
+    const size_t total = static_cast<size_t>(n) * h * w;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(i % w);
+        const int y = static_cast<int>((i / w) % h);
+        const int img = static_cast<int>(i / (static_cast<size_t>(w) * h));
+        float acc[CO];
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+            if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+            const __nv_bfloat16* zp = z + ((static_cast<size_t>(img) * h + yy) * w + xx) * z_pitch + t * CO;
+#pragma unroll
+            for (int c = 0; c < CO; ++c) acc[c] += __bfloat162float(zp[c]);
+        }
+        const size_t plane = static_cast<size_t>(h) * w, pix = static_cast<size_t>(y) * w + x;
+        float rv[CO];
+#pragma unroll
+        for (int c = 0; c < CO; ++c)
+            rv[c] = r32 ? __ldg(r32 + (static_cast<size_t>(img) * r_pitch + r_coff + c) * plane + pix) : 0.f;
+#pragma unroll
+        for (int c = 0; c < CO; ++c) out[(static_cast<size_t>(img) * out_pitch + out_coff + c) * plane + pix] = acc[c] + rv[c];
+    }
+}
+}  // namespace csbsr
+
+extern "C" int csbsr_tap_gather3x3(const void* z, int z_pitch, int z_coff, float* out, int out_pitch, int out_coff,
+                                   const float* r32, int r_pitch, int r_coff, int n, int h, int w, int co, void* stream) {
+    CSBSR_REQUIRE(z && out && n > 0 && h > 0 && w > 0, "tap_gather3x3: bad arguments");
+    CSBSR_REQUIRE(co == 3 || co == 6 || co == 9 || co == 12, "tap_gather3x3: co=%d must be 3, 6, 9 or 12", co);
+    const __nv_bfloat16* zp = reinterpret_cast<const __nv_bfloat16*>(z) + z_coff;
+    const size_t total = static_cast<size_t>(n) * h * w;
+    const int grid = grid_for(total, 256);
+#define CSBSR_TG(CO)                                                                                              \
+    tap_gather_kernel<CO><<<grid, 256, 0, STREAM(stream)>>>(zp, z_pitch, out, out_pitch, out_coff, r32, r_pitch, \
+                                                             r_coff, n, h, w)
+    if (co == 3) CSBSR_TG(3);
+    else if (co == 6) CSBSR_TG(6);
+    else if (co == 9) CSBSR_TG(9);
+    else CSBSR_TG(12);
+#undef CSBSR_TG
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

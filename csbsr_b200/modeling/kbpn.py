@@ -81,7 +81,7 @@ class KBPNEngine:
             # sr_reconst of stage s reads concat_h[0:(s+1)C]; by linearity its response is a sum over the C-channel
             # slices, so slice j is read ONCE more after its KBlock update for all later consumers (see forward)
             w_sr = g(sp + "kb.sr_reconst.layer.weight")                  # [3, (s+1)C, 3, 3]
-            st["kb.sr_own"] = K.pack_conv(w_sr[:, s * C:(s + 1) * C].contiguous(), padding=1)
+            st["kb.sr_own"] = K.pack_tapexp3x3(w_sr[:, s * C:(s + 1) * C].contiguous())
             kp = sp + "kb.kernel_predictor."
             st["sr0"] = K.pack_conv(as1x1(g(kp + "fe_SR.0.layer.weight")), cout_pad=64, cin_pad=32)   # K = 27 -> 32
             st["sr1"] = K.pack_conv(g(kp + "fe_SR.1.layer.weight"), cout_pad=64)
@@ -131,7 +131,7 @@ class KBPNEngine:
             # consumers of the final slice j: sr_reconst of stages j+1..S-1 (3 channels each), then output_conv
             ws = [g("back_projection_stages.%d.kb.sr_reconst.layer.weight" % c)[:, j * C:(j + 1) * C] for c in range(j + 1, self.S)]
             ws.append(w_out[:, j * C:(j + 1) * C])
-            P[j]["kb.sr_later"] = K.pack_conv(torch.cat(ws, 0).contiguous(), padding=1)
+            P[j]["kb.sr_later"] = K.pack_tapexp3x3(torch.cat(ws, 0).contiguous())
         self.p = P
         return self
 
@@ -186,8 +186,8 @@ class KBPNEngine:
             # ---- KBlock (kbpn.py:382-412)
             pre = concat_h.window(0, (s + 1) * C)
             # sr_t = sr_reconst(cat(slices)) = own-slice conv + contributions of the earlier (final) slices in sr_acc
-            sr_t = K.conv(hs, st["kb.sr_own"], ws.f32("sr_t", B, 3, H, W),
-                          r32=K.PlanarWin(sr_acc, 3 * (s - 1), 3) if s > 0 else None)
+            sr_t = self._conv3x3_few(hs, st["kb.sr_own"], ws.f32("sr_t", B, 3, H, W),
+                                     K.PlanarWin(sr_acc, 3 * (s - 1), 3) if s > 0 else None)
             kvec = self._kernel_predictor(st, sr_t, kvec, B, H, W, s)
             if self.debug is not None:
                 self.debug["sr_t%d" % s] = sr_t.clone()
@@ -199,9 +199,9 @@ class KBPNEngine:
             # sr_reconst of stages s+1.., then output_conv), reading the 448^2 x C slice only once
             later = K.PlanarWin(sr_acc, 3 * s, 3 * (self.S - s))
             if s == self.S - 1:
-                K.conv(hs, st["kb.sr_later"], sr, r32=later)                # output_conv + bicubic residual -> sr
+                self._conv3x3_few(hs, st["kb.sr_later"], sr, later)        # output_conv + bicubic residual -> sr
                 break
-            K.conv(hs, st["kb.sr_later"], later, r32=later if s > 0 else up_tail)
+            self._conv3x3_few(hs, st["kb.sr_later"], later, later if s > 0 else up_tail)
             # ---- DownBlock (kbpn.py:484-489) on concat_h[0:(s+1)C], result into its concat_l slice
             xh = K.conv(pre, st["dn.conv"][0], t0, act=ACT_LEAKY, slope=st["dn.conv"][1])
             l0 = K.conv(xh, st["dn.c1"][0], ws.fmap("lr_x", B, h, w, C), act=ACT_LEAKY, slope=st["dn.c1"][1])
@@ -210,6 +210,11 @@ class KBPNEngine:
             # ---- SFT layer (kbpn.py:511-518)
             low = self._sft(st, concat_l.window(0, (s + 1) * C), kvec, B, h, w, s)
         return sr, kvec.clone()
+
+    def _conv3x3_few(self, x, pc, out, r32):
+        """3x3 conv to <= 12 channels as tap expansion: one 1x1 GEMM with N = 9*co, then the shifted gather (fp32 planes)."""
+        z = K.conv(x, pc, self.ws.fmap("hr_z%d" % pc.cout_pad, x.n, x.h, x.w, pc.cout_pad))
+        return K.tap_gather3x3(z, pc.tap_co, out, r32)
 
     def _kernel_predictor(self, st, sr_t, kvec, B, H, W, s):
         """KernelPredictorLikeIKC.forward + KBlock renormalisation (kbpn.py:562-578, :391-392)."""

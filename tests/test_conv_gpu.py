@@ -141,3 +141,22 @@ def test_f32_planar_output_and_class_bias():
     idx = ci[:, None] * 5 + cj[None, :]
     ref2 = F.conv2d(x, wt2) + cb[:, idx].permute(0, 3, 1, 2)
     _check(y2.to_nchw_f32(cout), ref2)
+
+
+@pytest.mark.parametrize("co", [3, 6, 12])
+def test_tap_expansion_3x3_few_channels(co):
+    """128 -> co 3x3 conv as a 1x1 GEMM with N = 9*co plus the shifted gather, accumulated into fp32 planes."""
+    from csbsr_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n, ci, h, w = 2, 128, 24, 40
+    x = _bf(torch.randn(n, ci, h, w, device="cuda", generator=g))
+    wt = _bf(torch.randn(co, ci, 3, 3, device="cuda", generator=g) / (ci * 9) ** 0.5)
+    acc = torch.randn(n, co + 2, h, w, device="cuda", generator=g)
+    ref = F.conv2d(x, wt, None, padding=1) + acc[:, 1:1 + co]
+    pc = K.pack_tapexp3x3(wt)
+    z = K.conv(K.Fmap.from_nchw(x), pc, K.Fmap.empty(n, h, w, pc.cout_pad))
+    out = torch.zeros(n, co + 2, h, w, device="cuda")
+    K.tap_gather3x3(z, co, K.PlanarWin(out, 1, co), K.PlanarWin(acc, 1, co))
+    torch.cuda.synchronize()
+    assert (out[:, 0] == 0).all() and (out[:, co + 1] == 0).all()
+    _check(out[:, 1:1 + co], ref)
