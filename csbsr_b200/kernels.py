@@ -12,7 +12,8 @@ from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, OUT_BF16_NHWC, OU
                    ConvDesc)
 
 
-PROFILE = None        # set to a list to collect (label, flops, start_event, end_event) per conv launch
+PROFILE = None
+PROFILE_WG = None          # list of (label, flops, start event, end event) per csbsr_conv_wgrad call when set        # set to a list to collect (label, flops, start_event, end_event) per conv launch
 
 
 def round_up(v, m):
@@ -293,9 +294,16 @@ def wgrad(g, s, taps, stride=1):
         d.dh[i], d.dw[i] = dh, dw
     out = torch.empty((round_up(g.c, 128), len(taps), s.c), dtype=torch.float32, device=g.t.device)
     d.wg = out.data_ptr()
+    if PROFILE_WG is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = _lib.lib().csbsr_conv_wgrad(C.byref(d), _lib.stream_ptr())
     _lib.check(rc, "csbsr_conv_wgrad")
     _lib.count_launch("csbsr_conv_wgrad")
+    if PROFILE_WG is not None:
+        e1.record()
+        PROFILE_WG.append(("wgrad n%d %dx%d cg%d cs%d taps%d s%d" % (g.n, g.h, g.w, g.c, s.c, len(taps), stride),
+                           2.0 * g.n * g.h * g.w * g.c * s.c * len(taps), e0, e1))
     return out
 
 

@@ -1,6 +1,8 @@
-"""Turns the raw ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/.
+"""Turns the raw ncu outputs brought back in gpurun_out/ (scripts/gpu_profile_round.sh) into the tracked summaries
+under profiles/.
 
-  python scripts/summarize_profiles.py gpurun_out/launches_r01.csv gpurun_out/prof_conv_r01.ncu-rep r01 <images in the run>
+  python scripts/summarize_profiles.py gpurun_out/launches_r01.csv gpurun_out/prof_conv_r01b.ncu-rep r01 <images in the run> \
+         [gpurun_out/prof_wgrad_r01.ncu-rep]
 """
 import collections
 import csv
@@ -35,9 +37,13 @@ def launch_summary(path, tag, n_img):
             wr[name] += to_bytes(v, r[ui])
     tot = sum(t.values())
     lines = ["# ncu launch list summary (%s)" % tag, "",
-             "Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-             "python bench.py --steps 1 --warmup 1 --batch 16 --no-cpu-baseline` (cold-cache, serialised launches: compare SHARES).",
-             "The run executes %d images through the hot path (3 warm-up + 1 timed + 2 e2e + 1 roofline step of 16)." % n_img, "",
+             "Command: `ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 1 --batch 16 "
+             "--no-cpu-baseline --train-steps 1` (cold-cache, serialised launches: compare SHARES, not absolute times).",
+             "The run executes %d images through the eval hot path (3 warm-up + 1 timed + 2 e2e + 1 roofline step of 16) and then "
+             "4 joint training steps (3 warm-up + 1 timed; batch 8, 224^2 crops): `conv_wgrad_kernel`, `adam_kernel`, `prelu_*` and "
+             "the `at::native` glue kernels belong to the training leg; `us / image` divides by the eval images only. DRAM columns "
+             "are zero in this time-only pass (the per-kernel DRAM bytes of the conv kernel are in `%s_conv_traffic.json`, "
+             "captured earlier in the round with the dram metrics enabled)." % (n_img, tag), "",
              "| kernel | launches | total ms | us / image | share | DRAM read MB / image | DRAM write MB / image |", "|---|---|---|---|---|---|---|"]
     for k, v in sorted(t.items(), key=lambda kv: -kv[1]):
         if v / tot < 0.001:
@@ -47,16 +53,17 @@ def launch_summary(path, tag, n_img):
     lines.append("")
     lines.append("Total kernel time: %.2f ms (%.3f ms / image)." % (tot / 1e6, tot / 1e6 / n_img))
     conv = "csbsr::conv_igemm_kernel"
-    out = {"kernel": conv, "share_of_gpu_time": t[conv] / tot, "launches_per_image": n[conv] / n_img,
-           "dram_bytes_per_image": (rd[conv] + wr[conv]) / n_img, "us_per_image": t[conv] / 1e3 / n_img}
-    with open(os.path.join(ROOT, "profiles", "%s_conv_traffic.json" % tag), "w") as f:
-        json.dump(out, f, indent=1)
+    if rd[conv] > 0:
+        out = {"kernel": conv, "share_of_gpu_time": t[conv] / tot, "launches_per_image": n[conv] / n_img,
+               "dram_bytes_per_image": (rd[conv] + wr[conv]) / n_img, "us_per_image": t[conv] / 1e3 / n_img}
+        with open(os.path.join(ROOT, "profiles", "%s_conv_traffic.json" % tag), "w") as f:
+            json.dump(out, f, indent=1)
     with open(os.path.join(ROOT, "profiles", "%s_launches.md" % tag), "w") as f:
         f.write("\n".join(lines) + "\n")
     print("\n".join(lines[:14]))
 
 
-def full_summary(rep, tag):
+def full_summary(rep, tag, kernel="conv_igemm", cmd=None):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -66,15 +73,15 @@ def full_summary(rep, tag):
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
             "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active"]
     idx = [(w, hdr.index(w)) for w in want if w in hdr]
-    lines = ["# ncu --set full capture of `csbsr::conv_igemm_kernel` (%s)" % tag, "",
-             "Command: `ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 700 -c 12 python bench.py "
-             "--steps 1 --warmup 1 --batch 8 --no-cpu-baseline` (12 consecutive conv launches of one KBPN stage).", "",
+    lines = ["# ncu --set full capture of `csbsr::%s_kernel` (%s)" % (kernel, tag), "",
+             cmd or ("Command: `ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 700 -c 8 python bench.py "
+                     "--steps 1 --warmup 1 --batch 8 --no-cpu-baseline --no-train` (8 consecutive conv launches of one KBPN stage)."), "",
              "| " + " | ".join("%s [%s]" % (w.replace("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active %")
                                               .replace(".avg.pct_of_peak_sustained_elapsed", " %").replace("launch__", ""), units[i]) for w, i in idx) + " |",
              "|" + "---|" * len(idx)]
     for r in data:
         lines.append("| " + " | ".join(r[i] for _, i in idx) + " |")
-    with open(os.path.join(ROOT, "profiles", "%s_conv_igemm_ncu_full.md" % tag), "w") as f:
+    with open(os.path.join(ROOT, "profiles", "%s_%s_ncu_full.md" % (tag, kernel)), "w") as f:
         f.write("\n".join(lines) + "\n")
     print("\n".join(lines[4:10]))
 
@@ -85,3 +92,8 @@ if __name__ == "__main__":
     launch_summary(launches, tag, n_img)
     if os.path.exists(rep):
         full_summary(rep, tag)
+    if len(sys.argv) > 5 and os.path.exists(sys.argv[5]):
+        full_summary(sys.argv[5], tag, "conv_wgrad",
+                     "Command: `ncu --set full --clock-control none --import-source on -k regex:conv_wgrad -s 40 -c 4 python "
+                     "scripts/time_train.py --steps 1 --warmup 1` (4 consecutive weight-gradient launches of the backward pass, "
+                     "batch 8, 224^2 crops).")

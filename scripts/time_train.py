@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--layers", action="store_true")
     a = ap.parse_args()
     from csbsr_b200 import _lib
     from csbsr_b200.config import cfg
@@ -57,6 +58,22 @@ def main():
             step(40010)
             torch.cuda.synchronize()
         print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+    if a.layers:
+        import collections
+        from csbsr_b200 import kernels as K
+        K.PROFILE, K.PROFILE_WG = [], []
+        step(40015)
+        torch.cuda.synchronize()
+        for name, rec in (("conv fwd+dgrad", K.PROFILE), ("wgrad", K.PROFILE_WG)):
+            agg = collections.OrderedDict()
+            for r in rec:
+                a_ = agg.setdefault(r[0], [0, 0.0, 0.0])
+                a_[0] += 1; a_[1] += r[2].elapsed_time(r[3]); a_[2] += r[1]
+            tot = sum(v[1] for v in agg.values())
+            print("== %s: %.2f ms, %.0f TFLOP/s (padded)" % (name, tot, sum(v[2] for v in agg.values()) / tot / 1e9))
+            for k, (n, t, f) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+                print("   %-52s x%3d %7.3f ms %5.1f%% %7.1f TF/s" % (k, n, t, 100 * t / tot, f / t / 1e9))
+        K.PROFILE = K.PROFILE_WG = None
     n0 = _lib.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
