@@ -700,29 +700,36 @@ extern "C" int csbsr_softmax_gather(const float* logits, const void* feats, floa
 
 // ---------------------------------------------------------------------------------------------------------------
 // 3x3 conv with very few output channels (sr_reconst / output_conv, 128 -> 3: kbpn.py:361, :68) as "tap expansion":
-// a 1x1 GEMM z[q][t*co + c] = sum_ci x[q][ci] * w[c][ci][t] on the tensor cores (N = 9*co instead of nine N = co GEMMs
-// that each pay the full 128-row A-operand read), then this gather: out[p][c] = sum_t z[p + d_t][t*co + c] (zero outside
+// a 1x1 GEMM z[q][t*cp + c] = sum_ci x[q][ci] * w[c][ci][t] (cp = co rounded up to 4) on the tensor cores (N = 9*co instead of nine N = co GEMMs
+// that each pay the full 128-row A-operand read), then this gather: out[p][c] = sum_t z[p + d_t][t*cp + c] (zero outside
 // the image = the conv zero padding), accumulated into fp32 planar windows.
 namespace csbsr {
 template <int CO>
 __global__ void tap_gather_kernel(const __nv_bfloat16* __restrict__ z, int z_pitch, float* out, int out_pitch,
                                   int out_coff, const float* r32, int r_pitch, int r_coff, int n, int h, int w) {
+    constexpr int CP = (CO + 3) / 4 * 4;            // channels of one tap are padded to 4 -> 8-byte aligned uint2 loads
     const size_t total = static_cast<size_t>(n) * h * w;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int x = static_cast<int>(i % w);
         const int y = static_cast<int>((i / w) % h);
         const int img = static_cast<int>(i / (static_cast<size_t>(w) * h));
-        float acc[CO];
+        float acc[CP];
 #pragma unroll
-        for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+        for (int c = 0; c < CP; ++c) acc[c] = 0.f;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
             if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
-            const __nv_bfloat16* zp = z + ((static_cast<size_t>(img) * h + yy) * w + xx) * z_pitch + t * CO;
+            const uint2* zp = reinterpret_cast<const uint2*>(z + ((static_cast<size_t>(img) * h + yy) * w + xx) * z_pitch + t * CP);
 #pragma unroll
-            for (int c = 0; c < CO; ++c) acc[c] += __bfloat162float(zp[c]);
+            for (int v = 0; v < CP / 4; ++v) {
+                const uint2 q = __ldg(zp + v);
+                acc[4 * v + 0] += __uint_as_float(q.x << 16);
+                acc[4 * v + 1] += __uint_as_float(q.x & 0xFFFF0000u);
+                acc[4 * v + 2] += __uint_as_float(q.y << 16);
+                acc[4 * v + 3] += __uint_as_float(q.y & 0xFFFF0000u);
+            }
         }
         const size_t plane = static_cast<size_t>(h) * w, pix = static_cast<size_t>(y) * w + x;
         float rv[CO];
@@ -739,6 +746,7 @@ extern "C" int csbsr_tap_gather3x3(const void* z, int z_pitch, int z_coff, float
                                    const float* r32, int r_pitch, int r_coff, int n, int h, int w, int co, void* stream) {
     CSBSR_REQUIRE(z && out && n > 0 && h > 0 && w > 0, "tap_gather3x3: bad arguments");
     CSBSR_REQUIRE(co == 3 || co == 6 || co == 9 || co == 12, "tap_gather3x3: co=%d must be 3, 6, 9 or 12", co);
+    CSBSR_REQUIRE(z_pitch % 4 == 0 && z_coff % 4 == 0, "tap_gather3x3: z pitch / offset must be multiples of 4 channels");
     const __nv_bfloat16* zp = reinterpret_cast<const __nv_bfloat16*>(z) + z_coff;
     const size_t total = static_cast<size_t>(n) * h * w;
     const int grid = grid_for(total, 256);

@@ -261,11 +261,14 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
 
 
 def pack_tapexp3x3(weight, cout_pad=None):
-    """[co, ci, 3, 3] conv weight (padding 1) -> 1x1 PackedConv with 9*co outputs, channel t*co + c = tap t of output c."""
+    """[co, ci, 3, 3] conv weight (padding 1) -> 1x1 PackedConv with 9*cp outputs (cp = co rounded up to 4 so one tap is
+    a whole number of 8-byte words), channel t*cp + c = tap t of output c."""
     co, ci, R, S = weight.shape
     assert R == 3 and S == 3
-    w = weight.detach().float().permute(2, 3, 0, 1).reshape(9 * co, ci, 1, 1)
-    pc = pack_conv(w, cout_pad=cout_pad or round_up(9 * co, 16))
+    cp = round_up(co, 4)
+    w = torch.zeros((9, cp, ci), dtype=torch.float32, device=weight.device)
+    w[:, :co] = weight.detach().float().permute(2, 3, 0, 1).reshape(9, co, ci)
+    pc = pack_conv(w.reshape(9 * cp, ci, 1, 1), cout_pad=cout_pad or round_up(9 * cp, 16))
     pc.macs_per_pixel = 9 * co * ci
     pc.tap_co = co
     return pc
@@ -275,7 +278,7 @@ def tap_gather3x3(z, co, out, r32=None):
     """out (PlanarWin or fp32 [N,co,H,W]) = r32 + sum over the 9 taps of the shifted tap-expanded map `z` (Fmap)."""
     ow = out if isinstance(out, PlanarWin) else PlanarWin(out, 0, co)
     rw = None if r32 is None else (r32 if isinstance(r32, PlanarWin) else PlanarWin(r32, 0, co))
-    assert ow.c == co and (rw is None or rw.c == co) and z.c >= 9 * co
+    assert ow.c == co and (rw is None or rw.c == co) and z.c >= 9 * round_up(co, 4)
     _call("csbsr_tap_gather3x3", z.ptr(), z.pitch, z.coff, ow.t.data_ptr(), ow.t.shape[1], ow.coff,
           rw.t.data_ptr() if rw is not None else None, rw.t.shape[1] if rw is not None else 0, rw.coff if rw is not None else 0,
           z.n, z.h, z.w, co)

@@ -179,8 +179,8 @@ int csbsr_bilinear_add_nhwc(const void* x, const void* base, void* y, int n, int
 int csbsr_softmax_gather(const float* logits, const void* feats, float* ctx, int n, int hw, int c, int f_pitch,
                          int f_coff, void* stream);
 /* 3x3 conv with <= 12 output channels as tap expansion: `z` is the bf16 NHWC result of the 1x1 conv whose output
- * channel t*co + c holds tap t (row-major 3x3) of output channel c; this gathers
- * out[n][out_coff+c][y][x] = (r32 ? r32[n][r_coff+c][y][x] : 0) + sum_t z[n][y+t/3-1][x+t%3-1][t*co+c]  (fp32 planar,
+ * channel t*cp + c (cp = co rounded up to 4) holds tap t (row-major 3x3) of output channel c; this gathers
+ * out[n][out_coff+c][y][x] = (r32 ? r32[n][r_coff+c][y][x] : 0) + sum_t z[n][y+t/3-1][x+t%3-1][t*cp+c]  (fp32 planar,
  * zero outside the image).  sr_reconst / output_conv of KBPN (model/modeling/kbpn.py:361, :68, :113). */
 int csbsr_tap_gather3x3(const void* z, int z_pitch, int z_coff, float* out, int out_pitch, int out_coff, const float* r32,
                         int r_pitch, int r_coff, int n, int h, int w, int co, void* stream);
