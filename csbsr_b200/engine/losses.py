@@ -101,9 +101,16 @@ def kbpn_loss(sr, hr, lr, kvec, k_gt, weights=(0.4, 0.4, 0, 2), ksize=21, factor
     return loss, kn.view(b, 1, ksize, ksize)
 
 
-def calc_loss(sr_loss, segment_loss_mean, task_loss_weight):
-    """trainer.calc_loss (trainer.py:406-430): (1-beta)*mean(sr_loss) + beta*mean(segment_loss)."""
-    return (1 - task_loss_weight) * sr_loss.mean() + task_loss_weight * segment_loss_mean
+def calc_loss(sr_loss, segment_loss_mean, task_loss_weight, iteration=None, cfg=None):
+    """trainer.calc_loss + calc_pretrain_loss (trainer.py:406-438): (1-beta)*mean(sr_loss) + beta*mean(segment_loss); only
+    the SR term while `iteration` is inside SOLVER.SR_PRETRAIN_ITER, only the segmentation term inside SEG_PRETRAIN_ITER."""
+    loss = (1 - task_loss_weight) * sr_loss.mean() + task_loss_weight * segment_loss_mean
+    if iteration is not None and cfg is not None:
+        if cfg.SOLVER.SR_PRETRAIN_ITER[0] <= iteration < cfg.SOLVER.SR_PRETRAIN_ITER[1]:
+            loss = sr_loss.mean()
+        if cfg.SOLVER.SEG_PRETRAIN_ITER[0] <= iteration < cfg.SOLVER.SEG_PRETRAIN_ITER[1]:
+            loss = segment_loss_mean
+    return loss
 
 
 # ------------------------------------------------------------------ differentiable forms used by the training step

@@ -35,12 +35,15 @@ class FusedAdam:
         self.exp_avg = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(self.n, dtype=torch.float32, device=dev)
         off = 0
+        self.slots = []                       # (offset, padded size) of every parameter in the flat buffers
         for p, sz in zip(self.params, sizes):
             view = self.flat_p[off:off + p.numel()].view(p.shape)
             view.copy_(p.data)
             p.data = view
             p.grad = self.flat_g[off:off + p.numel()].view(p.shape)
+            self.slots.append((off, sz))
             off += sz
+        self.param_steps = [0] * len(self.params)   # torch.optim.Adam keeps one step counter per parameter
         self.base_lr, self.betas, self.eps = lr, betas, eps
         self.lr_lambda = lr_lambda
         self.step_count = 0                   # optimizer steps taken
@@ -61,12 +64,28 @@ class FusedAdam:
         return allreduce_flat(self.flat_g, self.bucket_elems, group)
 
     def step(self, world_size=1):
+        """One Adam step on every parameter with requires_grad (frozen ones are skipped like torch's `grad is None`:
+        neither their value nor their moments nor their step counter move).  Adjacent active parameters with the same step
+        counter are updated by one launch -- a single launch over the whole buffer outside the pre-training phases."""
         self.step_count += 1
-        rc = _lib.lib().csbsr_adam_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
-                                        self.exp_avg_sq.data_ptr(), self.n, self.lr, self.betas[0], self.betas[1], self.eps,
-                                        self.step_count, 1.0 / world_size, 1, _lib.stream_ptr())
-        _lib.check(rc, "csbsr_adam_step")
-        _lib.count_launch("csbsr_adam_step")
+        runs, cur = [], None
+        for i, (p, (off, sz)) in enumerate(zip(self.params, self.slots)):
+            if not p.requires_grad:
+                cur = None
+                continue
+            self.param_steps[i] += 1
+            if cur is not None and cur[2] == self.param_steps[i] and cur[0] + cur[1] == off:
+                cur[1] += sz
+            else:
+                cur = [off, sz, self.param_steps[i]]
+                runs.append(cur)
+        for off, n, step in runs:
+            rc = _lib.lib().csbsr_adam_step(self.flat_p.data_ptr() + 4 * off, self.flat_g.data_ptr() + 4 * off,
+                                            self.exp_avg.data_ptr() + 4 * off, self.exp_avg_sq.data_ptr() + 4 * off, n, self.lr,
+                                            self.betas[0], self.betas[1], self.eps, step, 1.0 / world_size, 1,
+                                            _lib.stream_ptr())
+            _lib.check(rc, "csbsr_adam_step")
+            _lib.count_launch("csbsr_adam_step")
 
     def scheduler_step(self):
         self.sched_count += 1

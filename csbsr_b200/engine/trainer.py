@@ -17,7 +17,7 @@ def train_step(model, optimizer, cfg, iteration, hr, mask, params, world_size=1)
     lr_img, kernels = G.degrade(hr, params, ksize=cfg.BLUR.KERNEL_SIZE_OUTPUT, factor=cfg.MODEL.SCALE_FACTOR)
     seg_loss, sr_loss, seg, sr, kp = model(iteration, lr_img, sr_targets=hr, segment_targets=mask,
                                            kernel_targets=kernels.unsqueeze(1))
-    loss = calc_loss(sr_loss, seg_loss.mean(), cfg.SOLVER.TASK_LOSS_WEIGHT)
+    loss = calc_loss(sr_loss, seg_loss.mean(), cfg.SOLVER.TASK_LOSS_WEIGHT, iteration, cfg)
     loss.backward()
     if world_size > 1:
         optimizer.all_reduce_grads()
@@ -31,9 +31,14 @@ def do_train(args, cfg, model, optimizer, batches, rank=0, world_size=1, log=pri
     model.train()
     t0 = time.time()
     for iteration, hr, mask, params in batches:
+        # boundary-loss alpha schedule, poked from the trainer before every step (fix_1st_stage_model_params,
+        # trainer.py:495-508): frozen at its start value during SR pre-training, one schedule tick per iteration after it
+        if cfg.SOLVER.SR_PRETRAIN_ITER[0] <= iteration < cfg.SOLVER.SR_PRETRAIN_ITER[1]:
+            model.ss_loss_fn.fix_alpha, model.ss_loss_fn.iter = True, 1
+        else:
+            model.ss_loss_fn.fix_alpha = False
+            model.ss_loss_fn.update_alpha()
         loss, seg_l, sr_l = train_step(model, optimizer, cfg, iteration, hr, mask, params, world_size)
-        # boundary-loss alpha schedule: poked from the trainer once per iteration in the joint phase (trainer.py:497-508)
-        model.ss_loss_fn.update_alpha()
         if iteration % args.log_step == 0 and rank == 0:
             torch.cuda.synchronize()
             log("===> Iter: {:07d}, LR: {:.06f}, Cost: {:.2f}s, Loss: {:.6f} (seg {:.6f}, sr {:.6f}), alpha {:.3f}".format(

@@ -150,6 +150,25 @@ class JointModelWithLoss(JointModel):
         self.dropout = True                       # parity harness switches Dropout2d off (masks are random)
         self.freeze_bn = False                    # True: BatchNorm uses its running statistics in train mode too
 
+    def apply_phase(self, iter):
+        """requires_grad switches of KBPN._pretrain_check / KBlock._pretrain_check (kbpn.py:118-155, 414-447) as a function
+        of the iteration.  Returns True while the ground-truth kernel drives KBPN (SR-module pre-training)."""
+        s = self.cfg.SOLVER
+        in_sr = s.SR_SR_MODULE_PRETRAIN_ITER[0] <= iter < s.SR_SR_MODULE_PRETRAIN_ITER[1]
+        k_lo, k_hi = s.SR_KERNEL_MODULE_PRETRAIN_ITER
+        in_k = k_lo <= iter < k_hi
+        in_k_early = k_lo <= iter < k_hi - 1          # KBPN re-enables its SR layers one iteration early (kbpn.py:135)
+        for name, p in self.sr_model.named_parameters():
+            if ".kb.kernel_predictor." in name:
+                p.requires_grad_(not in_sr)
+            elif ".kb.sr_reconst." in name or ".kb.up_conv1." in name:
+                p.requires_grad_(not in_k)
+            elif name.startswith("predictor."):
+                p.requires_grad_(True)
+            else:                                      # feat, UpBlock / DownBlock / SFTlayer of every stage, output_conv
+                p.requires_grad_(not in_k_early)
+        return in_sr
+
     def _tensors(self):
         t = dict(self.named_parameters())
         t.update(dict(self.named_buffers()))
@@ -161,11 +180,10 @@ class JointModelWithLoss(JointModel):
         if not torch.cuda.is_available() or not _lib.lib().csbsr_device_ok():
             raise _lib.CsbsrError("csbsr_b200 needs an sm_100 CUDA device; there is no CPU fallback")
         cfg = self.cfg
-        for lo, hi in (cfg.SOLVER.SR_PRETRAIN_ITER, cfg.SOLVER.SEG_PRETRAIN_ITER, cfg.SOLVER.SR_SR_MODULE_PRETRAIN_ITER,
-                       cfg.SOLVER.SR_KERNEL_MODULE_PRETRAIN_ITER):
-            if lo <= iter < hi:
-                raise NotImplementedError("training graph covers the joint phase only (iteration %d is inside the "
-                                          "pre-training window [%d, %d))" % (iter, lo, hi))
+        if cfg.SOLVER.SEG_PRETRAIN_ITER[0] <= iter < cfg.SOLVER.SEG_PRETRAIN_ITER[1]:
+            raise NotImplementedError("segmentation pre-training (SEG_PRETRAIN_ITER) is not built")
+        sr_module_pre = self.apply_phase(iter)
+        sr_only = cfg.SOLVER.SR_PRETRAIN_ITER[0] <= iter < cfg.SOLVER.SR_PRETRAIN_ITER[1]   # loss = sr_loss (trainer.py:432-434)
         device = torch.device("cuda", torch.cuda.current_device())
         mv = lambda t: None if t is None else t.to(device=device, dtype=torch.float32)
         x, sr_targets, segment_targets, kernel_targets = mv(x), mv(sr_targets), mv(segment_targets), mv(kernel_targets)
@@ -173,11 +191,14 @@ class JointModelWithLoss(JointModel):
         was = torch.backends.cudnn.enabled
         torch.backends.cudnn.enabled = False        # glue ops (BN, pooling, resampling) stay on native aten kernels
         try:
-            sr, kvec = TG.kbpn_forward(P, x, self.num_stages, self.ksize, self.scale_factor)
-            normed = torch.nn.functional.instance_norm(sr, eps=1e-5)              # norm_sr, build_model.py:135-137
+            sr, kvec = TG.kbpn_forward(P, x, self.num_stages, self.ksize, self.scale_factor,
+                                       gt_kernel=kernel_targets if sr_module_pre else None)
             seg_fwd = TG.hrnet_ocr_forward if self.seg_model_name == "HRNet_OCR" else TG.pspnet_forward
-            seg, aux = seg_fwd(P, normed, bn_training=self.training and not self.freeze_bn,
-                               dropout=self.dropout and self.training)
+            # while only sr_loss is optimised the segmentation net is evaluated for logging only: no tape needed
+            with torch.set_grad_enabled(torch.is_grad_enabled() and not sr_only):
+                normed = torch.nn.functional.instance_norm(sr, eps=1e-5)          # norm_sr, build_model.py:135-137
+                seg, aux = seg_fwd(P, normed, bn_training=self.training and not self.freeze_bn,
+                                   dropout=self.dropout and self.training)
             sr_loss, kernel_preds = LS.kbpn_loss_train(sr, sr_targets, x, kvec, kernel_targets, self.sr_loss_weights,
                                                        self.ksize, self.scale_factor)
             amp = self.wf_amp if self.oriented_w_iter <= iter else 0.0

@@ -117,9 +117,10 @@ def _down_block(P, p, x):
     return l1 + l0
 
 
-def _k_block(P, p, concat_h, h, x_lr, kvec, k_out, scale):
+def _k_block(P, p, concat_h, h, x_lr, kvec, k_out, scale, predict_kernel=True):
     sr_t = _convblock(P, p + ".sr_reconst", concat_h, padding=1)
-    d_kernel = _kernel_predictor(P, p + ".kernel_predictor", sr_t, kvec, k_out)
+    # during the SR-module pre-training the (ground-truth) kernel passes through unchanged (kbpn.py:386-388)
+    d_kernel = _kernel_predictor(P, p + ".kernel_predictor", sr_t, kvec, k_out) if predict_kernel else kvec
     vec = d_kernel / d_kernel.sum(dim=1, keepdim=True)
     pseudo_lr = blur_per_sample(to_nchw(sr_t, 3), vec, k_out, scale)
     e_h = _deconvblock(P, p + ".up_conv1", to_nhwc(pseudo_lr - x_lr))
@@ -135,25 +136,30 @@ def _sft(P, p, feats, kvec):
     return feats * torch.sigmoid(branch("scale")) + branch("shift")
 
 
-def kbpn_forward(P, x_lr, num_stages=4, k_out=21, scale=4, prefix="sr_model."):
-    """x_lr fp32 [B,3,h,w] -> (sr fp32 [B,3,4h,4w], kernel vector fp32 [B, 441] (normalised, as KBlock returns it))."""
+def kbpn_forward(P, x_lr, num_stages=4, k_out=21, scale=4, prefix="sr_model.", gt_kernel=None):
+    """x_lr fp32 [B,3,h,w] -> (sr fp32 [B,3,4h,4w], kernel vector fp32 [B, 441] (normalised, as KBlock returns it)).
+    `gt_kernel` (B,1,k,k): SR-module pre-training (kbpn.py:89-91, 386-388) -- the ground-truth kernel replaces the initial
+    prediction and the per-stage kernel predictors are skipped."""
     p = prefix
     f = to_nhwc(x_lr)
     for i in (0, 2, 4, 6):
         f = F.relu(conv2d(f, P[p + "feat.%d.weight" % i], P[p + "feat.%d.bias" % i], padding=1))
     init_f = f
-    z = init_f
-    for i in range(3):
-        z = _convblock(P, p + "predictor.feat_ext.%d" % i, z, padding=1, act="prelu")
-    ke2 = P[p + "predictor.feat_ext.2.layer.weight"].shape[0]
-    ker = _upscale_kernel(_gap(z, ke2), k_out)
-    kvec = (ker / ker.sum(dim=(2, 3), keepdim=True)).reshape(x_lr.shape[0], k_out * k_out)
+    if gt_kernel is not None:
+        kvec = gt_kernel.reshape(x_lr.shape[0], k_out * k_out).float()
+    else:
+        z = init_f
+        for i in range(3):
+            z = _convblock(P, p + "predictor.feat_ext.%d" % i, z, padding=1, act="prelu")
+        ke2 = P[p + "predictor.feat_ext.2.layer.weight"].shape[0]
+        ker = _upscale_kernel(_gap(z, ke2), k_out)
+        kvec = (ker / ker.sum(dim=(2, 3), keepdim=True)).reshape(x_lr.shape[0], k_out * k_out)
     low, concat_h, concat_l = init_f, None, None
     for s in range(num_stages):
         sp = p + "back_projection_stages.%d" % s
         h = _up_block(P, sp + ".up", low)
         pre = h if concat_h is None else torch.cat((concat_h, h), dim=3)
-        h, kvec = _k_block(P, sp + ".kb", pre, h, x_lr, kvec, k_out, scale)
+        h, kvec = _k_block(P, sp + ".kb", pre, h, x_lr, kvec, k_out, scale, predict_kernel=gt_kernel is None)
         concat_h = h if concat_h is None else torch.cat((concat_h, h), dim=3)
         if s < num_stages - 1:
             low = _down_block(P, sp + ".down", concat_h)

@@ -97,10 +97,10 @@ def down_block(sd, p, x):
     return l1 + l0
 
 
-def k_block(sd, p, concat_h, h, x_lr, kvec, k_out, scale):
-    """KBlock.forward (SUM_LR_ERROR_POS='HR', outside SR pretrain): kbpn.py:382-412."""
+def k_block(sd, p, concat_h, h, x_lr, kvec, k_out, scale, predict_kernel=True):
+    """KBlock.forward (SUM_LR_ERROR_POS='HR'): kbpn.py:382-412; the kernel predictor is skipped during SR pretrain (:386)."""
     sr_t = _convblock(sd, p + ".sr_reconst", concat_h, 3, padding=1, act=None)
-    d_kernel = kernel_predictor_ikc(sd, p + ".kernel_predictor", sr_t, kvec, k_out)
+    d_kernel = kernel_predictor_ikc(sd, p + ".kernel_predictor", sr_t, kvec, k_out) if predict_kernel else kvec
     vec = d_kernel / d_kernel.sum(dim=1).view(-1, 1, 1, 1)       # GAP of a constant map is the vector itself
     weight = vec.view(-1, 1, k_out, k_out)
     pad = (k_out - 1) // 2
@@ -121,21 +121,24 @@ def sft_layer(sd, p, features, kvec):
     return features * torch.sigmoid(scale) + shift
 
 
-def kbpn_forward(sd, x, num_stages=4, k_out=21, scale=4, prefix="sr_model.", return_intermediates=False):
+def kbpn_forward(sd, x, num_stages=4, k_out=21, scale=4, prefix="sr_model.", return_intermediates=False, gt_kernel=None):
     """KBPN.forward with iter=-1 (eval): kbpn.py:84-116. Returns sr (B,3,4h,4w) and kernel vec (B,441,1,1)."""
     p = prefix
     f = x
     for i in (0, 2, 4, 6):                                        # VGG16 head, :42-44
         f = F.relu(_conv(sd, p + "feat.%d" % i, f, padding=1))
     init_f = f
-    kvec = predictor_with_gap(sd, p + "predictor", init_f, k_out)
+    if gt_kernel is not None:                                     # SR-module pre-training: kbpn.py:89-91
+        kvec = gt_kernel.reshape(-1, k_out * k_out, 1, 1)
+    else:
+        kvec = predictor_with_gap(sd, p + "predictor", init_f, k_out)
     inter = {"init_f": init_f, "init_kernel": kvec}
     low, concat_h, concat_l = init_f, None, None
     for s in range(num_stages):                                   # KernelBackProjectionStageWithSFT.forward :172-189
         sp = p + "back_projection_stages.%d" % s
         h = up_block(sd, sp + ".up", low)
         pre = h if concat_h is None else torch.cat((concat_h, h), dim=1)
-        h, kvec, sr_t = k_block(sd, sp + ".kb", pre, h, x, kvec, k_out, scale)
+        h, kvec, sr_t = k_block(sd, sp + ".kb", pre, h, x, kvec, k_out, scale, predict_kernel=gt_kernel is None)
         inter["sr_t%d" % s] = sr_t
         inter["kvec%d" % s] = kvec
         concat_h = h if concat_h is None else torch.cat((concat_h, h), dim=1)

@@ -14,16 +14,17 @@ from . import loss_ref as L
 from . import torch_ref as T
 
 
-def train_forward(sd, lr, hr, mask, kgt, alpha, beta=0.3, wf_amp=1.0, bn_train=True, hrnet=False):
+def train_forward(sd, lr, hr, mask, kgt, alpha, beta=0.3, wf_amp=1.0, bn_train=True, hrnet=False, gt_kernel_phase=False,
+                  sr_only=False):
     """-> (loss, seg_loss, sr_loss, sr, seg, aux).  `sd` tensors that require grad receive gradients."""
     T.BN_TRAIN = bn_train
     try:
-        sr, kvec = T.kbpn_forward(sd, lr)
+        sr, kvec = T.kbpn_forward(sd, lr, gt_kernel=kgt if gt_kernel_phase else None)
         seg, aux = (T.hrnet_ocr_forward if hrnet else T.pspnet_forward)(sd, F.instance_norm(sr, eps=1e-5))
     finally:
         T.BN_TRAIN = False
     kmap = kvec.expand(-1, -1, lr.shape[2], lr.shape[3])
     sr_loss, _, _ = L.kbpn_loss(sr, hr, lr, kmap, kgt)
     seg_loss = L.seg_loss(seg, aux, mask, alpha, wf_amp=wf_amp)
-    loss = (1 - beta) * sr_loss.mean() + beta * seg_loss.mean()
+    loss = sr_loss.mean() if sr_only else (1 - beta) * sr_loss.mean() + beta * seg_loss.mean()   # calc_pretrain_loss
     return loss, seg_loss, sr_loss, sr, seg, aux

@@ -195,7 +195,7 @@ if __name__ == "__main__":
         gen_joint(hrnet=True)
 
 
-def gen_train(bn_eval=False, hrnet=False):
+def gen_train(bn_eval=False, hrnet=False, iteration=40000):
     """One JointModelWithLoss forward + backward of the UNMODIFIED reference at iteration 40000 (all phases active,
     w^F on, m^F = 1), Dropout2d disabled (p = 0) so the step is deterministic: losses and a sample of gradients.
     bn_eval=True additionally puts the BatchNorm layers in eval mode (running statistics): with random weights and a
@@ -212,7 +212,7 @@ def gen_train(bn_eval=False, hrnet=False):
         cfg.SOLVER.TASK_LOSS_WEIGHT = 0.9                       # config #4 (beta = 0.9)
         rh.patch_hrnet_configer()
     with contextlib.redirect_stdout(io.StringIO()):
-        m = JointModelWithLoss(cfg, num_train_ds=100, resume_iter=40000, sr_transforms=FactorResize(4, "bicubic"))
+        m = JointModelWithLoss(cfg, num_train_ds=100, resume_iter=iteration, sr_transforms=FactorResize(4, "bicubic"))
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
     sd.update(P.synth_state_dict(P.hrnet_ocr_param_shapes() if hrnet else P.pspnet_param_shapes(), prefix="segmentation_model."))
     missing, unexpected = m.load_state_dict(sd, strict=False)
@@ -236,12 +236,12 @@ def gen_train(bn_eval=False, hrnet=False):
     kgt = torch.rand(2, 1, 21, 21, generator=g)
     kgt = kgt / kgt.sum(dim=(2, 3), keepdim=True)
     with contextlib.redirect_stdout(io.StringIO()):
-        seg_loss, sr_loss, seg, sr, kp = m(40000, lr.clone(), sr_targets=hr.clone(), segment_targets=mask.clone(),
+        seg_loss, sr_loss, seg, sr, kp = m(iteration, lr.clone(), sr_targets=hr.clone(), segment_targets=mask.clone(),
                                            kernel_targets=kgt.clone())
 
         class A:
             pass
-        loss, _, _ = calc_loss(seg_loss, 0.0, sr_loss, 0.0, 40000, cfg, A())
+        loss, _, _ = calc_loss(seg_loss, 0.0, sr_loss, 0.0, iteration, cfg, A())
     loss.backward()
     out = {"hr": hr_np, "mask": mask_np, "lr": lr.numpy(), "kgt": kgt.numpy(), "alpha": np.float32(alpha),
            "loss": np.float64(loss.item()), "seg_loss_mean": np.float64(seg_loss.mean().item()),
@@ -271,17 +271,26 @@ def gen_train(bn_eval=False, hrnet=False):
             norms[k] = float(p_.grad.double().norm().item())
     out["grad_norm_names"] = np.array(sorted(norms))
     out["grad_norms"] = np.array([norms[k] for k in sorted(norms)])
+    out["iteration"] = np.int64(iteration)
+    out["requires_grad_names"] = np.array(sorted(k for k, p_ in params.items() if p_.requires_grad))
+    names = [k for k in names if params[k].grad is not None]
     for k in names:                      # flattened gradients, subsampled with a fixed stride to keep the fixture small
         gflat = params[k].grad.numpy().astype(np.float32).reshape(-1)
         stride = max(1, gflat.size // 20000)
         out["grad:" + k] = gflat[::stride].astype(np.float16 if False else np.float32)
         out["stride:" + k] = np.int64(stride)
-    np.savez_compressed(os.path.join(HERE, "train_step_hrnet.npz" if hrnet else "train_step_bneval.npz" if bn_eval else "train_step.npz"), **out)
+    fname = "train_step_hrnet.npz" if hrnet else "train_step_bneval.npz" if bn_eval else "train_step.npz"
+    if iteration != 40000:
+        fname = "train_step_it%d.npz" % iteration
+    np.savez_compressed(os.path.join(HERE, fname), **out)
     print("train_step.npz loss", loss.item(), "seg", seg_loss.mean().item(), "sr", sr_loss.detach().numpy(), "grads", len(norms))
 
 
 if __name__ == "__main__" and "train" in sys.argv[1:]:
-    if "hrnet" in sys.argv[1:]:
+    if "pretrain" in sys.argv[1:]:
+        for it in (5, 15000, 20000, 25000):    # SR-module / kernel-module pre-training, its last iteration, SR-only phase
+            gen_train(bn_eval=True, iteration=it)
+    elif "hrnet" in sys.argv[1:]:
         gen_train(bn_eval=True, hrnet=True)
     else:
         gen_train()

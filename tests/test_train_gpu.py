@@ -148,7 +148,7 @@ def _train_model(hrnet=False):
     return m.cuda(), sd, c
 
 
-@pytest.mark.parametrize("variant", ["pspnet_bneval", "pspnet", "hrnet_bneval"])
+@pytest.mark.parametrize("variant", ["pspnet_bneval", "pspnet", "hrnet_bneval", "it5", "it15000", "it20000", "it25000"])
 def test_train_step_vs_reference_golden(variant):
     """One joint training step (iteration 40000, w^F on, Dropout2d off) of the tcgen05 training graph against the
     unmodified reference's losses and gradients (tests/golden/train_step*.npz; the fp32 oracle is pinned to the same
@@ -162,18 +162,23 @@ def test_train_step_vs_reference_golden(variant):
     import os
     import numpy as np
     from csbsr_b200.engine.losses import calc_loss
-    bn_eval, hrnet = variant.endswith("bneval"), variant.startswith("hrnet")     # hrnet: config #4 (HRNet-W48 + OCR, beta 0.9)
+    # itN: the pre-training phases (5: SR modules with the ground-truth kernel, 15000: kernel predictors only, 20000: its
+    # last iteration where KBPN re-enables its SR layers one step early, 25000: whole SR net, loss = sr_loss throughout)
+    bn_eval, hrnet = variant.endswith("bneval") or variant.startswith("it"), variant.startswith("hrnet")
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
                              {"pspnet": "train_step.npz", "pspnet_bneval": "train_step_bneval.npz",
-                              "hrnet_bneval": "train_step_hrnet.npz"}[variant]))
+                              "hrnet_bneval": "train_step_hrnet.npz"}.get(variant, "train_step_%s.npz" % variant)))
+    it = int(g["iteration"]) if "iteration" in g.files else 40000
     m, sd, c = _train_model(hrnet)
     m.train()
     m.dropout = False
     m.freeze_bn = bn_eval
     m.ss_loss_fn.alpha = float(g["alpha"])
     lr, hr, mask, kgt = (torch.from_numpy(g[k]).cuda() for k in ("lr", "hr", "mask", "kgt"))
-    seg_loss, sr_loss, seg, sr, kp = m(40000, lr, sr_targets=hr, segment_targets=mask, kernel_targets=kgt)
-    loss = calc_loss(sr_loss, seg_loss.mean(), c.SOLVER.TASK_LOSS_WEIGHT)
+    for p_ in m.parameters():
+        p_.grad = torch.zeros_like(p_)
+    seg_loss, sr_loss, seg, sr, kp = m(it, lr, sr_targets=hr, segment_targets=mask, kernel_targets=kgt)
+    loss = calc_loss(sr_loss, seg_loss.mean(), c.SOLVER.TASK_LOSS_WEIGHT, it, c)
     loss.backward()
     torch.cuda.synchronize()
     seg_err = np.abs(seg.detach().cpu().numpy() - g["seg"].astype(np.float32)).mean()
@@ -204,6 +209,8 @@ def test_train_step_vs_reference_golden(variant):
     bad = []
     for k, p_ in params.items():
         assert p_.grad is not None and torch.isfinite(p_.grad).all(), k
+        if k not in names:                       # frozen / not on the loss path in this phase: the reference has grad None
+            assert p_.grad.abs().max().item() == 0, k
         if k in names:
             ref_n = norms[names.index(k)]
             if p_.numel() == 1:
@@ -249,8 +256,13 @@ def test_fused_adam_vs_torch_adam():
     opt = FusedAdam(ps, lr=2e-5, lr_lambda=lambda it: 10 if it >= 3 else 1)
     topt = torch.optim.Adam(ref, lr=2e-5, betas=(0.9, 0.999), eps=1e-8)
     sched = torch.optim.lr_scheduler.LambdaLR(topt, lr_lambda=lambda it: 10 if it >= 3 else 1)
-    for step in range(5):
-        for p, r in zip(ps, ref):
+    for step in range(7):
+        frozen = {1, 3} if step in (2, 3, 4) else set()          # pre-training phases freeze modules: torch skips grad None
+        for i, (p, r) in enumerate(zip(ps, ref)):
+            p.requires_grad_(i not in frozen)
+            if i in frozen:
+                r.grad = None
+                continue
             gr = torch.randn(p.shape, generator=g).cuda() * 10 ** float(torch.randint(-4, 2, (1,), generator=g))
             p.grad.copy_(gr)
             r.grad = gr.clone()
