@@ -105,6 +105,8 @@ _SIGNATURES = {
     "csbsr_seg_loss": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_float] * 3 + [C.c_void_p] * 5 +
                        [C.c_size_t, C.c_void_p]),
     "csbsr_seg_loss_wf_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "csbsr_seg_loss_wf_grad": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_void_p] * 4 +
+                               [C.c_size_t, C.c_void_p]),
     "csbsr_seg_loss_wf_mean": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_void_p,
                                                                                               C.c_size_t, C.c_void_p]),
     "csbsr_sr_loss_workspace_bytes": (C.c_size_t, [C.c_int]),

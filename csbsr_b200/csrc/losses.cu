@@ -224,26 +224,69 @@ __global__ void wf_cross_kernel(const float* __restrict__ pm, const float* __res
         Dall[1] += sums[(j * 2 + 1) * 8 + 2] + sums[(j * 2 + 1) * 8 + 3];
     }
     const double numel = static_cast<double>(B) * HW;
-    double acc[2] = {0, 0};
+    double acc[2] = {0, 0}, accq[2] = {0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
         const double w = wmap[i];
 #pragma unroll
         for (int hd = 0; hd < 2; ++hd) {
             const float* pp = hd == 0 ? pm : pa;
             if (!pp) continue;
-            double dj = 0.0;
+            double dj = 0.0, nj = 0.0;
             for (int j = 0; j < B; ++j) {
                 const size_t o = static_cast<size_t>(j) * HW + i;
                 const double p = fmaxf(pp[o], smooth);
                 dj += 1.0 / numel - (2.0 * p * g[o] + dice_smooth) / Dall[hd];
+                nj += 2.0 * p * g[o] + dice_smooth;
             }
             acc[hd] += w * dj;
+            accq[hd] += w * nj;                       // Q = sum_hw W[hw] * sum_j (2 p_j g_j + eps): backward of the Dall term
         }
     }
 #pragma unroll
     for (int hd = 0; hd < 2; ++hd) {
-        const double v = warp_sum(acc[hd]);
+        const double v = warp_sum(acc[hd]), q = warp_sum(accq[hd]);
         if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&cross[hd], v);
+        if ((threadIdx.x & 31) == 0 && q != 0.0) atomicAdd(&cross[2 + hd], q);
+    }
+}
+
+// gradient of the w^F-weighted (B,B,H,W) mean w.r.t. the raw predictions (w^F itself is detached, oriented_weight.py:81):
+//   d/dp_k[hw] = w_hd * up * [ W_k (alpha/2 dbce + (1-alpha) sdf) / (B HW)
+//                              + (alpha/2) / (B^2 HW) * ( -2 g_k SW[hw] / Dall + 2 p_k Q / Dall^2 ) ],  zero where p < smooth
+__global__ void wf_grad_kernel(const float* __restrict__ pm, const float* __restrict__ pa, const float* __restrict__ g,
+                               const float* __restrict__ sdf, const float* __restrict__ wmap, const double* __restrict__ sums,
+                               const double* __restrict__ cross, float* __restrict__ grad_m, float* __restrict__ grad_a,
+                               const float* __restrict__ upstream, int B, int HW, float alpha, float main_w, float aux_w,
+                               float wf_amp, float smooth, float dice_smooth) {
+    const int b = blockIdx.y;
+    double Dall[2] = {dice_smooth, dice_smooth};
+    for (int j = 0; j < B; ++j) {
+        Dall[0] += sums[(j * 2) * 8 + 2] + sums[(j * 2) * 8 + 3];
+        Dall[1] += sums[(j * 2 + 1) * 8 + 2] + sums[(j * 2 + 1) * 8 + 3];
+    }
+    const double up = upstream ? static_cast<double>(*upstream) : 1.0;
+    const double c1 = 1.0 / (static_cast<double>(B) * HW), c2 = (alpha / 2.0) / (static_cast<double>(B) * B * HW);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const size_t o = static_cast<size_t>(b) * HW + i;
+        const float t = g[o], sd = sdf[o];
+        const double W = expf(wf_amp * fabsf(pm[o] - t));
+        const double SW = wmap[i];
+#pragma unroll
+        for (int hd = 0; hd < 2; ++hd) {
+            const float* pp = hd == 0 ? pm : pa;
+            float* gp = hd == 0 ? grad_m : grad_a;
+            if (!pp || !gp) continue;
+            const float raw = pp[o];
+            float gr = 0.f;
+            if (raw >= smooth) {
+                const double p = raw;
+                const double dbce = -(t / (p + smooth) - (1.0 - t) / (1.0 - p + smooth)) / 2.0;
+                const double t1 = c1 * W * (alpha / 2.0 * dbce + (1.0 - alpha) * sd);
+                const double t2 = c2 * (-2.0 * t * SW / Dall[hd] + 2.0 * p * cross[2 + hd] / (Dall[hd] * Dall[hd]));
+                gr = static_cast<float>((hd == 0 ? main_w : aux_w) * up * (t1 + t2));
+            }
+            gp[o] = gr;
+        }
     }
 }
 __global__ void wf_final_kernel(const double* __restrict__ sums, const double* __restrict__ cross, double* __restrict__ out, int B,
@@ -332,7 +375,7 @@ extern "C" int csbsr_sdf(const float* mask, float* sdf, int b, int h, int w, voi
 
 extern "C" size_t csbsr_seg_loss_workspace_bytes(int b) { return al(sizeof(double) * 16 * static_cast<size_t>(b)); }
 extern "C" size_t csbsr_seg_loss_wf_workspace_bytes(int b, int hw) {
-    return al(sizeof(double) * 16 * static_cast<size_t>(b)) + al(sizeof(double) * 2) + al(sizeof(float) * static_cast<size_t>(hw));
+    return al(sizeof(double) * 16 * static_cast<size_t>(b)) + al(sizeof(double) * 4) + al(sizeof(float) * static_cast<size_t>(hw));
 }
 
 extern "C" int csbsr_seg_loss(const float* p_main, const float* p_aux, const float* target, const float* sdf, int b, int hw,
@@ -364,12 +407,35 @@ extern "C" int csbsr_seg_loss_wf_mean(const float* p_main, const float* p_aux, c
     CSBSR_REQUIRE(workspace_bytes >= need, "seg_loss_wf_mean: workspace too small (%zu < %zu)", workspace_bytes, need);
     double* sums = static_cast<double*>(workspace);
     double* cross = reinterpret_cast<double*>(static_cast<char*>(workspace) + al(sizeof(double) * 16 * b));
-    float* wmap = reinterpret_cast<float*>(static_cast<char*>(workspace) + al(sizeof(double) * 16 * b) + al(sizeof(double) * 2));
+    float* wmap = reinterpret_cast<float*>(static_cast<char*>(workspace) + al(sizeof(double) * 16 * b) + al(sizeof(double) * 4));
     CSBSR_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need, stream));
     int slices = (hw + 256 * 8 - 1) / (256 * 8);
     seg_loss_reduce_kernel<<<dim3(slices, b), 256, 0, stream>>>(p_main, p_aux, target, sdf, sums, wmap, hw, wf_amp, 1e-8f);
     wf_cross_kernel<<<slices, 256, 0, stream>>>(p_main, p_aux, target, wmap, sums, cross, b, hw, 1e-8f, 1e-6f);
     wf_final_kernel<<<1, 1, 0, stream>>>(sums, cross, out, b, hw, alpha, main_w, p_aux ? aux_w : 0.f, p_aux != nullptr);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Backward of csbsr_seg_loss_wf_mean: grad_main / grad_aux [B,HW] = upstream * d mean / d p (upstream: DEVICE float or NULL = 1).
+extern "C" int csbsr_seg_loss_wf_grad(const float* p_main, const float* p_aux, const float* target, const float* sdf, int b,
+                                      int hw, float alpha, float main_w, float aux_w, float wf_amp, const float* upstream,
+                                      float* grad_main, float* grad_aux, void* workspace, size_t workspace_bytes,
+                                      void* stream_) {
+    cudaStream_t stream = STREAM(stream_);
+    CSBSR_REQUIRE(p_main && target && sdf && grad_main && workspace && b > 0 && hw > 0, "seg_loss_wf_grad: bad arguments");
+    CSBSR_REQUIRE(!p_aux == !grad_aux, "seg_loss_wf_grad: p_aux and grad_aux go together");
+    const size_t need = csbsr_seg_loss_wf_workspace_bytes(b, hw);
+    CSBSR_REQUIRE(workspace_bytes >= need, "seg_loss_wf_grad: workspace too small (%zu < %zu)", workspace_bytes, need);
+    double* sums = static_cast<double*>(workspace);
+    double* cross = reinterpret_cast<double*>(static_cast<char*>(workspace) + al(sizeof(double) * 16 * b));
+    float* wmap = reinterpret_cast<float*>(static_cast<char*>(workspace) + al(sizeof(double) * 16 * b) + al(sizeof(double) * 4));
+    CSBSR_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need, stream));
+    int slices = (hw + 256 * 8 - 1) / (256 * 8);
+    seg_loss_reduce_kernel<<<dim3(slices, b), 256, 0, stream>>>(p_main, p_aux, target, sdf, sums, wmap, hw, wf_amp, 1e-8f);
+    wf_cross_kernel<<<slices, 256, 0, stream>>>(p_main, p_aux, target, wmap, sums, cross, b, hw, 1e-8f, 1e-6f);
+    wf_grad_kernel<<<dim3(slices, b), 256, 0, stream>>>(p_main, p_aux, target, sdf, wmap, sums, cross, grad_main, grad_aux,
+                                                       upstream, b, hw, alpha, main_w, aux_w, wf_amp, 1e-8f, 1e-6f);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -131,16 +131,50 @@ class _SegLossFn(torch.autograd.Function):
         return gm, ga, None, None, None, None, None
 
 
-def seg_loss_train(p_main, p_aux, target, alpha, wf_amp=0.0, main_w=1.0, aux_w=0.4):
+class _SegLossWfMeanFn(torch.autograd.Function):
+    """Mean of the w^F-weighted (B,B,H,W) loss tensor and its gradient w.r.t. both prediction maps, on the fused kernels."""
+
+    @staticmethod
+    def forward(ctx, p_main, p_aux, target, sdf, alpha, wf_amp, main_w, aux_w):
+        ctx.save_for_backward(p_main, p_aux, target, sdf)
+        ctx.cfg = (alpha, wf_amp, main_w, aux_w)
+        return seg_loss_wf_mean(p_main, p_aux, target, alpha, wf_amp, main_w, aux_w, sdf=sdf).to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, up):
+        p_main, p_aux, target, sdf = ctx.saved_tensors
+        alpha, wf_amp, main_w, aux_w = ctx.cfg
+        pm, pa, g = _f(p_main), _f(p_aux), _f(target)
+        b, hw = pm.shape[0], pm[0].numel()
+        gm, ga = torch.empty_like(pm), torch.empty_like(pa)
+        upf = up.to(torch.float32).contiguous()
+        L = _lib.lib()
+        n = L.csbsr_seg_loss_wf_workspace_bytes(b, hw)
+        ws = _ws(n)
+        rc = L.csbsr_seg_loss_wf_grad(pm.data_ptr(), pa.data_ptr(), g.data_ptr(), sdf.data_ptr(), b, hw, C.c_float(alpha),
+                                      C.c_float(main_w), C.c_float(aux_w), C.c_float(wf_amp), upf.data_ptr(), gm.data_ptr(),
+                                      ga.data_ptr(), ws.data_ptr(), n, _lib.stream_ptr())
+        _lib.check(rc, "csbsr_seg_loss_wf_grad")
+        _lib.count_launch("csbsr_seg_loss_wf_grad")
+        return gm, ga, None, None, None, None, None, None
+
+
+def seg_loss_train(p_main, p_aux, target, alpha, wf_amp=0.0, main_w=1.0, aux_w=0.4, fused=True):
     """MetaSSLossCalc.calc_ss_loss + JointModelWithLoss.multiple_weight (build_model.py:258-278, 422-438) as an autograd
     node.  wf_amp == 0: per-sample (B,) loss on the fused fwd/bwd kernel.  wf_amp != 0: the reference's out_map=True
     path, whose BCE map (B,1,H,W) + Dice term (B,H,W) broadcast to (B,B,H,W) before the w^F weight
-    exp(amp*|p.detach() - g|) multiplies it (loss_functions.py:196-210, 284-345; oriented_weight.py:80-83); formed with
-    elementwise torch ops (the SDF comes from the EDT kernel either way)."""
+    exp(amp*|p.detach() - g|) multiplies it (loss_functions.py:196-210, 284-345; oriented_weight.py:80-83).  fused=True:
+    csbsr_seg_loss_wf_mean / _grad evaluate the mean of that tensor and its gradient in closed form; fused=False forms the
+    tensor itself with elementwise torch ops (kept for callers that need the per-element map)."""
     g = _f(target)
     sdf = compute_sdf(g)
     if wf_amp == 0:
         return _SegLossFn.apply(p_main, p_aux, g, sdf, alpha, main_w, aux_w)
+    if fused and p_aux is not None:
+        # the trainer only ever takes .mean() of the (B,B,H,W) tensor (trainer.py:407): compute that scalar and its gradient
+        # in closed form on the device and hand back a broadcast view with the reference's shape and the same mean
+        b, _, h, w = p_main.shape
+        return _SegLossWfMeanFn.apply(p_main, p_aux, g, sdf, alpha, wf_amp, main_w, aux_w).expand(b, b, h, w)
 
     def combo(p):
         p = p.clamp(min=1e-8)

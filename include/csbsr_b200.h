@@ -221,6 +221,12 @@ size_t csbsr_seg_loss_wf_workspace_bytes(int b, int hw);
 int csbsr_seg_loss_wf_mean(const float* p_main, const float* p_aux, const float* target, const float* sdf, int b, int hw,
                            float alpha, float main_w, float aux_w, float wf_amp, double* out, void* workspace,
                            size_t workspace_bytes, void* stream);
+/* Backward of csbsr_seg_loss_wf_mean: grad_main / grad_aux [B,HW] = (*upstream) * d mean / d prediction (w^F itself is
+ * detached, oriented_weight.py:81; zero where the prediction is below the 1e-8 clamp).  `upstream` is a DEVICE float or
+ * NULL (= 1).  Same workspace as the forward. */
+int csbsr_seg_loss_wf_grad(const float* p_main, const float* p_aux, const float* target, const float* sdf, int b, int hw,
+                           float alpha, float main_w, float aux_w, float wf_amp, const float* upstream, float* grad_main,
+                           float* grad_aux, void* workspace, size_t workspace_bytes, void* stream);
 /* KBPNLoss.forward (model/utils/sr_loss_functions.py:39-56) given the pseudo-LR image of Get_pseudo_lr (:84-102, built
  * with csbsr_blur_per_sample stride 1 + csbsr_resize_bicubic_aa): loss[b] = w_hr*mean|sr-hr| + w_lr*mean|plr-lr| +
  * w_k*mean((k_pred-k_gt)^2); n_* = elements per sample */

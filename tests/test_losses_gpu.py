@@ -52,3 +52,26 @@ def test_kbpn_loss_vs_reference_golden():
     assert np.allclose(kn.cpu().numpy(), g["kbpn_kernel"], rtol=1e-5, atol=1e-9)
     total = LS.calc_loss(loss, torch.tensor(0.25, device=loss.device), 0.3).item()
     assert abs(total - (0.7 * float(g["kbpn_loss"].mean()) + 0.3 * 0.25)) < 1e-5
+
+
+def test_wf_loss_fused_mean_and_gradient_vs_elementwise_autograd():
+    """csbsr_seg_loss_wf_mean / _grad (closed form of the (B,B,H,W) mean) against the elementwise torch formulation."""
+    from csbsr_b200.engine import losses as LS
+    g = torch.Generator().manual_seed(21)
+    B, H, W = 3, 40, 56
+    mask = (torch.rand(B, 1, H, W, generator=g) > 0.8).float().cuda()
+    pm0 = (0.02 + 0.96 * torch.rand(B, 1, H, W, generator=g)).cuda()
+    pm0[0, 0, :2, :3] = 1e-9                                         # below the clamp: zero gradient there
+    pa0 = (0.02 + 0.96 * torch.rand(B, 1, H, W, generator=g)).cuda()
+    outs = []
+    for fused in (True, False):
+        pm, pa = pm0.clone().requires_grad_(True), pa0.clone().requires_grad_(True)
+        lm = LS.seg_loss_train(pm, pa, mask, 0.37, wf_amp=1.0, fused=fused)
+        assert tuple(lm.shape) == (B, B, H, W)
+        (lm.mean() * 1.7).backward()
+        outs.append((lm.mean().item(), pm.grad.clone(), pa.grad.clone()))
+    (v1, gm1, ga1), (v0, gm0, ga0) = outs
+    assert abs(v1 - v0) <= 2e-6 * abs(v0)
+    assert (gm1 - gm0).abs().max().item() <= 1e-4 * gm0.abs().max().item()
+    assert (ga1 - ga0).abs().max().item() <= 1e-4 * ga0.abs().max().item()
+    assert gm1[0, 0, :2, :3].abs().max().item() == 0
