@@ -165,3 +165,77 @@ class _PReLUFn(torch.autograd.Function):
 
 def prelu(x, slope):
     return _PReLUFn.apply(x, slope)
+
+
+class _BlurFn(torch.autograd.Function):
+    """Per-sample depthwise blur, stride s, zero padding (k-1)/2: every image of the batch with its own k x k kernel
+    (KBlock pseudo-LR, kbpn.py:395-402; Get_pseudo_lr of KBPNLoss, sr_loss_functions.py:73-102).  img fp32 [B,C,H,W],
+    kvec fp32 [B,k*k] -> fp32 [B,C,ceil(H/s),ceil(W/s)]; gradients w.r.t. both on the device kernels of csrc/train.cu."""
+
+    @staticmethod
+    def forward(ctx, img, kvec, ksize, stride):
+        from . import kernels as K
+        img, kvec = img.contiguous(), kvec.contiguous()
+        b, c, h, w = img.shape
+        out = torch.empty((b, c, (h - 1) // stride + 1, (w - 1) // stride + 1), dtype=torch.float32, device=img.device)
+        K.blur_per_sample(img, kvec, None, out, ksize, stride)
+        ctx.save_for_backward(img, kvec)
+        ctx.cfg = (ksize, stride)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _lib
+        img, kvec = ctx.saved_tensors
+        ksize, stride = ctx.cfg
+        b, c, h, w = img.shape
+        dy = dy.contiguous().float()
+        dx = dk = None
+        L = _lib.lib()
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(img)
+            _lib.check(L.csbsr_blur_ps_bwd_input(dy.data_ptr(), kvec.data_ptr(), dx.data_ptr(), b, c, h, w, ksize, stride,
+                                                 _lib.stream_ptr()), "csbsr_blur_ps_bwd_input")
+            _lib.count_launch("csbsr_blur_ps_bwd_input")
+        if ctx.needs_input_grad[1]:
+            dk = torch.empty_like(kvec)
+            _lib.check(L.csbsr_blur_ps_bwd_kernel(img.data_ptr(), dy.data_ptr(), dk.data_ptr(), b, c, h, w, ksize, stride,
+                                                  _lib.stream_ptr()), "csbsr_blur_ps_bwd_kernel")
+            _lib.count_launch("csbsr_blur_ps_bwd_kernel")
+        return dx, dk, None, None
+
+
+class _ResizeAAFn(torch.autograd.Function):
+    """FactorResize(factor, 'bicubic') = antialiased bicubic downscale (transforms.py:516-531) with its transpose as backward."""
+
+    @staticmethod
+    def forward(ctx, x, factor):
+        from . import _lib
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        oh, ow = int(h / factor), int(w / factor)
+        out = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().csbsr_resize_bicubic_aa(x.data_ptr(), out.data_ptr(), n * c, h, w, oh, ow, 0, _lib.stream_ptr()),
+                   "csbsr_resize_bicubic_aa")
+        _lib.count_launch("csbsr_resize_bicubic_aa")
+        ctx.shape = (n, c, h, w, oh, ow)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _lib
+        n, c, h, w, oh, ow = ctx.shape
+        dy = dy.contiguous().float()
+        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=dy.device)
+        _lib.check(_lib.lib().csbsr_resize_bicubic_aa_bwd(dy.data_ptr(), dx.data_ptr(), n * c, h, w, oh, ow, _lib.stream_ptr()),
+                   "csbsr_resize_bicubic_aa_bwd")
+        _lib.count_launch("csbsr_resize_bicubic_aa_bwd")
+        return dx, None
+
+
+def blur_per_sample(img, kvec, ksize, stride):
+    return _BlurFn.apply(img, kvec, ksize, stride)
+
+
+def resize_aa(x, factor):
+    return _ResizeAAFn.apply(x, factor)

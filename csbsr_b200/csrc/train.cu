@@ -9,6 +9,8 @@
 
 namespace csbsr {
 
+static int grid_cap(size_t work, int block);
+
 __device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
@@ -26,6 +28,14 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
         w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
     return r;
+}
+
+__device__ __forceinline__ float aa_cubic_t(float x) {       // Keys cubic, a = -0.5 (antialiased bicubic of torchvision Resize)
+    const float a = -0.5f;
+    x = fabsf(x);
+    if (x < 1.f) return ((a + 2.f) * x - (a + 3.f)) * x * x + 1.f;
+    if (x < 2.f) return (((x - 5.f) * x + 8.f) * x - 4.f) * a;
+    return 0.f;
 }
 
 __global__ void prelu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ slope,
@@ -138,6 +148,172 @@ extern "C" int csbsr_adam_step(float* p, float* g, float* m, float* v, long long
     adam_kernel<<<grid_cap(n4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
         n4, static_cast<float>(lr / bc1), beta1, beta2, eps, static_cast<float>(1.0 / sqrt(bc2)), grad_scale, zero_grad);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of the per-sample depthwise blur (csbsr_blur_per_sample; KBlock pseudo-LR, kbpn.py:395-402, and Get_pseudo_lr of
+// KBPNLoss, sr_loss_functions.py:73-102) and of the antialiased bicubic downscale (FactorResize, transforms.py:516-531).
+//   forward   y[b,c,Y,X] = sum_ij k[b,i,j] * x[b,c,Y*s+i-pad, X*s+j-pad]
+//   d input   dx[b,c,y,x] = sum over (Y,X,i,j) with Y*s+i-pad = y, X*s+j-pad = x of k[b,i,j] * dy[b,c,Y,X]
+//   d kernel  dk[b,i,j]   = sum_{c,Y,X} dy[b,c,Y,X] * x[b,c,Y*s+i-pad, X*s+j-pad]
+namespace csbsr {
+
+__global__ void blur_bwd_input_kernel(const float* __restrict__ dy, const float* __restrict__ kvec, float* __restrict__ dx,
+                                      int C, int H, int W, int OH, int OW, int ks, int stride) {
+    extern __shared__ float sk[];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < ks * ks; i += blockDim.x) sk[i] = kvec[static_cast<size_t>(b) * ks * ks + i];
+    __syncthreads();
+    const int pad = (ks - 1) / 2;
+    const size_t per = static_cast<size_t>(C) * H * W;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < per;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(i % W);
+        const int y = static_cast<int>((i / W) % H);
+        const int c = static_cast<int>(i / (static_cast<size_t>(W) * H));
+        // Y*s + ti - pad = y  ->  ti = y + pad - Y*s in [0, ks)
+        const int Y0 = max(0, (y + pad - (ks - 1) + stride - 1) / stride), Y1 = min(OH - 1, (y + pad) / stride);
+        const int X0 = max(0, (x + pad - (ks - 1) + stride - 1) / stride), X1 = min(OW - 1, (x + pad) / stride);
+        const float* dp = dy + (static_cast<size_t>(b) * C + c) * OH * OW;
+        float acc = 0.f;
+        for (int Y = Y0; Y <= Y1; ++Y) {
+            const int ti = y + pad - Y * stride;
+            for (int X = X0; X <= X1; ++X) acc = fmaf(sk[ti * ks + (x + pad - X * stride)], dp[static_cast<size_t>(Y) * OW + X], acc);
+        }
+        dx[static_cast<size_t>(b) * per + i] = acc;
+    }
+}
+
+// one block per (pixel tile of dy, channel, sample); thread t < ks*ks owns tap t and walks the dy tile staged in shared memory
+// next to the x halo tile; partial sums are added atomically (fp32) into dk
+template <int TILE>
+__global__ void blur_bwd_kernel_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk, int C,
+                                       int H, int W, int OH, int OW, int ks, int stride) {
+    extern __shared__ float sm[];
+    const int XT = (TILE - 1) * stride + ks;                 // x halo tile edge
+    float* sdy = sm;                                         // [TILE][TILE]
+    float* sx = sm + TILE * TILE;                            // [XT][XT]
+    const int tiles_w = (OW + TILE - 1) / TILE;
+    const int ty0 = (blockIdx.x / tiles_w) * TILE, tx0 = (blockIdx.x % tiles_w) * TILE;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const int pad = (ks - 1) / 2;
+    const float* xp = x + (static_cast<size_t>(b) * C + c) * H * W;
+    const float* dp = dy + (static_cast<size_t>(b) * C + c) * OH * OW;
+    for (int i = threadIdx.x; i < TILE * TILE; i += blockDim.x) {
+        const int Y = ty0 + i / TILE, X = tx0 + i % TILE;
+        sdy[i] = (Y < OH && X < OW) ? dp[static_cast<size_t>(Y) * OW + X] : 0.f;
+    }
+    const int y0 = ty0 * stride - pad, x0 = tx0 * stride - pad;
+    for (int i = threadIdx.x; i < XT * XT; i += blockDim.x) {
+        const int yy = y0 + i / XT, xx = x0 + i % XT;
+        sx[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? xp[static_cast<size_t>(yy) * W + xx] : 0.f;
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < ks * ks) {
+        const int ti = t / ks, tj = t % ks;
+        float acc = 0.f;
+        for (int Y = 0; Y < TILE; ++Y) {
+            const float* xr = sx + (Y * stride + ti) * XT + tj;
+            const float* dr = sdy + Y * TILE;
+#pragma unroll 8
+            for (int X = 0; X < TILE; ++X) acc = fmaf(dr[X], xr[X * stride], acc);
+        }
+        atomicAdd(dk + static_cast<size_t>(b) * ks * ks + t, acc);
+    }
+}
+
+__global__ void resize_aa_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int NC, int H, int W, int OH, int OW) {
+    const size_t total = static_cast<size_t>(NC) * H * W;
+    const float sh = static_cast<float>(H) / OH, sw = static_cast<float>(W) / OW;
+    const float ish = 1.f / sh, isw = 1.f / sw;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(i % W);
+        const int y = static_cast<int>((i / W) % H);
+        const int nc = static_cast<int>(i / (static_cast<size_t>(W) * H));
+        // candidate outputs whose (antialiased, support 2*scale) window may contain this input pixel
+        float wy[8], wx[8];
+        int oy0 = static_cast<int>(floorf((y - 2.f * sh) * ish - 0.5f)), ox0 = static_cast<int>(floorf((x - 2.f * sw) * isw - 0.5f));
+        for (int k = 0; k < 8; ++k) {
+            wy[k] = wx[k] = 0.f;
+            const int oy = oy0 + k, ox = ox0 + k;
+            if (oy >= 0 && oy < OH) {
+                const float center = sh * (oy + 0.5f), support = 2.f * sh;
+                const int lo = max(static_cast<int>(center - support + 0.5f), 0), hi = min(static_cast<int>(center + support + 0.5f), H);
+                if (y >= lo && y < hi) {
+                    float s = 0.f;
+                    for (int r = lo; r < hi; ++r) s += aa_cubic_t((r - center + 0.5f) * ish);
+                    wy[k] = aa_cubic_t((y - center + 0.5f) * ish) / s;
+                }
+            }
+            if (ox >= 0 && ox < OW) {
+                const float center = sw * (ox + 0.5f), support = 2.f * sw;
+                const int lo = max(static_cast<int>(center - support + 0.5f), 0), hi = min(static_cast<int>(center + support + 0.5f), W);
+                if (x >= lo && x < hi) {
+                    float s = 0.f;
+                    for (int r = lo; r < hi; ++r) s += aa_cubic_t((r - center + 0.5f) * isw);
+                    wx[k] = aa_cubic_t((x - center + 0.5f) * isw) / s;
+                }
+            }
+        }
+        const float* dp = dy + static_cast<size_t>(nc) * OH * OW;
+        float acc = 0.f;
+        for (int a = 0; a < 8; ++a) {
+            if (wy[a] == 0.f) continue;
+            float row = 0.f;
+            for (int k = 0; k < 8; ++k)
+                if (wx[k] != 0.f) row = fmaf(wx[k], dp[static_cast<size_t>(oy0 + a) * OW + ox0 + k], row);
+            acc = fmaf(wy[a], row, acc);
+        }
+        dx[i] = acc;
+    }
+}
+
+}  // namespace csbsr
+
+extern "C" int csbsr_blur_ps_bwd_input(const float* dy, const float* kvec, float* dx, int b, int c, int h, int w, int ksize,
+                                       int stride, void* stream) {
+    CSBSR_REQUIRE(dy && kvec && dx && b > 0 && c > 0 && ksize > 0 && (ksize & 1) && stride >= 1, "blur_ps_bwd_input: bad arguments");
+    const int oh = (h - 1) / stride + 1, ow = (w - 1) / stride + 1;
+    const size_t per = static_cast<size_t>(c) * h * w;
+    dim3 grid(grid_cap(per, 256), b);
+    blur_bwd_input_kernel<<<grid, 256, sizeof(float) * ksize * ksize, reinterpret_cast<cudaStream_t>(stream)>>>(
+        dy, kvec, dx, c, h, w, oh, ow, ksize, stride);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_blur_ps_bwd_kernel(const float* x, const float* dy, float* dk, int b, int c, int h, int w, int ksize,
+                                        int stride, void* stream) {
+    CSBSR_REQUIRE(x && dy && dk && b > 0 && c > 0 && ksize > 0 && (ksize & 1) && ksize * ksize <= 512 && stride >= 1,
+                  "blur_ps_bwd_kernel: bad arguments");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int oh = (h - 1) / stride + 1, ow = (w - 1) / stride + 1;
+    CSBSR_CHECK_CUDA(cudaMemsetAsync(dk, 0, sizeof(float) * static_cast<size_t>(b) * ksize * ksize, st));
+    if (stride == 1) {
+        constexpr int T = 32;
+        const int xt = (T - 1) * stride + ksize;
+        dim3 grid(((oh + T - 1) / T) * ((ow + T - 1) / T), c, b);
+        blur_bwd_kernel_kernel<T><<<grid, 512, sizeof(float) * (T * T + xt * xt), st>>>(x, dy, dk, c, h, w, oh, ow, ksize, stride);
+    } else {
+        constexpr int T = 8;
+        const int xt = (T - 1) * stride + ksize;
+        CSBSR_REQUIRE(sizeof(float) * (T * T + xt * xt) <= 48 * 1024, "blur_ps_bwd_kernel: stride %d too large", stride);
+        dim3 grid(((oh + T - 1) / T) * ((ow + T - 1) / T), c, b);
+        blur_bwd_kernel_kernel<T><<<grid, 512, sizeof(float) * (T * T + xt * xt), st>>>(x, dy, dk, c, h, w, oh, ow, ksize, stride);
+    }
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_resize_bicubic_aa_bwd(const float* dy, float* dx, int nc, int h, int w, int oh, int ow, void* stream) {
+    CSBSR_REQUIRE(dy && dx && nc > 0 && oh > 0 && ow > 0 && oh <= h && ow <= w && h <= 5 * oh && w <= 5 * ow,
+                  "resize_bicubic_aa_bwd: downscale factors up to 5 only");
+    const size_t total = static_cast<size_t>(nc) * h * w;
+    resize_aa_bwd_kernel<<<grid_cap(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, dx, nc, h, w, oh, ow);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -189,11 +189,9 @@ def seg_loss_train(p_main, p_aux, target, alpha, wf_amp=0.0, main_w=1.0, aux_w=0
 def kbpn_loss_train(sr, hr, lr, kvec, k_gt, weights=(0.4, 0.4, 0, 2), ksize=21, factor=4):
     """KBPNLoss.forward (sr_loss_functions.py:39-56, Get_pseudo_lr :73-102) as an autograd graph: gradients reach the SR
     image (through the L1 terms, the per-sample blur and the antialiased bicubic resize) and the kernel vector."""
-    import torch.nn.functional as F
-    from ..modeling.train_graph import blur_per_sample
+    from ..autograd import blur_per_sample, resize_aa
     k = kvec / kvec.sum(dim=1, keepdim=True)
-    plr = F.interpolate(blur_per_sample(sr, k, ksize, 1), size=(sr.shape[2] // factor, sr.shape[3] // factor),
-                        mode="bicubic", antialias=True, align_corners=False)
+    plr = resize_aa(blur_per_sample(sr, k, ksize, 1), factor)          # csbsr blur / antialiased-bicubic kernels, fwd + bwd
     kn = k.view(-1, 1, ksize, ksize)
     loss = weights[0] * (sr - hr).abs().mean((1, 2, 3)) + weights[1] * (plr - lr).abs().mean((1, 2, 3))
     if weights[2] != 0:

@@ -94,11 +94,9 @@ def _kernel_predictor(P, p, sr_t, kvec, k_out):
 
 def blur_per_sample(img, kvec, k_out, stride):
     """Depthwise cross-correlation of every sample with its own kernel (kbpn.py:395-402; sr_loss_functions.py:73-102).
-    img fp32 [B,3,H,W], kvec [B, k*k] -> [B,3,H/stride,W/stride]."""
-    b, c, h, w = img.shape
-    wgt = kvec.view(b, 1, 1, k_out, k_out).expand(b, c, 1, k_out, k_out).reshape(b * c, 1, k_out, k_out)
-    out = F.conv2d(img.reshape(1, b * c, h, w), wgt, stride=stride, padding=(k_out - 1) // 2, groups=b * c)
-    return out.view(b, c, out.shape[2], out.shape[3])
+    img fp32 [B,3,H,W], kvec [B, k*k] -> [B,3,H/stride,W/stride]; forward and both gradients on csbsr kernels."""
+    from ..autograd import blur_per_sample as _blur
+    return _blur(img, kvec, k_out, stride)
 
 
 def _up_block(P, p, x):

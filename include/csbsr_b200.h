@@ -119,6 +119,17 @@ int csbsr_prelu_bwd(const void* x, const void* dy, void* dx, const float* slope,
 int csbsr_adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                     int step, float grad_scale, int zero_grad, void* stream);
 
+/* Backward of csbsr_blur_per_sample (stride s, zero padding (k-1)/2; KBlock pseudo-LR kbpn.py:395-402, Get_pseudo_lr
+ * sr_loss_functions.py:73-102) and of csbsr_resize_bicubic_aa (FactorResize, transforms.py:516-531); fp32 planar tensors.
+ *   csbsr_blur_ps_bwd_input : dx[b,c,h,w]  from dy[b,c,ceil(h/s),ceil(w/s)] and the per-sample kernels kvec[b,k*k]
+ *   csbsr_blur_ps_bwd_kernel: dk[b,k*k] (overwritten) = sum_{c,Y,X} dy[b,c,Y,X] * x[b,c,Y*s+i-pad,X*s+j-pad]
+ *   csbsr_resize_bicubic_aa_bwd: dx[nc,h,w] from dy[nc,oh,ow] (transpose of the normalised antialiased taps) */
+int csbsr_blur_ps_bwd_input(const float* dy, const float* kvec, float* dx, int b, int c, int h, int w, int ksize, int stride,
+                            void* stream);
+int csbsr_blur_ps_bwd_kernel(const float* x, const float* dy, float* dk, int b, int c, int h, int w, int ksize, int stride,
+                             void* stream);
+int csbsr_resize_bicubic_aa_bwd(const float* dy, float* dx, int nc, int h, int w, int oh, int ow, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound support kernels (csrc/support.cu).  NHWC tensors are bf16 with `*_pitch` channels per
  * pixel and a channel window starting at `*_coff`; planar tensors are fp32 NCHW.

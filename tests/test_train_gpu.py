@@ -273,3 +273,40 @@ def test_fused_adam_vs_torch_adam():
         for p, r in zip(ps, ref):
             assert (p.grad == 0).all()
             assert torch.allclose(p.detach(), r.detach(), rtol=2e-6, atol=1e-9), (step, (p - r).abs().max().item())
+
+
+@pytest.mark.parametrize("stride", [1, 4])
+def test_blur_fn_vs_torch_autograd(stride):
+    """Per-sample blur forward / d input / d kernel against grouped F.conv2d autograd."""
+    from csbsr_b200 import autograd as A
+    g = torch.Generator().manual_seed(31)
+    B, H, W, k = 3, 40, 52, 21
+    x0 = torch.rand(B, 3, H, W, generator=g).cuda()
+    k0 = torch.rand(B, k * k, generator=g).cuda()
+    k0 = k0 / k0.sum(1, keepdim=True)
+    up = torch.randn(B, 3, (H - 1) // stride + 1, (W - 1) // stride + 1, generator=g).cuda()
+    x, kv = x0.clone().requires_grad_(True), k0.clone().requires_grad_(True)
+    y = A.blur_per_sample(x, kv, k, stride)
+    y.backward(up)
+    xr, kr = x0.clone().requires_grad_(True), k0.clone().requires_grad_(True)
+    wgt = kr.view(B, 1, 1, k, k).expand(B, 3, 1, k, k).reshape(B * 3, 1, k, k)
+    yr = F.conv2d(xr.reshape(1, B * 3, H, W), wgt, stride=stride, padding=10, groups=B * 3).view(B, 3, *up.shape[2:])
+    yr.backward(up)
+    assert (y - yr).abs().max().item() <= 2e-6
+    assert (x.grad - xr.grad).abs().max().item() <= 1e-5 * max(1.0, xr.grad.abs().max().item())
+    assert (kv.grad - kr.grad).abs().max().item() <= 2e-4 * kr.grad.abs().max().item()
+
+
+def test_resize_aa_fn_vs_torch_autograd():
+    from csbsr_b200 import autograd as A
+    g = torch.Generator().manual_seed(32)
+    x0 = torch.rand(2, 3, 48, 64, generator=g).cuda()
+    up = torch.randn(2, 3, 12, 16, generator=g).cuda()
+    x = x0.clone().requires_grad_(True)
+    y = A.resize_aa(x, 4)
+    y.backward(up)
+    xr = x0.clone().requires_grad_(True)
+    yr = F.interpolate(xr, size=(12, 16), mode="bicubic", antialias=True, align_corners=False)
+    yr.backward(up)
+    assert (y - yr).abs().max().item() <= 2e-6
+    assert (x.grad - xr.grad).abs().max().item() <= 2e-6
