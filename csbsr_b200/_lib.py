@@ -77,6 +77,7 @@ _SIGNATURES = {
     "csbsr_blur_ps_bwd_input": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]),
     "csbsr_blur_ps_bwd_kernel": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]),
     "csbsr_resize_bicubic_aa_bwd": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 5 + [C.c_void_p]),
+    "csbsr_pack_weights": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]),
     "csbsr_prelu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "csbsr_prelu_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
     "csbsr_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong] + [C.c_float] * 4 + [C.c_int, C.c_float, C.c_int,

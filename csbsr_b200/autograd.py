@@ -48,7 +48,7 @@ class _Conv2dFn(torch.autograd.Function):
         n, h, w, cp = x.shape
         assert cp == cpad(ci), "input has %d channels, expected %d (padded %d)" % (cp, ci, cpad(ci))
         oh, ow = _out_size(h, R, stride, padding, dilation), _out_size(w, S, stride, padding, dilation)
-        pc = K.pack_conv(weight, bias, stride=stride, padding=padding, dilation=dilation, cin_pad=cp, cout_pad=cpad(co))
+        pc = K.pack_conv_train(weight, bias, stride=stride, padding=padding, dilation=dilation, cin_pad=cp, cout_pad=cpad(co))
         y = Fmap.empty(n, oh, ow, cpad(co), device=x.device)
         K.conv(Fmap(x), pc, y)
         ctx.save_for_backward(x, weight)
@@ -65,7 +65,7 @@ class _Conv2dFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             if R == 8 and stride == 4 and padding == 2 and dilation == 1 and h == 4 * dy.shape[1] and w == 4 * dy.shape[2]:
-                pc = K.pack_deconv8s4(weight, cin_pad=dy.shape[3], cout_pad=cp)        # conv 8/4/2 <-> convT 8/4/2
+                pc = K.pack_deconv8s4_train(weight, cin_pad=dy.shape[3], cout_pad=cp)  # conv 8/4/2 <-> convT 8/4/2
                 g = Fmap.empty(n, h, w, cp, device=x.device)
                 K.conv(Fmap(dy), pc, g)
             else:
@@ -74,9 +74,8 @@ class _Conv2dFn(torch.autograd.Function):
                     hs, ws = h + 2 * padding - dilation * (R - 1), w + 2 * padding - dilation * (S - 1)
                     src = torch.zeros((n, hs, ws, dy.shape[3]), dtype=dy.dtype, device=dy.device)
                     src[:, ::stride, ::stride][:, :dy.shape[1], :dy.shape[2]] = dy
-                wt = weight.detach().flip(2, 3).transpose(0, 1)
-                pc = K.pack_conv(wt, None, stride=1, padding=dilation * (R - 1) - padding, dilation=dilation,
-                                 cin_pad=dy.shape[3], cout_pad=cp)
+                pc = K.pack_conv_train(weight, None, stride=1, padding=dilation * (R - 1) - padding, dilation=dilation,
+                                       cin_pad=dy.shape[3], cout_pad=cp, transpose_flip=True)
                 g = Fmap.empty(n, h, w, cp, device=x.device)
                 K.conv(Fmap(src), pc, g)
             dx = g.t
@@ -99,7 +98,7 @@ class _Deconv8s4Fn(torch.autograd.Function):
         assert R == 8 and S == 8
         n, h, w, cp = x.shape
         assert cp == cpad(ci)
-        pc = K.pack_deconv8s4(weight, bias, cin_pad=cp, cout_pad=cpad(co))
+        pc = K.pack_deconv8s4_train(weight, bias, cin_pad=cp, cout_pad=cpad(co))
         y = Fmap.empty(n, 4 * h, 4 * w, cpad(co), device=x.device)
         K.conv(Fmap(x), pc, y)
         ctx.save_for_backward(x, weight)
@@ -114,7 +113,7 @@ class _Deconv8s4Fn(torch.autograd.Function):
         dy = dy.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            pc = K.pack_conv(weight, None, stride=4, padding=2, cin_pad=dy.shape[3], cout_pad=cp)
+            pc = K.pack_conv_train(weight, None, stride=4, padding=2, cin_pad=dy.shape[3], cout_pad=cp)
             g = Fmap.empty(n, h, w, cp, device=x.device)
             K.conv(Fmap(dy), pc, g)
             dx = g.t

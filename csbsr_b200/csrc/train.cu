@@ -317,3 +317,38 @@ extern "C" int csbsr_resize_bicubic_aa_bwd(const float* dy, float* dx, int nc, i
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 parameter [A][B][R][S] -> packed bf16 GEMM operand [R*S][rows_pad][cols_pad] in one launch (the training step re-packs
+// every weight twice per iteration: forward and dgrad layouts).  mode 0: rows = A, cols = B (nn.Conv2d forward; deconv dgrad);
+// mode 1: rows = B, cols = A, taps flipped (stride-1 conv dgrad); mode 2: rows = B, cols = A (ConvTranspose2d forward phases;
+// dgrad of the 8x8/s4 conv).  Padding rows / columns are written as zeros.
+namespace csbsr {
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int A, int B, int R, int S,
+                                    int rows_pad, int cols_pad, int mode) {
+    const size_t total = static_cast<size_t>(R) * S * rows_pad * cols_pad;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int col = static_cast<int>(i % cols_pad);
+        const int row = static_cast<int>((i / cols_pad) % rows_pad);
+        const int t = static_cast<int>(i / (static_cast<size_t>(cols_pad) * rows_pad));
+        int r = t / S, s = t % S;
+        const int a = mode == 0 ? row : col, b = mode == 0 ? col : row;
+        if (mode == 1) { r = R - 1 - r; s = S - 1 - s; }
+        float v = 0.f;
+        if (a < A && b < B) v = w[((static_cast<size_t>(a) * B + b) * R + r) * S + s];
+        out[i] = __float2bfloat16(v);
+    }
+}
+}  // namespace csbsr
+
+extern "C" int csbsr_pack_weights(const float* w, void* out, int a, int b, int r, int s, int rows_pad, int cols_pad, int mode,
+                                  void* stream) {
+    CSBSR_REQUIRE(w && out && a > 0 && b > 0 && r > 0 && s > 0 && mode >= 0 && mode <= 2, "pack_weights: bad arguments");
+    CSBSR_REQUIRE(rows_pad >= (mode == 0 ? a : b) && cols_pad >= (mode == 0 ? b : a), "pack_weights: padded extents too small");
+    const size_t total = static_cast<size_t>(r) * s * rows_pad * cols_pad;
+    pack_weights_kernel<<<grid_cap(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        w, reinterpret_cast<__nv_bfloat16*>(out), a, b, r, s, rows_pad, cols_pad, mode);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -260,6 +260,58 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
     return y
 
 
+def _pack_device(weight, rows_pad, cols_pad, mode):
+    """One-launch packing of a contiguous fp32 CUDA parameter (csbsr_pack_weights)."""
+    a, b, R, S = weight.shape
+    out = torch.empty((R * S, rows_pad, cols_pad), dtype=torch.bfloat16, device=weight.device)
+    _call("csbsr_pack_weights", weight.data_ptr(), out.data_ptr(), a, b, R, S, rows_pad, cols_pad, mode)
+    return out
+
+
+def pack_conv_train(weight, bias=None, stride=1, padding=0, dilation=1, cin_pad=None, cout_pad=None, transpose_flip=False):
+    """pack_conv for the training step: the fp32 parameter is packed by one kernel.  transpose_flip=True gives the operand of
+    the stride-1 dgrad conv (roles of cin / cout swapped, taps flipped, padding = dilation*(k-1) - padding given by the caller)."""
+    w = weight.detach()
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+    a, b, R, S = w.shape
+    cout, cin = (b, a) if transpose_flip else (a, b)
+    cout_pad = cout_pad or round_up(cout, 16)
+    cin_pad = cin_pad or round_up(cin, 64)
+    wp = _pack_device(w, cout_pad, cin_pad, 1 if transpose_flip else 0)
+    taps = [(r * dilation - padding, s * dilation - padding, r * S + s) for r in range(R) for s in range(S)]
+    return PackedConv(wp, taps, 1, R * S, stride, 1, [0], [0], cout, _pad_bias(bias, cout_pad, w.device),
+                      macs_per_pixel=R * S * cin * cout)
+
+
+def pack_deconv8s4_train(weight, bias=None, cin_pad=None, cout_pad=None):
+    """pack_deconv8s4 with the one-kernel packing (weight [Cin, Cout, 8, 8] of the transposed conv being evaluated)."""
+    w = weight.detach()
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.shape[2:] == (8, 8)
+    cin, cout = w.shape[:2]
+    cout_pad = cout_pad or round_up(cout, 16)
+    cin_pad = cin_pad or round_up(cin, 64)
+    wp = _pack_device(w, cout_pad, cin_pad, 2)
+    taps, ooh, oow = _DECONV_TAPS
+    return PackedConv(wp, taps, 16, 4, 1, 4, ooh, oow, cout, _pad_bias(bias, cout_pad, w.device), macs_per_pixel=4 * cin * cout)
+
+
+def _deconv_taps():
+    def axis_taps(rho):
+        return [(-1, rho + 6), (0, rho + 2)] if rho < 2 else [(0, rho + 2), (1, rho - 2)]
+    taps, ooh, oow = [], [], []
+    for rh in range(4):
+        for rw in range(4):
+            for dh, r in axis_taps(rh):
+                for dw, s in axis_taps(rw):
+                    taps.append((dh, dw, r * 8 + s))
+            ooh.append(rh)
+            oow.append(rw)
+    return taps, ooh, oow
+
+
+_DECONV_TAPS = _deconv_taps()
+
+
 def pack_tapexp3x3(weight, cout_pad=None):
     """[co, ci, 3, 3] conv weight (padding 1) -> 1x1 PackedConv with 9*cp outputs (cp = co rounded up to 4 so one tap is
     a whole number of 8-byte words), channel t*cp + c = tap t of output c."""

@@ -130,6 +130,12 @@ int csbsr_blur_ps_bwd_kernel(const float* x, const float* dy, float* dk, int b, 
                              void* stream);
 int csbsr_resize_bicubic_aa_bwd(const float* dy, float* dx, int nc, int h, int w, int oh, int ow, void* stream);
 
+/* fp32 parameter [A][B][R][S] -> packed bf16 conv operand [R*S][rows_pad][cols_pad] (zero padding) in one launch.
+ * mode 0: rows = A, cols = B (nn.Conv2d weight for the forward conv; ConvTranspose2d weight for its dgrad);
+ * mode 1: rows = B, cols = A with the taps flipped (dgrad of a stride-1 conv);
+ * mode 2: rows = B, cols = A (ConvTranspose2d forward phases; dgrad of the 8x8/s4 conv). */
+int csbsr_pack_weights(const float* w, void* out, int a, int b, int r, int s, int rows_pad, int cols_pad, int mode, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound support kernels (csrc/support.cu).  NHWC tensors are bf16 with `*_pitch` channels per
  * pixel and a channel window starting at `*_coff`; planar tensors are fp32 NCHW.
