@@ -29,15 +29,19 @@ struct WgradParams {
     int N, OH, OW, TH, TW, tiles_h, tiles_w, ptiles;
     int stride, ntaps, ncs, cs_pad, units_total, upp, passes_per_m, npass, nsplit, tiles_per_split, nitems;
     int stages, stage_bytes;
+    // tap groups: G taps that share dw and whose dh are dh0 + j*rs*stride are served by ONE S box of TH + (G-1)*rs rows per
+    // 64-channel chunk (the descriptor start moves by whole swizzle atoms); a unit = (group, 128-channel chunk of S)
+    int G, ngroups, rs, b_box_bytes;
     float* wg;
     int* err_flag;
-    int8_t dh[CSBSR_MAX_TAPS], dw[CSBSR_MAX_TAPS];
+    int8_t dh[CSBSR_MAX_TAPS], dw[CSBSR_MAX_TAPS];      // per group: offsets of its first tap
+    int8_t tap[CSBSR_MAX_TAPS];                          // [group*G + j] -> tap index in the caller's order
 };
 
 // MN-major, 128B-swizzled operand: 8 pixel rows of 128 B form one swizzle atom (SBO = 1024 B between K groups of 8 pixels),
 // the next 64 channels live one TMA box further (LBO = 8 KB).
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
-    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((static_cast<uint32_t>(kWgBox) >> 4) << 16);
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes = kWgBox) {
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     return (static_cast<uint64_t>(hi) << 32) | lo;
 }
@@ -92,7 +96,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                     uint32_t bytes = 2 * kWgBox;
                     for (int u = u0; u < u1; ++u) {
                         const int csc = u % p.ncs;
-                        bytes += (min(128, p.cs_pad - csc * 128) / 64) * kWgBox;
+                        bytes += (min(128, p.cs_pad - csc * 128) / 64) * p.b_box_bytes;
                     }
                     mbar_arrive_expect_tx(&full_bar[stage], bytes);
                     uint32_t dst = smem_base + stage * p.stage_bytes;
@@ -100,12 +104,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                     tma_load_4d(dst + kWgBox, &tmG, &full_bar[stage], mt * 128 + 64, ox0, oy0, img);
                     dst += 2 * kWgBox;
                     for (int u = u0; u < u1; ++u) {
-                        const int tap = u / p.ncs, csc = u - tap * p.ncs;
+                        const int grp = u / p.ncs, csc = u - grp * p.ncs;
                         const int nb = min(128, p.cs_pad - csc * 128) / 64;
-                        const int sx = ox0 * p.stride + p.dw[tap], sy = oy0 * p.stride + p.dh[tap];
+                        const int sx = ox0 * p.stride + p.dw[grp], sy = oy0 * p.stride + p.dh[grp];
                         for (int h = 0; h < nb; ++h)
-                            tma_load_4d(dst + h * kWgBox, &tmS, &full_bar[stage], csc * 128 + h * 64, sx, sy, img);
-                        dst += 2 * kWgBox;
+                            tma_load_4d(dst + h * p.b_box_bytes, &tmS, &full_bar[stage], csc * 128 + h * 64, sx, sy, img);
+                        dst += 2 * p.b_box_bytes;
                     }
                 }
                 __syncwarp();
@@ -134,12 +138,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                         const int nw = min(128, p.cs_pad - csc * 128);
                         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                                (static_cast<uint32_t>(nw >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
-                        const uint32_t b_addr = a_addr + 2 * kWgBox * (1 + (u - u0));
-                        const uint32_t d_addr = tmem_base + static_cast<uint32_t>((u - u0) * 128);
+                        const uint32_t b_unit = a_addr + 2 * kWgBox + 2 * p.b_box_bytes * (u - u0);
+                        for (int j = 0; j < p.G; ++j) {
+                            const uint32_t b_addr = b_unit + static_cast<uint32_t>(j * p.rs * p.TW * 128);   // vertical tap shift
+                            const uint32_t d_addr = tmem_base + static_cast<uint32_t>(((u - u0) * p.G + j) * 128);
 #pragma unroll
-                        for (int k = 0; k < kWgK / 16; ++k)
-                            umma_bf16(d_addr, make_desc_mn(a_addr + k * 2048), make_desc_mn(b_addr + k * 2048), idesc,
-                                      (t > t0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < kWgK / 16; ++k)
+                                umma_bf16(d_addr, make_desc_mn(a_addr + k * 2048),
+                                          make_desc_mn(b_addr + k * 2048, static_cast<uint32_t>(p.b_box_bytes)), idesc,
+                                          (t > t0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);
                     if (t == t1 - 1) umma_commit(tmem_full);
@@ -163,17 +171,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             const int row = mt * 128 + q * 32 + lane;
             float* wrow = p.wg + static_cast<size_t>(row) * p.ntaps * p.cs_pad;
             for (int u = u0; u < u1; ++u) {
-                const int tap = u / p.ncs, csc = u - tap * p.ncs;
+                const int grp = u / p.ncs, csc = u - grp * p.ncs;
                 const int nw = min(128, p.cs_pad - csc * 128);
-                float* dst = wrow + static_cast<size_t>(tap) * p.cs_pad + csc * 128;
-                for (int c = 0; c < nw; c += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((u - u0) * 128 + c), v);
-                    tmem_ld_wait();
+                for (int jt = 0; jt < p.G; ++jt) {
+                    float* dst = wrow + static_cast<size_t>(p.tap[grp * p.G + jt]) * p.cs_pad + csc * 128;
+                    const uint32_t col0 = static_cast<uint32_t>(((u - u0) * p.G + jt) * 128);
+                    for (int c = 0; c < nw; c += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col0 + static_cast<uint32_t>(c), v);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        red_add_v4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                   __uint_as_float(v[j + 3]));
+                        for (int j = 0; j < 16; j += 4)
+                            red_add_v4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                       __uint_as_float(v[j + 3]));
+                    }
                 }
             }
             tcgen05_fence_before();
@@ -232,10 +243,55 @@ extern "C" int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream_) {
     p.stride = d->stride; p.ntaps = d->ntaps;
     p.cs_pad = d->cs;
     p.ncs = (d->cs + 127) / 128;
-    p.units_total = p.ntaps * p.ncs;
+    // ---- tap groups (same rule as the forward kernel): taps with equal dw and equal dh modulo the stride, dh in uniform steps
+    int G = 1, ngroups = d->ntaps, rs = 0;
+    int8_t g_dh[CSBSR_MAX_TAPS], g_dw[CSBSR_MAX_TAPS], g_tap[CSBSR_MAX_TAPS];
+    for (int t = 0; t < d->ntaps; ++t) { g_dh[t] = d->dh[t]; g_dw[t] = d->dw[t]; g_tap[t] = static_cast<int8_t>(t); }
+    if (d->ntaps >= 2 && !getenv("CSBSR_NO_GROUPING")) {
+        const int st = d->stride;
+        auto key_of = [&](int t) { return d->dw[t] * 64 + (((d->dh[t] % st) + st) % st); };
+        int keys[CSBSR_MAX_TAPS], nk = 0;
+        for (int t = 0; t < d->ntaps; ++t) {
+            bool seen = false;
+            for (int i = 0; i < nk; ++i) seen |= (keys[i] == key_of(t));
+            if (!seen) keys[nk++] = key_of(t);
+        }
+        bool ok = d->ntaps % nk == 0 && d->ntaps / nk >= 2 && d->ntaps / nk <= 4;
+        const int gsz = ok ? d->ntaps / nk : 1;
+        int step = 0;
+        int8_t n_dh[CSBSR_MAX_TAPS], n_dw[CSBSR_MAX_TAPS], n_tap[CSBSR_MAX_TAPS];
+        for (int gi = 0; gi < nk && ok; ++gi) {
+            int idx[CSBSR_MAX_TAPS], cnt = 0;
+            for (int t = 0; t < d->ntaps; ++t)
+                if (key_of(t) == keys[gi]) idx[cnt++] = t;
+            if (cnt != gsz) { ok = false; break; }
+            for (int a = 0; a < cnt; ++a)
+                for (int b2 = a + 1; b2 < cnt; ++b2)
+                    if (d->dh[idx[b2]] < d->dh[idx[a]]) { const int tmp = idx[a]; idx[a] = idx[b2]; idx[b2] = tmp; }
+            for (int j = 0; j < cnt; ++j) {
+                if (j > 0) {
+                    const int sd = d->dh[idx[j]] - d->dh[idx[j - 1]];
+                    if (sd <= 0 || sd % st != 0 || (step != 0 && sd != step)) ok = false;
+                    step = sd;
+                }
+                n_tap[gi * gsz + j] = static_cast<int8_t>(idx[j]);
+            }
+            n_dh[gi] = d->dh[idx[0]];
+            n_dw[gi] = d->dw[idx[0]];
+        }
+        const int rows = p.TH + (gsz - 1) * (step / (st > 0 ? st : 1));
+        if (ok && rows * st <= 256 && 2 * (2 * kWgBox + 2 * rows * p.TW * 128) <= kWgSmem - 2048) {
+            G = gsz; ngroups = nk; rs = step / st;
+            memcpy(g_dh, n_dh, sizeof(g_dh)); memcpy(g_dw, n_dw, sizeof(g_dw)); memcpy(g_tap, n_tap, sizeof(g_tap));
+        }
+    }
+    p.G = G; p.ngroups = ngroups; p.rs = rs;
+    p.b_box_bytes = (p.TH + (G - 1) * rs) * p.TW * 128;
+    p.units_total = ngroups * p.ncs;
     const int m_tiles = (d->cg + 127) / 128;
-    // units per pass: at most 4 (TMEM columns); spread the units evenly over the passes
-    const int min_passes = (p.units_total + kWgMaxUnits - 1) / kWgMaxUnits;
+    // units per pass: every tap of a unit owns 128 TMEM columns; spread the units evenly over the passes
+    const int max_units = kWgMaxUnits / G > 0 ? kWgMaxUnits / G : 1;
+    const int min_passes = (p.units_total + max_units - 1) / max_units;
     p.upp = (p.units_total + min_passes - 1) / min_passes;
     p.passes_per_m = (p.units_total + p.upp - 1) / p.upp;
     p.npass = m_tiles * p.passes_per_m;
@@ -246,13 +302,14 @@ extern "C" int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream_) {
     p.tiles_per_split = (p.ptiles + nsplit - 1) / nsplit;
     p.nsplit = (p.ptiles + p.tiles_per_split - 1) / p.tiles_per_split;
     p.nitems = p.npass * p.nsplit;
-    p.stage_bytes = 2 * kWgBox * (1 + p.upp);
+    p.stage_bytes = 2 * kWgBox + 2 * p.b_box_bytes * p.upp;
     p.stages = (kWgSmem - 2048) / p.stage_bytes;
     if (p.stages > 8) p.stages = 8;
     CSBSR_REQUIRE(p.stages >= 2, "conv_wgrad: not enough shared memory for 2 stages");
     p.wg = d->wg;
-    memcpy(p.dh, d->dh, sizeof(p.dh));
-    memcpy(p.dw, d->dw, sizeof(p.dw));
+    memcpy(p.dh, g_dh, sizeof(p.dh));
+    memcpy(p.dw, g_dw, sizeof(p.dw));
+    memcpy(p.tap, g_tap, sizeof(p.tap));
     if (!g_wg_err) {
         CSBSR_CHECK_CUDA(cudaMalloc(&g_wg_err, sizeof(int)));
         CSBSR_CHECK_CUDA(cudaMemset(g_wg_err, 0, sizeof(int)));
@@ -278,7 +335,7 @@ extern "C" int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream_) {
         cuuint64_t dims[4] = {(cuuint64_t)d->cs, (cuuint64_t)d->sw, (cuuint64_t)d->sh, (cuuint64_t)d->n};
         const cuuint64_t pb = (cuuint64_t)d->s_pitch * 2;
         cuuint64_t strides[3] = {pb, pb * d->sw, pb * d->sw * d->sh};
-        cuuint32_t box[4] = {64, (cuuint32_t)(p.TW * d->stride), (cuuint32_t)(p.TH * d->stride), 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)(p.TW * d->stride), (cuuint32_t)((p.TH + (G - 1) * rs) * d->stride), 1};
         cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
         CUresult r = encode(&tmS, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
