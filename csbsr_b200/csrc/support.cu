@@ -192,13 +192,21 @@ __global__ void broadcast_vec_kernel(const float* __restrict__ v, __nv_bfloat16*
 // err[n,c,oh,ow] = sum_{r,s} x[n,c,oh*st+r-pad, ow*st+s-pad] * k[n,r,s] - lr[n,c,oh,ow]   (kbpn.py:395-405)
 // block = one (n, c, tile of 8x32 outputs); the input patch and the kernel are staged in shared memory.
 template <int KS, int ST>
-__global__ void blur_ps_kernel(const float* __restrict__ x, const float* __restrict__ kvec,
-                               const float* __restrict__ lr, float* __restrict__ err, int C, int H, int W, int OH,
-                               int OW) {
-    constexpr int TOH = 8, TOW = 32;
-    constexpr int PH = (TOH - 1) * ST + KS, PW = (TOW - 1) * ST + KS;
-    __shared__ float sk[KS * KS];
-    __shared__ float sp[PH][PW + 1];
+__global__ void __launch_bounds__(256)
+blur_ps_kernel(const float* __restrict__ x, const float* __restrict__ kvec, const float* __restrict__ lr,
+               float* __restrict__ err, int C, int H, int W, int OH, int OW) {
+    // register-tiled: every thread produces OPT horizontally adjacent outputs; per kernel row it loads the (OPT-1)*ST + KS
+    // input values it needs with 128-bit shared-memory loads and reuses each kernel tap for OPT FMAs (the one-output-per-
+    // thread form issued two shared loads per FMA and ran at 10 % of the fp32 peak)
+    constexpr int OPT = ST == 1 ? 8 : 4;                     // outputs per thread
+    constexpr int TXN = 16, TYN = 16;                        // thread grid -> tile of TYN x (TXN*OPT) outputs
+    constexpr int TOH = TYN, TOW = TXN * OPT;
+    constexpr int NIN = ((OPT - 1) * ST + KS + 3) / 4 * 4;   // input values per thread and row, padded to float4
+    constexpr int PH = (TOH - 1) * ST + KS;
+    constexpr int PW = ((TOW - 1) * ST + KS + 3 + 4) / 4 * 4;   // row pitch: multiple of 4 floats, covers the padded reads
+    extern __shared__ __align__(16) float blur_sm[];
+    float* sk = blur_sm;                                     // [KS*KS] (+ pad)
+    float* sp = blur_sm + (KS * KS + 3) / 4 * 4;             // [PH][PW]
     const int nc = blockIdx.z;
     const int n = nc / C;
     const int oh0 = blockIdx.y * TOH, ow0 = blockIdx.x * TOW;
@@ -209,19 +217,39 @@ __global__ void blur_ps_kernel(const float* __restrict__ x, const float* __restr
     for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
         const int r = i / PW, c = i % PW;
         const int ih = ih0 + r, iw = iw0 + c;
-        sp[r][c] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? xp[static_cast<size_t>(ih) * W + iw] : 0.f;
+        sp[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? xp[static_cast<size_t>(ih) * W + iw] : 0.f;
     }
     __syncthreads();
-    const int tx = threadIdx.x % TOW, ty = threadIdx.x / TOW;
-    const int oh = oh0 + ty, ow = ow0 + tx;
-    if (oh < OH && ow < OW) {
-        float acc = 0.f;
-#pragma unroll 3
-        for (int r = 0; r < KS; ++r)
+    const int tx = threadIdx.x % TXN, ty = threadIdx.x / TXN;
+    float acc[OPT];
 #pragma unroll
-            for (int s = 0; s < KS; ++s) acc += sp[ty * ST + r][tx * ST + s] * sk[r * KS + s];
-        const size_t o = (static_cast<size_t>(nc) * OH + oh) * OW + ow;
-        err[o] = lr ? acc - lr[o] : acc;
+    for (int o = 0; o < OPT; ++o) acc[o] = 0.f;
+    const float* prow = sp + (ty * ST) * PW + tx * OPT * ST;          // 16-byte aligned: OPT*ST is a multiple of 4
+#pragma unroll 1
+    for (int r = 0; r < KS; ++r) {
+        float in[NIN];
+#pragma unroll
+        for (int v = 0; v < NIN / 4; ++v) {
+            const float4 q = *reinterpret_cast<const float4*>(prow + r * PW + 4 * v);
+            in[4 * v] = q.x; in[4 * v + 1] = q.y; in[4 * v + 2] = q.z; in[4 * v + 3] = q.w;
+        }
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const float kv = sk[r * KS + s];
+#pragma unroll
+            for (int o = 0; o < OPT; ++o) acc[o] = fmaf(in[o * ST + s], kv, acc[o]);
+        }
+    }
+    const int oh = oh0 + ty;
+    if (oh < OH) {
+#pragma unroll
+        for (int o = 0; o < OPT; ++o) {
+            const int ow = ow0 + tx * OPT + o;
+            if (ow < OW) {
+                const size_t oidx = (static_cast<size_t>(nc) * OH + oh) * OW + ow;
+                err[oidx] = lr ? acc[o] - lr[oidx] : acc[o];
+            }
+        }
     }
 }
 
@@ -585,11 +613,25 @@ extern "C" int csbsr_blur_per_sample(const float* x, const float* kvec, const fl
     CSBSR_REQUIRE(ksize == 21 && (stride == 4 || stride == 1), "blur_per_sample: only ksize=21, stride in {1,4}");
     const int pad = (ksize - 1) / 2;
     const int oh = (h + 2 * pad - ksize) / stride + 1, ow = (w + 2 * pad - ksize) / stride + 1;
-    dim3 grid((ow + 31) / 32, (oh + 7) / 8, n * c);
-    if (stride == 4)
-        blur_ps_kernel<21, 4><<<grid, 256, 0, STREAM(stream)>>>(x, kvec, lr, err, c, h, w, oh, ow);
-    else
-        blur_ps_kernel<21, 1><<<grid, 256, 0, STREAM(stream)>>>(x, kvec, lr, err, c, h, w, oh, ow);
+    // tile = 16 x (16 * outputs-per-thread) outputs; dynamic shared memory = kernel + input patch (see blur_ps_kernel)
+    auto smem_of = [](int st, int opt) {
+        const int tow = 16 * opt, ph = 15 * st + 21, pw = ((tow - 1) * st + 21 + 3 + 4) / 4 * 4;
+        return static_cast<int>(sizeof(float)) * ((21 * 21 + 3) / 4 * 4 + ph * pw);
+    };
+    if (stride == 4) {
+        const int smem = smem_of(4, 4);
+        static bool attr4 = false;
+        if (!attr4) {
+            CSBSR_CHECK_CUDA(cudaFuncSetAttribute(blur_ps_kernel<21, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr4 = true;
+        }
+        dim3 grid((ow + 63) / 64, (oh + 15) / 16, n * c);
+        blur_ps_kernel<21, 4><<<grid, 256, smem, STREAM(stream)>>>(x, kvec, lr, err, c, h, w, oh, ow);
+    } else {
+        const int smem = smem_of(1, 8);
+        dim3 grid((ow + 127) / 128, (oh + 15) / 16, n * c);
+        blur_ps_kernel<21, 1><<<grid, 256, smem, STREAM(stream)>>>(x, kvec, lr, err, c, h, w, oh, ow);
+    }
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
