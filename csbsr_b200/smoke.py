@@ -43,5 +43,35 @@ def run():
     hd, msd = metrics_ref.distance_metrics(seg.cpu().numpy(), mask.numpy(), 50)
     assert np.array_equal(r["inter"], inter) and np.array_equal(r["union"], union), "AIU counts mismatch"
     assert np.array_equal(r["hd"], hd) and np.array_equal(r["msd"], msd), "HD/MSD mismatch"
-    print("smoke ok: sr max-abs %.4f, seg max-abs %.4f, AIU %.4f, AHD(p50) %.3f, %d kernel launches"
-          % (e_sr, e_seg, float(np.mean(r["iou"])), float(np.mean(r["hd"])), _lib.LAUNCHES))
+    n_eval = _lib.LAUNCHES
+
+    # ---- one tiny joint training step (forward, loss, backward through the conv dgrad / wgrad kernels, fused Adam),
+    # loss checked against the fp32 oracle's (BatchNorm on running statistics and Dropout2d off so both are deterministic)
+    from csbsr_b200.engine.losses import calc_loss
+    from csbsr_b200.engine.optim import FusedAdam
+    from csbsr_b200.modeling.build_model import JointModelWithLoss
+    from oracle import train_ref
+    tc = c.clone()
+    tc.SOLVER.SEG_FAIL_ORIENTED_WEIGHT4SS_AMP = 1.0
+    tm = JointModelWithLoss(tc, num_train_ds=100, resume_iter=40000)
+    tm.load_state_dict(sd, strict=True)
+    tm.cuda().train()
+    tm.dropout, tm.freeze_bn = False, True
+    opt = FusedAdam(tm.parameters(), lr=tc.SOLVER.LR)
+    hr_t, mask_t = synth.batch(4, 2, 64)
+    lr_t, kern_t = G.degrade(hr_t, synth.degradation_params(2, seed=9))
+    seg_loss, sr_loss, *_ = tm(40001, lr_t, sr_targets=hr_t, segment_targets=mask_t, kernel_targets=kern_t.unsqueeze(1))
+    loss = calc_loss(sr_loss, seg_loss.mean(), tc.SOLVER.TASK_LOSS_WEIGHT, 40001, tc)
+    loss.backward()
+    gnorm = opt.flat_g.norm().item()
+    opt.step()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref_loss = train_ref.train_forward(sdc, lr_t.cuda(), hr_t.cuda(), mask_t.cuda(), kern_t.unsqueeze(1), tm.ss_loss_fn.alpha,
+                                           beta=tc.SOLVER.TASK_LOSS_WEIGHT, wf_amp=1.0, bn_train=False)[0].item()
+    assert np.isfinite(gnorm) and gnorm > 0, "training step produced no gradient"
+    assert abs(loss.item() - ref_loss) <= 3e-2 * abs(ref_loss), "train loss %g vs oracle %g" % (loss.item(), ref_loss)
+    print("smoke ok: sr max-abs %.4f, seg max-abs %.4f, AIU %.4f, AHD(p50) %.3f, %d kernel launches (eval); "
+          "train step loss %.5f (oracle %.5f), |grad| %.3e, %d launches"
+          % (e_sr, e_seg, float(np.mean(r["iou"])), float(np.mean(r["hd"])), n_eval, loss.item(), ref_loss, gnorm,
+             _lib.LAUNCHES - n_eval))

@@ -79,11 +79,12 @@ def main():
         print("Trained model is loaded from {}".format(trained_model))
     elif args.synthetic:
         sd = synth.model_state_dict()
-        if cfg.MODEL.DETECTOR_TYPE == "PSPNet_BlurSkip":
+        if cfg.MODEL.DETECTOR_TYPE in ("PSPNet_BlurSkip", "HRNet_OCR"):
             from csbsr_b200.modeling import params as P
             sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-            sd.update(P.synth_state_dict(P.pspnet_param_shapes(blur_dim=cfg.BLUR.KERNEL_SIZE_OUTPUT ** 2),
-                                         prefix="segmentation_model."))
+            seg_shapes = P.hrnet_ocr_param_shapes() if cfg.MODEL.DETECTOR_TYPE == "HRNet_OCR" else \
+                P.pspnet_param_shapes(blur_dim=cfg.BLUR.KERNEL_SIZE_OUTPUT ** 2)
+            sd.update(P.synth_state_dict(seg_shapes, prefix="segmentation_model."))
         model.load_state_dict(sd, strict=True)
         print("checkpoint %s not found: synthetic weights loaded" % trained_model)
     else:
