@@ -26,10 +26,80 @@ def train_step(model, optimizer, cfg, iteration, hr, mask, params, world_size=1)
     return loss.detach(), seg_loss.detach().mean(), sr_loss.detach().mean()
 
 
+class GraphedTrainStep:
+    """train_step with forward + loss + backward replayed from a CUDA graph (the step launches ~4000 small kernels; from
+    Python it is launch-bound at ~60 ms, replayed it takes the ~50 ms of GPU time).  One graph per (training phase, alpha of
+    the boundary loss, input shape): the iteration only enters the forward through the phase switches, alpha is a kernel
+    scalar.  Inputs are copied into static buffers; the gradient all-reduce and the fused Adam step stay outside the graph
+    (the bias corrections change every step)."""
+
+    def __init__(self, model, optimizer, cfg, world_size=1):
+        self.model, self.opt, self.cfg, self.world = model, optimizer, cfg, world_size
+        self.graphs = {}
+        self.launches_per_step = 0
+
+    def _phase_key(self, it):
+        s = self.cfg.SOLVER
+        inside = lambda r: r[0] <= it < r[1]
+        return (inside(s.SR_PRETRAIN_ITER), inside(s.SR_SR_MODULE_PRETRAIN_ITER), inside(s.SR_KERNEL_MODULE_PRETRAIN_ITER),
+                s.SR_KERNEL_MODULE_PRETRAIN_ITER[0] <= it < s.SR_KERNEL_MODULE_PRETRAIN_ITER[1] - 1,
+                s.ORIENTED_WEIGHT_ITER <= it)
+
+    def _body(self, st, it):
+        cfg = self.cfg
+        lr_img, kernels = G.degrade(st["hr"], st["params"], ksize=cfg.BLUR.KERNEL_SIZE_OUTPUT, factor=cfg.MODEL.SCALE_FACTOR)
+        seg_loss, sr_loss, seg, sr, kp = self.model(it, lr_img, sr_targets=st["hr"], segment_targets=st["mask"],
+                                                    kernel_targets=kernels.unsqueeze(1))
+        seg_mean = seg_loss.mean()
+        loss = calc_loss(sr_loss, seg_mean, cfg.SOLVER.TASK_LOSS_WEIGHT, it, cfg)
+        loss.backward()
+        return loss.detach(), seg_mean.detach(), sr_loss.detach().mean()
+
+    def _capture(self, it, hr, mask, params):
+        st = {"hr": hr.clone(), "mask": mask.clone(), "params": torch.as_tensor(params).to(hr.device).clone()}
+        buffers = [(b, b.clone()) for b in self.model.buffers()]         # warm-up must not advance the BN running stats
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._body(st, it)
+        torch.cuda.current_stream().wait_stream(side)
+        for b, saved in buffers:
+            b.copy_(saved)
+        self.opt.flat_g.zero_()
+        from .. import _lib
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.LAUNCHES
+        with torch.cuda.graph(graph):
+            st["out"] = self._body(st, it)
+        self.launches_per_step = _lib.LAUNCHES - n0 + 1          # own kernels inside the graph + the Adam launch
+        self.opt.flat_g.zero_()
+        for b, saved in buffers:
+            b.copy_(saved)
+        st["graph"] = graph
+        return st
+
+    def __call__(self, iteration, hr, mask, params):
+        key = (self._phase_key(iteration), float(self.model.ss_loss_fn.alpha), tuple(hr.shape))
+        st = self.graphs.get(key)
+        if st is None:
+            st = self.graphs[key] = self._capture(iteration, hr, mask, params)
+        st["hr"].copy_(hr, non_blocking=True)
+        st["mask"].copy_(mask, non_blocking=True)
+        st["params"].copy_(torch.as_tensor(params).to(st["params"].device), non_blocking=True)
+        st["graph"].replay()
+        if self.world > 1:
+            self.opt.all_reduce_grads()
+        self.opt.step(self.world)
+        self.opt.scheduler_step()
+        return st["out"]
+
+
 def do_train(args, cfg, model, optimizer, batches, rank=0, world_size=1, log=print):
     """`batches` yields (iteration, hr [B,3,H,W], mask [B,1,H,W], blur params [B,3]) for THIS rank."""
     model.train()
     t0 = time.time()
+    graphed = GraphedTrainStep(model, optimizer, cfg, world_size) if getattr(args, "cuda_graph", False) else None
     for iteration, hr, mask, params in batches:
         # boundary-loss alpha schedule, poked from the trainer before every step (fix_1st_stage_model_params,
         # trainer.py:495-508): frozen at its start value during SR pre-training, one schedule tick per iteration after it
@@ -38,7 +108,10 @@ def do_train(args, cfg, model, optimizer, batches, rank=0, world_size=1, log=pri
         else:
             model.ss_loss_fn.fix_alpha = False
             model.ss_loss_fn.update_alpha()
-        loss, seg_l, sr_l = train_step(model, optimizer, cfg, iteration, hr, mask, params, world_size)
+        if graphed is not None:
+            loss, seg_l, sr_l = graphed(iteration, hr, mask, params)
+        else:
+            loss, seg_l, sr_l = train_step(model, optimizer, cfg, iteration, hr, mask, params, world_size)
         if iteration % args.log_step == 0 and rank == 0:
             torch.cuda.synchronize()
             log("===> Iter: {:07d}, LR: {:.06f}, Cost: {:.2f}s, Loss: {:.6f} (seg {:.6f}, sr {:.6f}), alpha {:.3f}".format(

@@ -73,6 +73,28 @@ def _expand_vec(kvec, h, w):
     return v.view(b, 1, 1, -1).expand(b, h, w, -1)
 
 
+_CLASS_IDX = {}
+
+
+def _border_classes(n, bw, device):
+    """Class index of every position along an axis of length n for a response that only feels the zero padding within
+    `bw` pixels of the border: 0..bw-1 at the start, bw in the interior, bw+1..2bw at the end (cached per shape)."""
+    key = (n, bw, str(device))
+    if key not in _CLASS_IDX:
+        idx = [bw] * n
+        for i in range(min(bw, n)):
+            idx[i] = i
+            idx[n - 1 - i] = 2 * bw - i
+        _CLASS_IDX[key] = torch.tensor(idx, dtype=torch.long).to(device)
+    return _CLASS_IDX[key]
+
+
+def _expand_classes(small, h, w, bw):
+    """[B, 2bw+1, 2bw+1, C] per-class responses -> [B, h, w, C] (differentiable gather; backward = scatter-add)."""
+    yi, xi = _border_classes(h, bw, small.device), _border_classes(w, bw, small.device)
+    return small[:, yi][:, :, xi]
+
+
 def _kernel_predictor(P, p, sr_t, kvec, k_out):
     n, H, W, _ = sr_t.shape
     fsr = _convblock(P, p + ".fe_SR.0", sr_t, padding=1, act="relu")
@@ -80,9 +102,13 @@ def _kernel_predictor(P, p, sr_t, kvec, k_out):
     fsr = _convblock(P, p + ".fe_SR.2", fsr, padding=1, act="lrelu")
     fsr = _convblock(P, p + ".fe_SR.3", fsr, padding=1, act="lrelu")
     fsr = _convblock(P, p + ".fe_SR.4", fsr, padding=1, act="lrelu")
-    fh = _expand_vec(kvec, H, W).contiguous()
+    # fe_kernel sees a spatially constant map (kbpn.py:572-573): two stacked zero-padded 3x3 convs respond identically
+    # everywhere except within 2 px of the border -> evaluate them on a 5x5 image of border classes and gather
+    # (exactly the reference's values; gradients reach the kernel vector and both convs through the gather)
+    fh = _expand_vec(kvec, 5, 5).contiguous()
     fh = _convblock(P, p + ".fe_kernel.0", fh, padding=1, act="lrelu")
     fh = _convblock(P, p + ".fe_kernel.1", fh, padding=1, act="lrelu")
+    fh = _expand_classes(fh, H, W, 2)
     c = P[p + ".fe_SR.4.layer.weight"].shape[0]
     d = _cat((fsr, fh), real=(c, c))
     d = _convblock(P, p + ".fe_cat.0", d, act="lrelu")
@@ -126,10 +152,17 @@ def _k_block(P, p, concat_h, h, x_lr, kvec, k_out, scale, predict_kernel=True):
 
 
 def _sft(P, p, feats, kvec):
-    n, h, w, _ = feats.shape
-    c = _cat((feats, _expand_vec(kvec, h, w)[..., :kvec.shape[1]]))
+    """SFTlayer.forward (kbpn.py:511-518).  conv0 acts on cat(features, kernel map); the 441 kernel-map channels are
+    spatially constant, so their part of the (linear) conv is evaluated on a 3x3 image of border classes and added as a
+    per-sample, per-class bias: conv0(cat(f, k)) = conv(f, W[:, :fc]) + gather(conv(k_3x3, W[:, fc:]) + b)."""
+    n, h, w, fc = feats.shape
+    cond = _expand_vec(kvec, 3, 3).contiguous()
+
     def branch(name):
-        t = conv2d(c, P[p + ".SFT_%s_conv0.weight" % name], P[p + ".SFT_%s_conv0.bias" % name], padding=1)
+        w0 = P[p + ".SFT_%s_conv0.weight" % name]
+        t = conv2d(feats, w0[:, :fc].contiguous(), None, padding=1)
+        tb = conv2d(cond, w0[:, fc:].contiguous(), P[p + ".SFT_%s_conv0.bias" % name], padding=1)
+        t = t + _expand_classes(tb, h, w, 1)
         return conv2d(F.leaky_relu(t, 0.1), P[p + ".SFT_%s_conv1.weight" % name], P[p + ".SFT_%s_conv1.bias" % name], padding=1)
     return feats * torch.sigmoid(branch("scale")) + branch("shift")
 

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--layers", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="capture forward + loss + backward in a CUDA graph")
     a = ap.parse_args()
     from csbsr_b200 import _lib
     from csbsr_b200.config import cfg
@@ -48,6 +49,25 @@ def main():
         opt.step()
         return loss
 
+    if a.graph:
+        m.dropout = True
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(3):
+                l = step(40000 + i)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        static_loss = None
+        with torch.cuda.graph(graph):
+            seg_loss, sr_loss, *_ = m(40100, lr, sr_targets=hr, segment_targets=mask, kernel_targets=kgt)
+            static_loss = calc_loss(sr_loss, seg_loss.mean(), c.SOLVER.TASK_LOSS_WEIGHT)
+            static_loss.backward()
+
+        def step(it):                                     # noqa: F811
+            graph.replay()
+            opt.step()
+            return static_loss
     for i in range(a.warmup):
         l = step(40000 + i)
     torch.cuda.synchronize()

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--max_iter", type=int, default=None, help="stop after this iteration (default SOLVER.MAX_ITER)")
     ap.add_argument("--synthetic", type=int, default=0, help="train on N synthetic crack images")
     ap.add_argument("--crop", type=int, default=None, help="HR crop size (default INPUT.IMAGE_SIZE of the config)")
+    ap.add_argument("--cuda_graph", type=int, default=1, help="replay forward+loss+backward from a CUDA graph (1) or launch eagerly (0)")
     args = ap.parse_args()
 
     from csbsr_b200.config import cfg
