@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE metric part 2)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the eval hot path eagerly instead of replaying a CUDA graph")
     ap.add_argument("--train-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -243,13 +244,48 @@ def main():
     def gather(res):
         return D.gather_rows(res)                # the only exchange: B x 396 fp64 per rank (no-op at world size 1)
 
+    # The hot path of one batch is ~1400 launches: replay it from a CUDA graph (same kernels, no per-launch CPU cost).
+    # Static input buffers; falls back to eager launches if capture is not possible.
+    graph_state = {"graph": None, "hr": hr_dev.clone(), "mask": mask_dev.clone(), "out": None}
+
+    def try_capture():
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                hot_path(graph_state["hr"], graph_state["mask"])
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                graph_state["out"] = hot_path(graph_state["hr"], graph_state["mask"])
+            graph_state["graph"] = g
+        except Exception as e:                                  # noqa: BLE001
+            graph_state["graph"] = None
+            torch.cuda.synchronize()
+            if rank == 0:
+                print("cuda graph capture failed, launching eagerly: %r" % (e,), file=sys.stderr)
+
+    def run_hot_path(hr, mask):
+        if graph_state["graph"] is None:
+            return hot_path(hr, mask)
+        if hr.data_ptr() != graph_state["hr"].data_ptr():
+            graph_state["hr"].copy_(hr, non_blocking=True)
+            graph_state["mask"].copy_(mask, non_blocking=True)
+        graph_state["graph"].replay()
+        return graph_state["out"]
+
     def step_device():
-        return gather(hot_path(hr_dev, mask_dev))
+        return gather(run_hot_path(graph_state["hr"], graph_state["mask"]))
 
     def step_e2e():
-        hr = hr_host.to(dev, non_blocking=True)
-        mask = mask_host.to(dev, non_blocking=True)
-        res = gather(hot_path(hr, mask)).cpu().numpy()
+        if graph_state["graph"] is not None:                    # H2D straight into the graph's static input buffers
+            graph_state["hr"].copy_(hr_host, non_blocking=True)
+            graph_state["mask"].copy_(mask_host, non_blocking=True)
+            res = gather(run_hot_path(graph_state["hr"], graph_state["mask"])).cpu().numpy()
+        else:
+            hr = hr_host.to(dev, non_blocking=True)
+            mask = mask_host.to(dev, non_blocking=True)
+            res = gather(hot_path(hr, mask)).cpu().numpy()
         inter, union, hd = res[:, :99], res[:, 99:198], res[:, 198:297]
         iou = (inter + 1e-5) / (union + 1e-5)
         return float(np.mean(iou)), float(np.mean(hd))     # AIU, AHD (inference.py:171-173)
@@ -272,6 +308,12 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), out
 
+    hot_path(hr_dev, mask_dev)                                  # first call packs the weights and sizes the workspaces
+    torch.cuda.synchronize()
+    l_cap = _lib.LAUNCHES
+    if not args.no_graph:
+        try_capture()
+    launches_per_step = (_lib.LAUNCHES - l_cap) // 2 if graph_state["graph"] is not None else None
     for _ in range(max(args.warmup, 3)):
         step_device()
     sampler = ClockSampler(local)
@@ -279,14 +321,14 @@ def main():
         sampler.start()
     l0 = _lib.LAUNCHES
     ms_dev, _ = timed(step_device, args.steps)
-    launches = (_lib.LAUNCHES - l0) // max(args.steps, 1)
+    launches = launches_per_step if launches_per_step is not None else (_lib.LAUNCHES - l0) // max(args.steps, 1)
     step_e2e()
     ms_e2e, (aiu, ahd) = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel (conv_igemm_kernel), measured live with CUDA events per launch
     K.PROFILE = []
-    step_device()
+    hot_path(hr_dev, mask_dev)                  # eager launches: the per-launch events cannot be recorded inside a graph replay
     torch.cuda.synchronize()
     conv_ms = sum(r[2].elapsed_time(r[3]) for r in K.PROFILE)
     conv_useful = sum(r[4] for r in K.PROFILE)
@@ -314,7 +356,8 @@ def main():
                                "anisotropic-blur degradation, AIU + HD(p50)/MSD sweep over 99 thresholds" % B,
                    "batch_per_gpu": B, "chunk": args.chunk, "hr": HR, "scale": 4, "weights": "synthetic random-init (seed 1121)",
                    "l2": "per-step inputs (%.0f MB) and activations exceed the 126 MB L2; no flush needed" % (h2d / 1e6),
-                   "aiu": aiu, "ahd_p50": ahd},
+                   "aiu": aiu, "ahd_p50": ahd,
+                   "launch": "CUDA graph replay of the hot path" if graph_state["graph"] is not None else "eager launches"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
