@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE metric part 2)")
     ap.add_argument("--no-graph", action="store_true", help="launch the eval hot path eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--detector", default="PSPNet", choices=["PSPNet", "PSPNet_BlurSkip", "HRNet_OCR"],
+                    help="segmentation net of the eval leg: PSPNet = the headline config (#2); the others are configs #5 / #4")
     ap.add_argument("--train-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -216,8 +218,18 @@ def main():
     B = args.batch
     c = cfg.clone()
     c.merge_from_file(os.path.join(ROOT, "config", "config_csbsr_pspnet.yaml"))
+    c.MODEL.DETECTOR_TYPE = args.detector
     model = JointModel(c)
-    model.load_state_dict(synth.model_state_dict(), strict=True)
+    if args.detector == "PSPNet":
+        model.load_state_dict(synth.model_state_dict(), strict=True)
+    else:
+        from csbsr_b200.modeling import params as MP
+        sd_ = MP.synth_state_dict(MP.kbpn_param_shapes(), prefix="sr_model.")
+        seg_shapes = MP.hrnet_ocr_param_shapes() if args.detector == "HRNet_OCR" else \
+            MP.pspnet_param_shapes(blur_dim=c.BLUR.KERNEL_SIZE_OUTPUT ** 2)
+        sd_.update(MP.synth_state_dict(seg_shapes, prefix="segmentation_model."))
+        model.load_state_dict(sd_, strict=True)
+        args.no_train = True                      # the training leg is the PSPNet config (#3)
     model.chunk = args.chunk
 
     # synthetic inputs: a few distinct images tiled to the batch (generation is untimed); each rank its own shard
@@ -352,7 +364,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "CSBSR w/ PSPNet x4 eval (config_csbsr_pspnet.yaml), batch %d x 448^2 HR per GPU, on-the-fly "
+        "config": {"workload": "CSBSR w/ " + args.detector + " x4 eval (config_csbsr_pspnet.yaml), batch %d x 448^2 HR per GPU, on-the-fly "
                                "anisotropic-blur degradation, AIU + HD(p50)/MSD sweep over 99 thresholds" % B,
                    "batch_per_gpu": B, "chunk": args.chunk, "hr": HR, "scale": 4, "weights": "synthetic random-init (seed 1121)",
                    "l2": "per-step inputs (%.0f MB) and activations exceed the 126 MB L2; no flush needed" % (h2d / 1e6),
