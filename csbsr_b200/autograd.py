@@ -238,3 +238,62 @@ def blur_per_sample(img, kvec, ksize, stride):
 
 def resize_aa(x, factor):
     return _ResizeAAFn.apply(x, factor)
+
+
+class _BatchNormFn(torch.autograd.Function):
+    """nn.BatchNorm2d on an NHWC bf16 map with optional fused residual add and ReLU:  y = relu?(bn(x) + res?).
+    training=True: batch statistics (and the in-place momentum update of the running buffers); False: running statistics."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, res, training, momentum, eps, relu):
+        from . import _lib
+        assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+        n, h, w, pitch = x.shape
+        c, m = gamma.numel(), n * h * w
+        L = _lib.lib()
+        if training:
+            mean = torch.empty(c, dtype=torch.float32, device=x.device)
+            rstd = torch.empty(c, dtype=torch.float32, device=x.device)
+            ws = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+            _lib.check(L.csbsr_bn_stats(x.data_ptr(), pitch, c, m, eps, momentum, mean.data_ptr(), rstd.data_ptr(),
+                                        running_mean.data_ptr() if running_mean is not None else None,
+                                        running_var.data_ptr() if running_var is not None else None, ws.data_ptr(),
+                                        _lib.stream_ptr()), "csbsr_bn_stats")
+            _lib.count_launch("csbsr_bn_stats")
+        else:
+            mean = running_mean.detach().float().contiguous()
+            rstd = torch.rsqrt(running_var.detach().float() + eps).contiguous()
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        if res is not None:
+            res = res.contiguous()
+            assert res.shape == x.shape and res.dtype == torch.bfloat16
+        y = torch.empty_like(x)
+        _lib.check(L.csbsr_bn_apply(x.data_ptr(), res.data_ptr() if res is not None else None, y.data_ptr(), mean.data_ptr(),
+                                    rstd.data_ptr(), g32.data_ptr(), b32.data_ptr(), pitch, c, m, int(relu), _lib.stream_ptr()),
+                   "csbsr_bn_apply")
+        _lib.count_launch("csbsr_bn_apply")
+        ctx.save_for_backward(x, y if relu else None, g32, mean, rstd)
+        ctx.cfg = (bool(training), res is not None, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _lib
+        x, y, g32, mean, rstd = ctx.saved_tensors
+        training, has_res, c = ctx.cfg
+        dy = dy.contiguous()
+        n, h, w, pitch = x.shape
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if has_res else None
+        dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().csbsr_bn_backward(dy.data_ptr(), x.data_ptr(), y.data_ptr() if y is not None else None,
+                                                mean.data_ptr(), rstd.data_ptr(), g32.data_ptr(), pitch, c, n * h * w,
+                                                int(training), dx.data_ptr(), dres.data_ptr() if has_res else None,
+                                                dgamma.data_ptr(), dbeta.data_ptr(), _lib.stream_ptr()), "csbsr_bn_backward")
+        _lib.count_launch("csbsr_bn_backward")
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None
+
+
+def batch_norm(x, gamma, beta, running_mean, running_var, training, momentum=0.1, eps=1e-5, relu=False, res=None):
+    return _BatchNormFn.apply(x, gamma, beta, running_mean, running_var, res, training, momentum, eps, relu)

@@ -352,3 +352,236 @@ extern "C" int csbsr_pack_weights(const float* w, void* out, int a, int b, int r
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// BatchNorm2d for the training graph on NHWC bf16 maps [m pixels][pitch channels] (first c channels real, the rest zero
+// padding): batch statistics or running statistics, optional fused residual add and ReLU (BasicBlock / Bottleneck tails,
+// pspnet_pytorch/extractors.py:52-70; hrnet_backbone.py), with the matching backward.  Replaces at::native batch_norm_*.
+//   y = relu?( (x - mean) * rstd * gamma + beta + res? )
+//   dyz = dy * (y > 0 if relu);  dbeta = sum dyz;  dgamma = sum dyz * xhat;  dres = dyz
+//   dx = gamma * rstd * (dyz - [training] (dbeta + xhat * dgamma) / m)
+namespace csbsr {
+
+// thread -> (pixel lane, 8-channel group); per-channel partial sums are combined through shared memory, then atomics
+template <int NS>   // NS accumulators per channel
+struct ChanAcc {
+    float v[NS][8];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[s][j] = 0.f;
+    }
+};
+
+template <int NS>
+__device__ __forceinline__ void chan_block_reduce(ChanAcc<NS>& a, int grp, int lane_pix, int lanes, int groups, float* smem,
+                                                  float* const* out) {
+    // smem: [lanes][groups*8] per accumulator, processed one accumulator at a time
+    for (int s = 0; s < NS; ++s) {
+        __syncthreads();
+        if (grp < groups) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) smem[(lane_pix * groups + grp) * 8 + j] = a.v[s][j];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < groups * 8; i += blockDim.x) {
+            float t = 0.f;
+            for (int l = 0; l < lanes; ++l) t += smem[l * groups * 8 + i];
+            atomicAdd(out[s] + i, t);
+        }
+    }
+}
+
+__global__ void bn_stats_kernel(const uint4* __restrict__ x, int pitch8, int groups, long long m, float* sum, float* sumsq) {
+    extern __shared__ float bn_sm[];
+    const int lanes = blockDim.x / groups;
+    const int grp = threadIdx.x % groups, lane_pix = threadIdx.x / groups;
+    ChanAcc<2> a;
+    a.zero();
+    if (lane_pix < lanes) {
+        for (long long p = static_cast<long long>(blockIdx.x) * lanes + lane_pix; p < m; p += static_cast<long long>(gridDim.x) * lanes) {
+            float f[8];
+            unpack8(x[p * pitch8 + grp], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a.v[0][j] += f[j]; a.v[1][j] = fmaf(f[j], f[j], a.v[1][j]); }
+        }
+    }
+    float* outs[2] = {sum, sumsq};
+    chan_block_reduce<2>(a, lane_pix < lanes ? grp : groups, lane_pix < lanes ? lane_pix : 0, lanes, groups, bn_sm, outs);
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, long long m, int c, float eps,
+                                   float momentum, float* mean, float* rstd, float* running_mean, float* running_var) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const double mu = static_cast<double>(sum[i]) / m;
+    double var = static_cast<double>(sumsq[i]) / m - mu * mu;
+    if (var < 0) var = 0;
+    mean[i] = static_cast<float>(mu);
+    rstd[i] = static_cast<float>(1.0 / sqrt(var + eps));
+    if (running_mean) {                                        // nn.BatchNorm2d: unbiased variance in the running estimate
+        const double unb = m > 1 ? var * m / (m - 1) : var;
+        running_mean[i] = static_cast<float>((1.0 - momentum) * running_mean[i] + momentum * mu);
+        running_var[i] = static_cast<float>((1.0 - momentum) * running_var[i] + momentum * unb);
+    }
+}
+
+__global__ void bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res, uint4* __restrict__ y,
+                                const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int groups, int pitch8, long long m, int relu) {
+    const long long total = m * pitch8;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % pitch8);
+        float f[8];
+        if (g < groups) {
+            unpack8(x[i], f);
+            float r[8];
+            if (res) unpack8(res[i], r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ch = g * 8 + j;
+                float v = (f[j] - mean[ch]) * rstd[ch] * gamma[ch] + beta[ch];
+                if (res) v += r[j];
+                f[j] = relu ? fmaxf(v, 0.f) : v;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        }
+        y[i] = pack8(f);
+    }
+}
+
+__global__ void bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ y,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd, int pitch8, int groups,
+                                     long long m, float* s1, float* s2) {
+    extern __shared__ float bn_sm[];
+    const int lanes = blockDim.x / groups;
+    const int grp = threadIdx.x % groups, lane_pix = threadIdx.x / groups;
+    ChanAcc<2> a;
+    a.zero();
+    if (lane_pix < lanes) {
+        float mu[8], rs[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { mu[j] = mean[grp * 8 + j]; rs[j] = rstd[grp * 8 + j]; }
+        for (long long p = static_cast<long long>(blockIdx.x) * lanes + lane_pix; p < m; p += static_cast<long long>(gridDim.x) * lanes) {
+            float g[8], f[8], o[8];
+            unpack8(dy[p * pitch8 + grp], g);
+            unpack8(x[p * pitch8 + grp], f);
+            if (y) unpack8(y[p * pitch8 + grp], o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = (y && !(o[j] > 0.f)) ? 0.f : g[j];
+                a.v[0][j] += d;
+                a.v[1][j] = fmaf(d, (f[j] - mu[j]) * rs[j], a.v[1][j]);
+            }
+        }
+    }
+    float* outs[2] = {s1, s2};
+    chan_block_reduce<2>(a, lane_pix < lanes ? grp : groups, lane_pix < lanes ? lane_pix : 0, lanes, groups, bn_sm, outs);
+}
+
+__global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ y,
+                                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ s1, const float* __restrict__ s2, int groups, int pitch8, long long m,
+                                    int training, uint4* __restrict__ dx, uint4* __restrict__ dres) {
+    const long long total = m * pitch8;
+    const float inv_m = 1.f / static_cast<float>(m);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % pitch8);
+        float d[8], o8[8];
+        if (g < groups) {
+            float f[8], o[8];
+            unpack8(dy[i], d);
+            unpack8(x[i], f);
+            if (y) unpack8(y[i], o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ch = g * 8 + j;
+                const float dz = (y && !(o[j] > 0.f)) ? 0.f : d[j];
+                const float xh = (f[j] - mean[ch]) * rstd[ch];
+                float v = dz;
+                if (training) v -= (s1[ch] + xh * s2[ch]) * inv_m;
+                o8[j] = gamma[ch] * rstd[ch] * v;
+                d[j] = dz;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { d[j] = 0.f; o8[j] = 0.f; }
+        }
+        dx[i] = pack8(o8);
+        if (dres) dres[i] = pack8(d);
+    }
+}
+
+static int bn_block_cfg(int groups, int& lanes) {      // threads per block: whole number of pixel lanes, <= 256 when possible
+    lanes = 256 / groups;
+    if (lanes < 1) lanes = 1;
+    return lanes * groups;
+}
+
+}  // namespace csbsr
+
+extern "C" int csbsr_bn_stats(const void* x, int pitch, int c, long long m, float eps, float momentum, float* mean, float* rstd,
+                              float* running_mean, float* running_var, float* workspace, void* stream) {
+    CSBSR_REQUIRE(x && mean && rstd && workspace && c > 0 && c % 8 == 0 && pitch % 8 == 0 && c <= pitch && c <= 8192 && m > 0,
+                  "bn_stats: bad arguments (c=%d pitch=%d)", c, pitch);
+    CSBSR_REQUIRE(!running_mean == !running_var, "bn_stats: running_mean and running_var go together");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    float* sum = workspace;
+    float* sumsq = workspace + c;
+    CSBSR_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * 2 * c, st));
+    const int groups = c / 8;
+    int lanes;
+    const int threads = bn_block_cfg(groups, lanes);
+    CSBSR_REQUIRE(threads <= 1024, "bn_stats: too many channels");
+    long long blocks = (m + lanes * 64 - 1) / (static_cast<long long>(lanes) * 64);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    if (blocks < 1) blocks = 1;
+    bn_stats_kernel<<<static_cast<int>(blocks), threads, sizeof(float) * lanes * groups * 8, st>>>(
+        reinterpret_cast<const uint4*>(x), pitch / 8, groups, m, sum, sumsq);
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sum, sumsq, m, c, eps, momentum, mean, rstd, running_mean, running_var);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_bn_apply(const void* x, const void* res, void* y, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, int pitch, int c, long long m, int relu, void* stream) {
+    CSBSR_REQUIRE(x && y && mean && rstd && gamma && beta && c > 0 && c % 8 == 0 && pitch % 8 == 0 && c <= pitch && m > 0,
+                  "bn_apply: bad arguments");
+    const long long total = m * (pitch / 8);
+    bn_apply_kernel<<<grid_cap(static_cast<size_t>(total), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(res), reinterpret_cast<uint4*>(y), mean, rstd, gamma,
+        beta, c / 8, pitch / 8, m, relu);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_bn_backward(const void* dy, const void* x, const void* y_relu, const float* mean, const float* rstd,
+                                 const float* gamma, int pitch, int c, long long m, int training, void* dx, void* dres,
+                                 float* dgamma, float* dbeta, void* stream) {
+    CSBSR_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && c > 0 && c % 8 == 0 && pitch % 8 == 0 &&
+                      c <= pitch && c <= 8192 && m > 0, "bn_backward: bad arguments");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CSBSR_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * c, st));
+    CSBSR_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * c, st));
+    const int groups = c / 8;
+    int lanes;
+    const int threads = bn_block_cfg(groups, lanes);
+    CSBSR_REQUIRE(threads <= 1024, "bn_backward: too many channels");
+    long long blocks = (m + lanes * 64 - 1) / (static_cast<long long>(lanes) * 64);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    if (blocks < 1) blocks = 1;
+    bn_bwd_reduce_kernel<<<static_cast<int>(blocks), threads, sizeof(float) * lanes * groups * 8, st>>>(
+        reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(y_relu), mean, rstd,
+        pitch / 8, groups, m, dbeta, dgamma);
+    const long long total = m * (pitch / 8);
+    bn_bwd_apply_kernel<<<grid_cap(static_cast<size_t>(total), 256), 256, 0, st>>>(
+        reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(y_relu), mean, rstd,
+        gamma, dbeta, dgamma, groups, pitch / 8, m, training, reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dres));
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

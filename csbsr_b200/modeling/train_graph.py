@@ -15,7 +15,7 @@ Mirrors, in train mode and outside the pre-training phases (iteration >= SR_PRET
 import torch
 import torch.nn.functional as F
 
-from ..autograd import conv2d, cpad, deconv8s4, prelu, to_nchw, to_nhwc
+from ..autograd import batch_norm, conv2d, cpad, deconv8s4, prelu, to_nchw, to_nhwc
 from .params import RESNET34_LAYERS
 
 
@@ -89,10 +89,35 @@ def _border_classes(n, bw, device):
     return _CLASS_IDX[key]
 
 
+class _ExpandClassesFn(torch.autograd.Function):
+    """[B, 2bw+1, 2bw+1, C] per-class responses -> [B, h, w, C].  Backward sums the gradient over the pixels of every class
+    with slice reductions (border rows / columns individually, the interior block as one sum) instead of a scatter-add."""
+
+    @staticmethod
+    def forward(ctx, small, h, w, bw):
+        ctx.cfg = (h, w, bw)
+        yi, xi = _border_classes(h, bw, small.device), _border_classes(w, bw, small.device)
+        return small[:, yi][:, :, xi]
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w, bw = ctx.cfg
+
+        def fold(t, dim, n):
+            if n <= 2 * bw:                                   # degenerate (tiny) axis: generic path
+                idx = _border_classes(n, bw, t.device)
+                shape = list(t.shape)
+                shape[dim] = 2 * bw + 1
+                return torch.zeros(shape, dtype=t.dtype, device=t.device).index_add_(dim, idx, t)
+            head = t.narrow(dim, 0, bw)
+            mid = t.narrow(dim, bw, n - 2 * bw).sum(dim=dim, keepdim=True, dtype=torch.float32).to(t.dtype)
+            tail = t.narrow(dim, n - bw, bw)
+            return torch.cat((head, mid, tail), dim=dim)
+        return fold(fold(g, 1, h), 2, w), None, None, None
+
+
 def _expand_classes(small, h, w, bw):
-    """[B, 2bw+1, 2bw+1, C] per-class responses -> [B, h, w, C] (differentiable gather; backward = scatter-add)."""
-    yi, xi = _border_classes(h, bw, small.device), _border_classes(w, bw, small.device)
-    return small[:, yi][:, :, xi]
+    return _ExpandClassesFn.apply(small, h, w, bw)
 
 
 def _kernel_predictor(P, p, sr_t, kvec, k_out):
@@ -202,17 +227,14 @@ def kbpn_forward(P, x_lr, num_stages=4, k_out=21, scale=4, prefix="sr_model.", g
 
 
 # ---------------------------------------------------------------------------------------------- PSPNet (train mode)
-def _bn(P, p, x, training, momentum=0.1):
-    """BatchNorm2d on an NHWC tensor; train mode uses batch statistics and updates the running buffers in place.
-    Tensors whose channel count was padded to 64 are normalised on their real channels and re-padded with zeros."""
-    c = P[p + ".weight"].numel()
-    xin = x if x.shape[3] == c else x[..., :c]
-    y = F.batch_norm(_nchw(xin), P[p + ".running_mean"], P[p + ".running_var"], P[p + ".weight"], P[p + ".bias"],
-                     training=training, momentum=momentum, eps=1e-5)
+def _bn(P, p, x, training, momentum=0.1, relu=False, res=None):
+    """BatchNorm2d (+ fused residual add and ReLU) on an NHWC tensor with the csbsr_bn_* kernels; train mode uses batch
+    statistics and updates the running buffers in place.  Channel-padded tensors stay zero in the padding channels."""
+    y = batch_norm(x, P[p + ".weight"], P[p + ".bias"], P[p + ".running_mean"], P[p + ".running_var"], training, momentum,
+                   1e-5, relu=relu, res=res)
     if training and (p + ".num_batches_tracked") in P:
         P[p + ".num_batches_tracked"] += 1
-    y = _nhwc(y)
-    return y if x.shape[3] == c else F.pad(y, (0, x.shape[3] - c))
+    return y
 
 
 def _drop(x, p, on):
@@ -224,7 +246,7 @@ def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_
     p = prefix
     H, W = img.shape[2:]
     x = to_nhwc(img)
-    x = F.relu(_bn(P, p + "feats.bn1", conv2d(x, P[p + "feats.conv1.weight"], None, stride=2, padding=3), bn_training))
+    x = _bn(P, p + "feats.bn1", conv2d(x, P[p + "feats.conv1.weight"], None, stride=2, padding=3), bn_training, relu=True)
     x = _nhwc(F.max_pool2d(_nchw(x), kernel_size=3, stride=2, padding=1))
     x3 = None
     for li, (planes, blocks, stride, dil) in enumerate(RESNET34_LAYERS, 1):
@@ -232,12 +254,13 @@ def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_
             bp = p + "feats.layer%d.%d" % (li, b)
             st = stride if b == 0 else 1
             d = 1 if b == 0 else dil
-            out = F.relu(_bn(P, bp + ".bn1", conv2d(x, P[bp + ".conv1.weight"], None, stride=st, padding=d, dilation=d), bn_training))
-            out = _bn(P, bp + ".bn2", conv2d(out, P[bp + ".conv2.weight"], None, padding=d, dilation=d), bn_training)
+            out = _bn(P, bp + ".bn1", conv2d(x, P[bp + ".conv1.weight"], None, stride=st, padding=d, dilation=d), bn_training,
+                      relu=True)
             res = x
             if (bp + ".downsample.0.weight") in P:
                 res = _bn(P, bp + ".downsample.1", conv2d(x, P[bp + ".downsample.0.weight"], None, stride=st), bn_training)
-            x = F.relu(out + res)
+            x = _bn(P, bp + ".bn2", conv2d(out, P[bp + ".conv2.weight"], None, padding=d, dilation=d), bn_training,
+                    relu=True, res=res)                                # relu(bn2(conv2) + residual), extractors.py:62-70
         if li == 3:
             x3 = x
     f = x
@@ -257,7 +280,7 @@ def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_
         y = prelu(y, P[p + name + ".conv.2.weight"])
         y = _drop(y, dp, dropout)
     seg = torch.sigmoid(to_nchw(conv2d(y, P[p + "final.0.weight"], P[p + "final.0.bias"]), 1))
-    a = F.relu(_bn(P, p + "aux.1", conv2d(x3, P[p + "aux.0.weight"], None, padding=1), bn_training))
+    a = _bn(P, p + "aux.1", conv2d(x3, P[p + "aux.0.weight"], None, padding=1), bn_training, relu=True)
     a = _drop(a, 0.1, dropout)
     a = torch.sigmoid(to_nchw(conv2d(a, P[p + "aux.4.weight"], P[p + "aux.4.bias"]), 1))
     aux = F.interpolate(a, size=(H, W), mode="bilinear", align_corners=True)
@@ -265,9 +288,9 @@ def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_
 
 
 # ---------------------------------------------------------------------------------------------- HRNet-W48 + OCR (train mode)
-def _cbr(P, pc, pb, x, training, stride=1, padding=0, relu=True):
-    y = _bn(P, pb, conv2d(x, P[pc + ".weight"], P.get(pc + ".bias"), stride=stride, padding=padding), training)
-    return F.relu(y) if relu else y
+def _cbr(P, pc, pb, x, training, stride=1, padding=0, relu=True, res=None):
+    return _bn(P, pb, conv2d(x, P[pc + ".weight"], P.get(pc + ".bias"), stride=stride, padding=padding), training,
+               relu=relu, res=res)
 
 
 def _resize_ac(x, size):
@@ -283,9 +306,8 @@ def hrnet_w48(P, p, x, training):
         bp = p + "layer1.%d" % i
         out = _cbr(P, bp + ".conv1", bp + ".bn1", x, training)
         out = _cbr(P, bp + ".conv2", bp + ".bn2", out, training, padding=1)
-        out = _cbr(P, bp + ".conv3", bp + ".bn3", out, training, relu=False)
         res = _cbr(P, bp + ".downsample.0", bp + ".downsample.1", x, training, relu=False) if i == 0 else x
-        x = F.relu(out + res)
+        x = _cbr(P, bp + ".conv3", bp + ".bn3", out, training, relu=True, res=res)
     ys, pre = [x], (256,)
     for si, (modules, chans) in enumerate(HRNET48_STAGES, 2):
         t = p + "transition%d" % (si - 1)
@@ -301,8 +323,7 @@ def hrnet_w48(P, p, x, training):
                 for k in range(4):
                     bp = mp + ".branches.%d.%d" % (bi, k)
                     out = _cbr(P, bp + ".conv1", bp + ".bn1", xs[bi], training, padding=1)
-                    out = _cbr(P, bp + ".conv2", bp + ".bn2", out, training, padding=1, relu=False)
-                    xs[bi] = F.relu(out + xs[bi])
+                    xs[bi] = _cbr(P, bp + ".conv2", bp + ".bn2", out, training, padding=1, relu=True, res=xs[bi])
             fused = []
             for i in range(len(chans)):
                 y = None
@@ -333,9 +354,9 @@ def hrnet_ocr_forward(P, img, prefix="segmentation_model.", bn_training=True, dr
     ys, chans = hrnet_w48(P, p + "backbone.", to_nhwc(img), tr)
     h, w = ys[0].shape[1:3]
     feats = _cat([ys[0]] + [_resize_ac(y, (h, w)) for y in ys[1:]], real=chans)                 # 720 -> 768
-    a = F.relu(_bn(P, p + "aux_head.1.0", conv2d(feats, P[p + "aux_head.0.weight"], P[p + "aux_head.0.bias"], padding=1), tr))
+    a = _bn(P, p + "aux_head.1.0", conv2d(feats, P[p + "aux_head.0.weight"], P[p + "aux_head.0.bias"], padding=1), tr, relu=True)
     out_aux = to_nchw(conv2d(a, P[p + "aux_head.2.weight"], P[p + "aux_head.2.bias"]), 1)      # [B,1,h,w] fp32
-    f = F.relu(_bn(P, p + "conv3x3.1.0", conv2d(feats, P[p + "conv3x3.0.weight"], P[p + "conv3x3.0.bias"], padding=1), tr))
+    f = _bn(P, p + "conv3x3.1.0", conv2d(feats, P[p + "conv3x3.0.weight"], P[p + "conv3x3.0.bias"], padding=1), tr, relu=True)
     B, C = f.shape[0], f.shape[3]
     probs = F.softmax(out_aux.view(B, 1, -1), dim=2)                                            # (B, K=1, HW)
     ctx = torch.matmul(probs, f.view(B, h * w, C).float())                                      # (B, 1, C)
@@ -343,17 +364,17 @@ def hrnet_ocr_forward(P, img, prefix="segmentation_model.", bn_training=True, dr
     o = p + "ocr_distri_head.object_context_block."
 
     def seq2(name, t):
-        t = F.relu(_bn(P, o + name + ".1.0", conv2d(t, P[o + name + ".0.weight"], P.get(o + name + ".0.bias")), tr))
-        return F.relu(_bn(P, o + name + ".3.0", conv2d(t, P[o + name + ".2.weight"], P.get(o + name + ".2.bias")), tr))
+        t = _bn(P, o + name + ".1.0", conv2d(t, P[o + name + ".0.weight"], P.get(o + name + ".0.bias")), tr, relu=True)
+        return _bn(P, o + name + ".3.0", conv2d(t, P[o + name + ".2.weight"], P.get(o + name + ".2.bias")), tr, relu=True)
 
     query = seq2("f_pixel", f).view(B, h * w, 256).float()
     key = seq2("f_object", ctx).view(B, 1, 256).float().permute(0, 2, 1)
-    value = F.relu(_bn(P, o + "f_down.1.0", conv2d(ctx, P[o + "f_down.0.weight"], P.get(o + "f_down.0.bias")), tr))
+    value = _bn(P, o + "f_down.1.0", conv2d(ctx, P[o + "f_down.0.weight"], P.get(o + "f_down.0.bias")), tr, relu=True)
     sim = F.softmax((256 ** -0.5) * torch.matmul(query, key), dim=-1)                           # (B, HW, K=1) == 1
     context = torch.matmul(sim, value.view(B, 1, 256).float()).to(torch.bfloat16).view(B, h, w, 256)
-    context = F.relu(_bn(P, o + "f_up.1.0", conv2d(context, P[o + "f_up.0.weight"], P.get(o + "f_up.0.bias")), tr))
+    context = _bn(P, o + "f_up.1.0", conv2d(context, P[o + "f_up.0.weight"], P.get(o + "f_up.0.bias")), tr, relu=True)
     q = p + "ocr_distri_head.conv_bn_dropout."
-    f2 = F.relu(_bn(P, q + "1.0", conv2d(torch.cat((context, f), dim=3), P[q + "0.weight"], P.get(q + "0.bias")), tr))
+    f2 = _bn(P, q + "1.0", conv2d(torch.cat((context, f), dim=3), P[q + "0.weight"], P.get(q + "0.bias")), tr, relu=True)
     f2 = _drop(f2, 0.05, dropout)
     out = to_nchw(conv2d(f2, P[p + "cls_head.weight"], P[p + "cls_head.bias"]), 1)
     up = lambda t: F.interpolate(t, size=(H, W), mode="bilinear", align_corners=True)

@@ -136,6 +136,21 @@ int csbsr_resize_bicubic_aa_bwd(const float* dy, float* dx, int nc, int h, int w
  * mode 2: rows = B, cols = A (ConvTranspose2d forward phases; dgrad of the 8x8/s4 conv). */
 int csbsr_pack_weights(const float* w, void* out, int a, int b, int r, int s, int rows_pad, int cols_pad, int mode, void* stream);
 
+/* BatchNorm2d of the training graph on NHWC bf16 maps [m][pitch] whose first c channels are real (nn.BatchNorm2d in
+ * pspnet_pytorch/extractors.py:52-70, pspnet.py:44-57, hrnet_backbone.py; reference runs them through cuDNN / aten).
+ *   csbsr_bn_stats   : batch mean / rstd (biased variance, eps) into mean[c] / rstd[c]; updates running_mean / running_var with
+ *                      `momentum` and the unbiased variance when they are given; workspace = 2*c floats.
+ *   csbsr_bn_apply   : y = relu?((x - mean) * rstd * gamma + beta + res?)   (res may be NULL; padding channels written as 0)
+ *   csbsr_bn_backward: dy -> dx (+ dres = dy masked by y_relu > 0 when y_relu is given), dgamma[c], dbeta[c] (overwritten);
+ *                      training != 0 subtracts the batch-statistics terms, 0 treats mean / rstd as constants (eval mode). */
+int csbsr_bn_stats(const void* x, int pitch, int c, long long m, float eps, float momentum, float* mean, float* rstd,
+                   float* running_mean, float* running_var, float* workspace, void* stream);
+int csbsr_bn_apply(const void* x, const void* res, void* y, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, int pitch, int c, long long m, int relu, void* stream);
+int csbsr_bn_backward(const void* dy, const void* x, const void* y_relu, const float* mean, const float* rstd, const float* gamma,
+                      int pitch, int c, long long m, int training, void* dx, void* dres, float* dgamma, float* dbeta,
+                      void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound support kernels (csrc/support.cu).  NHWC tensors are bf16 with `*_pitch` channels per
  * pixel and a channel window starting at `*_coff`; planar tensors are fp32 NCHW.

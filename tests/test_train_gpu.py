@@ -310,3 +310,51 @@ def test_resize_aa_fn_vs_torch_autograd():
     yr.backward(up)
     assert (y - yr).abs().max().item() <= 2e-6
     assert (x.grad - xr.grad).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("training,relu,with_res,c,pitch", [
+    (True, True, True, 64, 64), (True, False, False, 48, 64), (False, True, False, 128, 128), (False, False, True, 256, 256),
+    (True, True, False, 1024, 1024),
+])
+def test_batch_norm_fn_vs_torch(training, relu, with_res, c, pitch):
+    """csbsr_bn_stats / _apply / _backward (batch or running statistics, fused residual + ReLU, channel padding) against
+    F.batch_norm + add + relu autograd in fp32 on the same bf16-rounded input."""
+    from csbsr_b200 import autograd as A
+    g = torch.Generator().manual_seed(41)
+    n, h, w = 3, 10, 14
+    x0 = torch.zeros(n, h, w, pitch, dtype=torch.bfloat16)
+    x0[..., :c] = (torch.randn(n, h, w, c, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    r0 = torch.zeros_like(x0)
+    r0[..., :c] = torch.randn(n, h, w, c, generator=g).to(torch.bfloat16)
+    up = torch.zeros_like(x0)
+    up[..., :c] = torch.randn(n, h, w, c, generator=g).to(torch.bfloat16)
+    x0, r0, up = x0.cuda(), r0.cuda(), up.cuda()
+    gam0, bet0 = (0.5 + torch.rand(c, generator=g)).cuda(), (0.1 * torch.randn(c, generator=g)).cuda()
+    rm0, rv0 = (0.1 * torch.randn(c, generator=g)).cuda(), (0.5 + torch.rand(c, generator=g)).cuda()
+
+    x, res = x0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+    gam, bet = gam0.clone().requires_grad_(True), bet0.clone().requires_grad_(True)
+    rm, rv = rm0.clone(), rv0.clone()
+    y = A.batch_norm(x, gam, bet, rm, rv, training, 0.1, 1e-5, relu=relu, res=res if with_res else None)
+    y.backward(up)
+
+    xr = x0[..., :c].float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    rr = r0[..., :c].float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    gr, br = gam0.clone().requires_grad_(True), bet0.clone().requires_grad_(True)
+    rm2, rv2 = rm0.clone(), rv0.clone()
+    yr = F.batch_norm(xr, rm2, rv2, gr, br, training=training, momentum=0.1, eps=1e-5)
+    if with_res:
+        yr = yr + rr
+    if relu:
+        yr = F.relu(yr)
+    yr.backward(up[..., :c].float().permute(0, 3, 1, 2))
+    nchw = lambda t: t[..., :c].float().permute(0, 3, 1, 2)
+    assert (y[..., c:] == 0).all()
+    assert (nchw(y) - yr).abs().max().item() <= 2e-2 * yr.abs().max().item()
+    assert (nchw(x.grad) - xr.grad).abs().max().item() <= 2e-2 * xr.grad.abs().max().item() + 1e-3
+    assert (gam.grad - gr.grad).abs().max().item() <= 1e-2 * gr.grad.abs().max().item()
+    assert (bet.grad - br.grad).abs().max().item() <= 1e-2 * br.grad.abs().max().item()
+    if with_res:
+        assert (nchw(res.grad) - rr.grad).abs().max().item() <= 1e-2 * rr.grad.abs().max().item() + 1e-3
+    if training:
+        assert torch.allclose(rm, rm2, rtol=1e-4, atol=1e-5) and torch.allclose(rv, rv2, rtol=1e-3, atol=1e-5)
