@@ -81,6 +81,8 @@ _SIGNATURES = {
     "csbsr_bn_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_float] + [C.c_void_p] * 6),
     "csbsr_bn_apply": (C.c_int, [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     "csbsr_bn_backward": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_longlong, C.c_int] + [C.c_void_p] * 5),
+    "csbsr_psnr_ssim_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "csbsr_psnr_ssim": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p]),
     "csbsr_prelu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "csbsr_prelu_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
     "csbsr_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong] + [C.c_float] * 4 + [C.c_int, C.c_float, C.c_int,

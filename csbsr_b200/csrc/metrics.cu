@@ -668,3 +668,112 @@ extern "C" int csbsr_seg_metrics(const float* prob, const float* mask, const flo
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// PSNR and SSIM of the SR image (model/utils/estimate_metrics.py:89-100 PSNR, :134-191 SSIM: 11x11 Gaussian window,
+// sigma 1.5, zero padding 5, C1 = 0.01^2, C2 = 0.03^2, per-image mean over (C,H,W)); evaluated by inference_for_ss
+// (model/engine/inference.py:94-100).  One kernel: each block produces a 16x16 tile of the SSIM map of one (image, channel)
+// plane from a 26x26 input tile of both images (separable window in shared memory) and accumulates the per-image sums.
+namespace csbsr {
+
+struct Gauss11 {
+    float v[11];
+};
+
+__global__ void psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int C, int H, int W,
+                                 double* __restrict__ acc /* [B][2]: sum sq diff, sum ssim */, const Gauss11 g11) {
+    constexpr int T = 16, R = 5, P = T + 2 * R;
+    __shared__ float sa[P][P + 1], sb[P][P + 1];
+    __shared__ float hq[5][P][T + 1];
+    __shared__ float sg[11];
+    const int plane = blockIdx.z;                 // image * C + channel
+    const int img = plane / C;
+    const int y0 = blockIdx.y * T, x0 = blockIdx.x * T;
+    const float* ap = a + static_cast<size_t>(plane) * H * W;
+    const float* bp = b + static_cast<size_t>(plane) * H * W;
+    if (threadIdx.x < 11) sg[threadIdx.x] = g11.v[threadIdx.x];
+    for (int i = threadIdx.x; i < P * P; i += blockDim.x) {
+        const int r = i / P, c = i % P;
+        const int yy = y0 + r - R, xx = x0 + c - R;
+        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        sa[r][c] = in ? ap[static_cast<size_t>(yy) * W + xx] : 0.f;
+        sb[r][c] = in ? bp[static_cast<size_t>(yy) * W + xx] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P * T; i += blockDim.x) {          // horizontal pass
+        const int r = i / T, c = i % T;
+        float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            const float u = sa[r][c + k], v = sb[r][c + k], w = sg[k];
+            m1 = fmaf(w, u, m1); m2 = fmaf(w, v, m2);
+            s11 = fmaf(w, u * u, s11); s22 = fmaf(w, v * v, s22); s12 = fmaf(w, u * v, s12);
+        }
+        hq[0][r][c] = m1; hq[1][r][c] = m2; hq[2][r][c] = s11; hq[3][r][c] = s22; hq[4][r][c] = s12;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / T, tx = threadIdx.x % T;          // 256 threads = 16 x 16 outputs
+    double ssim = 0.0, sq = 0.0;
+    if (y0 + ty < H && x0 + tx < W) {
+        float q[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            const float w = sg[k];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) q[j] = fmaf(w, hq[j][ty + k][tx], q[j]);
+        }
+        const float mu1 = q[0], mu2 = q[1];
+        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+        const float s1 = q[2] - mu1_sq, s2 = q[3] - mu2_sq, s12 = q[4] - mu12;
+        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+        ssim = ((2.f * mu12 + C1) * (2.f * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2));
+        const float d = sa[ty + R][tx + R] - sb[ty + R][tx + R];
+        sq = static_cast<double>(d) * d;
+    }
+    ssim = warp_sum(ssim);
+    sq = warp_sum(sq);
+    __shared__ double red[2][8];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][wp] = sq; red[1][wp] = ssim; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+        atomicAdd(&acc[img * 2 + threadIdx.x], t);
+    }
+}
+
+__global__ void psnr_ssim_finish_kernel(const double* __restrict__ acc, double* __restrict__ psnr, double* __restrict__ ssim, int B,
+                                        double n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float mse = static_cast<float>(acc[i * 2] / n);          // the reference reduces in fp32 (torch.mean)
+    psnr[i] = static_cast<double>(10.f * log10f(1.f / mse));
+    ssim[i] = static_cast<double>(static_cast<float>(acc[i * 2 + 1] / n));
+}
+
+}  // namespace csbsr
+
+extern "C" size_t csbsr_psnr_ssim_workspace_bytes(int b) { return sizeof(double) * 2 * static_cast<size_t>(b); }
+
+extern "C" int csbsr_psnr_ssim(const float* pred, const float* target, int b, int c, int h, int w, double* psnr, double* ssim,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CSBSR_REQUIRE(pred && target && psnr && ssim && workspace && b > 0 && c > 0 && h > 0 && w > 0, "psnr_ssim: bad arguments");
+    CSBSR_REQUIRE(workspace_bytes >= csbsr_psnr_ssim_workspace_bytes(b), "psnr_ssim: workspace too small");
+    double* acc = static_cast<double*>(workspace);
+    CSBSR_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * b, stream));
+    // gaussian(11, 1.5) of estimate_metrics.py:140-142: exp(-(x-5)^2 / (2 sigma^2)) in double, normalised as fp32
+    Gauss11 g11;
+    float* hg = g11.v;
+    double gs[11];
+    for (int i = 0; i < 11; ++i) gs[i] = exp(-static_cast<double>((i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5));
+    float fsum = 0.f;
+    for (int i = 0; i < 11; ++i) { hg[i] = static_cast<float>(gs[i]); fsum += hg[i]; }
+    for (int i = 0; i < 11; ++i) hg[i] = hg[i] / fsum;
+    dim3 grid((w + 15) / 16, (h + 15) / 16, b * c);
+    psnr_ssim_kernel<<<grid, 256, 0, stream>>>(pred, target, c, h, w, acc, g11);
+    psnr_ssim_finish_kernel<<<(b + 127) / 128, 128, 0, stream>>>(acc, psnr, ssim, b, static_cast<double>(c) * h * w);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

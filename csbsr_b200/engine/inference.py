@@ -86,11 +86,44 @@ def calc_distance_metrics(segment_preds, gts, num_hd_outliner=0, num_msd_outline
 
 
 # ------------------------------------------------------------------ evaluation loop (host glue around the kernels)
+def psnr_ssim(pred, target):
+    """PSNR()(pred, target) and SSIM()(pred, target) of the reference (model/utils/estimate_metrics.py:89-100, 134-191) for
+    [B,C,H,W] tensors in [0,1]: one csbsr_psnr_ssim launch -> (psnr float64 [B], ssim float64 [B]) numpy arrays."""
+    import ctypes as C
+    dev = torch.device("cuda", torch.cuda.current_device())
+    a = pred.to(device=dev, dtype=torch.float32).contiguous()
+    b = target.to(device=dev, dtype=torch.float32).contiguous()
+    n, c, h, w = a.shape
+    out = torch.empty(2, n, dtype=torch.float64, device=dev)
+    L = _lib.lib()
+    nb = L.csbsr_psnr_ssim_workspace_bytes(n)
+    ws = torch.empty(max(int(nb), 8), dtype=torch.uint8, device=dev)
+    _lib.check(L.csbsr_psnr_ssim(a.data_ptr(), b.data_ptr(), n, c, h, w, out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(),
+                                 C.c_size_t(nb), _lib.stream_ptr()), "csbsr_psnr_ssim")
+    _lib.count_launch("csbsr_psnr_ssim")
+    res = out.cpu().numpy()
+    return res[0], res[1]
+
+
 def psnr_per_image(pred, target):
-    """PSNR of [0,1] images per sample: 10*log10(1/mse) (model/utils/estimate_metrics.py:89-100); torch reductions on
-    the device are plumbing here, the hot path stays in the C-ABI kernels."""
-    mse = ((pred.float() - target.to(pred.device).float()) ** 2).flatten(1).mean(1)
-    return (10.0 * torch.log10(1.0 / mse)).cpu().numpy()
+    return psnr_ssim(pred, target)[0]
+
+
+class PSNR:
+    """Drop-in for estimate_metrics.PSNR (returns a numpy array per image)."""
+    name = "PSNR"
+
+    def __call__(self, img1, img2):
+        return psnr_ssim(img1, img2)[0].astype(np.float32)
+
+
+class SSIM:
+    """Drop-in for estimate_metrics.SSIM(window_size=11, size_average=False)."""
+
+    def __call__(self, img1, img2):
+        return psnr_ssim(img1, img2)[1].astype(np.float32)
+
+    forward = __call__
 
 
 def inference_for_ss(model, loader, test_surface_distance=True, percent=HD_PERCENTILE, output_dir=None, log=print):
@@ -100,12 +133,14 @@ def inference_for_ss(model, loader, test_surface_distance=True, percent=HD_PERCE
     Under torch.distributed every rank evaluates its own loader shard; results are gathered on all ranks."""
     import os
     from . import distributed as D
-    rows, fnames, psnrs, kpsnrs = [], [], [], []
+    rows, fnames, psnrs, kpsnrs, ssims = [], [], [], [], []
     n_hd_out = 0
     for it, (imgs, sr_targets, masks, kernel_targets, names) in enumerate(loader, 1):
         sr, seg, kp = model(imgs, torch.zeros(imgs.shape[0], 1, model.blur_ksize, model.blur_ksize), sr_targets=sr_targets)
-        psnrs.append(psnr_per_image(sr, sr_targets))
-        kpsnrs.append(psnr_per_image(kp.clamp(0, 1), kernel_targets))
+        ps, ss = psnr_ssim(sr, sr_targets)                              # inference.py:96-97
+        psnrs.append(ps)
+        ssims.append(ss)
+        kpsnrs.append(psnr_per_image(kp, kernel_targets))                 # inference.py:100
         r = seg_metrics(seg, masks, with_hd=test_surface_distance, percent=percent, to_host=False)
         hd = r["hd"] if test_surface_distance else torch.zeros_like(r["inter"], dtype=torch.float64)
         msd = r["msd"] if test_surface_distance else torch.zeros_like(hd)
@@ -117,11 +152,13 @@ def inference_for_ss(model, loader, test_surface_distance=True, percent=HD_PERCE
     inter, union, hd, msd = D.unpack_metrics(packed)
     iou = (inter + 1e-5) / (union + 1e-5)
     out = {"AIU": float(np.mean(iou)), "IoU_max": float(np.max(np.mean(iou, axis=0))), "iou": iou,
-           "PSNR": float(np.mean(np.concatenate(psnrs))), "PSNR_kernel": float(np.mean(np.concatenate(kpsnrs)))}
+           "PSNR": float(np.mean(np.concatenate(psnrs))), "SSIM": float(np.mean(np.concatenate(ssims))),
+           "PSNR_kernel": float(np.mean(np.concatenate(kpsnrs)))}
     if test_surface_distance:
         out.update({"AHD": float(np.mean(hd)), "HD_min": float(np.min(np.mean(hd, axis=0))), "AMSD": float(np.mean(msd)),
                     "hd": hd, "msd": msd})
-    log("estimation finish!!  PSNR_mean:%.4f PSNR(Kernel)_mean:%.4f AIU_mean:%.4f" % (out["PSNR"], out["PSNR_kernel"], out["AIU"])
+    log("estimation finish!!  PSNR_mean:%.4f  SSIM_mean:%.4f PSNR(Kernel)_mean:%.4f AIU_mean:%.4f"
+        % (out["PSNR"], out["SSIM"], out["PSNR_kernel"], out["AIU"])
         + ("  HD%d_mean:%.4f MSD_mean:%.4f" % (percent, out["AHD"], out["AMSD"]) if test_surface_distance else ""))
     rank, _ = D.world()
     if output_dir and rank == 0:

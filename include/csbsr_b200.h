@@ -283,6 +283,13 @@ int csbsr_seg_metrics(const float* prob, const float* mask, const float* thresho
                       long long* inter, long long* uni, double* hd, double* msd, double percent, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* PSNR = 10*log10(1/mse) and SSIM (11x11 Gaussian window, sigma 1.5, zero padding, C1 = 1e-4, C2 = 9e-4) per image of two
+ * fp32 [b,c,h,w] tensors in [0,1]: PSNR.__call__ / SSIM.forward of model/utils/estimate_metrics.py:89-100,134-191 as used by
+ * inference_for_ss (model/engine/inference.py:94-100).  psnr / ssim: DEVICE double[b]. */
+size_t csbsr_psnr_ssim_workspace_bytes(int b);
+int csbsr_psnr_ssim(const float* pred, const float* target, int b, int c, int h, int w, double* psnr, double* ssim,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,3 +118,31 @@ def distance_metrics(prob, mask, percent=50):
             else:
                 msd[i, j] = (np.sum(d_g2p * a_g) / np.sum(a_g) + np.sum(d_p2g * a_p) / np.sum(a_p)) / 2
     return hd, msd
+
+
+def psnr(img1, img2):
+    """PSNR.__call__ (model/utils/estimate_metrics.py:89-100): 10*log10(1/mse), mse over (C,H,W) per image, fp32 torch."""
+    import torch
+    a, b = torch.as_tensor(img1).float(), torch.as_tensor(img2).float()
+    mse = torch.mean((a - b) ** 2, [1, 2, 3])
+    return (10 * torch.log10(1 / mse)).numpy().copy()
+
+
+def ssim(img1, img2, window_size=11, sigma=1.5):
+    """SSIM.forward / _ssim with size_average=False (estimate_metrics.py:134-191): Gaussian window = outer product of the
+    normalised 1-D window, depthwise conv with zero padding window_size//2, C1 = 0.01^2, C2 = 0.03^2, mean over (C,H,W)."""
+    import math
+    import torch
+    import torch.nn.functional as F
+    a, b = torch.as_tensor(img1).float(), torch.as_tensor(img2).float()
+    c = a.shape[1]
+    g = torch.Tensor([math.exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)])
+    g = (g / g.sum()).unsqueeze(1)
+    window = g.mm(g.t()).float().unsqueeze(0).unsqueeze(0).expand(c, 1, window_size, window_size).contiguous()
+    conv = lambda t: F.conv2d(t, window, padding=window_size // 2, groups=c)
+    mu1, mu2 = conv(a), conv(b)
+    mu1_sq, mu2_sq, mu12 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1, s2, s12 = conv(a * a) - mu1_sq, conv(b * b) - mu2_sq, conv(a * b) - mu12
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    m = ((2 * mu12 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))
+    return m.mean(1).mean(1).mean(1).numpy().copy()

@@ -195,6 +195,18 @@ if __name__ == "__main__":
         gen_joint(hrnet=True)
 
 
+def gen_psnr_ssim():
+    """PSNR / SSIM classes of the reference (model/utils/estimate_metrics.py) on seeded images."""
+    rh.setup()
+    from model.utils.estimate_metrics import PSNR, SSIM
+    g = torch.Generator().manual_seed(51)
+    a = torch.rand(3, 3, 40, 56, generator=g)
+    b = (a + 0.05 * torch.randn(3, 3, 40, 56, generator=g)).clamp(0, 1)
+    b[2] = torch.nn.functional.avg_pool2d(a[2:3], 5, 1, 2)[0]
+    np.savez_compressed(os.path.join(HERE, "psnr_ssim.npz"), a=a.numpy(), b=b.numpy(), psnr=PSNR()(a, b), ssim=SSIM()(a, b))
+    print("psnr_ssim.npz", PSNR()(a, b), SSIM()(a, b))
+
+
 def gen_train(bn_eval=False, hrnet=False, iteration=40000):
     """One JointModelWithLoss forward + backward of the UNMODIFIED reference at iteration 40000 (all phases active,
     w^F on, m^F = 1), Dropout2d disabled (p = 0) so the step is deterministic: losses and a sample of gradients.
@@ -285,6 +297,9 @@ def gen_train(bn_eval=False, hrnet=False, iteration=40000):
     np.savez_compressed(os.path.join(HERE, fname), **out)
     print("train_step.npz loss", loss.item(), "seg", seg_loss.mean().item(), "sr", sr_loss.detach().numpy(), "grads", len(norms))
 
+
+if __name__ == "__main__" and "psnr" in sys.argv[1:]:
+    gen_psnr_ssim()
 
 if __name__ == "__main__" and "train" in sys.argv[1:]:
     if "pretrain" in sys.argv[1:]:

@@ -134,3 +134,19 @@ def test_degrade_matches_golden_and_oracle():
     b = G.conv_kernel2d(img, k)
     assert np.abs(b.cpu().numpy() - D.blur(img, k.cpu()).numpy()).max() <= 2e-6
     assert np.abs(G.FactorResize(4, "bicubic")(b).cpu().numpy() - D.downsample(b.cpu()).numpy()).max() <= 2e-6
+
+
+def test_psnr_ssim_kernel_vs_reference_golden_and_oracle():
+    """csbsr_psnr_ssim against the reference's PSNR / SSIM outputs and, on a 448^2 batch, the oracle (fp32: 2e-4 dB / 2e-5)."""
+    import os
+    from csbsr_b200.engine import inference as E
+    from oracle import metrics_ref as M
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "psnr_ssim.npz"))
+    ps, ss = E.psnr_ssim(torch.from_numpy(g["a"]), torch.from_numpy(g["b"]))
+    assert np.abs(ps - g["psnr"]).max() <= 2e-4 and np.abs(ss - g["ssim"]).max() <= 2e-5
+    gen = torch.Generator().manual_seed(3)
+    a = torch.rand(2, 3, 448, 448, generator=gen)
+    b = (a + 0.02 * torch.randn(2, 3, 448, 448, generator=gen)).clamp(0, 1)
+    ps, ss = E.psnr_ssim(a, b)
+    assert np.abs(ps - M.psnr(a, b)).max() <= 2e-4 and np.abs(ss - M.ssim(a, b)).max() <= 2e-5
+    assert np.allclose(E.SSIM()(a, a), 1.0, atol=1e-6)

@@ -258,3 +258,11 @@ def test_train_oracle_matches_reference_golden(variant):
         assert cos >= 0.9995 and np.abs(got - ref).max() <= 0.1 * np.abs(ref).max(), (k, cos)
         if k in ("segmentation_model.final.0.weight", "segmentation_model.aux.4.bias", "segmentation_model.cls_head.weight"):
             assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-7, k
+
+
+def test_psnr_ssim_oracle_matches_reference_golden():
+    """oracle/metrics_ref.py psnr / ssim against the reference's PSNR / SSIM classes (tests/golden/psnr_ssim.npz)."""
+    from oracle import metrics_ref as M
+    g = np.load(os.path.join(GOLD, "psnr_ssim.npz"))
+    assert np.abs(M.psnr(g["a"], g["b"]) - g["psnr"]).max() <= 1e-5
+    assert np.abs(M.ssim(g["a"], g["b"]) - g["ssim"]).max() <= 1e-6
