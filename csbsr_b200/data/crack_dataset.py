@@ -46,6 +46,50 @@ class CrackDataSetTest(torch.utils.data.Dataset):
         return lr, hr, mask, kernel, name
 
 
+class CrackDataSet(torch.utils.data.Dataset):
+    """Training set reader (reference CrackDataSet, model/data/crack_dataset.py:28-69, with the TrainTransforms of
+    config_csbsr_pspnet.yaml: ConvertFromInts, RandomMirror, ToTensor, RandomVerticalFlip(0.3), RandomCrop, /255 --
+    data_preprocess.py:13-46, transforms.py:356-362, 534-549, 738-748).  Returns the HR crop and its mask; the blur, the
+    x4 downscale and the blur-kernel target are produced on the GPU for the whole batch by the trainer
+    (csbsr_degrade with theta ~ U(0, 180) deg, sigma ~ U(0.2, 4) per sample, blur.py:128-179, 207-238)."""
+
+    def __init__(self, cfg, image_dir=None, seg_dir=None, seed=None):
+        from pathlib import Path
+        self.image_dir = image_dir or cfg.DATASET.TRAIN_IMAGE_DIR
+        self.seg_dir = seg_dir or cfg.DATASET.TRAIN_MASK_DIR
+        self.fnames = sorted(path.name for path in Path(self.image_dir).glob("*.jpg"))
+        self.size = tuple(cfg.INPUT.IMAGE_SIZE)
+        self.vflip_p = 0.3
+        for name, arg in cfg.DATASET.DATA_AUGMENTATION:
+            if name == "RandomVerticalFlip":
+                self.vflip_p = float(arg)
+        self.rng = np.random.default_rng(seed)
+
+    def __len__(self):
+        return len(self.fnames)
+
+    def __getitem__(self, i):
+        from PIL import Image
+        fname = self.fnames[i]
+        img = np.array(Image.open(os.path.join(self.image_dir, fname))).astype(np.float32)            # H x W x 3
+        seg = np.array(Image.open(os.path.join(self.seg_dir, fname))).astype(np.float32)
+        if seg.ndim == 2:
+            seg = seg[:, :, None]
+        if self.rng.integers(2):                                       # RandomMirror
+            img, seg = img[:, ::-1], seg[:, ::-1]
+        if self.vflip_p <= self.rng.random():                          # RandomVerticalFlip: flips when p <= rand (sic)
+            img, seg = img[::-1], seg[::-1]
+        h, w = img.shape[:2]
+        th, tw = self.size
+        if h < th or w < tw:
+            raise ValueError("image %s (%dx%d) is smaller than the crop %dx%d" % (fname, h, w, th, tw))
+        y0 = int(self.rng.integers(0, h - th + 1))                     # RandomCrop.get_params
+        x0 = int(self.rng.integers(0, w - tw + 1))
+        img = np.ascontiguousarray(img[y0:y0 + th, x0:x0 + tw])
+        seg = np.ascontiguousarray(seg[y0:y0 + th, x0:x0 + tw])
+        return (torch.from_numpy(img).permute(2, 0, 1) / 255, torch.from_numpy(seg[:, :, :1]).permute(2, 0, 1) / 255)
+
+
 class SyntheticCrackTestSet(torch.utils.data.Dataset):
     """Seeded synthetic crack images degraded on the fly by the device kernels (utils/synth.py + data/degrade.py)."""
 

@@ -266,3 +266,23 @@ def test_psnr_ssim_oracle_matches_reference_golden():
     g = np.load(os.path.join(GOLD, "psnr_ssim.npz"))
     assert np.abs(M.psnr(g["a"], g["b"]) - g["psnr"]).max() <= 1e-5
     assert np.abs(M.ssim(g["a"], g["b"]) - g["ssim"]).max() <= 1e-6
+
+
+def test_crack_dataset_reader_on_a_tiny_image_folder(tmp_path):
+    """Training reader: jpg + mask folder -> [3,h,w] / [1,h,w] crops in [0,1] with the config's flips and crop size."""
+    from PIL import Image
+    from csbsr_b200.config import cfg
+    from csbsr_b200.data.crack_dataset import CrackDataSet
+    c = cfg.clone()
+    c.merge_from_file(os.path.join(os.path.dirname(GOLD), "..", "config", "config_csbsr_pspnet.yaml"))
+    img_dir, seg_dir = tmp_path / "images", tmp_path / "masks"
+    img_dir.mkdir(); seg_dir.mkdir()
+    rng = np.random.default_rng(0)
+    for i in range(3):
+        Image.fromarray(rng.integers(0, 256, (260, 300, 3), dtype=np.uint8)).save(img_dir / ("im%d.jpg" % i))
+        Image.fromarray(((rng.random((260, 300)) > 0.9) * 255).astype(np.uint8)).save(seg_dir / ("im%d.jpg" % i))
+    ds = CrackDataSet(c, str(img_dir), str(seg_dir), seed=1)
+    assert len(ds) == 3
+    hr, mask = ds[1]
+    assert tuple(hr.shape) == (3, 224, 224) and tuple(mask.shape) == (1, 224, 224)
+    assert hr.dtype == torch.float32 and 0 <= hr.min() and hr.max() <= 1 and 0 <= mask.min() and mask.max() <= 1

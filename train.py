@@ -45,8 +45,6 @@ def main():
     if args.output_dirname:
         cfg.OUTPUT_DIR = args.output_dirname
     cfg.freeze()
-    if not args.synthetic:
-        raise NotImplementedError("the image-folder training set reader is not built yet: use --synthetic N")
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -56,7 +54,14 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.manual_seed(cfg.SEED)
 
-    model = JointModelWithLoss(cfg, num_train_ds=args.synthetic, resume_iter=args.resume_iter)
+    dataset = None
+    if not args.synthetic:
+        from csbsr_b200.data.crack_dataset import CrackDataSet
+        dataset = CrackDataSet(cfg, seed=cfg.SEED + rank)
+        n_train = int(len(dataset) * cfg.SOLVER.TRAIN_DATASET_RATIO)     # train.py:52 (the rest is the validation split)
+        if n_train == 0:
+            raise FileNotFoundError("no *.jpg images under %s (use --synthetic N to train offline)" % dataset.image_dir)
+    model = JointModelWithLoss(cfg, num_train_ds=args.synthetic or n_train, resume_iter=args.resume_iter)
     ckpt = os.path.join(cfg.OUTPUT_DIR, "model", "iteration_{}.pth".format(args.resume_iter))
     if args.resume_iter > 0 and os.path.exists(ckpt):
         sd = torch.load(ckpt, map_location="cpu")
@@ -78,8 +83,12 @@ def main():
 
     def batches():
         for it in range(args.resume_iter + 1, max_iter + 1):
-            idx = rng.integers(0, args.synthetic, size=per_rank)
-            hr, mask = zip(*(synth.crack_image(int(i), size) for i in idx))
+            if dataset is not None:
+                idx = rng.integers(0, n_train, size=per_rank)
+                hr, mask = zip(*(dataset[int(i)] for i in idx))
+            else:
+                idx = rng.integers(0, args.synthetic, size=per_rank)
+                hr, mask = zip(*(synth.crack_image(int(i), size) for i in idx))
             theta = rng.uniform(0, 180, per_rank) * np.pi / 180.0
             sig = rng.uniform(0.2, 4.0, (per_rank, 2))
             params = np.concatenate([theta[:, None], sig], axis=1)
