@@ -38,7 +38,7 @@ def launch_summary(path, tag, n_img):
     tot = sum(t.values())
     lines = ["# ncu launch list summary (%s)" % tag, "",
              "Command: `ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 1 --batch 16 "
-             "--no-cpu-baseline --train-steps 1` (cold-cache, serialised launches: compare SHARES, not absolute times).",
+             "--no-cpu-baseline --train-steps 1 --no-graph` (cold-cache, serialised launches: compare SHARES, not absolute times).",
              "The run executes %d images through the eval hot path (3 warm-up + 1 timed + 2 e2e + 1 roofline step of 16) and then "
              "4 joint training steps (3 warm-up + 1 timed; batch 8, 224^2 crops): `conv_wgrad_kernel`, `adam_kernel`, `prelu_*` and "
              "the `at::native` glue kernels belong to the training leg; `us / image` divides by the eval images only. DRAM columns "
