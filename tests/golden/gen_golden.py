@@ -195,6 +195,29 @@ if __name__ == "__main__":
         gen_joint(hrnet=True)
 
 
+def gen_alpha_schedule():
+    """alpha of BoundaryComboLoss over 40 update_alpha() calls (loss_functions.py:26-41, 76-81) for two resume points."""
+    rh.setup()
+    import contextlib, io
+    from model.utils.loss_functions import BoundaryComboLoss
+    out = {}
+    for tag, (per_epoch, resume, ratio) in {"a": (7, 0, 1.0), "b": (5, 23, 2.0)}.items():
+        with contextlib.redirect_stdout(io.StringIO()):
+            fn = BoundaryComboLoss(per_epoch=per_epoch, resume_iter=resume, decrease_ratio=ratio)
+        seq = [fn.alpha]
+        for i in range(40):
+            if i == 20:
+                fn.fix_alpha = True
+            if i == 26:
+                fn.fix_alpha = False
+            fn.update_alpha()
+            seq.append(fn.alpha)
+        out["alpha_" + tag] = np.array(seq, dtype=np.float64)
+        out["cfg_" + tag] = np.array([per_epoch, resume, ratio], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "alpha_schedule.npz"), **out)
+    print("alpha_schedule.npz", out["alpha_a"][:10], out["alpha_b"][:10])
+
+
 def gen_psnr_ssim():
     """PSNR / SSIM classes of the reference (model/utils/estimate_metrics.py) on seeded images."""
     rh.setup()
@@ -300,6 +323,9 @@ def gen_train(bn_eval=False, hrnet=False, iteration=40000):
 
 if __name__ == "__main__" and "psnr" in sys.argv[1:]:
     gen_psnr_ssim()
+
+if __name__ == "__main__" and "alpha" in sys.argv[1:]:
+    gen_alpha_schedule()
 
 if __name__ == "__main__" and "train" in sys.argv[1:]:
     if "pretrain" in sys.argv[1:]:

@@ -286,3 +286,39 @@ def test_crack_dataset_reader_on_a_tiny_image_folder(tmp_path):
     hr, mask = ds[1]
     assert tuple(hr.shape) == (3, 224, 224) and tuple(mask.shape) == (1, 224, 224)
     assert hr.dtype == torch.float32 and 0 <= hr.min() and hr.max() <= 1 and 0 <= mask.min() and mask.max() <= 1
+
+
+def test_boundary_alpha_schedule_matches_reference():
+    """BoundaryComboSchedule (the attributes the trainer pokes) against the reference class's alpha sequence."""
+    from csbsr_b200.modeling.build_model import BoundaryComboSchedule
+    g = np.load(os.path.join(GOLD, "alpha_schedule.npz"))
+    for tag in ("a", "b"):
+        per_epoch, resume, ratio = g["cfg_" + tag]
+        fn = BoundaryComboSchedule(int(per_epoch), int(resume), decrease_ratio=float(ratio))
+        seq = [fn.alpha]
+        for i in range(40):
+            if i == 20:
+                fn.fix_alpha = True
+            if i == 26:
+                fn.fix_alpha = False
+            fn.update_alpha()
+            seq.append(fn.alpha)
+        assert np.array_equal(np.array(seq), g["alpha_" + tag])
+
+
+@pytest.mark.parametrize("it", [5, 15000, 20000, 25000, 40000])
+def test_training_phase_switches_match_reference(it):
+    """JointModelWithLoss.apply_phase: the set of trainable parameters per iteration equals the reference's after its
+    KBPN / KBlock _pretrain_check (fixtures record requires_grad of every parameter after one forward)."""
+    from csbsr_b200.config import cfg
+    from csbsr_b200.modeling.build_model import JointModelWithLoss
+    name = "train_step_bneval.npz" if it == 40000 else "train_step_it%d.npz" % it
+    g = np.load(os.path.join(GOLD, name))
+    if "requires_grad_names" not in g.files:
+        pytest.skip("fixture predates the requires_grad record")
+    c = cfg.clone()
+    c.merge_from_file(os.path.join(os.path.dirname(GOLD), "..", "config", "config_csbsr_pspnet.yaml"))
+    m = JointModelWithLoss(c, num_train_ds=100, resume_iter=it)
+    m.apply_phase(it)
+    mine = sorted(k for k, p in m.named_parameters() if p.requires_grad)
+    assert mine == sorted(str(k) for k in g["requires_grad_names"])
