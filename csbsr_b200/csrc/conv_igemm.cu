@@ -53,6 +53,8 @@ struct ConvKParams {
     int tiles_h, tiles_w, m_tiles, n_tiles, nphases, total_tiles;
     int TH, TW, block_n, kchunks, ntaps, stride, stages;
     int kb;              // K elements per pipeline chunk: 64 (128B swizzle rows), 32 (64B) or 16 (32B)
+    int cluster;         // 1, or 2: CTA pairs work on neighbouring pixel tiles of the same (n tile, phase) and each loads
+                         // half of every weight tile, multicast to both (halves the L2 -> SM weight traffic)
     int OH, OW, os, YH, YW, N;
     int out_mode, y_pitch, y_coff, cout_store;
     int bias_sn, bias_sc, cls_bw, act;
@@ -75,10 +77,18 @@ struct ConvKParams {
 };
 
 // tile index -> (n tile, phase, image, first output row / column); tiles are ordered n fastest, then phase, then m
-__device__ __forceinline__ void decode_tile(const ConvKParams& p, int tile, int& nt, int& ph, int& img, int& oh0, int& ow0) {
+// In cluster mode `tile` counts PAIRS of pixel tiles and the CTA of rank `crank` takes pixel tile 2*pair + crank; a pair's
+// second tile may not exist: it is mapped to image N (all its loads and TMA stores fall outside the tensors).
+__device__ __forceinline__ void decode_tile(const ConvKParams& p, int tile, uint32_t crank, int& nt, int& ph, int& img, int& oh0,
+                                            int& ow0) {
     uint32_t rest, mt, tr, a, b, c, d2;
     fast_divmod(static_cast<uint32_t>(tile), p.fd_ntiles, rest, a);
     fast_divmod(rest, p.fd_nphases, mt, b);
+    if (p.cluster == 2) mt = 2 * mt + crank;
+    if (mt >= static_cast<uint32_t>(p.m_tiles)) {
+        nt = static_cast<int>(a); ph = static_cast<int>(b); img = p.N; oh0 = 0; ow0 = 0;
+        return;
+    }
     fast_divmod(mt, p.fd_tiles_per_img, c, tr);
     uint32_t trh;
     fast_divmod(tr, p.fd_tiles_w, trh, d2);
@@ -341,6 +351,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    uint32_t crank = 0;
+    if (p.cluster == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int wid = blockIdx.x / p.cluster;                    // work stream of this CTA (cluster index)
+    const int wstep = gridDim.x / p.cluster;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -353,7 +367,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], p.cluster);               // cluster mode: released by the MMAs of both CTAs
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
@@ -365,6 +379,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 2) tmem_alloc(tmem_ptr_smem, kTmemCols);
     tcgen05_fence_before();
     __syncthreads();
+    if (p.cluster == 2) {                                      // the peer's barriers must exist before anything remote lands
+        asm volatile("barrier.cluster.arrive.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+    }
     tcgen05_fence_after();
     // The CTA allocates all 512 TMEM columns, so the allocation starts at column 0 / lane 0.  Using the literal 0
     // keeps every TMEM address warp-uniform for the compiler: with a value loaded from shared memory each
@@ -383,10 +401,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = p.a_stage_bytes + b_stage_bytes;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = wid; tile < p.total_tiles; tile += wstep) {
                 int nt, ph, img, oh0, ow0;
-                decode_tile(p, tile, nt, ph, img, oh0, ow0);
-                if (p.trace && blockIdx.x == 0 && lane == 0 && tile / gridDim.x < 256) p.trace[0 * 256 + tile / gridDim.x] = clock64();
+                decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
+                if (p.trace && blockIdx.x == 0 && lane == 0 && tile / wstep < 256) p.trace[0 * 256 + tile / wstep] = clock64();
                 for (int g = 0; g < p.ngroups; ++g) {
                     const int gi = (ph * p.ngroups + g) * p.G;          // first tap of the group
                     const int ih0 = oh0 * p.stride + p.dh[gi];
@@ -398,9 +416,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             // one A box covers the G vertically shifted taps of the group (rows TH + (G-1)*dstep)
                             tma_load_4d(smem_u32(smem_a + stage * p.a_stage_bytes), &tmA, &full_bar[stage],
                                         kc * p.kb, iw0, ih0, img);
-                            for (int j = 0; j < p.G; ++j)
-                                tma_load_3d(smem_u32(smem_b + stage * b_stage_bytes + j * b_tile_bytes), &tmB,
-                                            &full_bar[stage], kc * p.kb, nt * p.block_n, p.widx[gi + j]);
+                            if (p.cluster == 2) {
+                                // this CTA fetches its half of every weight tile and multicasts it to both CTAs of the pair
+                                const int half_rows = p.block_n >> 1;
+                                const uint32_t half_off = crank * static_cast<uint32_t>(half_rows * p.kb * 2);
+                                for (int j = 0; j < p.G; ++j)
+                                    tma_load_3d_mc(smem_u32(smem_b + stage * b_stage_bytes + j * b_tile_bytes) + half_off, &tmB,
+                                                   &full_bar[stage], kc * p.kb, nt * p.block_n + static_cast<int>(crank) * half_rows,
+                                                   p.widx[gi + j], 0x3);
+                            } else {
+                                for (int j = 0; j < p.G; ++j)
+                                    tma_load_3d(smem_u32(smem_b + stage * b_stage_bytes + j * b_tile_bytes), &tmB,
+                                                &full_bar[stage], kc * p.kb, nt * p.block_n, p.widx[gi + j]);
+                            }
                         }
                         __syncwarp();
                         if (++stage == p.stages) {
@@ -431,7 +459,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int stage = 0;
             uint32_t phase = 0, a_lo = a_lo0, b_lo = b_lo0;
             int local = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+            for (int tile = wid; tile < p.total_tiles; tile += wstep, ++local) {
                 const int as = local & 1;
                 const uint32_t aphase = (local >> 1) & 1;
                 mbar_wait(&tmem_empty[as], aphase ^ 1u, p.err_flag, 2);
@@ -461,7 +489,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             ja += a_shift16;
                             jb += b_tile16;
                         }
-                        umma_commit(&empty_bar[stage]);      // frees the smem slot when these MMAs retire
+                        if (p.cluster == 2) umma_commit_mc(&empty_bar[stage], 0x3);   // frees the slot in both CTAs of the pair
+                        else umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                         if (kb == kblocks - 1) umma_commit(&tmem_full[as]);
                     }
                     __syncwarp();
@@ -501,7 +530,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int as = team;
             auto load_residual = [&](int tile) {
                 int nt, ph, img, oh0, ow0;
-                decode_tile(p, tile, nt, ph, img, oh0, ow0);
+                decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
                 mbar_arrive_expect_tx(&res_full[as], res_bytes);
                 for (int pn = 0; pn < n_panels; ++pn) {
                     const uint32_t dst = smem_u32(stage_set + pn * kATileBytes);
@@ -510,15 +539,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     else tma_load_5d(dst, &tmR, &res_full[as], c, p.oow[ph], ow0, p.ooh[ph], img * p.OH + oh0);
                 }
             };
-            const int stride_tiles = 2 * gridDim.x;
-            const int first_tile = blockIdx.x + team * gridDim.x;
+            const int stride_tiles = 2 * wstep;
+            const int first_tile = wid + team * wstep;
             if (leader && p.res_mode && first_tile < p.total_tiles) load_residual(first_tile);
             int n_use = 0;                                  // how many tiles this team has processed
             for (int tile = first_tile; tile < p.total_tiles; tile += stride_tiles, ++n_use) {
                 const uint32_t aphase = n_use & 1;
                 const int local = 2 * n_use + team;
                 int nt, ph, img, oh0, ow0;
-                decode_tile(p, tile, nt, ph, img, oh0, ow0);
+                decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
                 if (p.res_mode) {
                     mbar_wait(&res_full[as], aphase, p.err_flag, 5);
                 } else {
@@ -531,7 +560,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (p.cls_bw > 0)
                     cls = border_class(min(oy, p.YH - 1), p.YH, p.cls_bw) * (2 * p.cls_bw + 1) +
                           border_class(min(ox, p.YW - 1), p.YW, p.cls_bw);
-                const float* bias_row = p.bias ? p.bias + static_cast<size_t>(img) * p.bias_sn +
+                const float* bias_row = p.bias ? p.bias + static_cast<size_t>(min(img, p.N - 1)) * p.bias_sn +
                                                      static_cast<size_t>(cls) * p.bias_sc
                                                : nullptr;
                 mbar_wait(&tmem_full[as], aphase, p.err_flag, 4);
@@ -570,21 +599,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (leader) tma_store_wait_read<0>();
         } else {
         int local = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+        for (int tile = wid; tile < p.total_tiles; tile += wstep, ++local) {
             const int as = local & 1;
             const uint32_t aphase = (local >> 1) & 1;
             int nt, ph, img, oh0d, ow0d;
-            decode_tile(p, tile, nt, ph, img, oh0d, ow0d);
+            decode_tile(p, tile, crank, nt, ph, img, oh0d, ow0d);
             const int oh = oh0d + th;
             const int ow = ow0d + tw;
-            const bool valid = (oh < p.OH) && (ow < p.OW);
+            const bool valid = (oh < p.OH) && (ow < p.OW) && (img < p.N);
             const int oy = oh * p.os + p.ooh[ph];
             const int ox = ow * p.os + p.oow[ph];
             const size_t pix = (static_cast<size_t>(img) * p.YH + oy) * p.YW + ox;
             int cls = 0;
             if (p.cls_bw > 0)
                 cls = border_class(oy, p.YH, p.cls_bw) * (2 * p.cls_bw + 1) + border_class(ox, p.YW, p.cls_bw);
-            const float* bias_row = p.bias ? p.bias + static_cast<size_t>(img) * p.bias_sn +
+            const float* bias_row = p.bias ? p.bias + static_cast<size_t>(min(img, p.N - 1)) * p.bias_sn +
                                                  static_cast<size_t>(cls) * p.bias_sc
                                            : nullptr;
 
@@ -620,6 +649,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     tcgen05_fence_before();
     __syncthreads();
+    if (p.cluster == 2) {                                      // nobody leaves while the peer may still signal its barriers
+        asm volatile("barrier.cluster.arrive.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+    }
     if (warp == 2) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -716,7 +749,13 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     p.m_tiles = d->n * p.tiles_h * p.tiles_w;
     p.n_tiles = d->cout_pad / block_n;
     p.nphases = d->nphases;
-    p.total_tiles = p.m_tiles * p.n_tiles * p.nphases;
+    // CTA pairs with multicast weight tiles: worth it when the weight tile of a stage is at least as large as the activation
+    // tile (the weight stream dominates the L2 -> SM traffic) and there are enough pixel tiles to keep every pair busy
+    const char* cl_env = getenv("CSBSR_CLUSTER");
+    int cluster = 1;
+    if (cl_env) cluster = (atoi(cl_env) == 2 && block_n % 16 == 0 && p.m_tiles >= 2) ? 2 : 1;
+    p.cluster = cluster;
+    p.total_tiles = ((p.m_tiles + cluster - 1) / cluster) * p.n_tiles * p.nphases;
     p.fd_ntiles = make_fastdiv(p.n_tiles); p.fd_nphases = make_fastdiv(p.nphases);
     p.fd_tiles_per_img = make_fastdiv(p.tiles_h * p.tiles_w); p.fd_tiles_w = make_fastdiv(p.tiles_w);
     p.kchunks = d->cin / kb;
@@ -851,7 +890,7 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     {
         cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)d->cout_pad, (cuuint64_t)d->w_taps};
         cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * d->cout_pad};
-        cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)block_n, 1};
+        cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)(block_n / cluster), 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d->wgt, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz_in, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -902,8 +941,23 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
                                               kSmemBudget));
         smem_attr_set = kSmemBudget;
     }
-    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmY, tmR, p);
+    int grid = p.total_tiles * cluster < num_sms() ? p.total_tiles * cluster : (num_sms() / cluster) * cluster;
+    if (cluster == 1) {
+        conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmY, tmR, p);
+    } else {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid, 1, 1);
+        cfg.blockDim = dim3(kThreads, 1, 1);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CSBSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmA, tmB, tmY, tmR, p));
+    }
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

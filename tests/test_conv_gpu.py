@@ -160,3 +160,20 @@ def test_tap_expansion_3x3_few_channels(co):
     torch.cuda.synchronize()
     assert (out[:, 0] == 0).all() and (out[:, co + 1] == 0).all()
     _check(out[:, 1:1 + co], ref)
+
+
+def test_conv_cluster_multicast_mode(monkeypatch):
+    """CSBSR_CLUSTER=2: CTA pairs on neighbouring pixel tiles, each loading half of every weight tile with TMA multicast
+    (odd tile count -> one dummy tile; per-sample class bias; staged and direct epilogues)."""
+    from csbsr_b200 import kernels as K
+    monkeypatch.setenv("CSBSR_CLUSTER", "2")
+    g = torch.Generator(device="cuda").manual_seed(12)
+    for (n, cin, cout, h, w) in ((3, 128, 128, 24, 40), (1, 192, 208, 40, 24)):
+        x = _bf(torch.randn(n, cin, h, w, device="cuda", generator=g))
+        wt = _bf(torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (cin * 9) ** 0.5)
+        b = torch.randn(cout, device="cuda", generator=g)
+        ref = F.conv2d(x, wt, b, padding=1)
+        y = K.Fmap.empty(n, h, w, K.round_up(cout, 16))
+        K.conv(K.Fmap.from_nchw(x), K.pack_conv(wt, b, padding=1), y)
+        torch.cuda.synchronize()
+        _check(y.to_nchw_f32(cout), ref)
