@@ -18,6 +18,14 @@
 
 namespace csbsr {
 
+// CTA-0 timeline instrumentation (scripts/trace_conv.py) is compiled in only with -DCSBSR_CONV_TRACE_BUILD: the runtime checks
+// alone cost ~20 instructions per k-block in the single-thread producer / MMA loops, which bound the small layers
+#ifdef CSBSR_CONV_TRACE_BUILD
+#define CSBSR_TRACE(...) __VA_ARGS__
+#else
+#define CSBSR_TRACE(...)
+#endif
+
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;                  // bf16 elements = 128 bytes = one swizzle row
 static constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
@@ -366,7 +374,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], 2);                        // one arrive.expect_tx from each of the two producer warps
             mbar_init(&empty_bar[s], p.cluster);               // cluster mode: released by the MMAs of both CTAs
         }
         for (int a = 0; a < 2; ++a) {
@@ -395,43 +403,53 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     const int kblocks = p.ngroups * p.kchunks;
 
-    if (warp == 0) {
-        // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    if (warp == 0 || warp == 3) {
+        // ===================== TMA producers (whole warp loops, one elected lane issues) =====================
+        // Two warps share the job -- warp 0 loads the activation boxes, warp 3 the weight tiles -- because the scalar
+        // per-k-block bookkeeping of a single issuing thread (~100 dependent instructions) bounds the small layers.
         {
+            const bool load_a = (warp == 0);
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = p.a_stage_bytes + b_stage_bytes;
+            const uint32_t tx_a = p.a_stage_bytes, tx_b = b_stage_bytes;
+            const int half_rows = p.block_n >> 1;
+            const uint32_t half_off = crank * static_cast<uint32_t>(half_rows * p.kb * 2);
+            const int G = p.G, kchunks = p.kchunks, ngroups = p.ngroups, kbk = p.kb, nstages = p.stages;
             for (int tile = wid; tile < p.total_tiles; tile += wstep) {
                 int nt, ph, img, oh0, ow0;
                 decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
-                if (p.trace && blockIdx.x == 0 && lane == 0 && tile / wstep < 256) p.trace[0 * 256 + tile / wstep] = clock64();
-                for (int g = 0; g < p.ngroups; ++g) {
-                    const int gi = (ph * p.ngroups + g) * p.G;          // first tap of the group
+                CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && lane == 0 && load_a && tile / wstep < 256) p.trace[0 * 256 + tile / wstep] = clock64();)
+                const int n0 = nt * p.block_n + (p.cluster == 2 ? static_cast<int>(crank) * half_rows : 0);
+                for (int g = 0; g < ngroups; ++g) {
+                    const int gi = (ph * ngroups + g) * G;              // first tap of the group
                     const int ih0 = oh0 * p.stride + p.dh[gi];
                     const int iw0 = ow0 * p.stride + p.dw[gi];
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int kc = 0; kc < kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 1);
                         if (elect_one_sync()) {
-                            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                            // one A box covers the G vertically shifted taps of the group (rows TH + (G-1)*dstep)
-                            tma_load_4d(smem_u32(smem_a + stage * p.a_stage_bytes), &tmA, &full_bar[stage],
-                                        kc * p.kb, iw0, ih0, img);
-                            if (p.cluster == 2) {
-                                // this CTA fetches its half of every weight tile and multicasts it to both CTAs of the pair
-                                const int half_rows = p.block_n >> 1;
-                                const uint32_t half_off = crank * static_cast<uint32_t>(half_rows * p.kb * 2);
-                                for (int j = 0; j < p.G; ++j)
-                                    tma_load_3d_mc(smem_u32(smem_b + stage * b_stage_bytes + j * b_tile_bytes) + half_off, &tmB,
-                                                   &full_bar[stage], kc * p.kb, nt * p.block_n + static_cast<int>(crank) * half_rows,
-                                                   p.widx[gi + j], 0x3);
+                            if (load_a) {
+                                mbar_arrive_expect_tx(&full_bar[stage], tx_a);
+                                // one A box covers the G vertically shifted taps of the group (rows TH + (G-1)*dstep)
+                                tma_load_4d(smem_u32(smem_a + stage * p.a_stage_bytes), &tmA, &full_bar[stage], kc * kbk, iw0, ih0,
+                                            img);
                             } else {
-                                for (int j = 0; j < p.G; ++j)
-                                    tma_load_3d(smem_u32(smem_b + stage * b_stage_bytes + j * b_tile_bytes), &tmB,
-                                                &full_bar[stage], kc * p.kb, nt * p.block_n, p.widx[gi + j]);
+                                mbar_arrive_expect_tx(&full_bar[stage], tx_b);
+                                const uint32_t dst0 = smem_u32(smem_b + stage * b_stage_bytes);
+                                if (p.cluster == 2) {
+                                    // this CTA fetches its half of every weight tile and multicasts it to both CTAs of the pair
+#pragma unroll 1
+                                    for (int j = 0; j < G; ++j)
+                                        tma_load_3d_mc(dst0 + j * b_tile_bytes + half_off, &tmB, &full_bar[stage], kc * kbk, n0,
+                                                       p.widx[gi + j], 0x3);
+                                } else {
+#pragma unroll 1
+                                    for (int j = 0; j < G; ++j)
+                                        tma_load_3d(dst0 + j * b_tile_bytes, &tmB, &full_bar[stage], kc * kbk, n0, p.widx[gi + j]);
+                                }
                             }
                         }
                         __syncwarp();
-                        if (++stage == p.stages) {
+                        if (++stage == nstages) {
                             stage = 0;
                             phase ^= 1u;
                         }
@@ -464,17 +482,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint32_t aphase = (local >> 1) & 1;
                 mbar_wait(&tmem_empty[as], aphase ^ 1u, p.err_flag, 2);
                 tcgen05_fence_after();
-                if (p.trace && blockIdx.x == 0 && lane == 0 && local < 256) p.trace[1 * 256 + local] = clock64();
+                CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && lane == 0 && local < 256) p.trace[1 * 256 + local] = clock64();)
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * 256);
                 uint32_t acc = 0;
-                long long wait_cyc = 0;
+                CSBSR_TRACE(long long wait_cyc = 0;)
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    const long long tw0 = p.trace ? clock64() : 0;
+                    CSBSR_TRACE(const long long tw0 = p.trace ? clock64() : 0;)
                     mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
                     tcgen05_fence_after();
-                    if (p.trace) wait_cyc += clock64() - tw0;
+                    CSBSR_TRACE(if (p.trace) wait_cyc += clock64() - tw0;)
                     if (elect_one_sync()) {
                         uint32_t ja = a_lo, jb = b_lo;
+#pragma unroll 1
                         for (int j = 0; j < G; ++j) {
                             // +32 bytes per K=16 step inside the 128B swizzle row -> +2 in the >>4 address field
                             umma_bf16_lohi(tmem_d, ja, jb, desc_hi, idesc, acc);
@@ -495,10 +514,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                     __syncwarp();
                     acc = 1u;
-                    if (kb == kblocks - 1 && p.trace && blockIdx.x == 0 && lane == 0 && local < 256) {
+                    CSBSR_TRACE(if (kb == kblocks - 1 && p.trace && blockIdx.x == 0 && lane == 0 && local < 256) {
                         p.trace[2 * 256 + local] = wait_cyc;
                         p.trace[3 * 256 + local] = clock64();
-                    }
+                    })
                     a_lo += a_stage16;
                     b_lo += b_stage16;
                     if (++stage == p.stages) {
@@ -565,7 +584,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                                : nullptr;
                 mbar_wait(&tmem_full[as], aphase, p.err_flag, 4);
                 tcgen05_fence_after();
-                if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[4 * 256 + local] = clock64();
+                CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[4 * 256 + local] = clock64();)
                 const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * 256);
                 const int c_base = nt * p.block_n;
                 switch (p.act) {
@@ -587,7 +606,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         else tma_store_5d(&tmY, src, c, p.oow[ph], ow0, p.ooh[ph], img * p.OH + oh0);
                     }
                     tma_store_commit();
-                    if (p.trace && blockIdx.x == 0 && local < 256) p.trace[5 * 256 + local] = clock64();
+                    CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && local < 256) p.trace[5 * 256 + local] = clock64();)
                     // the set is single-buffered per team: its next residual tile can only land once the store has
                     // finished reading; the other team's tile hides this latency
                     if (p.res_mode && tile + stride_tiles < p.total_tiles) {
