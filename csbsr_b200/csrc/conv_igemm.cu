@@ -415,10 +415,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int half_rows = p.block_n >> 1;
             const uint32_t half_off = crank * static_cast<uint32_t>(half_rows * p.kb * 2);
             const int G = p.G, kchunks = p.kchunks, ngroups = p.ngroups, kbk = p.kb, nstages = p.stages;
+            // ONE elected thread runs the whole loop: no per-k-block elect / reconvergence / warp sync in the issue path
+            if (elect_one_sync())
             for (int tile = wid; tile < p.total_tiles; tile += wstep) {
                 int nt, ph, img, oh0, ow0;
                 decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
-                CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && lane == 0 && load_a && tile / wstep < 256) p.trace[0 * 256 + tile / wstep] = clock64();)
+                CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && load_a && tile / wstep < 256) p.trace[0 * 256 + tile / wstep] = clock64();)
                 const int n0 = nt * p.block_n + (p.cluster == 2 ? static_cast<int>(crank) * half_rows : 0);
                 for (int g = 0; g < ngroups; ++g) {
                     const int gi = (ph * ngroups + g) * G;              // first tap of the group
@@ -426,7 +428,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const int iw0 = ow0 * p.stride + p.dw[gi];
                     for (int kc = 0; kc < kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 1);
-                        if (elect_one_sync()) {
+                        {
                             if (load_a) {
                                 mbar_arrive_expect_tx(&full_bar[stage], tx_a);
                                 // one A box covers the G vertically shifted taps of the group (rows TH + (G-1)*dstep)
@@ -448,7 +450,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                 }
                             }
                         }
-                        __syncwarp();
                         if (++stage == nstages) {
                             stage = 0;
                             phase ^= 1u;
@@ -456,6 +457,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
@@ -477,12 +479,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int stage = 0;
             uint32_t phase = 0, a_lo = a_lo0, b_lo = b_lo0;
             int local = 0;
-            for (int tile = wid; tile < p.total_tiles; tile += wstep, ++local) {
+            const int nstages = p.stages, total_tiles = p.total_tiles;
+            const bool mc = p.cluster == 2;
+            // ONE elected thread runs the whole issue loop (see the producers)
+            if (elect_one_sync())
+            for (int tile = wid; tile < total_tiles; tile += wstep, ++local) {
                 const int as = local & 1;
                 const uint32_t aphase = (local >> 1) & 1;
                 mbar_wait(&tmem_empty[as], aphase ^ 1u, p.err_flag, 2);
                 tcgen05_fence_after();
-                CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && lane == 0 && local < 256) p.trace[1 * 256 + local] = clock64();)
+                CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && local < 256) p.trace[1 * 256 + local] = clock64();)
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * 256);
                 uint32_t acc = 0;
                 CSBSR_TRACE(long long wait_cyc = 0;)
@@ -491,7 +497,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
                     tcgen05_fence_after();
                     CSBSR_TRACE(if (p.trace) wait_cyc += clock64() - tw0;)
-                    if (elect_one_sync()) {
+                    {
                         uint32_t ja = a_lo, jb = b_lo;
 #pragma unroll 1
                         for (int j = 0; j < G; ++j) {
@@ -508,19 +514,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             ja += a_shift16;
                             jb += b_tile16;
                         }
-                        if (p.cluster == 2) umma_commit_mc(&empty_bar[stage], 0x3);   // frees the slot in both CTAs of the pair
+                        if (mc) umma_commit_mc(&empty_bar[stage], 0x3);   // frees the slot in both CTAs of the pair
                         else umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                         if (kb == kblocks - 1) umma_commit(&tmem_full[as]);
                     }
-                    __syncwarp();
                     acc = 1u;
-                    CSBSR_TRACE(if (kb == kblocks - 1 && p.trace && blockIdx.x == 0 && lane == 0 && local < 256) {
+                    CSBSR_TRACE(if (kb == kblocks - 1 && p.trace && blockIdx.x == 0 && local < 256) {
                         p.trace[2 * 256 + local] = wait_cyc;
                         p.trace[3 * 256 + local] = clock64();
                     })
                     a_lo += a_stage16;
                     b_lo += b_stage16;
-                    if (++stage == p.stages) {
+                    if (++stage == nstages) {
                         stage = 0;
                         phase ^= 1u;
                         a_lo = a_lo0;
@@ -528,6 +533,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                 }
             }
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===================== epilogue: TMEM -> registers -> global =====================
