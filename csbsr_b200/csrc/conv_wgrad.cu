@@ -81,6 +81,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
         uint32_t it = 0;
+        // one elected thread runs the whole loop (no per-stage elect / reconvergence in the issue path)
+        if (elect_one_sync())
         for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
             const int split = item / p.npass, pass = item - split * p.npass;
             const int mt = pass / p.passes_per_m, pl = pass - mt * p.passes_per_m;
@@ -90,7 +92,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 const int stage = it % p.stages;
                 const uint32_t par = (it / p.stages) & 1u;
                 mbar_wait(&empty_bar[stage], par ^ 1u, p.err_flag, 21);
-                if (elect_one_sync()) {
+                {
                     const int img = t / tiles_per_img, tr = t - img * tiles_per_img;
                     const int oy0 = (tr / p.tiles_w) * p.TH, ox0 = (tr % p.tiles_w) * p.TW;
                     uint32_t bytes = 2 * kWgBox;
@@ -112,12 +114,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                         dst += 2 * p.b_box_bytes;
                     }
                 }
-                __syncwarp();
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
         uint32_t it = 0, nitem = 0;
+        if (elect_one_sync())
         for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
             const int split = item / p.npass, pass = item - split * p.npass;
             const int pl = pass % p.passes_per_m;
@@ -131,7 +134,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 const uint32_t par = (it / p.stages) & 1u;
                 mbar_wait(&full_bar[stage], par, p.err_flag, 23);
                 tcgen05_fence_after();
-                if (elect_one_sync()) {
+                {
                     const uint32_t a_addr = smem_base + stage * p.stage_bytes;
                     for (int u = u0; u < u1; ++u) {
                         const int csc = u % p.ncs;
@@ -152,10 +155,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                     umma_commit(&empty_bar[stage]);
                     if (t == t1 - 1) umma_commit(tmem_full);
                 }
-                __syncwarp();
             }
             ++nitem;
         }
+        __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------ epilogue: TMEM -> red.add into the fp32 gradient
         const int q = warp - 4;                           // TMEM lane quarter
