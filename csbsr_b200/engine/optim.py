@@ -17,6 +17,22 @@ class UpDownScheduler:
         return 10 if (70000 < main < 95000 and self.scheduler_flag) else 1
 
 
+def active_runs(active, slots, steps):
+    """Merge the flat-buffer slots of the active parameters into launch runs: adjacent slots whose parameters share the
+    same (already incremented) step counter become one [offset, length, step] run.  Pure host logic (CPU-testable)."""
+    runs, cur = [], None
+    for on, (off, sz), step in zip(active, slots, steps):
+        if not on:
+            cur = None
+            continue
+        if cur is not None and cur[2] == step and cur[0] + cur[1] == off:
+            cur[1] += sz
+        else:
+            cur = [off, sz, step]
+            runs.append(cur)
+    return runs
+
+
 class FusedAdam:
     """torch.optim.Adam(params, lr, betas=(0.9, 0.999), eps=1e-8) semantics (no weight decay / amsgrad).
 
@@ -68,18 +84,11 @@ class FusedAdam:
         neither their value nor their moments nor their step counter move).  Adjacent active parameters with the same step
         counter are updated by one launch -- a single launch over the whole buffer outside the pre-training phases."""
         self.step_count += 1
-        runs, cur = [], None
-        for i, (p, (off, sz)) in enumerate(zip(self.params, self.slots)):
-            if not p.requires_grad:
-                cur = None
-                continue
-            self.param_steps[i] += 1
-            if cur is not None and cur[2] == self.param_steps[i] and cur[0] + cur[1] == off:
-                cur[1] += sz
-            else:
-                cur = [off, sz, self.param_steps[i]]
-                runs.append(cur)
-        for off, n, step in runs:
+        active = [p.requires_grad for p in self.params]
+        for i, on in enumerate(active):
+            if on:
+                self.param_steps[i] += 1
+        for off, n, step in active_runs(active, self.slots, self.param_steps):
             rc = _lib.lib().csbsr_adam_step(self.flat_p.data_ptr() + 4 * off, self.flat_g.data_ptr() + 4 * off,
                                             self.exp_avg.data_ptr() + 4 * off, self.exp_avg_sq.data_ptr() + 4 * off, n, self.lr,
                                             self.betas[0], self.betas[1], self.eps, step, 1.0 / world_size, 1,

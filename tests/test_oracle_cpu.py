@@ -322,3 +322,25 @@ def test_training_phase_switches_match_reference(it):
     m.apply_phase(it)
     mine = sorted(k for k, p in m.named_parameters() if p.requires_grad)
     assert mine == sorted(str(k) for k in g["requires_grad_names"])
+
+
+def test_fused_adam_launch_runs_host_logic():
+    """FusedAdam groups active parameters into contiguous launch runs with a common step counter (frozen ones are skipped)."""
+    from csbsr_b200.engine.optim import active_runs
+    slots = [(0, 8), (8, 4), (12, 16), (28, 4), (32, 8)]
+    assert active_runs([True] * 5, slots, [3] * 5) == [[0, 40, 3]]
+    assert active_runs([True, False, True, True, False], slots, [3, 1, 3, 3, 1]) == [[0, 8, 3], [12, 20, 3]]
+    assert active_runs([True, True, True, True, True], slots, [5, 5, 2, 2, 5]) == [[0, 12, 5], [12, 20, 2], [32, 8, 5]]
+    assert active_runs([False] * 5, slots, [0] * 5) == []
+
+
+def test_graphed_step_phase_key_host_logic():
+    """One CUDA graph per training phase: the key changes exactly at the phase boundaries of the shipped config."""
+    from csbsr_b200.config import cfg
+    from csbsr_b200.engine.trainer import GraphedTrainStep
+    c = cfg.clone()
+    c.merge_from_file(os.path.join(os.path.dirname(GOLD), "..", "config", "config_csbsr_pspnet.yaml"))
+    gs = GraphedTrainStep(None, None, c)
+    keys = [gs._phase_key(it) for it in (1, 10000, 10001, 19999, 20000, 20001, 30000, 30001, 400000)]
+    assert keys[0] == keys[1] and keys[1] != keys[2] and keys[2] == keys[3] and keys[3] != keys[4]
+    assert keys[4] != keys[5] and keys[5] == keys[6] and keys[6] != keys[7] and keys[7] == keys[8]
