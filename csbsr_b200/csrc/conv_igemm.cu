@@ -572,6 +572,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint32_t aphase = n_use & 1;
                 const int local = 2 * n_use + team;
                 int nt, ph, img, oh0, ow0;
+                CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[6 * 256 + local] = clock64();)
                 decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
                 if (p.res_mode) {
                     mbar_wait(&res_full[as], aphase, p.err_flag, 5);
@@ -579,6 +580,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (leader) tma_store_wait_read<0>();       // the previous store of this team is done reading the set
                     team_bar_sync(team);
                 }
+                CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[7 * 256 + local] = clock64();)
                 const int oy = (oh0 + th) * p.os + p.ooh[ph];
                 const int ox = (ow0 + tw) * p.os + p.oow[ph];
                 int cls = 0;
@@ -599,10 +601,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     case CSBSR_ACT_SIGMOID: epilogue_staged<CSBSR_ACT_SIGMOID>(p, stage_set, row, taddr0, c_base, u_begin, u_end, bias_row); break;
                     default:                epilogue_staged<CSBSR_ACT_NONE>(p, stage_set, row, taddr0, c_base, u_begin, u_end, bias_row); break;
                 }
+                CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[8 * 256 + local] = clock64();)
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[as]);
                 fence_proxy_async_smem();                       // make the generic-proxy writes visible to the TMA store
+                CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[9 * 256 + local] = clock64();)
                 team_bar_sync(team);
                 if (leader) {
                     for (int pn = 0; pn < n_panels; ++pn) {
@@ -703,7 +707,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 static int* g_err_flag = nullptr;
-static long long* g_trace = nullptr;   // debug timeline of CTA 0 (CSBSR_CONV_TRACE=1): [6][256] clock64 stamps   // device int, lazily allocated (one per process; diagnostic only)
+static long long* g_trace = nullptr;   // debug timeline of CTA 0 (CSBSR_CONV_TRACE=1): [10][256] clock64 stamps   // device int, lazily allocated (one per process; diagnostic only)
 
 }  // namespace csbsr
 
@@ -889,8 +893,8 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     p.err_flag = g_err_flag;
     p.trace = nullptr;
     if (getenv("CSBSR_CONV_TRACE")) {
-        if (!g_trace) CSBSR_CHECK_CUDA(cudaMalloc(&g_trace, sizeof(long long) * 6 * 256));
-        CSBSR_CHECK_CUDA(cudaMemsetAsync(g_trace, 0, sizeof(long long) * 6 * 256, stream));
+        if (!g_trace) CSBSR_CHECK_CUDA(cudaMalloc(&g_trace, sizeof(long long) * 10 * 256));
+        CSBSR_CHECK_CUDA(cudaMemsetAsync(g_trace, 0, sizeof(long long) * 10 * 256, stream));
         p.trace = g_trace;
     }
 
@@ -990,5 +994,5 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
 // debug only (not part of the public header): copies the CTA-0 timeline recorded under CSBSR_CONV_TRACE=1
 extern "C" int csbsr_conv_trace_read(long long* host_out) {
     if (!csbsr::g_trace) return -1;
-    return cudaMemcpy(host_out, csbsr::g_trace, sizeof(long long) * 6 * 256, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+    return cudaMemcpy(host_out, csbsr::g_trace, sizeof(long long) * 10 * 256, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }

@@ -23,10 +23,10 @@ else:
     r = K.Fmap.empty(B, 448, 448, 128); r.t.normal_(); kw = dict(act=K.ACT_LEAKY, slope=0.1, r1=r)
 for _ in range(3): K.conv(x, pc, y, **kw)
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * (6 * 256))()
+buf = (ctypes.c_longlong * (10 * 256))()
 L = ctypes.CDLL(_lib.LIB_PATH)
 assert L.csbsr_conv_trace_read(buf) == 0
-t = np.array(buf[:]).reshape(6, 256).astype(np.int64)
+t = np.array(buf[:]).reshape(10, 256).astype(np.int64)
 n = int((t[5] > 0).sum())
 t0 = t[0, 0]
 names = ["prod_issue", "mma_acc_free", "mma_first", "mma_commit", "epi_start", "epi_store"]
@@ -38,3 +38,11 @@ print("MMA warp: cycles waiting on full barriers per tile: mean %.0f ; tile span
 print("epi duration mean", (t[5, 10:n-2] - t[4, 10:n-2]).mean(), " mma commit->epi start", (t[4, 10:n-2] - t[3, 10:n-2]).mean(),
       " acc_free->first mma", (t[2, 10:n-2] - t[1, 10:n-2]).mean(), " first mma->commit", (t[3, 10:n-2] - t[2, 10:n-2]).mean(),
       " prod lead over mma_first", (t[2, 10:n-2] - t[0, 10:n-2]).mean())
+
+# staged epilogue breakdown of the leader warp (rows 6..9 need the -DCSBSR_CONV_TRACE_BUILD build)
+if (t[6, 10:n - 2] > 0).all():
+    sl = slice(10, n - 2)
+    print("epilogue leader: loop top -> store-read wait + team barrier %.0f | -> accumulator ready %.0f | math %.0f | fence.proxy %.0f | "
+          "team barrier -> store issued %.0f | store issued -> next loop top (other work / idle) %.0f" % (
+              (t[7, sl] - t[6, sl]).mean(), (t[4, sl] - t[7, sl]).mean(), (t[8, sl] - t[4, sl]).mean(), (t[9, sl] - t[8, sl]).mean(),
+              (t[5, sl] - t[9, sl]).mean(), (t[6, 12:n - 2] - t[5, 10:n - 4]).mean()))
