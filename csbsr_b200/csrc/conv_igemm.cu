@@ -571,6 +571,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int tile = first_tile; tile < p.total_tiles; tile += stride_tiles, ++n_use) {
                 const uint32_t aphase = n_use & 1;
                 const int local = 2 * n_use + team;
+                (void)local;                                    // only the trace build reads it
                 int nt, ph, img, oh0, ow0;
                 CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[6 * 256 + local] = clock64();)
                 decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
