@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--layers", action="store_true")
+    ap.add_argument("--detector", default="PSPNet", choices=["PSPNet", "HRNet_OCR"])
     ap.add_argument("--graph", action="store_true", help="capture forward + loss + backward in a CUDA graph")
     a = ap.parse_args()
     from csbsr_b200 import _lib
@@ -28,9 +29,13 @@ def main():
     c = cfg.clone()
     c.merge_from_file("config/config_csbsr_pspnet.yaml")
     c.SOLVER.SEG_FAIL_ORIENTED_WEIGHT4SS_AMP = 1.0
+    if a.detector == "HRNet_OCR":                              # config #4: HRNet-W48 + OCR, beta = 0.9
+        c.MODEL.DETECTOR_TYPE = "HRNet_OCR"
+        c.SOLVER.TASK_LOSS_WEIGHT = 0.9
     m = JointModelWithLoss(c, num_train_ds=1000, resume_iter=40000)
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-    sd.update(P.synth_state_dict(P.pspnet_param_shapes(), prefix="segmentation_model."))
+    seg_shapes = P.hrnet_ocr_param_shapes() if a.detector == "HRNet_OCR" else P.pspnet_param_shapes()
+    sd.update(P.synth_state_dict(seg_shapes, prefix="segmentation_model."))
     m.load_state_dict(sd)
     m.cuda().train()
     opt = FusedAdam(m.parameters(), lr=c.SOLVER.LR)
