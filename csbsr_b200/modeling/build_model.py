@@ -132,8 +132,11 @@ class JointModelWithLoss(JointModel):
 
     def __init__(self, cfg, num_train_ds, resume_iter=0, sr_transforms=None):
         super().__init__(cfg)
-        if self.seg_model_name not in ("PSPNet", "HRNet_OCR"):
+        if self.seg_model_name not in ("PSPNet", "HRNet_OCR", "PSPNet_BlurSkip"):
             raise NotImplementedError("training graph: DETECTOR_TYPE=%r" % (self.seg_model_name,))
+        if self.seg_model_name == "PSPNet_BlurSkip":             # only the BlurSkip branch is trained (build_model.py:352-366)
+            for name, p_ in self.named_parameters():
+                p_.requires_grad_(name.startswith("segmentation_model.blur_skip."))
         if cfg.SOLVER.SEG_LOSS_FUNC != "BoundaryCombo" or cfg.SOLVER.SR_LOSS_FUNC != "KBPN":
             raise NotImplementedError("training graph: SEG_LOSS_FUNC=%r SR_LOSS_FUNC=%r" %
                                       (cfg.SOLVER.SEG_LOSS_FUNC, cfg.SOLVER.SR_LOSS_FUNC))
@@ -182,7 +185,7 @@ class JointModelWithLoss(JointModel):
         cfg = self.cfg
         if cfg.SOLVER.SEG_PRETRAIN_ITER[0] <= iter < cfg.SOLVER.SEG_PRETRAIN_ITER[1]:
             raise NotImplementedError("segmentation pre-training (SEG_PRETRAIN_ITER) is not built")
-        sr_module_pre = self.apply_phase(iter)
+        sr_module_pre = self.apply_phase(iter) if self.seg_model_name != "PSPNet_BlurSkip" else False
         sr_only = cfg.SOLVER.SR_PRETRAIN_ITER[0] <= iter < cfg.SOLVER.SR_PRETRAIN_ITER[1]   # loss = sr_loss (trainer.py:432-434)
         device = torch.device("cuda", torch.cuda.current_device())
         mv = lambda t: None if t is None else t.to(device=device, dtype=torch.float32)
@@ -195,10 +198,11 @@ class JointModelWithLoss(JointModel):
                                        gt_kernel=kernel_targets if sr_module_pre else None)
             seg_fwd = TG.hrnet_ocr_forward if self.seg_model_name == "HRNet_OCR" else TG.pspnet_forward
             # while only sr_loss is optimised the segmentation net is evaluated for logging only: no tape needed
+            extra = {"kvec": kvec} if self.seg_model_name == "PSPNet_BlurSkip" else {}
             with torch.set_grad_enabled(torch.is_grad_enabled() and not sr_only):
                 normed = torch.nn.functional.instance_norm(sr, eps=1e-5)          # norm_sr, build_model.py:135-137
                 seg, aux = seg_fwd(P, normed, bn_training=self.training and not self.freeze_bn,
-                                   dropout=self.dropout and self.training)
+                                   dropout=self.dropout and self.training, **extra)
             sr_loss, kernel_preds = LS.kbpn_loss_train(sr, sr_targets, x, kvec, kernel_targets, self.sr_loss_weights,
                                                        self.ksize, self.scale_factor)
             amp = self.wf_amp if self.oriented_w_iter <= iter else 0.0

@@ -241,8 +241,25 @@ def _drop(x, p, on):
     return _nhwc(F.dropout2d(_nchw(x), p, training=True)) if (on and p > 0) else x
 
 
-def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_training=True, dropout=True):
-    """img fp32 [B,3,H,W] (already normalised) -> (seg, aux) fp32 [B,1,H,W]."""
+def _sft_like(P, p, feats, kvec):
+    """SFTLikeBlock.forward (model/modeling/blocks.py:105-120) on cat(features[64], kernel map[441]); the spatially constant
+    kernel-map half of conv 0 is evaluated on a 3x3 image of border classes (as in _sft)."""
+    n, h, w, fc = feats.shape
+    cond = _expand_vec(kvec, 3, 3).contiguous()
+
+    def branch(name):
+        bp = p + ".conv_%s" % name
+        w0 = P[bp + ".0.layer.weight"]
+        t = conv2d(feats, w0[:, :fc].contiguous(), None, padding=1)
+        tb = conv2d(cond, w0[:, fc:].contiguous(), P[bp + ".0.layer.bias"], padding=1)
+        t = prelu(t + _expand_classes(tb, h, w, 1), P[bp + ".0.act.weight"])
+        return conv2d(t, P[bp + ".1.layer.weight"], P[bp + ".1.layer.bias"], padding=1)
+    return feats * torch.sigmoid(branch("scale")) + branch("shift")
+
+
+def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_training=True, dropout=True, kvec=None):
+    """img fp32 [B,3,H,W] (already normalised) -> (seg, aux) fp32 [B,1,H,W].  With `kvec` (B, 441) and blur_skip
+    parameters: PSPNet_BlurSkip.forward (pspnet.py:174-207), p + BlurSkip(p, kernel)."""
     p = prefix
     H, W = img.shape[2:]
     x = to_nhwc(img)
@@ -279,6 +296,14 @@ def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_
                 bn_training)
         y = prelu(y, P[p + name + ".conv.2.weight"])
         y = _drop(y, dp, dropout)
+    if kvec is not None:
+        t, i = y, 0
+        while (p + "blur_skip.%d.conv_scale.0.layer.weight" % (2 * i)) in P:
+            t = _sft_like(P, p + "blur_skip.%d" % (2 * i), t, kvec)
+            bp = p + "blur_skip.%d" % (2 * i + 1)
+            t = _bn(P, bp + ".norm", conv2d(t, P[bp + ".layer.weight"], None, padding=1), bn_training, relu=True)
+            i += 1
+        y = y + t
     seg = torch.sigmoid(to_nchw(conv2d(y, P[p + "final.0.weight"], P[p + "final.0.bias"]), 1))
     a = _bn(P, p + "aux.1", conv2d(x3, P[p + "aux.0.weight"], None, padding=1), bn_training, relu=True)
     a = _drop(a, 0.1, dropout)

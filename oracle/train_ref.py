@@ -15,12 +15,15 @@ from . import torch_ref as T
 
 
 def train_forward(sd, lr, hr, mask, kgt, alpha, beta=0.3, wf_amp=1.0, bn_train=True, hrnet=False, gt_kernel_phase=False,
-                  sr_only=False):
+                  sr_only=False, blur_skip=False):
     """-> (loss, seg_loss, sr_loss, sr, seg, aux).  `sd` tensors that require grad receive gradients."""
     T.BN_TRAIN = bn_train
     try:
         sr, kvec = T.kbpn_forward(sd, lr, gt_kernel=kgt if gt_kernel_phase else None)
-        seg, aux = (T.hrnet_ocr_forward if hrnet else T.pspnet_forward)(sd, F.instance_norm(sr, eps=1e-5))
+        if blur_skip:
+            seg, aux = T.pspnet_forward(sd, F.instance_norm(sr, eps=1e-5), kvec=kvec)
+        else:
+            seg, aux = (T.hrnet_ocr_forward if hrnet else T.pspnet_forward)(sd, F.instance_norm(sr, eps=1e-5))
     finally:
         T.BN_TRAIN = False
     kmap = kvec.expand(-1, -1, lr.shape[2], lr.shape[3])

@@ -230,7 +230,7 @@ def gen_psnr_ssim():
     print("psnr_ssim.npz", PSNR()(a, b), SSIM()(a, b))
 
 
-def gen_train(bn_eval=False, hrnet=False, iteration=40000):
+def gen_train(bn_eval=False, hrnet=False, iteration=40000, blurskip=False):
     """One JointModelWithLoss forward + backward of the UNMODIFIED reference at iteration 40000 (all phases active,
     w^F on, m^F = 1), Dropout2d disabled (p = 0) so the step is deterministic: losses and a sample of gradients.
     bn_eval=True additionally puts the BatchNorm layers in eval mode (running statistics): with random weights and a
@@ -242,14 +242,15 @@ def gen_train(bn_eval=False, hrnet=False, iteration=40000):
     from model.modeling.build_model import JointModelWithLoss
     from model.data.transforms.transforms import FactorResize
     from model.engine.trainer import calc_loss
-    cfg = rh.make_cfg(wf_amp=1.0, detector="HRNet_OCR" if hrnet else "PSPNet")
+    cfg = rh.make_cfg(wf_amp=1.0, detector="HRNet_OCR" if hrnet else "PSPNet_BlurSkip" if blurskip else "PSPNet")
     if hrnet:
         cfg.SOLVER.TASK_LOSS_WEIGHT = 0.9                       # config #4 (beta = 0.9)
         rh.patch_hrnet_configer()
     with contextlib.redirect_stdout(io.StringIO()):
         m = JointModelWithLoss(cfg, num_train_ds=100, resume_iter=iteration, sr_transforms=FactorResize(4, "bicubic"))
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-    sd.update(P.synth_state_dict(P.hrnet_ocr_param_shapes() if hrnet else P.pspnet_param_shapes(), prefix="segmentation_model."))
+    seg_shapes = P.hrnet_ocr_param_shapes() if hrnet else P.pspnet_param_shapes(blur_dim=441 if blurskip else None)
+    sd.update(P.synth_state_dict(seg_shapes, prefix="segmentation_model."))
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected and all(k.startswith("sr_loss_fn") or "vgg" in k.lower() for k in missing), (missing, unexpected)
     m.train()
@@ -290,6 +291,11 @@ def gen_train(bn_eval=False, hrnet=False, iteration=40000):
              "segmentation_model.feats.conv1.weight", "segmentation_model.feats.layer3.2.conv1.weight",
              "segmentation_model.feats.layer4.2.bn2.weight", "segmentation_model.psp.bottleneck.weight",
              "segmentation_model.up_2.conv.0.weight", "segmentation_model.final.0.weight", "segmentation_model.aux.4.bias"]
+    if blurskip:
+        names = ["segmentation_model.blur_skip.0.conv_scale.0.layer.weight", "segmentation_model.blur_skip.0.conv_shift.1.layer.weight",
+                 "segmentation_model.blur_skip.0.conv_scale.0.act.weight", "segmentation_model.blur_skip.1.layer.weight",
+                 "segmentation_model.blur_skip.1.norm.weight", "segmentation_model.blur_skip.2.conv_shift.0.layer.bias",
+                 "segmentation_model.blur_skip.3.layer.weight"]
     if hrnet:
         names = [n for n in names if n.startswith("sr_model.")] + [
             "segmentation_model.backbone.conv1.weight", "segmentation_model.backbone.layer1.2.conv2.weight",
@@ -314,7 +320,8 @@ def gen_train(bn_eval=False, hrnet=False, iteration=40000):
         stride = max(1, gflat.size // 20000)
         out["grad:" + k] = gflat[::stride].astype(np.float16 if False else np.float32)
         out["stride:" + k] = np.int64(stride)
-    fname = "train_step_hrnet.npz" if hrnet else "train_step_bneval.npz" if bn_eval else "train_step.npz"
+    fname = "train_step_hrnet.npz" if hrnet else "train_step_blurskip.npz" if blurskip else \
+        "train_step_bneval.npz" if bn_eval else "train_step.npz"
     if iteration != 40000:
         fname = "train_step_it%d.npz" % iteration
     np.savez_compressed(os.path.join(HERE, fname), **out)
@@ -328,7 +335,9 @@ if __name__ == "__main__" and "alpha" in sys.argv[1:]:
     gen_alpha_schedule()
 
 if __name__ == "__main__" and "train" in sys.argv[1:]:
-    if "pretrain" in sys.argv[1:]:
+    if "blurskip" in sys.argv[1:]:
+        gen_train(bn_eval=True, blurskip=True)
+    elif "pretrain" in sys.argv[1:]:
         for it in (5, 15000, 20000, 25000):    # SR-module / kernel-module pre-training, its last iteration, SR-only phase
             gen_train(bn_eval=True, iteration=it)
     elif "hrnet" in sys.argv[1:]:

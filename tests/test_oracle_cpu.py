@@ -226,24 +226,26 @@ def test_deconv_phase_decomposition_matches_conv_transpose():
     assert (out - ref).abs().max().item() < 0.05 * ref.abs().max().item()        # bf16-rounded weights
 
 
-@pytest.mark.parametrize("variant", ["pspnet", "pspnet_bneval", "hrnet_bneval", "it5", "it15000", "it25000"])
+@pytest.mark.parametrize("variant", ["pspnet", "pspnet_bneval", "hrnet_bneval", "blurskip_bneval", "it5", "it15000", "it25000"])
 def test_train_oracle_matches_reference_golden(variant):
     """oracle/train_ref.py (fp32 autograd) against the unmodified JointModelWithLoss forward + backward; it5 / it15000 /
     it25000 = the SR-module, kernel-module and SR-only pre-training phases (ground-truth kernel, frozen modules, loss = sr)."""
     from csbsr_b200.modeling import params as P
     from oracle import train_ref as TR
     bn_eval, hrnet = variant.endswith("bneval") or variant.startswith("it"), variant.startswith("hrnet")
-    g = np.load(os.path.join(GOLD, {"pspnet": "train_step.npz", "pspnet_bneval": "train_step_bneval.npz",
+    blurskip = variant.startswith("blurskip")             # config #5: only the BlurSkip branch receives gradients
+    g = np.load(os.path.join(GOLD, {"pspnet": "train_step.npz", "pspnet_bneval": "train_step_bneval.npz", "blurskip_bneval": "train_step_blurskip.npz",
                                     "hrnet_bneval": "train_step_hrnet.npz"}.get(variant, "train_step_%s.npz" % variant)))
     it = int(g["iteration"]) if "iteration" in g.files else 40000
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-    sd.update(P.synth_state_dict(P.hrnet_ocr_param_shapes() if hrnet else P.pspnet_param_shapes(), prefix="segmentation_model."))
+    sd.update(P.synth_state_dict(P.hrnet_ocr_param_shapes() if hrnet else P.pspnet_param_shapes(blur_dim=441 if blurskip else None),
+                                 prefix="segmentation_model."))
     names = [k[5:] for k in g.files if k.startswith("grad:")]
     for k in names:
         sd[k] = sd[k].clone().requires_grad_(True)
     loss, seg_loss, sr_loss, sr, seg, _ = TR.train_forward(sd, *(torch.from_numpy(g[k]) for k in ("lr", "hr", "mask", "kgt")),
                                                            alpha=float(g["alpha"]), beta=0.9 if hrnet else 0.3, wf_amp=1.0, bn_train=not bn_eval,
-                                                           hrnet=hrnet, gt_kernel_phase=1 <= it < 10001, sr_only=it < 30001)
+                                                           hrnet=hrnet, gt_kernel_phase=1 <= it < 10001, sr_only=it < 30001, blur_skip=blurskip)
     loss.backward()
     assert tuple(seg_loss.shape) == tuple(g["seg_loss_shape"])
     assert abs(loss.item() - float(g["loss"])) <= 1e-5

@@ -131,7 +131,7 @@ def test_deconv8s4_autograd_fn():
         assert _rel(x.grad, x_ref.grad) <= 1e-2 and _rel(w_.grad, w_ref.grad) <= 1e-2
 
 
-def _train_model(hrnet=False):
+def _train_model(hrnet=False, blurskip=False):
     from csbsr_b200.config import cfg
     from csbsr_b200.modeling.build_model import JointModelWithLoss
     from csbsr_b200.modeling import params as P
@@ -141,14 +141,17 @@ def _train_model(hrnet=False):
     if hrnet:
         c.MODEL.DETECTOR_TYPE = "HRNet_OCR"
         c.SOLVER.TASK_LOSS_WEIGHT = 0.9
+    if blurskip:
+        c.MODEL.DETECTOR_TYPE = "PSPNet_BlurSkip"
     m = JointModelWithLoss(c, num_train_ds=100, resume_iter=40000)
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-    sd.update(P.synth_state_dict(P.hrnet_ocr_param_shapes() if hrnet else P.pspnet_param_shapes(), prefix="segmentation_model."))
+    sd.update(P.synth_state_dict(P.hrnet_ocr_param_shapes() if hrnet else P.pspnet_param_shapes(blur_dim=441 if blurskip else None),
+                                 prefix="segmentation_model."))
     m.load_state_dict(sd, strict=True)
     return m.cuda(), sd, c
 
 
-@pytest.mark.parametrize("variant", ["pspnet_bneval", "pspnet", "hrnet_bneval", "it5", "it15000", "it20000", "it25000"])
+@pytest.mark.parametrize("variant", ["pspnet_bneval", "pspnet", "hrnet_bneval", "blurskip_bneval", "it5", "it15000", "it20000", "it25000"])
 def test_train_step_vs_reference_golden(variant):
     """One joint training step (iteration 40000, w^F on, Dropout2d off) of the tcgen05 training graph against the
     unmodified reference's losses and gradients (tests/golden/train_step*.npz; the fp32 oracle is pinned to the same
@@ -166,10 +169,10 @@ def test_train_step_vs_reference_golden(variant):
     # last iteration where KBPN re-enables its SR layers one step early, 25000: whole SR net, loss = sr_loss throughout)
     bn_eval, hrnet = variant.endswith("bneval") or variant.startswith("it"), variant.startswith("hrnet")
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
-                             {"pspnet": "train_step.npz", "pspnet_bneval": "train_step_bneval.npz",
+                             {"pspnet": "train_step.npz", "pspnet_bneval": "train_step_bneval.npz", "blurskip_bneval": "train_step_blurskip.npz",
                               "hrnet_bneval": "train_step_hrnet.npz"}.get(variant, "train_step_%s.npz" % variant)))
     it = int(g["iteration"]) if "iteration" in g.files else 40000
-    m, sd, c = _train_model(hrnet)
+    m, sd, c = _train_model(hrnet, variant.startswith("blurskip"))    # blurskip: only segmentation_model.blur_skip.* is trained
     m.train()
     m.dropout = False
     m.freeze_bn = bn_eval
