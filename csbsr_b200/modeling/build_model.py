@@ -183,10 +183,11 @@ class JointModelWithLoss(JointModel):
         if not torch.cuda.is_available() or not _lib.lib().csbsr_device_ok():
             raise _lib.CsbsrError("csbsr_b200 needs an sm_100 CUDA device; there is no CPU fallback")
         cfg = self.cfg
-        if cfg.SOLVER.SEG_PRETRAIN_ITER[0] <= iter < cfg.SOLVER.SEG_PRETRAIN_ITER[1]:
-            raise NotImplementedError("segmentation pre-training (SEG_PRETRAIN_ITER) is not built")
         sr_module_pre = self.apply_phase(iter) if self.seg_model_name != "PSPNet_BlurSkip" else False
-        sr_only = cfg.SOLVER.SR_PRETRAIN_ITER[0] <= iter < cfg.SOLVER.SR_PRETRAIN_ITER[1]   # loss = sr_loss (trainer.py:432-434)
+        # loss = sr_loss inside SR_PRETRAIN_ITER unless SEG_PRETRAIN_ITER overrides it with segment_loss (trainer.py:432-437);
+        # the forward graph itself does not depend on SEG_PRETRAIN_ITER
+        sr_only = cfg.SOLVER.SR_PRETRAIN_ITER[0] <= iter < cfg.SOLVER.SR_PRETRAIN_ITER[1] and not \
+            cfg.SOLVER.SEG_PRETRAIN_ITER[0] <= iter < cfg.SOLVER.SEG_PRETRAIN_ITER[1]
         device = torch.device("cuda", torch.cuda.current_device())
         mv = lambda t: None if t is None else t.to(device=device, dtype=torch.float32)
         x, sr_targets, segment_targets, kernel_targets = mv(x), mv(sr_targets), mv(segment_targets), mv(kernel_targets)

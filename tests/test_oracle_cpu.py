@@ -326,6 +326,33 @@ def test_training_phase_switches_match_reference(it):
     assert mine == sorted(str(k) for k in g["requires_grad_names"])
 
 
+def test_blurskip_training_freezes_all_but_the_blurskip_branch():
+    """Config #5: JointModelWithLoss(PSPNet_BlurSkip) leaves only segmentation_model.blur_skip.* trainable, like the
+    reference constructor (build_model.py:352-366; fixture records requires_grad after one reference forward)."""
+    from csbsr_b200.config import cfg
+    from csbsr_b200.modeling.build_model import JointModelWithLoss
+    g = np.load(os.path.join(GOLD, "train_step_blurskip.npz"))
+    c = cfg.clone()
+    c.merge_from_file(os.path.join(os.path.dirname(GOLD), "..", "config", "config_csbsr_pspnet.yaml"))
+    c.MODEL.DETECTOR_TYPE = "PSPNet_BlurSkip"
+    m = JointModelWithLoss(c, num_train_ds=100, resume_iter=40000)
+    mine = sorted(k for k, p in m.named_parameters() if p.requires_grad)
+    assert mine == sorted(str(k) for k in g["requires_grad_names"]) and len(mine) == 26
+
+
+def test_calc_loss_pretrain_windows():
+    """trainer.calc_loss + calc_pretrain_loss (trainer.py:406-438): the SEG window overrides the SR window."""
+    from csbsr_b200.config import cfg
+    from csbsr_b200.engine.losses import calc_loss
+    c = cfg.clone()
+    c.SOLVER.SR_PRETRAIN_ITER, c.SOLVER.SEG_PRETRAIN_ITER = [0, 100], [50, 200]
+    sr, seg = torch.tensor([0.2, 0.4]), torch.tensor(0.7)
+    assert calc_loss(sr, seg, 0.3, 10, c).item() == pytest.approx(0.3)
+    assert calc_loss(sr, seg, 0.3, 60, c).item() == pytest.approx(0.7)
+    assert calc_loss(sr, seg, 0.3, 150, c).item() == pytest.approx(0.7)
+    assert calc_loss(sr, seg, 0.3, 200, c).item() == pytest.approx(0.7 * 0.3 + 0.3 * 0.7)
+
+
 def test_fused_adam_launch_runs_host_logic():
     """FusedAdam groups active parameters into contiguous launch runs with a common step counter (frozen ones are skipped)."""
     from csbsr_b200.engine.optim import active_runs
