@@ -171,16 +171,14 @@ __device__ __forceinline__ void epilogue_bf16(const ConvKParams& p, const EpiRow
     for (int u = u0; u < units; u += kEpiWarps / 4) {
         const int c0 = c_base + u * 16;
         const bool on = er.valid && c0 < p.cout_store;
-        uint4 q0[2], qm[2], q1[2];
-        if (on) {
+        uint4 q0[2], qm[2], q1[2];                          // always initialised: conditionally written arrays end up in local memory
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const int c = c0 + g * 8;
-                const bool okc = c < p.cout_store;
-                q0[g] = (r0p && okc) ? *reinterpret_cast<const uint4*>(r0p + c) : make_uint4(0, 0, 0, 0);
-                qm[g] = (rmp && okc) ? *reinterpret_cast<const uint4*>(rmp + c) : make_uint4(0, 0, 0, 0);
-                q1[g] = (r1p && okc) ? *reinterpret_cast<const uint4*>(r1p + c) : make_uint4(0, 0, 0, 0);
-            }
+        for (int g = 0; g < 2; ++g) {
+            const int c = c0 + g * 8;
+            const bool okc = on && c < p.cout_store;
+            q0[g] = (r0p && okc) ? *reinterpret_cast<const uint4*>(r0p + c) : make_uint4(0, 0, 0, 0);
+            qm[g] = (rmp && okc) ? *reinterpret_cast<const uint4*>(rmp + c) : make_uint4(0, 0, 0, 0);
+            q1[g] = (r1p && okc) ? *reinterpret_cast<const uint4*>(r1p + c) : make_uint4(0, 0, 0, 0);
         }
         uint32_t v[16];
         __syncwarp();
@@ -227,46 +225,64 @@ __device__ __forceinline__ void epilogue_bf16(const ConvKParams& p, const EpiRow
     }
 }
 
+// 16-byte shared-memory accesses by 32-bit shared-window address (generic pointers cost 64-bit address arithmetic per access)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // Staged bf16 epilogue of ONE tile: the (optional) residual tile was TMA-loaded into the swizzled staging panels
 // (64 channels x 128 pixels x bf16 = 16 KB each, 128B swizzle like the A operand); every thread owns one pixel row,
 // combines accumulator + bias + residual + activation in place and the panels leave through one TMA store each.
-template <int ACT>
-__device__ __forceinline__ void epilogue_staged(const ConvKParams& p, uint8_t* stage_set, int row, uint32_t taddr0,
-                                                int c_base, int u_begin, int u_end, const float* bias_row) {
-    const float slope = p.slope, r1s = p.r1_sign;
-    const int res_mode = p.res_mode;
+// `srow` = shared address of this thread's 128-byte row in panel 0, `sw` = (row & 7) << 4 (the swizzle XOR of the row),
+// `bias_u` = this pixel's bias row at the tile's first channel (or null).  RES: 0 none, 1 add before the activation,
+// 2 fused multiply-add (r1_sign) after it -- compile-time so that the residual registers never live in local memory.
+template <int ACT, int RES>
+__device__ __forceinline__ void epilogue_staged(uint32_t srow, uint32_t sw, uint32_t taddr0, int u_begin, int u_end,
+                                                const float* bias_u, float slope, float r1s) {
     for (int u = u_begin; u < u_end; ++u) {
-        uint8_t* prow = stage_set + (u >> 2) * kATileBytes + row * 128;
-        const int j0 = (u & 3) * 2;                        // first 16-byte chunk of this unit inside the 128-byte row
-        uint4 q[2];
-        if (res_mode) {
-#pragma unroll
-            for (int g = 0; g < 2; ++g) q[g] = *reinterpret_cast<const uint4*>(prow + (((j0 + g) ^ (row & 7)) << 4));
-        }
+        const uint32_t a0 = srow + static_cast<uint32_t>(u >> 2) * kATileBytes + ((static_cast<uint32_t>(u & 3) << 5) ^ sw);
+        const uint32_t a1 = a0 ^ 16u;                      // the unit's second 16-byte chunk
         uint32_t v[16];
         __syncwarp();
         tmem_ld16(taddr0 + static_cast<uint32_t>(u * 16), v);
+        // residual and bias operands are requested while the TMEM load is in flight
+        uint4 q[2];
+        if (RES) {
+            q[0] = lds128(a0);
+            q[1] = lds128(a1);
+        }
+        float4 b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias_u) {
+            const float4* bp = reinterpret_cast<const float4*>(bias_u + u * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b[i] = __ldg(bp + i);
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-            const int c = c_base + u * 16 + g * 8;
-            float fg[8], r[8];
+            float fg[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) fg[i] = __uint_as_float(v[g * 8 + i]);
-            if (bias_row) {
-                const float4 b0 = *reinterpret_cast<const float4*>(bias_row + c);
-                const float4 b1 = *reinterpret_cast<const float4*>(bias_row + c + 4);
-                fg[0] += b0.x; fg[1] += b0.y; fg[2] += b0.z; fg[3] += b0.w;
-                fg[4] += b1.x; fg[5] += b1.y; fg[6] += b1.z; fg[7] += b1.w;
-            }
-            if (res_mode) bf16x8_to_f32(q[g], r);
-            if (res_mode == 1) {
+            fg[0] += b[2 * g].x; fg[1] += b[2 * g].y; fg[2] += b[2 * g].z; fg[3] += b[2 * g].w;
+            fg[4] += b[2 * g + 1].x; fg[5] += b[2 * g + 1].y; fg[6] += b[2 * g + 1].z; fg[7] += b[2 * g + 1].w;
+            if (RES == 1) {
+                float r[8];
+                bf16x8_to_f32(q[g], r);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) fg[i] += r[i];
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) fg[i] = act_fn<ACT>(fg[i], slope);
-            if (res_mode == 2) {
+            if (RES == 2) {
+                float r[8];
+                bf16x8_to_f32(q[g], r);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) fg[i] = fmaf(r1s, r[i], fg[i]);
             }
@@ -274,9 +290,17 @@ __device__ __forceinline__ void epilogue_staged(const ConvKParams& p, uint8_t* s
             __nv_bfloat162* oh2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
             for (int i = 0; i < 4; ++i) oh2[i] = __floats2bfloat162_rn(fg[2 * i], fg[2 * i + 1]);
-            *reinterpret_cast<uint4*>(prow + (((j0 + g) ^ (row & 7)) << 4)) = o;
+            sts128(g ? a1 : a0, o);
         }
     }
+}
+
+template <int ACT>
+__device__ __forceinline__ void epilogue_staged_res(int res_mode, uint32_t srow, uint32_t sw, uint32_t taddr0, int u_begin,
+                                                    int u_end, const float* bias_u, float slope, float r1s) {
+    if (res_mode == 0) epilogue_staged<ACT, 0>(srow, sw, taddr0, u_begin, u_end, bias_u, slope, r1s);
+    else if (res_mode == 1) epilogue_staged<ACT, 1>(srow, sw, taddr0, u_begin, u_end, bias_u, slope, r1s);
+    else epilogue_staged<ACT, 2>(srow, sw, taddr0, u_begin, u_end, bias_u, slope, r1s);
 }
 
 // fp32 outputs (NHWC for the class biases, planar for images / probabilities): few columns, simple loop
@@ -552,6 +576,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int u_begin = (units * share) / 2, u_end = (units * (share + 1)) / 2;
             const uint32_t res_bytes = static_cast<uint32_t>(n_panels) * kATileBytes;
             uint8_t* stage_set = smem_stage + team * n_panels * kATileBytes;
+            const uint32_t srow = smem_u32(stage_set) + static_cast<uint32_t>(row) * 128u;   // this thread's row in panel 0
+            const uint32_t sw = static_cast<uint32_t>(row & 7) << 4;
+            const int res_mode = p.res_mode;
+            const float slope = p.slope, r1s = p.r1_sign;
             const int as = team;
             auto load_residual = [&](int tile) {
                 int nt, ph, img, oh0, ow0;
@@ -596,11 +624,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[4 * 256 + local] = clock64();)
                 const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * 256);
                 const int c_base = nt * p.block_n;
+                const float* bias_u = bias_row ? bias_row + c_base : nullptr;
                 switch (p.act) {
-                    case CSBSR_ACT_RELU:    epilogue_staged<CSBSR_ACT_RELU>(p, stage_set, row, taddr0, c_base, u_begin, u_end, bias_row); break;
-                    case CSBSR_ACT_LEAKY:   epilogue_staged<CSBSR_ACT_LEAKY>(p, stage_set, row, taddr0, c_base, u_begin, u_end, bias_row); break;
-                    case CSBSR_ACT_SIGMOID: epilogue_staged<CSBSR_ACT_SIGMOID>(p, stage_set, row, taddr0, c_base, u_begin, u_end, bias_row); break;
-                    default:                epilogue_staged<CSBSR_ACT_NONE>(p, stage_set, row, taddr0, c_base, u_begin, u_end, bias_row); break;
+                    case CSBSR_ACT_RELU:    epilogue_staged_res<CSBSR_ACT_RELU>(res_mode, srow, sw, taddr0, u_begin, u_end, bias_u, slope, r1s); break;
+                    case CSBSR_ACT_LEAKY:   epilogue_staged_res<CSBSR_ACT_LEAKY>(res_mode, srow, sw, taddr0, u_begin, u_end, bias_u, slope, r1s); break;
+                    case CSBSR_ACT_SIGMOID: epilogue_staged_res<CSBSR_ACT_SIGMOID>(res_mode, srow, sw, taddr0, u_begin, u_end, bias_u, slope, r1s); break;
+                    default:                epilogue_staged_res<CSBSR_ACT_NONE>(res_mode, srow, sw, taddr0, u_begin, u_end, bias_u, slope, r1s); break;
                 }
                 CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[8 * 256 + local] = clock64();)
                 tcgen05_fence_before();
