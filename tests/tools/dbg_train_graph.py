@@ -3,7 +3,7 @@ import os, sys
 import numpy as np
 import torch
 import torch.nn.functional as F
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from csbsr_b200.modeling import params as P, train_graph as TG
 from oracle import torch_ref as T
 
