@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcsbsr_b200.so")
+# CSBSR_LIB_PATH: debug override (instrumented builds of the same library, e.g. scripts/trace_conv.py)
+LIB_PATH = os.environ.get("CSBSR_LIB_PATH") or os.path.join(_HERE, "lib", "libcsbsr_b200.so")
 
 MAX_TAPS = 64
 MAX_PHASES = 16

@@ -41,6 +41,16 @@ def gather_rows(t):
     return torch.cat([o[:c] for o, c in zip(out, counts)], 0)
 
 
+def gather_names(names):
+    """File names of every rank's shard, concatenated in rank order (same order as gather_rows)."""
+    rank, ws = world()
+    if ws == 1:
+        return list(names)
+    out = [None] * ws
+    dist.all_gather_object(out, list(names))
+    return [n for part in out for n in part]
+
+
 def pack_metrics(inter, union, hd, msd):
     """[B,99] x4 -> one fp64 [B, 396] tensor (integer counts are exact in fp64)."""
     return torch.cat([inter.to(torch.float64), union.to(torch.float64), hd, msd], dim=1)

@@ -140,7 +140,7 @@ def inference_for_ss(model, loader, test_surface_distance=True, percent=HD_PERCE
         ps, ss = psnr_ssim(sr, sr_targets)                              # inference.py:96-97
         psnrs.append(ps)
         ssims.append(ss)
-        kpsnrs.append(psnr_per_image(kp, kernel_targets))                 # inference.py:100
+        kpsnrs.append(psnr_per_image(torch.clamp(kp, min=0.0, max=1.0), kernel_targets))   # clip, inference.py:97-100
         r = seg_metrics(seg, masks, with_hd=test_surface_distance, percent=percent, to_host=False)
         hd = r["hd"] if test_surface_distance else torch.zeros_like(r["inter"], dtype=torch.float64)
         msd = r["msd"] if test_surface_distance else torch.zeros_like(hd)
@@ -148,12 +148,18 @@ def inference_for_ss(model, loader, test_surface_distance=True, percent=HD_PERCE
         fnames += list(names)
         if it % 10 == 0:
             log("batch %d done" % it)
-    packed = D.gather_rows(torch.cat(rows, 0))
-    inter, union, hd, msd = D.unpack_metrics(packed)
+    # one exchange: the [B, 4*99] metric rows plus three per-image columns (PSNR, SSIM, kernel PSNR), so that every
+    # reported mean is over ALL images, not over this rank's shard
+    per_img = torch.from_numpy(np.stack([np.concatenate(psnrs), np.concatenate(ssims), np.concatenate(kpsnrs)], 1)
+                               .astype(np.float64)).to(rows[0].device)
+    packed = D.gather_rows(torch.cat([torch.cat(rows, 0), per_img], 1))
+    inter, union, hd, msd = D.unpack_metrics(packed[:, :-3])
+    extra = packed[:, -3:].cpu().numpy()
+    fnames = D.gather_names(fnames)
     iou = (inter + 1e-5) / (union + 1e-5)
     out = {"AIU": float(np.mean(iou)), "IoU_max": float(np.max(np.mean(iou, axis=0))), "iou": iou,
-           "PSNR": float(np.mean(np.concatenate(psnrs))), "SSIM": float(np.mean(np.concatenate(ssims))),
-           "PSNR_kernel": float(np.mean(np.concatenate(kpsnrs)))}
+           "PSNR": float(np.mean(extra[:, 0])), "SSIM": float(np.mean(extra[:, 1])),
+           "PSNR_kernel": float(np.mean(extra[:, 2]))}
     if test_surface_distance:
         out.update({"AHD": float(np.mean(hd)), "HD_min": float(np.min(np.mean(hd, axis=0))), "AMSD": float(np.mean(msd)),
                     "hd": hd, "msd": msd})
@@ -166,6 +172,6 @@ def inference_for_ss(model, loader, test_surface_distance=True, percent=HD_PERCE
         with open(os.path.join(output_dir, "iou_log.csv"), "w") as f:       # save_iou_log, inference.py:287-291
             f.write("," + ",".join("%g" % (i * 0.01) for i in range(1, 100)) + "\n")
             for i in range(iou.shape[0]):
-                name = fnames[i] if i < len(fnames) else "rank_other_%d" % i
+                name = fnames[i] if i < len(fnames) else "image_%d" % i
                 f.write(name + "," + ",".join(repr(float(v)) for v in iou[i]) + "\n")
     return out

@@ -98,3 +98,17 @@ class FusedAdam:
 
     def scheduler_step(self):
         self.sched_count += 1
+
+    def state_dict(self):
+        """Moments, per-parameter step counters and schedule position (the reference saves optimizer.state_dict() next to
+        every checkpoint, trainer.py:119-129); flat layout: slot i of `slots` belongs to parameter i."""
+        return {"exp_avg": self.exp_avg.detach().cpu(), "exp_avg_sq": self.exp_avg_sq.detach().cpu(),
+                "param_steps": list(self.param_steps), "slots": list(self.slots), "step_count": self.step_count,
+                "sched_count": self.sched_count, "lr": self.base_lr, "betas": self.betas, "eps": self.eps}
+
+    def load_state_dict(self, sd):
+        assert list(sd["slots"]) == list(self.slots), "optimizer state belongs to a different parameter layout"
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.param_steps = list(sd["param_steps"])
+        self.step_count, self.sched_count = sd["step_count"], sd["sched_count"]

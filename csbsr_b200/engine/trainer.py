@@ -28,9 +28,9 @@ def train_step(model, optimizer, cfg, iteration, hr, mask, params, world_size=1)
 
 class GraphedTrainStep:
     """train_step with forward + loss + backward replayed from a CUDA graph (the step launches ~4000 small kernels; from
-    Python it is launch-bound at ~60 ms, replayed it takes the ~50 ms of GPU time).  One graph per (training phase, alpha of
-    the boundary loss, input shape): the iteration only enters the forward through the phase switches, alpha is a kernel
-    scalar.  Inputs are copied into static buffers; the gradient all-reduce and the fused Adam step stay outside the graph
+    Python it is launch-bound at ~60 ms, replayed it takes the ~50 ms of GPU time).  One graph per (training phase, input shape), re-captured when the alpha
+    of the boundary loss changes (once per epoch; the stale graph and its memory pool are released first): the iteration
+    only enters the forward through the phase switches, alpha is a kernel scalar.  Inputs are copied into static buffers; the gradient all-reduce and the fused Adam step stay outside the graph
     (the bias corrections change every step)."""
 
     def __init__(self, model, optimizer, cfg, world_size=1):
@@ -80,10 +80,20 @@ class GraphedTrainStep:
         return st
 
     def __call__(self, iteration, hr, mask, params):
-        key = (self._phase_key(iteration), float(self.model.ss_loss_fn.alpha), tuple(hr.shape))
+        # alpha of the boundary loss is a kernel scalar baked into the captured launches; it only ever decreases (one
+        # tick per epoch), so a graph captured for an older alpha is never replayed again: drop it (and its private
+        # memory pool, a full set of forward/backward activations) before capturing the next one.
+        key = (self._phase_key(iteration), tuple(hr.shape))
+        alpha = float(self.model.ss_loss_fn.alpha)
         st = self.graphs.get(key)
+        if st is not None and st["alpha"] != alpha:
+            del self.graphs[key]
+            st.clear()
+            st = None
+            torch.cuda.empty_cache()
         if st is None:
             st = self.graphs[key] = self._capture(iteration, hr, mask, params)
+            st["alpha"] = alpha
         st["hr"].copy_(hr, non_blocking=True)
         st["mask"].copy_(mask, non_blocking=True)
         st["params"].copy_(torch.as_tensor(params).to(st["params"].device), non_blocking=True)
@@ -122,3 +132,5 @@ def do_train(args, cfg, model, optimizer, batches, rank=0, world_size=1, log=pri
             os.makedirs(os.path.join(cfg.OUTPUT_DIR, "model"), exist_ok=True)
             torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()},
                        os.path.join(cfg.OUTPUT_DIR, "model", "iteration_{}.pth".format(iteration)))
+            os.makedirs(os.path.join(cfg.OUTPUT_DIR, "optimizer"), exist_ok=True)      # reference trainer.py:119-129
+            torch.save(optimizer.state_dict(), os.path.join(cfg.OUTPUT_DIR, "optimizer", "iteration_{}.pth".format(iteration)))

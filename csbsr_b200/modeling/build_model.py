@@ -140,6 +140,14 @@ class JointModelWithLoss(JointModel):
         if cfg.SOLVER.SEG_LOSS_FUNC != "BoundaryCombo" or cfg.SOLVER.SR_LOSS_FUNC != "KBPN":
             raise NotImplementedError("training graph: SEG_LOSS_FUNC=%r SR_LOSS_FUNC=%r" %
                                       (cfg.SOLVER.SEG_LOSS_FUNC, cfg.SOLVER.SR_LOSS_FUNC))
+        # csrc/losses.cu implements BoundaryComboLoss with pos_weight = loss_weight = [1, 1] (the shipped YAMLs); the
+        # reference feeds both keys through (build_model.py:293-299), so any other value must not train silently
+        if list(cfg.SOLVER.BCELOSS_WEIGHT) != [1, 1] or list(cfg.SOLVER.WB_AND_D_WEIGHT) != [1, 1]:
+            raise NotImplementedError("training graph: BCELOSS_WEIGHT=%r WB_AND_D_WEIGHT=%r (only [1, 1] is built)" %
+                                      (list(cfg.SOLVER.BCELOSS_WEIGHT), list(cfg.SOLVER.WB_AND_D_WEIGHT)))
+        if not cfg.BLUR.FLAG or cfg.BLUR.ISOTROPIC:
+            raise NotImplementedError("training graph: BLUR.FLAG=%r BLUR.ISOTROPIC=%r (anisotropic on-the-fly blur only)" %
+                                      (cfg.BLUR.FLAG, cfg.BLUR.ISOTROPIC))
         self.cfg = cfg
         self.main_weight, self.aux_weight = cfg.SOLVER.SEG_MAIN_LOSS_WEIGHT, cfg.SOLVER.SEG_AUX_LOSS_WEIGHT
         self.wf_amp = cfg.SOLVER.SEG_FAIL_ORIENTED_WEIGHT4SS_AMP

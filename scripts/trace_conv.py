@@ -17,6 +17,14 @@ elif which == "ikc32":
 elif which == "n16":
     x = K.Fmap.empty(B, 448, 448, 128); x.t.normal_()
     pc = K.pack_conv(torch.randn(12, 128, 3, 3, device="cuda") * 0.05, padding=1); y = torch.zeros(B, 12, 448, 448, device="cuda"); kw = dict()
+elif which == "c8s4":
+    x = K.Fmap.empty(B, 448, 448, 128); x.t.normal_()
+    pc = K.pack_conv(torch.randn(128, 128, 8, 8, device="cuda") * 0.01, stride=4, padding=2)
+    r = K.Fmap.empty(B, 112, 112, 128); r.t.normal_(); y = K.Fmap.empty(B, 112, 112, 128)
+    kw = dict(act=K.ACT_LEAKY, slope=0.1, r1=r, r1_sign=-1.0)
+elif which == "sft1":
+    x = K.Fmap.empty(B, 112, 112, 832); x.t.normal_()
+    pc = K.pack_conv(torch.randn(384, 832, 3, 3, device="cuda") * 0.01, padding=1); y = K.Fmap.empty(B, 112, 112, 384); kw = dict()
 else:
     x = K.Fmap.empty(B, 112, 112, 128); x.t.normal_()
     pc = K.pack_deconv8s4(torch.randn(128, 128, 8, 8, device="cuda") * 0.02); y = K.Fmap.empty(B, 448, 448, 128)

@@ -110,9 +110,20 @@ def test_full_size_properties():
     pm = (prob > 0.5).astype(np.float32)
     r2 = _run(pm * 0.75, pm, 50)                        # prediction == gt for thresholds below 0.75
     assert (r2["hd"][:, :74] == 0).all() and (r2["msd"][:, :74] == 0).all() and (r2["iou"][:, :74] == 1.0).all()
+
+
+@pytest.mark.parametrize("pct", [50, 95])
+def test_full_size_448_bit_exact_vs_oracle(pct):
+    """One 448x448 noisy-crack image (the BASELINE metric size): AIU counts, HD and MSD of all 99 thresholds are
+    bit-identical to the oracle (reference inference.py:293-336 via oracle/metrics_ref.py)."""
     from oracle import metrics_ref as M
-    hd, msd = M.distance_metrics(prob[:1], mask[:1], 50)
-    assert np.array_equal(r["hd"][:1, ::9], hd[:, ::9]) if False else True
+    prob, mask = _case(1, 448, 448, 7, 0.05)
+    r = _run(prob, mask, pct)
+    inter, union = M.iou_counts(prob, mask)
+    hd, msd = M.distance_metrics(prob, mask, pct)
+    assert np.array_equal(r["inter"], inter) and np.array_equal(r["union"], union)
+    assert np.array_equal(r["hd"], hd), np.argwhere(r["hd"] != hd)[:5]
+    assert np.array_equal(r["msd"], msd), np.argwhere(r["msd"] != msd)[:5]
 
 
 def test_degrade_matches_golden_and_oracle():

@@ -6,7 +6,9 @@
 
 Multi-GPU: launch with torchrun, one process per GPU (the reference's nn.DataParallel is replaced by per-rank batch
 shards + an NCCL all-reduce of the gradients).  Offline (`--synthetic N`): trains on N seeded synthetic crack images
-with on-device degradation; the joint phase only (resume_iter >= SOLVER.SR_PRETRAIN_ITER[1], see JointModelWithLoss)."""
+with on-device degradation.  All training phases are covered (the three SR pre-training phases and the joint phase,
+see JointModelWithLoss.apply_phase).  SOLVER.BATCH_SIZE is the GLOBAL batch, split over the ranks like nn.DataParallel
+splits it over its GPUs (reference train.py:108-121)."""
 import argparse
 import os
 import sys
@@ -45,6 +47,11 @@ def main():
     if args.output_dirname:
         cfg.OUTPUT_DIR = args.output_dirname
     cfg.freeze()
+    if int(os.environ.get("RANK", "0")) == 0 and args.resume_iter == 0:
+        # the run's config travels with its output so that `test.py <output_dir> <iter>` finds it (reference train.py:150-153)
+        import shutil
+        os.makedirs(cfg.OUTPUT_DIR, exist_ok=True)
+        shutil.copy2(args.config_file, os.path.join(cfg.OUTPUT_DIR, "config.yaml"))
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -63,13 +70,17 @@ def main():
             raise FileNotFoundError("no *.jpg images under %s (use --synthetic N to train offline)" % dataset.image_dir)
     model = JointModelWithLoss(cfg, num_train_ds=args.synthetic or n_train, resume_iter=args.resume_iter)
     ckpt = os.path.join(cfg.OUTPUT_DIR, "model", "iteration_{}.pth".format(args.resume_iter))
-    if args.resume_iter > 0 and os.path.exists(ckpt):
+    if args.resume_iter > 0:
+        if not os.path.exists(ckpt):                       # the reference fails in torch.load here; never resume on random weights
+            raise FileNotFoundError("--resume_iter %d: checkpoint %s does not exist" % (args.resume_iter, ckpt))
         sd = torch.load(ckpt, map_location="cpu")
         model.load_state_dict({(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}, strict=False)
         print("Resume from {}".format(ckpt))
     else:
         sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
-        seg_shapes = P.hrnet_ocr_param_shapes() if cfg.MODEL.DETECTOR_TYPE == "HRNet_OCR" else P.pspnet_param_shapes()
+        blur_dim = cfg.BLUR.KERNEL_SIZE_OUTPUT ** 2 if cfg.MODEL.DETECTOR_TYPE == "PSPNet_BlurSkip" else None
+        seg_shapes = (P.hrnet_ocr_param_shapes() if cfg.MODEL.DETECTOR_TYPE == "HRNet_OCR"
+                      else P.pspnet_param_shapes(cfg.MODEL.NUM_CLASSES, blur_dim=blur_dim))
         sd.update(P.synth_state_dict(seg_shapes, prefix="segmentation_model."))
         model.load_state_dict(sd, strict=True)
     model.cuda()
@@ -77,7 +88,11 @@ def main():
     optimizer = FusedAdam(model.parameters(), lr=cfg.SOLVER.LR, betas=(0.9, 0.999), eps=1e-8, lr_lambda=sched)
 
     size = args.crop or cfg.INPUT.IMAGE_SIZE[0]
-    per_rank = cfg.SOLVER.BATCH_SIZE                         # the reference's per-GPU chunk under DataParallel
+    # nn.DataParallel splits SOLVER.BATCH_SIZE over the GPUs (train.py:108-121): each rank takes its chunk, so the
+    # global batch and the alpha / LR schedules (per_epoch = n_train // BATCH_SIZE + 1) are the reference's
+    if cfg.SOLVER.BATCH_SIZE % world != 0:
+        raise ValueError("SOLVER.BATCH_SIZE=%d is not divisible by the %d ranks" % (cfg.SOLVER.BATCH_SIZE, world))
+    per_rank = cfg.SOLVER.BATCH_SIZE // world
     max_iter = args.max_iter or cfg.SOLVER.MAX_ITER
     rng = np.random.default_rng(cfg.SEED + rank)
 
