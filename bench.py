@@ -256,10 +256,13 @@ def main():
     params_dev = torch.as_tensor(params).to(dev)
     mchunk = 16
 
+    keep = {}
+
     def hot_path(hr, mask):
         """degrade -> SR -> seg -> metrics for one batch resident on the device; returns device tensors."""
         lr, _ = G.degrade(hr, params_dev)
         sr, seg, kp = model(lr, None)
+        keep["seg"] = seg                       # parity self-check below reads the probability maps of the last eager call
         outs = []
         for i in range(0, B, mchunk):
             r = E.seg_metrics(seg[i:i + mchunk], mask[i:i + mchunk], with_hd=True, to_host=False)
@@ -333,8 +336,21 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), out
 
-    hot_path(hr_dev, mask_dev)                                  # first call packs the weights and sizes the workspaces
+    first = hot_path(hr_dev, mask_dev)                          # first call packs the weights and sizes the workspaces
     torch.cuda.synchronize()
+    # parity self-check (oracle as the checker only): the step's integer I / U counts of every image and the HD / MSD
+    # rows of image 0 must equal the reference's sweep (inference.py:111-121, 293-336) on the same probability maps
+    parity = None
+    if rank == 0:
+        from oracle import metrics_ref
+        seg_h, mask_h = keep["seg"].cpu().numpy(), mask_dev.cpu().numpy()
+        inter_o, union_o = metrics_ref.iou_counts(seg_h, mask_h)
+        hd_o, msd_o = metrics_ref.distance_metrics(seg_h[:1], mask_h[:1], 50)
+        inter_d, union_d, hd_d, msd_d = D.unpack_metrics(first)
+        parity = bool(np.array_equal(inter_d, inter_o) and np.array_equal(union_d, union_o)
+                      and np.array_equal(hd_d[:1], hd_o) and np.array_equal(msd_d[:1], msd_o))
+        if not parity:
+            raise AssertionError("bench.py: AIU counts / HD / MSD of the step differ from the oracle sweep")
     l_cap = _lib.LAUNCHES
     if not args.no_graph:
         try_capture()
@@ -382,6 +398,7 @@ def main():
                    "batch_per_gpu": B, "chunk": args.chunk, "hr": HR, "scale": 4, "weights": "synthetic random-init (seed 1121)",
                    "l2": "per-step inputs (%.0f MB) and activations exceed the 126 MB L2; no flush needed" % (h2d / 1e6),
                    "aiu": aiu, "ahd_p50": ahd,
+                   "parity_check": "I/U counts of all %d images and HD/MSD of image 0 bit-equal to the oracle sweep: %s" % (B, parity),
                    "launch": "CUDA graph replay of the hot path" if graph_state["graph"] is not None else "eager launches"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},

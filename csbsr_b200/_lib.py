@@ -91,6 +91,10 @@ _SIGNATURES = {
     "csbsr_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]),
     "csbsr_patchify": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 12 + [C.c_void_p, C.c_void_p, C.c_int,
                                                                             C.c_void_p]),
+    "csbsr_kpred_wpack_bytes": (C.c_size_t, [C.c_int]),
+    "csbsr_kpred_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
+    "csbsr_kpred_sr_chain": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_float, C.c_void_p]),
+    "csbsr_kpred_cat_chain": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_size_t] + [C.c_int] * 3 + [C.c_float, C.c_void_p]),
     "csbsr_gap_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "csbsr_kernel_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "csbsr_vec_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
@@ -161,7 +165,7 @@ def stream_ptr():
 
 
 # kernels launched per C-ABI call (our own __global__ functions only; memsets are not counted)
-KERNELS_PER_CALL = {"csbsr_conv_igemm": 1, "csbsr_clip_instnorm_stats": 2, "csbsr_degrade": 3, "csbsr_seg_metrics": 14}
+KERNELS_PER_CALL = {"csbsr_conv_igemm": 1, "csbsr_kpred_cat_chain": 2, "csbsr_clip_instnorm_stats": 2, "csbsr_degrade": 3, "csbsr_seg_metrics": 14}
 LAUNCHES = 0
 
 

@@ -46,4 +46,18 @@ __device__ __forceinline__ int warp_sum(int v) {
     return v;
 }
 
+// Block-wide sum in a FIXED order (shuffle tree inside each warp, then the warps in index order): bit-reproducible, unlike
+// shared-memory atomics.  `scratch` holds one value per warp (<= 32); every thread returns the total.
+template <typename T>
+__device__ __forceinline__ T block_sum_det(T v, T* scratch) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[w] = v;
+    __syncthreads();
+    T s = scratch[0];
+    for (int i = 1; i < nw; ++i) s += scratch[i];
+    return s;
+}
+
 }  // namespace csbsr

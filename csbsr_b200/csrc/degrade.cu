@@ -11,7 +11,6 @@ namespace csbsr {
 // one block per sample; params[b] = (theta [rad], sigma_x, sigma_y) in fp64
 __global__ void kernel_synth_kernel(const double* __restrict__ params, float* __restrict__ out, int ks) {
     extern __shared__ double sv[];
-    __shared__ double ssum;
     const int b = blockIdx.x;
     const double theta = params[b * 3], sx = params[b * 3 + 1], sy = params[b * 3 + 2];
     const double ct = cos(theta), st = sin(theta);
@@ -21,8 +20,6 @@ __global__ void kernel_synth_kernel(const double* __restrict__ params, float* __
     const double bb = st * ct * (1.0 / sy2 - 1.0 / sx2);
     const double c = st2 / sx2 + ct2 / sy2;
     const int r = ks / 2;
-    if (threadIdx.x == 0) ssum = 0.0;
-    __syncthreads();
     double local = 0.0;
     for (int i = threadIdx.x; i < ks * ks; i += blockDim.x) {
         const double y = static_cast<double>(i / ks - r), x = static_cast<double>(i % ks - r);
@@ -30,10 +27,9 @@ __global__ void kernel_synth_kernel(const double* __restrict__ params, float* __
         sv[i] = v;
         local += v;
     }
-    local = warp_sum(local);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&ssum, local);
-    __syncthreads();
-    for (int i = threadIdx.x; i < ks * ks; i += blockDim.x) out[b * ks * ks + i] = static_cast<float>(sv[i] / ssum);
+    __shared__ double red[32];
+    const double total = block_sum_det(local, red);            // fixed summation order: bit-reproducible kernels
+    for (int i = threadIdx.x; i < ks * ks; i += blockDim.x) out[b * ks * ks + i] = static_cast<float>(sv[i] / total);
 }
 
 // antialiased bicubic weights as aten's upsample_bicubic2d_aa (a = -0.5, support = 2*scale for scale >= 1)

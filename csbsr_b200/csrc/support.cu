@@ -89,19 +89,40 @@ __global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __re
 }
 
 // ------------------------------------------------------------------ global average pool NHWC bf16 -> f32 [N][C]
+// One block per image, 8-channel (128-bit) loads; the block's 256 threads split into (pixel lane, channel vector); per-thread
+// sums run over pixels in a fixed stride order and the pixel lanes are combined in index order: bit-reproducible (the first
+// version used atomicAdd across slices).  Only the initial kernel prediction still pools through here (12544 pixels x 64
+// channels per image); the per-stage pools of the kernel predictor live in the fused chain (kpred_chain.cu).
 __global__ void gap_nhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int HW, int pitch,
-                                int coff, int C, int slices) {
-    // grid: (N, slices); block: C threads (rounded to 32). Each block sums a slice of pixels; atomicAdd to out.
-    const int n = blockIdx.x, sl = blockIdx.y;
-    const int c = threadIdx.x;
-    if (c >= C) return;
-    const int per = (HW + slices - 1) / slices;
-    const int p0 = sl * per;
-    const int p1 = min(HW, p0 + per);
-    const __nv_bfloat16* base = x + static_cast<size_t>(n) * HW * pitch + coff + c;
-    float acc = 0.f;
-    for (int p = p0; p < p1; ++p) acc += __bfloat162float(base[static_cast<size_t>(p) * pitch]);
-    atomicAdd(out + n * C + c, acc / static_cast<float>(HW));
+                                int coff, int C) {
+    extern __shared__ float gp[];                       // [lanes][nvec * 8]
+    const int n = blockIdx.x;
+    const int nvec = (C + 7) / 8;
+    const int lanes = blockDim.x / nvec;
+    const int cv = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (pl < lanes) {
+        const __nv_bfloat16* base = x + static_cast<size_t>(n) * HW * pitch + coff + cv * 8;
+        for (int p = pl; p < HW; p += lanes) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(p) * pitch));
+            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[2 * i] += __uint_as_float(w[i] << 16);
+                acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gp[(pl * nvec + cv) * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += gp[l * nvec * 8 + c];
+        out[n * C + c] = t / static_cast<float>(HW);
+    }
 }
 
 // ------------------------------------------------------------------ kernel-vector update
@@ -124,10 +145,8 @@ __global__ void kernel_update_kernel(const float* __restrict__ v, const float* _
     extern __shared__ float sh[];
     float* sv = sh;                    // ke*ke
     float* so = sh + ke * ke;          // ko*ko
-    __shared__ float ssum;
     const int b = blockIdx.x;
     for (int i = threadIdx.x; i < ke * ke; i += blockDim.x) sv[i] = v[b * ke * ke + i];
-    if (threadIdx.x == 0) ssum = 0.f;
     __syncthreads();
     const float scale = static_cast<float>(ke) / static_cast<float>(ko);
     float local = 0.f;
@@ -154,25 +173,20 @@ __global__ void kernel_update_kernel(const float* __restrict__ v, const float* _
         so[i] = acc;
         local += acc;
     }
-    local = warp_sum(local);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&ssum, local);
-    __syncthreads();
-    const float inv = normalize ? 1.f / ssum : 1.f;
+    __shared__ float red[32];
+    const float total = block_sum_det(local, red);             // fixed summation order: bit-reproducible
+    const float inv = normalize ? 1.f / total : 1.f;
     for (int i = threadIdx.x; i < ko * ko; i += blockDim.x) out[b * ko * ko + i] = so[i] * inv;
 }
 
 // out[b] = v[b] / sum(v[b])   (build_model.py:491-494)
 __global__ void vec_normalize_kernel(const float* __restrict__ v, float* __restrict__ out, int L) {
-    __shared__ float ssum;
-    if (threadIdx.x == 0) ssum = 0.f;
-    __syncthreads();
     const int b = blockIdx.x;
     float local = 0.f;
     for (int i = threadIdx.x; i < L; i += blockDim.x) local += v[b * L + i];
-    local = warp_sum(local);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&ssum, local);
-    __syncthreads();
-    for (int i = threadIdx.x; i < L; i += blockDim.x) out[b * L + i] = v[b * L + i] / ssum;
+    __shared__ float red[32];
+    const float total = block_sum_det(local, red);
+    for (int i = threadIdx.x; i < L; i += blockDim.x) out[b * L + i] = v[b * L + i] / total;
 }
 
 // broadcast a per-sample vector over a small NHWC bf16 image (spatially constant conditioning)
@@ -286,8 +300,9 @@ __global__ void bicubic_up_kernel(const float* __restrict__ x, float* __restrict
 }
 
 // ------------------------------------------------------------------ clip to [0,1] in place + per-(n,c) statistics
-__global__ void clip_stats_kernel(float* __restrict__ x, double* __restrict__ sums, int HW, int do_clip) {
-    // grid: (slices, N*C). sums[nc*2+0] += sum, sums[nc*2+1] += sum of squares (fp64 accumulation)
+__global__ void clip_stats_kernel(float* __restrict__ x, double* __restrict__ part, int HW, int do_clip) {
+    // grid: (slices, N*C). part[(nc*slices + slice)*2 + {0,1}] = this block's sum / sum of squares (fp64), reduced in a
+    // fixed order: bit-reproducible statistics
     const int nc = blockIdx.y;
     float* xp = x + static_cast<size_t>(nc) * HW;
     double s = 0.0, ss = 0.0;
@@ -300,19 +315,25 @@ __global__ void clip_stats_kernel(float* __restrict__ x, double* __restrict__ su
         s += v;
         ss += static_cast<double>(v) * v;
     }
-    s = warp_sum(s);
-    ss = warp_sum(ss);
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&sums[nc * 2], s);
-        atomicAdd(&sums[nc * 2 + 1], ss);
+    __shared__ double red[32];
+    s = block_sum_det(s, red);
+    ss = block_sum_det(ss, red);
+    if (threadIdx.x == 0) {
+        part[(static_cast<size_t>(nc) * gridDim.x + blockIdx.x) * 2] = s;
+        part[(static_cast<size_t>(nc) * gridDim.x + blockIdx.x) * 2 + 1] = ss;
     }
 }
-__global__ void finish_stats_kernel(const double* __restrict__ sums, float* __restrict__ mean,
-                                    float* __restrict__ rstd, int NC, int HW, float eps) {
+__global__ void finish_stats_kernel(const double* __restrict__ part, float* __restrict__ mean,
+                                    float* __restrict__ rstd, int NC, int HW, float eps, int slices) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NC) return;
-    const double m = sums[i * 2] / HW;
-    double var = sums[i * 2 + 1] / HW - m * m;      // biased variance (InstanceNorm2d)
+    double sum = 0.0, sq = 0.0;
+    for (int k = 0; k < slices; ++k) {                  // fixed order
+        sum += part[(static_cast<size_t>(i) * slices + k) * 2];
+        sq += part[(static_cast<size_t>(i) * slices + k) * 2 + 1];
+    }
+    const double m = sum / HW;
+    double var = sq / HW - m * m;                       // biased variance (InstanceNorm2d)
     if (var < 0) var = 0;
     mean[i] = static_cast<float>(m);
     rstd[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
@@ -571,13 +592,15 @@ extern "C" int csbsr_patchify(const float* x, void* y, int n, int c, int h, int 
 
 extern "C" int csbsr_gap_nhwc(const void* x, float* out, int n, int hw, int pitch, int coff, int c, void* stream) {
     CSBSR_REQUIRE(x && out && n > 0 && hw > 0 && c > 0 && c <= 1024, "gap_nhwc: bad arguments");
-    CSBSR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n * c, STREAM(stream)));
-    int slices = hw / 256;
-    if (slices < 1) slices = 1;
-    if (slices > 128) slices = 128;
-    dim3 grid(n, slices);
-    gap_nhwc_kernel<<<grid, (c + 31) / 32 * 32, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, hw,
-                                                                    pitch, coff, c, slices);
+    // whole 8-channel vectors are read (channels up to the next multiple of 8 must exist inside the pixel's pitch)
+    CSBSR_REQUIRE(pitch % 8 == 0 && coff % 8 == 0 && coff + (c + 7) / 8 * 8 <= pitch,
+                  "gap_nhwc: pitch / offset must be multiples of 8 and cover the rounded-up channel window");
+    const int nvec = (c + 7) / 8;
+    const int threads = nvec <= 256 ? 256 : 1024;
+    CSBSR_REQUIRE(nvec <= threads, "gap_nhwc: too many channels");
+    const int lanes = threads / nvec;
+    gap_nhwc_kernel<<<n, threads, sizeof(float) * lanes * nvec * 8, STREAM(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), out, hw, pitch, coff, c);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -644,18 +667,21 @@ extern "C" int csbsr_bicubic_upsample(const float* x, float* y, int nc, int h, i
     return 0;
 }
 
-extern "C" size_t csbsr_instnorm_workspace_bytes(int nc) { return sizeof(double) * 2 * static_cast<size_t>(nc); }
+static constexpr int kInstnormMaxSlices = 64;
+extern "C" size_t csbsr_instnorm_workspace_bytes(int nc) {
+    return sizeof(double) * 2 * kInstnormMaxSlices * static_cast<size_t>(nc);
+}
 
 extern "C" int csbsr_clip_instnorm_stats(float* x, float* mean, float* rstd, void* workspace, int nc, int hw,
                                          int do_clip, float eps, void* stream) {
     CSBSR_REQUIRE(x && mean && rstd && workspace && nc > 0 && hw > 0, "clip_instnorm_stats: bad arguments");
-    double* sums = reinterpret_cast<double*>(workspace);
-    CSBSR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * nc, STREAM(stream)));
+    double* part = reinterpret_cast<double*>(workspace);
     int slices = (hw + 256 * 16 - 1) / (256 * 16);
     if (slices < 1) slices = 1;
+    if (slices > kInstnormMaxSlices) slices = kInstnormMaxSlices;
     dim3 grid(slices, nc);
-    clip_stats_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, sums, hw, do_clip);
-    finish_stats_kernel<<<(nc + 127) / 128, 128, 0, STREAM(stream)>>>(sums, mean, rstd, nc, hw, eps);
+    clip_stats_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, part, hw, do_clip);
+    finish_stats_kernel<<<(nc + 127) / 128, 128, 0, STREAM(stream)>>>(part, mean, rstd, nc, hw, eps, slices);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -398,6 +398,44 @@ def gap(x, out, c=None):
     return out
 
 
+def pack_chain(layers):
+    """Weights of a fused conv chain (csrc/kpred_chain.cu) in its shared-memory plane layout: per layer
+    [tap][cin_pad/8][cout_pad][8] bf16, concatenated.  `layers`: list of (weight [co,ci,R,S], cin_pad, cout_pad).
+    Runs on the host (no device launches); returns a CPU uint8 tensor."""
+    parts = []
+    for w, cin_pad, cout_pad in layers:
+        w = w.detach().float().cpu()
+        co, ci, R, S = w.shape
+        assert ci <= cin_pad and co <= cout_pad and cin_pad % 8 == 0
+        a = torch.zeros((R * S, cin_pad, cout_pad), dtype=torch.float32)
+        a[:, :ci, :co] = w.permute(2, 3, 1, 0).reshape(R * S, ci, co)
+        a = a.view(R * S, cin_pad // 8, 8, cout_pad).permute(0, 1, 3, 2).contiguous()       # [tap][plane][n][8]
+        parts.append(a.to(torch.bfloat16).view(torch.uint8).reshape(-1))
+    return torch.cat(parts)
+
+
+def kpred_sr_chain(img, wpack, out, slope=0.01):
+    """fe_SR.0..4 of the kernel predictor in one kernel: img fp32 [B,3,H,W] -> out Fmap [B,H,W,64]."""
+    n, c, h, w = img.shape
+    assert c == 3 and out.pitch == 64 and out.coff == 0 and (out.n, out.h, out.w) == (n, h, w)
+    assert wpack.numel() == _lib.lib().csbsr_kpred_wpack_bytes(0)
+    rc = _lib.lib().csbsr_kpred_sr_chain(_f32(img), wpack.data_ptr(), out.ptr(), n, h, w, C.c_float(slope), _lib.stream_ptr())
+    _lib.check(rc, "csbsr_kpred_sr_chain")
+    _lib.count_launch("csbsr_kpred_sr_chain")
+    return out
+
+
+def kpred_cat_chain(x, wpack, cls_bias, out, ws, slope=0.01):
+    """fe_cat.0..2 + global average pool in one kernel: x Fmap [B,H,W,64], cls_bias fp32 [B,5,5,64] -> out fp32 [B,c]."""
+    assert x.pitch == 64 and x.coff == 0 and cls_bias.shape == (x.n, 5, 5, 64) and out.shape[0] == x.n
+    assert wpack.numel() == _lib.lib().csbsr_kpred_wpack_bytes(1)
+    rc = _lib.lib().csbsr_kpred_cat_chain(x.ptr(), wpack.data_ptr(), _f32(cls_bias), _f32(out), out.shape[1], ws.data_ptr(),
+                                          ws.numel() * ws.element_size(), x.n, x.h, x.w, C.c_float(slope), _lib.stream_ptr())
+    _lib.check(rc, "csbsr_kpred_cat_chain")
+    _lib.count_launch("csbsr_kpred_cat_chain")
+    return out
+
+
 def kernel_update(v, pre, out, ke, ko, normalize=True):
     _call("csbsr_kernel_update", _f32(v), _f32(pre) if pre is not None else None, _f32(out), v.shape[0], ke, ko,
           int(normalize))

@@ -51,6 +51,9 @@ class KBPNEngine:
         self.ws = _Workspace(device)
         self.p = None
         self.debug = None                 # set to a dict to capture per-stage intermediates (tests only)
+        # kernel predictor as two fused chain kernels (default) or one conv launch per layer (CSBSR_KPRED_FUSED=0, for A/B runs)
+        import os
+        self.fused_kpred = os.environ.get("CSBSR_KPRED_FUSED", "1") != "0"
 
     # ------------------------------------------------------------------ weight packing
     def load(self, sd, prefix="sr_model."):
@@ -94,6 +97,16 @@ class KBPNEngine:
             st["cat0_k"] = K.pack_conv(wcat[:, kc:].contiguous(), cout_pad=64)
             st["cat1"] = K.pack_conv(g(kp + "fe_cat.1.layer.weight"), padding=1, cout_pad=64, cin_pad=32)
             st["cat2"] = K.pack_conv(g(kp + "fe_cat.2.layer.weight"), padding=1, cout_pad=64, cin_pad=32)
+            # the same layers for the fused chain kernels (csrc/kpred_chain.cu), packed on the host into their smem layout
+            raw = lambda k: sd[prefix + k].detach().float().cpu()
+            st["chain_sr"] = K.pack_chain([(as1x1(raw(kp + "fe_SR.0.layer.weight")), 32, 64),
+                                           (raw(kp + "fe_SR.1.layer.weight"), 64, 32),
+                                           (raw(kp + "fe_SR.2.layer.weight"), 32, 32),
+                                           (raw(kp + "fe_SR.3.layer.weight"), 32, 32),
+                                           (raw(kp + "fe_SR.4.layer.weight"), 32, 64)]).to(dev)
+            st["chain_cat"] = K.pack_chain([(raw(kp + "fe_cat.0.layer.weight")[:, :kc].contiguous(), 64, 32),
+                                            (raw(kp + "fe_cat.1.layer.weight"), 32, 32),
+                                            (raw(kp + "fe_cat.2.layer.weight"), 32, 64)]).to(dev)
             # KBlock.up_conv1: ConvTranspose2d(3 -> C, 8, 4, 2) evaluated on the 3x3-patchified LR error:
             # per output phase a 1x1 conv over K = (a*3+b)*3+c with w[c, co, rho_h+6-4a, rho_w+6-4b]
             w = g(sp + "kb.up_conv1.layer.weight")                       # [3, C, 8, 8]
@@ -225,7 +238,16 @@ class KBPNEngine:
         a = K.conv(small, st["fk0"], ws.fmap("k5a", B, 5, 5, 64), act=ACT_LEAKY, slope=0.01)
         a = K.conv(a, st["fk1"], ws.fmap("k5b", B, 5, 5, 64), act=ACT_LEAKY, slope=0.01)
         cb = K.conv(a, st["cat0_k"], F32Map(ws.f32("k5bias", B, 5, 5, 64)))
-        # image branch (fe_SR) at HR
+        if self.fused_kpred:
+            # image branch + fe_cat + GAP as two fused chains: the 32..64-channel 448^2 intermediates never leave the SM
+            a = K.kpred_sr_chain(sr_t, st["chain_sr"], ws.fmap("hr_a64", B, H, W, 64), slope=0.01)
+            nws = K._lib.lib().csbsr_kpred_workspace_bytes(B, H, W)
+            d49 = K.kpred_cat_chain(a, st["chain_cat"], cb.t, ws.f32("v49", B, kc), ws.f32("kpred_ws", nws // 4), slope=0.01)
+            if self.debug is not None:
+                self.debug["delta49_%d" % s] = d49.clone()
+            out = ws.f32("kvec_b" if (s % 2 == 0) else "kvec_a", B, cond)
+            return K.kernel_update(d49, kvec, out, self.ke, self.ko, True)
+        # image branch (fe_SR) at HR, one conv launch per layer
         sp = K.patchify(sr_t, ws.fmap("hr_p64", B, H, W, 64), 3, 3, 1, 1)
         a = K.conv(sp, st["sr0"], ws.fmap("hr_a64", B, H, W, 64), act=ACT_RELU)
         b = K.conv(a, st["sr1"], ws.fmap("hr_b64", B, H, W, 64), act=ACT_LEAKY, slope=0.01)

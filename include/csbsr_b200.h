@@ -164,6 +164,20 @@ int csbsr_nchw_f32_to_nhwc_bf16(const float* x, void* y, int n, int c, int h, in
  * (kbpn.py:528), KBlock.up_conv1 (kbpn.py:375) and ResNet conv1 (extractors.py:115). */
 int csbsr_patchify(const float* x, void* y, int n, int c, int h, int w, int oh, int ow, int r, int s, int stride,
                    int pad, int y_pitch, int cwrite, const float* mean, const float* rstd, int clamp01, void* stream);
+/* Fused kernel-predictor chains of KBlock (KernelPredictorLikeIKC.forward, model/modeling/kbpn.py:562-578, layers :528-541):
+ * every intermediate of the chain stays in shared memory / TMEM (csrc/kpred_chain.cu).
+ *   sr chain : img fp32 [b,3,h,w] -> fe_SR.0 (3x3, ReLU) -> fe_SR.1 (1x1) -> fe_SR.2 -> fe_SR.3 -> fe_SR.4 (3x3, LeakyReLU `slope`)
+ *              -> out bf16 NHWC [b,h,w,64] (49 channels used);
+ *   cat chain: in bf16 NHWC [b,h,w,64] -> fe_cat.0 (1x1 over the image branch + cls_bias fp32 [b,5,5,64]: the kernel branch
+ *              fe_kernel(...) folded into a per-sample border-class bias) -> fe_cat.1 -> fe_cat.2 -> nn.AdaptiveAvgPool2d(1)
+ *              -> gap_out fp32 [b, gap_c] (mean over h*w).
+ * wpack: the chain's weights in the kernel's shared-memory layout, per layer [tap][cin/8][cout_pad][8] bf16, layers in order
+ * (csbsr_kpred_wpack_bytes(which) bytes; which = 0 sr chain, 1 cat chain).  ws: csbsr_kpred_workspace_bytes(b,h,w) bytes. */
+size_t csbsr_kpred_wpack_bytes(int which);
+size_t csbsr_kpred_workspace_bytes(int b, int h, int w);
+int csbsr_kpred_sr_chain(const float* img, const void* wpack, void* out, int b, int h, int w, float slope, void* stream);
+int csbsr_kpred_cat_chain(const void* in, const void* wpack, const float* cls_bias, float* gap_out, int gap_c, void* ws,
+                          size_t ws_bytes, int b, int h, int w, float slope, void* stream);
 /* nn.AdaptiveAvgPool2d(1) (kbpn.py:324,391,565,572): out[n][c] = mean over h*w, fp32 */
 int csbsr_gap_nhwc(const void* x, float* out, int n, int hw, int pitch, int coff, int c, void* stream);
 /* out[b] = norm((pre ? pre[b] : 0) + bicubic_{ke x ke -> ko x ko}(v[b])), norm = divide by the sum when

@@ -230,7 +230,7 @@ def gen_psnr_ssim():
     print("psnr_ssim.npz", PSNR()(a, b), SSIM()(a, b))
 
 
-def gen_train(bn_eval=False, hrnet=False, iteration=40000, blurskip=False):
+def gen_train(bn_eval=False, hrnet=False, iteration=40000, blurskip=False, batch8=False):
     """One JointModelWithLoss forward + backward of the UNMODIFIED reference at iteration 40000 (all phases active,
     w^F on, m^F = 1), Dropout2d disabled (p = 0) so the step is deterministic: losses and a sample of gradients.
     bn_eval=True additionally puts the BatchNorm layers in eval mode (running statistics): with random weights and a
@@ -262,14 +262,17 @@ def gen_train(bn_eval=False, hrnet=False, iteration=40000, blurskip=False):
     alpha = 0.63
     m.ss_loss_fn.alpha = alpha
     m.ss_loss_fn.fix_alpha = True
-    _, mask_np = synthetic_case(2, 64, 96, 77)
+    # batch8: batch-statistics BatchNorm on 8 x 128^2 crops -- statistics over 8 x 16^2 .. 8 x 64^2 values per channel
+    # are well conditioned, unlike the batch of 2
+    nb, hh, ww = (8, 128, 128) if batch8 else (2, 64, 96)
+    _, mask_np = synthetic_case(nb, hh, ww, 77)
     rng = np.random.default_rng(79)
-    hr_np = np.clip(0.55 + 0.1 * rng.standard_normal((2, 3, 64, 96)) - 0.3 * mask_np, 0, 1).astype(np.float32)
+    hr_np = np.clip(0.55 + 0.1 * rng.standard_normal((nb, 3, hh, ww)) - 0.3 * mask_np, 0, 1).astype(np.float32)
     hr = torch.from_numpy(hr_np)
     mask = torch.from_numpy(mask_np)
     g = torch.Generator().manual_seed(78)
-    lr = torch.nn.functional.interpolate(hr, size=(16, 24), mode="bicubic", antialias=True).clamp(0, 1)
-    kgt = torch.rand(2, 1, 21, 21, generator=g)
+    lr = torch.nn.functional.interpolate(hr, size=(hh // 4, ww // 4), mode="bicubic", antialias=True).clamp(0, 1)
+    kgt = torch.rand(nb, 1, 21, 21, generator=g)
     kgt = kgt / kgt.sum(dim=(2, 3), keepdim=True)
     with contextlib.redirect_stdout(io.StringIO()):
         seg_loss, sr_loss, seg, sr, kp = m(iteration, lr.clone(), sr_targets=hr.clone(), segment_targets=mask.clone(),
@@ -321,7 +324,7 @@ def gen_train(bn_eval=False, hrnet=False, iteration=40000, blurskip=False):
         out["grad:" + k] = gflat[::stride].astype(np.float16 if False else np.float32)
         out["stride:" + k] = np.int64(stride)
     fname = "train_step_hrnet.npz" if hrnet else "train_step_blurskip.npz" if blurskip else \
-        "train_step_bneval.npz" if bn_eval else "train_step.npz"
+        "train_step_bneval.npz" if bn_eval else "train_step_b8.npz" if batch8 else "train_step.npz"
     if iteration != 40000:
         fname = "train_step_it%d.npz" % iteration
     np.savez_compressed(os.path.join(HERE, fname), **out)
@@ -342,6 +345,8 @@ if __name__ == "__main__" and "train" in sys.argv[1:]:
             gen_train(bn_eval=True, iteration=it)
     elif "hrnet" in sys.argv[1:]:
         gen_train(bn_eval=True, hrnet=True)
+    elif "b8" in sys.argv[1:]:
+        gen_train(batch8=True)
     else:
         gen_train()
         gen_train(bn_eval=True)

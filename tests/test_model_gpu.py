@@ -3,7 +3,7 @@ itself pinned to the unmodified reference by tests/golden) on the same synthetic
 
 Tolerances (bf16 activations/weights, fp32 accumulation, ~100 conv layers deep):
   SR image: max-abs <= 3e-2 on a [0,1] image and PSNR(ours, oracle) >= 40 dB;
-  segmentation probability: max-abs <= 5e-2, mean-abs <= 5e-3;  blur kernel: max-abs <= 2% of max|kernel| (the kernel is renormalised by its own
+  segmentation probability: max-abs <= 2e-2, mean-abs <= 5e-3 (measured 0.012 / 0.002);  blur kernel: max-abs <= 2% of max|kernel| (the kernel is renormalised by its own
   sum at every stage, kbpn.py:391-392, which amplifies rounding when that sum is far from 1)."""
 import math
 
@@ -63,8 +63,8 @@ def test_pspnet_vs_oracle():
         seg_ref, aux_ref = T.pspnet_forward(sdc, img)
     torch.cuda.synchronize()
     print("seg max-abs", (seg - seg_ref).abs().max().item(), "aux max-abs", (aux - aux_ref).abs().max().item())
-    assert (seg - seg_ref).abs().max().item() <= 5e-2
-    assert (aux - aux_ref).abs().max().item() <= 5e-2
+    assert (seg - seg_ref).abs().max().item() <= 2e-2
+    assert (aux - aux_ref).abs().max().item() <= 4e-2          # auxiliary head (training loss only, not an eval output): measured 0.028
     assert (seg - seg_ref).abs().mean().item() <= 5e-3
 
 
@@ -84,7 +84,7 @@ def test_joint_model_vs_oracle(b, h, w):
     print("sr", (sr - sr_ref).abs().max().item(), _psnr(sr, sr_ref), "seg", (seg - seg_ref).abs().max().item(),
           (seg - seg_ref).abs().mean().item(), "kp", (kp - kp_ref).abs().max().item())
     assert (sr - sr_ref).abs().max().item() <= 3e-2 and _psnr(sr, sr_ref) >= 40.0
-    assert (seg - seg_ref).abs().max().item() <= 5e-2 and (seg - seg_ref).abs().mean().item() <= 5e-3
+    assert (seg - seg_ref).abs().max().item() <= 2e-2 and (seg - seg_ref).abs().mean().item() <= 5e-3
     assert (kp - kp_ref).abs().max().item() <= 2e-2 * kp_ref.abs().max().item()
     assert sr.min().item() >= 0.0 and sr.max().item() <= 1.0
 
@@ -104,10 +104,69 @@ def test_blurskip_joint_model_vs_oracle_and_golden():
     torch.cuda.synchronize()
     print("blurskip sr", (sr - sr_ref).abs().max().item(), "seg", (seg - seg_ref).abs().max().item(), (seg - seg_ref).abs().mean().item())
     assert (sr - sr_ref).abs().max().item() <= 3e-2 and _psnr(sr, sr_ref) >= 40.0
-    assert (seg - seg_ref).abs().max().item() <= 5e-2 and (seg - seg_ref).abs().mean().item() <= 5e-3
+    assert (seg - seg_ref).abs().max().item() <= 2e-2 and (seg - seg_ref).abs().mean().item() <= 5e-3
     # and against the unmodified reference's own outputs (fp16-stored fixture)
-    assert np.abs(seg.cpu().numpy() - g["seg"].astype(np.float32)).max() <= 5e-2
+    assert np.abs(seg.cpu().numpy() - g["seg"].astype(np.float32)).max() <= 2e-2
     assert np.abs(sr.cpu().numpy() - g["sr"].astype(np.float32)).max() <= 3e-2
+
+
+def test_baseline_shape_joint_model_eager_graph_and_metrics():
+    """The benchmarked path itself (BASELINE config #2): 40 synthetic 448^2 crack images degraded on the device,
+    JointModel at 112^2 -> 448^2 with KBPN chunk 8 and segmentation chunk 32 (+ a ragged chunk of 8).
+      * eager outputs vs the fp32 oracle (TF32 off) on the first and last four images, tolerances of this file;
+      * the CUDA-graph replay bench.py times must reproduce the eager outputs bit for bit;
+      * AIU counts / HD / MSD of the device sweep on the model's own probability maps equal the oracle's sweep on the same maps."""
+    import numpy as np
+    from oracle import metrics_ref as M
+    from oracle import torch_ref as T
+    from csbsr_b200.data import degrade as G
+    from csbsr_b200.engine import inference as E
+    from csbsr_b200.utils import synth
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m, sd = _model_and_sd()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    B = 40
+    hr_u, mask_u = synth.batch(0, 8, 448)
+    hr = hr_u.repeat(5, 1, 1, 1).cuda()
+    mask = mask_u.repeat(5, 1, 1, 1).cuda()
+    params = torch.as_tensor(synth.degradation_params(B, seed=5)).cuda()
+    m.chunk, m.seg_chunk = 8, 32
+    lr, _ = G.degrade(hr, params)
+    sr, seg, kp = m(lr, None)
+    sr, seg, kp = sr.clone(), seg.clone(), kp.clone()
+    torch.cuda.synchronize()
+    for sl in (slice(0, 4), slice(B - 4, B)):
+        with torch.no_grad():
+            sr_ref, seg_ref, kp_ref, _ = T.joint_forward(sdc, lr[sl])
+        e_sr = (sr[sl] - sr_ref).abs().max().item()
+        e_seg, m_seg = (seg[sl] - seg_ref).abs().max().item(), (seg[sl] - seg_ref).abs().mean().item()
+        print("448^2", sl, "sr", e_sr, _psnr(sr[sl], sr_ref), "seg", e_seg, m_seg, "kp", (kp[sl] - kp_ref).abs().max().item())
+        assert e_sr <= 3e-2 and _psnr(sr[sl], sr_ref) >= 40.0
+        assert e_seg <= 2e-2 and m_seg <= 5e-3
+        assert (kp[sl] - kp_ref).abs().max().item() <= 2e-2 * kp_ref.abs().max().item()
+        del sr_ref, seg_ref
+    # graph replay of the same forward (what bench.py times)
+    static_lr = lr.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        m(static_lr, None)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_sr, g_seg, g_kp = m(static_lr, None)
+    g_sr.zero_(); g_seg.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(g_sr, sr) and torch.equal(g_seg, seg) and torch.equal(g_kp, kp)
+    # metric sweep on the network's own maps: bit-exact vs the oracle sweep (two images: full oracle HD is ~4 s each)
+    r = E.seg_metrics(seg[:16], mask[:16], with_hd=True, percent=50)
+    seg_h, mask_h = seg[:2].cpu().numpy(), mask[:2].cpu().numpy()
+    inter, union = M.iou_counts(seg[:16].cpu().numpy(), mask[:16].cpu().numpy())
+    hd, msd = M.distance_metrics(seg_h, mask_h, 50)
+    assert np.array_equal(r["inter"], inter) and np.array_equal(r["union"], union)
+    assert np.array_equal(r["hd"][:2], hd) and np.array_equal(r["msd"][:2], msd)
 
 
 def _hrnet_model_and_sd():
@@ -139,7 +198,7 @@ def test_hrnet_ocr_vs_oracle():
     torch.cuda.synchronize()
     print("hrnet seg", (seg - seg_ref).abs().max().item(), (seg - seg_ref).abs().mean().item(), "aux", (aux - aux_ref).abs().max().item())
     assert (seg - seg_ref).abs().mean().item() <= 5e-3 and (aux - aux_ref).abs().mean().item() <= 5e-3
-    assert (seg - seg_ref).abs().max().item() <= 8e-2 and (aux - aux_ref).abs().max().item() <= 8e-2
+    assert (seg - seg_ref).abs().max().item() <= 2e-2 and (aux - aux_ref).abs().max().item() <= 2e-2
 
 
 def test_hrnet_joint_model_vs_reference_golden():
@@ -153,5 +212,5 @@ def test_hrnet_joint_model_vs_reference_golden():
     assert sr.shape == (2, 3, 64, 96) and seg.shape == (2, 1, 64, 96) and kp.shape == (2, 1, 21, 21)
     d = np.abs(seg.cpu().numpy() - g["seg"].astype(np.float32))
     print("hrnet joint seg", d.max(), d.mean())
-    assert d.max() <= 5e-2 and d.mean() <= 5e-3
+    assert d.max() <= 2e-2 and d.mean() <= 5e-3
     assert np.abs(sr.cpu().numpy() - g["sr"].astype(np.float32)).max() <= 3e-2
