@@ -77,6 +77,8 @@ struct ConvKParams {
     int* err_flag;
     long long* trace;
     int G, ngroups, dstep, a_stage_bytes;   // tap groups: G taps sharing dw, dh = dh0 + j*dstep, one A box per group
+    int cg2;             // cluster == 2 only: tcgen05.mma.cta_group::2 -- the pair's leader issues M = 256 MMAs over both CTAs'
+                         // A tiles, every CTA holds half of the weight rows (no multicast), TMA bytes land on the leader's barriers
     int staged;          // 1: epilogue through swizzled smem panels, residual via TMA load, output via TMA store
     int res_mode;        // staged only: 0 none, 1 pre-activation add (r0), 2 post-activation add/sub (r1)
     int8_t dh[CSBSR_MAX_TAPS], dw[CSBSR_MAX_TAPS];
@@ -360,6 +362,9 @@ __device__ __forceinline__ void epilogue_units(const ConvKParams& p, const EpiRo
 }
 
 // ------------------------------------------------------------------ kernel
+// kCg2: the cta_group::2 variant is a separate instantiation -- a kernel containing cta_group::2 instructions can only be
+// launched as whole CTA pairs (a plain launch fails with "cluster misconfiguration"), so the default path must not contain them
+template <bool kCg2>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
@@ -367,7 +372,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x A tile][stages x B tile][barriers]
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_tile_bytes = p.block_n * p.kb * 2;
+    // cta_group::2: every CTA of the pair holds only ITS half of the weight rows (the MMA reads both halves), so a pipeline
+    // stage is smaller and more stages fit
+    const int b_tile_bytes = (kCg2 ? p.block_n / 2 : p.block_n) * p.kb * 2;
     const int b_stage_bytes = p.G * b_tile_bytes;
     const int b_total_bytes = (p.stages * b_stage_bytes + 1023) & ~1023;      // keeps the staging panels 1024-B aligned
     uint8_t* smem_a = smem;
@@ -399,16 +406,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 2);                        // one arrive.expect_tx from each of the two producer warps
-            mbar_init(&empty_bar[s], p.cluster);               // cluster mode: released by the MMAs of both CTAs
+            mbar_init(&empty_bar[s], kCg2 ? 1 : p.cluster);   // multicast-B mode: released by the MMAs of both CTAs
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], p.staged ? kEpiWarps / 2 : kEpiWarps);   // one arrive per draining warp
+            // one arrive per draining warp; cta_group::2: the leader's MMA thread waits for the warps of both CTAs
+            mbar_init(&tmem_empty[a], (p.staged ? kEpiWarps / 2 : kEpiWarps) * (kCg2 ? 2 : 1));
             mbar_init(&res_full[a], 1);
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_ptr_smem, kTmemCols);
+    if (warp == 2) {
+        if constexpr (kCg2) tmem_alloc_cg2(tmem_ptr_smem, kTmemCols);
+        else tmem_alloc(tmem_ptr_smem, kTmemCols);
+    }
     tcgen05_fence_before();
     __syncthreads();
     if (p.cluster == 2) {                                      // the peer's barriers must exist before anything remote lands
@@ -433,6 +444,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // per-k-block bookkeeping of a single issuing thread (~100 dependent instructions) bounds the small layers.
         {
             const bool load_a = (warp == 0);
+            const bool cg2 = kCg2;
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_a = p.a_stage_bytes, tx_b = b_stage_bytes;
@@ -453,7 +465,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int kc = 0; kc < kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 1);
                         {
-                            if (load_a) {
+                            if constexpr (kCg2) {
+                                // the leader's barrier collects the bytes of both CTAs: own A tile + peer A tile, two half B tiles
+                                if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], load_a ? 2 * tx_a : 2 * tx_b);
+                                if (load_a) {
+                                    tma_load_4d_cg2(smem_u32(smem_a + stage * p.a_stage_bytes), &tmA, &full_bar[stage], kc * kbk, iw0,
+                                                    ih0, img);
+                                } else {
+                                    const uint32_t dst0 = smem_u32(smem_b + stage * b_stage_bytes);
+#pragma unroll 1
+                                    for (int j = 0; j < G; ++j)
+                                        tma_load_3d_cg2(dst0 + j * b_tile_bytes, &tmB, &full_bar[stage], kc * kbk, n0, p.widx[gi + j]);
+                                }
+                            } else if (load_a) {
                                 mbar_arrive_expect_tx(&full_bar[stage], tx_a);
                                 // one A box covers the G vertically shifted taps of the group (rows TH + (G-1)*dstep)
                                 tma_load_4d(smem_u32(smem_a + stage * p.a_stage_bytes), &tmA, &full_bar[stage], kc * kbk, iw0, ih0,
@@ -486,8 +510,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
         {
+            const bool cg2 = kCg2;
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.block_n >> 3) << 17) |
-                                   (static_cast<uint32_t>(kBlockM >> 4) << 24);
+                                   (static_cast<uint32_t>((cg2 ? 2 * kBlockM : kBlockM) >> 4) << 24);
             // descriptor words: lo = (smem address >> 4) | LBO(1) << 16 ; hi = SBO (8 rows of kb*2 bytes) | version 1 |
             // swizzle mode of the row width (128B: 2, 64B: 4, 32B: 6)
             const uint32_t row_bytes = static_cast<uint32_t>(p.kb) * 2u;
@@ -506,7 +531,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int nstages = p.stages, total_tiles = p.total_tiles;
             const bool mc = p.cluster == 2;
             // ONE elected thread runs the whole issue loop (see the producers)
-            if (elect_one_sync())
+            if (elect_one_sync() && !(cg2 && crank != 0))       // cta_group::2: only the leader issues
             for (int tile = wid; tile < total_tiles; tile += wstep, ++local) {
                 const int as = local & 1;
                 const uint32_t aphase = (local >> 1) & 1;
@@ -526,6 +551,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll 1
                         for (int j = 0; j < G; ++j) {
                             // +32 bytes per K=16 step inside the 128B swizzle row -> +2 in the >>4 address field
+                            if constexpr (kCg2) {
+                                for (int s2 = 0; s2 < ksteps; ++s2)
+                                    umma_bf16_lohi_cg2(tmem_d, ja + 2 * s2, jb + 2 * s2, desc_hi, idesc, s2 ? 1u : acc);
+                            } else {
                             umma_bf16_lohi(tmem_d, ja, jb, desc_hi, idesc, acc);
                             if (ksteps == 4) {
                                 umma_bf16_lohi(tmem_d, ja + 2, jb + 2, desc_hi, idesc, 1u);
@@ -534,13 +563,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             } else if (ksteps == 2) {
                                 umma_bf16_lohi(tmem_d, ja + 2, jb + 2, desc_hi, idesc, 1u);
                             }
+                            }
                             acc = 1u;
                             ja += a_shift16;
                             jb += b_tile16;
                         }
-                        if (mc) umma_commit_mc(&empty_bar[stage], 0x3);   // frees the slot in both CTAs of the pair
-                        else umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                        if (kb == kblocks - 1) umma_commit(&tmem_full[as]);
+                        if constexpr (kCg2) {
+                            umma_commit_cg2_mc(&empty_bar[stage], 0x3);        // slot free / accumulator ready in both CTAs
+                            if (kb == kblocks - 1) umma_commit_cg2_mc(&tmem_full[as], 0x3);
+                        } else {
+                            if (mc) umma_commit_mc(&empty_bar[stage], 0x3);   // frees the slot in both CTAs of the pair
+                            else umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                            if (kb == kblocks - 1) umma_commit(&tmem_full[as]);
+                        }
                     }
                     acc = 1u;
                     CSBSR_TRACE(if (kb == kblocks - 1 && p.trace && blockIdx.x == 0 && local < 256) {
@@ -634,7 +669,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[8 * 256 + local] = clock64();)
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                if (lane == 0) {
+                    if constexpr (kCg2) mbar_arrive_cluster(&tmem_empty[as], 0);   // the leader's MMA thread owns both accumulators
+                    else mbar_arrive(&tmem_empty[as]);
+                }
                 fence_proxy_async_smem();                       // make the generic-proxy writes visible to the TMA store
                 CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[9 * 256 + local] = clock64();)
                 team_bar_sync(team);
@@ -701,7 +739,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) {
+                if constexpr (kCg2) mbar_arrive_cluster(&tmem_empty[as], 0);
+                else mbar_arrive(&tmem_empty[as]);
+            }
         }
         }  // direct epilogue
     }
@@ -714,7 +755,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (warp == 2) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (kCg2) tmem_dealloc_cg2(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -813,7 +855,18 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     const char* cl_env = getenv("CSBSR_CLUSTER");
     int cluster = 1;
     if (cl_env) cluster = (atoi(cl_env) == 2 && block_n % 16 == 0 && p.m_tiles >= 2) ? 2 : 1;
+    // cta_group::2 (CTA pairs, M = 256 per instruction, each CTA holds half of the weight rows -> smaller pipeline stages,
+    // more of them in flight): measured -9..-23 % on the layers with K = taps x cin >= 1152 and at least a wave of pixel
+    // tiles (8x8/s4 convs, SFT / PSP / ResNet 3x3s), +10..+40 % on short-K or tiny layers (profiles/r02_cg2_layers.md), so
+    // it is switched on by that rule.  CSBSR_CTA_GROUP=1 / 2 forces it off / on.
+    const char* cg_env = getenv("CSBSR_CTA_GROUP");
+    int cg2 = 0;
+    const bool cg2_ok = block_n % 32 == 0 && p.m_tiles >= 2;
+    if (cg_env) cg2 = (atoi(cg_env) == 2 && cg2_ok) ? 1 : 0;
+    else cg2 = (cg2_ok && d->ntaps * d->cin >= 1024 && p.m_tiles >= 128) ? 1 : 0;
+    if (cg2) cluster = 2;
     p.cluster = cluster;
+    p.cg2 = cg2;
     p.total_tiles = ((p.m_tiles + cluster - 1) / cluster) * p.n_tiles * p.nphases;
     p.fd_ntiles = make_fastdiv(p.n_tiles); p.fd_nphases = make_fastdiv(p.nphases);
     p.fd_tiles_per_img = make_fastdiv(p.tiles_h * p.tiles_w); p.fd_tiles_w = make_fastdiv(p.tiles_w);
@@ -829,7 +882,7 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     memcpy(g_dh, d->dh, sizeof(g_dh)); memcpy(g_dw, d->dw, sizeof(g_dw)); memcpy(g_widx, d->widx, sizeof(g_widx));
     const int staging_bytes = staged ? 2 * (block_n / 64) * kATileBytes : 0;
     const int smem_avail = kSmemBudget - 3072 - staging_bytes;
-    const int b_tile = block_n * kb * 2;
+    const int b_tile = (cg2 ? block_n / 2 : block_n) * kb * 2;      // per-CTA weight tile of one tap and K chunk
     int cand = 1, cand_groups = d->ntaps, cand_step = 0;
     int8_t n_dh[CSBSR_MAX_TAPS], n_dw[CSBSR_MAX_TAPS];
     int16_t n_widx[CSBSR_MAX_TAPS];
@@ -996,13 +1049,15 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     const int smem_bytes = stages * stage_bytes + staging_bytes + 2048 /*align slack (base + staging)*/ + 512 /*barriers*/;
     static int smem_attr_set = 0;
     if (smem_attr_set < smem_bytes) {
-        CSBSR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CSBSR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              kSmemBudget));
+        CSBSR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               kSmemBudget));
         smem_attr_set = kSmemBudget;
     }
     int grid = p.total_tiles * cluster < num_sms() ? p.total_tiles * cluster : (num_sms() / cluster) * cluster;
     if (cluster == 1) {
-        conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmY, tmR, p);
+        conv_igemm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmY, tmR, p);
     } else {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -1015,7 +1070,8 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        CSBSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmA, tmB, tmY, tmR, p));
+        if (cg2) CSBSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, tmA, tmB, tmY, tmR, p));
+        else CSBSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, tmA, tmB, tmY, tmR, p));
     }
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -151,7 +151,7 @@ def _train_model(hrnet=False, blurskip=False):
     return m.cuda(), sd, c
 
 
-@pytest.mark.parametrize("variant", ["pspnet_bneval", "pspnet", "hrnet_bneval", "blurskip_bneval", "it5", "it15000", "it20000", "it25000"])
+@pytest.mark.parametrize("variant", ["pspnet_bneval", "pspnet", "pspnet_b8", "hrnet_bneval", "blurskip_bneval", "it5", "it15000", "it20000", "it25000"])
 def test_train_step_vs_reference_golden(variant):
     """One joint training step (iteration 40000, w^F on, Dropout2d off) of the tcgen05 training graph against the
     unmodified reference's losses and gradients (tests/golden/train_step*.npz; the fp32 oracle is pinned to the same
@@ -159,6 +159,8 @@ def test_train_step_vs_reference_golden(variant):
 
     bn_eval=True  (BatchNorm on running statistics): well conditioned -> losses within 2 %, gradient cosine >= 0.98 for
                   every sampled parameter, norms within 10 %.
+    pspnet_b8     (batch statistics, 8 x 128^2 crops: BatchNorm statistics over 8 x 16^2 .. 8 x 64^2 values per channel are
+                  well conditioned): losses within 2 %, every gradient norm within 15 %, sampled gradients cosine >= 0.95.
     bn_eval=False (batch statistics, batch of 2, random weights): the network is chaotic under bf16 rounding -- the fp32
                   oracle with its conv operands rounded to bf16 decorrelates from the exact one just as much (cosine
                   0.2-0.9 below the heads) -- so this variant checks losses (3 %), gradient norms (within a factor of 2, at most 20 % of the tensors off by more than 50 %) and the heads."""
@@ -168,8 +170,9 @@ def test_train_step_vs_reference_golden(variant):
     # itN: the pre-training phases (5: SR modules with the ground-truth kernel, 15000: kernel predictors only, 20000: its
     # last iteration where KBPN re-enables its SR layers one step early, 25000: whole SR net, loss = sr_loss throughout)
     bn_eval, hrnet = variant.endswith("bneval") or variant.startswith("it"), variant.startswith("hrnet")
+    b8 = variant == "pspnet_b8"
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
-                             {"pspnet": "train_step.npz", "pspnet_bneval": "train_step_bneval.npz", "blurskip_bneval": "train_step_blurskip.npz",
+                             {"pspnet": "train_step.npz", "pspnet_b8": "train_step_b8.npz", "pspnet_bneval": "train_step_bneval.npz", "blurskip_bneval": "train_step_blurskip.npz",
                               "hrnet_bneval": "train_step_hrnet.npz"}.get(variant, "train_step_%s.npz" % variant)))
     it = int(g["iteration"]) if "iteration" in g.files else 40000
     m, sd, c = _train_model(hrnet, variant.startswith("blurskip"))    # blurskip: only segmentation_model.blur_skip.* is trained
@@ -187,7 +190,7 @@ def test_train_step_vs_reference_golden(variant):
     seg_err = np.abs(seg.detach().cpu().numpy() - g["seg"].astype(np.float32)).mean()
     print("train loss", loss.item(), "ref", float(g["loss"]), "seg", seg_loss.mean().item(), float(g["seg_loss_mean"]),
           "sr", sr_loss.tolist(), g["sr_loss"].tolist(), "seg mean abs diff", seg_err)
-    tol = 2e-2 if bn_eval else 3e-2
+    tol = 2e-2 if (bn_eval or b8) else 3e-2
     assert tuple(seg_loss.shape) == tuple(g["seg_loss_shape"])
     assert abs(loss.item() - float(g["loss"])) <= tol * abs(float(g["loss"]))
     assert abs(seg_loss.mean().item() - float(g["seg_loss_mean"])) <= tol * abs(float(g["seg_loss_mean"]))
@@ -203,6 +206,8 @@ def test_train_step_vs_reference_golden(variant):
         print("  grad %-75s cos %.5f  norm ratio %.3f" % (k, cos, ratio))
         if bn_eval:
             assert cos >= 0.98 and abs(ratio - 1) <= 0.1, (k, cos, ratio)
+        elif b8:
+            assert cos >= 0.95 and abs(ratio - 1) <= 0.15, (k, cos, ratio)
         else:
             assert abs(ratio - 1) <= 1.0, (k, ratio)          # chaotic variant: within a factor of 2
             if k in ("segmentation_model.final.0.weight", "segmentation_model.aux.4.bias"):
@@ -226,10 +231,10 @@ def test_train_step_vs_reference_golden(variant):
                 assert p_.grad.abs().max().item() == 0, k
                 continue
             r = p_.grad.double().norm().item() / (ref_n + 1e-30)
-            if abs(r - 1) > (0.15 if bn_eval else 0.5):
+            if abs(r - 1) > (0.15 if (bn_eval or b8) else 0.5):
                 bad.append((k, r))
     print("grad-norm outliers:", bad[:10], len(bad), "of", len(names))
-    assert len(bad) <= (0 if bn_eval else len(names) // 5)
+    assert len(bad) <= (0 if (bn_eval or b8) else len(names) // 5)
 
 
 def test_prelu_fn_vs_torch():
