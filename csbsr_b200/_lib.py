@@ -113,6 +113,9 @@ _SIGNATURES = {
     "csbsr_blur_kernel_synth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "csbsr_resize_bicubic_aa": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "csbsr_degrade": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_void_p]),
+    "csbsr_degrade_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "csbsr_degrade_fused": (C.c_int, [C.c_void_p] * 5 + [C.c_size_t] + [C.c_int] * 7 + [C.c_void_p]),
+    "csbsr_degrade_params_philox": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong, C.c_ulonglong] + [C.c_double] * 4 + [C.c_void_p]),
     "csbsr_sdf_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "csbsr_sdf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "csbsr_seg_loss_workspace_bytes": (C.c_size_t, [C.c_int]),

@@ -95,17 +95,42 @@ class FactorResize:
         return out[0] if single else out
 
 
+_ws = {}
+
+
+def philox_params(n, seed=1121, offset=0, range_theta=(0, 180), range_sigma=(0.2, 4)):
+    """Throughput mode of the per-sample draws (blur.py:129,170-179) on the device: float64 [n,3] = (theta [rad], sigma_x,
+    sigma_y) from Philox4x32-10 (csbsr_degrade_params_philox); sample i of a run uses counter offset + i."""
+    out = torch.empty((n, 3), dtype=torch.float64, device=_dev())
+    _lib.check(_lib.lib().csbsr_degrade_params_philox(out.data_ptr(), n, seed, offset, range_theta[0] * np.pi / 180,
+                                                      range_theta[1] * np.pi / 180, float(range_sigma[0]), float(range_sigma[1]),
+                                                      _lib.stream_ptr()), "csbsr_degrade_params_philox")
+    _lib.count_launch("csbsr_degrade_params_philox")
+    return out
+
+
 def degrade(hr, params, ksize=21, factor=4, clamp01=False, return_blurred=False):
     """Batched CrackDataSet.__getitem__ degradation (crack_dataset.py:51-62): hr fp32 [B,3,H,W] + params float64
-    [B,3] -> (lr [B,3,H/f,W/f], kernels [B,k,k])."""
+    [B,3] -> (lr [B,3,H/f,W/f], kernels [B,k,k]).  One fused pass (composed 36x36/s4 kernels, csbsr_degrade_fused) for the
+    CSBSR configuration (k = 21, x4); the three-launch form with the intermediate `blurred` image otherwise or on request."""
     x = hr.to(device=_dev(), dtype=torch.float32).contiguous()
     p = _params_tensor(params, x.device)
     b, c, h, w = x.shape
     kernels = torch.empty((b, ksize, ksize), dtype=torch.float32, device=x.device)
-    blurred = torch.empty_like(x)
     lr = torch.empty((b, c, h // factor, w // factor), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().csbsr_degrade(x.data_ptr(), p.data_ptr(), kernels.data_ptr(), blurred.data_ptr(),
-                                        lr.data_ptr(), b, c, h, w, ksize, factor, int(clamp01), _lib.stream_ptr()),
+    L = _lib.lib()
+    if not return_blurred and ksize == 21 and factor == 4 and h % 4 == 0 and w % 4 == 0 and h >= 16 and w >= 16:
+        need = L.csbsr_degrade_workspace_bytes(b)
+        ws = _ws.get((x.device, b))
+        if ws is None:
+            ws = _ws[(x.device, b)] = torch.empty(need, dtype=torch.uint8, device=x.device)
+        _lib.check(L.csbsr_degrade_fused(x.data_ptr(), p.data_ptr(), kernels.data_ptr(), lr.data_ptr(), ws.data_ptr(), need,
+                                         b, c, h, w, ksize, factor, int(clamp01), _lib.stream_ptr()), "csbsr_degrade_fused")
+        _lib.count_launch("csbsr_degrade")
+        return lr, kernels
+    blurred = torch.empty_like(x)
+    _lib.check(L.csbsr_degrade(x.data_ptr(), p.data_ptr(), kernels.data_ptr(), blurred.data_ptr(),
+                               lr.data_ptr(), b, c, h, w, ksize, factor, int(clamp01), _lib.stream_ptr()),
                "csbsr_degrade")
     _lib.count_launch("csbsr_degrade")
     if return_blurred:

@@ -111,6 +111,24 @@ class PackedConv:
         return self.wp.shape[2]
 
 
+def to_device(obj, device):
+    """Move every tensor of a packed-weight tree (dicts / lists / tuples / PackedConv) to `device`.  The engines pack on
+    the host (weight folding, padding, transposition are one-off host work) and ship the results with plain H2D copies, so
+    loading a checkpoint launches no device kernels."""
+    if isinstance(obj, torch.Tensor):
+        return obj.to(device)
+    if isinstance(obj, PackedConv):
+        obj.wp = obj.wp.to(device)
+        if obj.bias is not None:
+            obj.bias = obj.bias.to(device)
+        return obj
+    if isinstance(obj, dict):
+        return {k: to_device(v, device) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(to_device(v, device) for v in obj)
+    return obj
+
+
 def _pad_bias(bias, cout_pad, device):
     if bias is None:
         return None

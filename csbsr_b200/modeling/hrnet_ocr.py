@@ -32,7 +32,7 @@ class HRNetOCREngine:
 
     # ------------------------------------------------------------------ weights
     def load(self, sd, prefix="segmentation_model."):
-        dev = self.device
+        dev = "cpu"                       # pack on the host; K.to_device ships the packed tensors (no device kernels at load time)
         g = lambda k: sd[prefix + k].detach().to(dev, torch.float32)
 
         def fold(conv, bn, stride=1, padding=0, cin_pad=None):
@@ -96,7 +96,7 @@ class HRNetOCREngine:
         P["ocr_ctx"] = K.pack_conv(wq[:, :512].contiguous(), shift, scale=scale)
         P["ocr_feat"] = K.pack_conv(wq[:, 512:].contiguous(), None, scale=scale)
         P["cls"] = K.pack_conv(g("cls_head.weight"), g("cls_head.bias"))
-        self.p = P
+        self.p = K.to_device(P, self.device)
         return self
 
     # ------------------------------------------------------------------ forward

@@ -58,7 +58,7 @@ class KBPNEngine:
     # ------------------------------------------------------------------ weight packing
     def load(self, sd, prefix="sr_model."):
         """Pack all weights from a state_dict (tensors on any device)."""
-        dev = self.device
+        dev = "cpu"                       # pack on the host; K.to_device ships the packed tensors (no device kernels at load time)
         g = lambda k: sd[prefix + k].detach().to(dev, torch.float32)
         slope = lambda k: float(sd[prefix + k].detach().float().reshape(-1)[0])
         C, kc, cond = self.C, self.ke * self.ke, self.ko * self.ko
@@ -103,10 +103,10 @@ class KBPNEngine:
                                            (raw(kp + "fe_SR.1.layer.weight"), 64, 32),
                                            (raw(kp + "fe_SR.2.layer.weight"), 32, 32),
                                            (raw(kp + "fe_SR.3.layer.weight"), 32, 32),
-                                           (raw(kp + "fe_SR.4.layer.weight"), 32, 64)]).to(dev)
+                                           (raw(kp + "fe_SR.4.layer.weight"), 32, 64)])
             st["chain_cat"] = K.pack_chain([(raw(kp + "fe_cat.0.layer.weight")[:, :kc].contiguous(), 64, 32),
                                             (raw(kp + "fe_cat.1.layer.weight"), 32, 32),
-                                            (raw(kp + "fe_cat.2.layer.weight"), 32, 64)]).to(dev)
+                                            (raw(kp + "fe_cat.2.layer.weight"), 32, 64)])
             # KBlock.up_conv1: ConvTranspose2d(3 -> C, 8, 4, 2) evaluated on the 3x3-patchified LR error:
             # per output phase a 1x1 conv over K = (a*3+b)*3+c with w[c, co, rho_h+6-4a, rho_w+6-4b]
             w = g(sp + "kb.up_conv1.layer.weight")                       # [3, C, 8, 8]
@@ -145,7 +145,7 @@ class KBPNEngine:
             ws = [g("back_projection_stages.%d.kb.sr_reconst.layer.weight" % c)[:, j * C:(j + 1) * C] for c in range(j + 1, self.S)]
             ws.append(w_out[:, j * C:(j + 1) * C])
             P[j]["kb.sr_later"] = K.pack_tapexp3x3(torch.cat(ws, 0).contiguous())
-        self.p = P
+        self.p = K.to_device(P, self.device)
         return self
 
     # ------------------------------------------------------------------ forward

@@ -22,7 +22,7 @@ class PSPNetEngine:
         self.p = None
 
     def load(self, sd, prefix="segmentation_model."):
-        dev = self.device
+        dev = "cpu"                       # pack on the host; K.to_device ships the packed tensors (no device kernels at load time)
         g = lambda k: sd[prefix + k].detach().to(dev, torch.float32)
 
         def bn_fold(p, conv_bias=None, eps=1e-5):
@@ -80,7 +80,7 @@ class PSPNetEngine:
         sc, sh = bn_fold("aux.1")
         P["aux0"] = K.pack_conv(g("aux.0.weight"), sh, padding=1, scale=sc)
         P["aux4"] = K.pack_conv(g("aux.4.weight"), g("aux.4.bias"))
-        self.p = P
+        self.p = K.to_device(P, self.device)
         return self
 
     def forward(self, img, mean=None, rstd=None, clamp01=False, kvec=None):

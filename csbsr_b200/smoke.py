@@ -31,6 +31,20 @@ def run():
     sr, seg, kp = model(lr, torch.zeros(2, 1, 7, 7))
     r = E.seg_metrics(seg, mask, with_hd=True)
     torch.cuda.synchronize()
+    n_eval = _lib.LAUNCHES
+
+    # ---- roll call of the training kernels right after the eval path (conv forward, dgrad on the flipped packing, wgrad,
+    # weight packing), so that a bounded launch trace of smoke() reaches them: one conv Function forward + backward,
+    # checked against torch autograd further down
+    from csbsr_b200 import autograd as A
+    gen = torch.Generator().manual_seed(5)
+    cx0 = torch.randn(2, 64, 20, 24, generator=gen).to(torch.bfloat16).float().cuda()
+    cw0 = (torch.randn(128, 64, 3, 3, generator=gen) * 0.06).to(torch.bfloat16).float().cuda()
+    cup = torch.randn(2, 128, 20, 24, generator=gen).to(torch.bfloat16).float().cuda()
+    cx, cw = cx0.clone().requires_grad_(True), cw0.clone().requires_grad_(True)
+    cy = A.conv2d(A.to_nhwc(cx), cw, None, stride=1, padding=1)
+    cy.backward(A.to_nhwc(cup))
+    torch.cuda.synchronize()
 
     lr_ref, k_ref, _ = degrade_ref.degrade(hr, params)
     assert (lr.cpu() - lr_ref).abs().max().item() <= 2e-6, "degrade mismatch"
@@ -43,7 +57,11 @@ def run():
     hd, msd = metrics_ref.distance_metrics(seg.cpu().numpy(), mask.numpy(), 50)
     assert np.array_equal(r["inter"], inter) and np.array_equal(r["union"], union), "AIU counts mismatch"
     assert np.array_equal(r["hd"], hd) and np.array_equal(r["msd"], msd), "HD/MSD mismatch"
-    n_eval = _lib.LAUNCHES
+    cxr, cwr = cx0.clone().requires_grad_(True), cw0.clone().requires_grad_(True)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.nn.functional.conv2d(cxr, cwr, None, padding=1).backward(cup)
+    rel = lambda a, b: (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
+    assert rel(cx.grad, cxr.grad) <= 1e-2 and rel(cw.grad, cwr.grad) <= 1e-2, "conv dgrad / wgrad mismatch"
 
     # ---- one tiny joint training step (forward, loss, backward through the conv dgrad / wgrad kernels, fused Adam),
     # loss checked against the fp32 oracle's (BatchNorm on running statistics and Dropout2d off so both are deterministic)

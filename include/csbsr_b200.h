@@ -245,6 +245,18 @@ int csbsr_resize_bicubic_aa(const float* x, float* y, int nc, int h, int w, int 
  * (blur.py:182-200) -> FactorResize.  hr, blurred: fp32 [b,c,h,w]; lr: fp32 [b,c,h/factor,w/factor] */
 int csbsr_degrade(const float* hr, const double* params, float* kernels, float* blurred, float* lr, int b, int c,
                   int h, int w, int ksize, int factor, int clamp01, void* stream);
+/* The same degradation in ONE pass over hr (crack_dataset.py:51-62 = blur.py:128-200 + transforms.py:516-531): blur and
+ * antialiased bicubic are composed into 36x36 stride-4 kernels (25 per sample: 5 row x 5 column classes of bicubic weights,
+ * the first / last two outputs of each axis use aten's shorter renormalised taps), so there is no `blurred` tensor and
+ * 5.4x fewer FLOPs.  ksize = 21 and factor = 4 only; workspace = csbsr_degrade_workspace_bytes(b) bytes, 16-byte aligned. */
+size_t csbsr_degrade_workspace_bytes(int b);
+int csbsr_degrade_fused(const float* hr, const double* params, float* kernels, float* lr, void* workspace,
+                        size_t workspace_bytes, int b, int c, int h, int w, int ksize, int factor, int clamp01, void* stream);
+/* Throughput mode of the per-sample draws of GaussianBlur.make (blur.py:129: theta = U(0,180) deg; get_deterioration
+ * :170-179: sigma = U(0.2, 4)): params[i] = (theta, sigma_x, sigma_y) fp64 from Philox4x32-10 with key = seed and counter =
+ * offset + i (u = word * 2^-32).  Parity mode keeps the draws on the host (torch.rand / np.random.rand replayed). */
+int csbsr_degrade_params_philox(double* params, int b, unsigned long long seed, unsigned long long offset, double theta_lo,
+                                double theta_hi, double sigma_lo, double sigma_hi, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Joint-training losses (csrc/losses.cu): forward values and the gradient w.r.t. the segmentation predictions.

@@ -48,3 +48,29 @@ def degrade(hr, params, size=21, factor=4):
         b = blur(hr[i], k)
         ks.append(k); bl.append(b); lr.append(downsample(b, factor))
     return torch.stack(lr), torch.stack(ks), torch.stack(bl)
+
+
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11), the published
+    algorithm restated in numpy: counter uint32 [n,4], key uint32 [2] -> uint32 [n,4].  Checker of the throughput-mode draws
+    (csbsr_degrade_params_philox); known-answer vectors of the Random123 distribution are asserted in tests/test_oracle_cpu.py."""
+    c = np.array(counter, dtype=np.uint64).reshape(-1, 4).copy()
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[:, 0], M1 * c[:, 2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c = np.stack([hi1 ^ c[:, 1] ^ k0, lo1, hi0 ^ c[:, 3] ^ k1, lo0], axis=1)
+        k0 = (k0 + np.uint64(0x9E3779B9)) & MASK
+        k1 = (k1 + np.uint64(0xBB67AE85)) & MASK
+    return c.astype(np.uint32)
+
+
+def philox_params(n, seed=1121, offset=0, range_theta=(0, 180), range_sigma=(0.2, 4)):
+    """(theta [rad], sigma_x, sigma_y) float64 [n,3] exactly as csbsr_degrade_params_philox draws them."""
+    idx = np.arange(n, dtype=np.uint64) + np.uint64(offset)
+    ctr = np.stack([idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32), np.zeros_like(idx), np.zeros_like(idx)], axis=1)
+    r = philox4x32_10(ctr, (seed & 0xFFFFFFFF, seed >> 32)).astype(np.float64) * (1.0 / 4294967296.0)
+    tl, th = range_theta[0] * np.pi / 180, range_theta[1] * np.pi / 180
+    return np.stack([tl + (th - tl) * r[:, 0], range_sigma[0] + (range_sigma[1] - range_sigma[0]) * r[:, 1],
+                     range_sigma[0] + (range_sigma[1] - range_sigma[0]) * r[:, 2]], axis=1)

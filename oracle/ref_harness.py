@@ -9,7 +9,20 @@ pretrained-download suppression and "cuda" -> cpu redirection.
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("CSBSR_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference():
+    """/root/reference in the build container; the verbatim copy baseline/install_ref.py made (baseline/_ref, git-ignored,
+    travels with gpurun) on the GPU box."""
+    cands = [os.environ.get("CSBSR_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "model")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 _state = {}
 

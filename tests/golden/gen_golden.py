@@ -230,6 +230,9 @@ def gen_psnr_ssim():
     print("psnr_ssim.npz", PSNR()(a, b), SSIM()(a, b))
 
 
+B8_DAMP = 0.1
+
+
 def gen_train(bn_eval=False, hrnet=False, iteration=40000, blurskip=False, batch8=False):
     """One JointModelWithLoss forward + backward of the UNMODIFIED reference at iteration 40000 (all phases active,
     w^F on, m^F = 1), Dropout2d disabled (p = 0) so the step is deterministic: losses and a sample of gradients.
@@ -251,6 +254,15 @@ def gen_train(bn_eval=False, hrnet=False, iteration=40000, blurskip=False, batch
     sd = P.synth_state_dict(P.kbpn_param_shapes(), prefix="sr_model.")
     seg_shapes = P.hrnet_ocr_param_shapes() if hrnet else P.pspnet_param_shapes(blur_dim=441 if blurskip else None)
     sd.update(P.synth_state_dict(seg_shapes, prefix="segmentation_model."))
+    if batch8:
+        # random-init ResNet with batch-statistics BatchNorm is chaotic under bf16 operand rounding at ANY batch size
+        # (tests/tools/conditioning_probe.py: the fp32 oracle with bf16-rounded conv operands moves the segmentation map by
+        # 0.08 mean-abs and gradient norms by up to 3.2x on the un-damped weights).  Damping the residual branches
+        # (bn2.weight x 0.1, what zero-init-residual training starts from) makes the step well conditioned (probe: every
+        # sampled gradient cosine >= 0.975, norms within 8 %) while BatchNorm still runs on batch statistics everywhere.
+        for k in sd:
+            if ".feats.layer" in k and k.endswith("bn2.weight"):
+                sd[k] = sd[k] * B8_DAMP
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected and all(k.startswith("sr_loss_fn") or "vgg" in k.lower() for k in missing), (missing, unexpected)
     m.train()
@@ -286,6 +298,8 @@ def gen_train(bn_eval=False, hrnet=False, iteration=40000, blurskip=False, batch
            "loss": np.float64(loss.item()), "seg_loss_mean": np.float64(seg_loss.mean().item()),
            "sr_loss": sr_loss.detach().numpy(), "seg_loss_shape": np.array(seg_loss.shape),
            "sr": sr.detach().numpy().astype(np.float16), "seg": seg.detach().numpy().astype(np.float16)}
+    if batch8:
+        out["bn2_damp"] = np.float32(B8_DAMP)
     names = ["sr_model.feat.0.weight", "sr_model.predictor.feat_ext.2.layer.weight",
              "sr_model.back_projection_stages.0.up.up_conv1.layer.weight",
              "sr_model.back_projection_stages.1.sft.SFT_scale_conv0.weight",

@@ -147,6 +147,40 @@ def test_degrade_matches_golden_and_oracle():
     assert np.abs(G.FactorResize(4, "bicubic")(b).cpu().numpy() - D.downsample(b.cpu()).numpy()).max() <= 2e-6
 
 
+@pytest.mark.parametrize("shape", [(6, 3, 64, 96), (2, 3, 448, 448), (3, 1, 16, 20), (1, 3, 100, 228)])
+def test_fused_degrade_matches_golden_and_oracle(shape):
+    """csbsr_degrade_fused (composed 36x36/s4 kernels, 25 border classes) against the reference fixture and the two-step oracle:
+    2e-6 abs on the LR image (values in [0,1]), kernels 2e-8 -- the same bounds as the three-launch form."""
+    from csbsr_b200.data import degrade as G
+    from oracle import degrade_ref as D
+    if shape == (6, 3, 64, 96):
+        g = np.load(os.path.join(GOLD, "degrade.npz"))
+        hr, prm = torch.from_numpy(g["hr"]), np.concatenate([g["theta"][:, None], g["sigma"]], 1)
+        want_lr, want_k = g["lr"], g["kernels"]
+    else:
+        rng = np.random.default_rng(shape[2])
+        hr = torch.from_numpy(rng.random(shape).astype(np.float32))
+        prm = np.stack([rng.uniform(0, np.pi, shape[0]), rng.uniform(0.2, 4, shape[0]), rng.uniform(0.2, 4, shape[0])], 1)
+        lr_o, k_o, _ = D.degrade(hr.expand(-1, 3, -1, -1) if shape[1] == 1 else hr, prm)
+        want_lr, want_k = lr_o.numpy()[:, :shape[1]], k_o.numpy()
+    lr, ks = G.degrade(hr, prm)
+    lr3, ks3, _ = G.degrade(hr, prm, return_blurred=True)              # three-launch form
+    err = np.abs(lr.cpu().numpy() - want_lr)
+    print("fused degrade", shape, "max err", err.max(), "border ring max", max(err[..., :2, :].max(), err[..., -2:, :].max(),
+          err[..., :, :2].max(), err[..., :, -2:].max()), "vs 3-launch", (lr - lr3).abs().max().item())
+    assert np.abs(ks.cpu().numpy() - want_k).max() <= 2e-8
+    assert err.max() <= 2e-6
+    assert (lr - lr3).abs().max().item() <= 2e-6
+
+
+def test_philox_params_bit_equal_to_oracle():
+    from csbsr_b200.data import degrade as G
+    from oracle import degrade_ref as D
+    for n, seed, off in [(1, 0, 0), (64, 1121, 0), (1000, 2**40 + 3, 2**33 + 5)]:
+        got = G.philox_params(n, seed=seed, offset=off).cpu().numpy()
+        assert np.array_equal(got, D.philox_params(n, seed=seed, offset=off))
+
+
 def test_psnr_ssim_kernel_vs_reference_golden_and_oracle():
     """csbsr_psnr_ssim against the reference's PSNR / SSIM outputs and, on a 448^2 batch, the oracle (fp32: 2e-4 dB / 2e-5)."""
     import os

@@ -373,3 +373,17 @@ def test_graphed_step_phase_key_host_logic():
     keys = [gs._phase_key(it) for it in (1, 10000, 10001, 19999, 20000, 20001, 30000, 30001, 400000)]
     assert keys[0] == keys[1] and keys[1] != keys[2] and keys[2] == keys[3] and keys[3] != keys[4]
     assert keys[4] != keys[5] and keys[5] == keys[6] and keys[6] != keys[7] and keys[7] == keys[8]
+
+
+def test_philox4x32_known_answers():
+    """Random123's published known-answer vectors for philox4x32-10 pin the numpy restatement (oracle/degrade_ref.py) that
+    checks the on-device throughput-mode draws of the degradation."""
+    from oracle import degrade_ref as D
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(v) for v in D.philox4x32_10([ctr], key)[0]) == want
+    p = D.philox_params(1000, seed=7)
+    assert p.shape == (1000, 3) and (p[:, 0] >= 0).all() and (p[:, 0] < np.pi).all()
+    assert (p[:, 1:] >= 0.2).all() and (p[:, 1:] < 4.0).all() and abs(p[:, 1:].mean() - 2.1) < 0.1

@@ -159,8 +159,11 @@ def test_train_step_vs_reference_golden(variant):
 
     bn_eval=True  (BatchNorm on running statistics): well conditioned -> losses within 2 %, gradient cosine >= 0.98 for
                   every sampled parameter, norms within 10 %.
-    pspnet_b8     (batch statistics, 8 x 128^2 crops: BatchNorm statistics over 8 x 16^2 .. 8 x 64^2 values per channel are
-                  well conditioned): losses within 2 %, every gradient norm within 15 %, sampled gradients cosine >= 0.95.
+    pspnet_b8     (batch statistics on 8 x 128^2 crops, residual branches of the ResNet damped: bn2.weight x 0.1 in the fixture
+                  and here -- tests/tools/conditioning_probe.py shows the un-damped random-init ResNet chaotic under bf16
+                  operand rounding at any batch size, and this one well conditioned: fp32 oracle exact vs bf16-rounded
+                  operands cosine >= 0.975, norms within 8 %): losses within 2 %, every sampled gradient cosine >= 0.95 and
+                  norm within 15 %, all gradient norms within 15 %.
     bn_eval=False (batch statistics, batch of 2, random weights): the network is chaotic under bf16 rounding -- the fp32
                   oracle with its conv operands rounded to bf16 decorrelates from the exact one just as much (cosine
                   0.2-0.9 below the heads) -- so this variant checks losses (3 %), gradient norms (within a factor of 2, at most 20 % of the tensors off by more than 50 %) and the heads."""
@@ -176,6 +179,11 @@ def test_train_step_vs_reference_golden(variant):
                               "hrnet_bneval": "train_step_hrnet.npz"}.get(variant, "train_step_%s.npz" % variant)))
     it = int(g["iteration"]) if "iteration" in g.files else 40000
     m, sd, c = _train_model(hrnet, variant.startswith("blurskip"))    # blurskip: only segmentation_model.blur_skip.* is trained
+    if b8:
+        with torch.no_grad():
+            for k, p_ in m.named_parameters():
+                if ".feats.layer" in k and k.endswith("bn2.weight"):
+                    p_.mul_(float(g["bn2_damp"]))
     m.train()
     m.dropout = False
     m.freeze_bn = bn_eval
@@ -196,7 +204,7 @@ def test_train_step_vs_reference_golden(variant):
     assert abs(seg_loss.mean().item() - float(g["seg_loss_mean"])) <= tol * abs(float(g["seg_loss_mean"]))
     assert np.abs(sr_loss.detach().cpu().numpy() - g["sr_loss"]).max() <= 2e-2 * g["sr_loss"].max()
     assert np.abs(sr.detach().cpu().numpy() - g["sr"].astype(np.float32)).max() <= 5e-2
-    assert seg_err <= (1e-2 if bn_eval else 0.15)
+    assert seg_err <= (1e-2 if bn_eval else 4e-2 if b8 else 0.15)
     params = dict(m.named_parameters())
     for k in [k[5:] for k in g.files if k.startswith("grad:")]:
         ref = g["grad:" + k].astype(np.float64)
@@ -214,6 +222,15 @@ def test_train_step_vs_reference_golden(variant):
                 assert cos >= 0.99, (k, cos)
     # every trainable tensor received a finite gradient; whole-model gradient norms against the reference's
     names, norms = list(g["grad_norm_names"]), g["grad_norms"]
+    gmax = float(np.max(norms))
+    alt = {}
+    if b8:
+        # second opinion for the ill-conditioned tensors: the SAME pinned fp32 oracle with its conv operands rounded to bf16
+        # (tests/tools/conditioning_probe.py --save): scalar PReLU slopes (sum_{x<0} dy*x cancels) and kb.sr_reconst move by
+        # 17 % .. 4x under operand rounding alone -- a tensor passes when its norm is within tolerance of the unmodified
+        # reference's OR of that run's
+        a = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_step_b8_bf16ops.npz"))
+        alt = dict(zip([str(n) for n in a["names"]], a["norm_bf16ops"]))
     bad = []
     for k, p_ in params.items():
         assert p_.grad is not None and torch.isfinite(p_.grad).all(), k
@@ -221,17 +238,35 @@ def test_train_step_vs_reference_golden(variant):
             assert p_.grad.abs().max().item() == 0, k
         if k in names:
             ref_n = norms[names.index(k)]
+            got_n = p_.grad.double().norm().item()
+            if b8:
+                if ref_n <= 1e-6 * gmax:        # conv bias in front of a batch-statistics BatchNorm: the exact gradient is 0
+                    assert got_n <= 1e-4 * gmax, (k, got_n)
+                    continue
+                alt_n = float(alt.get(k, ref_n))
+                if p_.numel() == 1:
+                    # scalar PReLU slope: sum_{x<0} dy*x over ~1e6 signed terms cancelling to ~1e-3 of the gradient scale;
+                    # operand rounding alone moves it by up to 4x in the oracle (probe) -> absolute bound
+                    ok = abs(got_n - ref_n) <= max(0.5 * max(ref_n, alt_n), 5e-3)
+                else:
+                    # kb.sr_reconst (3 output channels feeding two nearly cancelling paths): the oracle moves by 17-18 % under
+                    # operand rounding alone (probe) -> 30 %; every other tensor 15 % of either reference
+                    tol_k = 0.30 if k.endswith("kb.sr_reconst.layer.weight") else 0.15
+                    ok = abs(got_n / ref_n - 1) <= tol_k or abs(got_n / (alt_n + 1e-30) - 1) <= tol_k
+                if not ok:
+                    bad.append((k, got_n, ref_n, alt_n))
+                continue
             if p_.numel() == 1:
                 # scalar PReLU slopes: sum_{x<0} dy*x cancels down to 1e-5..1e-3, so bf16 activations move it by O(1)
                 # relative (the fp32 oracle with bf16-rounded conv operands shows the same outliers): absolute bound
-                if abs(p_.grad.double().norm().item() - ref_n) > max(0.5 * ref_n, 2e-3):
+                if abs(got_n - ref_n) > max(0.5 * ref_n, 2e-3):
                     bad.append((k, p_.grad.item(), ref_n))
                 continue
             if ref_n == 0:                      # OCR f_pixel / f_object: softmax over K = 1 object region -> exactly zero
                 assert p_.grad.abs().max().item() == 0, k
                 continue
-            r = p_.grad.double().norm().item() / (ref_n + 1e-30)
-            if abs(r - 1) > (0.15 if (bn_eval or b8) else 0.5):
+            r = got_n / (ref_n + 1e-30)
+            if abs(r - 1) > (0.15 if bn_eval else 0.5):
                 bad.append((k, r))
     print("grad-norm outliers:", bad[:10], len(bad), "of", len(names))
     assert len(bad) <= (0 if (bn_eval or b8) else len(names) // 5)
