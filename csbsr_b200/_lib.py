@@ -79,6 +79,11 @@ _SIGNATURES = {
     "csbsr_blur_ps_bwd_kernel": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]),
     "csbsr_resize_bicubic_aa_bwd": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 5 + [C.c_void_p]),
     "csbsr_pack_weights": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]),
+    "csbsr_pack_weights_window": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
+    "csbsr_pack_job_bytes": (C.c_size_t, []),
+    "csbsr_pack_job_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_ulonglong]),
+    "csbsr_pack_weights_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong, C.c_void_p]),
+    "csbsr_wgrad_unpack_add": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "csbsr_bn_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_float] + [C.c_void_p] * 6),
     "csbsr_bn_apply": (C.c_int, [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     "csbsr_bn_backward": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_longlong, C.c_int] + [C.c_void_p] * 5),
@@ -116,6 +121,26 @@ _SIGNATURES = {
     "csbsr_degrade_workspace_bytes": (C.c_size_t, [C.c_int]),
     "csbsr_degrade_fused": (C.c_int, [C.c_void_p] * 5 + [C.c_size_t] + [C.c_int] * 7 + [C.c_void_p]),
     "csbsr_degrade_params_philox": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong, C.c_ulonglong] + [C.c_double] * 4 + [C.c_void_p]),
+    "csbsr_colsum_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "csbsr_bias_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csbsr_act_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_longlong, C.c_float, C.c_void_p]),
+    "csbsr_axpby": (C.c_int, [C.c_void_p] * 3 + [C.c_longlong, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "csbsr_sft_combine": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_void_p]),
+    "csbsr_sft_combine_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
+    "csbsr_window_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p]),
+    "csbsr_bilinear_nhwc_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 11 + [C.c_void_p]),
+    "csbsr_adaptive_avgpool_nhwc_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
+    "csbsr_maxpool3s2_nhwc_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 10 + [C.c_void_p]),
+    "csbsr_dropout2d_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_ulonglong, C.c_void_p, C.c_uint, C.c_void_p]),
+    "csbsr_counter_inc": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "csbsr_channel_scale": (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    "csbsr_expand_classes": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    "csbsr_expand_classes_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "csbsr_expand_classes_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csbsr_instnorm_apply": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_longlong, C.c_void_p]),
+    "csbsr_instnorm_bwd_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "csbsr_instnorm_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_longlong, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csbsr_nhwc_bf16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "csbsr_sdf_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "csbsr_sdf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "csbsr_seg_loss_workspace_bytes": (C.c_size_t, [C.c_int]),

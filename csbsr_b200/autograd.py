@@ -8,14 +8,41 @@ checkpoints are unchanged; they are packed to bf16 per call.
 forward   y  = conv(x, w) + b                       -> csbsr_conv_igemm
 backward  dx = conv^T(dy, w)                        -> csbsr_conv_igemm with the transposed / flipped packing
           dw = sum_pix dy (x) x                     -> csbsr_conv_wgrad
-          db = sum_pix dy                           (torch reduction)
+          db = sum_pix dy                           -> csbsr_bias_grad (fixed-order column sums)
+An activation (ReLU / LeakyReLU) can ride in the forward epilogue; its backward masks dy by the sign of the saved output
+(csbsr_act_bwd) before dgrad / wgrad / bias-grad.
 Replaces autograd through cuDNN for nn.Conv2d / nn.ConvTranspose2d (reference model/modeling/kbpn.py:190-277,
 pspnet_pytorch/extractors.py:37-70, trainer.py:57-72).
 """
 import torch
 
+import ctypes as C
+
+from . import _lib
 from . import kernels as K
 from .kernels import Fmap, round_up
+
+_ACT = {None: (K.ACT_NONE, 0.0), "relu": (K.ACT_RELU, 0.0)}
+
+
+def _act_code(act):
+    """act: None | 'relu' | ('lrelu', slope) -> (epilogue code, slope)"""
+    if isinstance(act, tuple):
+        return K.ACT_LEAKY, float(act[1])
+    return _ACT[act]
+
+
+def _mask_by_act(dy, y, slope):
+    g = torch.empty_like(dy)
+    _lib.check(_lib.lib().csbsr_act_bwd(dy.data_ptr(), y.data_ptr(), g.data_ptr(), dy.numel(), C.c_float(slope), _lib.stream_ptr()),
+               "csbsr_act_bwd")
+    _lib.count_launch("csbsr_act_bwd")
+    return g
+
+
+def _bias_grad(dy, c):
+    from .glue import bias_grad
+    return bias_grad(dy, c)
 
 
 def cpad(c):
@@ -42,29 +69,41 @@ def _out_size(h, k, stride, pad, dil):
 
 class _Conv2dFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, dilation):
+    def forward(ctx, x, weight, bias, stride, padding, dilation, act=None, cin_range=None):
         assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
         co, ci, R, S = weight.shape
+        if cin_range is not None:                    # only input channels [b0, b0 + ci) of the parameter take part
+            ci = cin_range[1]
         n, h, w, cp = x.shape
         assert cp == cpad(ci), "input has %d channels, expected %d (padded %d)" % (cp, ci, cpad(ci))
         oh, ow = _out_size(h, R, stride, padding, dilation), _out_size(w, S, stride, padding, dilation)
-        pc = K.pack_conv_train(weight, bias, stride=stride, padding=padding, dilation=dilation, cin_pad=cp, cout_pad=cpad(co))
+        pc = K.pack_conv_train(weight, bias, stride=stride, padding=padding, dilation=dilation, cin_pad=cp, cout_pad=cpad(co),
+                               cin_range=cin_range)
         y = Fmap.empty(n, oh, ow, cpad(co), device=x.device)
-        K.conv(Fmap(x), pc, y)
-        ctx.save_for_backward(x, weight)
-        ctx.cfg = (stride, padding, dilation, bias is not None)
+        code, slope = _act_code(act)
+        K.conv(Fmap(x), pc, y, act=code, slope=slope)
+        if act is None:
+            ctx.save_for_backward(x, weight)
+        else:
+            ctx.save_for_backward(x, weight, y.t)
+        ctx.cfg = (stride, padding, dilation, bias is not None, act is not None, slope, cin_range)
         return y.t
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
-        stride, padding, dilation, has_bias = ctx.cfg
+        stride, padding, dilation, has_bias, has_act, slope, cin_range = ctx.cfg
+        x, weight = ctx.saved_tensors[:2]
         co, ci, R, S = weight.shape
+        if cin_range is not None:
+            ci = cin_range[1]
         n, h, w, cp = x.shape
         dy = dy.contiguous()
+        if has_act:
+            dy = _mask_by_act(dy, ctx.saved_tensors[2], slope)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             if R == 8 and stride == 4 and padding == 2 and dilation == 1 and h == 4 * dy.shape[1] and w == 4 * dy.shape[2]:
+                assert cin_range is None
                 pc = K.pack_deconv8s4_train(weight, cin_pad=dy.shape[3], cout_pad=cp)  # conv 8/4/2 <-> convT 8/4/2
                 g = Fmap.empty(n, h, w, cp, device=x.device)
                 K.conv(Fmap(dy), pc, g)
@@ -75,17 +114,19 @@ class _Conv2dFn(torch.autograd.Function):
                     src = torch.zeros((n, hs, ws, dy.shape[3]), dtype=dy.dtype, device=dy.device)
                     src[:, ::stride, ::stride][:, :dy.shape[1], :dy.shape[2]] = dy
                 pc = K.pack_conv_train(weight, None, stride=1, padding=dilation * (R - 1) - padding, dilation=dilation,
-                                       cin_pad=dy.shape[3], cout_pad=cp, transpose_flip=True)
+                                       cin_pad=dy.shape[3], cout_pad=cp, transpose_flip=True, cin_range=cin_range)
                 g = Fmap.empty(n, h, w, cp, device=x.device)
                 K.conv(Fmap(src), pc, g)
             dx = g.t
         if ctx.needs_input_grad[1]:
             taps = [(r * dilation - padding, s * dilation - padding) for r in range(R) for s in range(S)]
             wg = K.wgrad(Fmap(dy), Fmap(x), taps, stride=stride)
-            dw = wg[:co, :, :ci].reshape(co, R, S, ci).permute(0, 3, 1, 2).contiguous()
+            if not K.wgrad_accumulate(wg, weight, cin_range):          # registered parameter: folded into its .grad in place
+                assert cin_range is None
+                dw = wg[:co, :, :ci].reshape(co, R, S, ci).permute(0, 3, 1, 2).contiguous()
         if has_bias and ctx.needs_input_grad[2]:
-            db = dy[..., :co].sum(dim=(0, 1, 2), dtype=torch.float32)
-        return dx, dw, db, None, None, None
+            db = _bias_grad(dy, co)
+        return dx, dw, db, None, None, None, None, None
 
 
 class _Deconv8s4Fn(torch.autograd.Function):
@@ -120,14 +161,19 @@ class _Deconv8s4Fn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             taps = [(r - 2, s - 2) for r in range(8) for s in range(8)]
             wg = K.wgrad(Fmap(x), Fmap(dy), taps, stride=4)
-            dw = wg[:ci, :, :co].reshape(ci, 8, 8, co).permute(0, 3, 1, 2).contiguous()
+            if not K.wgrad_accumulate(wg, weight):
+                dw = wg[:ci, :, :co].reshape(ci, 8, 8, co).permute(0, 3, 1, 2).contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy[..., :co].sum(dim=(0, 1, 2), dtype=torch.float32)
+            db = _bias_grad(dy, co)
         return dx, dw, db
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1):
-    return _Conv2dFn.apply(x, weight, bias, stride, padding, dilation)
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, act=None, cin_range=None):
+    """act: None | 'relu' | ('lrelu', slope) -- applied in the conv epilogue.  cin_range = (b0, b): only input channels
+    [b0, b0 + b) of `weight` (a parameter registered with kernels.register_params) are used -- the two halves of one conv."""
+    if cin_range is not None and K.registered(weight) is None:
+        weight, cin_range = weight[:, cin_range[0]:cin_range[0] + cin_range[1]].contiguous(), None
+    return _Conv2dFn.apply(x, weight, bias, stride, padding, dilation, act, cin_range)
 
 
 def deconv8s4(x, weight, bias=None):

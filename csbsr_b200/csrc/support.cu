@@ -2,6 +2,7 @@
 // (im2col for the 3-channel image inputs), pooling, resampling, per-sample kernel-vector updates,
 // per-sample depthwise blur (KBlock), clip + instance-norm statistics.  All are coalesced along the
 // NHWC channel axis (128-bit vectors where the channel count allows) or along W for planar fp32.
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "../../include/csbsr_b200.h"
 
@@ -93,19 +94,29 @@ __global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __re
 // sums run over pixels in a fixed stride order and the pixel lanes are combined in index order: bit-reproducible (the first
 // version used atomicAdd across slices).  Only the initial kernel prediction still pools through here (12544 pixels x 64
 // channels per image); the per-stage pools of the kernel predictor live in the fused chain (kpred_chain.cu).
-__global__ void gap_nhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int HW, int pitch,
-                                int coff, int C) {
-    extern __shared__ float gp[];                       // [lanes][nvec * 8]
-    const int n = blockIdx.x;
+// One thread-block CLUSTER of kGapCluster CTAs per sample: every CTA sums a contiguous slice of the pixels, the lanes are
+// combined in index order inside the CTA, and rank 0 adds the kGapCluster partial vectors in rank order through distributed
+// shared memory -- no workspace, no atomics, bit-reproducible, and 8x the memory-level parallelism of one CTA per sample.
+constexpr int kGapCluster = 8;
+__global__ void __cluster_dims__(kGapCluster, 1, 1)
+gap_nhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int HW, int pitch, int coff, int C) {
+    extern __shared__ float gp[];                       // [lanes][nvec * 8] + [nvec * 8] (this CTA's partial vector)
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = static_cast<int>(cluster.block_rank());
+    const int n = blockIdx.x / kGapCluster;
     const int nvec = (C + 7) / 8;
     const int lanes = blockDim.x / nvec;
     const int cv = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    float* part = gp + lanes * nvec * 8;
+    const int per = (HW + kGapCluster - 1) / kGapCluster;
+    const int p0 = rank * per, p1 = min(HW, p0 + per);
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     if (pl < lanes) {
         const __nv_bfloat16* base = x + static_cast<size_t>(n) * HW * pitch + coff + cv * 8;
-        for (int p = pl; p < HW; p += lanes) {
+        for (int p = p0 + pl; p < p1; p += lanes) {
             const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(p) * pitch));
             const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
@@ -118,11 +129,20 @@ __global__ void gap_nhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __re
         for (int i = 0; i < 8; ++i) gp[(pl * nvec + cv) * 8 + i] = acc[i];
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c = threadIdx.x; c < nvec * 8; c += blockDim.x) {
         float t = 0.f;
         for (int l = 0; l < lanes; ++l) t += gp[l * nvec * 8 + c];
-        out[n * C + c] = t / static_cast<float>(HW);
+        part[c] = t;
     }
+    cluster.sync();
+    if (rank == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float t = 0.f;
+            for (int r = 0; r < kGapCluster; ++r) t += cluster.map_shared_rank(part, r)[c];
+            out[n * C + c] = t / static_cast<float>(HW);
+        }
+    }
+    cluster.sync();                                     // the partial vectors stay alive until rank 0 has read them
 }
 
 // ------------------------------------------------------------------ kernel-vector update
@@ -599,7 +619,7 @@ extern "C" int csbsr_gap_nhwc(const void* x, float* out, int n, int hw, int pitc
     const int threads = nvec <= 256 ? 256 : 1024;
     CSBSR_REQUIRE(nvec <= threads, "gap_nhwc: too many channels");
     const int lanes = threads / nvec;
-    gap_nhwc_kernel<<<n, threads, sizeof(float) * lanes * nvec * 8, STREAM(stream)>>>(
+    gap_nhwc_kernel<<<n * kGapCluster, threads, sizeof(float) * (lanes * nvec * 8 + nvec * 8), STREAM(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), out, hw, pitch, coff, c);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;

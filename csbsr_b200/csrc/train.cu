@@ -324,31 +324,124 @@ extern "C" int csbsr_resize_bicubic_aa_bwd(const float* dy, float* dx, int nc, i
 // mode 1: rows = B, cols = A, taps flipped (stride-1 conv dgrad); mode 2: rows = B, cols = A (ConvTranspose2d forward phases;
 // dgrad of the 8x8/s4 conv).  Padding rows / columns are written as zeros.
 namespace csbsr {
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int A, int B, int R, int S,
-                                    int rows_pad, int cols_pad, int mode) {
-    const size_t total = static_cast<size_t>(R) * S * rows_pad * cols_pad;
+// one packing job: source parameter [A][Btot][R][S], columns [b0, b0 + B) of its second axis are packed
+struct PackJob {
+    const float* w;
+    __nv_bfloat16* out;
+    int A, B, Btot, b0, R, S, rows_pad, cols_pad, mode;
+    int pad_;
+    unsigned long long start;      // first element of this job in the concatenated index space of a multi-job launch
+};
+
+__device__ __forceinline__ void pack_one(const PackJob& j, size_t i) {
+    const int col = static_cast<int>(i % j.cols_pad);
+    const int row = static_cast<int>((i / j.cols_pad) % j.rows_pad);
+    const int t = static_cast<int>(i / (static_cast<size_t>(j.cols_pad) * j.rows_pad));
+    int r = t / j.S, s = t % j.S;
+    const int a = j.mode == 0 ? row : col, b = j.mode == 0 ? col : row;
+    if (j.mode == 1) { r = j.R - 1 - r; s = j.S - 1 - s; }
+    float v = 0.f;
+    if (a < j.A && b < j.B) v = j.w[((static_cast<size_t>(a) * j.Btot + j.b0 + b) * j.R + r) * j.S + s];
+    j.out[i] = __float2bfloat16(v);
+}
+
+__global__ void pack_weights_kernel(const PackJob job) {
+    const size_t total = static_cast<size_t>(job.R) * job.S * job.rows_pad * job.cols_pad;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        pack_one(job, i);
+}
+
+// every registered (parameter, layout) pair of the model in ONE launch: jobs[] lives in device memory, `start` is the
+// exclusive prefix of the job sizes; each block walks a contiguous chunk of the concatenated index space
+__global__ void pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int njobs, unsigned long long total) {
+    const unsigned long long per = (total + gridDim.x - 1) / gridDim.x;
+    const unsigned long long lo = per * blockIdx.x, hi = min(total, lo + per);
+    if (lo >= hi) return;
+    int j = 0;                                            // first job containing `lo` (binary search on start)
+    {
+        int a = 0, b = njobs - 1;
+        while (a < b) {
+            const int m = (a + b + 1) >> 1;
+            if (jobs[m].start <= lo) a = m; else b = m - 1;
+        }
+        j = a;
+    }
+    __shared__ PackJob cur;
+    unsigned long long pos = lo;
+    while (pos < hi) {
+        __syncthreads();
+        if (threadIdx.x == 0) cur = jobs[j];
+        __syncthreads();
+        const unsigned long long jsize = static_cast<unsigned long long>(cur.R) * cur.S * cur.rows_pad * cur.cols_pad;
+        const unsigned long long jend = min(hi, cur.start + jsize);
+        for (unsigned long long i = pos + threadIdx.x; i < jend; i += blockDim.x) pack_one(cur, static_cast<size_t>(i - cur.start));
+        pos = jend;
+        ++j;
+    }
+}
+
+// grad[a][b0 + b][r][s] += wg[a][t = r*S+s][b]  (a < A, b < B): the fp32 accumulator of csbsr_conv_wgrad ([rows][taps][cs])
+// folded into the parameter's gradient in the parameter's own layout ([A][Btot][R][S]) -- replaces permute + contiguous + add
+__global__ void wgrad_unpack_add_kernel(const float* __restrict__ wg, float* __restrict__ grad, int A, int B, int Btot, int b0,
+                                        int T, int cs) {
+    const size_t total = static_cast<size_t>(A) * B * T;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int col = static_cast<int>(i % cols_pad);
-        const int row = static_cast<int>((i / cols_pad) % rows_pad);
-        const int t = static_cast<int>(i / (static_cast<size_t>(cols_pad) * rows_pad));
-        int r = t / S, s = t % S;
-        const int a = mode == 0 ? row : col, b = mode == 0 ? col : row;
-        if (mode == 1) { r = R - 1 - r; s = S - 1 - s; }
-        float v = 0.f;
-        if (a < A && b < B) v = w[((static_cast<size_t>(a) * B + b) * R + r) * S + s];
-        out[i] = __float2bfloat16(v);
+        const int t = static_cast<int>(i % T);
+        const int b = static_cast<int>((i / T) % B);
+        const int a = static_cast<int>(i / (static_cast<size_t>(T) * B));
+        grad[(static_cast<size_t>(a) * Btot + b0 + b) * T + t] += wg[(static_cast<size_t>(a) * T + t) * cs + b];
     }
 }
 }  // namespace csbsr
 
 extern "C" int csbsr_pack_weights(const float* w, void* out, int a, int b, int r, int s, int rows_pad, int cols_pad, int mode,
                                   void* stream) {
-    CSBSR_REQUIRE(w && out && a > 0 && b > 0 && r > 0 && s > 0 && mode >= 0 && mode <= 2, "pack_weights: bad arguments");
+    return csbsr_pack_weights_window(w, out, a, b, b, 0, r, s, rows_pad, cols_pad, mode, stream);
+}
+
+extern "C" int csbsr_pack_weights_window(const float* w, void* out, int a, int b, int b_total, int b0, int r, int s, int rows_pad,
+                                         int cols_pad, int mode, void* stream) {
+    CSBSR_REQUIRE(w && out && a > 0 && b > 0 && r > 0 && s > 0 && mode >= 0 && mode <= 2 && b0 >= 0 && b0 + b <= b_total,
+                  "pack_weights: bad arguments");
     CSBSR_REQUIRE(rows_pad >= (mode == 0 ? a : b) && cols_pad >= (mode == 0 ? b : a), "pack_weights: padded extents too small");
     const size_t total = static_cast<size_t>(r) * s * rows_pad * cols_pad;
-    pack_weights_kernel<<<grid_cap(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        w, reinterpret_cast<__nv_bfloat16*>(out), a, b, r, s, rows_pad, cols_pad, mode);
+    csbsr::PackJob job{w, reinterpret_cast<__nv_bfloat16*>(out), a, b, b_total, b0, r, s, rows_pad, cols_pad, mode, 0, 0ull};
+    csbsr::pack_weights_kernel<<<grid_cap(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(job);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" size_t csbsr_pack_job_bytes(void) { return sizeof(csbsr::PackJob); }
+
+extern "C" int csbsr_pack_job_fill(void* job_host, const float* w, void* out, int a, int b, int b_total, int b0, int r, int s,
+                                   int rows_pad, int cols_pad, int mode, unsigned long long start) {
+    CSBSR_REQUIRE(job_host && w && out && a > 0 && b > 0 && b0 >= 0 && b0 + b <= b_total && mode >= 0 && mode <= 2,
+                  "pack_job_fill: bad arguments");
+    csbsr::PackJob job{w, reinterpret_cast<__nv_bfloat16*>(out), a, b, b_total, b0, r, s, rows_pad, cols_pad, mode, 0, start};
+    memcpy(job_host, &job, sizeof(job));
+    return 0;
+}
+
+extern "C" int csbsr_pack_weights_multi(const void* jobs_device, int njobs, unsigned long long total, void* stream) {
+    CSBSR_REQUIRE(jobs_device && njobs > 0 && total > 0, "pack_weights_multi: bad arguments");
+    int blocks = static_cast<int>((total + 256ull * 16 - 1) / (256ull * 16));
+    const int cap = csbsr::num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    csbsr::pack_weights_multi_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        static_cast<const csbsr::PackJob*>(jobs_device), njobs, total);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_wgrad_unpack_add(const float* wg, float* grad, int a, int b, int b_total, int b0, int taps, int cs,
+                                      void* stream) {
+    CSBSR_REQUIRE(wg && grad && a > 0 && b > 0 && b <= cs && b0 >= 0 && b0 + b <= b_total && taps > 0, "wgrad_unpack_add: bad arguments");
+    const size_t total = static_cast<size_t>(a) * b * taps;
+    csbsr::wgrad_unpack_add_kernel<<<grid_cap(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(wg, grad, a, b, b_total,
+                                                                                                          b0, taps, cs);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

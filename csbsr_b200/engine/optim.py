@@ -59,6 +59,9 @@ class FusedAdam:
             p.grad = self.flat_g[off:off + p.numel()].view(p.shape)
             self.slots.append((off, sz))
             off += sz
+        from .. import kernels as K
+        K.register_params(self.params)              # packed bf16 operands are cached per step; wgrad accumulates into .grad
+        K.invalidate_packed()
         self.param_steps = [0] * len(self.params)   # torch.optim.Adam keeps one step counter per parameter
         self.base_lr, self.betas, self.eps = lr, betas, eps
         self.lr_lambda = lr_lambda
@@ -95,6 +98,8 @@ class FusedAdam:
                                             _lib.stream_ptr())
             _lib.check(rc, "csbsr_adam_step")
             _lib.count_launch("csbsr_adam_step")
+        from .. import kernels as K
+        K.invalidate_packed()
 
     def scheduler_step(self):
         self.sched_count += 1

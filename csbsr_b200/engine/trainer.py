@@ -67,7 +67,9 @@ class GraphedTrainStep:
         for b, saved in buffers:
             b.copy_(saved)
         self.opt.flat_g.zero_()
-        from .. import _lib
+        from .. import _lib, kernels as K
+        K.flush_pack_table()                 # job table of the multi-tensor weight pack on the device before the capture
+        K.invalidate_packed()                # the captured step must contain the pack launch: replays follow optimizer steps
         graph = torch.cuda.CUDAGraph()
         n0 = _lib.LAUNCHES
         with torch.cuda.graph(graph):

@@ -278,24 +278,108 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
     return y
 
 
-def _pack_device(weight, rows_pad, cols_pad, mode):
-    """One-launch packing of a contiguous fp32 CUDA parameter (csbsr_pack_weights)."""
-    a, b, R, S = weight.shape
-    out = torch.empty((R * S, rows_pad, cols_pad), dtype=torch.bfloat16, device=weight.device)
-    _call("csbsr_pack_weights", weight.data_ptr(), out.data_ptr(), a, b, R, S, rows_pad, cols_pad, mode)
-    return out
+# ------------------------------------------------------------------ training-step weight cache
+# Parameters registered by the optimizer (engine/optim.py::FusedAdam) keep their packed bf16 GEMM operands across the step:
+# every (parameter, layout) pair is packed on first use and afterwards refreshed by ONE multi-tensor launch at the first
+# request that follows an optimizer step (invalidate_packed()), instead of one launch per use (297 per step).
+_REG = {}                      # data_ptr -> parameter
+_PACKS = {}                    # (data_ptr, A, Btot, b0, B, R, S, rows_pad, cols_pad, mode) -> entry
+_PACK_STATE = {"epoch": 0, "dev": None, "n": 0, "total": 0, "dirty": True}
 
 
-def pack_conv_train(weight, bias=None, stride=1, padding=0, dilation=1, cin_pad=None, cout_pad=None, transpose_flip=False):
+def register_params(params):
+    """Called by the optimizer that owns the flat parameter / gradient buffers; a new optimizer replaces the previous set."""
+    _REG.clear()
+    _PACKS.clear()
+    _PACK_STATE.update(dev=None, n=0, total=0, dirty=True)
+    for p in params:
+        _REG[p.data_ptr()] = p
+
+
+def registered(weight):
+    p = _REG.get(weight.data_ptr())
+    return p if (p is not None and p.shape == weight.shape) else None
+
+
+def invalidate_packed():
+    """The parameters changed (optimizer step / load_state_dict): cached packs are stale from now on."""
+    _PACK_STATE["epoch"] += 1
+
+
+def flush_pack_table():
+    """Upload the job table of the multi-tensor pack if entries were added (call before a CUDA-graph capture)."""
+    st = _PACK_STATE
+    if not st["dirty"] or not _PACKS:
+        return
+    L = _lib.lib()
+    jb = L.csbsr_pack_job_bytes()
+    buf = (C.c_ubyte * (jb * len(_PACKS)))()
+    start = 0
+    for i, (key, e) in enumerate(_PACKS.items()):
+        _, a, btot, b0, b, R, S, rows_pad, cols_pad, mode = key
+        _lib.check(L.csbsr_pack_job_fill(C.byref(buf, i * jb), e["w"].data_ptr(), e["out"].data_ptr(), a, b, btot, b0, R, S,
+                                         rows_pad, cols_pad, mode, start), "csbsr_pack_job_fill")
+        start += R * S * rows_pad * cols_pad
+    dev = next(iter(_PACKS.values()))["out"].device
+    st["dev"] = torch.frombuffer(buf, dtype=torch.uint8).clone().to(dev)
+    st["n"], st["total"], st["dirty"] = len(_PACKS), start, False
+
+
+def _refresh_all():
+    st = _PACK_STATE
+    flush_pack_table()
+    _call("csbsr_pack_weights_multi", st["dev"].data_ptr(), st["n"], st["total"])
+    for e in _PACKS.values():
+        e["epoch"], e["version"] = st["epoch"], e["w"]._version
+
+
+def _pack_device(weight, rows_pad, cols_pad, mode, cin_range=None):
+    """Packing of a contiguous fp32 CUDA parameter (csbsr_pack_weights*); cin_range = (b0, b) packs a window of its second axis."""
+    a, btot, R, S = weight.shape
+    b0, b = cin_range if cin_range is not None else (0, btot)
+    reg = registered(weight)
+    if reg is None:
+        out = torch.empty((R * S, rows_pad, cols_pad), dtype=torch.bfloat16, device=weight.device)
+        _call("csbsr_pack_weights_window", weight.data_ptr(), out.data_ptr(), a, b, btot, b0, R, S, rows_pad, cols_pad, mode)
+        return out
+    key = (weight.data_ptr(), a, btot, b0, b, R, S, rows_pad, cols_pad, mode)
+    e = _PACKS.get(key)
+    if e is None:
+        out = torch.empty((R * S, rows_pad, cols_pad), dtype=torch.bfloat16, device=weight.device)
+        _call("csbsr_pack_weights_window", weight.data_ptr(), out.data_ptr(), a, b, btot, b0, R, S, rows_pad, cols_pad, mode)
+        _PACKS[key] = {"w": reg, "out": out, "epoch": _PACK_STATE["epoch"], "version": reg._version}
+        _PACK_STATE["dirty"] = True
+        return out
+    if e["epoch"] != _PACK_STATE["epoch"] or e["version"] != reg._version:
+        _refresh_all()
+    return e["out"]
+
+
+def wgrad_accumulate(wg, weight, cin_range=None):
+    """Fold a csbsr_conv_wgrad accumulator into the gradient of a registered parameter in place (its .grad is a view of the
+    optimizer's flat gradient buffer).  Returns False when the parameter is not registered / has no gradient buffer."""
+    reg = registered(weight)
+    if reg is None or reg.grad is None or not reg.grad.is_contiguous():
+        return False
+    a, btot, R, S = weight.shape
+    b0, b = cin_range if cin_range is not None else (0, btot)
+    _call("csbsr_wgrad_unpack_add", wg.data_ptr(), reg.grad.data_ptr(), a, b, btot, b0, R * S, wg.shape[2])
+    return True
+
+
+def pack_conv_train(weight, bias=None, stride=1, padding=0, dilation=1, cin_pad=None, cout_pad=None, transpose_flip=False,
+                    cin_range=None):
     """pack_conv for the training step: the fp32 parameter is packed by one kernel.  transpose_flip=True gives the operand of
     the stride-1 dgrad conv (roles of cin / cout swapped, taps flipped, padding = dilation*(k-1) - padding given by the caller)."""
     w = weight.detach()
     assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
     a, b, R, S = w.shape
+    if cin_range is not None:
+        b = cin_range[1]
     cout, cin = (b, a) if transpose_flip else (a, b)
     cout_pad = cout_pad or round_up(cout, 16)
     cin_pad = cin_pad or round_up(cin, 64)
-    wp = _pack_device(w, cout_pad, cin_pad, 1 if transpose_flip else 0)
+    wp = _pack_device(w, cout_pad, cin_pad, 1 if transpose_flip else 0, cin_range)
     taps = [(r * dilation - padding, s * dilation - padding, r * S + s) for r in range(R) for s in range(S)]
     return PackedConv(wp, taps, 1, R * S, stride, 1, [0], [0], cout, _pad_bias(bias, cout_pad, w.device),
                       macs_per_pixel=R * S * cin * cout)

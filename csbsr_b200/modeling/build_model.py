@@ -209,9 +209,15 @@ class JointModelWithLoss(JointModel):
             # while only sr_loss is optimised the segmentation net is evaluated for logging only: no tape needed
             extra = {"kvec": kvec} if self.seg_model_name == "PSPNet_BlurSkip" else {}
             with torch.set_grad_enabled(torch.is_grad_enabled() and not sr_only):
-                normed = torch.nn.functional.instance_norm(sr, eps=1e-5)          # norm_sr, build_model.py:135-137
-                seg, aux = seg_fwd(P, normed, bn_training=self.training and not self.freeze_bn,
-                                   dropout=self.dropout and self.training, **extra)
+                from .. import glue as G
+                normed = G.instance_norm(sr, eps=1e-5)                            # norm_sr, build_model.py:135-137
+                drop = None
+                if self.dropout and self.training:
+                    if getattr(self, "_drop_state", None) is None or self._drop_state.counter.device != device:
+                        self._drop_state = G.DropoutState(device, seed=cfg.SEED)
+                    drop = self._drop_state
+                    drop.begin_step()
+                seg, aux = seg_fwd(P, normed, bn_training=self.training and not self.freeze_bn, dropout=drop, **extra)
             sr_loss, kernel_preds = LS.kbpn_loss_train(sr, sr_targets, x, kvec, kernel_targets, self.sr_loss_weights,
                                                        self.ksize, self.scale_factor)
             amp = self.wf_amp if self.oriented_w_iter <= iter else 0.0

@@ -1,9 +1,11 @@
 """Training-mode forward of KBPN + PSPNet as an autograd graph over the tcgen05 conv Functions.
 
-Every dense conv / transposed conv runs forward, dgrad and wgrad on the csbsr_b200 engine (csbsr_b200/autograd.py);
-the elementwise / pooling / resampling / normalisation glue between them is plain aten (cuDNN disabled by the caller:
-no cuDNN kernel runs in the step).  Activations are NHWC bf16 with channels zero-padded to a multiple of 64; the SR
-image, the blur-kernel vectors and everything feeding the losses stay fp32.
+Every dense conv / transposed conv runs forward, dgrad and wgrad on the csbsr_b200 engine (csbsr_b200/autograd.py), and
+the glue between them -- activations, residual adds, SFT combine, concat, bilinear / adaptive / max pooling, Dropout2d,
+BatchNorm, instance norm, layout changes -- runs forward and backward on the kernels of csrc/glue.cu, csrc/support.cu and
+csrc/train.cu (csbsr_b200/glue.py); torch.autograd is the tape.  What is left to aten are O(B x 441)-sized vector ops on the
+blur-kernel estimates and fp32 adds on 3-channel images.  Activations are NHWC bf16 with channels zero-padded to a multiple of
+64; the SR image, the blur-kernel vectors and everything feeding the losses stay fp32.
 
 Mirrors, in train mode and outside the pre-training phases (iteration >= SR_PRETRAIN_ITER[1]):
   KBPN.forward                      model/modeling/kbpn.py:84-116
@@ -15,50 +17,31 @@ Mirrors, in train mode and outside the pre-training phases (iteration >= SR_PRET
 import torch
 import torch.nn.functional as F
 
-from ..autograd import batch_norm, conv2d, cpad, deconv8s4, prelu, to_nchw, to_nhwc
+from .. import glue as G
+from ..autograd import batch_norm, conv2d, cpad, deconv8s4, prelu
+from ..glue import to_nchw, to_nhwc
 from .params import RESNET34_LAYERS
 
-
-def _nchw(x):          # NHWC tensor -> NCHW view (channels_last strides), no copy
-    return x.permute(0, 3, 1, 2)
-
-
-def _nhwc(x):          # NCHW (channels_last) -> NHWC contiguous
-    return x.permute(0, 2, 3, 1).contiguous()
+_EPI_ACT = {"relu": "relu", "lrelu": ("lrelu", 0.01)}          # activations that ride in the conv epilogue
 
 
 def _cat(parts, real=None):
-    """Concatenate NHWC tensors along channels (taking the first real[i] channels of part i) and zero-pad to 64."""
-    if real is not None:
-        parts = [p[..., :r] for p, r in zip(parts, real)]
-    c = sum(p.shape[3] for p in parts)
-    if cpad(c) != c:
-        n, h, w, _ = parts[0].shape
-        parts = list(parts) + [torch.zeros((n, h, w, cpad(c) - c), dtype=parts[0].dtype, device=parts[0].device)]
-    return torch.cat(parts, dim=3)
-
-
-def _act(P, p, y, act):
-    if act == "prelu":
-        return prelu(y, P[p + ".act.weight"])
-    if act == "relu":
-        return F.relu(y)
-    if act == "lrelu":
-        return F.leaky_relu(y, 0.01)
-    return y
+    """Concatenate NHWC maps along channels (the first real[i] channels of part i), zero-padded to a multiple of 64."""
+    return G.concat(parts, real)
 
 
 def _convblock(P, p, x, stride=1, padding=0, act=None):
-    y = conv2d(x, P[p + ".layer.weight"], P.get(p + ".layer.bias"), stride=stride, padding=padding)
-    return _act(P, p, y, act)
+    y = conv2d(x, P[p + ".layer.weight"], P.get(p + ".layer.bias"), stride=stride, padding=padding, act=_EPI_ACT.get(act))
+    return prelu(y, P[p + ".act.weight"]) if act == "prelu" else y
 
 
 def _deconvblock(P, p, x, act="prelu"):
-    return _act(P, p, deconv8s4(x, P[p + ".layer.weight"], P.get(p + ".layer.bias")), act)
+    y = deconv8s4(x, P[p + ".layer.weight"], P.get(p + ".layer.bias"))
+    return prelu(y, P[p + ".act.weight"]) if act == "prelu" else y
 
 
 def _gap(x, c):
-    return x[..., :c].mean(dim=(1, 2), dtype=torch.float32)          # [B, c] fp32
+    return G.gap(x, c)                                                # [B, c] fp32
 
 
 def _upscale_kernel(vec, k_out):
@@ -68,56 +51,35 @@ def _upscale_kernel(vec, k_out):
 
 def _expand_vec(kvec, h, w):
     """(B, 441) fp32 -> NHWC bf16 [B, h, w, 448] conditioning map (differentiable)."""
-    b, c = kvec.shape
-    v = F.pad(kvec, (0, cpad(c) - c)).to(torch.bfloat16)
-    return v.view(b, 1, 1, -1).expand(b, h, w, -1)
+    return _BroadcastVecFn.apply(kvec, h, w)
 
 
-_CLASS_IDX = {}
-
-
-def _border_classes(n, bw, device):
-    """Class index of every position along an axis of length n for a response that only feels the zero padding within
-    `bw` pixels of the border: 0..bw-1 at the start, bw in the interior, bw+1..2bw at the end (cached per shape)."""
-    key = (n, bw, str(device))
-    if key not in _CLASS_IDX:
-        idx = [bw] * n
-        for i in range(min(bw, n)):
-            idx[i] = i
-            idx[n - 1 - i] = 2 * bw - i
-        _CLASS_IDX[key] = torch.tensor(idx, dtype=torch.long).to(device)
-    return _CLASS_IDX[key]
-
-
-class _ExpandClassesFn(torch.autograd.Function):
-    """[B, 2bw+1, 2bw+1, C] per-class responses -> [B, h, w, C].  Backward sums the gradient over the pixels of every class
-    with slice reductions (border rows / columns individually, the interior block as one sum) instead of a scatter-add."""
+class _BroadcastVecFn(torch.autograd.Function):
+    """fp32 [B, c] -> NHWC bf16 [B, h, w, cpad(c)] with out[b, y, x, :c] = v[b]; backward = per-sample sum over the pixels."""
 
     @staticmethod
-    def forward(ctx, small, h, w, bw):
-        ctx.cfg = (h, w, bw)
-        yi, xi = _border_classes(h, bw, small.device), _border_classes(w, bw, small.device)
-        return small[:, yi][:, :, xi]
+    def forward(ctx, v, h, w):
+        from .. import kernels as K
+        b, c = v.shape
+        out = torch.empty((b, h, w, cpad(c)), dtype=torch.bfloat16, device=v.device)
+        K.broadcast_vec(v.contiguous().float(), K.Fmap(out))
+        ctx.cfg = (c, h, w)
+        return out
 
     @staticmethod
-    def backward(ctx, g):
-        h, w, bw = ctx.cfg
-
-        def fold(t, dim, n):
-            if n <= 2 * bw:                                   # degenerate (tiny) axis: generic path
-                idx = _border_classes(n, bw, t.device)
-                shape = list(t.shape)
-                shape[dim] = 2 * bw + 1
-                return torch.zeros(shape, dtype=t.dtype, device=t.device).index_add_(dim, idx, t)
-            head = t.narrow(dim, 0, bw)
-            mid = t.narrow(dim, bw, n - 2 * bw).sum(dim=dim, keepdim=True, dtype=torch.float32).to(t.dtype)
-            tail = t.narrow(dim, n - bw, bw)
-            return torch.cat((head, mid, tail), dim=dim)
-        return fold(fold(g, 1, h), 2, w), None, None, None
+    def backward(ctx, dy):
+        from .. import kernels as K
+        c, h, w = ctx.cfg
+        dy = dy.contiguous()
+        g = torch.empty((dy.shape[0], c), dtype=torch.float32, device=dy.device)
+        K.gap(K.Fmap(dy), g, c)
+        return g * float(h * w), None, None
 
 
 def _expand_classes(small, h, w, bw):
-    return _ExpandClassesFn.apply(small, h, w, bw)
+    """[B, 2bw+1, 2bw+1, C] responses per border class -> [B, h, w, C] (class of a position: 0..bw-1 at the start of an axis,
+    bw in the interior, bw+1..2bw at the end); backward sums the gradient over the pixels of every class."""
+    return G.expand_classes(small, h, w, bw)
 
 
 def _kernel_predictor(P, p, sr_t, kvec, k_out):
@@ -130,13 +92,19 @@ def _kernel_predictor(P, p, sr_t, kvec, k_out):
     # fe_kernel sees a spatially constant map (kbpn.py:572-573): two stacked zero-padded 3x3 convs respond identically
     # everywhere except within 2 px of the border -> evaluate them on a 5x5 image of border classes and gather
     # (exactly the reference's values; gradients reach the kernel vector and both convs through the gather)
-    fh = _expand_vec(kvec, 5, 5).contiguous()
+    fh = _expand_vec(kvec, 5, 5)
     fh = _convblock(P, p + ".fe_kernel.0", fh, padding=1, act="lrelu")
     fh = _convblock(P, p + ".fe_kernel.1", fh, padding=1, act="lrelu")
     fh = _expand_classes(fh, H, W, 2)
     c = P[p + ".fe_SR.4.layer.weight"].shape[0]
-    d = _cat((fsr, fh), real=(c, c))
-    d = _convblock(P, p + ".fe_cat.0", d, act="lrelu")
+    # cat(fsr[:c], fh[:c]) with c = 49: the padded maps are concatenated whole (64 + 64 channels) and the input channels of the
+    # 1x1 fe_cat.0 weight are scattered to the padded positions instead (differentiable, a [32, 98] -> [32, 128] copy)
+    cp_ = fsr.shape[3]
+    d = _cat((fsr, fh))
+    w_cat = P[p + ".fe_cat.0.layer.weight"]
+    w_pad = torch.zeros((w_cat.shape[0], 2 * cp_, 1, 1), dtype=w_cat.dtype, device=w_cat.device)
+    w_pad = torch.cat((w_cat[:, :c], w_pad[:, c:cp_], w_cat[:, c:], w_pad[:, cp_ + c:]), dim=1)
+    d = conv2d(d, w_pad, None, act=_EPI_ACT["lrelu"])
     d = _convblock(P, p + ".fe_cat.1", d, padding=1, act="lrelu")
     d = _convblock(P, p + ".fe_cat.2", d, padding=1, act=None)
     delta = _upscale_kernel(_gap(d, c), k_out).reshape(n, k_out * k_out)
@@ -154,16 +122,16 @@ def _up_block(P, p, x):
     x = _convblock(P, p + ".conv", x, act="prelu")
     h0 = _deconvblock(P, p + ".up_conv1", x)
     l0 = _convblock(P, p + ".up_conv2", h0, stride=4, padding=2, act="prelu")
-    h1 = _deconvblock(P, p + ".up_conv3", l0 - x)
-    return h1 + h0
+    h1 = _deconvblock(P, p + ".up_conv3", G.sub(l0, x))
+    return G.add(h1, h0)
 
 
 def _down_block(P, p, x):
     x = _convblock(P, p + ".conv", x, act="prelu")
     l0 = _convblock(P, p + ".down_conv1", x, stride=4, padding=2, act="prelu")
     h0 = _deconvblock(P, p + ".down_conv2", l0)
-    l1 = _convblock(P, p + ".down_conv3", h0 - x, stride=4, padding=2, act="prelu")
-    return l1 + l0
+    l1 = _convblock(P, p + ".down_conv3", G.sub(h0, x), stride=4, padding=2, act="prelu")
+    return G.add(l1, l0)
 
 
 def _k_block(P, p, concat_h, h, x_lr, kvec, k_out, scale, predict_kernel=True):
@@ -173,7 +141,7 @@ def _k_block(P, p, concat_h, h, x_lr, kvec, k_out, scale, predict_kernel=True):
     vec = d_kernel / d_kernel.sum(dim=1, keepdim=True)
     pseudo_lr = blur_per_sample(to_nchw(sr_t, 3), vec, k_out, scale)
     e_h = _deconvblock(P, p + ".up_conv1", to_nhwc(pseudo_lr - x_lr))
-    return h + e_h, vec
+    return G.add(h, e_h), vec
 
 
 def _sft(P, p, feats, kvec):
@@ -181,15 +149,16 @@ def _sft(P, p, feats, kvec):
     spatially constant, so their part of the (linear) conv is evaluated on a 3x3 image of border classes and added as a
     per-sample, per-class bias: conv0(cat(f, k)) = conv(f, W[:, :fc]) + gather(conv(k_3x3, W[:, fc:]) + b)."""
     n, h, w, fc = feats.shape
-    cond = _expand_vec(kvec, 3, 3).contiguous()
+    cond = _expand_vec(kvec, 3, 3)
 
     def branch(name):
         w0 = P[p + ".SFT_%s_conv0.weight" % name]
-        t = conv2d(feats, w0[:, :fc].contiguous(), None, padding=1)
-        tb = conv2d(cond, w0[:, fc:].contiguous(), P[p + ".SFT_%s_conv0.bias" % name], padding=1)
-        t = t + _expand_classes(tb, h, w, 1)
-        return conv2d(F.leaky_relu(t, 0.1), P[p + ".SFT_%s_conv1.weight" % name], P[p + ".SFT_%s_conv1.bias" % name], padding=1)
-    return feats * torch.sigmoid(branch("scale")) + branch("shift")
+        fcr = w0.shape[1] - kvec.shape[1]                 # real feature channels (fc is their padded count)
+        t = conv2d(feats, w0, None, padding=1, cin_range=(0, fcr))
+        tb = conv2d(cond, w0, P[p + ".SFT_%s_conv0.bias" % name], padding=1, cin_range=(fcr, kvec.shape[1]))
+        t = G.leaky_relu(G.add(t, _expand_classes(tb, h, w, 1)), 0.1)
+        return conv2d(t, P[p + ".SFT_%s_conv1.weight" % name], P[p + ".SFT_%s_conv1.bias" % name], padding=1)
+    return G.sft_combine(feats, branch("scale"), branch("shift"))
 
 
 def kbpn_forward(P, x_lr, num_stages=4, k_out=21, scale=4, prefix="sr_model.", gt_kernel=None):
@@ -199,7 +168,7 @@ def kbpn_forward(P, x_lr, num_stages=4, k_out=21, scale=4, prefix="sr_model.", g
     p = prefix
     f = to_nhwc(x_lr)
     for i in (0, 2, 4, 6):
-        f = F.relu(conv2d(f, P[p + "feat.%d.weight" % i], P[p + "feat.%d.bias" % i], padding=1))
+        f = conv2d(f, P[p + "feat.%d.weight" % i], P[p + "feat.%d.bias" % i], padding=1, act="relu")
     init_f = f
     if gt_kernel is not None:
         kvec = gt_kernel.reshape(x_lr.shape[0], k_out * k_out).float()
@@ -214,16 +183,18 @@ def kbpn_forward(P, x_lr, num_stages=4, k_out=21, scale=4, prefix="sr_model.", g
     for s in range(num_stages):
         sp = p + "back_projection_stages.%d" % s
         h = _up_block(P, sp + ".up", low)
-        pre = h if concat_h is None else torch.cat((concat_h, h), dim=3)
+        pre = h if concat_h is None else _cat((concat_h, h))
         h, kvec = _k_block(P, sp + ".kb", pre, h, x_lr, kvec, k_out, scale, predict_kernel=gt_kernel is None)
-        concat_h = h if concat_h is None else torch.cat((concat_h, h), dim=3)
+        concat_h = h if concat_h is None else _cat((concat_h, h))
         if s < num_stages - 1:
             low = _down_block(P, sp + ".down", concat_h)
-            concat_l = low if concat_l is None else torch.cat((concat_l, low), dim=3)
+            concat_l = low if concat_l is None else _cat((concat_l, low))
             low = _sft(P, sp + ".sft", concat_l, kvec)
     sr = to_nchw(_convblock(P, p + "output_conv", concat_h, padding=1), 3)
-    sr = sr + F.interpolate(x_lr, scale_factor=scale, mode="bicubic")
-    return sr, kvec
+    from .. import kernels as K
+    up = torch.empty_like(sr)
+    K.bicubic_upsample(x_lr.contiguous(), up, scale)                 # nn.Upsample(bicubic) of the (constant) LR input, kbpn.py:70,113
+    return sr + up, kvec
 
 
 # ---------------------------------------------------------------------------------------------- PSPNet (train mode)
@@ -233,28 +204,39 @@ def _bn(P, p, x, training, momentum=0.1, relu=False, res=None):
     y = batch_norm(x, P[p + ".weight"], P[p + ".bias"], P[p + ".running_mean"], P[p + ".running_var"], training, momentum,
                    1e-5, relu=relu, res=res)
     if training and (p + ".num_batches_tracked") in P:
-        P[p + ".num_batches_tracked"] += 1
+        _TRACKED.append(P[p + ".num_batches_tracked"])
     return y
 
 
-def _drop(x, p, on):
-    return _nhwc(F.dropout2d(_nchw(x), p, training=True)) if (on and p > 0) else x
+_TRACKED = []          # num_batches_tracked buffers touched by the current forward: advanced by one batched launch at its end
+
+
+def _flush_tracked():
+    if _TRACKED:
+        torch._foreach_add_(_TRACKED, 1)
+        _TRACKED.clear()
+
+
+def _drop(x, p, state, c=None):
+    """nn.Dropout2d(p) in train mode; `state` = glue.DropoutState (seed + device step counter) or a false value = off."""
+    return G.dropout2d(x, c or x.shape[3], p, state) if (state and p > 0) else x
 
 
 def _sft_like(P, p, feats, kvec):
     """SFTLikeBlock.forward (model/modeling/blocks.py:105-120) on cat(features[64], kernel map[441]); the spatially constant
     kernel-map half of conv 0 is evaluated on a 3x3 image of border classes (as in _sft)."""
     n, h, w, fc = feats.shape
-    cond = _expand_vec(kvec, 3, 3).contiguous()
+    cond = _expand_vec(kvec, 3, 3)
 
     def branch(name):
         bp = p + ".conv_%s" % name
         w0 = P[bp + ".0.layer.weight"]
-        t = conv2d(feats, w0[:, :fc].contiguous(), None, padding=1)
-        tb = conv2d(cond, w0[:, fc:].contiguous(), P[bp + ".0.layer.bias"], padding=1)
-        t = prelu(t + _expand_classes(tb, h, w, 1), P[bp + ".0.act.weight"])
+        fcr = w0.shape[1] - kvec.shape[1]
+        t = conv2d(feats, w0, None, padding=1, cin_range=(0, fcr))
+        tb = conv2d(cond, w0, P[bp + ".0.layer.bias"], padding=1, cin_range=(fcr, kvec.shape[1]))
+        t = prelu(G.add(t, _expand_classes(tb, h, w, 1)), P[bp + ".0.act.weight"])
         return conv2d(t, P[bp + ".1.layer.weight"], P[bp + ".1.layer.bias"], padding=1)
-    return feats * torch.sigmoid(branch("scale")) + branch("shift")
+    return G.sft_combine(feats, branch("scale"), branch("shift"))
 
 
 def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_training=True, dropout=True, kvec=None):
@@ -264,7 +246,7 @@ def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_
     H, W = img.shape[2:]
     x = to_nhwc(img)
     x = _bn(P, p + "feats.bn1", conv2d(x, P[p + "feats.conv1.weight"], None, stride=2, padding=3), bn_training, relu=True)
-    x = _nhwc(F.max_pool2d(_nchw(x), kernel_size=3, stride=2, padding=1))
+    x = G.maxpool3s2(x)
     x3 = None
     for li, (planes, blocks, stride, dil) in enumerate(RESNET34_LAYERS, 1):
         for b in range(blocks):
@@ -284,14 +266,14 @@ def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_
     h, w = f.shape[1:3]
     priors = []
     for i, s in enumerate(sizes):
-        pooled = _nhwc(F.adaptive_avg_pool2d(_nchw(f), (s, s)))
+        pooled = G.adaptive_avgpool(f, s)
         pr = conv2d(pooled, P[p + "psp.stages.%d.1.weight" % i], None)
-        priors.append(_nhwc(F.interpolate(_nchw(pr), size=(h, w), mode="bilinear")))
+        priors.append(G.bilinear(pr, (h, w)))
     priors.append(f)
-    y = F.relu(conv2d(torch.cat(priors, dim=3), P[p + "psp.bottleneck.weight"], P[p + "psp.bottleneck.bias"]))
+    y = conv2d(_cat(priors), P[p + "psp.bottleneck.weight"], P[p + "psp.bottleneck.bias"], act="relu")
     y = _drop(y, 0.3, dropout)
     for name, dp in (("up_1", 0.15), ("up_2", 0.15), ("up_3", 0.15)):      # drop_2 after every up block (pspnet.py:106-113)
-        y = _nhwc(F.interpolate(_nchw(y), size=(2 * y.shape[1], 2 * y.shape[2]), mode="bilinear"))
+        y = G.bilinear(y, (2 * y.shape[1], 2 * y.shape[2]))
         y = _bn(P, p + name + ".conv.1", conv2d(y, P[p + name + ".conv.0.weight"], P[p + name + ".conv.0.bias"], padding=1),
                 bn_training)
         y = prelu(y, P[p + name + ".conv.2.weight"])
@@ -303,12 +285,13 @@ def pspnet_forward(P, img, sizes=(1, 2, 3, 6), prefix="segmentation_model.", bn_
             bp = p + "blur_skip.%d" % (2 * i + 1)
             t = _bn(P, bp + ".norm", conv2d(t, P[bp + ".layer.weight"], None, padding=1), bn_training, relu=True)
             i += 1
-        y = y + t
+        y = G.add(y, t)
     seg = torch.sigmoid(to_nchw(conv2d(y, P[p + "final.0.weight"], P[p + "final.0.bias"]), 1))
     a = _bn(P, p + "aux.1", conv2d(x3, P[p + "aux.0.weight"], None, padding=1), bn_training, relu=True)
     a = _drop(a, 0.1, dropout)
     a = torch.sigmoid(to_nchw(conv2d(a, P[p + "aux.4.weight"], P[p + "aux.4.bias"]), 1))
     aux = F.interpolate(a, size=(H, W), mode="bilinear", align_corners=True)
+    _flush_tracked()
     return seg, aux
 
 
@@ -319,7 +302,7 @@ def _cbr(P, pc, pb, x, training, stride=1, padding=0, relu=True, res=None):
 
 
 def _resize_ac(x, size):
-    return _nhwc(F.interpolate(_nchw(x), size=size, mode="bilinear", align_corners=True))
+    return G.bilinear(x, size, align_corners=True)
 
 
 def hrnet_w48(P, p, x, training):
@@ -363,8 +346,8 @@ def hrnet_w48(P, p, x, training):
                         for k in range(i - j):
                             term = _cbr(P, fp + ".%d.0" % k, fp + ".%d.1" % k, term, training, stride=2, padding=1,
                                         relu=(k != i - j - 1))
-                    y = term if y is None else y + term
-                fused.append(F.relu(y))
+                    y = term if y is None else G.add(y, term)
+                fused.append(G.relu(y))
             xs = fused
         ys, pre = xs, chans
     return ys, HRNET48_STAGES[-1][1]
@@ -399,8 +382,9 @@ def hrnet_ocr_forward(P, img, prefix="segmentation_model.", bn_training=True, dr
     context = torch.matmul(sim, value.view(B, 1, 256).float()).to(torch.bfloat16).view(B, h, w, 256)
     context = _bn(P, o + "f_up.1.0", conv2d(context, P[o + "f_up.0.weight"], P.get(o + "f_up.0.bias")), tr, relu=True)
     q = p + "ocr_distri_head.conv_bn_dropout."
-    f2 = _bn(P, q + "1.0", conv2d(torch.cat((context, f), dim=3), P[q + "0.weight"], P.get(q + "0.bias")), tr, relu=True)
+    f2 = _bn(P, q + "1.0", conv2d(_cat((context, f)), P[q + "0.weight"], P.get(q + "0.bias")), tr, relu=True)
     f2 = _drop(f2, 0.05, dropout)
     out = to_nchw(conv2d(f2, P[p + "cls_head.weight"], P[p + "cls_head.bias"]), 1)
     up = lambda t: F.interpolate(t, size=(H, W), mode="bilinear", align_corners=True)
+    _flush_tracked()
     return torch.sigmoid(up(out)), torch.sigmoid(up(out_aux))

@@ -135,6 +135,20 @@ int csbsr_resize_bicubic_aa_bwd(const float* dy, float* dx, int nc, int h, int w
  * mode 1: rows = B, cols = A with the taps flipped (dgrad of a stride-1 conv);
  * mode 2: rows = B, cols = A (ConvTranspose2d forward phases; dgrad of the 8x8/s4 conv). */
 int csbsr_pack_weights(const float* w, void* out, int a, int b, int r, int s, int rows_pad, int cols_pad, int mode, void* stream);
+/* the same for the input-channel window [b0, b0 + b) of a parameter whose second axis has b_total entries (the feature /
+ * conditioning halves of SFTlayer's conv0, kbpn.py:513-516, are packed straight from the one parameter) */
+int csbsr_pack_weights_window(const float* w, void* out, int a, int b, int b_total, int b0, int r, int s, int rows_pad,
+                              int cols_pad, int mode, void* stream);
+/* all (parameter, layout) pairs of a model in ONE launch per optimisation step: `jobs_device` is an array of njobs opaque
+ * job records (csbsr_pack_job_bytes() each, filled on the host by csbsr_pack_job_fill and copied to the device by the caller),
+ * `start` = exclusive prefix of the packed sizes r*s*rows_pad*cols_pad, `total` = their sum */
+size_t csbsr_pack_job_bytes(void);
+int csbsr_pack_job_fill(void* job_host, const float* w, void* out, int a, int b, int b_total, int b0, int r, int s, int rows_pad,
+                        int cols_pad, int mode, unsigned long long start);
+int csbsr_pack_weights_multi(const void* jobs_device, int njobs, unsigned long long total, void* stream);
+/* grad[a][b0 + b][tap] += wg[a][tap][b]: folds the accumulator of csbsr_conv_wgrad ([rows][taps][cs] fp32) into the parameter
+ * gradient in the parameter's own [A][b_total][R][S] layout (autograd's permute + contiguous + accumulate, trainer.py:69) */
+int csbsr_wgrad_unpack_add(const float* wg, float* grad, int a, int b, int b_total, int b0, int taps, int cs, void* stream);
 
 /* BatchNorm2d of the training graph on NHWC bf16 maps [m][pitch] whose first c channels are real (nn.BatchNorm2d in
  * pspnet_pytorch/extractors.py:52-70, pspnet.py:44-57, hrnet_backbone.py; reference runs them through cuDNN / aten).
@@ -257,6 +271,56 @@ int csbsr_degrade_fused(const float* hr, const double* params, float* kernels, f
  * offset + i (u = word * 2^-32).  Parity mode keeps the draws on the host (torch.rand / np.random.rand replayed). */
 int csbsr_degrade_params_philox(double* params, int b, unsigned long long seed, unsigned long long offset, double theta_lo,
                                 double theta_hi, double sigma_lo, double sigma_hi, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Training-step glue (csrc/glue.cu): what the reference's train step runs between its convolutions, and what autograd runs
+ * behind them (trainer.py:57-72 loss.backward()).  NHWC bf16 maps, channel windows (pitch, coff) in multiples of 8.
+ * ------------------------------------------------------------------------------------------- */
+/* bias gradient of nn.Conv2d / nn.ConvTranspose2d (kbpn.py:266-277): out[c] = sum over rows of dy[row, coff + c], fp32, fixed order */
+size_t csbsr_colsum_workspace_bytes(int c);
+int csbsr_bias_grad(const void* dy, int pitch, int coff, int c, long long rows, float* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* backward of ReLU (slope 0) / LeakyReLU on the saved output: dx = dy * (y > 0 ? 1 : slope) (kbpn.py:196-214, 513-516) */
+int csbsr_act_bwd(const void* dy, const void* y, void* dx, long long n, float slope, void* stream);
+/* out = [relu](alpha * a + beta * b), b may be NULL: residual adds / subs of the projection units (kbpn.py:464-469, 484-489) */
+int csbsr_axpby(const void* a, const void* b, void* out, long long n, float alpha, float beta, int relu, void* stream);
+/* SFTlayer.forward (kbpn.py:516-518): out = f * sigmoid(s) + t; backward df = dy*sig(s), ds = dy*f*sig*(1-sig) (dt = dy) */
+int csbsr_sft_combine(const void* f, const void* s, const void* t, void* out, long long n, void* stream);
+int csbsr_sft_combine_bwd(const void* dy, const void* f, const void* s, void* df, void* ds, long long n, void* stream);
+/* torch.cat along channels and its backward slices (kbpn.py:173-186, pspnet.py:40): copy a c-channel window, optionally
+ * zeroing `zero_tail` channels after it in the destination */
+int csbsr_window_copy(const void* src, int src_pitch, int src_coff, void* dst, int dst_pitch, int dst_coff, int c, int zero_tail,
+                      long long rows, void* stream);
+/* backward of csbsr_bilinear_nhwc (F.interpolate bilinear, pspnet.py:39,56): gather form, exact transpose of the forward */
+int csbsr_bilinear_nhwc_bwd(const void* dy, void* dx, int n, int h, int w, int oh, int ow, int c, int dy_pitch, int dy_coff,
+                            int dx_pitch, int dx_coff, int align_corners, void* stream);
+/* backward of csbsr_adaptive_avgpool_nhwc (nn.AdaptiveAvgPool2d, pspnet.py:32) */
+int csbsr_adaptive_avgpool_nhwc_bwd(const void* dy, void* dx, int n, int h, int w, int s, int c, int dy_pitch, int dy_coff,
+                                    int dx_pitch, int dx_coff, void* stream);
+/* backward of csbsr_maxpool3s2_nhwc (extractors.py:119): the gradient goes to the first maximum of each window */
+int csbsr_maxpool3s2_nhwc_bwd(const void* x, const void* dy, void* dx, int n, int h, int w, int c, int x_pitch, int x_coff,
+                              int dy_pitch, int dy_coff, int dx_pitch, int dx_coff, void* stream);
+/* nn.Dropout2d (pspnet.py:67,73,83): per-(sample, channel) keep mask scaled by 1/(1-p) from Philox4x32-10 keyed by `seed`,
+ * counter (index, salt, *counter) -- the step counter is read on the device so CUDA-graph replays draw fresh masks;
+ * csbsr_channel_scale applies it (forward and backward) */
+int csbsr_dropout2d_mask(float* scale, int n, int c, int c_pad, float p, unsigned long long seed,
+                         const unsigned long long* counter, unsigned int salt, void* stream);
+int csbsr_counter_inc(unsigned long long* counter, void* stream);
+int csbsr_channel_scale(const void* x, const float* scale, void* y, int n, long long hw, int c_pad, void* stream);
+/* spatially constant conditioning (kbpn.py:404, 513-516): [n, 2bw+1, 2bw+1, c] border-class responses -> [n, h, w, c], and the
+ * per-class sums of the gradient (two fixed-order stages) */
+int csbsr_expand_classes(const void* small, void* out, int n, int h, int w, int bw, int c_pad, void* stream);
+size_t csbsr_expand_classes_workspace_bytes(int n, int h, int bw, int c_pad);
+int csbsr_expand_classes_bwd(const void* dy, void* dsmall, int n, int h, int w, int bw, int c_pad, void* workspace,
+                             size_t workspace_bytes, void* stream);
+/* norm_sr 'instance' in training (build_model.py:135-137, no clip): y = (x - mean) * rstd with the statistics of
+ * csbsr_clip_instnorm_stats(do_clip = 0), and its backward dx = rstd * (dy - mean(dy) - xhat * mean(dy * xhat)) */
+int csbsr_instnorm_apply(const float* x, const float* mean, const float* rstd, float* y, int nc, long long hw, void* stream);
+size_t csbsr_instnorm_bwd_workspace_bytes(int nc);
+int csbsr_instnorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, float* dx, int nc, long long hw,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* NHWC bf16 window -> fp32 NCHW (the first c channels): images / logits leaving the networks */
+int csbsr_nhwc_bf16_to_nchw_f32(const void* x, float* y, int n, long long hw, int c, int x_pitch, int x_coff, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Joint-training losses (csrc/losses.cu): forward values and the gradient w.r.t. the segmentation predictions.

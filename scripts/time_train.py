@@ -82,7 +82,7 @@ def main():
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             step(40010)
             torch.cuda.synchronize()
-        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
     if a.layers:
         import collections
         from csbsr_b200 import kernels as K

@@ -247,7 +247,8 @@ def test_train_step_vs_reference_golden(variant):
                 if p_.numel() == 1:
                     # scalar PReLU slope: sum_{x<0} dy*x over ~1e6 signed terms cancelling to ~1e-3 of the gradient scale;
                     # operand rounding alone moves it by up to 4x in the oracle (probe) -> absolute bound
-                    ok = abs(got_n - ref_n) <= max(0.5 * max(ref_n, alt_n), 5e-3)
+                    # (the oracle's own shift under operand rounding, |alt - ref|, sets the scale of the noise)
+                    ok = abs(got_n - ref_n) <= max(0.5 * max(ref_n, alt_n), 2 * abs(alt_n - ref_n), 5e-3)
                 else:
                     # kb.sr_reconst (3 output channels feeding two nearly cancelling paths): the oracle moves by 17-18 % under
                     # operand rounding alone (probe) -> 30 %; every other tensor 15 % of either reference
