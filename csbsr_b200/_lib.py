@@ -61,6 +61,9 @@ class WgradDesc(C.Structure):
         ("ntaps", C.c_int32), ("stride", C.c_int32),
         ("dh", C.c_int8 * MAX_TAPS), ("dw", C.c_int8 * MAX_TAPS),
         ("wg", C.c_void_p),
+        ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
+        ("grad", C.c_void_p),
+        ("grad_a", C.c_int32), ("grad_b", C.c_int32), ("grad_btot", C.c_int32), ("grad_b0", C.c_int32), ("grad_cp", C.c_int32),
     ]
 
 
@@ -73,6 +76,7 @@ _SIGNATURES = {
     "csbsr_device_ok": (C.c_int, []),
     "csbsr_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "csbsr_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    "csbsr_conv_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(WgradDesc)]),
     "csbsr_tap_gather3x3": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "csbsr_blur_ps_bwd_input": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]),
@@ -84,6 +88,9 @@ _SIGNATURES = {
     "csbsr_pack_job_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_ulonglong]),
     "csbsr_pack_weights_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong, C.c_void_p]),
     "csbsr_wgrad_unpack_add": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_wgrad_unpack_add_tapexp": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_tapexp_gather_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_tapexp_scatter_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "csbsr_bn_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_float] + [C.c_void_p] * 6),
     "csbsr_bn_apply": (C.c_int, [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     "csbsr_bn_backward": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_longlong, C.c_int] + [C.c_void_p] * 5),

@@ -120,9 +120,12 @@ class _Conv2dFn(torch.autograd.Function):
             dx = g.t
         if ctx.needs_input_grad[1]:
             taps = [(r * dilation - padding, s * dilation - padding) for r in range(R) for s in range(S)]
-            wg = K.wgrad(Fmap(dy), Fmap(x), taps, stride=stride)
-            if not K.wgrad_accumulate(wg, weight, cin_range):          # registered parameter: folded into its .grad in place
+            tgt = K.wgrad_target(weight)
+            if tgt is not None:                    # registered parameter: reduced straight into its .grad, in its own layout
+                K.wgrad(Fmap(dy), Fmap(x), taps, stride=stride, into=(tgt, cin_range, 0))
+            else:
                 assert cin_range is None
+                wg = K.wgrad(Fmap(dy), Fmap(x), taps, stride=stride)
                 dw = wg[:co, :, :ci].reshape(co, R, S, ci).permute(0, 3, 1, 2).contiguous()
         if has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy, co)
@@ -160,12 +163,67 @@ class _Deconv8s4Fn(torch.autograd.Function):
             dx = g.t
         if ctx.needs_input_grad[1]:
             taps = [(r - 2, s - 2) for r in range(8) for s in range(8)]
-            wg = K.wgrad(Fmap(x), Fmap(dy), taps, stride=4)
-            if not K.wgrad_accumulate(wg, weight):
+            tgt = K.wgrad_target(weight)
+            if tgt is not None:
+                K.wgrad(Fmap(x), Fmap(dy), taps, stride=4, into=(tgt, None, 0))
+            else:
+                wg = K.wgrad(Fmap(x), Fmap(dy), taps, stride=4)
                 dw = wg[:ci, :, :co].reshape(ci, 8, 8, co).permute(0, 3, 1, 2).contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy, co)
         return dx, dw, db
+
+
+class _TapExpConv3x3Fn(torch.autograd.Function):
+    """3x3 / padding-1 conv with <= 4 output channels and no bias (KBlock.sr_reconst kbpn.py:361, output_conv :68): N = 3 would
+    pay the whole 9-tap A-operand stream for three useful columns, forward, dgrad and wgrad alike.  Instead z = x . W_exp is ONE
+    1x1 GEMM with 9 * 4 outputs (output t*4 + m = tap t of channel m at the same pixel), y gathers the nine shifted taps
+    (csbsr_tapexp_gather_nhwc); backward scatters dy into the same layout, so dx = dz . W_exp^T and dW = dz^T x are 1x1 GEMMs."""
+    CP = 4
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
+        co, ci, R, S = weight.shape
+        n, h, w, cp_in = x.shape
+        assert (R, S) == (3, 3) and co <= _TapExpConv3x3Fn.CP and cp_in == cpad(ci)
+        z = Fmap.empty(n, h, w, 64, device=x.device)
+        K.conv(Fmap(x), K.pack_tapexp_train(weight, cp_in, _TapExpConv3x3Fn.CP), z)
+        y = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=x.device)
+        _lib.check(_lib.lib().csbsr_tapexp_gather_nhwc(z.ptr(), 64, y.data_ptr(), 64, n, h, w, _TapExpConv3x3Fn.CP, co,
+                                                       _lib.stream_ptr()), "csbsr_tapexp_gather_nhwc")
+        _lib.count_launch("csbsr_tapexp_gather_nhwc")
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        co, ci = weight.shape[:2]
+        n, h, w, cp_in = x.shape
+        cp = _TapExpConv3x3Fn.CP
+        dy = dy.contiguous()
+        dz = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=x.device)
+        _lib.check(_lib.lib().csbsr_tapexp_scatter_nhwc(dy.data_ptr(), dy.shape[3], dz.data_ptr(), 64, n, h, w, cp, co,
+                                                        _lib.stream_ptr()), "csbsr_tapexp_scatter_nhwc")
+        _lib.count_launch("csbsr_tapexp_scatter_nhwc")
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            g = Fmap.empty(n, h, w, cp_in, device=x.device)
+            K.conv(Fmap(dz), K.pack_tapexp_train(weight, cp_in, cp, transpose=True), g)
+            dx = g.t
+        if ctx.needs_input_grad[1]:
+            tgt = K.wgrad_target(weight)
+            if tgt is not None:
+                K.wgrad(Fmap(dz), Fmap(x), [(0, 0)], into=(tgt, None, cp))
+            else:
+                wg = K.wgrad(Fmap(dz), Fmap(x), [(0, 0)])                   # [128][1][cp_in]
+                dw = wg[:9 * cp, 0, :ci].reshape(9, cp, ci)[:, :co].permute(1, 2, 0).reshape(co, ci, 3, 3).contiguous()
+        return dx, dw
+
+
+def conv3x3_few_outputs(x, weight):
+    return _TapExpConv3x3Fn.apply(x, weight)
 
 
 def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, act=None, cin_range=None):

@@ -32,6 +32,15 @@ struct WgradParams {
     // tap groups: G taps that share dw and whose dh are dh0 + j*rs*stride are served by ONE S box of TH + (G-1)*rs rows per
     // 64-channel chunk (the descriptor start moves by whole swizzle atoms); a unit = (group, 128-channel chunk of S)
     int G, ngroups, rs, b_box_bytes;
+    // accumulator columns: a unit owns unit_cols TMEM columns, tap j of the unit starts at j * col_stride.  merge = 1 (single
+    // 64-channel chunk of S and G > 1 vertical taps): ONE MMA of N = 64 * G covers all taps of the unit -- the N dimension's
+    // second-level stride (LBO) of the MN-major B descriptor is the vertical tap shift inside the shared S box
+    int merge, unit_cols, col_stride;
+    // ws != nullptr: every (pixel split, output element) is written once into ws[split][tap * cs_pad + c][row] with plain
+    // coalesced stores (32 lanes = 32 consecutive rows) and reduced over the splits by wgrad_reduce_kernel -- no atomics, no
+    // zero-fill of the result, bit-reproducible.  ws == nullptr: red.global.add into the zeroed wg (round-1 path)
+    float* ws;
+    int rows_pad, cg;
     float* wg;
     int* err_flag;
     int8_t dh[CSBSR_MAX_TAPS], dw[CSBSR_MAX_TAPS];      // per group: offsets of its first tap
@@ -142,9 +151,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                                (static_cast<uint32_t>(nw >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
                         const uint32_t b_unit = a_addr + 2 * kWgBox + 2 * p.b_box_bytes * (u - u0);
+                        const uint32_t d_unit = tmem_base + static_cast<uint32_t>((u - u0) * p.unit_cols);
+                        if (p.merge) {
+                            const uint32_t idesc_m = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                                     (static_cast<uint32_t>((64 * p.G) >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+                            const uint32_t tap_shift = static_cast<uint32_t>(p.rs * p.TW * 128);
+#pragma unroll
+                            for (int k = 0; k < kWgK / 16; ++k)
+                                umma_bf16(d_unit, make_desc_mn(a_addr + k * 2048), make_desc_mn(b_unit + k * 2048, tap_shift), idesc_m,
+                                          (t > t0 || k > 0) ? 1u : 0u);
+                            continue;
+                        }
                         for (int j = 0; j < p.G; ++j) {
                             const uint32_t b_addr = b_unit + static_cast<uint32_t>(j * p.rs * p.TW * 128);   // vertical tap shift
-                            const uint32_t d_addr = tmem_base + static_cast<uint32_t>(((u - u0) * p.G + j) * 128);
+                            const uint32_t d_addr = d_unit + static_cast<uint32_t>(j * p.col_stride);
 #pragma unroll
                             for (int k = 0; k < kWgK / 16; ++k)
                                 umma_bf16(d_addr, make_desc_mn(a_addr + k * 2048),
@@ -173,20 +193,31 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             tcgen05_fence_after();
             const int row = mt * 128 + q * 32 + lane;
             float* wrow = p.wg + static_cast<size_t>(row) * p.ntaps * p.cs_pad;
+            float* wsp = p.ws ? p.ws + static_cast<size_t>(split) * p.ntaps * p.cs_pad * p.rows_pad + row : nullptr;
+            const bool live = mt * 128 + q * 32 < p.cg;          // rows >= cg are zero padding of the last m tile: never read
             for (int u = u0; u < u1; ++u) {
                 const int grp = u / p.ncs, csc = u - grp * p.ncs;
                 const int nw = min(128, p.cs_pad - csc * 128);
                 for (int jt = 0; jt < p.G; ++jt) {
-                    float* dst = wrow + static_cast<size_t>(p.tap[grp * p.G + jt]) * p.cs_pad + csc * 128;
-                    const uint32_t col0 = static_cast<uint32_t>(((u - u0) * p.G + jt) * 128);
+                    const int gcol0 = p.tap[grp * p.G + jt] * p.cs_pad + csc * 128;
+                    float* dst = wrow + gcol0;
+                    const uint32_t col0 = static_cast<uint32_t>((u - u0) * p.unit_cols + jt * p.col_stride);
                     for (int c = 0; c < nw; c += 16) {
                         uint32_t v[16];
                         tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col0 + static_cast<uint32_t>(c), v);
                         tmem_ld_wait();
+                        if (wsp) {
+                            if (live) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            red_add_v4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                       __uint_as_float(v[j + 3]));
+                                for (int j = 0; j < 16; ++j)
+                                    wsp[static_cast<size_t>(gcol0 + c + j) * p.rows_pad] = __uint_as_float(v[j]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                red_add_v4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                           __uint_as_float(v[j + 3]));
+                        }
                     }
                 }
             }
@@ -199,6 +230,65 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// Sum of the per-split partials P[s][gcol][row] (gcol = tap * cs + c) with a shared-memory transpose so that both the reads
+// (along rows) and the writes are coalesced.  Tile columns enumerate j = c * T + tap (the order of a parameter gradient).
+//   mode 0: wg[row][tap][c] = sum            (rows >= cg are written as zero)
+//   mode 1: grad[row][b0 + c][tap] += sum    (row < A, c < B: the parameter's own [A][Btot][R][S] layout)
+__global__ void __launch_bounds__(1024)
+wgrad_reduce_kernel(const float* __restrict__ ws, int nsplit, int rows_pad, int cg, int T, int cs, float* __restrict__ out, int mode,
+                    int A, int B, int Btot, int b0) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 32: one element per thread, splits unrolled by 8
+    const int ncols = T * cs;
+    const int j0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const size_t sstride = static_cast<size_t>(ncols) * rows_pad;
+    {
+        const int j = j0 + ty, r = r0 + tx;
+        float v = 0.f;
+        if (j < ncols && r < cg) {
+            const int c = j / T, t = j - c * T;
+            const float* src = ws + static_cast<size_t>(t * cs + c) * rows_pad + r;
+            int sidx = 0;
+            for (; sidx + 8 <= nsplit; sidx += 8) {
+                float a[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) a[q] = src[(sidx + q) * sstride];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v += a[q];
+            }
+            for (; sidx < nsplit; ++sidx) v += src[sidx * sstride];
+        }
+        tile[ty][tx] = v;
+    }
+    __syncthreads();
+    {
+        const int r = r0 + ty, j = j0 + tx;
+        if (j >= ncols || r >= rows_pad) return;
+        const float v = tile[tx][ty];
+        const int c = j / T, t = j - c * T;
+        if (mode == 0) {
+            out[(static_cast<size_t>(r) * T + t) * cs + c] = v;
+        } else if (r < A && c < B) {
+            out[(static_cast<size_t>(r) * Btot + b0 + c) * T + t] += v;
+        }
+    }
+}
+// tap-expanded accumulator (one "tap", rows = t * cp + m): grad[m][b0 + c][t] += sum_s P[s][c][t * cp + m]
+__global__ void wgrad_reduce_tapexp_kernel(const float* __restrict__ ws, int nsplit, int rows_pad, int cs, float* __restrict__ grad,
+                                           int A, int B, int Btot, int b0, int cp) {
+    const size_t total = static_cast<size_t>(A) * B * 9;
+    const size_t sstride = static_cast<size_t>(cs) * rows_pad;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int t = static_cast<int>(i % 9);
+        const int c = static_cast<int>((i / 9) % B);
+        const int m = static_cast<int>(i / (static_cast<size_t>(9) * B));
+        const float* src = ws + static_cast<size_t>(c) * rows_pad + t * cp + m;
+        float v = 0.f;
+        for (int sidx = 0; sidx < nsplit; ++sidx) v += src[sidx * sstride];
+        grad[(static_cast<size_t>(m) * Btot + b0 + c) * 9 + t] += v;
+    }
 }
 
 typedef CUresult (*PFN_encodeTiledW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -222,9 +312,8 @@ static int* g_wg_err = nullptr;
 
 using namespace csbsr;
 
-extern "C" int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream_) {
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    CSBSR_REQUIRE(d && d->g && d->s && d->wg, "conv_wgrad: null pointer");
+static int wg_check(const csbsr_wgrad_desc* d) {
+    CSBSR_REQUIRE(d && d->g && d->s, "conv_wgrad: null pointer");
     CSBSR_REQUIRE(d->cg > 0 && d->cg % 64 == 0 && d->cs > 0 && d->cs % 64 == 0,
                   "conv_wgrad: channel counts (%d, %d) must be positive multiples of 64", d->cg, d->cs);
     CSBSR_REQUIRE(d->g_pitch % 8 == 0 && d->g_coff % 8 == 0 && d->s_pitch % 8 == 0 && d->s_coff % 8 == 0,
@@ -232,10 +321,12 @@ extern "C" int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream_) {
     CSBSR_REQUIRE(d->ntaps >= 1 && d->ntaps <= CSBSR_MAX_TAPS, "conv_wgrad: bad tap count %d", d->ntaps);
     CSBSR_REQUIRE(d->stride >= 1 && d->stride <= 8, "conv_wgrad: bad stride %d", d->stride);
     CSBSR_REQUIRE(d->n >= 1 && d->gh >= 1 && d->gw >= 1 && d->sh >= 1 && d->sw >= 1, "conv_wgrad: empty tensor");
-    PFN_encodeTiledW encode = wg_encode_fn();
-    CSBSR_REQUIRE(encode, "conv_wgrad: cuTensorMapEncodeTiled entry point unavailable");
+    return 0;
+}
 
-    WgradParams p;
+// work decomposition of one wgrad launch (tap groups, passes, pixel splits, pipeline stages)
+static int wg_plan(const csbsr_wgrad_desc* d, WgradParams& p) {
+    int G = 1;
     memset(&p, 0, sizeof(p));
     p.N = d->n; p.OH = d->gh; p.OW = d->gw;
     p.TW = d->gw > 8 ? 16 : 8;
@@ -247,7 +338,7 @@ extern "C" int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream_) {
     p.cs_pad = d->cs;
     p.ncs = (d->cs + 127) / 128;
     // ---- tap groups (same rule as the forward kernel): taps with equal dw and equal dh modulo the stride, dh in uniform steps
-    int G = 1, ngroups = d->ntaps, rs = 0;
+    int ngroups = d->ntaps, rs = 0;
     int8_t g_dh[CSBSR_MAX_TAPS], g_dw[CSBSR_MAX_TAPS], g_tap[CSBSR_MAX_TAPS];
     for (int t = 0; t < d->ntaps; ++t) { g_dh[t] = d->dh[t]; g_dw[t] = d->dw[t]; g_tap[t] = static_cast<int8_t>(t); }
     if (d->ntaps >= 2 && !getenv("CSBSR_NO_GROUPING")) {
@@ -293,13 +384,19 @@ extern "C" int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream_) {
     p.units_total = ngroups * p.ncs;
     const int m_tiles = (d->cg + 127) / 128;
     // units per pass: every tap of a unit owns 128 TMEM columns; spread the units evenly over the passes
-    const int max_units = kWgMaxUnits / G > 0 ? kWgMaxUnits / G : 1;
+    p.merge = (G > 1 && d->cs == 64 && !getenv("CSBSR_WGRAD_NO_MERGE")) ? 1 : 0;
+    p.col_stride = p.merge ? 64 : 128;
+    p.unit_cols = G * p.col_stride;
+    const int max_units = (kWgMaxUnits * 128) / p.unit_cols > 0 ? (kWgMaxUnits * 128) / p.unit_cols : 1;
     const int min_passes = (p.units_total + max_units - 1) / max_units;
     p.upp = (p.units_total + min_passes - 1) / min_passes;
     p.passes_per_m = (p.units_total + p.upp - 1) / p.upp;
     p.npass = m_tiles * p.passes_per_m;
     const int sms = num_sms();
-    int nsplit = (2 * sms + p.npass - 1) / p.npass;
+    // one work item per SM (the accumulators are single-buffered, so a second item per SM cannot overlap anyway), and every
+    // split costs one more pass over the output in the epilogue stores and in the reduction.  CSBSR_WGRAD_ITEMS_PER_SM overrides.
+    static const int items_per_sm = getenv("CSBSR_WGRAD_ITEMS_PER_SM") ? atoi(getenv("CSBSR_WGRAD_ITEMS_PER_SM")) : 1;
+    int nsplit = (items_per_sm * sms + p.npass - 1) / p.npass;
     if (nsplit > p.ptiles) nsplit = p.ptiles;
     if (nsplit < 1) nsplit = 1;
     p.tiles_per_split = (p.ptiles + nsplit - 1) / nsplit;
@@ -309,16 +406,54 @@ extern "C" int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream_) {
     p.stages = (kWgSmem - 2048) / p.stage_bytes;
     if (p.stages > 8) p.stages = 8;
     CSBSR_REQUIRE(p.stages >= 2, "conv_wgrad: not enough shared memory for 2 stages");
-    p.wg = d->wg;
+    p.rows_pad = m_tiles * 128;
+    p.cg = d->cg;
     memcpy(p.dh, g_dh, sizeof(p.dh));
     memcpy(p.dw, g_dw, sizeof(p.dw));
     memcpy(p.tap, g_tap, sizeof(p.tap));
+    return 0;
+}
+
+extern "C" size_t csbsr_conv_wgrad_workspace_bytes(const csbsr_wgrad_desc* d) {
+    WgradParams p;
+    if (wg_check(d) || wg_plan(d, p)) return 0;
+    return sizeof(float) * static_cast<size_t>(p.nsplit) * p.ntaps * p.cs_pad * p.rows_pad;
+}
+
+extern "C" int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (int rc = wg_check(d)) return rc;
+    CSBSR_REQUIRE(d->wg || (d->ws && d->grad), "conv_wgrad: no output (wg, or ws + grad)");
+    PFN_encodeTiledW encode = wg_encode_fn();
+    CSBSR_REQUIRE(encode, "conv_wgrad: cuTensorMapEncodeTiled entry point unavailable");
+    WgradParams p;
+    if (int rc = wg_plan(d, p)) return rc;
+    const int G = p.G, rs = p.rs, m_tiles = p.rows_pad / 128;
+    const int sms = num_sms();
+    const size_t ws_need = sizeof(float) * static_cast<size_t>(p.nsplit) * p.ntaps * p.cs_pad * p.rows_pad;
+    if (d->ws) {
+        CSBSR_REQUIRE(d->ws_bytes >= ws_need, "conv_wgrad: workspace too small (%zu < %zu)", (size_t)d->ws_bytes, ws_need);
+        CSBSR_REQUIRE((reinterpret_cast<uintptr_t>(d->ws) & 15) == 0, "conv_wgrad: workspace must be 16-byte aligned");
+        p.ws = static_cast<float*>(d->ws);
+    }
+    if (d->grad) {
+        CSBSR_REQUIRE(d->ws, "conv_wgrad: accumulating into a parameter gradient needs the workspace path");
+        if (d->grad_cp > 0)
+            CSBSR_REQUIRE(d->ntaps == 1 && d->grad_a <= d->grad_cp && 9 * d->grad_cp <= d->cg && d->grad_b <= d->cs,
+                          "conv_wgrad: bad tap-expanded gradient target");
+        else
+            CSBSR_REQUIRE(d->grad_a <= d->cg && d->grad_b <= d->cs, "conv_wgrad: gradient target larger than the operands");
+        CSBSR_REQUIRE(d->grad_a > 0 && d->grad_b > 0 && d->grad_b0 >= 0 && d->grad_b0 + d->grad_b <= d->grad_btot,
+                      "conv_wgrad: bad gradient window");
+    }
+    p.wg = d->wg;
     if (!g_wg_err) {
         CSBSR_CHECK_CUDA(cudaMalloc(&g_wg_err, sizeof(int)));
         CSBSR_CHECK_CUDA(cudaMemset(g_wg_err, 0, sizeof(int)));
     }
     p.err_flag = g_wg_err;
-    CSBSR_CHECK_CUDA(cudaMemsetAsync(d->wg, 0, sizeof(float) * static_cast<size_t>(m_tiles) * 128 * p.ntaps * p.cs_pad, stream));
+    if (!p.ws)
+        CSBSR_CHECK_CUDA(cudaMemsetAsync(d->wg, 0, sizeof(float) * static_cast<size_t>(m_tiles) * 128 * p.ntaps * p.cs_pad, stream));
 
     CUtensorMap tmG, tmS;
     {
@@ -353,6 +488,22 @@ extern "C" int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream_) {
     }
     const int grid = p.nitems < sms ? p.nitems : sms;
     conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tmG, tmS, p);
+    if (p.ws) {
+        const int ncols = p.ntaps * p.cs_pad;
+        if (d->wg)
+            wgrad_reduce_kernel<<<dim3((ncols + 31) / 32, p.rows_pad / 32), 1024, 0, stream>>>(p.ws, p.nsplit, p.rows_pad, p.cg, p.ntaps,
+                                                                                           p.cs_pad, d->wg, 0, 0, 0, 0, 0);
+        if (d->grad && d->grad_cp > 0) {
+            const size_t total = static_cast<size_t>(d->grad_a) * d->grad_b * 9;
+            int blocks = static_cast<int>((total + 255) / 256);
+            if (blocks > sms * 8) blocks = sms * 8;
+            wgrad_reduce_tapexp_kernel<<<blocks, 256, 0, stream>>>(p.ws, p.nsplit, p.rows_pad, p.cs_pad, d->grad, d->grad_a, d->grad_b,
+                                                                  d->grad_btot, d->grad_b0, d->grad_cp);
+        } else if (d->grad) {
+            wgrad_reduce_kernel<<<dim3((ncols + 31) / 32, (d->grad_a + 31) / 32), 1024, 0, stream>>>(
+                p.ws, p.nsplit, p.rows_pad, p.cg, p.ntaps, p.cs_pad, d->grad, 1, d->grad_a, d->grad_b, d->grad_btot, d->grad_b0);
+        }
+    }
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -488,6 +488,57 @@ __global__ void nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, flo
     }
 }
 
+// ------------------------------------------------------------------ tap-expanded 3x3 conv with <= 4 outputs (kbpn.py:361, :68)
+// z[pix, t*cp + m] = tap t of output m evaluated AT pix (a 1x1 GEMM over the input channels); the conv result gathers the nine
+// shifted taps: y[n, h, w, m] = sum_t z[n, h + t/3 - 1, w + t%3 - 1, t*cp + m] (zero outside); channels [co, yp) are zeroed
+__global__ void tapexp_gather_kernel(const __nv_bfloat16* __restrict__ z, int zp, __nv_bfloat16* __restrict__ y, int yp, int N,
+                                     int H, int W, int cp, int co) {
+    const size_t total = static_cast<size_t>(N) * H * W;
+    for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total; pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int w = static_cast<int>(pix % W);
+        const int h = static_cast<int>((pix / W) % H);
+        const size_t nb = pix - static_cast<size_t>(h) * W - w;          // first pixel of the image
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+            const __nv_bfloat16* src = z + (nb + static_cast<size_t>(hh) * W + ww) * zp + t * cp;
+            for (int m = 0; m < co; ++m) acc[m] += __bfloat162float(src[m]);
+        }
+        for (int m = co; m < 8; ++m) acc[m] = 0.f;
+        uint4* dst = reinterpret_cast<uint4*>(y + pix * yp);
+        dst[0] = g_pack8(acc);
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int g = 1; g < yp / 8; ++g) dst[g] = zero;
+    }
+}
+// its transpose (the gradient w.r.t. z): dz[n, h, w, t*cp + m] = dy[n, h - (t/3 - 1), w - (t%3 - 1), m]; channels >= 9*cp zero
+__global__ void tapexp_scatter_kernel(const __nv_bfloat16* __restrict__ dy, int dyp, __nv_bfloat16* __restrict__ dz, int zp, int N,
+                                      int H, int W, int cp, int co) {
+    const int G = zp / 8;
+    const size_t total = static_cast<size_t>(N) * H * W * G;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const size_t pix = i / G;
+        const int w = static_cast<int>(pix % W);
+        const int h = static_cast<int>((pix / W) % H);
+        const size_t nb = pix - static_cast<size_t>(h) * W - w;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = g * 8 + j, t = e / cp, m = e - t * cp;
+            float val = 0.f;
+            if (t < 9 && m < co) {
+                const int hh = h - (t / 3 - 1), ww = w - (t % 3 - 1);
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __bfloat162float(dy[(nb + static_cast<size_t>(hh) * W + ww) * dyp + m]);
+            }
+            v[j] = val;
+        }
+        *reinterpret_cast<uint4*>(dz + pix * zp + g * 8) = g_pack8(v);
+    }
+}
+
 }  // namespace csbsr
 
 using namespace csbsr;
@@ -673,6 +724,22 @@ extern "C" int csbsr_instnorm_bwd(const float* dy, const float* x, const float* 
 extern "C" int csbsr_nhwc_bf16_to_nchw_f32(const void* x, float* y, int n, long long hw, int c, int x_pitch, int x_coff, void* stream) {
     CSBSR_REQUIRE(x && y && n > 0 && hw > 0 && c > 0 && x_coff + c <= x_pitch, "nhwc_bf16_to_nchw_f32: bad arguments");
     nhwc_to_nchw_f32_kernel<<<glue_grid(static_cast<size_t>(n) * c * hw, 256), 256, 0, STREAM(stream)>>>(CBF(x), y, n, hw, c, x_pitch, x_coff);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_tapexp_gather_nhwc(const void* z, int z_pitch, void* y, int y_pitch, int n, int h, int w, int cp, int co, void* stream) {
+    CSBSR_REQUIRE(z && y && n > 0 && co >= 1 && co <= cp && cp <= 8 && 9 * cp <= z_pitch && z_pitch % 8 == 0 && y_pitch % 8 == 0 && co <= 8,
+                  "tapexp_gather: bad arguments");
+    tapexp_gather_kernel<<<glue_grid(static_cast<size_t>(n) * h * w, 256), 256, 0, STREAM(stream)>>>(CBF(z), z_pitch, BF(y), y_pitch, n, h, w, cp, co);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_tapexp_scatter_nhwc(const void* dy, int dy_pitch, void* dz, int z_pitch, int n, int h, int w, int cp, int co, void* stream) {
+    CSBSR_REQUIRE(dy && dz && n > 0 && co >= 1 && co <= cp && 9 * cp <= z_pitch && z_pitch % 8 == 0 && co <= dy_pitch, "tapexp_scatter: bad arguments");
+    tapexp_scatter_kernel<<<glue_grid(static_cast<size_t>(n) * h * w * (z_pitch / 8), 256), 256, 0, STREAM(stream)>>>(CBF(dy), dy_pitch, BF(dz),
+                                                                                                                  z_pitch, n, h, w, cp, co);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

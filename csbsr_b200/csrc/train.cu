@@ -336,6 +336,16 @@ struct PackJob {
 __device__ __forceinline__ void pack_one(const PackJob& j, size_t i) {
     const int col = static_cast<int>(i % j.cols_pad);
     const int row = static_cast<int>((i / j.cols_pad) % j.rows_pad);
+    if (j.mode >= 3) {
+        // tap expansion of a 3x3 conv with few outputs (A <= 4): one 1x1 GEMM with 9 * cp outputs, output t * cp + m = tap t
+        // of output m (cp = j.pad_).  mode 3: rows = (t, m), cols = input channel; mode 4 (its dgrad): the transpose
+        const int e = j.mode == 3 ? row : col, c = j.mode == 3 ? col : row;
+        const int t = e / j.pad_, m = e - t * j.pad_;
+        float v = 0.f;
+        if (t < 9 && m < j.A && c < j.B) v = j.w[(static_cast<size_t>(m) * j.Btot + j.b0 + c) * 9 + t];
+        j.out[i] = __float2bfloat16(v);
+        return;
+    }
     const int t = static_cast<int>(i / (static_cast<size_t>(j.cols_pad) * j.rows_pad));
     int r = t / j.S, s = t % j.S;
     const int a = j.mode == 0 ? row : col, b = j.mode == 0 ? col : row;
@@ -394,6 +404,18 @@ __global__ void wgrad_unpack_add_kernel(const float* __restrict__ wg, float* __r
         grad[(static_cast<size_t>(a) * Btot + b0 + b) * T + t] += wg[(static_cast<size_t>(a) * T + t) * cs + b];
     }
 }
+// tap-expanded form: grad[m][b0 + c][t] += wg[t * cp + m][c]   (wg: [rows][cs], a single "tap")
+__global__ void wgrad_unpack_add_tapexp_kernel(const float* __restrict__ wg, float* __restrict__ grad, int A, int B, int Btot, int b0,
+                                               int cp, int cs) {
+    const size_t total = static_cast<size_t>(A) * B * 9;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int t = static_cast<int>(i % 9);
+        const int c = static_cast<int>((i / 9) % B);
+        const int m = static_cast<int>(i / (static_cast<size_t>(9) * B));
+        grad[(static_cast<size_t>(m) * Btot + b0 + c) * 9 + t] += wg[static_cast<size_t>(t * cp + m) * cs + c];
+    }
+}
 }  // namespace csbsr
 
 extern "C" int csbsr_pack_weights(const float* w, void* out, int a, int b, int r, int s, int rows_pad, int cols_pad, int mode,
@@ -401,13 +423,25 @@ extern "C" int csbsr_pack_weights(const float* w, void* out, int a, int b, int r
     return csbsr_pack_weights_window(w, out, a, b, b, 0, r, s, rows_pad, cols_pad, mode, stream);
 }
 
+static int pack_job_check(int a, int b, int b_total, int b0, int r, int s, int rows_pad, int cols_pad, int mode) {
+    CSBSR_REQUIRE(a > 0 && b > 0 && r > 0 && s > 0 && mode >= 0 && mode <= 4 + 8 * 16 && b0 >= 0 && b0 + b <= b_total,
+                  "pack_weights: bad arguments");
+    const int m = mode & 7, cp = mode >> 3;
+    if (m >= 3) {
+        CSBSR_REQUIRE(m <= 4 && r == 1 && s == 1 && cp >= a && 9 * cp <= (m == 3 ? rows_pad : cols_pad) && b <= (m == 3 ? cols_pad : rows_pad),
+                      "pack_weights: tap-expanded modes need r = s = 1 (the 3x3 source is implied), cp >= a, 9 * cp within the padded extent");
+    } else {
+        CSBSR_REQUIRE(cp == 0 && rows_pad >= (m == 0 ? a : b) && cols_pad >= (m == 0 ? b : a), "pack_weights: padded extents too small");
+    }
+    return 0;
+}
+
 extern "C" int csbsr_pack_weights_window(const float* w, void* out, int a, int b, int b_total, int b0, int r, int s, int rows_pad,
                                          int cols_pad, int mode, void* stream) {
-    CSBSR_REQUIRE(w && out && a > 0 && b > 0 && r > 0 && s > 0 && mode >= 0 && mode <= 2 && b0 >= 0 && b0 + b <= b_total,
-                  "pack_weights: bad arguments");
-    CSBSR_REQUIRE(rows_pad >= (mode == 0 ? a : b) && cols_pad >= (mode == 0 ? b : a), "pack_weights: padded extents too small");
+    CSBSR_REQUIRE(w && out, "pack_weights: null pointer");
+    if (int rc = pack_job_check(a, b, b_total, b0, r, s, rows_pad, cols_pad, mode)) return rc;
     const size_t total = static_cast<size_t>(r) * s * rows_pad * cols_pad;
-    csbsr::PackJob job{w, reinterpret_cast<__nv_bfloat16*>(out), a, b, b_total, b0, r, s, rows_pad, cols_pad, mode, 0, 0ull};
+    csbsr::PackJob job{w, reinterpret_cast<__nv_bfloat16*>(out), a, b, b_total, b0, r, s, rows_pad, cols_pad, mode & 7, mode >> 3, 0ull};
     csbsr::pack_weights_kernel<<<grid_cap(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(job);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -417,9 +451,9 @@ extern "C" size_t csbsr_pack_job_bytes(void) { return sizeof(csbsr::PackJob); }
 
 extern "C" int csbsr_pack_job_fill(void* job_host, const float* w, void* out, int a, int b, int b_total, int b0, int r, int s,
                                    int rows_pad, int cols_pad, int mode, unsigned long long start) {
-    CSBSR_REQUIRE(job_host && w && out && a > 0 && b > 0 && b0 >= 0 && b0 + b <= b_total && mode >= 0 && mode <= 2,
-                  "pack_job_fill: bad arguments");
-    csbsr::PackJob job{w, reinterpret_cast<__nv_bfloat16*>(out), a, b, b_total, b0, r, s, rows_pad, cols_pad, mode, 0, start};
+    CSBSR_REQUIRE(job_host && w && out, "pack_job_fill: null pointer");
+    if (int rc = pack_job_check(a, b, b_total, b0, r, s, rows_pad, cols_pad, mode)) return rc;
+    csbsr::PackJob job{w, reinterpret_cast<__nv_bfloat16*>(out), a, b, b_total, b0, r, s, rows_pad, cols_pad, mode & 7, mode >> 3, start};
     memcpy(job_host, &job, sizeof(job));
     return 0;
 }
@@ -432,6 +466,16 @@ extern "C" int csbsr_pack_weights_multi(const void* jobs_device, int njobs, unsi
     if (blocks < 1) blocks = 1;
     csbsr::pack_weights_multi_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         static_cast<const csbsr::PackJob*>(jobs_device), njobs, total);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_wgrad_unpack_add_tapexp(const float* wg, float* grad, int a, int b, int b_total, int b0, int cp, int cs,
+                                             void* stream) {
+    CSBSR_REQUIRE(wg && grad && a > 0 && a <= cp && b > 0 && b <= cs && b0 >= 0 && b0 + b <= b_total, "wgrad_unpack_add_tapexp: bad arguments");
+    const size_t total = static_cast<size_t>(a) * b * 9;
+    csbsr::wgrad_unpack_add_tapexp_kernel<<<grid_cap(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(wg, grad, a, b,
+                                                                                                                 b_total, b0, cp, cs);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -334,8 +334,12 @@ def _refresh_all():
 
 
 def _pack_device(weight, rows_pad, cols_pad, mode, cin_range=None):
-    """Packing of a contiguous fp32 CUDA parameter (csbsr_pack_weights*); cin_range = (b0, b) packs a window of its second axis."""
+    """Packing of a contiguous fp32 CUDA parameter (csbsr_pack_weights*); cin_range = (b0, b) packs a window of its second axis.
+    mode & 7 >= 3: tap-expanded 3x3 weight (one packed "tap", cp = mode >> 3)."""
     a, btot, R, S = weight.shape
+    if (mode & 7) >= 3:
+        assert (R, S) == (3, 3)
+        R = S = 1
     b0, b = cin_range if cin_range is not None else (0, btot)
     reg = registered(weight)
     if reg is None:
@@ -355,18 +359,6 @@ def _pack_device(weight, rows_pad, cols_pad, mode, cin_range=None):
     return e["out"]
 
 
-def wgrad_accumulate(wg, weight, cin_range=None):
-    """Fold a csbsr_conv_wgrad accumulator into the gradient of a registered parameter in place (its .grad is a view of the
-    optimizer's flat gradient buffer).  Returns False when the parameter is not registered / has no gradient buffer."""
-    reg = registered(weight)
-    if reg is None or reg.grad is None or not reg.grad.is_contiguous():
-        return False
-    a, btot, R, S = weight.shape
-    b0, b = cin_range if cin_range is not None else (0, btot)
-    _call("csbsr_wgrad_unpack_add", wg.data_ptr(), reg.grad.data_ptr(), a, b, btot, b0, R * S, wg.shape[2])
-    return True
-
-
 def pack_conv_train(weight, bias=None, stride=1, padding=0, dilation=1, cin_pad=None, cout_pad=None, transpose_flip=False,
                     cin_range=None):
     """pack_conv for the training step: the fp32 parameter is packed by one kernel.  transpose_flip=True gives the operand of
@@ -383,6 +375,19 @@ def pack_conv_train(weight, bias=None, stride=1, padding=0, dilation=1, cin_pad=
     taps = [(r * dilation - padding, s * dilation - padding, r * S + s) for r in range(R) for s in range(S)]
     return PackedConv(wp, taps, 1, R * S, stride, 1, [0], [0], cout, _pad_bias(bias, cout_pad, w.device),
                       macs_per_pixel=R * S * cin * cout)
+
+
+def pack_tapexp_train(weight, cin_pad, cp=4, transpose=False):
+    """[co <= cp, ci, 3, 3] parameter -> 1x1 PackedConv of the tap-expanded conv (outputs t*cp + m, padded to 64) or, with
+    transpose=True, of its dgrad (64 tap-expanded channels -> ci)."""
+    w = weight.detach()
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.shape[2:] == (3, 3) and w.shape[0] <= cp
+    co, ci = w.shape[:2]
+    if transpose:
+        wp = _pack_device(w, cin_pad, 64, 4 | (cp << 3))
+        return PackedConv(wp, [(0, 0, 0)], 1, 1, 1, 1, [0], [0], ci, None, macs_per_pixel=9 * co * ci)
+    wp = _pack_device(w, 64, cin_pad, 3 | (cp << 3))
+    return PackedConv(wp, [(0, 0, 0)], 1, 1, 1, 1, [0], [0], 9 * cp, None, macs_per_pixel=9 * co * ci)
 
 
 def pack_deconv8s4_train(weight, bias=None, cin_pad=None, cout_pad=None):
@@ -439,9 +444,14 @@ def tap_gather3x3(z, co, out, r32=None):
     return out
 
 
-def wgrad(g, s, taps, stride=1):
+_WG_WS = {}
+
+
+def wgrad(g, s, taps, stride=1, into=None):
     """Weight gradient wg[m][t][c] = sum_pix g[pix, m] * s[pix*stride + taps[t], c] (fp32 [round_up(g.c,128), T, s.c]).
-    `g`, `s`: Fmaps whose channel windows are multiples of 64; `taps`: list of (dh, dw)."""
+    `g`, `s`: Fmaps whose channel windows are multiples of 64; `taps`: list of (dh, dw).  The pixel splits go through a
+    workspace and a fixed-order reduction (no atomics).  into = (parameter, cin_range or None, cp): instead of returning wg the
+    result is added to parameter.grad in the parameter's layout (cp > 0: tap-expanded accumulator) and None is returned."""
     d = _lib.WgradDesc()
     assert g.c % 64 == 0 and s.c % 64 == 0 and g.n == s.n and len(taps) <= _lib.MAX_TAPS
     d.g, d.n, d.gh, d.gw, d.g_pitch, d.g_coff, d.cg = g.ptr(), g.n, g.h, g.w, g.pitch, g.coff, g.c
@@ -449,12 +459,27 @@ def wgrad(g, s, taps, stride=1):
     d.ntaps, d.stride = len(taps), stride
     for i, (dh, dw) in enumerate(taps):
         d.dh[i], d.dw[i] = dh, dw
-    out = torch.empty((round_up(g.c, 128), len(taps), s.c), dtype=torch.float32, device=g.t.device)
-    d.wg = out.data_ptr()
+    L = _lib.lib()
+    need = L.csbsr_conv_wgrad_workspace_bytes(C.byref(d))
+    dev = g.t.device
+    ws = _WG_WS.get(str(dev))
+    if ws is None or ws.numel() < need:
+        ws = _WG_WS[str(dev)] = torch.empty(max(need, 1 << 26), dtype=torch.uint8, device=dev)
+    d.ws, d.ws_bytes = ws.data_ptr(), ws.numel()
+    out = None
+    if into is None:
+        out = torch.empty((round_up(g.c, 128), len(taps), s.c), dtype=torch.float32, device=dev)
+        d.wg = out.data_ptr()
+    else:
+        param, cin_range, cp = into
+        a, btot = param.shape[:2]
+        b0, b = cin_range if cin_range is not None else (0, btot)
+        d.wg = None
+        d.grad, d.grad_a, d.grad_b, d.grad_btot, d.grad_b0, d.grad_cp = param.grad.data_ptr(), a, b, btot, b0, cp
     if PROFILE_WG is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = _lib.lib().csbsr_conv_wgrad(C.byref(d), _lib.stream_ptr())
+    rc = L.csbsr_conv_wgrad(C.byref(d), _lib.stream_ptr())
     _lib.check(rc, "csbsr_conv_wgrad")
     _lib.count_launch("csbsr_conv_wgrad")
     if PROFILE_WG is not None:
@@ -462,6 +487,12 @@ def wgrad(g, s, taps, stride=1):
         PROFILE_WG.append(("wgrad n%d %dx%d cg%d cs%d taps%d s%d" % (g.n, g.h, g.w, g.c, s.c, len(taps), stride),
                            2.0 * g.n * g.h * g.w * g.c * s.c * len(taps), e0, e1))
     return out
+
+
+def wgrad_target(weight):
+    """The registered parameter whose .grad (a contiguous view of the optimizer's flat gradient) wgrad can accumulate into."""
+    reg = registered(weight)
+    return reg if (reg is not None and reg.grad is not None and reg.grad.is_contiguous()) else None
 
 
 # ------------------------------------------------------------------ support-kernel launchers

@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import glue as G
-from ..autograd import batch_norm, conv2d, cpad, deconv8s4, prelu
+from ..autograd import batch_norm, conv2d, conv3x3_few_outputs, cpad, deconv8s4, prelu
 from ..glue import to_nchw, to_nhwc
 from .params import RESNET34_LAYERS
 
@@ -31,6 +31,10 @@ def _cat(parts, real=None):
 
 
 def _convblock(P, p, x, stride=1, padding=0, act=None):
+    w_ = P[p + ".layer.weight"]
+    if (act is None and stride == 1 and padding == 1 and tuple(w_.shape[2:]) == (3, 3) and w_.shape[0] <= 4 and w_.shape[1] >= 64
+            and (p + ".layer.bias") not in P):
+        return conv3x3_few_outputs(x, w_)                 # sr_reconst / output_conv: tap-expanded 1x1 GEMMs
     y = conv2d(x, P[p + ".layer.weight"], P.get(p + ".layer.bias"), stride=stride, padding=padding, act=_EPI_ACT.get(act))
     return prelu(y, P[p + ".act.weight"]) if act == "prelu" else y
 

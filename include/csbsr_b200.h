@@ -100,9 +100,20 @@ typedef struct csbsr_wgrad_desc {
     int32_t sh, sw, s_pitch, s_coff, cs;
     int32_t ntaps, stride;
     int8_t dh[CSBSR_MAX_TAPS], dw[CSBSR_MAX_TAPS];
-    float* wg;
+    float* wg;                 /* [round_up(cg,128)][ntaps][cs] fp32 result; may be NULL when `grad` is given */
+    /* Optional workspace of csbsr_conv_wgrad_workspace_bytes(d) bytes (16-byte aligned): the pixel splits then write their
+     * partial sums with plain coalesced stores and a second kernel reduces them in a fixed order -- no atomics, no zero-fill,
+     * bit-reproducible.  Without it the splits add into the zeroed `wg` with red.global. */
+    void* ws;
+    size_t ws_bytes;
+    /* Optional (needs ws): fold the result straight into a parameter gradient in the parameter's own layout,
+     * grad[a][grad_b0 + b][tap] += wg[a][tap][b] for a < grad_a, b < grad_b (second axis of the parameter: grad_btot entries);
+     * grad_cp > 0: tap-expanded 3x3 accumulator, grad[m][grad_b0 + c][t] += wg[t * grad_cp + m][0][c] (m < grad_a, t < 9). */
+    float* grad;
+    int32_t grad_a, grad_b, grad_btot, grad_b0, grad_cp;
 } csbsr_wgrad_desc;
 
+size_t csbsr_conv_wgrad_workspace_bytes(const csbsr_wgrad_desc* d);
 int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -149,6 +160,8 @@ int csbsr_pack_weights_multi(const void* jobs_device, int njobs, unsigned long l
 /* grad[a][b0 + b][tap] += wg[a][tap][b]: folds the accumulator of csbsr_conv_wgrad ([rows][taps][cs] fp32) into the parameter
  * gradient in the parameter's own [A][b_total][R][S] layout (autograd's permute + contiguous + accumulate, trainer.py:69) */
 int csbsr_wgrad_unpack_add(const float* wg, float* grad, int a, int b, int b_total, int b0, int taps, int cs, void* stream);
+/* the same for the tap-expanded accumulator: grad[m][b0 + c][t] += wg[t * cp + m][c] */
+int csbsr_wgrad_unpack_add_tapexp(const float* wg, float* grad, int a, int b, int b_total, int b0, int cp, int cs, void* stream);
 
 /* BatchNorm2d of the training graph on NHWC bf16 maps [m][pitch] whose first c channels are real (nn.BatchNorm2d in
  * pspnet_pytorch/extractors.py:52-70, pspnet.py:44-57, hrnet_backbone.py; reference runs them through cuDNN / aten).
@@ -319,6 +332,11 @@ int csbsr_instnorm_apply(const float* x, const float* mean, const float* rstd, f
 size_t csbsr_instnorm_bwd_workspace_bytes(int nc);
 int csbsr_instnorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, float* dx, int nc, long long hw,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* 3x3 / padding-1 convs with <= 4 outputs (KBlock.sr_reconst kbpn.py:361, output_conv :68) in the training step: one 1x1 GEMM
+ * with 9 * cp outputs (pack modes 3 / 4 of csbsr_pack_weights_window, cp in mode >> 3), then y = gather of the nine shifted
+ * taps; its backward scatters dy back to the tap-expanded layout, so dgrad and wgrad are 1x1 GEMMs too (9x fewer MMAs) */
+int csbsr_tapexp_gather_nhwc(const void* z, int z_pitch, void* y, int y_pitch, int n, int h, int w, int cp, int co, void* stream);
+int csbsr_tapexp_scatter_nhwc(const void* dy, int dy_pitch, void* dz, int z_pitch, int n, int h, int w, int cp, int co, void* stream);
 /* NHWC bf16 window -> fp32 NCHW (the first c channels): images / logits leaving the networks */
 int csbsr_nhwc_bf16_to_nchw_f32(const void* x, float* y, int n, long long hw, int c, int x_pitch, int x_coff, void* stream);
 

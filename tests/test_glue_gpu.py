@@ -168,3 +168,24 @@ def test_bias_grad_and_conv_act_epilogue():
         _close(x.grad, xr.grad, 1e-2, "dx")
         _close(w_.grad, wr.grad, 1e-2, "dw")
         _close(b_.grad, br.grad, 1e-2, "db")
+
+
+@pytest.mark.parametrize("ci,h,w", [(128, 12, 16), (512, 9, 11)])
+def test_tap_expanded_conv3x3_fwd_bwd(ci, h, w):
+    """sr_reconst / output_conv as tap-expanded 1x1 GEMMs against F.conv2d (3 outputs, padding 1), forward, dx and dw."""
+    from csbsr_b200 import autograd as A
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(21)
+    x0 = torch.randn(2, ci, h, w, generator=g).to(torch.bfloat16).float().cuda()
+    w0 = (torch.randn(3, ci, 3, 3, generator=g) * (2.0 / (9 * ci)) ** 0.5).to(torch.bfloat16).float().cuda()
+    x, w_ = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    xr, wr = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    y = A.conv3x3_few_outputs(A.to_nhwc(x), w_)
+    yr = F.conv2d(xr, wr, None, padding=1)
+    assert (y[..., 3:] == 0).all()
+    _close(A.to_nchw(y, 3), yr, 2e-2, "tapexp forward")          # z is rounded to bf16 before the nine taps are summed
+    up = torch.randn(yr.shape, generator=torch.Generator().manual_seed(22)).to(torch.bfloat16).float().cuda()
+    y.backward(A.to_nhwc(up))
+    yr.backward(up)
+    _close(x.grad, xr.grad, 1e-2, "tapexp dx")
+    _close(w_.grad, wr.grad, 1e-2, "tapexp dw")
