@@ -86,7 +86,8 @@ _SIGNATURES = {
     "csbsr_pack_weights_window": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
     "csbsr_pack_job_bytes": (C.c_size_t, []),
     "csbsr_pack_job_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_ulonglong]),
-    "csbsr_pack_weights_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong, C.c_void_p]),
+    "csbsr_pack_job_tiles": (C.c_longlong, [C.c_int] * 7),
+    "csbsr_pack_weights_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong, C.c_int, C.c_void_p]),
     "csbsr_wgrad_unpack_add": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "csbsr_wgrad_unpack_add_tapexp": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "csbsr_tapexp_gather_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),

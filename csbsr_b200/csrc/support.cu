@@ -30,6 +30,33 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
     }
 }
 
+// 128-bit form: one thread per (pixel, 8-channel group) -> consecutive threads write consecutive 16-byte chunks of a pixel row
+__global__ void nchw_to_nhwc_vec_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int H, int W,
+                                        int pitch, int coff, int cwrite) {
+    const int G = cwrite / 8;
+    const size_t HW = static_cast<size_t>(H) * W;
+    const size_t total = static_cast<size_t>(N) * HW * G;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const size_t pix = i / G;
+        const size_t n = pix / HW, p = pix - n * HW;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (g * 8 < C) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = g * 8 + j;
+                v[j] = c < C ? x[(n * C + c) * HW + p] : 0.f;
+            }
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        }
+        *reinterpret_cast<uint4*>(y + pix * pitch + coff + g * 8) = o;
+    }
+}
+
 // ------------------------------------------------------------------ 3-channel patch gather (im2col)
 // y[n,oh,ow,(r*S+s)*C+c] = f(x[n,c,oh*st+r*dil-pad, ow*st+s*dil-pad]) (0 outside), channels >= R*S*C zero.
 // f = identity, or clamp to [0,1] followed by (v-mean[n,c])*rstd[n,c] (clip_sr + norm_sr, build_model.py:135-146).
@@ -587,8 +614,12 @@ extern "C" int csbsr_nchw_f32_to_nhwc_bf16(const float* x, void* y, int n, int c
                                            int y_coff, int cwrite, void* stream) {
     CSBSR_REQUIRE(x && y && n > 0 && c > 0 && h > 0 && w > 0 && cwrite >= c, "nchw_to_nhwc: bad arguments");
     const size_t total = static_cast<size_t>(n) * h * w * cwrite;
-    nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, c,
-                                                                         h, w, y_pitch, y_coff, cwrite);
+    if (cwrite % 8 == 0 && y_pitch % 8 == 0 && y_coff % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)
+        nchw_to_nhwc_vec_kernel<<<grid_for(total / 8, 256), 256, 0, STREAM(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, c, h, w,
+                                                                                     y_pitch, y_coff, cwrite);
+    else
+        nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, c,
+                                                                             h, w, y_pitch, y_coff, cwrite);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -362,13 +362,52 @@ __global__ void pack_weights_kernel(const PackJob job) {
         pack_one(job, i);
 }
 
-// every registered (parameter, layout) pair of the model in ONE launch: jobs[] lives in device memory, `start` is the
-// exclusive prefix of the job sizes; each block walks a contiguous chunk of the concatenated index space
-__global__ void pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int njobs, unsigned long long total) {
-    const unsigned long long per = (total + gridDim.x - 1) / gridDim.x;
-    const unsigned long long lo = per * blockIdx.x, hi = min(total, lo + per);
+// every registered (parameter, layout) pair of the model in ONE launch: jobs[] lives in device memory, `start` is the exclusive
+// prefix of the jobs' TILE counts.  A tile is 4 x 32 (mode 0: a x b) or 32 x 4 (modes 1, 2) source rows/columns with all R*S taps:
+// the source is read in runs of 32*T (4*T) contiguous floats, transposed through shared memory and written as 64-byte runs
+// along the packed operand's contiguous axis -- the element-wise form reads with a stride of T floats (12.5 % sector efficiency
+// for the 8x8 weights).  Only the valid region is written: the cached packed buffers are zero-initialised once.
+__host__ __device__ __forceinline__ int pack_tile_factor(int T) { return T > 32 ? 1 : (T > 16 ? 2 : (T > 8 ? 4 : 8)); }
+__host__ __device__ __forceinline__ long long pack_job_tiles(int A, int B, int T, int rows_pad, int cols_pad, int mode) {
+    if (mode >= 3) return (static_cast<long long>(rows_pad) * cols_pad + 1023) / 1024;
+    const int f = pack_tile_factor(T);
+    return mode == 0 ? static_cast<long long>((A + 4 * f - 1) / (4 * f)) * ((B + 31) / 32)
+                     : static_cast<long long>((A + 31) / 32) * ((B + 4 * f - 1) / (4 * f));
+}
+// one tile of a mode 0 / 1 / 2 job: every thread owns one (a, b) pair and walks its R*S taps -- nested loops instead of index
+// divisions, no shared memory.  Lanes run along the packed operand's contiguous axis (b for mode 0, a for modes 1 / 2), so the
+// bf16 stores are 64-byte runs; the fp32 source is read in per-warp regions of 32*T (mode 0) or 4f*T per lane (modes 1 / 2)
+// contiguous floats that stay in L1 across the tap loop.
+template <bool M0>
+__device__ __forceinline__ void pack_tile(const PackJob& cur, int lt) {
+    const int T = cur.R * cur.S;
+    const int f = pack_tile_factor(T);
+    const int na = M0 ? 4 * f : 32, nb = M0 ? 32 : 4 * f;
+    const int tiles_b = (cur.B + nb - 1) / nb;
+    const int a0 = (lt / tiles_b) * na, bb0 = (lt % tiles_b) * nb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t plane = static_cast<size_t>(cur.rows_pad) * cur.cols_pad;
+    for (int k = warp; k < (M0 ? na : nb); k += 8) {
+        const int a = a0 + (M0 ? k : lane), b = bb0 + (M0 ? lane : k);
+        if (a >= cur.A || b >= cur.B) continue;
+        const float* src = cur.w + (static_cast<size_t>(a) * cur.Btot + cur.b0 + b) * T;
+        __nv_bfloat16* dst = cur.out + (M0 ? static_cast<size_t>(a) * cur.cols_pad + b : static_cast<size_t>(b) * cur.cols_pad + a);
+        if (cur.mode == 1) {
+            for (int t = 0; t < T; ++t) dst[static_cast<size_t>(T - 1 - t) * plane] = __float2bfloat16(src[t]);   // taps flipped
+        } else {
+            for (int t = 0; t < T; ++t) dst[static_cast<size_t>(t) * plane] = __float2bfloat16(src[t]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int njobs, unsigned long long total_tiles) {
+    __shared__ PackJob cur;
+    // every block owns a contiguous range of tiles: the job is searched once and then advanced sequentially
+    const unsigned long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const unsigned long long lo = per * blockIdx.x, hi = min(total_tiles, lo + per);
     if (lo >= hi) return;
-    int j = 0;                                            // first job containing `lo` (binary search on start)
+    int j;
     {
         int a = 0, b = njobs - 1;
         while (a < b) {
@@ -377,17 +416,26 @@ __global__ void pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int 
         }
         j = a;
     }
-    __shared__ PackJob cur;
-    unsigned long long pos = lo;
-    while (pos < hi) {
-        __syncthreads();
-        if (threadIdx.x == 0) cur = jobs[j];
-        __syncthreads();
-        const unsigned long long jsize = static_cast<unsigned long long>(cur.R) * cur.S * cur.rows_pad * cur.cols_pad;
-        const unsigned long long jend = min(hi, cur.start + jsize);
-        for (unsigned long long i = pos + threadIdx.x; i < jend; i += blockDim.x) pack_one(cur, static_cast<size_t>(i - cur.start));
-        pos = jend;
-        ++j;
+    unsigned long long jend = 0;
+    bool have = false;
+    for (unsigned long long tile = lo; tile < hi; ++tile) {
+        if (!have || tile >= jend) {
+            if (have) ++j;
+            __syncthreads();
+            if (threadIdx.x == 0) cur = jobs[j];
+            __syncthreads();
+            jend = cur.start + static_cast<unsigned long long>(pack_job_tiles(cur.A, cur.B, cur.R * cur.S, cur.rows_pad, cur.cols_pad, cur.mode));
+            have = true;
+            if (tile >= jend) { --tile; continue; }         // (empty job: cannot happen, sizes are positive)
+        }
+        const int lt = static_cast<int>(tile - cur.start);
+        const int T = cur.R * cur.S;
+        if (cur.mode >= 3) {
+            const size_t n = static_cast<size_t>(cur.rows_pad) * cur.cols_pad;
+            for (size_t i = static_cast<size_t>(lt) * 1024 + threadIdx.x; i < min(n, static_cast<size_t>(lt + 1) * 1024); i += 256) pack_one(cur, i);
+            continue;
+        }
+        if (cur.mode == 0) pack_tile<true>(cur, lt); else pack_tile<false>(cur, lt);
     }
 }
 
@@ -458,14 +506,19 @@ extern "C" int csbsr_pack_job_fill(void* job_host, const float* w, void* out, in
     return 0;
 }
 
-extern "C" int csbsr_pack_weights_multi(const void* jobs_device, int njobs, unsigned long long total, void* stream) {
-    CSBSR_REQUIRE(jobs_device && njobs > 0 && total > 0, "pack_weights_multi: bad arguments");
-    int blocks = static_cast<int>((total + 256ull * 16 - 1) / (256ull * 16));
-    const int cap = csbsr::num_sms() * 8;
+extern "C" long long csbsr_pack_job_tiles(int a, int b, int r, int s, int rows_pad, int cols_pad, int mode) {
+    return csbsr::pack_job_tiles(a, b, r * s, rows_pad, cols_pad, mode & 7);
+}
+
+extern "C" int csbsr_pack_weights_multi(const void* jobs_device, int njobs, unsigned long long total_tiles, int max_taps, void* stream) {
+    CSBSR_REQUIRE(jobs_device && njobs > 0 && total_tiles > 0 && max_taps >= 1 && max_taps <= 64, "pack_weights_multi: bad arguments");
+    unsigned long long blocks = total_tiles;
+    const unsigned long long cap = static_cast<unsigned long long>(csbsr::num_sms()) * 8;
     if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    csbsr::pack_weights_multi_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        static_cast<const csbsr::PackJob*>(jobs_device), njobs, total);
+    (void)max_taps;
+    const int smem = 0;
+    csbsr::pack_weights_multi_kernel<<<static_cast<int>(blocks), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        static_cast<const csbsr::PackJob*>(jobs_device), njobs, total_tiles);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -284,14 +284,14 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
 # request that follows an optimizer step (invalidate_packed()), instead of one launch per use (297 per step).
 _REG = {}                      # data_ptr -> parameter
 _PACKS = {}                    # (data_ptr, A, Btot, b0, B, R, S, rows_pad, cols_pad, mode) -> entry
-_PACK_STATE = {"epoch": 0, "dev": None, "n": 0, "total": 0, "dirty": True}
+_PACK_STATE = {"epoch": 0, "dev": None, "n": 0, "total": 0, "taps": 1, "dirty": True}
 
 
 def register_params(params):
     """Called by the optimizer that owns the flat parameter / gradient buffers; a new optimizer replaces the previous set."""
     _REG.clear()
     _PACKS.clear()
-    _PACK_STATE.update(dev=None, n=0, total=0, dirty=True)
+    _PACK_STATE.update(dev=None, n=0, total=0, taps=1, dirty=True)
     for p in params:
         _REG[p.data_ptr()] = p
 
@@ -314,21 +314,22 @@ def flush_pack_table():
     L = _lib.lib()
     jb = L.csbsr_pack_job_bytes()
     buf = (C.c_ubyte * (jb * len(_PACKS)))()
-    start = 0
+    start, taps = 0, 1
     for i, (key, e) in enumerate(_PACKS.items()):
         _, a, btot, b0, b, R, S, rows_pad, cols_pad, mode = key
         _lib.check(L.csbsr_pack_job_fill(C.byref(buf, i * jb), e["w"].data_ptr(), e["out"].data_ptr(), a, b, btot, b0, R, S,
                                          rows_pad, cols_pad, mode, start), "csbsr_pack_job_fill")
-        start += R * S * rows_pad * cols_pad
+        start += L.csbsr_pack_job_tiles(a, b, R, S, rows_pad, cols_pad, mode)
+        taps = max(taps, R * S)
     dev = next(iter(_PACKS.values()))["out"].device
     st["dev"] = torch.frombuffer(buf, dtype=torch.uint8).clone().to(dev)
-    st["n"], st["total"], st["dirty"] = len(_PACKS), start, False
+    st["n"], st["total"], st["taps"], st["dirty"] = len(_PACKS), start, taps, False
 
 
 def _refresh_all():
     st = _PACK_STATE
     flush_pack_table()
-    _call("csbsr_pack_weights_multi", st["dev"].data_ptr(), st["n"], st["total"])
+    _call("csbsr_pack_weights_multi", st["dev"].data_ptr(), st["n"], st["total"], st["taps"])
     for e in _PACKS.values():
         e["epoch"], e["version"] = st["epoch"], e["w"]._version
 

@@ -152,11 +152,13 @@ int csbsr_pack_weights_window(const float* w, void* out, int a, int b, int b_tot
                               int cols_pad, int mode, void* stream);
 /* all (parameter, layout) pairs of a model in ONE launch per optimisation step: `jobs_device` is an array of njobs opaque
  * job records (csbsr_pack_job_bytes() each, filled on the host by csbsr_pack_job_fill and copied to the device by the caller),
- * `start` = exclusive prefix of the packed sizes r*s*rows_pad*cols_pad, `total` = their sum */
+ * `start` = exclusive prefix of the jobs' tile counts csbsr_pack_job_tiles(...), `total_tiles` = their sum, max_taps = the
+ * largest r*s among the jobs (<= 64).  Only the valid region of every packed buffer is written: zero-initialise them once. */
+long long csbsr_pack_job_tiles(int a, int b, int r, int s, int rows_pad, int cols_pad, int mode);
 size_t csbsr_pack_job_bytes(void);
 int csbsr_pack_job_fill(void* job_host, const float* w, void* out, int a, int b, int b_total, int b0, int r, int s, int rows_pad,
                         int cols_pad, int mode, unsigned long long start);
-int csbsr_pack_weights_multi(const void* jobs_device, int njobs, unsigned long long total, void* stream);
+int csbsr_pack_weights_multi(const void* jobs_device, int njobs, unsigned long long total_tiles, int max_taps, void* stream);
 /* grad[a][b0 + b][tap] += wg[a][tap][b]: folds the accumulator of csbsr_conv_wgrad ([rows][taps][cs] fp32) into the parameter
  * gradient in the parameter's own [A][b_total][R][S] layout (autograd's permute + contiguous + accumulate, trainer.py:69) */
 int csbsr_wgrad_unpack_add(const float* wg, float* grad, int a, int b, int b_total, int b0, int taps, int cs, void* stream);
