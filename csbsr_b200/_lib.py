@@ -80,7 +80,8 @@ _SIGNATURES = {
     "csbsr_tap_gather3x3": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "csbsr_blur_ps_bwd_input": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]),
-    "csbsr_blur_ps_bwd_kernel": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_blur_ps_bwd_kernel_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
+    "csbsr_blur_ps_bwd_kernel": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
     "csbsr_resize_bicubic_aa_bwd": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 5 + [C.c_void_p]),
     "csbsr_pack_weights": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]),
     "csbsr_pack_weights_window": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
@@ -92,13 +93,18 @@ _SIGNATURES = {
     "csbsr_wgrad_unpack_add_tapexp": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "csbsr_tapexp_gather_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "csbsr_tapexp_scatter_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_patch_split": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_patch_join": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "csbsr_crop_flip_u8": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_float, C.c_void_p]),
     "csbsr_bn_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_float] + [C.c_void_p] * 6),
     "csbsr_bn_apply": (C.c_int, [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
-    "csbsr_bn_backward": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_longlong, C.c_int] + [C.c_void_p] * 5),
+    "csbsr_bn_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "csbsr_bn_backward": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_longlong, C.c_int] + [C.c_void_p] * 6),
     "csbsr_psnr_ssim_workspace_bytes": (C.c_size_t, [C.c_int]),
     "csbsr_psnr_ssim": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p]),
     "csbsr_prelu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
-    "csbsr_prelu_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
+    "csbsr_prelu_bwd_workspace_bytes": (C.c_size_t, []),
+    "csbsr_prelu_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p, C.c_void_p]),
     "csbsr_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong] + [C.c_float] * 4 + [C.c_int, C.c_float, C.c_int,
                                                                                        C.c_void_p]),
     "csbsr_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]),

@@ -40,6 +40,18 @@ def _mask_by_act(dy, y, slope):
     return g
 
 
+_SCRATCH = {}
+
+
+def _scratch(nbytes, device, tag):
+    """Grow-only scratch buffer per (tag, device) for the fixed-order reductions; launches on one stream run in order."""
+    key = (tag, str(device))
+    ws = _SCRATCH.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = _SCRATCH[key] = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    return ws
+
+
 def _bias_grad(dy, c):
     from .glue import bias_grad
     return bias_grad(dy, c)
@@ -260,8 +272,9 @@ class _PReLUFn(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty_like(x)
         ds = torch.empty(1, dtype=torch.float32, device=x.device)
+        ws = _scratch(_lib.lib().csbsr_prelu_bwd_workspace_bytes(), x.device, "prelu")
         _lib.check(_lib.lib().csbsr_prelu_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), slope.data_ptr(), ds.data_ptr(),
-                                              x.numel(), _lib.stream_ptr()), "csbsr_prelu_bwd")
+                                              x.numel(), ws.data_ptr(), _lib.stream_ptr()), "csbsr_prelu_bwd")
         _lib.count_launch("csbsr_prelu_bwd")
         return dx, ds.view(slope.shape)
 
@@ -302,8 +315,9 @@ class _BlurFn(torch.autograd.Function):
             _lib.count_launch("csbsr_blur_ps_bwd_input")
         if ctx.needs_input_grad[1]:
             dk = torch.empty_like(kvec)
+            ws = _scratch(L.csbsr_blur_ps_bwd_kernel_workspace_bytes(b, c, h, w, ksize, stride), img.device, "blur_dk")
             _lib.check(L.csbsr_blur_ps_bwd_kernel(img.data_ptr(), dy.data_ptr(), dk.data_ptr(), b, c, h, w, ksize, stride,
-                                                  _lib.stream_ptr()), "csbsr_blur_ps_bwd_kernel")
+                                                  ws.data_ptr(), _lib.stream_ptr()), "csbsr_blur_ps_bwd_kernel")
             _lib.count_launch("csbsr_blur_ps_bwd_kernel")
         return dx, dk, None, None
 
@@ -358,7 +372,7 @@ class _BatchNormFn(torch.autograd.Function):
         if training:
             mean = torch.empty(c, dtype=torch.float32, device=x.device)
             rstd = torch.empty(c, dtype=torch.float32, device=x.device)
-            ws = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+            ws = _scratch(L.csbsr_bn_workspace_bytes(c), x.device, "bn")
             _lib.check(L.csbsr_bn_stats(x.data_ptr(), pitch, c, m, eps, momentum, mean.data_ptr(), rstd.data_ptr(),
                                         running_mean.data_ptr() if running_mean is not None else None,
                                         running_var.data_ptr() if running_var is not None else None, ws.data_ptr(),
@@ -391,10 +405,12 @@ class _BatchNormFn(torch.autograd.Function):
         dres = torch.empty_like(x) if has_res else None
         dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+        ws = _scratch(_lib.lib().csbsr_bn_workspace_bytes(c), x.device, "bn")
         _lib.check(_lib.lib().csbsr_bn_backward(dy.data_ptr(), x.data_ptr(), y.data_ptr() if y is not None else None,
                                                 mean.data_ptr(), rstd.data_ptr(), g32.data_ptr(), pitch, c, n * h * w,
                                                 int(training), dx.data_ptr(), dres.data_ptr() if has_res else None,
-                                                dgamma.data_ptr(), dbeta.data_ptr(), _lib.stream_ptr()), "csbsr_bn_backward")
+                                                dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), _lib.stream_ptr()),
+                   "csbsr_bn_backward")
         _lib.count_launch("csbsr_bn_backward")
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None
 

@@ -858,12 +858,15 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     // cta_group::2 (CTA pairs, M = 256 per instruction, each CTA holds half of the weight rows -> smaller pipeline stages,
     // more of them in flight): measured -9..-23 % on the layers with K = taps x cin >= 1152 and at least a wave of pixel
     // tiles (8x8/s4 convs, SFT / PSP / ResNet 3x3s), +10..+40 % on short-K or tiny layers (profiles/r02_cg2_layers.md), so
-    // it is switched on by that rule.  CSBSR_CTA_GROUP=1 / 2 forces it off / on.
+    // it is switched on by that rule -- stated per IMAGE (>= 16 pixel tiles = 2048 output pixels), not per launch: M = 256
+    // instructions round differently from M = 128 ones, and the result of an image must not depend on how many other images
+    // share its launch (rank shards of a batch reproduce the single-process result bit for bit, tests/test_multigpu_gpu.py).
+    // CSBSR_CTA_GROUP=1 / 2 forces it off / on.
     const char* cg_env = getenv("CSBSR_CTA_GROUP");
     int cg2 = 0;
     const bool cg2_ok = block_n % 32 == 0 && p.m_tiles >= 2;
     if (cg_env) cg2 = (atoi(cg_env) == 2 && cg2_ok) ? 1 : 0;
-    else cg2 = (cg2_ok && d->ntaps * d->cin >= 1024 && p.m_tiles >= 128) ? 1 : 0;
+    else cg2 = (cg2_ok && d->ntaps * d->cin >= 1024 && p.tiles_h * p.tiles_w >= 16) ? 1 : 0;
     if (cg2) cluster = 2;
     p.cluster = cluster;
     p.cg2 = cg2;

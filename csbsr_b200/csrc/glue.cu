@@ -539,6 +539,43 @@ __global__ void tapexp_scatter_kernel(const __nv_bfloat16* __restrict__ dy, int 
     }
 }
 
+// ------------------------------------------------------------------ input pipeline
+// SplitPatch / JointPatch (model/data/samplers/patch_sampler.py:15-50): an image [C, H, W] <-> its non-overlapping ph x pw
+// patches [(iy * nx + ix), C, ph, pw] (unfold with stride = size; remainders are dropped exactly like Tensor.unfold).
+// join == 0: img -> patches;  join == 1: patches -> img  (B images: patch index b * ny * nx + iy * nx + ix)
+__global__ void patch_split_join_kernel(float* __restrict__ img, float* __restrict__ patches, int B, int C, int H, int W, int ph,
+                                        int pw, int ny, int nx, int join) {
+    const size_t total = static_cast<size_t>(B) * ny * nx * C * ph * pw;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(i % pw);
+        const int y = static_cast<int>((i / pw) % ph);
+        const int c = static_cast<int>((i / (static_cast<size_t>(pw) * ph)) % C);
+        const size_t pidx = i / (static_cast<size_t>(pw) * ph * C);
+        const int ix = static_cast<int>(pidx % nx), iy = static_cast<int>((pidx / nx) % ny);
+        const size_t b = pidx / (static_cast<size_t>(nx) * ny);
+        const size_t io = ((b * C + c) * H + iy * ph + y) * W + ix * pw + x;
+        if (join) img[io] = patches[i]; else patches[i] = img[io];
+    }
+}
+// Training augmentation of CrackDataSet.__getitem__ (crack_dataset.py:42-48 with data_preprocess.py:13-46): ConvertFromInts,
+// RandomMirror, RandomVerticalFlip, RandomCrop, ToTensor, /255 in one pass over a decoded uint8 HWC image.
+// prm[b] = (y0, x0, hflip, vflip) in the coordinates of the FLIPPED image; out fp32 [B, C, th, tw]
+__global__ void crop_flip_u8_kernel(const unsigned char* const* __restrict__ imgs, const int* __restrict__ dims /* [B][3]: H, W, C */,
+                                    const int* __restrict__ prm, float* __restrict__ out, int B, int Cout, int th, int tw, float scale) {
+    const size_t total = static_cast<size_t>(B) * Cout * th * tw;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(i % tw);
+        const int y = static_cast<int>((i / tw) % th);
+        const int c = static_cast<int>((i / (static_cast<size_t>(tw) * th)) % Cout);
+        const int b = static_cast<int>(i / (static_cast<size_t>(tw) * th * Cout));
+        const int H = dims[b * 3], W = dims[b * 3 + 1], C = dims[b * 3 + 2];
+        int sy = prm[b * 4] + y, sx = prm[b * 4 + 1] + x;
+        if (prm[b * 4 + 2]) sx = W - 1 - sx;               // RandomMirror: img[:, ::-1]
+        if (prm[b * 4 + 3]) sy = H - 1 - sy;               // RandomVerticalFlip: img[::-1]
+        out[i] = static_cast<float>(imgs[b][(static_cast<size_t>(sy) * W + sx) * C + min(c, C - 1)]) * scale;
+    }
+}
+
 }  // namespace csbsr
 
 using namespace csbsr;
@@ -740,6 +777,33 @@ extern "C" int csbsr_tapexp_scatter_nhwc(const void* dy, int dy_pitch, void* dz,
     CSBSR_REQUIRE(dy && dz && n > 0 && co >= 1 && co <= cp && 9 * cp <= z_pitch && z_pitch % 8 == 0 && co <= dy_pitch, "tapexp_scatter: bad arguments");
     tapexp_scatter_kernel<<<glue_grid(static_cast<size_t>(n) * h * w * (z_pitch / 8), 256), 256, 0, STREAM(stream)>>>(CBF(dy), dy_pitch, BF(dz),
                                                                                                                   z_pitch, n, h, w, cp, co);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_patch_split(const float* img, float* patches, int b, int c, int h, int w, int ph, int pw, void* stream) {
+    CSBSR_REQUIRE(img && patches && b > 0 && c > 0 && ph > 0 && pw > 0 && ph <= h && pw <= w, "patch_split: bad arguments");
+    const int ny = h / ph, nx = w / pw;
+    const size_t total = static_cast<size_t>(b) * ny * nx * c * ph * pw;
+    patch_split_join_kernel<<<glue_grid(total, 256), 256, 0, STREAM(stream)>>>(const_cast<float*>(img), patches, b, c, h, w, ph, pw, ny, nx, 0);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_patch_join(const float* patches, float* img, int b, int c, int h, int w, int ph, int pw, void* stream) {
+    CSBSR_REQUIRE(img && patches && b > 0 && c > 0 && ph > 0 && pw > 0 && h % ph == 0 && w % pw == 0, "patch_join: the image must be a whole number of patches");
+    const int ny = h / ph, nx = w / pw;
+    const size_t total = static_cast<size_t>(b) * ny * nx * c * ph * pw;
+    patch_split_join_kernel<<<glue_grid(total, 256), 256, 0, STREAM(stream)>>>(img, const_cast<float*>(patches), b, c, h, w, ph, pw, ny, nx, 1);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int csbsr_crop_flip_u8(const unsigned char* const* imgs, const int* dims, const int* params, float* out, int b, int c_out,
+                                  int th, int tw, float scale, void* stream) {
+    CSBSR_REQUIRE(imgs && dims && params && out && b > 0 && c_out > 0 && th > 0 && tw > 0, "crop_flip_u8: bad arguments");
+    const size_t total = static_cast<size_t>(b) * c_out * th * tw;
+    crop_flip_u8_kernel<<<glue_grid(total, 256), 256, 0, STREAM(stream)>>>(imgs, dims, params, out, b, c_out, th, tw, scale);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -77,8 +77,14 @@ __global__ void prelu_bwd_kernel(const uint4* __restrict__ x, const uint4* __res
     if (warp == 0) {
         float v = lane < (blockDim.x >> 5) ? part[lane] : 0.f;
         v = warp_sum(v);
-        if (lane == 0) atomicAdd(dslope, v);
+        if (lane == 0) dslope[blockIdx.x] = v;               // per-block partial; prelu_finalize_kernel adds them in a fixed order
     }
+}
+__global__ void prelu_finalize_kernel(const float* __restrict__ part, int n, float* __restrict__ dslope) {
+    float v = 0.f;
+    for (int i = threadIdx.x; i < n; i += 32) v += part[i];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) *dslope = v;
 }
 
 __global__ void adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
@@ -126,14 +132,17 @@ extern "C" int csbsr_prelu_fwd(const void* x, void* y, const float* slope, long 
     return 0;
 }
 
+extern "C" size_t csbsr_prelu_bwd_workspace_bytes(void) { return sizeof(float) * static_cast<size_t>(num_sms()) * 16; }
+
 extern "C" int csbsr_prelu_bwd(const void* x, const void* dy, void* dx, const float* slope, float* dslope, long long n,
-                               void* stream) {
-    CSBSR_REQUIRE(x && dy && dx && slope && dslope && n > 0 && n % 8 == 0, "prelu_bwd: n must be a positive multiple of 8");
+                               float* workspace, void* stream) {
+    CSBSR_REQUIRE(x && dy && dx && slope && dslope && workspace && n > 0 && n % 8 == 0, "prelu_bwd: n must be a positive multiple of 8");
     const size_t n8 = static_cast<size_t>(n) / 8;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CSBSR_CHECK_CUDA(cudaMemsetAsync(dslope, 0, sizeof(float), st));
-    prelu_bwd_kernel<<<grid_cap(n8, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dy),
-                                                        reinterpret_cast<uint4*>(dx), slope, dslope, n8);
+    const int pblocks = grid_cap(n8, 256);                 // <= num_sms() * 16 partial sums (csbsr_prelu_bwd_workspace_bytes)
+    prelu_bwd_kernel<<<pblocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dy),
+                                              reinterpret_cast<uint4*>(dx), slope, workspace, n8);
+    prelu_finalize_kernel<<<1, 32, 0, st>>>(workspace, pblocks, dslope);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -221,7 +230,16 @@ __global__ void blur_bwd_kernel_kernel(const float* __restrict__ x, const float*
 #pragma unroll 8
             for (int X = 0; X < TILE; ++X) acc = fmaf(dr[X], xr[X * stride], acc);
         }
-        atomicAdd(dk + static_cast<size_t>(b) * ks * ks + t, acc);
+        // partial of this (tile, channel): part[b][tile * C + c][t]; blur_bwd_kernel_finalize_kernel adds them in order
+        dk[((static_cast<size_t>(b) * gridDim.x * C) + static_cast<size_t>(blockIdx.x) * C + c) * ks * ks + t] = acc;
+    }
+}
+__global__ void blur_bwd_kernel_finalize_kernel(const float* __restrict__ part, int nparts, int kk, float* __restrict__ dk) {
+    const int b = blockIdx.x;
+    for (int t = threadIdx.x; t < kk; t += blockDim.x) {
+        float v = 0.f;
+        for (int i = 0; i < nparts; ++i) v += part[(static_cast<size_t>(b) * nparts + i) * kk + t];
+        dk[static_cast<size_t>(b) * kk + t] = v;
     }
 }
 
@@ -286,25 +304,36 @@ extern "C" int csbsr_blur_ps_bwd_input(const float* dy, const float* kvec, float
     return 0;
 }
 
+static int blur_bwd_tiles(int h, int w, int stride) {
+    const int oh = (h - 1) / stride + 1, ow = (w - 1) / stride + 1;
+    const int T = stride == 1 ? 32 : 8;
+    return ((oh + T - 1) / T) * ((ow + T - 1) / T);
+}
+
+extern "C" size_t csbsr_blur_ps_bwd_kernel_workspace_bytes(int b, int c, int h, int w, int ksize, int stride) {
+    return sizeof(float) * static_cast<size_t>(b) * blur_bwd_tiles(h, w, stride) * c * ksize * ksize;
+}
+
 extern "C" int csbsr_blur_ps_bwd_kernel(const float* x, const float* dy, float* dk, int b, int c, int h, int w, int ksize,
-                                        int stride, void* stream) {
-    CSBSR_REQUIRE(x && dy && dk && b > 0 && c > 0 && ksize > 0 && (ksize & 1) && ksize * ksize <= 512 && stride >= 1,
+                                        int stride, float* workspace, void* stream) {
+    CSBSR_REQUIRE(x && dy && dk && workspace && b > 0 && c > 0 && ksize > 0 && (ksize & 1) && ksize * ksize <= 512 && stride >= 1,
                   "blur_ps_bwd_kernel: bad arguments");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int oh = (h - 1) / stride + 1, ow = (w - 1) / stride + 1;
-    CSBSR_CHECK_CUDA(cudaMemsetAsync(dk, 0, sizeof(float) * static_cast<size_t>(b) * ksize * ksize, st));
+    const int tiles = blur_bwd_tiles(h, w, stride);
     if (stride == 1) {
         constexpr int T = 32;
         const int xt = (T - 1) * stride + ksize;
-        dim3 grid(((oh + T - 1) / T) * ((ow + T - 1) / T), c, b);
-        blur_bwd_kernel_kernel<T><<<grid, 512, sizeof(float) * (T * T + xt * xt), st>>>(x, dy, dk, c, h, w, oh, ow, ksize, stride);
+        dim3 grid(tiles, c, b);
+        blur_bwd_kernel_kernel<T><<<grid, 512, sizeof(float) * (T * T + xt * xt), st>>>(x, dy, workspace, c, h, w, oh, ow, ksize, stride);
     } else {
         constexpr int T = 8;
         const int xt = (T - 1) * stride + ksize;
         CSBSR_REQUIRE(sizeof(float) * (T * T + xt * xt) <= 48 * 1024, "blur_ps_bwd_kernel: stride %d too large", stride);
-        dim3 grid(((oh + T - 1) / T) * ((ow + T - 1) / T), c, b);
-        blur_bwd_kernel_kernel<T><<<grid, 512, sizeof(float) * (T * T + xt * xt), st>>>(x, dy, dk, c, h, w, oh, ow, ksize, stride);
+        dim3 grid(tiles, c, b);
+        blur_bwd_kernel_kernel<T><<<grid, 512, sizeof(float) * (T * T + xt * xt), st>>>(x, dy, workspace, c, h, w, oh, ow, ksize, stride);
     }
+    blur_bwd_kernel_finalize_kernel<<<b, 256, 0, st>>>(workspace, tiles * c, ksize * ksize, dk);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -578,7 +607,7 @@ __device__ __forceinline__ void chan_block_reduce(ChanAcc<NS>& a, int grp, int l
         for (int i = threadIdx.x; i < groups * 8; i += blockDim.x) {
             float t = 0.f;
             for (int l = 0; l < lanes; ++l) t += smem[l * groups * 8 + i];
-            atomicAdd(out[s] + i, t);
+            out[s][static_cast<size_t>(blockIdx.x) * groups * 8 + i] = t;      // per-block partial, reduced in block order later
         }
     }
 }
@@ -601,12 +630,18 @@ __global__ void bn_stats_kernel(const uint4* __restrict__ x, int pitch8, int gro
     chan_block_reduce<2>(a, lane_pix < lanes ? grp : groups, lane_pix < lanes ? lane_pix : 0, lanes, groups, bn_sm, outs);
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, long long m, int c, float eps,
-                                   float momentum, float* mean, float* rstd, float* running_mean, float* running_var) {
+__global__ void bn_finalize_kernel(const float* __restrict__ sum_part, const float* __restrict__ sumsq_part, int nblocks, long long m,
+                                   int c, float eps, float momentum, float* mean, float* rstd, float* running_mean,
+                                   float* running_var) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
-    const double mu = static_cast<double>(sum[i]) / m;
-    double var = static_cast<double>(sumsq[i]) / m - mu * mu;
+    double s = 0.0, ss = 0.0;
+    for (int b = 0; b < nblocks; ++b) {                        // fixed order: bit-reproducible statistics
+        s += sum_part[static_cast<size_t>(b) * c + i];
+        ss += sumsq_part[static_cast<size_t>(b) * c + i];
+    }
+    const double mu = s / m;
+    double var = ss / m - mu * mu;
     if (var < 0) var = 0;
     mean[i] = static_cast<float>(mu);
     rstd[i] = static_cast<float>(1.0 / sqrt(var + eps));
@@ -707,6 +742,21 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* _
     }
 }
 
+// dbeta / dgamma = ordered sums of the per-block partials of bn_bwd_reduce_kernel
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int nblocks, int c,
+                                       float* __restrict__ dbeta, float* __restrict__ dgamma) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    float a = 0.f, b2 = 0.f;
+    for (int b = 0; b < nblocks; ++b) {
+        a += p1[static_cast<size_t>(b) * c + i];
+        b2 += p2[static_cast<size_t>(b) * c + i];
+    }
+    dbeta[i] = a;
+    dgamma[i] = b2;
+}
+
+static constexpr int kBnMaxBlocks = 128;
 static int bn_block_cfg(int groups, int& lanes) {      // threads per block: whole number of pixel lanes, <= 256 when possible
     lanes = 256 / groups;
     if (lanes < 1) lanes = 1;
@@ -715,25 +765,27 @@ static int bn_block_cfg(int groups, int& lanes) {      // threads per block: who
 
 }  // namespace csbsr
 
+extern "C" size_t csbsr_bn_workspace_bytes(int c) { return sizeof(float) * 2 * kBnMaxBlocks * static_cast<size_t>(c); }
+
 extern "C" int csbsr_bn_stats(const void* x, int pitch, int c, long long m, float eps, float momentum, float* mean, float* rstd,
                               float* running_mean, float* running_var, float* workspace, void* stream) {
     CSBSR_REQUIRE(x && mean && rstd && workspace && c > 0 && c % 8 == 0 && pitch % 8 == 0 && c <= pitch && c <= 8192 && m > 0,
                   "bn_stats: bad arguments (c=%d pitch=%d)", c, pitch);
     CSBSR_REQUIRE(!running_mean == !running_var, "bn_stats: running_mean and running_var go together");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    float* sum = workspace;
-    float* sumsq = workspace + c;
-    CSBSR_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * 2 * c, st));
+    float* sum = workspace;                                     // [blocks][c] partial sums, then [blocks][c] partial sums of squares
+    float* sumsq = workspace + static_cast<size_t>(kBnMaxBlocks) * c;
     const int groups = c / 8;
     int lanes;
     const int threads = bn_block_cfg(groups, lanes);
     CSBSR_REQUIRE(threads <= 1024, "bn_stats: too many channels");
     long long blocks = (m + lanes * 64 - 1) / (static_cast<long long>(lanes) * 64);
-    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    if (blocks > kBnMaxBlocks) blocks = kBnMaxBlocks;
     if (blocks < 1) blocks = 1;
     bn_stats_kernel<<<static_cast<int>(blocks), threads, sizeof(float) * lanes * groups * 8, st>>>(
         reinterpret_cast<const uint4*>(x), pitch / 8, groups, m, sum, sumsq);
-    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sum, sumsq, m, c, eps, momentum, mean, rstd, running_mean, running_var);
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sum, sumsq, static_cast<int>(blocks), m, c, eps, momentum, mean, rstd,
+                                                       running_mean, running_var);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -752,22 +804,23 @@ extern "C" int csbsr_bn_apply(const void* x, const void* res, void* y, const flo
 
 extern "C" int csbsr_bn_backward(const void* dy, const void* x, const void* y_relu, const float* mean, const float* rstd,
                                  const float* gamma, int pitch, int c, long long m, int training, void* dx, void* dres,
-                                 float* dgamma, float* dbeta, void* stream) {
-    CSBSR_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && c > 0 && c % 8 == 0 && pitch % 8 == 0 &&
+                                 float* dgamma, float* dbeta, float* workspace, void* stream) {
+    CSBSR_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace && c > 0 && c % 8 == 0 && pitch % 8 == 0 &&
                       c <= pitch && c <= 8192 && m > 0, "bn_backward: bad arguments");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CSBSR_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * c, st));
-    CSBSR_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * c, st));
+    float* p1 = workspace;
+    float* p2 = workspace + static_cast<size_t>(kBnMaxBlocks) * c;
     const int groups = c / 8;
     int lanes;
     const int threads = bn_block_cfg(groups, lanes);
     CSBSR_REQUIRE(threads <= 1024, "bn_backward: too many channels");
     long long blocks = (m + lanes * 64 - 1) / (static_cast<long long>(lanes) * 64);
-    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    if (blocks > kBnMaxBlocks) blocks = kBnMaxBlocks;
     if (blocks < 1) blocks = 1;
     bn_bwd_reduce_kernel<<<static_cast<int>(blocks), threads, sizeof(float) * lanes * groups * 8, st>>>(
         reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(y_relu), mean, rstd,
-        pitch / 8, groups, m, dbeta, dgamma);
+        pitch / 8, groups, m, p1, p2);
+    bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(p1, p2, static_cast<int>(blocks), c, dbeta, dgamma);
     const long long total = m * (pitch / 8);
     bn_bwd_apply_kernel<<<grid_cap(static_cast<size_t>(total), 256), 256, 0, st>>>(
         reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(y_relu), mean, rstd,

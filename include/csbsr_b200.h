@@ -126,7 +126,9 @@ int csbsr_conv_wgrad(const csbsr_wgrad_desc* d, void* stream);
  *   from 1 (bias corrections), zero_grad != 0 clears g for the next step (train.py:91; trainer.py:61,70).
  * ------------------------------------------------------------------------------------------- */
 int csbsr_prelu_fwd(const void* x, void* y, const float* slope, long long n, void* stream);
-int csbsr_prelu_bwd(const void* x, const void* dy, void* dx, const float* slope, float* dslope, long long n, void* stream);
+size_t csbsr_prelu_bwd_workspace_bytes(void);   /* per-block partials of the slope gradient, summed in a fixed order */
+int csbsr_prelu_bwd(const void* x, const void* dy, void* dx, const float* slope, float* dslope, long long n, float* workspace,
+                    void* stream);
 int csbsr_adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                     int step, float grad_scale, int zero_grad, void* stream);
 
@@ -137,8 +139,9 @@ int csbsr_adam_step(float* p, float* g, float* m, float* v, long long n, float l
  *   csbsr_resize_bicubic_aa_bwd: dx[nc,h,w] from dy[nc,oh,ow] (transpose of the normalised antialiased taps) */
 int csbsr_blur_ps_bwd_input(const float* dy, const float* kvec, float* dx, int b, int c, int h, int w, int ksize, int stride,
                             void* stream);
+size_t csbsr_blur_ps_bwd_kernel_workspace_bytes(int b, int c, int h, int w, int ksize, int stride);
 int csbsr_blur_ps_bwd_kernel(const float* x, const float* dy, float* dk, int b, int c, int h, int w, int ksize, int stride,
-                             void* stream);
+                             float* workspace, void* stream);
 int csbsr_resize_bicubic_aa_bwd(const float* dy, float* dx, int nc, int h, int w, int oh, int ow, void* stream);
 
 /* fp32 parameter [A][B][R][S] -> packed bf16 conv operand [R*S][rows_pad][cols_pad] (zero padding) in one launch.
@@ -168,17 +171,20 @@ int csbsr_wgrad_unpack_add_tapexp(const float* wg, float* grad, int a, int b, in
 /* BatchNorm2d of the training graph on NHWC bf16 maps [m][pitch] whose first c channels are real (nn.BatchNorm2d in
  * pspnet_pytorch/extractors.py:52-70, pspnet.py:44-57, hrnet_backbone.py; reference runs them through cuDNN / aten).
  *   csbsr_bn_stats   : batch mean / rstd (biased variance, eps) into mean[c] / rstd[c]; updates running_mean / running_var with
- *                      `momentum` and the unbiased variance when they are given; workspace = 2*c floats.
+ *                      `momentum` and the unbiased variance when they are given.
+ *   workspace (both reductions): csbsr_bn_workspace_bytes(c) bytes of per-block partial sums, added in block order --
+ *                      statistics and dgamma / dbeta are bit-reproducible (no atomics).
  *   csbsr_bn_apply   : y = relu?((x - mean) * rstd * gamma + beta + res?)   (res may be NULL; padding channels written as 0)
  *   csbsr_bn_backward: dy -> dx (+ dres = dy masked by y_relu > 0 when y_relu is given), dgamma[c], dbeta[c] (overwritten);
  *                      training != 0 subtracts the batch-statistics terms, 0 treats mean / rstd as constants (eval mode). */
+size_t csbsr_bn_workspace_bytes(int c);
 int csbsr_bn_stats(const void* x, int pitch, int c, long long m, float eps, float momentum, float* mean, float* rstd,
                    float* running_mean, float* running_var, float* workspace, void* stream);
 int csbsr_bn_apply(const void* x, const void* res, void* y, const float* mean, const float* rstd, const float* gamma,
                    const float* beta, int pitch, int c, long long m, int relu, void* stream);
 int csbsr_bn_backward(const void* dy, const void* x, const void* y_relu, const float* mean, const float* rstd, const float* gamma,
                       int pitch, int c, long long m, int training, void* dx, void* dres, float* dgamma, float* dbeta,
-                      void* stream);
+                      float* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound support kernels (csrc/support.cu).  NHWC tensors are bf16 with `*_pitch` channels per
@@ -339,6 +345,15 @@ int csbsr_instnorm_bwd(const float* dy, const float* x, const float* mean, const
  * taps; its backward scatters dy back to the tap-expanded layout, so dgrad and wgrad are 1x1 GEMMs too (9x fewer MMAs) */
 int csbsr_tapexp_gather_nhwc(const void* z, int z_pitch, void* y, int y_pitch, int n, int h, int w, int cp, int co, void* stream);
 int csbsr_tapexp_scatter_nhwc(const void* dy, int dy_pitch, void* dz, int z_pitch, int n, int h, int w, int cp, int co, void* stream);
+/* Input pipeline.  SplitPatch / JointPatch (model/data/samplers/patch_sampler.py:15-50): fp32 images [b, c, h, w] <-> their
+ * non-overlapping ph x pw patches [b * (h/ph) * (w/pw), c, ph, pw] (unfold with stride = size: remainders dropped on split) */
+int csbsr_patch_split(const float* img, float* patches, int b, int c, int h, int w, int ph, int pw, void* stream);
+int csbsr_patch_join(const float* patches, float* img, int b, int c, int h, int w, int ph, int pw, void* stream);
+/* CrackDataSet.__getitem__ augmentation (crack_dataset.py:42-48, data_preprocess.py:13-46; RandomMirror / RandomVerticalFlip /
+ * RandomCrop / ToTensor / 255) on decoded uint8 HWC images resident on the device: imgs[b] -> image b, dims[b] = (H, W, C),
+ * params[b] = (y0, x0, hflip, vflip) drawn by the caller; out fp32 [b, c_out, th, tw] = pixel * scale (c >= C repeats the last) */
+int csbsr_crop_flip_u8(const unsigned char* const* imgs, const int* dims, const int* params, float* out, int b, int c_out, int th,
+                       int tw, float scale, void* stream);
 /* NHWC bf16 window -> fp32 NCHW (the first c channels): images / logits leaving the networks */
 int csbsr_nhwc_bf16_to_nchw_f32(const void* x, float* y, int n, long long hw, int c, int x_pitch, int x_coff, void* stream);
 

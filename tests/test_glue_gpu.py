@@ -189,3 +189,41 @@ def test_tap_expanded_conv3x3_fwd_bwd(ci, h, w):
     yr.backward(up)
     _close(x.grad, xr.grad, 1e-2, "tapexp dx")
     _close(w_.grad, wr.grad, 1e-2, "tapexp dw")
+
+
+def test_patch_split_join_and_crop_flip_vs_oracle(tmp_path):
+    """Input pipeline kernels (SplitPatch / JointPatch, crop + flips) bit-equal to the oracle restatement of the reference's
+    host code (oracle/patch_ref.py, pinned to model/data/samplers/patch_sampler.py on CPU)."""
+    from csbsr_b200.data import augment as AU
+    from csbsr_b200.data.samplers.patch_sampler import JointPatch, SplitPatch
+    from csbsr_b200.utils import save_output as SO
+    from oracle import patch_ref as PR
+    g = torch.Generator().manual_seed(31)
+    x = torch.rand(3, 224, 336, generator=g)
+    patches, shape = SplitPatch(7, 3, 112, 112)(x)
+    p_ref, s_ref = PR.split_patch(x, 7, 3, 112, 112)
+    assert torch.equal(patches.cpu(), p_ref) and list(shape) == list(s_ref)
+    seg = torch.rand(2 * 6, 1, 448, 448, generator=g)                  # two images' x4 segmentation outputs
+    sh = shape.copy(); sh[[5, 6]] = sh[[5, 6]] * 4; sh[[1, 4]] = 1
+    assert torch.equal(JointPatch()(seg, sh).cpu(), PR.joint_patch(seg, sh))
+    rng = np.random.default_rng(5)
+    imgs = [(rng.random((300 + 7 * i, 280 + 5 * i, 3)) * 255).astype(np.uint8) for i in range(4)]
+    masks = [(rng.random(im.shape[:2]) > 0.5).astype(np.uint8) * 255 for im in imgs]
+    prm = AU.draw_params([im.shape[:2] for im in imgs], (224, 224), np.random.default_rng(9))
+    out = AU.crop_flip_batch(imgs, prm, (224, 224)).cpu()
+    outm = AU.crop_flip_batch(masks, prm, (224, 224)).cpu()
+    for i, (im, mk) in enumerate(zip(imgs, masks)):
+        y0, x0, hf, vf = [int(v) for v in prm[i]]
+        assert torch.equal(out[i], PR.crop_flip(im, y0, x0, hf, vf, 224, 224))
+        assert torch.equal(outm[i], PR.crop_flip(mk, y0, x0, hf, vf, 224, 224))
+    assert prm[:, 2].max() == 1 or prm[:, 3].max() == 1                # some flip drawn with this seed
+
+    class A:
+        output_dirname = str(tmp_path)
+    SO.save_img(str(tmp_path), out[:2], ["a.png", "b.png"])
+    SO.save_mask(A, outm[:2], ["a.png", "b.png"], 0.5)
+    SO.save_kernel(A, torch.rand(2, 1, 21, 21), ["a.png", "b.png"], 2)
+    from PIL import Image
+    back = np.asarray(Image.open(tmp_path / "images" / "a.png"))
+    assert back.shape == (224, 224, 3) and np.array_equal(back, (out[0] * 255).byte().permute(1, 2, 0).numpy())
+    assert (tmp_path / "masks" / "th_0.50" / "b.png").exists() and (tmp_path / "kernels_origin" / "b_0_origin.png").exists()

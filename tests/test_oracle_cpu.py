@@ -387,3 +387,30 @@ def test_philox4x32_known_answers():
     p = D.philox_params(1000, seed=7)
     assert p.shape == (1000, 3) and (p[:, 0] >= 0).all() and (p[:, 0] < np.pi).all()
     assert (p[:, 1:] >= 0.2).all() and (p[:, 1:] < 4.0).all() and abs(p[:, 1:].mean() - 2.1) < 0.1
+
+
+def test_patch_oracle_matches_reference():
+    """oracle/patch_ref.py against the unmodified SplitPatch / JointPatch (model/data/samplers/patch_sampler.py:15-50) when the
+    reference tree is importable (build container), and against a literal round-trip property everywhere."""
+    from oracle import patch_ref as PR
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(3, 24, 40, generator=g)
+    patches, shape = PR.split_patch(x, 5, 3, 8, 10)
+    assert patches.shape == (12, 3, 8, 10) and list(shape) == [5, 1, 3, 4, 3, 8, 10]
+    assert torch.equal(patches[5], x[:, 8:16, 10:20])                    # patch (iy=1, ix=1)
+    back = PR.joint_patch(patches, shape)
+    assert torch.equal(back[0], x)
+    up = torch.rand(12, 1, 32, 40, generator=g)                          # x4 outputs with one channel (segmentation)
+    sh2 = shape.copy(); sh2[[5, 6]] = sh2[[5, 6]] * 4; sh2[[1, 4]] = 1
+    j = PR.joint_patch(up, sh2)
+    assert j.shape == (1, 1, 96, 160) and torch.equal(j[0, :, 32:64, 40:80], up[5])
+    from oracle import ref_harness as rh
+    if rh.available():
+        rh.setup()
+        from model.data.samplers.patch_sampler import JointPatch, SplitPatch
+        p_ref, s_ref = SplitPatch(5, 3, 8, 10)(x)
+        assert torch.equal(p_ref, patches) and list(s_ref) == list(shape)
+        assert torch.equal(JointPatch()(up, sh2), j)
+    img = (torch.rand(30, 36, 3, generator=g) * 255).to(torch.uint8).numpy()
+    out = PR.crop_flip(img, 4, 6, True, False, 16, 20)
+    assert out.shape == (3, 16, 20) and abs(float(out[1, 0, 0]) - img[4, 36 - 1 - 6, 1] / 255) < 1e-7
