@@ -561,7 +561,7 @@ __global__ void patch_split_join_kernel(float* __restrict__ img, float* __restri
 // RandomMirror, RandomVerticalFlip, RandomCrop, ToTensor, /255 in one pass over a decoded uint8 HWC image.
 // prm[b] = (y0, x0, hflip, vflip) in the coordinates of the FLIPPED image; out fp32 [B, C, th, tw]
 __global__ void crop_flip_u8_kernel(const unsigned char* const* __restrict__ imgs, const int* __restrict__ dims /* [B][3]: H, W, C */,
-                                    const int* __restrict__ prm, float* __restrict__ out, int B, int Cout, int th, int tw, float scale) {
+                                    const int* __restrict__ prm, float* __restrict__ out, int B, int Cout, int th, int tw, float divisor) {
     const size_t total = static_cast<size_t>(B) * Cout * th * tw;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int x = static_cast<int>(i % tw);
@@ -572,7 +572,7 @@ __global__ void crop_flip_u8_kernel(const unsigned char* const* __restrict__ img
         int sy = prm[b * 4] + y, sx = prm[b * 4 + 1] + x;
         if (prm[b * 4 + 2]) sx = W - 1 - sx;               // RandomMirror: img[:, ::-1]
         if (prm[b * 4 + 3]) sy = H - 1 - sy;               // RandomVerticalFlip: img[::-1]
-        out[i] = static_cast<float>(imgs[b][(static_cast<size_t>(sy) * W + sx) * C + min(c, C - 1)]) * scale;
+        out[i] = static_cast<float>(imgs[b][(static_cast<size_t>(sy) * W + sx) * C + min(c, C - 1)]) / divisor;   // true division: bit-equal to `x / 255`
     }
 }
 
@@ -800,10 +800,11 @@ extern "C" int csbsr_patch_join(const float* patches, float* img, int b, int c, 
 }
 
 extern "C" int csbsr_crop_flip_u8(const unsigned char* const* imgs, const int* dims, const int* params, float* out, int b, int c_out,
-                                  int th, int tw, float scale, void* stream) {
+                                  int th, int tw, float divisor, void* stream) {
     CSBSR_REQUIRE(imgs && dims && params && out && b > 0 && c_out > 0 && th > 0 && tw > 0, "crop_flip_u8: bad arguments");
+    CSBSR_REQUIRE(divisor != 0.f, "crop_flip_u8: zero divisor");
     const size_t total = static_cast<size_t>(b) * c_out * th * tw;
-    crop_flip_u8_kernel<<<glue_grid(total, 256), 256, 0, STREAM(stream)>>>(imgs, dims, params, out, b, c_out, th, tw, scale);
+    crop_flip_u8_kernel<<<glue_grid(total, 256), 256, 0, STREAM(stream)>>>(imgs, dims, params, out, b, c_out, th, tw, divisor);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -39,20 +39,36 @@ __global__ void quantize_hist_kernel(const float* __restrict__ prob, const float
     __syncthreads();
     const float* pp = prob + static_cast<size_t>(b) * HW;
     const float* mp = mask + static_cast<size_t>(b) * HW;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-        const float p = pp[i];
+    auto one = [&](float p, float m, unsigned int& qv, unsigned int& gv) {
         // count thresholds strictly below p: thresholds are increasing -> binary search for the first t >= p
         int lo = 0, hi = kNumThr;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (p > sthr[mid]) lo = mid + 1; else hi = mid;
         }
-        const float m = mp[i];
         const int t_iou = m > 0.5f ? 1 : 0;              // IoU binarisation (estimate_metrics.py:79-80)
         const int t_hd = m != 0.f ? 1 : 0;               // astype(bool) (inference.py:305)
-        q[static_cast<size_t>(b) * HW + i] = static_cast<unsigned char>(lo);
-        gt[static_cast<size_t>(b) * HW + i] = static_cast<unsigned char>(t_iou | (t_hd << 1));
+        qv = static_cast<unsigned int>(lo);
+        gv = static_cast<unsigned int>(t_iou | (t_hd << 1));
         atomicAdd(&sh[t_iou][lo], 1);
+    };
+    if ((HW & 3) == 0 && ((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(mp)) & 15) == 0) {
+        // 128-bit loads of four probabilities / mask values, one 32-bit store of the four quantised bytes
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4; i += gridDim.x * blockDim.x) {
+            const float4 p4 = reinterpret_cast<const float4*>(pp)[i];
+            const float4 m4 = reinterpret_cast<const float4*>(mp)[i];
+            unsigned int qv[4], gv[4];
+            one(p4.x, m4.x, qv[0], gv[0]); one(p4.y, m4.y, qv[1], gv[1]); one(p4.z, m4.z, qv[2], gv[2]); one(p4.w, m4.w, qv[3], gv[3]);
+            reinterpret_cast<unsigned int*>(q + static_cast<size_t>(b) * HW)[i] = qv[0] | (qv[1] << 8) | (qv[2] << 16) | (qv[3] << 24);
+            reinterpret_cast<unsigned int*>(gt + static_cast<size_t>(b) * HW)[i] = gv[0] | (gv[1] << 8) | (gv[2] << 16) | (gv[3] << 24);
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+            unsigned int qv, gv;
+            one(pp[i], mp[i], qv, gv);
+            q[static_cast<size_t>(b) * HW + i] = static_cast<unsigned char>(qv);
+            gt[static_cast<size_t>(b) * HW + i] = static_cast<unsigned char>(gv);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 200; i += blockDim.x) {
@@ -100,8 +116,10 @@ __global__ void corner_kernel(const unsigned char* __restrict__ q, const unsigne
         const int a = pix(qb, y - 1, x - 1, H, W), bb = pix(qb, y - 1, x, H, W), c = pix(qb, y, x - 1, H, W),
                   d = pix(qb, y, x, H, W);
         const size_t o = static_cast<size_t>(b) * Hc * Wc + i;
-        qlo[o] = static_cast<unsigned char>(min(min(a, bb), min(c, d)));
-        qhi[o] = static_cast<unsigned char>(max(max(a, bb), max(c, d)));
+        if (qlo) {                                   // only the unfused (large-image) path keeps the per-corner range
+            qlo[o] = static_cast<unsigned char>(min(min(a, bb), min(c, d)));
+            qhi[o] = static_cast<unsigned char>(max(max(a, bb), max(c, d)));
+        }
         const int ga = (pix(gb, y - 1, x - 1, H, W) >> 1) & 1, gbb = (pix(gb, y - 1, x, H, W) >> 1) & 1,
                   gc = (pix(gb, y, x - 1, H, W) >> 1) & 1, gd = (pix(gb, y, x, H, W) >> 1) & 1;
         cg[o] = static_cast<unsigned char>(8 * ga + 4 * gbb + 2 * gc + gd);
@@ -543,6 +561,234 @@ __global__ void sort_replay_global_kernel(unsigned int* __restrict__ keys_g2p, u
     if (threadIdx.x == 0) replay_list(sk, n, pct, res + (static_cast<size_t>(bt) * 2 + dir) * 2);
 }
 
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int pow2_at_least(int v) { int m = 1; while (m < v) m <<= 1; return m; }
+
+// ------------------------------------------------------------------ fused per-(image, threshold) HD / MSD
+// One persistent CTA per SM takes (image, threshold) items from a global counter and keeps everything of the item on chip:
+//   1. the prediction-border corners of the threshold as a row-packed BIT MASK in shared memory ((H+1) x ceil((W+1)/32)
+//      words, 27 KB at 448^2), built with warp ballots straight from the quantised map q;
+//   2. distances_gt_to_pred: for every gt border corner an exact nearest-set-bit search in the mask (rows expanding from
+//      the corner, clz / ffs inside the row words, early exit when dy^2 >= best) -- no per-threshold column-distance map;
+//   3. distances_pred_to_gt: every set bit looks its squared distance up in the per-image gt EDT map d2g;
+//   4. both key lists are sorted in shared memory (bitonic, <= 32768 keys) and replayed in numpy's floating-point order;
+//      longer lists spill to a per-CTA global scratch area (one region per resident CTA, not per image).
+// This replaces column_scan<1> / g2p_keys / p2g_keys / sort_replay<*> / finalize and their 260 MB-per-image workspace
+// (99 x 449^2 uint16 column distances + 2 x 99 key lists per image).
+constexpr int kFusedThreads = 1024;
+constexpr int kFusedCap = 32768;                            // keys held in shared memory
+constexpr int kFusedLeaves = kFusedCap / 64 + 2;
+
+struct FusedArgs {
+    const unsigned char* q;
+    const unsigned char* cg;
+    const unsigned int* d2g;
+    const int* gt_list;
+    const int* count_gt;
+    int H, W, total_items;
+    double pct, max_img_len;
+    double* hd;
+    double* msd;
+    unsigned int* scratch;                                  // [gridDim.x][scratch_cap]
+    int scratch_cap;                                        // power of two >= (H+1)*(W+1)
+    int* counter;
+    int force_seq;
+};
+
+// distance from x to the nearest set bit of a row of the mask, or a value > maxdx when there is none within maxdx
+__device__ __forceinline__ int row_nearest(const unsigned int* __restrict__ row, int x, int WW, int maxdx) {
+    const int w0 = x >> 5, o = x & 31;
+    const unsigned int word = row[w0];
+    int best = 0x3FFFFFFF;
+    const unsigned int ml = word & (0xFFFFFFFFu >> (31 - o));          // bits at or left of x
+    if (ml) best = o - (31 - __clz(ml));
+    const unsigned int mr = word & (0xFFFFFFFFu << o);                 // bits at or right of x
+    if (mr) best = min(best, __ffs(mr) - 1 - o);
+    const int lim = min(best - 1, maxdx);                              // only strictly better candidates matter
+    for (int wl = w0 - 1; wl >= 0; --wl) {
+        const int dmin = o + 1 + 32 * (w0 - 1 - wl);                    // distance to the closest position of word wl
+        if (dmin > lim) break;
+        const unsigned int v = row[wl];
+        if (v) { best = min(best, dmin + __clz(v)); break; }
+    }
+    const int lim2 = min(best - 1, maxdx);
+    for (int wr = w0 + 1; wr < WW; ++wr) {
+        const int dmin = (32 - o) + 32 * (wr - w0 - 1);
+        if (dmin > lim2) break;
+        const unsigned int v = row[wr];
+        if (v) { best = min(best, dmin + __ffs(v) - 1); break; }
+    }
+    return best;
+}
+
+// exact squared Euclidean distance from corner (y, x) to the nearest set bit of the mask (at least one bit is set)
+__device__ __forceinline__ unsigned int mask_nearest_d2(const unsigned int* __restrict__ bits, int y, int x, int Hc, int WW) {
+    unsigned int best = kInfD2;
+    for (int dy = 0; dy < Hc; ++dy) {
+        const unsigned int dd = static_cast<unsigned int>(dy) * dy;
+        if (dd >= best) break;
+        const int up = y - dy, dn = y + dy;
+        if (up < 0 && dn >= Hc) break;
+        // |dx| that can still improve: dx^2 < best - dd
+        const int maxdx = best == kInfD2 ? 0x3FFFFFF : static_cast<int>(sqrtf(static_cast<float>(best - dd))) + 1;
+        if (up >= 0) {
+            const int dx = row_nearest(bits + static_cast<size_t>(up) * WW, x, WW, maxdx);
+            if (dx < 0x3FFFFFF) best = min(best, dd + static_cast<unsigned int>(dx) * dx);
+        }
+        if (dy > 0 && dn < Hc) {
+            const int dx = row_nearest(bits + static_cast<size_t>(dn) * WW, x, WW, maxdx);
+            if (dx < 0x3FFFFFF) best = min(best, dd + static_cast<unsigned int>(dx) * dx);
+        }
+    }
+    return best;
+}
+
+// block-wide bitonic sort of keys[0..n) (keys[n..m) padded with 0xFFFFFFFF, m = next power of two <= capacity)
+__device__ void block_bitonic(unsigned int* keys, int n) {
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int i = n + threadIdx.x; i < m; i += blockDim.x) keys[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned int a = keys[i], c = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > c) == up) { keys[i] = c; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1) hd_fused_kernel(const FusedArgs a) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    const int Hc = a.H + 1, Wc = a.W + 1, WW = (Wc + 31) / 32, NC = Hc * Wc;
+    unsigned int* bits = reinterpret_cast<unsigned int*>(fsm);
+    unsigned int* skeys = bits + ((Hc * WW + 3) & ~3);
+    unsigned char* aux_base = reinterpret_cast<unsigned char*>(skeys + kFusedCap);
+    __shared__ int s_item, s_np, s_cnt;
+    __shared__ double s_res[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFusedThreads / 32;
+    unsigned int* gkeys = a.scratch + static_cast<size_t>(blockIdx.x) * a.scratch_cap;
+
+    auto make_aux = [&](unsigned char* base, int max_leaves) {
+        ReplayAux ax;
+        ax.leaf_l = reinterpret_cast<double*>(base);
+        ax.leaf_w = ax.leaf_l + max_leaves;
+        ax.dres = ax.leaf_w + max_leaves;
+        ax.leaf_start = reinterpret_cast<int*>(ax.dres + 2);
+        ax.leaf_n = ax.leaf_start + max_leaves;
+        ax.cnt = ax.leaf_n + max_leaves;
+        ax.misc = ax.cnt + 3 * kFusedThreads;
+        return ax;
+    };
+    // sort + replay of the list that was just written to `keys` (shared or this CTA's global scratch)
+    auto sort_replay = [&](unsigned int* keys, int n, bool in_smem, double* out) {
+        block_bitonic(keys, n);
+        if (a.force_seq) {
+            if (tid == 0) replay_list(keys, n, a.pct, out);
+        } else if (in_smem) {
+            replay_parallel(keys, n, a.pct, out, make_aux(aux_base, kFusedLeaves));
+        } else {                                              // long list: the key area of shared memory is free for the leaves
+            replay_parallel(keys, n, a.pct, out, make_aux(reinterpret_cast<unsigned char*>(skeys), a.scratch_cap / 64 + 2));
+        }
+        __syncthreads();
+    };
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_item = atomicAdd(a.counter, 1); s_np = 0; s_cnt = 0; }
+        __syncthreads();
+        const int item = s_item;
+        if (item >= a.total_items) break;
+        const int b = item / kNumThr, t = item % kNumThr + 1;
+        const int ng = a.count_gt[b];
+        const unsigned char* qb = a.q + static_cast<size_t>(b) * a.H * a.W;
+        // ---- 1. border mask of threshold t: corner (y, x) is a border iff min < t <= max over its 2x2 pixel block
+        int local_np = 0;
+        for (int widx = warp; widx < Hc * WW; widx += nwarps) {
+            const int y = widx / WW, x = (widx - y * WW) * 32 + lane;
+            bool bit = false;
+            if (x < Wc) {
+                const int p00 = pix(qb, y - 1, x - 1, a.H, a.W), p01 = pix(qb, y - 1, x, a.H, a.W), p10 = pix(qb, y, x - 1, a.H, a.W),
+                          p11 = pix(qb, y, x, a.H, a.W);
+                const int lo = min(min(p00, p01), min(p10, p11)), hi = max(max(p00, p01), max(p10, p11));
+                bit = lo < t && t <= hi;
+            }
+            const unsigned int word = __ballot_sync(0xFFFFFFFFu, bit);
+            if (lane == 0) { bits[widx] = word; local_np += __popc(word); }
+        }
+        if (lane == 0 && local_np) atomicAdd(&s_np, local_np);
+        __syncthreads();
+        const int np_ = s_np;
+        if (ng == 0 || np_ == 0) {                            // empty-mask branches (inference.py:315-321)
+            if (tid == 0) {
+                const double v = (ng == 0 && np_ == 0) ? 0.0 : a.max_img_len;
+                a.hd[item] = v;
+                a.msd[item] = v;
+            }
+            continue;
+        }
+        // ---- 2. distances_gt_to_pred
+        {
+            const bool in_smem = ng <= kFusedCap;
+            unsigned int* keys = in_smem ? skeys : gkeys;
+            const int* list = a.gt_list + static_cast<size_t>(b) * NC;
+            const unsigned char* cgb = a.cg + static_cast<size_t>(b) * NC;
+            for (int k = tid; k < ng; k += kFusedThreads) {
+                const int i = list[k];
+                const int y = i / Wc, x = i - y * Wc;
+                keys[k] = (mask_nearest_d2(bits, y, x, Hc, WW) << 2) | len_class(cgb[i]);
+            }
+            __syncthreads();
+            sort_replay(keys, ng, in_smem, &s_res[0]);
+        }
+        // ---- 3. distances_pred_to_gt
+        {
+            const bool in_smem = np_ <= kFusedCap;
+            unsigned int* keys = in_smem ? skeys : gkeys;
+            const unsigned int* d2b = a.d2g + static_cast<size_t>(b) * NC;
+            for (int widx = warp; widx < Hc * WW; widx += nwarps) {
+                const unsigned int word = bits[widx];
+                if (word == 0) continue;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_cnt, __popc(word));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if ((word >> lane) & 1u) {
+                    const int y = widx / WW, x = (widx - y * WW) * 32 + lane;
+                    const int p00 = pix(qb, y - 1, x - 1, a.H, a.W), p01 = pix(qb, y - 1, x, a.H, a.W), p10 = pix(qb, y, x - 1, a.H, a.W),
+                              p11 = pix(qb, y, x, a.H, a.W);
+                    const int code = ((p00 >= t) << 3) | ((p01 >= t) << 2) | ((p10 >= t) << 1) | (p11 >= t);
+                    keys[base + __popc(word & ((1u << lane) - 1u))] = (d2b[y * Wc + x] << 2) | len_class(code);
+                }
+            }
+            __syncthreads();
+            sort_replay(keys, np_, in_smem, &s_res[2]);
+        }
+        if (tid == 0) {
+            a.hd[item] = fmax(s_res[0], s_res[2]);             // compute_robust_hausdorff: max of the two directions
+            a.msd[item] = (s_res[1] + s_res[3]) / 2;            // inference.py:327-334
+        }
+    }
+}
+
+static size_t fused_smem_bytes(int h, int w) {
+    const int Hc = h + 1, WW = (w + 1 + 31) / 32;
+    const size_t bits = static_cast<size_t>((Hc * WW + 3) & ~3) * 4;
+    const size_t aux = static_cast<size_t>(kFusedLeaves) * (8 + 8 + 4 + 4) + 16 + 3 * kFusedThreads * 4 + 64;
+    return bits + static_cast<size_t>(kFusedCap) * 4 + aux;
+}
+static bool fused_ok(int h, int w) {
+    // the long-list replay borrows the key area for its leaf tables: (cap / 64 + 2) * 24 B + counters must fit into it
+    const size_t cap = static_cast<size_t>(pow2_at_least((h + 1) * (w + 1)));
+    const size_t long_aux = (cap / 64 + 2) * 24 + 16 + 3 * kFusedThreads * 4 + 64;
+    return !getenv("CSBSR_METRICS_UNFUSED") && fused_smem_bytes(h, w) <= 200 * 1024 && long_aux <= static_cast<size_t>(kFusedCap) * 4;
+}
+
 // combine the two directions and resolve the empty-mask branches (inference.py:315-334)
 __global__ void finalize_kernel(const int* __restrict__ count_gt, const int* __restrict__ count_pred,
                                 const double* __restrict__ res, double* __restrict__ hd, double* __restrict__ msd,
@@ -564,8 +810,6 @@ __global__ void finalize_kernel(const int* __restrict__ count_gt, const int* __r
     }
 }
 
-static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-static inline int pow2_at_least(int v) { int m = 1; while (m < v) m <<= 1; return m; }
 
 struct MetricsWs {
     unsigned char *q, *gt, *qlo, *qhi, *cg;
@@ -573,7 +817,10 @@ struct MetricsWs {
     unsigned short *gcol_g, *gcol_t;
     unsigned int *d2g, *keys_g2p, *keys_p2g;
     double* res;
-    int cap;
+    unsigned int* scratch;       // fused path: [ctas][cap] spill area of the long key lists
+    int* counter;                // fused path: work-item counter
+    int cap, ctas;
+    bool fused;
     size_t total;
 };
 
@@ -586,7 +833,24 @@ static MetricsWs carve(void* base, int b, int h, int w, bool with_hd) {
     m.gt = static_cast<unsigned char*>(take(b * HW));
     m.hist = static_cast<int*>(take(sizeof(int) * b * 200));
     m.cap = pow2_at_least(static_cast<int>(NC));
-    if (with_hd) {
+    m.fused = with_hd && fused_ok(h, w);
+    m.ctas = num_sms();
+    if (m.fused) {
+        // per image: q, gt, cg (1 B / pixel or corner), gt border list, gt column distances + EDT map; per resident CTA: one
+        // spill region for key lists longer than 32768 -- ~2.9 MB per 448^2 image + 155 MB per device instead of 260 MB per image
+        m.qlo = m.qhi = nullptr;
+        m.cg = static_cast<unsigned char*>(take(b * NC));
+        m.gt_list = static_cast<int*>(take(sizeof(int) * b * NC));
+        m.count_gt = static_cast<int*>(take(sizeof(int) * b));
+        m.count_pred = nullptr;
+        m.gcol_g = static_cast<unsigned short*>(take(sizeof(short) * b * NC));
+        m.d2g = static_cast<unsigned int*>(take(sizeof(int) * b * NC));
+        m.gcol_t = nullptr;
+        m.keys_g2p = m.keys_p2g = nullptr;
+        m.res = nullptr;
+        m.scratch = static_cast<unsigned int*>(take(sizeof(int) * static_cast<size_t>(m.ctas) * m.cap));
+        m.counter = static_cast<int*>(take(sizeof(int)));
+    } else if (with_hd) {
         m.qlo = static_cast<unsigned char*>(take(b * NC));
         m.qhi = static_cast<unsigned char*>(take(b * NC));
         m.cg = static_cast<unsigned char*>(take(b * NC));
@@ -632,7 +896,30 @@ extern "C" int csbsr_seg_metrics(const float* prob, const float* mask, const flo
         quantize_hist_kernel<<<grid, 256, 0, stream>>>(prob, mask, thresholds, m.q, m.gt, m.hist, HW);
         aiu_counts_kernel<<<b, 128, 0, stream>>>(m.hist, inter, uni);
     }
-    if (with_hd) {
+    if (with_hd && m.fused) {
+        CSBSR_CHECK_CUDA(cudaMemsetAsync(m.count_gt, 0, sizeof(int) * b, stream));
+        CSBSR_CHECK_CUDA(cudaMemsetAsync(m.counter, 0, sizeof(int), stream));
+        const int cslices = (NC + 255) / 256;
+        corner_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.q, m.gt, nullptr, nullptr, m.cg, h, w);
+        column_scan_kernel<0><<<dim3((Wc + 127) / 128, b), 128, 0, stream>>>(m.cg, nullptr, nullptr, m.gcol_g, Hc, Wc);
+        gt_edt_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.gcol_g, m.d2g, Hc, Wc);
+        gt_list_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.cg, m.gt_list, m.count_gt, NC);
+        FusedArgs fa;
+        fa.q = m.q; fa.cg = m.cg; fa.d2g = m.d2g; fa.gt_list = m.gt_list; fa.count_gt = m.count_gt;
+        fa.H = h; fa.W = w; fa.total_items = b * kNumThr;
+        fa.pct = percent / 100.0; fa.max_img_len = static_cast<double>(w);
+        fa.hd = hd; fa.msd = msd;
+        fa.scratch = m.scratch; fa.scratch_cap = m.cap; fa.counter = m.counter;
+        fa.force_seq = getenv("CSBSR_METRICS_SEQUENTIAL") ? 1 : 0;
+        const int smem = static_cast<int>(fused_smem_bytes(h, w));
+        static bool fattr = false;
+        if (!fattr) {
+            CSBSR_CHECK_CUDA(cudaFuncSetAttribute(hd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            fattr = true;
+        }
+        const int grid = fa.total_items < m.ctas ? fa.total_items : m.ctas;
+        hd_fused_kernel<<<grid, kFusedThreads, smem, stream>>>(fa);
+    } else if (with_hd) {
         CSBSR_CHECK_CUDA(cudaMemsetAsync(m.count_gt, 0, sizeof(int) * b, stream));
         CSBSR_CHECK_CUDA(cudaMemsetAsync(m.count_pred, 0, sizeof(int) * b * kNumThr, stream));
         const int cslices = (NC + 255) / 256;

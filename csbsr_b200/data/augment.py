@@ -42,6 +42,6 @@ def crop_flip_batch(images, params, size, c_out=None, device=None):
     out = torch.empty((b, c_out, th, tw), dtype=torch.float32, device=dev)
     import ctypes as C
     _lib.check(_lib.lib().csbsr_crop_flip_u8(ptrs.data_ptr(), dims.data_ptr(), prm.data_ptr(), out.data_ptr(), b, c_out, th, tw,
-                                             C.c_float(1.0 / 255.0), _lib.stream_ptr()), "csbsr_crop_flip_u8")
+                                             C.c_float(255.0), _lib.stream_ptr()), "csbsr_crop_flip_u8")
     _lib.count_launch("csbsr_crop_flip_u8")
     return out

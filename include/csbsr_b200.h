@@ -351,9 +351,9 @@ int csbsr_patch_split(const float* img, float* patches, int b, int c, int h, int
 int csbsr_patch_join(const float* patches, float* img, int b, int c, int h, int w, int ph, int pw, void* stream);
 /* CrackDataSet.__getitem__ augmentation (crack_dataset.py:42-48, data_preprocess.py:13-46; RandomMirror / RandomVerticalFlip /
  * RandomCrop / ToTensor / 255) on decoded uint8 HWC images resident on the device: imgs[b] -> image b, dims[b] = (H, W, C),
- * params[b] = (y0, x0, hflip, vflip) drawn by the caller; out fp32 [b, c_out, th, tw] = pixel * scale (c >= C repeats the last) */
+ * params[b] = (y0, x0, hflip, vflip) drawn by the caller; out fp32 [b, c_out, th, tw] = pixel / divisor (255 for ToTensor; c >= C repeats the last) */
 int csbsr_crop_flip_u8(const unsigned char* const* imgs, const int* dims, const int* params, float* out, int b, int c_out, int th,
-                       int tw, float scale, void* stream);
+                       int tw, float divisor, void* stream);
 /* NHWC bf16 window -> fp32 NCHW (the first c channels): images / logits leaving the networks */
 int csbsr_nhwc_bf16_to_nchw_f32(const void* x, float* y, int n, long long hw, int c, int x_pitch, int x_coff, void* stream);
 
