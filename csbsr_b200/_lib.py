@@ -207,7 +207,7 @@ def stream_ptr():
 
 
 # kernels launched per C-ABI call (our own __global__ functions only; memsets are not counted)
-KERNELS_PER_CALL = {"csbsr_conv_igemm": 1, "csbsr_kpred_cat_chain": 2, "csbsr_clip_instnorm_stats": 2, "csbsr_degrade": 3, "csbsr_seg_metrics": 7}
+KERNELS_PER_CALL = {"csbsr_conv_igemm": 1, "csbsr_kpred_cat_chain": 2, "csbsr_clip_instnorm_stats": 2, "csbsr_degrade": 3, "csbsr_seg_metrics": 8}
 LAUNCHES = 0
 
 

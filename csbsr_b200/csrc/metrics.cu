@@ -187,15 +187,74 @@ __device__ __forceinline__ unsigned int row_search(const unsigned short* __restr
     return best;
 }
 
-// full squared-distance map to the gt borders (needed at every prediction-border corner)
-__global__ void gt_edt_kernel(const unsigned short* __restrict__ gcol, unsigned int* __restrict__ d2g, int Hc, int Wc) {
-    const int b = blockIdx.y;
-    const unsigned short* gb = gcol + static_cast<size_t>(b) * Hc * Wc;
-    unsigned int* ob = d2g + static_cast<size_t>(b) * Hc * Wc;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Hc * Wc; i += gridDim.x * blockDim.x) {
-        const int y = i / Wc, x = i % Wc;
-        ob[i] = row_search(gb + static_cast<size_t>(y) * Wc, x, Wc);
+// exact row search with block skipping: gmin[k] = min of grow[16k .. 16k+15] (kInf16 when the block has no finite entry); a block
+// whose lower bound dxmin^2 + gmin^2 cannot beat `best` is skipped as a whole -- long searches over uniform far-away borders (the
+// image frame when the prediction is "everything") cost Wc/16 bound checks instead of Wc steps.  Same minimum as row_search.
+__device__ __forceinline__ unsigned int row_search_blocked(const unsigned short* __restrict__ grow, const unsigned short* __restrict__ gmin,
+                                                           int x, int Wc) {
+    const int nb = (Wc + 15) >> 4, b0 = x >> 4;
+    unsigned int best = kInfD2;
+    auto scan = [&](int blk) {
+        const int lo = blk << 4, hi = min(Wc, lo + 16);
+        for (int xx = lo; xx < hi; ++xx) {
+            const unsigned int gv = grow[xx];
+            if (gv != kInf16) {
+                const unsigned int dx = static_cast<unsigned int>(abs(xx - x));
+                best = min(best, dx * dx + gv * gv);
+            }
+        }
+    };
+    scan(b0);
+    for (int k = 1; k < nb; ++k) {
+        const int bl = b0 - k, br = b0 + k;
+        if (bl < 0 && br >= nb) break;
+        bool any = false;
+        if (bl >= 0) {
+            const unsigned int dxm = static_cast<unsigned int>(x - ((bl << 4) + 15));      // distance to the block's closest column
+            if (dxm * dxm < best) {
+                any = true;
+                const unsigned int gm = gmin[bl];
+                if (gm != kInf16 && dxm * dxm + gm * gm < best) scan(bl);
+            }
+        }
+        if (br < nb) {
+            const unsigned int dxm = static_cast<unsigned int>((br << 4) - x);
+            if (dxm * dxm < best) {
+                any = true;
+                const unsigned int gm = gmin[br];
+                if (gm != kInf16 && dxm * dxm + gm * gm < best) scan(br);
+            }
+        }
+        if (!any && (bl < 0 || br >= nb || true)) {
+            // both sides are already too far in x alone (or off the row): farther blocks are farther still
+            const bool left_done = bl < 0 || static_cast<unsigned int>(x - ((bl << 4) + 15)) * static_cast<unsigned int>(x - ((bl << 4) + 15)) >= best;
+            const bool right_done = br >= nb || static_cast<unsigned int>((br << 4) - x) * static_cast<unsigned int>((br << 4) - x) >= best;
+            if (left_done && right_done) break;
+        }
     }
+    return best;
+}
+
+// full squared-distance map to the gt borders (needed at every prediction-border corner): one block per (image, corner row),
+// the row of column distances and its 16-column block minima staged in shared memory, block-skipping exact row search
+__global__ void __launch_bounds__(256) gt_edt_kernel(const unsigned short* __restrict__ gcol, unsigned int* __restrict__ d2g, int Hc,
+                                                     int Wc) {
+    extern __shared__ unsigned short ge_sm[];                 // [Wc] distances + [ceil(Wc/16)] block minima
+    unsigned short* grow = ge_sm;
+    unsigned short* gmin = ge_sm + ((Wc + 7) & ~7);
+    const int y = blockIdx.x, b = blockIdx.y;
+    const unsigned short* src = gcol + (static_cast<size_t>(b) * Hc + y) * Wc;
+    for (int x = threadIdx.x; x < Wc; x += blockDim.x) grow[x] = src[x];
+    __syncthreads();
+    const int nblk = (Wc + 15) >> 4;
+    for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
+        unsigned int mn = kInf16;
+        for (int j = 0; j < min(16, Wc - (k << 4)); ++j) mn = min(mn, static_cast<unsigned int>(grow[(k << 4) + j]));
+        gmin[k] = static_cast<unsigned short>(mn);
+    }
+    __syncthreads();
+    unsigned int* ob = d2g + (static_cast<size_t>(b) * Hc + y) * Wc;
+    for (int x = threadIdx.x; x < Wc; x += blockDim.x) ob[x] = row_search_blocked(grow, gmin, x, Wc);
 }
 
 // neighbour code -> contour-length class: 0 = none, 1 = diag (0.5*sqrt2), 2 = 1.0, 3 = 2*diag (lookup_tables.py:351-398)
@@ -388,9 +447,37 @@ __device__ void replay_parallel(const unsigned int* keys, int n, double pct, dou
     }
     __syncthreads();
     const int nl = ax.misc[0];
-    for (int i = tid; i < nl; i += nt) {
-        ax.leaf_l[i] = pairwise_leaf<false>(keys, ax.leaf_start[i], ax.leaf_n[i]);
-        ax.leaf_w[i] = pairwise_leaf<true>(keys, ax.leaf_start[i], ax.leaf_n[i]);
+    // every leaf sum (two per leaf: lengths, distance * length) is evaluated by 8 lanes, one per numpy accumulator, and
+    // combined in numpy's order ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) followed by the sequential tail
+    {
+        const int lane = tid & 31, sub = lane & 7, grp = lane >> 3;          // 4 groups of 8 lanes per warp
+        const int warp = tid >> 5, nwarps = nt >> 5;
+        for (int base = warp * 2; base < nl; base += nwarps * 2) {
+            const int li = base + (grp >> 1);
+            const bool prod = grp & 1;
+            double r = 0.0;
+            int ls = 0, ln = 0;
+            if (li < nl) {
+                ls = ax.leaf_start[li]; ln = ax.leaf_n[li];
+                if (ln >= 8) {
+                    r = prod ? elem<true>(keys, ls + sub) : elem<false>(keys, ls + sub);
+                    for (int i = 8 + sub; i < ln - (ln % 8); i += 8) r += prod ? elem<true>(keys, ls + i) : elem<false>(keys, ls + i);
+                }
+            }
+            const unsigned int full = 0xFFFFFFFFu;
+            const double r1 = r + __shfl_down_sync(full, r, 1);                 // lanes 0,2,4,6 of the group: r0+r1, r2+r3, ...
+            const double r2 = r1 + __shfl_down_sync(full, r1, 2);               // lanes 0,4: (r0+r1)+(r2+r3), (r4+r5)+(r6+r7)
+            double res = r2 + __shfl_down_sync(full, r2, 4);                    // lane 0 of the group
+            if (li < nl && sub == 0) {
+                if (ln < 8) {
+                    res = 0.0;
+                    for (int i = 0; i < ln; ++i) res += prod ? elem<true>(keys, ls + i) : elem<false>(keys, ls + i);
+                } else {
+                    for (int i = ln - (ln % 8); i < ln; ++i) res += prod ? elem<true>(keys, ls + i) : elem<false>(keys, ls + i);
+                }
+                (prod ? ax.leaf_w : ax.leaf_l)[li] = res;
+            }
+        }
     }
     // ---- class counts per contiguous chunk
     const int L = (n + nt - 1) / nt;
@@ -400,8 +487,31 @@ __device__ void replay_parallel(const unsigned int* keys, int n, double pct, dou
         const int c = keys[i] & 3;
         k1 += (c == 1); k2 += (c == 2); k3 += (c == 3);
     }
-    ax.cnt[tid * 3] = k1; ax.cnt[tid * 3 + 1] = k2; ax.cnt[tid * 3 + 2] = k3;
-    __syncthreads();
+    // exclusive prefix of the chunk counts over the block: warp scans + a scan of the warp totals (ax.cnt[0 .. 3*32))
+    {
+        const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+        int i1 = k1, i2 = k2, i3 = k3;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a1 = __shfl_up_sync(0xFFFFFFFFu, i1, o), a2 = __shfl_up_sync(0xFFFFFFFFu, i2, o), a3 = __shfl_up_sync(0xFFFFFFFFu, i3, o);
+            if (lane >= o) { i1 += a1; i2 += a2; i3 += a3; }
+        }
+        __syncthreads();                                   // leaf tables complete; ax.cnt free
+        if (lane == 31) { ax.cnt[warp * 3] = i1; ax.cnt[warp * 3 + 1] = i2; ax.cnt[warp * 3 + 2] = i3; }
+        __syncthreads();
+        if (tid == 0) {
+            int a1 = 0, a2 = 0, a3 = 0;
+            for (int w = 0; w < nwarps; ++w) {
+                const int b1 = ax.cnt[w * 3], b2 = ax.cnt[w * 3 + 1], b3 = ax.cnt[w * 3 + 2];
+                ax.cnt[w * 3] = a1; ax.cnt[w * 3 + 1] = a2; ax.cnt[w * 3 + 2] = a3;
+                a1 += b1; a2 += b2; a3 += b3;
+            }
+        }
+        __syncthreads();
+        const int e1 = ax.cnt[warp * 3] + i1 - k1, e2 = ax.cnt[warp * 3 + 1] + i2 - k2, e3 = ax.cnt[warp * 3 + 2] + i3 - k3;
+        __syncthreads();
+        ax.cnt[96 + tid * 3] = e1; ax.cnt[96 + tid * 3 + 1] = e2; ax.cnt[96 + tid * 3 + 2] = e3;     // exclusive prefix of chunk tid
+    }
     if (tid == 0) {
         // combine the leaf sums in recursion order: post-order over the same tree
         for (int pass = 0; pass < 2; ++pass) {
@@ -420,19 +530,12 @@ __device__ void replay_parallel(const unsigned int* keys, int n, double pct, dou
             }
             ax.dres[pass] = ret;
         }
-        // exclusive prefix of the chunk counts
-        int a1 = 0, a2 = 0, a3 = 0;
-        for (int t = 0; t < nt; ++t) {
-            const int b1 = ax.cnt[t * 3], b2 = ax.cnt[t * 3 + 1], b3 = ax.cnt[t * 3 + 2];
-            ax.cnt[t * 3] = a1; ax.cnt[t * 3 + 1] = a2; ax.cnt[t * 3 + 2] = a3;
-            a1 += b1; a2 += b2; a3 += b3;
-        }
     }
     __syncthreads();
     const double total = ax.dres[0];
     const double diag = 0.5 * 1.4142135623730951;
     const double margin = 1e-9;
-    k1 = ax.cnt[tid * 3]; k2 = ax.cnt[tid * 3 + 1]; k3 = ax.cnt[tid * 3 + 2];
+    k1 = ax.cnt[96 + tid * 3]; k2 = ax.cnt[96 + tid * 3 + 1]; k3 = ax.cnt[96 + tid * 3 + 2];
     for (int i = c0; i < c1; ++i) {
         const int c = keys[i] & 3;
         k1 += (c == 1); k2 += (c == 2); k3 += (c == 3);
@@ -449,7 +552,7 @@ __device__ void replay_parallel(const unsigned int* keys, int n, double pct, dou
         if (idx < n) {
             // recompute e at idx from the owning chunk
             const int t = idx / L;
-            int q1 = ax.cnt[t * 3], q2 = ax.cnt[t * 3 + 1], q3 = ax.cnt[t * 3 + 2];
+            int q1 = ax.cnt[96 + t * 3], q2 = ax.cnt[96 + t * 3 + 1], q3 = ax.cnt[96 + t * 3 + 2];
             for (int i = t * L; i <= idx; ++i) {
                 const int c = keys[i] & 3;
                 q1 += (c == 1); q2 += (c == 2); q3 += (c == 3);
@@ -489,7 +592,7 @@ __global__ void sort_replay_kernel(const unsigned int* __restrict__ keys_g2p, co
     ax.leaf_start = reinterpret_cast<int*>(ax.dres + 2);
     ax.leaf_n = ax.leaf_start + kMaxLeaves;
     ax.cnt = ax.leaf_n + kMaxLeaves;
-    ax.misc = ax.cnt + 3 * 1024;
+    ax.misc = ax.cnt + 96 + 3 * 1024;
     const int bt = blockIdx.x >> 1;
     const int dir = blockIdx.x & 1;                    // 0: gt->pred, 1: pred->gt
     const int b = bt / kNumThr;
@@ -525,7 +628,7 @@ __global__ void sort_replay_kernel(const unsigned int* __restrict__ keys_g2p, co
 
 template <int CAP>
 constexpr size_t sort_smem_bytes() {
-    return static_cast<size_t>(CAP) * 4 + (CAP / 64 + 2) * (8 + 8 + 4 + 4) + 16 + 3 * 1024 * 4 + 16;
+    return static_cast<size_t>(CAP) * 4 + (CAP / 64 + 2) * (8 + 8 + 4 + 4) + 16 + (96 + 3 * 1024) * 4 + 16;
 }
 
 // lists that do not fit in shared memory: bitonic sort in place in global memory by one block (rare, slow path)
@@ -564,12 +667,78 @@ __global__ void sort_replay_global_kernel(unsigned int* __restrict__ keys_g2p, u
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int pow2_at_least(int v) { int m = 1; while (m < v) m <<= 1; return m; }
 
+// per corner the range (qlo, qhi] of thresholds at which it is a prediction border, stored TRANSPOSED ([x][y], y padded to a
+// multiple of 32 with the never-a-border range (255, 0)): a warp of the fused kernel reads 32 consecutive y of one column
+// with one coalesced 64-byte load and its ballot is the column-packed mask word directly
+__global__ void corner_range_t_kernel(const unsigned char* __restrict__ q, uchar2* __restrict__ qr, int H, int W, int Hp) {
+    __shared__ uchar2 tile[32][33];
+    const int Hc = H + 1, Wc = W + 1;
+    const int b = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const unsigned char* qb = q + static_cast<size_t>(b) * H * W;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {              // coalesced along x
+        const int y = y0 + r, x = x0 + threadIdx.x;
+        uchar2 v = make_uchar2(255, 0);
+        if (y < Hc && x < Wc) {
+            const int a = pix(qb, y - 1, x - 1, H, W), bb = pix(qb, y - 1, x, H, W), c = pix(qb, y, x - 1, H, W), d = pix(qb, y, x, H, W);
+            v = make_uchar2(static_cast<unsigned char>(min(min(a, bb), min(c, d))), static_cast<unsigned char>(max(max(a, bb), max(c, d))));
+        }
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {              // coalesced along y
+        const int x = x0 + r, y = y0 + threadIdx.x;
+        if (x < Wc && y < Hp) qr[(static_cast<size_t>(b) * Wc + x) * Hp + y] = tile[threadIdx.x][r];
+    }
+}
+
+// gt border corners of one image as a ROW-SORTED list: list[row_start[y] .. row_start[y+1]) are the corners of corner-row y
+// (one block per image: per-row counts with ballots, exclusive scan, ordered fill); count[b] = row_start[Hc]
+__global__ void __launch_bounds__(1024) gt_rowlist_kernel(const unsigned char* __restrict__ cg, int* __restrict__ list,
+                                                          int* __restrict__ row_start, int* __restrict__ count, int Hc, int Wc) {
+    extern __shared__ int rl_sm[];                       // [Hc + 1]
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const unsigned char* cb = cg + static_cast<size_t>(b) * Hc * Wc;
+    for (int y = warp; y < Hc; y += nwarps) {
+        int n = 0;
+        for (int x0 = 0; x0 < Wc; x0 += 32) {
+            const int x = x0 + lane;
+            const int c = x < Wc ? cb[y * Wc + x] : 0;
+            n += __popc(__ballot_sync(0xFFFFFFFFu, c != 0 && c != 15));
+        }
+        if (lane == 0) rl_sm[y] = n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int y = 0; y < Hc; ++y) { const int n = rl_sm[y]; rl_sm[y] = acc; acc += n; }
+        rl_sm[Hc] = acc;
+        count[b] = acc;
+    }
+    __syncthreads();
+    for (int y = threadIdx.x; y <= Hc; y += blockDim.x) row_start[static_cast<size_t>(b) * (Hc + 1) + y] = rl_sm[y];
+    int* lb = list + static_cast<size_t>(b) * Hc * Wc;
+    for (int y = warp; y < Hc; y += nwarps) {
+        int base = rl_sm[y];
+        for (int x0 = 0; x0 < Wc; x0 += 32) {
+            const int x = x0 + lane;
+            const int c = x < Wc ? cb[y * Wc + x] : 0;
+            const bool on = c != 0 && c != 15;
+            const unsigned int m = __ballot_sync(0xFFFFFFFFu, on);
+            if (on) lb[base + __popc(m & ((1u << lane) - 1u))] = y * Wc + x;
+            base += __popc(m);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ fused per-(image, threshold) HD / MSD
 // One persistent CTA per SM takes (image, threshold) items from a global counter and keeps everything of the item on chip:
-//   1. the prediction-border corners of the threshold as a row-packed BIT MASK in shared memory ((H+1) x ceil((W+1)/32)
-//      words, 27 KB at 448^2), built with warp ballots straight from the quantised map q;
-//   2. distances_gt_to_pred: for every gt border corner an exact nearest-set-bit search in the mask (rows expanding from
-//      the corner, clz / ffs inside the row words, early exit when dy^2 >= best) -- no per-threshold column-distance map;
+//   1. the prediction-border corners of the threshold as a column-packed BIT MASK in shared memory ((W+1) columns x
+//      ceil((H+1)/32) words, 27 KB at 448^2), built with warp ballots (32x32 bit-tile transposes) straight from the map q;
+//   2. distances_gt_to_pred: the exact EDT as column pass + row search, in bands of 32 corner rows: every column thread turns
+//      its mask words into the vertical distances of the band's rows (clz / ffs for the nearest bits above / below, one sweep
+//      inside the band's own word), the band's [32][W+1] uint16 distances stay in shared memory, and the gt border corners of
+//      those rows (row-sorted list) run the expanding row search with early exit -- the per-threshold column-distance map
+//      (99 x 449^2 uint16 per image) never exists;
 //   3. distances_pred_to_gt: every set bit looks its squared distance up in the per-image gt EDT map d2g;
 //   4. both key lists are sorted in shared memory (bitonic, <= 32768 keys) and replayed in numpy's floating-point order;
 //      longer lists spill to a per-CTA global scratch area (one region per resident CTA, not per image).
@@ -578,12 +747,17 @@ static inline int pow2_at_least(int v) { int m = 1; while (m < v) m <<= 1; retur
 constexpr int kFusedThreads = 1024;
 constexpr int kFusedCap = 32768;                            // keys held in shared memory
 constexpr int kFusedLeaves = kFusedCap / 64 + 2;
+__host__ __device__ constexpr size_t fused_aux_bytes() {   // leaf tables + per-thread class counts of replay_parallel, 16-byte multiple
+    return (static_cast<size_t>(kFusedLeaves) * (8 + 8 + 4 + 4) + 16 + (96 + 3 * kFusedThreads) * 4 + 64 + 15) / 16 * 16;
+}
 
 struct FusedArgs {
     const unsigned char* q;
+    const uchar2* qr;                                       // [B][Wc][Hp] transposed threshold ranges (corner_range_t_kernel)
     const unsigned char* cg;
     const unsigned int* d2g;
-    const int* gt_list;
+    const int* gt_list;                                     // row-sorted (gt_rowlist_kernel)
+    const int* row_start;                                   // [B][Hc + 1]
     const int* count_gt;
     int H, W, total_items;
     double pct, max_img_len;
@@ -595,52 +769,59 @@ struct FusedArgs {
     int force_seq;
 };
 
-// distance from x to the nearest set bit of a row of the mask, or a value > maxdx when there is none within maxdx
-__device__ __forceinline__ int row_nearest(const unsigned int* __restrict__ row, int x, int WW, int maxdx) {
-    const int w0 = x >> 5, o = x & 31;
-    const unsigned int word = row[w0];
-    int best = 0x3FFFFFFF;
-    const unsigned int ml = word & (0xFFFFFFFFu >> (31 - o));          // bits at or left of x
-    if (ml) best = o - (31 - __clz(ml));
-    const unsigned int mr = word & (0xFFFFFFFFu << o);                 // bits at or right of x
-    if (mr) best = min(best, __ffs(mr) - 1 - o);
-    const int lim = min(best - 1, maxdx);                              // only strictly better candidates matter
-    for (int wl = w0 - 1; wl >= 0; --wl) {
-        const int dmin = o + 1 + 32 * (w0 - 1 - wl);                    // distance to the closest position of word wl
-        if (dmin > lim) break;
-        const unsigned int v = row[wl];
-        if (v) { best = min(best, dmin + __clz(v)); break; }
+// Counting sort of keys[0..n) in shared memory when every key is below `kmax` <= cap - n: the histogram lives in
+// keys[n .. n + kmax) of the same buffer.  O(n + kmax) instead of the O(n log^2 n) bitonic network: distances of a few dozen
+// pixels (keys = d^2 * 4 + class < 16384) are the common case.  Returns false (buffer untouched) when the range is too large.
+__device__ bool block_counting_sort(unsigned int* keys, int n, int cap, int* s_tmp /* [34] shared */) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    unsigned int mx = 0;
+    for (int i = tid; i < n; i += nt) mx = max(mx, keys[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    if (lane == 0) s_tmp[warp] = static_cast<int>(mx);
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0;
+        for (int w = 0; w < nwarps; ++w) m = max(m, s_tmp[w]);
+        s_tmp[32] = m;
     }
-    const int lim2 = min(best - 1, maxdx);
-    for (int wr = w0 + 1; wr < WW; ++wr) {
-        const int dmin = (32 - o) + 32 * (wr - w0 - 1);
-        if (dmin > lim2) break;
-        const unsigned int v = row[wr];
-        if (v) { best = min(best, dmin + __ffs(v) - 1); break; }
+    __syncthreads();
+    const long long kmax = static_cast<long long>(static_cast<unsigned int>(s_tmp[32])) + 1;
+    if (kmax > cap - n || kmax > 4LL * n + 1024) { __syncthreads(); return false; }
+    const int K = static_cast<int>(kmax);
+    unsigned int* hist = keys + n;
+    for (int i = tid; i < K; i += nt) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) atomicAdd(&hist[keys[i]], 1u);
+    __syncthreads();
+    // exclusive scan of hist over the block: contiguous chunks per thread
+    const int L = (K + nt - 1) / nt;
+    const int c0 = min(K, tid * L), c1 = min(K, c0 + L);
+    int sum = 0;
+    for (int i = c0; i < c1; ++i) sum += static_cast<int>(hist[i]);
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += v;
     }
-    return best;
-}
-
-// exact squared Euclidean distance from corner (y, x) to the nearest set bit of the mask (at least one bit is set)
-__device__ __forceinline__ unsigned int mask_nearest_d2(const unsigned int* __restrict__ bits, int y, int x, int Hc, int WW) {
-    unsigned int best = kInfD2;
-    for (int dy = 0; dy < Hc; ++dy) {
-        const unsigned int dd = static_cast<unsigned int>(dy) * dy;
-        if (dd >= best) break;
-        const int up = y - dy, dn = y + dy;
-        if (up < 0 && dn >= Hc) break;
-        // |dx| that can still improve: dx^2 < best - dd
-        const int maxdx = best == kInfD2 ? 0x3FFFFFF : static_cast<int>(sqrtf(static_cast<float>(best - dd))) + 1;
-        if (up >= 0) {
-            const int dx = row_nearest(bits + static_cast<size_t>(up) * WW, x, WW, maxdx);
-            if (dx < 0x3FFFFFF) best = min(best, dd + static_cast<unsigned int>(dx) * dx);
-        }
-        if (dy > 0 && dn < Hc) {
-            const int dx = row_nearest(bits + static_cast<size_t>(dn) * WW, x, WW, maxdx);
-            if (dx < 0x3FFFFFF) best = min(best, dd + static_cast<unsigned int>(dx) * dx);
-        }
+    if (lane == 31) s_tmp[warp] = inc;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int w = 0; w < nwarps; ++w) { const int v = s_tmp[w]; s_tmp[w] = acc; acc += v; }
     }
-    return best;
+    __syncthreads();
+    int pos = s_tmp[warp] + inc - sum;                        // first output index of this thread's key values
+    __syncthreads();
+    // every key value writes its run; reading hist and writing keys[0..n) never overlap (hist sits behind the keys)
+    for (int i = c0; i < c1; ++i) {
+        const int cnt = static_cast<int>(hist[i]);
+        for (int j = 0; j < cnt; ++j) keys[pos + j] = static_cast<unsigned int>(i);
+        pos += cnt;
+    }
+    __syncthreads();
+    return true;
 }
 
 // block-wide bitonic sort of keys[0..n) (keys[n..m) padded with 0xFFFFFFFF, m = next power of two <= capacity)
@@ -651,13 +832,12 @@ __device__ void block_bitonic(unsigned int* keys, int n) {
     __syncthreads();
     for (int k = 2; k <= m; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < m; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned int a = keys[i], c = keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > c) == up) { keys[i] = c; keys[ixj] = a; }
-                }
+            // one compare-exchange per pair index p: i = the p-th index with bit j clear, partner i | j
+            for (int p = threadIdx.x; p < (m >> 1); p += blockDim.x) {
+                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                const unsigned int a = keys[i], c = keys[i | j];
+                const bool up = (i & k) == 0;
+                if ((a > c) == up) { keys[i] = c; keys[i | j] = a; }
             }
             __syncthreads();
         }
@@ -666,11 +846,14 @@ __device__ void block_bitonic(unsigned int* keys, int n) {
 
 __global__ void __launch_bounds__(kFusedThreads, 1) hd_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(16) unsigned char fsm[];
-    const int Hc = a.H + 1, Wc = a.W + 1, WW = (Wc + 31) / 32, NC = Hc * Wc;
-    unsigned int* bits = reinterpret_cast<unsigned int*>(fsm);
-    unsigned int* skeys = bits + ((Hc * WW + 3) & ~3);
+    const int Hc = a.H + 1, Wc = a.W + 1, WH = (Hc + 31) / 32, WWt = (Wc + 31) / 32, NC = Hc * Wc;
+    unsigned int* bits = reinterpret_cast<unsigned int*>(fsm);                       // [Wc][WH]: bit r of word (x, k) = corner (32k + r, x)
+    unsigned int* skeys = bits + ((Wc * WH + 3) & ~3);
     unsigned char* aux_base = reinterpret_cast<unsigned char*>(skeys + kFusedCap);
+    unsigned short* gbuf = reinterpret_cast<unsigned short*>(aux_base + fused_aux_bytes());   // [32][Wc] vertical distances of a band
+    unsigned short* gminb = gbuf + 32 * Wc;                                                   // [32][ceil(Wc/16)] block minima
     __shared__ int s_item, s_np, s_cnt;
+    __shared__ int s_tmp[34];
     __shared__ double s_res[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFusedThreads / 32;
     unsigned int* gkeys = a.scratch + static_cast<size_t>(blockIdx.x) * a.scratch_cap;
@@ -683,13 +866,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) hd_fused_kernel(const FusedA
         ax.leaf_start = reinterpret_cast<int*>(ax.dres + 2);
         ax.leaf_n = ax.leaf_start + max_leaves;
         ax.cnt = ax.leaf_n + max_leaves;
-        ax.misc = ax.cnt + 3 * kFusedThreads;
+        ax.misc = ax.cnt + 96 + 3 * kFusedThreads;
         return ax;
     };
     // sort + replay of the list that was just written to `keys` (shared or this CTA's global scratch)
     auto sort_replay = [&](unsigned int* keys, int n, bool in_smem, double* out) {
-        block_bitonic(keys, n);
-        if (a.force_seq) {
+        if (a.force_seq & 4) { if (tid == 0) { out[0] = 0; out[1] = 0; } __syncthreads(); return; }
+        if (!(in_smem && !(a.force_seq & 16) && block_counting_sort(keys, n, kFusedCap, s_tmp))) block_bitonic(keys, n);
+        if (a.force_seq & 8) { if (tid == 0) { out[0] = 0; out[1] = 0; } __syncthreads(); return; }
+        if (a.force_seq & 1) {
             if (tid == 0) replay_list(keys, n, a.pct, out);
         } else if (in_smem) {
             replay_parallel(keys, n, a.pct, out, make_aux(aux_base, kFusedLeaves));
@@ -708,20 +893,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) hd_fused_kernel(const FusedA
         const int b = item / kNumThr, t = item % kNumThr + 1;
         const int ng = a.count_gt[b];
         const unsigned char* qb = a.q + static_cast<size_t>(b) * a.H * a.W;
-        // ---- 1. border mask of threshold t: corner (y, x) is a border iff min < t <= max over its 2x2 pixel block
+        // ---- 1. border mask of threshold t: corner (y, x) is a border iff qlo < t <= qhi of its 2x2 pixel block; one coalesced
+        // load of 32 consecutive y of a column + one ballot per mask word
         int local_np = 0;
-        for (int widx = warp; widx < Hc * WW; widx += nwarps) {
-            const int y = widx / WW, x = (widx - y * WW) * 32 + lane;
-            bool bit = false;
-            if (x < Wc) {
-                const int p00 = pix(qb, y - 1, x - 1, a.H, a.W), p01 = pix(qb, y - 1, x, a.H, a.W), p10 = pix(qb, y, x - 1, a.H, a.W),
-                          p11 = pix(qb, y, x, a.H, a.W);
-                const int lo = min(min(p00, p01), min(p10, p11)), hi = max(max(p00, p01), max(p10, p11));
-                bit = lo < t && t <= hi;
+        {
+            const uchar2* qrb = a.qr + static_cast<size_t>(b) * Wc * (WH * 32);
+            for (int widx = warp; widx < Wc * WH; widx += nwarps) {
+                const uchar2 v = qrb[static_cast<size_t>(widx) * 32 + lane];          // widx = x * WH + k  ->  (x, y = 32k + lane)
+                const unsigned int word = __ballot_sync(0xFFFFFFFFu, v.x < t && t <= v.y);
+                if (lane == 0) { bits[widx] = word; local_np += __popc(word); }
             }
-            const unsigned int word = __ballot_sync(0xFFFFFFFFu, bit);
-            if (lane == 0) { bits[widx] = word; local_np += __popc(word); }
         }
+        local_np = warp_sum(local_np);
         if (lane == 0 && local_np) atomicAdd(&s_np, local_np);
         __syncthreads();
         const int np_ = s_np;
@@ -733,18 +916,51 @@ __global__ void __launch_bounds__(kFusedThreads, 1) hd_fused_kernel(const FusedA
             }
             continue;
         }
-        // ---- 2. distances_gt_to_pred
+        // ---- 2. distances_gt_to_pred: column pass per band of 32 corner rows, then the row search of the band's gt corners
         {
             const bool in_smem = ng <= kFusedCap;
             unsigned int* keys = in_smem ? skeys : gkeys;
             const int* list = a.gt_list + static_cast<size_t>(b) * NC;
+            const int* rs = a.row_start + static_cast<size_t>(b) * (Hc + 1);
             const unsigned char* cgb = a.cg + static_cast<size_t>(b) * NC;
-            for (int k = tid; k < ng; k += kFusedThreads) {
-                const int i = list[k];
-                const int y = i / Wc, x = i - y * Wc;
-                keys[k] = (mask_nearest_d2(bits, y, x, Hc, WW) << 2) | len_class(cgb[i]);
+            for (int ky = 0; ky < WH; ++ky) {
+                const int y0 = ky * 32, y1 = min(Hc, y0 + 32);
+                const int k0 = rs[y0], k1 = rs[y1];
+                if (k0 == k1) continue;                                    // no gt border corner in these rows (uniform branch)
+                for (int x = tid; x < Wc; x += kFusedThreads) {
+                    const unsigned int* col = bits + x * WH;
+                    int last = -0x10000, next = 0x20000;                   // nearest set bit above / below the band
+                    for (int k = ky - 1; k >= 0; --k) { const unsigned int v = col[k]; if (v) { last = k * 32 + 31 - __clz(v); break; } }
+                    for (int k = ky + 1; k < WH; ++k) { const unsigned int v = col[k]; if (v) { next = k * 32 + __ffs(v) - 1; break; } }
+                    const unsigned int w = col[ky];
+                    for (int r = 0; r < y1 - y0; ++r) {
+                        if ((w >> r) & 1u) last = y0 + r;
+                        gbuf[r * Wc + x] = static_cast<unsigned short>(min(y0 + r - last, 0xFFFF));
+                    }
+                    for (int r = y1 - y0 - 1; r >= 0; --r) {
+                        if ((w >> r) & 1u) next = y0 + r;
+                        const int dn = next - (y0 + r);
+                        if (dn < gbuf[r * Wc + x]) gbuf[r * Wc + x] = static_cast<unsigned short>(dn);
+                    }
+                }
+                __syncthreads();
+                const int nblk = (Wc + 15) >> 4;
+                for (int e = tid; e < (y1 - y0) * nblk; e += kFusedThreads) {        // block minima of the band's distance rows
+                    const int r = e / nblk, blk = e - r * nblk;
+                    const unsigned short* gr = gbuf + r * Wc + (blk << 4);
+                    unsigned int mn = kInf16;
+                    for (int j = 0; j < min(16, Wc - (blk << 4)); ++j) mn = min(mn, static_cast<unsigned int>(gr[j]));
+                    gminb[r * nblk + blk] = static_cast<unsigned short>(mn);
+                }
+                __syncthreads();
+                for (int k = k0 + tid; k < k1; k += kFusedThreads) {
+                    const int i = list[k];
+                    const int y = i / Wc, x = i - y * Wc;
+                    const unsigned int d2 = (a.force_seq & 2) ? 1u : row_search_blocked(gbuf + (y - y0) * Wc, gminb + (y - y0) * nblk, x, Wc);
+                    keys[k] = (d2 << 2) | len_class(cgb[i]);
+                }
+                __syncthreads();
             }
-            __syncthreads();
             sort_replay(keys, ng, in_smem, &s_res[0]);
         }
         // ---- 3. distances_pred_to_gt
@@ -752,18 +968,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) hd_fused_kernel(const FusedA
             const bool in_smem = np_ <= kFusedCap;
             unsigned int* keys = in_smem ? skeys : gkeys;
             const unsigned int* d2b = a.d2g + static_cast<size_t>(b) * NC;
-            for (int widx = warp; widx < Hc * WW; widx += nwarps) {
-                const unsigned int word = bits[widx];
+            for (int widx = tid; widx < Wc * WH; widx += kFusedThreads) {          // one thread per mask word: most words are empty
+                unsigned int word = bits[widx];
                 if (word == 0) continue;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_cnt, __popc(word));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if ((word >> lane) & 1u) {
-                    const int y = widx / WW, x = (widx - y * WW) * 32 + lane;
+                int slot = atomicAdd(&s_cnt, __popc(word));
+                const int x = widx / WH, ybase = (widx - x * WH) * 32;
+                while (word) {
+                    const int y = ybase + __ffs(word) - 1;
+                    word &= word - 1;
                     const int p00 = pix(qb, y - 1, x - 1, a.H, a.W), p01 = pix(qb, y - 1, x, a.H, a.W), p10 = pix(qb, y, x - 1, a.H, a.W),
                               p11 = pix(qb, y, x, a.H, a.W);
                     const int code = ((p00 >= t) << 3) | ((p01 >= t) << 2) | ((p10 >= t) << 1) | (p11 >= t);
-                    keys[base + __popc(word & ((1u << lane) - 1u))] = (d2b[y * Wc + x] << 2) | len_class(code);
+                    keys[slot++] = (d2b[y * Wc + x] << 2) | len_class(code);
                 }
             }
             __syncthreads();
@@ -777,16 +993,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) hd_fused_kernel(const FusedA
 }
 
 static size_t fused_smem_bytes(int h, int w) {
-    const int Hc = h + 1, WW = (w + 1 + 31) / 32;
-    const size_t bits = static_cast<size_t>((Hc * WW + 3) & ~3) * 4;
-    const size_t aux = static_cast<size_t>(kFusedLeaves) * (8 + 8 + 4 + 4) + 16 + 3 * kFusedThreads * 4 + 64;
-    return bits + static_cast<size_t>(kFusedCap) * 4 + aux;
+    const int Wc = w + 1, WH = (h + 1 + 31) / 32;
+    const size_t bits = static_cast<size_t>((Wc * WH + 3) & ~3) * 4;
+    return bits + static_cast<size_t>(kFusedCap) * 4 + fused_aux_bytes() + static_cast<size_t>(32) * Wc * 2 + 32 * ((Wc + 15) / 16) * 2 + 16;
 }
 static bool fused_ok(int h, int w) {
     // the long-list replay borrows the key area for its leaf tables: (cap / 64 + 2) * 24 B + counters must fit into it
     const size_t cap = static_cast<size_t>(pow2_at_least((h + 1) * (w + 1)));
-    const size_t long_aux = (cap / 64 + 2) * 24 + 16 + 3 * kFusedThreads * 4 + 64;
-    return !getenv("CSBSR_METRICS_UNFUSED") && fused_smem_bytes(h, w) <= 200 * 1024 && long_aux <= static_cast<size_t>(kFusedCap) * 4;
+    const size_t long_aux = (cap / 64 + 2) * 24 + 16 + (96 + 3 * kFusedThreads) * 4 + 64;
+    return !getenv("CSBSR_METRICS_UNFUSED") && fused_smem_bytes(h, w) <= 220 * 1024 && h + 1 < 0xFFFF && long_aux <= static_cast<size_t>(kFusedCap) * 4;
 }
 
 // combine the two directions and resolve the empty-mask branches (inference.py:315-334)
@@ -813,10 +1028,11 @@ __global__ void finalize_kernel(const int* __restrict__ count_gt, const int* __r
 
 struct MetricsWs {
     unsigned char *q, *gt, *qlo, *qhi, *cg;
-    int *hist, *gt_list, *count_gt, *count_pred;
+    int *hist, *gt_list, *count_gt, *count_pred, *row_start;
     unsigned short *gcol_g, *gcol_t;
     unsigned int *d2g, *keys_g2p, *keys_p2g;
     double* res;
+    uchar2* qr;                  // fused path: transposed per-corner threshold ranges
     unsigned int* scratch;       // fused path: [ctas][cap] spill area of the long key lists
     int* counter;                // fused path: work-item counter
     int cap, ctas;
@@ -839,9 +1055,11 @@ static MetricsWs carve(void* base, int b, int h, int w, bool with_hd) {
         // per image: q, gt, cg (1 B / pixel or corner), gt border list, gt column distances + EDT map; per resident CTA: one
         // spill region for key lists longer than 32768 -- ~2.9 MB per 448^2 image + 155 MB per device instead of 260 MB per image
         m.qlo = m.qhi = nullptr;
+        m.qr = static_cast<uchar2*>(take(sizeof(uchar2) * static_cast<size_t>(b) * (w + 1) * ((h + 1 + 31) / 32 * 32)));
         m.cg = static_cast<unsigned char*>(take(b * NC));
         m.gt_list = static_cast<int*>(take(sizeof(int) * b * NC));
         m.count_gt = static_cast<int*>(take(sizeof(int) * b));
+        m.row_start = static_cast<int*>(take(sizeof(int) * static_cast<size_t>(b) * (h + 2)));
         m.count_pred = nullptr;
         m.gcol_g = static_cast<unsigned short*>(take(sizeof(short) * b * NC));
         m.d2g = static_cast<unsigned int*>(take(sizeof(int) * b * NC));
@@ -897,24 +1115,25 @@ extern "C" int csbsr_seg_metrics(const float* prob, const float* mask, const flo
         aiu_counts_kernel<<<b, 128, 0, stream>>>(m.hist, inter, uni);
     }
     if (with_hd && m.fused) {
-        CSBSR_CHECK_CUDA(cudaMemsetAsync(m.count_gt, 0, sizeof(int) * b, stream));
         CSBSR_CHECK_CUDA(cudaMemsetAsync(m.counter, 0, sizeof(int), stream));
         const int cslices = (NC + 255) / 256;
         corner_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.q, m.gt, nullptr, nullptr, m.cg, h, w);
+        const int Hp = (Hc + 31) / 32 * 32;
+        corner_range_t_kernel<<<dim3((Wc + 31) / 32, Hp / 32, b), dim3(32, 8), 0, stream>>>(m.q, m.qr, h, w, Hp);
         column_scan_kernel<0><<<dim3((Wc + 127) / 128, b), 128, 0, stream>>>(m.cg, nullptr, nullptr, m.gcol_g, Hc, Wc);
-        gt_edt_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.gcol_g, m.d2g, Hc, Wc);
-        gt_list_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.cg, m.gt_list, m.count_gt, NC);
+        gt_edt_kernel<<<dim3(Hc, b), 256, sizeof(short) * (((Wc + 7) & ~7) + ((Wc + 15) / 16) + 8), stream>>>(m.gcol_g, m.d2g, Hc, Wc);
+        gt_rowlist_kernel<<<b, 1024, sizeof(int) * (Hc + 1), stream>>>(m.cg, m.gt_list, m.row_start, m.count_gt, Hc, Wc);
         FusedArgs fa;
-        fa.q = m.q; fa.cg = m.cg; fa.d2g = m.d2g; fa.gt_list = m.gt_list; fa.count_gt = m.count_gt;
+        fa.q = m.q; fa.qr = m.qr; fa.cg = m.cg; fa.d2g = m.d2g; fa.gt_list = m.gt_list; fa.row_start = m.row_start; fa.count_gt = m.count_gt;
         fa.H = h; fa.W = w; fa.total_items = b * kNumThr;
         fa.pct = percent / 100.0; fa.max_img_len = static_cast<double>(w);
         fa.hd = hd; fa.msd = msd;
         fa.scratch = m.scratch; fa.scratch_cap = m.cap; fa.counter = m.counter;
-        fa.force_seq = getenv("CSBSR_METRICS_SEQUENTIAL") ? 1 : 0;
+        fa.force_seq = (getenv("CSBSR_METRICS_SEQUENTIAL") ? 1 : 0) | (getenv("CSBSR_HD_DEBUG") ? atoi(getenv("CSBSR_HD_DEBUG")) : 0);
         const int smem = static_cast<int>(fused_smem_bytes(h, w));
         static bool fattr = false;
         if (!fattr) {
-            CSBSR_CHECK_CUDA(cudaFuncSetAttribute(hd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CSBSR_CHECK_CUDA(cudaFuncSetAttribute(hd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             fattr = true;
         }
         const int grid = fa.total_items < m.ctas ? fa.total_items : m.ctas;
@@ -925,7 +1144,7 @@ extern "C" int csbsr_seg_metrics(const float* prob, const float* mask, const flo
         const int cslices = (NC + 255) / 256;
         corner_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.q, m.gt, m.qlo, m.qhi, m.cg, h, w);
         column_scan_kernel<0><<<dim3((Wc + 127) / 128, b), 128, 0, stream>>>(m.cg, m.qlo, m.qhi, m.gcol_g, Hc, Wc);
-        gt_edt_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.gcol_g, m.d2g, Hc, Wc);
+        gt_edt_kernel<<<dim3(Hc, b), 256, sizeof(short) * (((Wc + 7) & ~7) + ((Wc + 15) / 16) + 8), stream>>>(m.gcol_g, m.d2g, Hc, Wc);
         gt_list_kernel<<<dim3(cslices, b), 256, 0, stream>>>(m.cg, m.gt_list, m.count_gt, NC);
         column_scan_kernel<1><<<dim3((Wc + 127) / 128, b * kNumThr), 128, 0, stream>>>(m.cg, m.qlo, m.qhi, m.gcol_t,
                                                                                       Hc, Wc);
