@@ -229,7 +229,7 @@ def train_leg(args, c, dev, world, rank, timed):
             "reference_dense_tflops_equiv_per_gpu": dense_tf,
             "config": "iteration 40000 (joint phase), SR L1 + pseudo-LR L1 + BoundaryCombo with w^F (m^F=1), Dropout2d and "
                       "BatchNorm batch statistics on, Adam lr 2e-5; gradients all-reduced over NCCL when n_gpus > 1; "
-                      "elementwise / pooling / BatchNorm glue between the convs is aten (cuDNN disabled); forward + loss + backward replayed "
+                      "everything between the convs on own kernels (csrc/glue.cu, cuDNN disabled); forward + loss + backward replayed "
                       "from a CUDA graph (eager launches if capture is unavailable), all-reduce and fused Adam launched per step"}
 
 
@@ -424,7 +424,7 @@ def main():
     peak_tf, peak_bw, peak_src = _peaks()
     traffic = None                       # DRAM bytes of the conv kernel per step, from the committed ncu capture
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_conv_traffic.json")) as f:
             traffic = json.load(f)["dram_bytes_per_image"] * B
     except Exception:
         pass
@@ -450,7 +450,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "csbsr::conv_igemm_kernel", "achieved": achieved_tf, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
-                     "traffic_note": "dram__bytes_read+write of all conv launches of one step (profiles/r01_launches.md), bytes",
+                     "traffic_note": "dram__bytes_read+write of all conv launches of one step (profiles/r02_launches.md), bytes",
                      "peak_source": peak_src + " (sustained bf16)",
                      "launches_per_step": n_conv, "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / (ms_dev / args.steps),
                      "useful_gflop_per_step": conv_useful / 1e9, "padded_gflop_per_step": conv_padded / 1e9,

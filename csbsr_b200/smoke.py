@@ -48,19 +48,18 @@ def run():
 
     lr_ref, k_ref, _ = degrade_ref.degrade(hr, params)
     assert (lr.cpu() - lr_ref).abs().max().item() <= 2e-6, "degrade mismatch"
-    sdc = {k: v.cuda() for k, v in sd.items()}
+    # the oracle runs on the HOST (true fp32, no TF32, and no library kernels in a launch trace of smoke())
     with torch.no_grad():
-        sr_ref, seg_ref, kp_ref, _ = torch_ref.joint_forward(sdc, lr)
-    e_sr, e_seg = (sr - sr_ref).abs().max().item(), (seg - seg_ref).abs().max().item()
-    assert e_sr <= 3e-2 and e_seg <= 5e-2, "network mismatch sr %g seg %g" % (e_sr, e_seg)
+        sr_ref, seg_ref, kp_ref, _ = torch_ref.joint_forward(sd, lr.cpu())
+    e_sr, e_seg = (sr.cpu() - sr_ref).abs().max().item(), (seg.cpu() - seg_ref).abs().max().item()
+    assert e_sr <= 3e-2 and e_seg <= 2e-2, "network mismatch sr %g seg %g" % (e_sr, e_seg)
     inter, union = metrics_ref.iou_counts(seg.cpu().numpy(), mask.numpy())
     hd, msd = metrics_ref.distance_metrics(seg.cpu().numpy(), mask.numpy(), 50)
     assert np.array_equal(r["inter"], inter) and np.array_equal(r["union"], union), "AIU counts mismatch"
     assert np.array_equal(r["hd"], hd) and np.array_equal(r["msd"], msd), "HD/MSD mismatch"
-    cxr, cwr = cx0.clone().requires_grad_(True), cw0.clone().requires_grad_(True)
-    torch.backends.cudnn.allow_tf32 = False
-    torch.nn.functional.conv2d(cxr, cwr, None, padding=1).backward(cup)
-    rel = lambda a, b: (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
+    cxr, cwr = cx0.cpu().requires_grad_(True), cw0.cpu().requires_grad_(True)
+    torch.nn.functional.conv2d(cxr, cwr, None, padding=1).backward(cup.cpu())
+    rel = lambda a, b: (a.cpu() - b).abs().max().item() / (b.abs().max().item() + 1e-12)
     assert rel(cx.grad, cxr.grad) <= 1e-2 and rel(cw.grad, cwr.grad) <= 1e-2, "conv dgrad / wgrad mismatch"
 
     # ---- one tiny joint training step (forward, loss, backward through the conv dgrad / wgrad kernels, fused Adam),
@@ -85,7 +84,7 @@ def run():
     opt.step()
     torch.cuda.synchronize()
     with torch.no_grad():
-        ref_loss = train_ref.train_forward(sdc, lr_t.cuda(), hr_t.cuda(), mask_t.cuda(), kern_t.unsqueeze(1), tm.ss_loss_fn.alpha,
+        ref_loss = train_ref.train_forward(sd, lr_t.cpu(), hr_t.cpu(), mask_t.cpu(), kern_t.cpu().unsqueeze(1), tm.ss_loss_fn.alpha,
                                            beta=tc.SOLVER.TASK_LOSS_WEIGHT, wf_amp=1.0, bn_train=False)[0].item()
     assert np.isfinite(gnorm) and gnorm > 0, "training step produced no gradient"
     assert abs(loss.item() - ref_loss) <= 3e-2 * abs(ref_loss), "train loss %g vs oracle %g" % (loss.item(), ref_loss)

@@ -53,9 +53,11 @@ def launch_summary(path, tag, n_img):
     lines.append("")
     lines.append("Total kernel time: %.2f ms (%.3f ms / image)." % (tot / 1e6, tot / 1e6 / n_img))
     conv = "csbsr::conv_igemm_kernel"
-    if rd[conv] > 0:
-        out = {"kernel": conv, "share_of_gpu_time": t[conv] / tot, "launches_per_image": n[conv] / n_img,
-               "dram_bytes_per_image": (rd[conv] + wr[conv]) / n_img, "us_per_image": t[conv] / 1e3 / n_img}
+    ck = [k for k in t if "conv_igemm_kernel" in k]          # both template instances (cta_group::1 / ::2)
+    c_t, c_n, c_b = sum(t[k] for k in ck), sum(n[k] for k in ck), sum(rd[k] + wr[k] for k in ck)
+    if c_b > 0:
+        out = {"kernel": conv, "share_of_gpu_time": c_t / tot, "launches_per_image": c_n / n_img,
+               "dram_bytes_per_image": c_b / n_img, "us_per_image": c_t / 1e3 / n_img}
         with open(os.path.join(ROOT, "profiles", "%s_conv_traffic.json" % tag), "w") as f:
             json.dump(out, f, indent=1)
     with open(os.path.join(ROOT, "profiles", "%s_launches.md" % tag), "w") as f:

@@ -93,6 +93,11 @@ def main():
     if cfg.SOLVER.BATCH_SIZE % world != 0:
         raise ValueError("SOLVER.BATCH_SIZE=%d is not divisible by the %d ranks" % (cfg.SOLVER.BATCH_SIZE, world))
     per_rank = cfg.SOLVER.BATCH_SIZE // world
+    if world > 1 and cfg.SOLVER.SYNC_BATCHNORM and rank == 0:
+        # the reference converts to synchronised BatchNorm under DataParallel (train.py:98-100, statistics over the whole
+        # batch); here every rank normalises with the statistics of its own chunk, like DataParallel without the conversion
+        print("warning: SOLVER.SYNC_BATCHNORM is set, but BatchNorm statistics stay per rank (%d images each); running "
+              "statistics are checkpointed from rank 0" % per_rank, file=sys.stderr)
     max_iter = args.max_iter or cfg.SOLVER.MAX_ITER
     rng = np.random.default_rng(cfg.SEED + rank)
 
