@@ -48,6 +48,7 @@ class ConvDesc(C.Structure):
         ("r32", C.c_void_p),
         ("block_n", C.c_int32),
         ("r32_pitch", C.c_int32), ("r32_coff", C.c_int32),
+        ("nsub", C.c_int32),
     ]
 
 

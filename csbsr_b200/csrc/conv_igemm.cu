@@ -79,6 +79,8 @@ struct ConvKParams {
     int G, ngroups, dstep, a_stage_bytes;   // tap groups: G taps sharing dw, dh = dh0 + j*dstep, one A box per group
     int cg2;             // cluster == 2 only: tcgen05.mma.cta_group::2 -- the pair's leader issues M = 256 MMAs over both CTAs'
                          // A tiles, every CTA holds half of the weight rows (no multicast), TMA bytes land on the leader's barriers
+    int nsub, spt, sub_n;   // merged sub-phases (csbsr_conv_desc.nsub): nsub per tap class, spt = block_n / sub_n of them per tile,
+                            // sub_n = cout_pad columns each; the two epilogue teams then split every tile by sub-phase
     int staged;          // 1: epilogue through swizzled smem panels, residual via TMA load, output via TMA store
     int res_mode;        // staged only: 0 none, 1 pre-activation add (r0), 2 post-activation add/sub (r1)
     int8_t dh[CSBSR_MAX_TAPS], dw[CSBSR_MAX_TAPS];
@@ -379,7 +381,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int b_total_bytes = (p.stages * b_stage_bytes + 1023) & ~1023;      // keeps the staging panels 1024-B aligned
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + p.stages * p.a_stage_bytes;
-    const int n_panels = p.block_n >> 6;                      // staged epilogue: 64-channel panels per tile
+    const int n_panels = (p.nsub > 1 ? p.sub_n : p.block_n) >> 6;   // staged epilogue: 64-channel panels per team's staging set
     uint8_t* smem_stage = smem_b + b_total_bytes;             // 2 sets x n_panels x 16 KB (staged epilogue only)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage + (p.staged ? 2 * n_panels * kATileBytes : 0));
     uint64_t* empty_bar = full_bar + kMaxStages;
@@ -411,7 +413,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
             // one arrive per draining warp; cta_group::2: the leader's MMA thread waits for the warps of both CTAs
-            mbar_init(&tmem_empty[a], (p.staged ? kEpiWarps / 2 : kEpiWarps) * (kCg2 ? 2 : 1));
+            mbar_init(&tmem_empty[a], ((p.staged && p.nsub <= 1) ? kEpiWarps / 2 : kEpiWarps) * (kCg2 ? 2 : 1));
             mbar_init(&res_full[a], 1);
         }
         fence_barrier_init();
@@ -485,7 +487,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             } else {
                                 mbar_arrive_expect_tx(&full_bar[stage], tx_b);
                                 const uint32_t dst0 = smem_u32(smem_b + stage * b_stage_bytes);
-                                if (p.cluster == 2) {
+                                if (p.nsub > 1) {
+                                    // merged sub-phases: the N = block_n tile is spt weight slices of sub_n rows, one per sub-phase
+                                    const uint32_t sub_bytes = static_cast<uint32_t>(p.sub_n * kbk * 2);
+#pragma unroll 1
+                                    for (int j = 0; j < G; ++j)
+#pragma unroll 1
+                                        for (int s2 = 0; s2 < p.spt; ++s2)
+                                            tma_load_3d(dst0 + j * b_tile_bytes + s2 * sub_bytes, &tmB, &full_bar[stage], kc * kbk, 0,
+                                                        p.widx[(gi + j) * p.nsub + nt * p.spt + s2]);
+                                } else if (p.cluster == 2) {
                                     // this CTA fetches its half of every weight tile and multicasts it to both CTAs of the pair
 #pragma unroll 1
                                     for (int j = 0; j < G; ++j)
@@ -599,7 +610,84 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int q = warp & 3;                       // TMEM lane quarter owned by this warp
         const int row = q * 32 + lane;                // accumulator row == pixel inside the tile
         const int th = row / p.TW, tw = row % p.TW;
-        if (p.staged) {
+        if (p.staged && p.nsub > 1) {
+            // ---------------- staged epilogue, merged sub-phases: BOTH teams work on every tile, team t on the sub_n accumulator
+            // columns (= output sub-phase) t of it; each team keeps one staging set and its own residual barrier ----------------
+            const int team = (warp - 4) >> 3;
+            const int wteam = (warp - 4) & 7;
+            const bool leader = (wteam == 0 && lane == 0);
+            const int units = p.sub_n >> 4;
+            const int share = wteam >> 2;
+            const int u_begin = (units * share) / 2, u_end = (units * (share + 1)) / 2;
+            const uint32_t res_bytes = static_cast<uint32_t>(n_panels) * kATileBytes;
+            uint8_t* stage_set = smem_stage + team * n_panels * kATileBytes;
+            const uint32_t srow = smem_u32(stage_set) + static_cast<uint32_t>(row) * 128u;
+            const uint32_t sw = static_cast<uint32_t>(row & 7) << 4;
+            const int res_mode = p.res_mode;
+            const float slope = p.slope, r1s = p.r1_sign;
+            auto load_residual = [&](int tile) {
+                int nt, ph, img, oh0, ow0;
+                decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
+                const int sp = ph * p.nsub + nt * p.spt + team;
+                mbar_arrive_expect_tx(&res_full[team], res_bytes);
+                for (int pn = 0; pn < n_panels; ++pn) {
+                    const uint32_t dst = smem_u32(stage_set + pn * kATileBytes);
+                    if (p.os == 1) tma_load_4d(dst, &tmR, &res_full[team], pn * 64, ow0, oh0, img);
+                    else tma_load_5d(dst, &tmR, &res_full[team], pn * 64, p.oow[sp], ow0, p.ooh[sp], img * p.OH + oh0);
+                }
+            };
+            if (leader && res_mode && wid < p.total_tiles) load_residual(wid);
+            int local = 0;
+            for (int tile = wid; tile < p.total_tiles; tile += wstep, ++local) {
+                const int as = local & 1;
+                const uint32_t aphase = (local >> 1) & 1;
+                int nt, ph, img, oh0, ow0;
+                decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
+                const int sp = ph * p.nsub + nt * p.spt + team;
+                if (res_mode) {
+                    mbar_wait(&res_full[team], local & 1, p.err_flag, 5);
+                } else {
+                    if (leader) tma_store_wait_read<0>();       // the previous store of this team is done reading the set
+                    team_bar_sync(team);
+                }
+                const int oy = (oh0 + th) * p.os + p.ooh[sp];
+                const int ox = (ow0 + tw) * p.os + p.oow[sp];
+                int cls = 0;
+                if (p.cls_bw > 0)
+                    cls = border_class(min(oy, p.YH - 1), p.YH, p.cls_bw) * (2 * p.cls_bw + 1) +
+                          border_class(min(ox, p.YW - 1), p.YW, p.cls_bw);
+                const float* bias_u = p.bias ? p.bias + static_cast<size_t>(min(img, p.N - 1)) * p.bias_sn +
+                                                   static_cast<size_t>(cls) * p.bias_sc
+                                             : nullptr;
+                mbar_wait(&tmem_full[as], aphase, p.err_flag, 4);
+                tcgen05_fence_after();
+                const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * 256 + team * p.sub_n);
+                switch (p.act) {
+                    case CSBSR_ACT_RELU:    epilogue_staged_res<CSBSR_ACT_RELU>(res_mode, srow, sw, taddr0, u_begin, u_end, bias_u, slope, r1s); break;
+                    case CSBSR_ACT_LEAKY:   epilogue_staged_res<CSBSR_ACT_LEAKY>(res_mode, srow, sw, taddr0, u_begin, u_end, bias_u, slope, r1s); break;
+                    case CSBSR_ACT_SIGMOID: epilogue_staged_res<CSBSR_ACT_SIGMOID>(res_mode, srow, sw, taddr0, u_begin, u_end, bias_u, slope, r1s); break;
+                    default:                epilogue_staged_res<CSBSR_ACT_NONE>(res_mode, srow, sw, taddr0, u_begin, u_end, bias_u, slope, r1s); break;
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                fence_proxy_async_smem();                       // make the generic-proxy writes visible to the TMA store
+                team_bar_sync(team);
+                if (leader) {
+                    for (int pn = 0; pn < n_panels; ++pn) {
+                        const uint32_t src = smem_u32(stage_set + pn * kATileBytes);
+                        if (p.os == 1) tma_store_4d(&tmY, src, pn * 64, ow0, oh0, img);
+                        else tma_store_5d(&tmY, src, pn * 64, p.oow[sp], ow0, p.ooh[sp], img * p.OH + oh0);
+                    }
+                    tma_store_commit();
+                    if (res_mode && tile + wstep < p.total_tiles) {
+                        tma_store_wait_read<0>();
+                        load_residual(tile + wstep);
+                    }
+                }
+            }
+            if (leader) tma_store_wait_read<0>();
+        } else if (p.staged) {
             // ---------------- staged epilogue (see epilogue_staged) ----------------
             // Two teams of 8 warps; team t owns accumulator buffer t and staging set t and handles every other tile
             // of this CTA, so two tile epilogues are in flight and their latencies overlap.
@@ -813,7 +901,7 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
         CSBSR_REQUIRE(!d->r0 && !d->rm && !d->r1, "conv_igemm: bf16 residuals only with bf16 output");
     }
     CSBSR_REQUIRE(d->cout_store <= d->cout_pad, "conv_igemm: cout_store > cout_pad");
-    for (int i = 0; i < d->nphases * d->ntaps; ++i)
+    for (int i = 0; i < d->nphases * d->ntaps * (d->nsub > 1 ? d->nsub : 1); ++i)
         CSBSR_REQUIRE(d->widx[i] >= 0 && d->widx[i] < d->w_taps, "conv_igemm: widx[%d]=%d out of range", i, d->widx[i]);
 
     PFN_encodeTiled encode = get_encode_fn();
@@ -822,6 +910,13 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     ConvKParams p;
     memset(&p, 0, sizeof(p));
     int block_n = d->block_n;
+    const int nsub = d->nsub > 1 ? d->nsub : 1;
+    if (nsub > 1) {
+        CSBSR_REQUIRE(d->cout_pad == 128 && nsub % 2 == 0 && d->nphases * nsub <= CSBSR_MAX_PHASES &&
+                          d->nphases * d->ntaps * nsub <= CSBSR_MAX_TAPS && kb == kBlockK,
+                      "conv_igemm: merged sub-phases need cout_pad = 128, an even nsub and cin %% 64 == 0");
+        block_n = 256;
+    }
     const int TWh = d->ow > 8 ? 16 : 8, THh = kBlockM / TWh;
     const int os_h = d->os > 0 ? d->os : 1;
     // staged epilogue (smem panels + TMA residual load + TMA store): bf16 output, at most one residual operand,
@@ -839,8 +934,9 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
                 if (d->cout_pad % block_n == 0) break;
         }
     }
-    const bool staged = can_stage && (block_n == 64 || block_n == 128);
-    CSBSR_REQUIRE(block_n % 16 == 0 && block_n >= 16 && block_n <= 256 && d->cout_pad % block_n == 0,
+    const bool staged = can_stage && (block_n == 64 || block_n == 128 || nsub > 1);
+    CSBSR_REQUIRE(nsub == 1 || can_stage, "conv_igemm: merged sub-phases need the staged epilogue (bf16 NHWC output, whole tiles)");
+    CSBSR_REQUIRE(block_n % 16 == 0 && block_n >= 16 && block_n <= 256 && (d->cout_pad * nsub) % block_n == 0,
                   "conv_igemm: block_n=%d incompatible with cout_pad=%d", block_n, d->cout_pad);
     p.block_n = block_n;
     p.TW = d->ow > 8 ? 16 : 8;
@@ -848,13 +944,14 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     p.tiles_h = (d->oh + p.TH - 1) / p.TH;
     p.tiles_w = (d->ow + p.TW - 1) / p.TW;
     p.m_tiles = d->n * p.tiles_h * p.tiles_w;
-    p.n_tiles = d->cout_pad / block_n;
+    p.n_tiles = d->cout_pad * nsub / block_n;
+    p.nsub = nsub; p.sub_n = d->cout_pad; p.spt = nsub > 1 ? block_n / d->cout_pad : 1;
     p.nphases = d->nphases;
     // CTA pairs with multicast weight tiles: worth it when the weight tile of a stage is at least as large as the activation
     // tile (the weight stream dominates the L2 -> SM traffic) and there are enough pixel tiles to keep every pair busy
     const char* cl_env = getenv("CSBSR_CLUSTER");
     int cluster = 1;
-    if (cl_env) cluster = (atoi(cl_env) == 2 && block_n % 16 == 0 && p.m_tiles >= 2) ? 2 : 1;
+    if (cl_env) cluster = (atoi(cl_env) == 2 && block_n % 16 == 0 && p.m_tiles >= 2 && nsub == 1) ? 2 : 1;
     // cta_group::2 (CTA pairs, M = 256 per instruction, each CTA holds half of the weight rows -> smaller pipeline stages,
     // more of them in flight): measured -9..-23 % on the layers with K = taps x cin >= 1152 and at least a wave of pixel
     // tiles (8x8/s4 convs, SFT / PSP / ResNet 3x3s), +10..+40 % on short-K or tiny layers (profiles/r02_cg2_layers.md), so
@@ -864,7 +961,7 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     // CSBSR_CTA_GROUP=1 / 2 forces it off / on.
     const char* cg_env = getenv("CSBSR_CTA_GROUP");
     int cg2 = 0;
-    const bool cg2_ok = block_n % 32 == 0 && p.m_tiles >= 2;
+    const bool cg2_ok = block_n % 32 == 0 && p.m_tiles >= 2 && nsub == 1;
     if (cg_env) cg2 = (atoi(cg_env) == 2 && cg2_ok) ? 1 : 0;
     else cg2 = (cg2_ok && d->ntaps * d->cin >= 1024 && p.tiles_h * p.tiles_w >= 16) ? 1 : 0;
     if (cg2) cluster = 2;
@@ -883,13 +980,13 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     int8_t g_dh[CSBSR_MAX_TAPS], g_dw[CSBSR_MAX_TAPS];
     int16_t g_widx[CSBSR_MAX_TAPS];
     memcpy(g_dh, d->dh, sizeof(g_dh)); memcpy(g_dw, d->dw, sizeof(g_dw)); memcpy(g_widx, d->widx, sizeof(g_widx));
-    const int staging_bytes = staged ? 2 * (block_n / 64) * kATileBytes : 0;
+    const int staging_bytes = staged ? 2 * ((nsub > 1 ? d->cout_pad : block_n) / 64) * kATileBytes : 0;
     const int smem_avail = kSmemBudget - 3072 - staging_bytes;
     const int b_tile = (cg2 ? block_n / 2 : block_n) * kb * 2;      // per-CTA weight tile of one tap and K chunk
     int cand = 1, cand_groups = d->ntaps, cand_step = 0;
     int8_t n_dh[CSBSR_MAX_TAPS], n_dw[CSBSR_MAX_TAPS];
     int16_t n_widx[CSBSR_MAX_TAPS];
-    if (d->ntaps >= 2 && !getenv("CSBSR_NO_GROUPING")) {
+    if (d->ntaps >= 2 && nsub == 1 && !getenv("CSBSR_NO_GROUPING")) {
         const int st = d->stride;
         auto key_of = [&](int t) { return d->dw[t] * 64 + (((d->dh[t] % st) + st) % st); };
         bool ok = true;
@@ -967,7 +1064,7 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     p.G = G; p.ngroups = ngroups; p.dstep = dstep; p.a_stage_bytes = a_stage_bytes;
     memcpy(p.ooh, d->ooh, sizeof(p.ooh)); memcpy(p.oow, d->oow, sizeof(p.oow));
     CSBSR_REQUIRE(!d->bias || (d->bias_sn % 4 == 0 && d->bias_sc % 4 == 0), "conv_igemm: bias strides must be multiples of 4");
-    for (int ph = 0; ph < p.nphases; ++ph)
+    for (int ph = 0; ph < p.nphases * nsub; ++ph)
         CSBSR_REQUIRE((p.OH - 1) * p.os + p.ooh[ph] < p.YH && (p.OW - 1) * p.os + p.oow[ph] < p.YW && p.ooh[ph] >= 0 &&
                           p.oow[ph] >= 0,
                       "conv_igemm: phase %d writes outside the %dx%d output", ph, p.YH, p.YW);
@@ -1005,7 +1102,7 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     {
         cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)d->cout_pad, (cuuint64_t)d->w_taps};
         cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * d->cout_pad};
-        cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)(block_n / cluster), 1};
+        cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)(nsub > 1 ? d->cout_pad : block_n / cluster), 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d->wgt, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz_in, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

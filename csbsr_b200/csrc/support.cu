@@ -516,6 +516,47 @@ __global__ void bilinear_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_b
     }
 }
 
+// Exact x2 case of bilinear_nhwc_kernel (align_corners = false, OH = 2H, OW = 2W; PSPUpsample, pspnet.py:52-57): one thread
+// owns an input pixel (n, i, j) and 8 channels, reads its 3x3 neighbourhood once (9 x 16 B instead of 16 x 16 B for the four
+// outputs) and writes the 2x2 output block.  Source rows of output 2i are (i-1, i) with weight 0.75 on row i (at i = 0 the
+// clamped source gives weight 0 on the second row), of output 2i+1 (i, min(i+1, H-1)) with weight 0.25: the same indices,
+// weights and expression as bilinear_src / bilinear_nhwc_kernel, so both kernels produce identical bits.
+__global__ void __launch_bounds__(256) bilinear_x2_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                               int H, int W, int C, int xp, int xo, int yp, int yo) {
+    const int G = C >> 3;
+    const int row = blockIdx.x;                       // n * H + i
+    const int n = row / H, i = row - n * H;
+    const int e = blockIdx.y * blockDim.x + threadIdx.x;
+    if (e >= W * G) return;
+    const int j = e / G, g = e - j * G;
+    const int ra = i > 0 ? i - 1 : 0, rc = i < H - 1 ? i + 1 : i;
+    const int ca = j > 0 ? j - 1 : 0, cc = j < W - 1 ? j + 1 : j;
+    const float ly0 = i > 0 ? 0.75f : 0.f, lx0 = j > 0 ? 0.75f : 0.f;
+    const __nv_bfloat16* base = x + static_cast<size_t>(n) * H * W * xp + xo + g * 8;
+    const int rows[3] = {ra, i, rc}, cols[3] = {ca, j, cc};
+    float v[3][3][8];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<size_t>(rows[r]) * W + cols[c]) * xp), v[r][c]);
+    __nv_bfloat16* out = y + (static_cast<size_t>(n) * 2 * H + 2 * i) * (2 * static_cast<size_t>(W)) * yp + static_cast<size_t>(2 * j) * yp + yo + g * 8;
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+        const float ly = py ? 0.25f : ly0;
+#pragma unroll
+        for (int px = 0; px < 2; ++px) {
+            const float lx = px ? 0.25f : lx0;
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                o[k] = (1.f - ly) * ((1.f - lx) * v[py][px][k] + lx * v[py][px + 1][k]) +
+                       ly * ((1.f - lx) * v[py + 1][px][k] + lx * v[py + 1][px + 1][k]);
+            *reinterpret_cast<uint4*>(out + (static_cast<size_t>(py) * 2 * W + px) * yp) = pack8(o);
+        }
+    }
+}
+
 // y = [relu](base + bilinear(x)): branch fusion of HighResolutionModule.forward (hrnet_backbone.py:274-288)
 __global__ void bilinear_add_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ base,
                                          __nv_bfloat16* __restrict__ y, int N, int H, int W, int OH, int OW, int C, int xp,
@@ -768,6 +809,14 @@ extern "C" int csbsr_bilinear_nhwc(const void* x, void* y, int n, int h, int w, 
     CSBSR_REQUIRE(x && y && c % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && x_coff % 8 == 0 && y_coff % 8 == 0,
                   "bilinear_nhwc: channel counts/offsets must be multiples of 8");
     const size_t total = static_cast<size_t>(n) * oh * ow * (c / 8);
+    if (!align_corners && oh == 2 * h && ow == 2 * w && h > 1 && w > 1) {
+        const dim3 grid(static_cast<unsigned>(n) * h, (static_cast<unsigned>(w) * (c / 8) + 255) / 256);
+        bilinear_x2_nhwc_kernel<<<grid, 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                 reinterpret_cast<__nv_bfloat16*>(y), h, w, c, x_pitch, x_coff,
+                                                                 y_pitch, y_coff);
+        CSBSR_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     bilinear_nhwc_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), n, h, w, oh, ow, c, x_pitch,
         x_coff, y_pitch, y_coff, align_corners);

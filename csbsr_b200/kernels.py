@@ -4,6 +4,7 @@ Activations live in HBM as NHWC bf16 "feature maps" (`Fmap`): a [N,H,W,P] tensor
 window, so that the reference's torch.cat calls (kbpn.py:173-186) become writes into channel slices.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -199,11 +200,24 @@ def conv(x, pc, y, oh=None, ow=None, bias=None, bias_sn=0, bias_sc=0, cls_bw=0, 
     d.wgt = pc.wp.data_ptr()
     d.w_taps, d.cout_pad = pc.wp.shape[0], pc.cout_pad
     d.nphases, d.ntaps, d.stride = pc.nphases, pc.ntaps, pc.stride
-    for i, (dh, dw, wi) in enumerate(pc.taps):
-        d.dh[i], d.dw[i], d.widx[i] = dh, dw, wi
     d.os = pc.os
-    for i in range(pc.nphases):
-        d.ooh[i], d.oow[i] = pc.ooh[i], pc.oow[i]
+    merged = _deconv_merge_ok(x, pc, y, rm, r0, r1, oh, ow)
+    if merged:
+        # 8x8 / stride-4 transposed conv as 4 tap classes x 4 sub-phases: the sub-phases of a class share their 2x2 input
+        # taps, so two of them form one N = 256 tile on one A operand (csbsr_conv_desc.nsub)
+        taps_c, widx_c, ooh_c, oow_c = _DECONV_MERGED
+        d.nphases, d.nsub = 4, 4
+        for i, (dh, dw) in enumerate(taps_c):
+            d.dh[i], d.dw[i] = dh, dw
+        for i, wi in enumerate(widx_c):
+            d.widx[i] = wi
+        for i in range(16):
+            d.ooh[i], d.oow[i] = ooh_c[i], oow_c[i]
+    else:
+        for i, (dh, dw, wi) in enumerate(pc.taps):
+            d.dh[i], d.dw[i], d.widx[i] = dh, dw, wi
+        for i in range(pc.nphases):
+            d.ooh[i], d.oow[i] = pc.ooh[i], pc.oow[i]
     if isinstance(y, Fmap):
         d.out_mode = OUT_BF16_NHWC
         d.yh, d.yw = y.h, y.w
@@ -401,6 +415,45 @@ def pack_deconv8s4_train(weight, bias=None, cin_pad=None, cout_pad=None):
     wp = _pack_device(w, cout_pad, cin_pad, 2)
     taps, ooh, oow = _DECONV_TAPS
     return PackedConv(wp, taps, 16, 4, 1, 4, ooh, oow, cout, _pad_bias(bias, cout_pad, w.device), macs_per_pixel=4 * cin * cout)
+
+
+def _deconv_merged_tables():
+    """Tap classes of the 8x8 / stride-4 / pad-2 transposed conv (see pack_deconv8s4): class (a, b) = output phases with
+    rh in {2a, 2a+1}, rw in {2b, 2b+1}; sub-phase s = (rh % 2) * 2 + (rw % 2).  -> (taps [(dh, dw)] per class and tap,
+    widx [(class * 4 + tap) * 4 + s], ooh / oow [class * 4 + s])."""
+    def axis_taps(rho):
+        return [(-1, rho + 6), (0, rho + 2)] if rho < 2 else [(0, rho + 2), (1, rho - 2)]
+    taps, widx, ooh, oow = [], [], [], []
+    for a in range(2):
+        for b in range(2):
+            for ti in range(2):
+                for tj in range(2):
+                    taps.append((axis_taps(2 * a)[ti][0], axis_taps(2 * b)[tj][0]))
+                    for s in range(4):
+                        rh, rw = 2 * a + s // 2, 2 * b + s % 2
+                        assert axis_taps(rh)[ti][0] == taps[-1][0] and axis_taps(rw)[tj][0] == taps[-1][1]
+                        widx.append(axis_taps(rh)[ti][1] * 8 + axis_taps(rw)[tj][1])
+            for s in range(4):
+                ooh.append(2 * a + s // 2)
+                oow.append(2 * b + s % 2)
+    return taps, widx, ooh, oow
+
+
+_DECONV_MERGED = _deconv_merged_tables()
+DECONV_MERGE = os.environ.get("CSBSR_DECONV_MERGE") == "1"
+
+
+def _deconv_merge_ok(x, pc, y, rm, r0, r1, oh, ow):
+    """The merged form needs the staged epilogue: bf16 NHWC output covering whole 128-pixel tiles, at most one residual."""
+    if not (DECONV_MERGE and pc.nphases == 16 and pc.ntaps == 4 and pc.os == 4 and pc.cout_pad == 128 and isinstance(y, Fmap)):
+        return False
+    if pc.taps is not _DECONV_TAPS[0] and list(pc.taps) != list(_DECONV_TAPS[0]):
+        return False
+    if pc.cin_pad % 64 != 0 or rm is not None or (r0 is not None and r1 is not None):
+        return False
+    ih, iw = (oh, ow) if oh is not None else (x.h, x.w)
+    th = 8 if iw > 8 else 16
+    return y.h == 4 * ih and y.w == 4 * iw and ih % th == 0 and ih == x.h and iw == x.w
 
 
 def _deconv_taps():

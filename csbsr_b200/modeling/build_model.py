@@ -39,7 +39,7 @@ class JointModel(nn.Module):
         else:
             self.segmentation_model = ParamTree(pspnet_param_shapes(cfg.MODEL.NUM_CLASSES, blur_dim=blur_dim))
         self.sr_model = ParamTree(kbpn_param_shapes(self.num_stages, 128, self.blur_ksize, self.ksize))
-        self.chunk = 8                      # images per pass through KBPN (activation working set)
+        self.chunk = 16                     # images per pass through KBPN (activation working set; 16 fills whole waves of CTA pairs)
         self.seg_chunk = 32                 # images per pass through the segmentation net
         self._engines = None
         self._packed_version = None

@@ -80,6 +80,12 @@ typedef struct csbsr_conv_desc {
     /* out_mode 1: y / r32 are channel windows [coff, coff+cout_store) of planar buffers with `pitch` channels
      * (y_pitch / y_coff above and r32_pitch / r32_coff; pitch 0 = exactly cout_store channels) */
     int32_t r32_pitch, r32_coff;
+    /* nsub > 1: every phase p is a TAP CLASS shared by `nsub` output sub-phases (the 8x8 stride-4 transposed conv has 4
+     * classes of 4 sub-phases: the output phases whose rows / columns are both in {0,1} or {2,3} read the same 2x2 input
+     * taps).  The sub-phases of a class are evaluated by ONE GEMM with N = 2 * cout_pad (two sub-phases per tile share the
+     * A operand): widx is indexed [(p * ntaps + t) * nsub + s], ooh / oow [p * nsub + s]; cout_pad must be 128, the output
+     * bf16 NHWC with whole tiles per image.  0 / 1: plain phases (one weight slice per tap). */
+    int32_t nsub;
 } csbsr_conv_desc;
 
 int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream);

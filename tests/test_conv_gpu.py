@@ -82,6 +82,48 @@ def test_deconv8s4_matches_torch():
     _check(y.to_nchw_f32(cout), ref)
 
 
+@pytest.mark.parametrize("n,cin,h,w,res,act", [(2, 128, 16, 32, None, False), (3, 128, 8, 24, "r1", True), (1, 64, 16, 8, "r1m", True),
+                                               (2, 192, 24, 40, "r0", True), (2, 128, 16, 16, "bias", True)])
+def test_deconv8s4_merged_subphases(n, cin, h, w, res, act, monkeypatch):
+    """The merged form of the 8x8 / stride-4 transposed conv (4 tap classes x 4 sub-phases, N = 256 tiles, both epilogue
+    teams on every tile; csbsr_conv_desc.nsub) against torch and against the 16-phase form (same products; the taps are
+    accumulated in a different order, so single bf16 roundings may differ)."""
+    from csbsr_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(12)
+    cout = 128
+    x = _bf(torch.randn(n, cin, h, w, device="cuda", generator=g))
+    wt = _bf(torch.randn(cin, cout, 8, 8, device="cuda", generator=g) / (cin * 4) ** 0.5)
+    bias = torch.randn(cout, device="cuda", generator=g) if res == "bias" else None
+    r = _bf(torch.randn(n, cout, 4 * h, 4 * w, device="cuda", generator=g)) if res in ("r0", "r1", "r1m") else None
+    ref = F.conv_transpose2d(x, wt, bias, stride=4, padding=2)
+    if res == "r0":
+        ref = ref + r
+    if act:
+        ref = F.leaky_relu(ref, 0.1)
+    if res == "r1":
+        ref = ref + r
+    if res == "r1m":
+        ref = ref - r
+    pc = K.pack_deconv8s4(wt, bias)
+    kw = dict(act=K.ACT_LEAKY if act else K.ACT_NONE, slope=0.1)
+    if res == "r0":
+        kw["r0"] = K.Fmap.from_nchw(r)
+    if res in ("r1", "r1m"):
+        kw["r1"] = K.Fmap.from_nchw(r)
+        kw["r1_sign"] = 1.0 if res == "r1" else -1.0
+    xf = K.Fmap.from_nchw(x)
+    monkeypatch.setattr(K, "DECONV_MERGE", True)        # opt-in (CSBSR_DECONV_MERGE=1): measured no faster than 16 phases
+    assert K._deconv_merge_ok(xf, pc, K.Fmap.empty(n, 4 * h, 4 * w, cout), None, kw.get("r0"), kw.get("r1"), None, None)
+    y = K.conv(xf, pc, K.Fmap.empty(n, 4 * h, 4 * w, cout), **kw)
+    torch.cuda.synchronize()
+    _check(y.to_nchw_f32(cout), ref)
+    monkeypatch.setattr(K, "DECONV_MERGE", False)
+    y16 = K.conv(xf, pc, K.Fmap.empty(n, 4 * h, 4 * w, cout), **kw)
+    torch.cuda.synchronize()
+    a, b = y.t.float(), y16.t.float()
+    assert (a - b).abs().max().item() <= 2 ** -7 * ref.abs().max().item() and (a != b).float().mean().item() < 0.05
+
+
 def test_epilogue_variants():
     from csbsr_b200 import kernels as K
     g = torch.Generator(device="cuda").manual_seed(3)

@@ -224,6 +224,18 @@ def test_deconv_phase_decomposition_matches_conv_transpose():
             patch = xp[:, :, 1 + dh:1 + dh + 6, 1 + dw:1 + dw + 9]
             out[:, :, pc.ooh[ph]::4, pc.oow[ph]::4] += torch.einsum("oc,bchw->bohw", wp[wi], patch)
     assert (out - ref).abs().max().item() < 0.05 * ref.abs().max().item()        # bf16-rounded weights
+    # merged form (csbsr_conv_desc.nsub = 4): 4 tap classes, every sub-phase of a class reads the class's 2x2 input taps
+    taps_c, widx_c, ooh_c, oow_c = K._DECONV_MERGED
+    out2 = torch.zeros_like(ref)
+    for cl in range(4):
+        for t in range(4):
+            dh, dw = taps_c[cl * 4 + t]
+            patch = xp[:, :, 1 + dh:1 + dh + 6, 1 + dw:1 + dw + 9]
+            for sp in range(4):
+                out2[:, :, ooh_c[cl * 4 + sp]::4, oow_c[cl * 4 + sp]::4] += torch.einsum(
+                    "oc,bchw->bohw", wp[widx_c[(cl * 4 + t) * 4 + sp]], patch)
+    assert sorted(zip(ooh_c, oow_c)) == sorted((a, b) for a in range(4) for b in range(4))
+    assert torch.equal(out2, out) or (out2 - out).abs().max().item() < 1e-5 * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("variant", ["pspnet", "pspnet_bneval", "hrnet_bneval", "blurskip_bneval", "it5", "it15000", "it25000"])
