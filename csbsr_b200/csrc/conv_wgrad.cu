@@ -393,10 +393,28 @@ static int wg_plan(const csbsr_wgrad_desc* d, WgradParams& p) {
     p.passes_per_m = (p.units_total + p.upp - 1) / p.upp;
     p.npass = m_tiles * p.passes_per_m;
     const int sms = num_sms();
-    // one work item per SM (the accumulators are single-buffered, so a second item per SM cannot overlap anyway), and every
-    // split costs one more pass over the output in the epilogue stores and in the reduction.  CSBSR_WGRAD_ITEMS_PER_SM overrides.
-    static const int items_per_sm = getenv("CSBSR_WGRAD_ITEMS_PER_SM") ? atoi(getenv("CSBSR_WGRAD_ITEMS_PER_SM")) : 1;
-    int nsplit = (items_per_sm * sms + p.npass - 1) / p.npass;
+    // Pixel splits: the work items (pass, split) are dealt round-robin to one CTA per SM and all cost the same, so the launch
+    // takes rounds = ceil(items / SMs) items of tiles_per_split pipeline stages plus one accumulator drain each (the
+    // accumulators are single-buffered).  Choose the split count that minimises rounds * (stages + drain): rounding the
+    // items per SM UP (round 1: 160 items on 148 SMs for the 8x8/s4 layers) made 12 SMs work twice while the rest idled --
+    // 54 % efficiency on those layers.  Every split also costs one more pass over the output in the reduction.
+    // CSBSR_WGRAD_ITEMS_PER_SM forces the old rule (items = that many per SM, rounded up).
+    static const int items_per_sm = getenv("CSBSR_WGRAD_ITEMS_PER_SM") ? atoi(getenv("CSBSR_WGRAD_ITEMS_PER_SM")) : 0;
+    int nsplit = 1;
+    if (items_per_sm > 0) {
+        nsplit = (items_per_sm * sms + p.npass - 1) / p.npass;
+    } else {
+        const int drain = 2 + (p.upp * p.unit_cols) / 64;          // accumulator drain of one item, in pipeline stages (measured order)
+        long long best = -1;
+        const int ns_max = 4 * sms / p.npass + 2;
+        for (int ns = 1; ns <= ns_max && ns <= p.ptiles; ++ns) {
+            const int tps = (p.ptiles + ns - 1) / ns;
+            const int ns_eff = (p.ptiles + tps - 1) / tps;
+            const int rounds = (p.npass * ns_eff + sms - 1) / sms;
+            const long long cost = static_cast<long long>(rounds) * (tps + drain) * 16 + ns_eff * 4;   // + reduction passes
+            if (best < 0 || cost < best) { best = cost; nsplit = ns_eff; }
+        }
+    }
     if (nsplit > p.ptiles) nsplit = p.ptiles;
     if (nsplit < 1) nsplit = 1;
     p.tiles_per_split = (p.ptiles + nsplit - 1) / nsplit;
