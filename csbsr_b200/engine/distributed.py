@@ -71,3 +71,57 @@ def allreduce_flat(flat, bucket_elems=1 << 25, group=None):
     for s in range(0, flat.numel(), bucket_elems):
         dist.all_reduce(flat[s:s + bucket_elems], op=dist.ReduceOp.SUM, group=group)
     return ws
+
+
+class OverlappedGradAllReduce:
+    """SUM all-reduce of the flat gradient buffer in two parts: the segmentation net's slice [lo, hi) is launched (async, on
+    NCCL's own stream) from an autograd hook the moment its backward is complete and runs under the backward of the SR net;
+    the rest follows when backward returns.  Inside a CUDA-graph capture both become nodes of the graph (fork / join through
+    the events ProcessGroupNCCL records), so a replay contains the exchange.  Falls back to one all-reduce of the whole
+    buffer when the hook did not fire (segmentation net frozen / evaluated without a tape) or `span` is None."""
+
+    def __init__(self, flat, span, bucket_elems=1 << 25, group=None):
+        self.flat, self.span, self.bucket, self.group = flat, span, bucket_elems, group
+        self.works = []
+
+    @staticmethod
+    def prefix_span(named_params, opt_params, slots, prefix="segmentation_model."):
+        """(first element, one past the last element) of the `prefix` parameters in the flat buffer if their slots are
+        contiguous and something else is left, else None."""
+        index = {id(p): i for i, p in enumerate(opt_params)}
+        idx = sorted(index[id(p)] for n, p in named_params if n.startswith(prefix) and id(p) in index)
+        if not idx or idx != list(range(idx[0], idx[-1] + 1)) or len(idx) == len(opt_params):
+            return None
+        return slots[idx[0]][0], slots[idx[-1]][0] + slots[idx[-1]][1]
+
+    def _active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _reduce(self, lo, hi, async_op):
+        out = []
+        for s in range(lo, hi, self.bucket):
+            w = dist.all_reduce(self.flat[s:min(hi, s + self.bucket)], op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+            if async_op:
+                out.append(w)
+        return out
+
+    def seg_done(self):
+        if self.span is None or self.works or not self._active():
+            return
+        self.works = self._reduce(self.span[0], self.span[1], True)
+
+    def finish(self):
+        """All-reduce what is still local, then join the async part.  Returns the world size."""
+        if not self._active():
+            self.works = []
+            return 1
+        n = self.flat.numel()
+        if self.works:
+            self._reduce(0, self.span[0], False)
+            self._reduce(self.span[1], n, False)
+        else:
+            self._reduce(0, n, False)
+        for w in self.works:
+            w.wait()
+        self.works = []
+        return dist.get_world_size(self.group)

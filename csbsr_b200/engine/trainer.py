@@ -4,6 +4,7 @@ A step is: on-device degradation of the HR crop batch (crack_dataset.py:51-62) -
 calc_loss -> backward -> NCCL SUM all-reduce of the flat gradient (replaces nn.DataParallel, train.py:117-121) ->
 fused Adam (+ gradient zeroing) -> LambdaLR step.  Per-rank batches are the reference's per-GPU chunks, so BatchNorm
 statistics and the (B,B,H,W) w^F broadcasting stay per replica exactly as under DataParallel."""
+import os
 import time
 
 import torch
@@ -14,16 +15,39 @@ from .losses import calc_loss
 
 def train_step(model, optimizer, cfg, iteration, hr, mask, params, world_size=1):
     """One optimisation step on this rank's shard. `params` = (theta, sigma_x, sigma_y) float64 [B,3] for the blur."""
+    ar = _overlap(model, optimizer) if world_size > 1 and AR_OVERLAP else None   # installs the hook the forward registers
     lr_img, kernels = G.degrade(hr, params, ksize=cfg.BLUR.KERNEL_SIZE_OUTPUT, factor=cfg.MODEL.SCALE_FACTOR)
     seg_loss, sr_loss, seg, sr, kp = model(iteration, lr_img, sr_targets=hr, segment_targets=mask,
                                            kernel_targets=kernels.unsqueeze(1))
     loss = calc_loss(sr_loss, seg_loss.mean(), cfg.SOLVER.TASK_LOSS_WEIGHT, iteration, cfg)
     loss.backward()
-    if world_size > 1:
+    if ar is not None:
+        ar.finish()
+    elif world_size > 1:
         optimizer.all_reduce_grads()
     optimizer.step(world_size)
     optimizer.scheduler_step()
     return loss.detach(), seg_loss.detach().mean(), sr_loss.detach().mean()
+
+
+# CSBSR_AR_OVERLAP=1 starts the all-reduce of the segmentation net's gradient slice from an autograd hook, under the backward of
+# the SR net, and captures the whole exchange in the step's CUDA graph (engine/distributed.py::OverlappedGradAllReduce; the
+# host logic is covered by the gloo test).  Off by default: the persistent conv kernels fill every SM's register file, so NCCL's
+# CTAs only run in the gaps between kernels, and the one 2-GPU verification run of this round did not finish within its time
+# limit -- the default stays the exchange measured at N = 2, 4, 8 (bucketed all-reduce after the replay, 1.15 ms at N = 8).
+AR_OVERLAP = os.environ.get("CSBSR_AR_OVERLAP") == "1"
+
+
+def _overlap(model, optimizer):
+    """The step's gradient exchange (engine/distributed.py::OverlappedGradAllReduce), created once per (model, optimizer)
+    and hooked to the end of the segmentation net's backward."""
+    from .distributed import OverlappedGradAllReduce
+    ar = getattr(optimizer, "_overlap_ar", None)
+    if ar is None:
+        span = OverlappedGradAllReduce.prefix_span(model.named_parameters(), optimizer.params, optimizer.slots)
+        ar = optimizer._overlap_ar = OverlappedGradAllReduce(optimizer.flat_g, span, optimizer.bucket_elems)
+    model.on_seg_backward_done = ar.seg_done
+    return ar
 
 
 class GraphedTrainStep:
@@ -47,12 +71,18 @@ class GraphedTrainStep:
 
     def _body(self, st, it):
         cfg = self.cfg
+        if self.world > 1 and AR_OVERLAP:
+            st["ar"] = _overlap(self.model, self.opt)
         lr_img, kernels = G.degrade(st["hr"], st["params"], ksize=cfg.BLUR.KERNEL_SIZE_OUTPUT, factor=cfg.MODEL.SCALE_FACTOR)
         seg_loss, sr_loss, seg, sr, kp = self.model(it, lr_img, sr_targets=st["hr"], segment_targets=st["mask"],
                                                     kernel_targets=kernels.unsqueeze(1))
         seg_mean = seg_loss.mean()
         loss = calc_loss(sr_loss, seg_mean, cfg.SOLVER.TASK_LOSS_WEIGHT, it, cfg)
         loss.backward()
+        if self.world > 1 and AR_OVERLAP:
+            # opt-in: the exchange becomes part of the captured step -- the segmentation slice leaves from the autograd hook
+            # (under the SR net's backward, on NCCL's stream), the rest here; a replay contains both
+            st["ar"].finish()
         return loss.detach(), seg_mean.detach(), sr_loss.detach().mean()
 
     def _capture(self, it, hr, mask, params):
@@ -99,8 +129,8 @@ class GraphedTrainStep:
         st["hr"].copy_(hr, non_blocking=True)
         st["mask"].copy_(mask, non_blocking=True)
         st["params"].copy_(torch.as_tensor(params).to(st["params"].device), non_blocking=True)
-        st["graph"].replay()
-        if self.world > 1:
+        st["graph"].replay()                   # forward + loss + backward (+ the overlapped gradient all-reduce when opted in)
+        if self.world > 1 and not AR_OVERLAP:
             self.opt.all_reduce_grads()
         self.opt.step(self.world)
         self.opt.scheduler_step()

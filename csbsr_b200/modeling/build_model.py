@@ -211,6 +211,12 @@ class JointModelWithLoss(JointModel):
             with torch.set_grad_enabled(torch.is_grad_enabled() and not sr_only):
                 from .. import glue as G
                 normed = G.instance_norm(sr, eps=1e-5)                            # norm_sr, build_model.py:135-137
+                # every segmentation-net layer is downstream of `normed`: when its gradient arrives, all of their backward
+                # kernels (weight gradients folded into the flat buffer) are enqueued -- the trainer starts the NCCL
+                # all-reduce of that part of the gradient here, under the backward of the SR net (engine/trainer.py)
+                cb = getattr(self, "on_seg_backward_done", None)
+                if cb is not None and normed.requires_grad and self.seg_model_name != "PSPNet_BlurSkip":
+                    normed.register_hook(lambda g_, cb=cb: cb())
                 drop = None
                 if self.dropout and self.training:
                     if getattr(self, "_drop_state", None) is None or self._drop_state.counter.device != device:

@@ -89,3 +89,55 @@ def test_gradient_allreduce_is_mean_over_ranks():
         assert p.exitcode == 0
     ref = sum(torch.randn(1000, generator=torch.Generator().manual_seed(100 + r)) for r in range(2)) / 2
     assert ws == 2 and np.allclose(got, ref.numpy(), rtol=0, atol=1e-7)
+
+
+def _overlap_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from csbsr_b200.engine import distributed as D
+    out = []
+    for fire in (True, False):                                      # hook fired / segmentation net without a tape
+        g = torch.Generator().manual_seed(200 + rank)
+        flat = torch.randn(1000, generator=g)
+        ar = D.OverlappedGradAllReduce(flat, (300, 700), bucket_elems=256)
+        if fire:
+            ar.seg_done()                                           # the slice [300, 700) leaves first (async) ...
+            ar.seg_done()                                           # ... and only once
+            assert len(ar.works) == 2
+        ws = ar.finish()                                            # ... then [0, 300) and [700, 1000); join
+        assert ar.works == []
+        out.append((ws, flat.numpy().copy()))
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_gradient_allreduce_matches_plain_sum():
+    """OverlappedGradAllReduce (segmentation slice from the autograd hook, SR slice after backward) == SUM over ranks of the
+    whole flat gradient, with and without the hook firing; prefix_span finds the segmentation slice of the flat buffer."""
+    from csbsr_b200.engine import distributed as D
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29300 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = sum(torch.randn(1000, generator=torch.Generator().manual_seed(200 + r)) for r in range(2)).numpy()
+    for ws, got in out:
+        assert ws == 2 and np.allclose(got, ref, rtol=0, atol=1e-6)
+    ps = [torch.nn.Parameter(torch.zeros(3)) for _ in range(5)]
+    named = [("sr_model.a", ps[0]), ("sr_model.b", ps[1]), ("segmentation_model.c", ps[2]), ("segmentation_model.d", ps[3]),
+             ("segmentation_model.e", ps[4])]
+    slots = [(0, 4), (4, 4), (8, 4), (12, 4), (16, 4)]
+    span = D.OverlappedGradAllReduce.prefix_span
+    assert span(named, ps, slots) == (8, 20)
+    assert span([("segmentation_model.x", ps[0]), ("segmentation_model.y", ps[1]), ("sr_model.z", ps[2])], ps[:3], slots[:3]) == (0, 8)
+    assert span(named, [ps[2], ps[0], ps[3], ps[1], ps[4]], slots) is None      # not contiguous
+    assert span(named[2:], ps[2:], slots[:3]) is None                          # nothing else in the buffer
