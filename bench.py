@@ -240,6 +240,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--chunk", type=int, default=16, help="images per pass through the KBPN engine (measured: 8 -> 434, 16 -> 447, 32 -> 447 img/s)")
+    ap.add_argument("--seg-chunk", type=int, default=0, help="images per pass through the segmentation engine (0 = the model's default)")
+    ap.add_argument("--mchunk", type=int, default=16, help="images per csbsr_seg_metrics call")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE metric part 2)")
@@ -289,6 +291,8 @@ def main():
         model.load_state_dict(sd_, strict=True)
         args.no_train = True                      # the training leg is the PSPNet config (#3)
     model.chunk = args.chunk
+    if args.seg_chunk > 0:
+        model.seg_chunk = args.seg_chunk
 
     # synthetic inputs: a few distinct images tiled to the batch (generation is untimed); each rank its own shard
     n_unique = min(B, 16)
@@ -299,7 +303,7 @@ def main():
     params = synth.degradation_params(B, seed=5 + rank)
     hr_dev, mask_dev = hr_host.to(dev), mask_host.to(dev)
     params_dev = torch.as_tensor(params).to(dev)
-    mchunk = 16
+    mchunk = args.mchunk
 
     keep = {}
 
@@ -350,15 +354,21 @@ def main():
     def step_device():
         return gather(run_hot_path(graph_state["hr"], graph_state["mask"]))
 
+    # end-to-end leg: every step's inputs come from pinned host memory through the repo's prefetcher (data/prefetch.py: the copy
+    # of the next step's batch runs on its own stream under the current step, like a DataLoader with pin_memory feeding the
+    # reference's loop), and every step's result is read back to the host
+    from csbsr_b200.data.prefetch import DevicePrefetcher
+
+    def host_batches():
+        while True:
+            yield (hr_host, mask_host)
+    e2e_state = {"it": None}
+
     def step_e2e():
-        if graph_state["graph"] is not None:                    # H2D straight into the graph's static input buffers
-            graph_state["hr"].copy_(hr_host, non_blocking=True)
-            graph_state["mask"].copy_(mask_host, non_blocking=True)
-            res = gather(run_hot_path(graph_state["hr"], graph_state["mask"])).cpu().numpy()
-        else:
-            hr = hr_host.to(dev, non_blocking=True)
-            mask = mask_host.to(dev, non_blocking=True)
-            res = gather(hot_path(hr, mask)).cpu().numpy()
+        if e2e_state["it"] is None:
+            e2e_state["it"] = DevicePrefetcher(host_batches(), dev)
+        hr, mask = next(e2e_state["it"])
+        res = gather(run_hot_path(hr, mask)).cpu().numpy()
         inter, union, hd = res[:, :99], res[:, 99:198], res[:, 198:297]
         iou = (inter + 1e-5) / (union + 1e-5)
         return float(np.mean(iou)), float(np.mean(hd))     # AIU, AHD (inference.py:171-173)
@@ -446,7 +456,7 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "CSBSR w/ " + args.detector + " x4 eval (config_csbsr_pspnet.yaml), batch %d x 448^2 HR per GPU, on-the-fly "
                                "anisotropic-blur degradation, AIU + HD(p50)/MSD sweep over 99 thresholds" % B,
-                   "batch_per_gpu": B, "chunk": args.chunk, "hr": HR, "scale": 4, "weights": "synthetic random-init (seed 1121)",
+                   "batch_per_gpu": B, "chunk": args.chunk, "seg_chunk": model.seg_chunk, "metrics_chunk": mchunk, "hr": HR, "scale": 4, "weights": "synthetic random-init (seed 1121)",
                    "l2": "per-step inputs (%.0f MB) and activations exceed the 126 MB L2; no flush needed" % (h2d / 1e6),
                    "aiu": aiu, "ahd_p50": ahd,
                    "parity_check": "I/U counts of all %d images and HD/MSD of image 0 bit-equal to the oracle sweep: %s" % (B, parity),

@@ -227,3 +227,14 @@ def test_patch_split_join_and_crop_flip_vs_oracle(tmp_path):
     back = np.asarray(Image.open(tmp_path / "images" / "a.png"))
     assert back.shape == (224, 224, 3) and np.array_equal(back, (out[0] * 255).byte().permute(1, 2, 0).numpy())
     assert (tmp_path / "masks" / "th_0.50" / "b.png").exists() and (tmp_path / "kernels_origin" / "b_0_origin.png").exists()
+
+
+def test_device_prefetcher_order_and_contents():
+    """data/prefetch.py: batches arrive in order with the right contents while the next copy is already in flight."""
+    from csbsr_b200.data.prefetch import DevicePrefetcher
+    host = [(torch.full((3, 64, 64), float(i)).pin_memory(), torch.arange(16, dtype=torch.int32).add(i).pin_memory()) for i in range(5)]
+    got = []
+    for a, b in DevicePrefetcher(iter(host), torch.device("cuda", 0)):
+        x = a * 2.0                                    # some work on the current stream that reads the buffers
+        got.append((x.sum().item(), int(b[0].item())))
+    assert got == [(2.0 * i * 3 * 64 * 64, i) for i in range(5)]
