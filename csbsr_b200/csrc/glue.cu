@@ -226,6 +226,41 @@ __global__ void bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_b
     }
 }
 
+// Exact x2 case (align_corners = false, OH = 2H, OW = 2W: the PSPUpsample blocks, pspnet.py:52-57): along each axis input i
+// receives from outputs 2i-1 (0.25), 2i (0.75; 1 at i = 0, where the clamped source puts all weight on row 0), 2i+1 (0.75; 1 at
+// i = H-1, both taps on the last row) and 2i+2 (0.25) -- the same weights, products and summation order as the generic kernel,
+// without its per-candidate weight evaluation and 64-bit index arithmetic.  Block = one input row.
+__global__ void __launch_bounds__(256) bilinear_x2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
+                                                              int H, int W, int C, int gp, int go, int xp, int xo) {
+    const int G = C >> 3;
+    const int row = blockIdx.x;                       // n * H + iy
+    const int n = row / H, iy = row - n * H;
+    const int e = blockIdx.y * blockDim.x + threadIdx.x;
+    if (e >= W * G) return;
+    const int ix = e / G, g = e - ix * G;
+    const int OW = 2 * W;
+    const __nv_bfloat16* base = dy + static_cast<size_t>(n) * (2 * H) * OW * gp + go + g * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int oy = 2 * iy - 1 + a;
+        if (oy < 0 || oy >= 2 * H) continue;
+        const float wy = (a == 0 || a == 3) ? 0.25f : ((a == 1 && iy == 0) || (a == 2 && iy == H - 1)) ? 1.f : 0.75f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int ox = 2 * ix - 1 + b;
+            if (ox < 0 || ox >= OW) continue;
+            const float wx = (b == 0 || b == 3) ? 0.25f : ((b == 1 && ix == 0) || (b == 2 && ix == W - 1)) ? 1.f : 0.75f;
+            const float w = wy * wx;
+            float f[8];
+            g_unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<size_t>(oy) * OW + ox) * gp), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, f[j], acc[j]);
+        }
+    }
+    *reinterpret_cast<uint4*>(dx + (static_cast<size_t>(row) * W + ix) * xp + xo + g * 8) = g_pack8(acc);
+}
+
 // ------------------------------------------------------------------ adaptive average pool backward
 // bin o covers [floor(o*H/S), ceil((o+1)*H/S)); dx[ih, iw] = sum over covering bins of dy[bin] / npix(bin)
 __global__ void adaptive_avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int H,
@@ -653,6 +688,12 @@ extern "C" int csbsr_bilinear_nhwc_bwd(const void* dy, void* dx, int n, int h, i
     CSBSR_REQUIRE(dy && dx && c % 8 == 0 && dy_pitch % 8 == 0 && dx_pitch % 8 == 0 && dy_coff % 8 == 0 && dx_coff % 8 == 0,
                   "bilinear_nhwc_bwd: channel counts/offsets must be multiples of 8");
     const size_t total = static_cast<size_t>(n) * h * w * (c / 8);
+    if (!align_corners && oh == 2 * h && ow == 2 * w && h > 1 && w > 1) {
+        const dim3 grid(static_cast<unsigned>(n) * h, (static_cast<unsigned>(w) * (c / 8) + 255) / 256);
+        bilinear_x2_bwd_kernel<<<grid, 256, 0, STREAM(stream)>>>(CBF(dy), BF(dx), h, w, c, dy_pitch, dy_coff, dx_pitch, dx_coff);
+        CSBSR_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     bilinear_bwd_kernel<<<glue_grid(total, 256), 256, 0, STREAM(stream)>>>(CBF(dy), BF(dx), n, h, w, oh, ow, c, dy_pitch, dy_coff,
                                                                           dx_pitch, dx_coff, align_corners);
     CSBSR_CHECK_CUDA(cudaGetLastError());
