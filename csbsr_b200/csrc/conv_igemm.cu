@@ -81,6 +81,8 @@ struct ConvKParams {
                          // A tiles, every CTA holds half of the weight rows (no multicast), TMA bytes land on the leader's barriers
     int nsub, spt, sub_n;   // merged sub-phases (csbsr_conv_desc.nsub): nsub per tap class, spt = block_n / sub_n of them per tile,
                             // sub_n = cout_pad columns each; the two epilogue teams then split every tile by sub-phase
+    int res_sets;        // staged epilogue with a residual: staging sets per team (2 = the residual tile of the team's next tile is
+                         // fetched while the current one is processed; 1 when shared memory does not allow it)
     int staged;          // 1: epilogue through swizzled smem panels, residual via TMA load, output via TMA store
     int res_mode;        // staged only: 0 none, 1 pre-activation add (r0), 2 post-activation add/sub (r1)
     int8_t dh[CSBSR_MAX_TAPS], dw[CSBSR_MAX_TAPS];
@@ -383,12 +385,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t* smem_b = smem + p.stages * p.a_stage_bytes;
     const int n_panels = (p.nsub > 1 ? p.sub_n : p.block_n) >> 6;   // staged epilogue: 64-channel panels per team's staging set
     uint8_t* smem_stage = smem_b + b_total_bytes;             // 2 sets x n_panels x 16 KB (staged epilogue only)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage + (p.staged ? 2 * n_panels * kATileBytes : 0));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage + (p.staged ? 2 * p.res_sets * n_panels * kATileBytes : 0));
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint64_t* res_full = tmem_empty + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full + 2);
+    uint64_t* res_full = tmem_empty + 2;                     // [team * 2 + staging set]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -414,7 +416,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(&tmem_full[a], 1);
             // one arrive per draining warp; cta_group::2: the leader's MMA thread waits for the warps of both CTAs
             mbar_init(&tmem_empty[a], ((p.staged && p.nsub <= 1) ? kEpiWarps / 2 : kEpiWarps) * (kCg2 ? 2 : 1));
-            mbar_init(&res_full[a], 1);
+            mbar_init(&res_full[2 * a], 1);
+            mbar_init(&res_full[2 * a + 1], 1);
         }
         fence_barrier_init();
     }
@@ -629,11 +632,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 int nt, ph, img, oh0, ow0;
                 decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
                 const int sp = ph * p.nsub + nt * p.spt + team;
-                mbar_arrive_expect_tx(&res_full[team], res_bytes);
+                mbar_arrive_expect_tx(&res_full[2 * team], res_bytes);
                 for (int pn = 0; pn < n_panels; ++pn) {
                     const uint32_t dst = smem_u32(stage_set + pn * kATileBytes);
-                    if (p.os == 1) tma_load_4d(dst, &tmR, &res_full[team], pn * 64, ow0, oh0, img);
-                    else tma_load_5d(dst, &tmR, &res_full[team], pn * 64, p.oow[sp], ow0, p.ooh[sp], img * p.OH + oh0);
+                    if (p.os == 1) tma_load_4d(dst, &tmR, &res_full[2 * team], pn * 64, ow0, oh0, img);
+                    else tma_load_5d(dst, &tmR, &res_full[2 * team], pn * 64, p.oow[sp], ow0, p.ooh[sp], img * p.OH + oh0);
                 }
             };
             if (leader && res_mode && wid < p.total_tiles) load_residual(wid);
@@ -645,7 +648,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
                 const int sp = ph * p.nsub + nt * p.spt + team;
                 if (res_mode) {
-                    mbar_wait(&res_full[team], local & 1, p.err_flag, 5);
+                    mbar_wait(&res_full[2 * team], local & 1, p.err_flag, 5);
                 } else {
                     if (leader) tma_store_wait_read<0>();       // the previous store of this team is done reading the set
                     team_bar_sync(team);
@@ -698,36 +701,45 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int share = wteam >> 2;                   // the 2 warps of a lane quarter split the 16-column units
             const int u_begin = (units * share) / 2, u_end = (units * (share + 1)) / 2;
             const uint32_t res_bytes = static_cast<uint32_t>(n_panels) * kATileBytes;
-            uint8_t* stage_set = smem_stage + team * n_panels * kATileBytes;
-            const uint32_t srow = smem_u32(stage_set) + static_cast<uint32_t>(row) * 128u;   // this thread's row in panel 0
+            // staging sets of this team: nset = 2 (residual tiles only, when shared memory allows) alternates them per tile, so the
+            // residual of the team's NEXT tile is in flight while the current one is processed
+            const int nset = p.res_sets;
+            uint8_t* team_sets = smem_stage + team * nset * n_panels * kATileBytes;
             const uint32_t sw = static_cast<uint32_t>(row & 7) << 4;
             const int res_mode = p.res_mode;
             const float slope = p.slope, r1s = p.r1_sign;
             const int as = team;
-            auto load_residual = [&](int tile) {
+            auto load_residual = [&](int tile, int k) {
                 int nt, ph, img, oh0, ow0;
                 decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
-                mbar_arrive_expect_tx(&res_full[as], res_bytes);
+                uint64_t* bar = &res_full[2 * team + k];
+                mbar_arrive_expect_tx(bar, res_bytes);
                 for (int pn = 0; pn < n_panels; ++pn) {
-                    const uint32_t dst = smem_u32(stage_set + pn * kATileBytes);
+                    const uint32_t dst = smem_u32(team_sets + (k * n_panels + pn) * kATileBytes);
                     const int c = nt * p.block_n + pn * 64;
-                    if (p.os == 1) tma_load_4d(dst, &tmR, &res_full[as], c, ow0, oh0, img);
-                    else tma_load_5d(dst, &tmR, &res_full[as], c, p.oow[ph], ow0, p.ooh[ph], img * p.OH + oh0);
+                    if (p.os == 1) tma_load_4d(dst, &tmR, bar, c, ow0, oh0, img);
+                    else tma_load_5d(dst, &tmR, bar, c, p.oow[ph], ow0, p.ooh[ph], img * p.OH + oh0);
                 }
             };
             const int stride_tiles = 2 * wstep;
             const int first_tile = wid + team * wstep;
-            if (leader && p.res_mode && first_tile < p.total_tiles) load_residual(first_tile);
+            if (leader && p.res_mode && first_tile < p.total_tiles) {
+                load_residual(first_tile, 0);
+                if (nset == 2 && first_tile + stride_tiles < p.total_tiles) load_residual(first_tile + stride_tiles, 1);
+            }
             int n_use = 0;                                  // how many tiles this team has processed
             for (int tile = first_tile; tile < p.total_tiles; tile += stride_tiles, ++n_use) {
                 const uint32_t aphase = n_use & 1;
+                const int kset = nset == 2 ? (n_use & 1) : 0;
+                uint8_t* stage_set = team_sets + kset * n_panels * kATileBytes;
+                const uint32_t srow = smem_u32(stage_set) + static_cast<uint32_t>(row) * 128u;   // this thread's row in panel 0
                 const int local = 2 * n_use + team;
                 (void)local;                                    // only the trace build reads it
                 int nt, ph, img, oh0, ow0;
                 CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && leader && local < 256) p.trace[6 * 256 + local] = clock64();)
                 decode_tile(p, tile, crank, nt, ph, img, oh0, ow0);
                 if (p.res_mode) {
-                    mbar_wait(&res_full[as], aphase, p.err_flag, 5);
+                    mbar_wait(&res_full[2 * team + kset], nset == 2 ? ((n_use >> 1) & 1) : aphase, p.err_flag, 5);
                 } else {
                     if (leader) tma_store_wait_read<0>();       // the previous store of this team is done reading the set
                     team_bar_sync(team);
@@ -775,9 +787,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     CSBSR_TRACE(if (p.trace && blockIdx.x == 0 && local < 256) p.trace[5 * 256 + local] = clock64();)
                     // the set is single-buffered per team: its next residual tile can only land once the store has
                     // finished reading; the other team's tile hides this latency
-                    if (p.res_mode && tile + stride_tiles < p.total_tiles) {
-                        tma_store_wait_read<0>();
-                        load_residual(tile + stride_tiles);
+                    if (p.res_mode && tile + nset * stride_tiles < p.total_tiles) {
+                        tma_store_wait_read<0>();               // the set can only be refilled once the store has read it
+                        load_residual(tile + nset * stride_tiles, kset);
                     }
                 }
             }
@@ -1039,6 +1051,17 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
     }
     const int stage_bytes = a_stage_bytes + G * b_tile;
     if (stages > kMaxStages) stages = kMaxStages;
+    // a second staging set per team for residual tiles, when it still leaves 3 pipeline stages (short-K layers: the 3 -> 128
+    // transposed conv added in place to the 448^2 feature slice is a pure read-modify-write stream of residual tiles)
+    int res_sets = 1;
+    if (staged && nsub == 1 && (d->r0 || d->r1) && !getenv("CSBSR_NO_RES_PREFETCH")) {
+        const int st2 = (smem_avail - staging_bytes) / stage_bytes;
+        if (st2 >= 3) {
+            res_sets = 2;
+            if (stages > st2) stages = st2;
+        }
+    }
+    p.res_sets = res_sets;
     CSBSR_REQUIRE(stages >= 2, "conv_igemm: not enough shared memory for 2 stages");
     p.stages = stages;
     p.OH = d->oh; p.OW = d->ow; p.os = d->os > 0 ? d->os : 1; p.YH = d->yh; p.YW = d->yw; p.N = d->n;
@@ -1146,7 +1169,7 @@ extern "C" int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream_) {
         CSBSR_REQUIRE(r == 0, "conv_igemm: cuTensorMapEncodeTiled(R) failed with %d", r);
     }
 
-    const int smem_bytes = stages * stage_bytes + staging_bytes + 2048 /*align slack (base + staging)*/ + 512 /*barriers*/;
+    const int smem_bytes = stages * stage_bytes + staging_bytes * res_sets + 2048 /*align slack (base + staging)*/ + 512 /*barriers*/;
     static int smem_attr_set = 0;
     if (smem_attr_set < smem_bytes) {
         CSBSR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

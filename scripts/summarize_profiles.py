@@ -68,7 +68,23 @@ WANT = ["ID", "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum"
         "sm__warps_active.avg.pct_of_peak_sustained_active"]
 
 
-def full_summary(raw_csv, out_md, title, cmd):
+NOTES = {
+    "chain": "Reading: DRAM traffic is at or below the algorithmic bytes of a stage (SR chain: fp32 planes in, the 16 x 448^2 x 64 bf16 = 411 MB map "
+             "out, of which 357 MB reached DRAM inside the kernel's window; CAT chain: that map in, 64 floats per image out). L2->SM traffic of the "
+             "CAT chain is 2.5x its DRAM reads (halo columns of neighbouring strips, 136-pixel TMA rows for 112-122 valid columns, row bands "
+             "overlapping by the layers' vertical halo). The tensor pipe is 35 % active on N = 32 / 64 instructions whose floor is 40-48 cycles per "
+             "MMA against 16 / 32 at full rate (`r02_ubench_mma.txt`).",
+    "hd": "Reading: 24 MB of DRAM reads for 915 MB of L2->SM traffic per 16 images: every (image, threshold) item re-reads the image's per-corner "
+          "threshold ranges (431 KB) and looks distances up in the gt EDT map, all L2 hits; no tensor work, warps 50 % active -- integer / latency-bound.",
+    "conv": "Reading: the 8x8/s4 deconv phases (grid 148, 640 threads) show L2->SM traffic of 3-4x their DRAM bytes (weight tiles re-read per pixel "
+            "tile, DESIGN.md section 4.1) with lts throughput 60-75 %; the cta_group::2 launches (conv_igemm_kernel<1>) reach the highest tensor-pipe "
+            "activity.",
+    "wgrad": "Reading: the first launches of the backward pass are the small segmentation-head layers; the 8x8/s4 and 224^2 layers of KBPN follow "
+             "later in the step (per-layer table in `r02_train_step_kernels.txt`).",
+}
+
+
+def full_summary(raw_csv, out_md, title, cmd, note=None):
     rows = list(csv.reader(open(raw_csv, errors="ignore")))
     rows = [r for r in rows if r]
     hi = [i for i, r in enumerate(rows) if r[0] == "ID"][0]
@@ -79,7 +95,9 @@ def full_summary(raw_csv, out_md, title, cmd):
                         .replace("l1tex__m_xbar2l1tex_read_bytes.sum", "L2->SM bytes"))
     lines = ["# " + title, "", cmd, "", "| " + " | ".join("%s [%s]" % (short(w), units[i]) for w, i in idx) + " |", "|" + "---|" * len(idx)]
     for r in data:
-        lines.append("| " + " | ".join(r[i].split("(")[0][:44] for _, i in idx) + " |")
+        lines.append("| " + " | ".join((r[i].split("(")[0] if w == "Kernel Name" else r[i])[:44] for w, i in idx) + " |")
+    if note:
+        lines += ["", note]
     with open(out_md, "w") as f:
         f.write("\n".join(lines) + "\n")
     print(out_md, len(data), "launches")
@@ -105,4 +123,4 @@ if __name__ == "__main__":
         p = os.path.join(go, "prof_%s_%s_raw.csv" % (key, tag))
         if os.path.exists(p) and os.path.getsize(p) > 100:
             full_summary(p, os.path.join(pr, "%s_%s_ncu_full.md" % (tag, name)), "ncu --set full capture of `%s` (%s)" % (kern, tag),
-                         "Command: " + base % (kern, flags, what) + " (" + note + ").")
+                         "Command: " + base % (kern, flags, what) + " (" + note + ").", NOTES.get(key))
