@@ -33,6 +33,9 @@ def main():
     ap.add_argument("--max_iter", type=int, default=None, help="stop after this iteration (default SOLVER.MAX_ITER)")
     ap.add_argument("--synthetic", type=int, default=0, help="train on N synthetic crack images")
     ap.add_argument("--crop", type=int, default=None, help="HR crop size (default INPUT.IMAGE_SIZE of the config)")
+    ap.add_argument("--init_synthetic", action="store_true",
+                    help="offline demo: start the schedules at --resume_iter on seeded synthetic weights instead of a checkpoint "
+                         "(explicit only -- a missing checkpoint is an error otherwise)")
     ap.add_argument("--cuda_graph", type=int, default=1, help="replay forward+loss+backward from a CUDA graph (1) or launch eagerly (0)")
     args = ap.parse_args()
 
@@ -47,7 +50,7 @@ def main():
     if args.output_dirname:
         cfg.OUTPUT_DIR = args.output_dirname
     cfg.freeze()
-    if int(os.environ.get("RANK", "0")) == 0 and args.resume_iter == 0:
+    if int(os.environ.get("RANK", "0")) == 0 and (args.resume_iter == 0 or args.init_synthetic):
         # the run's config travels with its output so that `test.py <output_dir> <iter>` finds it (reference train.py:150-153)
         import shutil
         os.makedirs(cfg.OUTPUT_DIR, exist_ok=True)
@@ -70,7 +73,7 @@ def main():
             raise FileNotFoundError("no *.jpg images under %s (use --synthetic N to train offline)" % dataset.image_dir)
     model = JointModelWithLoss(cfg, num_train_ds=args.synthetic or n_train, resume_iter=args.resume_iter)
     ckpt = os.path.join(cfg.OUTPUT_DIR, "model", "iteration_{}.pth".format(args.resume_iter))
-    if args.resume_iter > 0:
+    if args.resume_iter > 0 and not args.init_synthetic:
         if not os.path.exists(ckpt):                       # the reference fails in torch.load here; never resume on random weights
             raise FileNotFoundError("--resume_iter %d: checkpoint %s does not exist" % (args.resume_iter, ckpt))
         sd = torch.load(ckpt, map_location="cpu")
