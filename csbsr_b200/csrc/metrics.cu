@@ -763,7 +763,7 @@ struct FusedArgs {
     double pct, max_img_len;
     double* hd;
     double* msd;
-    unsigned int* scratch;                                  // [gridDim.x][scratch_cap]
+    unsigned int* scratch;                                  // [gridDim.x][2][scratch_cap]: spilled key list + its sort target
     int scratch_cap;                                        // power of two >= (H+1)*(W+1)
     int* counter;
     int force_seq;
@@ -824,6 +824,108 @@ __device__ bool block_counting_sort(unsigned int* keys, int n, int cap, int* s_t
     return true;
 }
 
+// Sort of a LONG key list (n > kFusedCap, living in the CTA's global scratch `A`) into the second scratch region `B`:
+// most-significant-digit bucketing on the top 12 bits of the key range (histogram + cursors in shared memory, one scatter
+// A -> B), then every bucket -- a contiguous segment of B whose keys differ only in their low <= 9 bits -- is counting-sorted
+// by one warp with a private shared-memory histogram that regenerates the bucket's runs in place.  O(n) work, two passes over
+// the keys, instead of the ~150 global-memory passes of the bitonic network (10.8 of the 16.5 ms of the App. E fixture).
+// `sm` = the 32768-word key area of shared memory (free while the list is in global memory).  Returns B, or nullptr (A
+// untouched) when the key range needs more than 21 bits.
+__device__ unsigned int* block_msd_sort_global(const unsigned int* A, unsigned int* B, int n, unsigned int* sm, int* s_tmp) {
+    constexpr int kHiBits = 12, kBuckets = 1 << kHiBits, kLoMax = 9;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    unsigned int mx = 0;
+    for (int i = tid; i < n; i += nt) mx = max(mx, A[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    if (lane == 0) s_tmp[warp] = static_cast<int>(mx);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int m = 0;
+        for (int w = 0; w < nwarps; ++w) m = max(m, static_cast<unsigned int>(s_tmp[w]));
+        s_tmp[32] = static_cast<int>(m);
+    }
+    __syncthreads();
+    const unsigned int kmax = static_cast<unsigned int>(s_tmp[32]);
+    int shift = 0;
+    while ((kmax >> shift) >= static_cast<unsigned int>(kBuckets)) ++shift;
+    __syncthreads();
+    if (shift > kLoMax || nwarps * (1 << kLoMax) + 2 * kBuckets + 2 > kFusedCap) return nullptr;
+    unsigned int* off = sm;                              // [kBuckets + 1]
+    unsigned int* cur = sm + kBuckets + 1;               // [kBuckets]
+    unsigned int* whist = sm + 2 * kBuckets + 1;         // [nwarps][1 << shift]
+    for (int i = tid; i <= kBuckets; i += nt) off[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) atomicAdd(&off[A[i] >> shift], 1u);
+    __syncthreads();
+    {   // exclusive scan of the bucket counts: contiguous chunks per thread
+        const int L = (kBuckets + nt - 1) / nt;
+        const int c0 = min(kBuckets, tid * L), c1 = min(kBuckets, c0 + L);
+        int sum = 0;
+        for (int i = c0; i < c1; ++i) sum += static_cast<int>(off[i]);
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_tmp[warp] = inc;
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int w = 0; w < nwarps; ++w) { const int v = s_tmp[w]; s_tmp[w] = acc; acc += v; }
+        }
+        __syncthreads();
+        int pos = s_tmp[warp] + inc - sum;
+        for (int i = c0; i < c1; ++i) {
+            const int cnt = static_cast<int>(off[i]);
+            off[i] = static_cast<unsigned int>(pos);
+            cur[i] = static_cast<unsigned int>(pos);
+            pos += cnt;
+        }
+        if (tid == 0) off[kBuckets] = static_cast<unsigned int>(n);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        const unsigned int k = A[i];
+        B[atomicAdd(&cur[k >> shift], 1u)] = k;
+    }
+    __syncthreads();                                     // (block-scope: the scattered keys are visible to every warp)
+    const int nbins = 1 << shift, per_lane = (nbins + 31) >> 5;
+    const unsigned int lomask = static_cast<unsigned int>(nbins - 1);
+    unsigned int* wh = whist + warp * nbins;
+    if (shift > 0) {
+        for (int b = warp; b < kBuckets; b += nwarps) {
+            const int lo = static_cast<int>(off[b]), hi = static_cast<int>(off[b + 1]);
+            if (hi - lo < 2) continue;                   // warp-uniform
+            for (int v = lane; v < nbins; v += 32) wh[v] = 0;
+            __syncwarp();
+            for (int i = lo + lane; i < hi; i += 32) atomicAdd(&wh[B[i] & lomask], 1u);
+            __syncwarp();
+            // lane owns the bins [lane * per_lane, ...): exclusive prefix across the warp, then it writes its runs
+            const int v0 = min(nbins, lane * per_lane), v1 = min(nbins, v0 + per_lane);
+            int sum = 0;
+            for (int v = v0; v < v1; ++v) sum += static_cast<int>(wh[v]);
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t2 = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += t2;
+            }
+            int pos = lo + inc - sum;
+            const unsigned int base = static_cast<unsigned int>(b) << shift;
+            for (int v = v0; v < v1; ++v) {
+                const int cnt = static_cast<int>(wh[v]);
+                for (int j = 0; j < cnt; ++j) B[pos + j] = base | static_cast<unsigned int>(v);
+                pos += cnt;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    return B;
+}
+
 // block-wide bitonic sort of keys[0..n) (keys[n..m) padded with 0xFFFFFFFF, m = next power of two <= capacity)
 __device__ void block_bitonic(unsigned int* keys, int n) {
     int m = 1;
@@ -856,7 +958,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) hd_fused_kernel(const FusedA
     __shared__ int s_tmp[34];
     __shared__ double s_res[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFusedThreads / 32;
-    unsigned int* gkeys = a.scratch + static_cast<size_t>(blockIdx.x) * a.scratch_cap;
+    unsigned int* gkeys = a.scratch + static_cast<size_t>(blockIdx.x) * 2 * a.scratch_cap;      // [2][cap]: list, sort target
 
     auto make_aux = [&](unsigned char* base, int max_leaves) {
         ReplayAux ax;
@@ -872,7 +974,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) hd_fused_kernel(const FusedA
     // sort + replay of the list that was just written to `keys` (shared or this CTA's global scratch)
     auto sort_replay = [&](unsigned int* keys, int n, bool in_smem, double* out) {
         if (a.force_seq & 4) { if (tid == 0) { out[0] = 0; out[1] = 0; } __syncthreads(); return; }
-        if (!(in_smem && !(a.force_seq & 16) && block_counting_sort(keys, n, kFusedCap, s_tmp))) block_bitonic(keys, n);
+        bool sorted = false;
+        if (!(a.force_seq & 16)) {
+            if (in_smem) {
+                sorted = block_counting_sort(keys, n, kFusedCap, s_tmp);
+            } else {
+                unsigned int* r = block_msd_sort_global(keys, keys + a.scratch_cap, n, skeys, s_tmp);
+                if (r) { keys = r; sorted = true; }
+            }
+        }
+        if (!sorted) block_bitonic(keys, n);
         if (a.force_seq & 8) { if (tid == 0) { out[0] = 0; out[1] = 0; } __syncthreads(); return; }
         if (a.force_seq & 1) {
             if (tid == 0) replay_list(keys, n, a.pct, out);
@@ -1053,7 +1164,7 @@ static MetricsWs carve(void* base, int b, int h, int w, bool with_hd) {
     m.ctas = num_sms();
     if (m.fused) {
         // per image: q, gt, cg (1 B / pixel or corner), gt border list, gt column distances + EDT map; per resident CTA: one
-        // spill region for key lists longer than 32768 -- ~2.9 MB per 448^2 image + 155 MB per device instead of 260 MB per image
+        // spill region (list + sort target) for key lists longer than 32768 -- ~2.9 MB per 448^2 image + 310 MB per device instead of 260 MB per image
         m.qlo = m.qhi = nullptr;
         m.qr = static_cast<uchar2*>(take(sizeof(uchar2) * static_cast<size_t>(b) * (w + 1) * ((h + 1 + 31) / 32 * 32)));
         m.cg = static_cast<unsigned char*>(take(b * NC));
@@ -1066,7 +1177,7 @@ static MetricsWs carve(void* base, int b, int h, int w, bool with_hd) {
         m.gcol_t = nullptr;
         m.keys_g2p = m.keys_p2g = nullptr;
         m.res = nullptr;
-        m.scratch = static_cast<unsigned int*>(take(sizeof(int) * static_cast<size_t>(m.ctas) * m.cap));
+        m.scratch = static_cast<unsigned int*>(take(sizeof(int) * static_cast<size_t>(m.ctas) * 2 * m.cap));
         m.counter = static_cast<int*>(take(sizeof(int)));
     } else if (with_hd) {
         m.qlo = static_cast<unsigned char*>(take(b * NC));
