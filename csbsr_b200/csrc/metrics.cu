@@ -479,8 +479,8 @@ __device__ void replay_parallel(const unsigned int* keys, int n, double pct, dou
             }
         }
     }
-    // ---- class counts per contiguous chunk
-    const int L = (n + nt - 1) / nt;
+    // ---- class counts per contiguous chunk (odd chunk length: consecutive threads then start in different shared-memory banks)
+    const int L = ((n + nt - 1) / nt) | 1;
     const int c0 = min(n, tid * L), c1 = min(n, c0 + L);
     int k1 = 0, k2 = 0, k3 = 0;
     for (int i = c0; i < c1; ++i) {
@@ -1009,10 +1009,22 @@ __global__ void __launch_bounds__(kFusedThreads, 1) hd_fused_kernel(const FusedA
         int local_np = 0;
         {
             const uchar2* qrb = a.qr + static_cast<size_t>(b) * Wc * (WH * 32);
-            for (int widx = warp; widx < Wc * WH; widx += nwarps) {
-                const uchar2 v = qrb[static_cast<size_t>(widx) * 32 + lane];          // widx = x * WH + k  ->  (x, y = 32k + lane)
-                const unsigned int word = __ballot_sync(0xFFFFFFFFu, v.x < t && t <= v.y);
-                if (lane == 0) { bits[widx] = word; local_np += __popc(word); }
+            // four independent loads in flight per warp: one dependent L2 load per mask word made this loop latency-bound
+            // (~210 round trips per warp and item, the largest single stall of the kernel in ncu's source view)
+            const int nwords = Wc * WH;
+            for (int w0 = warp; w0 < nwords; w0 += 4 * nwarps) {
+                uchar2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int widx = w0 + u * nwarps;                                   // widx = x * WH + k  ->  (x, y = 32k + lane)
+                    v[u] = widx < nwords ? qrb[static_cast<size_t>(widx) * 32 + lane] : make_uchar2(255, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int widx = w0 + u * nwarps;
+                    const unsigned int word = __ballot_sync(0xFFFFFFFFu, v[u].x < t && t <= v[u].y);
+                    if (lane == 0 && widx < nwords) { bits[widx] = word; local_np += __popc(word); }
+                }
             }
         }
         local_np = warp_sum(local_np);
