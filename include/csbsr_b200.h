@@ -88,6 +88,8 @@ typedef struct csbsr_conv_desc {
     int32_t nsub;
 } csbsr_conv_desc;
 
+/* Zero-initialise the descriptor (memset) before filling it: launch plans (tensor maps, tiling, launch geometry) are cached by
+ * the descriptor's bytes, so a step that repeats its descriptors pays the planning once. */
 int csbsr_conv_igemm(const csbsr_conv_desc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
