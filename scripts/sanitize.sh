@@ -21,15 +21,16 @@ run() {   # tool, tag, pytest selection...
     local tests=$(grep -E "passed|failed" $log | tail -1)
     echo "$tool $tag: rc=$rc  reports=$errs  [$summ]  pytest: $tests" | tee -a $SUM
 }
-CONV="tests/test_conv_gpu.py::test_conv_matches_torch tests/test_conv_gpu.py::test_deconv8s4_matches_torch tests/test_conv_gpu.py::test_epilogue_variants tests/test_conv_gpu.py::test_f32_planar_output_and_class_bias"
+CONV="tests/test_conv_gpu.py::test_conv_matches_torch tests/test_conv_gpu.py::test_deconv8s4_matches_torch tests/test_conv_gpu.py::test_epilogue_variants tests/test_conv_gpu.py::test_f32_planar_output_and_class_bias tests/test_conv_gpu.py::test_deconv8s4_merged_subphases"
 run memcheck conv $CONV
 run memcheck kpred "tests/test_kpred_gpu.py::test_kpred_chains_vs_torch"
-run memcheck metrics tests/test_metrics_gpu.py::test_golden_vectors_bit_exact tests/test_metrics_gpu.py::test_edge_cases tests/test_metrics_gpu.py::test_degrade_matches_golden_and_oracle tests/test_metrics_gpu.py::test_psnr_ssim_kernel_vs_reference_golden_and_oracle
+run memcheck metrics tests/test_metrics_gpu.py::test_golden_vectors_bit_exact tests/test_metrics_gpu.py::test_edge_cases tests/test_metrics_gpu.py::test_large_lists_and_sequential_replay_agree tests/test_metrics_gpu.py::test_degrade_matches_golden_and_oracle tests/test_metrics_gpu.py::test_psnr_ssim_kernel_vs_reference_golden_and_oracle
 run memcheck losses tests/test_losses_gpu.py
+run memcheck glue tests/test_glue_gpu.py::test_bilinear_fwd_bwd tests/test_glue_gpu.py::test_adaptive_avgpool_fwd_bwd tests/test_glue_gpu.py::test_patch_split_join_and_crop_flip_vs_oracle
 run memcheck wgrad tests/test_train_gpu.py::test_conv_wgrad_vs_autograd tests/test_train_gpu.py::test_deconv_wgrad_vs_autograd tests/test_train_gpu.py::test_fused_adam_vs_torch_adam tests/test_train_gpu.py::test_batch_norm_fn_vs_torch
-run racecheck metrics tests/test_metrics_gpu.py::test_golden_vectors_bit_exact tests/test_metrics_gpu.py::test_edge_cases tests/test_metrics_gpu.py::test_degrade_matches_golden_and_oracle
+run racecheck metrics tests/test_metrics_gpu.py::test_golden_vectors_bit_exact tests/test_metrics_gpu.py::test_edge_cases tests/test_metrics_gpu.py::test_large_lists_and_sequential_replay_agree tests/test_metrics_gpu.py::test_degrade_matches_golden_and_oracle
 run racecheck losses tests/test_losses_gpu.py
-run racecheck conv "tests/test_conv_gpu.py::test_epilogue_variants" "tests/test_conv_gpu.py::test_deconv8s4_matches_torch"
-run synccheck conv "tests/test_conv_gpu.py::test_epilogue_variants" "tests/test_conv_gpu.py::test_deconv8s4_matches_torch"
+run racecheck conv "tests/test_conv_gpu.py::test_epilogue_variants" "tests/test_conv_gpu.py::test_deconv8s4_matches_torch" "tests/test_conv_gpu.py::test_deconv8s4_merged_subphases"
+run synccheck conv "tests/test_conv_gpu.py::test_epilogue_variants" "tests/test_conv_gpu.py::test_deconv8s4_matches_torch" "tests/test_conv_gpu.py::test_deconv8s4_merged_subphases"
 run synccheck kpred "tests/test_kpred_gpu.py::test_kpred_chains_vs_torch"
 cat $SUM
