@@ -2,8 +2,23 @@
 import os, sys, torch
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "scripts"))
 from csbsr_b200.engine import inference as E
-d = torch.load("build/bench_seg16.pt")
-seg, mask = d["seg"].cuda(), d["mask"].cuda()
+if os.path.exists("build/bench_seg16.pt"):                 # maps saved from an earlier run (build/ is git-ignored)
+    d = torch.load("build/bench_seg16.pt")
+    seg, mask = d["seg"].cuda(), d["mask"].cuda()
+else:                                                       # the bench's own maps: synthetic weights on 16 synthetic images
+    from csbsr_b200.config import cfg
+    from csbsr_b200.data import degrade as G
+    from csbsr_b200.modeling.build_model import JointModel
+    from csbsr_b200.utils import synth
+    c = cfg.clone(); c.merge_from_file("config/config_csbsr_pspnet.yaml")
+    m = JointModel(c); m.load_state_dict(synth.model_state_dict(), strict=True)
+    hr, mask = synth.batch(0, 16, 448)
+    lr, _ = G.degrade(hr.cuda(), torch.as_tensor(synth.degradation_params(16, seed=5)).cuda())
+    with torch.no_grad():
+        _, seg, _ = m(lr, None)
+    mask = mask.cuda()
+    os.makedirs("build", exist_ok=True)
+    torch.save({"seg": seg.cpu(), "mask": mask.cpu()}, "build/bench_seg16.pt")
 def t(fn, n=5):
     for _ in range(2): fn()
     torch.cuda.synchronize()
