@@ -32,6 +32,7 @@
 namespace csbsr {
 namespace kp {
 
+constexpr int kGapRows = 32;              // image rows per pooled partial sum (fixed: the reduction order is launch-independent)
 constexpr int kPX = 128;                  // pixels per row unit = MMA M
 constexpr int kPlanePx = 136;             // pad | 128 pixels | pad ... : the +-1 column taps read the pads at the strip ends; 136 makes a
                                           // plane 17 x 128 B, the alignment TMA needs for its shared-memory destination
@@ -100,7 +101,8 @@ struct Params {
     const void* wpack;           // packed weights, off_w(NU) - off_w(0) bytes
     void* out;                   // OUT_GLOBAL: bf16 NHWC [B,H,W,64]
     const float* cls_bias;       // fp32 [B,5,5,64] (cls_bias units)
-    float* partial;              // OUT_GAP: fp32 [items][64] partial sums
+    float* partial;              // OUT_GAP: fp32 [B][strips][gap_blocks][64] partial sums of kGapRows-row blocks
+    int gap_blocks;              // ceil(H / kGapRows)
     int B, H, W;
     int nstrips, nseg, vw;       // column strips per image, row segments per strip, valid output columns per strip
     int seg_rows;                // rows per segment (last one may be shorter)
@@ -110,7 +112,7 @@ struct Params {
 };
 
 struct Item {
-    int b, y0, y1, x0, vw;
+    int b, y0, y1, x0, vw, strip;
 };
 template <class P>
 __device__ __forceinline__ Item decode_item(const Params& p, int item) {
@@ -122,6 +124,7 @@ __device__ __forceinline__ Item decode_item(const Params& p, int item) {
     it.y0 = seg * p.seg_rows;
     it.y1 = min(p.H, it.y0 + p.seg_rows);
     const int xs = strip * p.vw;
+    it.strip = strip;
     it.vw = min(p.vw, p.W - xs);
     it.x0 = xs - P::halo(0);
     return it;
@@ -459,24 +462,30 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
             for (int t = tb; t <= te; ++t) {
                 epilogue_step_units<P, P::NU - 1>(p, bar, it, t, sbase, m3, group, q, lane, ph_acc, gap);
                 m3 = m3 == 2 ? 0 : m3 + 1;
-            }
-            if (P::out_kind(P::NU - 1) == OUT_GAP && P::epi_group(P::NU - 1) == group) {
-                // deterministic reduction of the item's per-pixel sums: lanes (shuffle tree), then the 4 quarter warps in order
+                if (P::out_kind(P::NU - 1) == OUT_GAP && P::epi_group(P::NU - 1) == group) {
+                    // The pooled sums leave in FIXED blocks of kGapRows image rows (segments start on block boundaries), so the
+                    // order of the additions -- rows of a block per thread, lanes (shuffle tree), the 4 quarter warps, then the
+                    // blocks of the image in gap_finalize_kernel -- does not depend on how the launch split the image into
+                    // segments, i.e. not on how many images share the launch.
+                    const int row = t - P::lag(P::NU - 1);             // the row the pooling unit handled in this step
+                    if (row >= it.y0 && row < it.y1 && (((row + 1) % kGapRows) == 0 || row == it.y1 - 1)) {
 #pragma unroll
-                for (int i = 0; i < 64; ++i) {
-                    float s = gap[i];
+                        for (int i = 0; i < 64; ++i) {
+                            float s = gap[i];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0) gap_smem[q * 64 + i] = s;
-                    gap[i] = 0.f;
+                            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                            if (lane == 0) gap_smem[q * 64 + i] = s;
+                            gap[i] = 0.f;
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (q == 0) {
+                            const size_t slot = (static_cast<size_t>(it.b) * p.nstrips + it.strip) * p.gap_blocks + row / kGapRows;
+                            for (int i = lane; i < 64; i += 32)
+                                p.partial[slot * 64 + i] = ((gap_smem[i] + gap_smem[64 + i]) + gap_smem[128 + i]) + gap_smem[192 + i];
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (q == 0) {
-                    for (int i = lane; i < 64; i += 32)
-                        p.partial[static_cast<size_t>(item) * 64 + i] =
-                            ((gap_smem[i] + gap_smem[64 + i]) + gap_smem[128 + i]) + gap_smem[192 + i];
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
         }
     }
@@ -528,8 +537,9 @@ static void plan(Params& p, int B, int H, int W) {
     int nseg = num_sms() / (B * p.nstrips);
     if (nseg < 1) nseg = 1;
     while (nseg > 1 && (H + nseg - 1) / nseg < 32) --nseg;
-    p.seg_rows = (H + nseg - 1) / nseg;
+    p.seg_rows = ((H + nseg - 1) / nseg + kGapRows - 1) / kGapRows * kGapRows;    // segments start on pooling-block boundaries
     p.nseg = (H + p.seg_rows - 1) / p.seg_rows;
+    p.gap_blocks = (H + kGapRows - 1) / kGapRows;
     p.nitems = B * p.nstrips * p.nseg;
 }
 
@@ -565,7 +575,7 @@ extern "C" size_t csbsr_kpred_workspace_bytes(int b, int h, int w) {
     kp::Params p;
     memset(&p, 0, sizeof(p));
     kp::plan<kp::ProgCAT>(p, b, h, w);
-    return static_cast<size_t>(p.nitems) * 64 * sizeof(float);
+    return static_cast<size_t>(b) * p.nstrips * p.gap_blocks * 64 * sizeof(float);
 }
 
 extern "C" int csbsr_kpred_sr_chain(const float* img, const void* wpack, void* out, int b, int h, int w, float slope,
@@ -593,7 +603,7 @@ extern "C" int csbsr_kpred_cat_chain(const void* in, const void* wpack, const fl
     kp::Params p;
     memset(&p, 0, sizeof(p));
     kp::plan<kp::ProgCAT>(p, b, h, w);
-    CSBSR_REQUIRE(ws_bytes >= static_cast<size_t>(p.nitems) * 64 * sizeof(float), "kpred_cat_chain: workspace too small");
+    CSBSR_REQUIRE(ws_bytes >= static_cast<size_t>(b) * p.nstrips * p.gap_blocks * 64 * sizeof(float), "kpred_cat_chain: workspace too small");
     p.wpack = wpack; p.cls_bias = cls_bias; p.partial = reinterpret_cast<float*>(ws); p.slope = slope;
     kp::PFN_encodeTiled encode = kp::encode_fn();
     CSBSR_REQUIRE(encode, "kpred_cat_chain: cuTensorMapEncodeTiled entry point unavailable");
@@ -612,7 +622,7 @@ extern "C" int csbsr_kpred_cat_chain(const void* in, const void* wpack, const fl
     }
     int rc = kp::launch<kp::ProgCAT>(p, tm, stream_);
     if (rc) return rc;
-    kp::gap_finalize_kernel<<<b, 64, 0, stream_>>>(p.partial, gap_out, p.nstrips * p.nseg, 1.0f / (static_cast<float>(h) * w), gap_c);
+    kp::gap_finalize_kernel<<<b, 64, 0, stream_>>>(p.partial, gap_out, p.nstrips * p.gap_blocks, 1.0f / (static_cast<float>(h) * w), gap_c);
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
