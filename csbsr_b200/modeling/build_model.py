@@ -46,7 +46,11 @@ class JointModel(nn.Module):
 
     # -------------------------------------------------------------- weights
     def _param_version(self):
-        return tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers())
+        # tensor versions catch in-place torch updates; the fused Adam / BatchNorm kernels write through raw pointers and do
+        # not bump them, so the optimizer's own change counter (kernels.invalidate_packed, called by FusedAdam.step) is part
+        # of the key: the eval engines are re-packed after every training step even with frozen BatchNorm buffers
+        from .. import kernels as K
+        return (K._PACK_STATE["epoch"],) + tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers())
 
     def load_state_dict(self, *a, **k):
         out = super().load_state_dict(*a, **k)
