@@ -452,7 +452,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // per-k-block bookkeeping of a single issuing thread (~100 dependent instructions) bounds the small layers.
         {
             const bool load_a = (warp == 0);
-            const bool cg2 = kCg2;
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_a = p.a_stage_bytes, tx_b = b_stage_bytes;

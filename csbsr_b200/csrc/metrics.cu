@@ -948,7 +948,7 @@ __device__ void block_bitonic(unsigned int* keys, int n) {
 
 __global__ void __launch_bounds__(kFusedThreads, 1) hd_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(16) unsigned char fsm[];
-    const int Hc = a.H + 1, Wc = a.W + 1, WH = (Hc + 31) / 32, WWt = (Wc + 31) / 32, NC = Hc * Wc;
+    const int Hc = a.H + 1, Wc = a.W + 1, WH = (Hc + 31) / 32, NC = Hc * Wc;
     unsigned int* bits = reinterpret_cast<unsigned int*>(fsm);                       // [Wc][WH]: bit r of word (x, k) = corner (32k + r, x)
     unsigned int* skeys = bits + ((Wc * WH + 3) & ~3);
     unsigned char* aux_base = reinterpret_cast<unsigned char*>(skeys + kFusedCap);
