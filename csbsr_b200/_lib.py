@@ -167,6 +167,7 @@ _SIGNATURES = {
     "csbsr_seg_loss_wf_mean": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_void_p,
                                                                                               C.c_size_t, C.c_void_p]),
     "csbsr_sr_loss_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "csbsr_sr_loss_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 4 + [C.c_float] * 3 + [C.c_void_p] * 4),
     "csbsr_sr_loss": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_float] * 3 + [C.c_void_p, C.c_void_p, C.c_size_t,
                                                                                  C.c_void_p]),
     "csbsr_metrics_workspace_bytes": (C.c_size_t, [C.c_int] * 4),

@@ -440,6 +440,28 @@ extern "C" int csbsr_seg_loss_wf_grad(const float* p_main, const float* p_aux, c
     return 0;
 }
 
+// backward of the per-sample means: d mean|a - b| / da = sign(a - b) / n (0 where a == b, as torch's abs), d mean((a - b)^2) / da
+// = 2 (a - b) / n, each scaled by the sample's upstream gradient
+__global__ void l1_mean_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ up,
+                                   float* __restrict__ d, int n, float w_over_n) {
+    const int s = blockIdx.y;
+    const float g = w_over_n * (up ? up[s] : 1.f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const size_t o = static_cast<size_t>(s) * n + i;
+        const float df = a[o] - b[o];
+        d[o] = df > 0.f ? g : (df < 0.f ? -g : 0.f);
+    }
+}
+__global__ void mse_mean_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ up,
+                                    float* __restrict__ d, int n, float w_over_n) {
+    const int s = blockIdx.y;
+    const float g = 2.f * w_over_n * (up ? up[s] : 1.f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const size_t o = static_cast<size_t>(s) * n + i;
+        d[o] = g * (a[o] - b[o]);
+    }
+}
+
 extern "C" size_t csbsr_sr_loss_workspace_bytes(int b) { return al(sizeof(double) * 3 * static_cast<size_t>(b)); }
 
 // KBPNLoss.forward given the pseudo-LR image (csbsr_blur_per_sample stride 1 + csbsr_resize_bicubic_aa of sr with the
@@ -456,6 +478,20 @@ extern "C" int csbsr_sr_loss(const float* sr, const float* hr, const float* pseu
     l1_mean_kernel<<<dim3((n_lr + 2047) / 2048, b), 256, 0, stream>>>(pseudo_lr, lr, acc + b, n_lr);
     mse_mean_kernel<<<dim3((n_k + 2047) / 2048, b), 256, 0, stream>>>(k_pred, k_gt, acc + 2 * b, n_k);
     sr_loss_finish_kernel<<<(b + 127) / 128, 128, 0, stream>>>(acc, loss, b, n_hr, n_lr, n_k, w_hr, w_lr, w_k);
+    CSBSR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Backward of csbsr_sr_loss w.r.t. sr, pseudo_lr and k_pred: d(sum_b upstream[b] * loss[b]) (upstream NULL = ones); d_k may be NULL.
+extern "C" int csbsr_sr_loss_bwd(const float* sr, const float* hr, const float* pseudo_lr, const float* lr, const float* k_pred,
+                                 const float* k_gt, const float* upstream, int b, int n_hr, int n_lr, int n_k, float w_hr, float w_lr,
+                                 float w_k, float* d_sr, float* d_plr, float* d_k, void* stream_) {
+    cudaStream_t stream = STREAM(stream_);
+    CSBSR_REQUIRE(sr && hr && pseudo_lr && lr && d_sr && d_plr && b > 0 && n_hr > 0 && n_lr > 0, "sr_loss_bwd: bad arguments");
+    CSBSR_REQUIRE(!d_k || (k_pred && k_gt && n_k > 0), "sr_loss_bwd: d_k needs k_pred and k_gt");
+    l1_mean_bwd_kernel<<<dim3((n_hr + 2047) / 2048, b), 256, 0, stream>>>(sr, hr, upstream, d_sr, n_hr, w_hr / static_cast<float>(n_hr));
+    l1_mean_bwd_kernel<<<dim3((n_lr + 2047) / 2048, b), 256, 0, stream>>>(pseudo_lr, lr, upstream, d_plr, n_lr, w_lr / static_cast<float>(n_lr));
+    if (d_k) mse_mean_bwd_kernel<<<dim3((n_k + 2047) / 2048, b), 256, 0, stream>>>(k_pred, k_gt, upstream, d_k, n_k, w_k / static_cast<float>(n_k));
     CSBSR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -193,7 +193,43 @@ def kbpn_loss_train(sr, hr, lr, kvec, k_gt, weights=(0.4, 0.4, 0, 2), ksize=21, 
     k = kvec / kvec.sum(dim=1, keepdim=True)
     plr = resize_aa(blur_per_sample(sr, k, ksize, 1), factor)          # csbsr blur / antialiased-bicubic kernels, fwd + bwd
     kn = k.view(-1, 1, ksize, ksize)
-    loss = weights[0] * (sr - hr).abs().mean((1, 2, 3)) + weights[1] * (plr - lr).abs().mean((1, 2, 3))
-    if weights[2] != 0:
-        loss = loss + weights[2] * ((kn - k_gt) ** 2).mean((1, 2, 3))
+    loss = _KBPNLossFn.apply(sr, hr, plr, lr, kn, k_gt, float(weights[0]), float(weights[1]), float(weights[2]))
     return loss, kn
+
+
+class _KBPNLossFn(torch.autograd.Function):
+    """loss[b] = w_hr mean|sr - hr| + w_lr mean|plr - lr| + w_k mean((k - k_gt)^2): csbsr_sr_loss forward, csbsr_sr_loss_bwd backward
+    (the autograd of nn.L1Loss / nn.MSELoss behind loss.backward(), sr_loss_functions.py:39-56)."""
+
+    @staticmethod
+    def forward(ctx, sr, hr, plr, lr, kn, k_gt, w_hr, w_lr, w_k):
+        f = lambda t: t.detach().contiguous().float()
+        s, h, p_, l, k, kg = f(sr), f(hr), f(plr), f(lr), f(kn), f(k_gt)
+        b = s.shape[0]
+        loss = torch.empty(b, dtype=torch.float32, device=s.device)
+        L = _lib.lib()
+        n = L.csbsr_sr_loss_workspace_bytes(b)
+        ws = torch.empty(max(int(n), 8), dtype=torch.uint8, device=s.device)
+        rc = L.csbsr_sr_loss(s.data_ptr(), h.data_ptr(), p_.data_ptr(), l.data_ptr(), k.data_ptr(), kg.data_ptr(), b, s[0].numel(),
+                             l[0].numel(), k[0].numel(), C.c_float(w_hr), C.c_float(w_lr), C.c_float(w_k), loss.data_ptr(),
+                             ws.data_ptr(), n, _lib.stream_ptr())
+        _lib.check(rc, "csbsr_sr_loss")
+        _lib.count_launch("csbsr_sr_loss")
+        ctx.save_for_backward(s, h, p_, l, k, kg)
+        ctx.w = (w_hr, w_lr, w_k)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        s, h, p_, l, k, kg = ctx.saved_tensors
+        w_hr, w_lr, w_k = ctx.w
+        g = g.contiguous().float()
+        d_sr, d_plr = torch.empty_like(s), torch.empty_like(p_)
+        d_k = torch.empty_like(k) if (w_k != 0 and ctx.needs_input_grad[4]) else None
+        rc = _lib.lib().csbsr_sr_loss_bwd(s.data_ptr(), h.data_ptr(), p_.data_ptr(), l.data_ptr(), k.data_ptr(), kg.data_ptr(),
+                                          g.data_ptr(), s.shape[0], s[0].numel(), l[0].numel(), k[0].numel(), C.c_float(w_hr),
+                                          C.c_float(w_lr), C.c_float(w_k), d_sr.data_ptr(), d_plr.data_ptr(),
+                                          d_k.data_ptr() if d_k is not None else None, _lib.stream_ptr())
+        _lib.check(rc, "csbsr_sr_loss_bwd")
+        _lib.count_launch("csbsr_sr_loss_bwd")
+        return d_sr, None, d_plr, None, d_k, None, None, None, None

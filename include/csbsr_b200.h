@@ -399,6 +399,13 @@ size_t csbsr_sr_loss_workspace_bytes(int b);
 int csbsr_sr_loss(const float* sr, const float* hr, const float* pseudo_lr, const float* lr, const float* k_pred,
                   const float* k_gt, int b, int n_hr, int n_lr, int n_k, float w_hr, float w_lr, float w_k, float* loss,
                   void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of csbsr_sr_loss (autograd of KBPNLoss.forward behind loss.backward(), trainer.py:67): d_sr = upstream[b] * w_hr *
+ * sign(sr - hr) / n_hr, d_plr likewise with w_lr / n_lr, d_k = upstream[b] * 2 w_k (k_pred - k_gt) / n_k (d_k may be NULL when
+ * w_k = 0); `upstream`: DEVICE float[b] or NULL (= 1).  The pseudo-LR gradient continues through csbsr_resize_bicubic_aa_bwd and
+ * csbsr_blur_ps_bwd_input / _bwd_kernel. */
+int csbsr_sr_loss_bwd(const float* sr, const float* hr, const float* pseudo_lr, const float* lr, const float* k_pred,
+                      const float* k_gt, const float* upstream, int b, int n_hr, int n_lr, int n_k, float w_hr, float w_lr,
+                      float w_k, float* d_sr, float* d_plr, float* d_k, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Segmentation metrics (csrc/metrics.cu): AIU threshold sweep and the Hausdorff / mean-surface-distance

@@ -75,3 +75,32 @@ def test_wf_loss_fused_mean_and_gradient_vs_elementwise_autograd():
     assert (gm1 - gm0).abs().max().item() <= 1e-4 * gm0.abs().max().item()
     assert (ga1 - ga0).abs().max().item() <= 1e-4 * ga0.abs().max().item()
     assert gm1[0, 0, :2, :3].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("w_k", [0.0, 2.0])
+def test_kbpn_loss_function_fwd_bwd_vs_torch_autograd(w_k):
+    """engine/losses.py::_KBPNLossFn (csbsr_sr_loss forward, csbsr_sr_loss_bwd backward) against the elementwise torch form of
+    KBPNLoss (sr_loss_functions.py:39-56) and its autograd, with a non-trivial upstream gradient per sample."""
+    from csbsr_b200.engine.losses import _KBPNLossFn
+    g = torch.Generator(device="cuda").manual_seed(31)
+    B = 3
+    sr = torch.rand(B, 3, 40, 56, device="cuda", generator=g)
+    hr = torch.rand(B, 3, 40, 56, device="cuda", generator=g)
+    hr[0, 0, :4] = sr[0, 0, :4]                               # exact ties: abs' subgradient 0 as in torch
+    plr = torch.rand(B, 3, 10, 14, device="cuda", generator=g)
+    lr = torch.rand(B, 3, 10, 14, device="cuda", generator=g)
+    kn = torch.rand(B, 1, 21, 21, device="cuda", generator=g) / 441
+    kg = torch.rand(B, 1, 21, 21, device="cuda", generator=g) / 441
+    up = torch.tensor([0.3, -1.2, 2.0], device="cuda")
+    a = [t.clone().requires_grad_(True) for t in (sr, plr, kn)]
+    b = [t.clone().requires_grad_(True) for t in (sr, plr, kn)]
+    loss = _KBPNLossFn.apply(a[0], hr, a[1], lr, a[2], kg, 0.4, 0.4, w_k)
+    ref = 0.4 * (b[0] - hr).abs().mean((1, 2, 3)) + 0.4 * (b[1] - lr).abs().mean((1, 2, 3)) + w_k * ((b[2] - kg) ** 2).mean((1, 2, 3))
+    (loss * up).sum().backward()
+    (ref * up).sum().backward()
+    assert torch.allclose(loss, ref, rtol=2e-6, atol=1e-7)
+    assert torch.allclose(a[0].grad, b[0].grad, rtol=1e-6, atol=1e-10) and torch.allclose(a[1].grad, b[1].grad, rtol=1e-6, atol=1e-10)
+    if w_k != 0:
+        assert torch.allclose(a[2].grad, b[2].grad, rtol=1e-5, atol=1e-10)
+    else:
+        assert a[2].grad is None
