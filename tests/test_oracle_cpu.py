@@ -426,3 +426,36 @@ def test_patch_oracle_matches_reference():
     img = (torch.rand(30, 36, 3, generator=g) * 255).to(torch.uint8).numpy()
     out = PR.crop_flip(img, 4, 6, True, False, 16, 20)
     assert out.shape == (3, 16, 20) and abs(float(out[1, 0, 0]) - img[4, 36 - 1 - 6, 1] / 255) < 1e-7
+
+
+def test_wgrad_split_plan_fills_whole_rounds():
+    """Host logic of csbsr_conv_wgrad's work decomposition (csrc/conv_wgrad.cu::wg_plan), through the workspace query (no device
+    needed: 148 SMs assumed): the pixel range is split so that (passes x splits) work items fill whole rounds of one CTA per SM.
+    The 8x8/s4 layers have 16 passes: 9 splits = 144 items in one round (the round-1 rule rounded up to 10 = 160 items, two
+    rounds with 12 busy SMs in the second)."""
+    import ctypes as C
+    from csbsr_b200 import _lib
+    L = _lib.lib()
+    L.csbsr_conv_wgrad_workspace_bytes.restype = C.c_size_t
+
+    def nsplit(n, gh, gw, cg, cs, k, stride, pad):
+        d = _lib.WgradDesc()
+        d.g, d.s = 1, 1                                  # non-null placeholders: the query never dereferences them
+        d.n, d.gh, d.gw, d.g_pitch, d.g_coff, d.cg = n, gh, gw, cg, 0, cg
+        d.sh, d.sw, d.s_pitch, d.s_coff, d.cs = gh * stride, gw * stride, cs, 0, cs
+        d.ntaps, d.stride = k * k, stride
+        for r in range(k):
+            for s in range(k):
+                d.dh[r * k + s], d.dw[r * k + s] = r - pad, s - pad
+        nbytes = L.csbsr_conv_wgrad_workspace_bytes(C.byref(d))
+        rows_pad = (cg + 127) // 128 * 128
+        per_split = 4 * k * k * cs * rows_pad
+        assert nbytes % per_split == 0
+        return nbytes // per_split
+
+    assert nsplit(8, 56, 56, 128, 128, 8, 4, 2) == 9          # 16 passes x 9 = 144 items <= 148
+    for shape, npass in (((8, 28, 28, 256, 256, 3, 1, 1), 12), ((8, 28, 28, 512, 512, 3, 1, 1), 48), ((8, 56, 56, 704, 256, 3, 1, 1), 36)):
+        ns = nsplit(*shape)
+        items = ns * npass
+        rounds = -(-items // 148)
+        assert items / (rounds * 148) >= 0.9, (shape, ns, items)      # at most 10 % of the SM-rounds idle
