@@ -459,3 +459,16 @@ def test_wgrad_split_plan_fills_whole_rounds():
         items = ns * npass
         rounds = -(-items // 148)
         assert items / (rounds * 148) >= 0.9, (shape, ns, items)      # at most 10 % of the SM-rounds idle
+
+
+def test_metrics_workspace_is_per_image_small():
+    """csbsr_metrics_workspace_bytes at 448^2 with the HD sweep: ~3 MB per image (quantised map, corner codes, gt list / EDT,
+    transposed threshold ranges) plus a fixed per-device part (one spill region + sort target per resident CTA) -- the round-1
+    layout needed 260 MB per image."""
+    import ctypes as C
+    from csbsr_b200 import _lib
+    L = _lib.lib()
+    L.csbsr_metrics_workspace_bytes.restype = C.c_size_t
+    one, many = L.csbsr_metrics_workspace_bytes(1, 448, 448, 1), L.csbsr_metrics_workspace_bytes(17, 448, 448, 1)
+    assert (many - one) / 16 <= 3.2e6
+    assert one <= 320e6
